@@ -1,0 +1,206 @@
+/*
+ * sg2im_b200 — C-ABI of libsg2im_b200.so (CUDA, sm_100a only).
+ *
+ * The reference (google/sg2im) has no FFI layer: its hot path is Python over
+ * torch ops.  Each entry point below replaces the torch op sequence at the
+ * cited reference location (paths relative to the reference tree).  The host
+ * mirror in sg2im_b200/*.py binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated; fp32 values, int64 indices
+ *    (the reference's LongTensors), int32 for library-built CSR tables;
+ *  - activations are NHWC ("pixels x channels" row-major); a tensor argument
+ *    followed by (cstride, coff) is a channel slice [coff, coff+C) of a wider
+ *    NHWC buffer whose pixel stride is cstride floats (virtual concat);
+ *  - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises,
+ *    nothing allocates; buffers (incl. zero-initialised accumulators where
+ *    stated) are owned by the caller;
+ *  - return 0 on success, <0 invalid argument / unsupported shape, >0 a
+ *    cudaError_t from the launch; sg2im_last_error_string() describes the last
+ *    failure on the calling thread.  There is no CPU fallback.
+ */
+#ifndef SG2IM_B200_H_
+#define SG2IM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sg2im_stream_t;           /* cudaStream_t */
+
+int sg2im_abi_version(void);
+const char* sg2im_last_error_string(void);
+/* 1 if the running device is compute capability 10.x, else 0 (no dispatch: the
+ * library refuses to run elsewhere). */
+int sg2im_device_ok(void);
+
+/* ---------------------------------------------------------------- graph --
+ * CSR of "which (triple, role) entries touch row r", entries ordered
+ * role 0 ascending t, then role 1 ascending t — the order the reference's two
+ * scatter_add calls impose (sg2im/graph.py:98-99).  idx[t*idx_stride + role]
+ * is the destination row.  nroles in {1,2}.  Also used with nroles=1 for
+ * obj_to_img (sg2im/layout.py:146-148).  row_ptr: int32[R+1]; entries:
+ * int32[nroles*T], entry = t*2 + role.  Out-of-range indices are dropped. */
+int sg2im_csr_build(const int64_t* idx, int64_t T, int64_t idx_stride, int nroles,
+                    int64_t R, int32_t* row_ptr, int32_t* entries,
+                    sg2im_stream_t stream);
+
+/* out[t] = [ rows[idx[t,0]] * f0 | mid[t] | rows[idx[t,1]] * f1 ], widths
+ * (Wr, Wm, Wr); f = 1/max(count,1) per row when row_ptr != NULL else 1.
+ * Forward use: cur_t_vecs = cat(obj[s], pred, obj[o]) (sg2im/graph.py:77-82).
+ * Backward use: gradient of the avg-pool scatter (graph.py:98-114), mid = grad
+ * of the predicate slice (NULL => zeros). */
+int sg2im_triple_gather(const float* rows, const float* mid, const int64_t* edges,
+                        int64_t T, int64_t Wr, int64_t Wm, const int32_t* row_ptr,
+                        float* out, sg2im_stream_t stream);
+
+/* out[r, 0:W] = sum over CSR entries (t, role) of row r, in CSR order, of
+ * src[t, off_role : off_role+W]   (/ max(count,1) if avg).  Sequential fp32
+ * adds in CSR order => bit-exact vs the CPU scatter_add (graph.py:92-114).
+ * Backward use: gradient of the gather (graph.py:77-78). */
+int sg2im_segment_sum(const float* src, int64_t src_stride, int64_t off0, int64_t off1,
+                      int64_t W, const int32_t* row_ptr, const int32_t* entries,
+                      int64_t R, int avg, float* out, sg2im_stream_t stream);
+
+/* ----------------------------------------------------------------- conv --
+ * Implicit-GEMM convolution, NHWC, fp32 FFMA (exact fp32) — replaces
+ * nn.Conv2d / nn.Linear (sg2im/crn.py:41-45,80-82, model.py:100,105,
+ * layers.py:178,221, discriminators.py:62-66).
+ *
+ * mode 0 (forward):  y[n,oy,ox,co] = b[co] + sum_{ky,kx,ci}
+ *      x[n, oy*S-P+ky, ox*S-P+kx, ci] * w[(ky*KW+kx)*Cin + ci][co]
+ * mode 1 (data gradient): x plays dY (N,Hin,Win,Cin=Cout_fwd), y plays dX
+ *      (N,Hout,Wout,Cout=Cin_fwd): y[n,iy,ix,c] = sum_{ky,kx,co: (iy+P-ky)%S==0..}
+ *      x[n,(iy+P-ky)/S,(ix+P-kx)/S,co] * w[(ky*KW+kx)*Cin + co][c]
+ * w is the packed (KH*KW*Cin) x Cout row-major matrix for the given mode.
+ * x is addressed with element strides (sxn,sxh,sxw,sxc) so NCHW callers need
+ * no copy.  Epilogue: + bias (may be NULL), act: 0 none, 1 leaky(slope)
+ * (slope 0 = ReLU).  Output written to the slice (y, y_cstride, y_coff).
+ * A Linear is KH=KW=1, Hin=Win=1, N=rows. */
+int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t sxw,
+                     int64_t sxc, int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                     const float* w, const float* bias, int KH, int KW, int S, int P,
+                     int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope,
+                     float* y, int64_t y_cstride, int64_t y_coff,
+                     sg2im_stream_t stream);
+
+/* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
+ *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
+ * reduction over pixels is split across CTAs and combined with fp32 atomics). */
+int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int64_t sxc,
+                     int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                     const float* dy, int KH, int KW, int S, int P,
+                     int64_t Hout, int64_t Wout, int64_t Cout,
+                     float* dw, sg2im_stream_t stream);
+
+/* out[c] = sum_m x[m, c]  (bias gradient), fp64 accumulation; out zeroed by
+ * the call. */
+int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out,
+                 double* scratch /* C doubles */, sg2im_stream_t stream);
+
+/* dx = dy * (y > 0 ? 1 : slope)   (in place allowed) — backward of a fused
+ * epilogue activation, keyed on the activation OUTPUT. */
+int sg2im_act_bwd(const float* dy, const float* y, float slope, int64_t n,
+                  float* dx, sg2im_stream_t stream);
+
+/* -------------------------------------------------------- batch norm etc --
+ * Train-mode nn.BatchNorm2d (+ LeakyReLU, + nearest x2 upsample, + channel
+ * concat) — sg2im/crn.py:43-47,63,107; layers.py:22-46; model.py:98-99.
+ *
+ * bn_stats:    sums[c] += sum_m x[m,c], sums[C+c] += sum_m x[m,c]^2 (fp64,
+ *              caller zeroes `sums`, 2C doubles).
+ * bn_finalize: mean/var from sums over `count` rows; scale = gamma*invstd,
+ *              shift = beta - mean*scale; running stats updated with momentum
+ *              and the unbiased factor n/(n-1), n = count*unbias_mult
+ *              (unbias_mult = 4 when BN follows a x2 upsample: same mean/var,
+ *              4x the elements).  training=0: scale/shift from running stats.
+ *              save[0:C]=mean, save[C:2C]=invstd.  gamma/beta NULL => 1/0.
+ * scale_act_fwd: y[n,Y,X,coff+c] = leaky(x[n,Y/up,X/up,c]*scale[c]+shift[c]);
+ *              scale NULL => identity affine; slope 1 => no activation.
+ */
+int sg2im_bn_stats(const float* x, int64_t M, int64_t C, double* sums,
+                   sg2im_stream_t stream);
+int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbias_mult, int64_t C,
+                      const float* gamma, const float* beta, float eps, float momentum,
+                      int training, float* running_mean, float* running_var,
+                      float* scale, float* shift, float* save, sg2im_stream_t stream);
+int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                        const float* scale, const float* shift, float slope, int up,
+                        float* y, int64_t y_cstride, int64_t y_coff,
+                        sg2im_stream_t stream);
+/* Backward of scale_act_fwd given dy on the (upsampled, sliced) output.
+ * reduce: with g = leaky'(x*scale+shift) * sum_{up x up} dy,
+ *         sums[c] += sum g, sums[C+c] += sum g*xhat, xhat = (x-mean)*invstd
+ *         (fp64; caller zeroes).
+ * apply:  training: dx = scale*(g - sums[c]/M - xhat*sums[C+c]/M)
+ *         else:     dx = scale*g ;   dgamma = sums[C+c], dbeta = sums[c]
+ *         (dgamma/dbeta NULL allowed; written, not accumulated). */
+int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, int64_t dy_coff,
+                               const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                               const float* scale, const float* shift, const float* save,
+                               float slope, int up, double* sums, sg2im_stream_t stream);
+int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, int64_t dy_coff,
+                              const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                              const float* scale, const float* shift, const float* save,
+                              float slope, int up, int training, const double* sums,
+                              float* dx, float* dgamma, float* dbeta,
+                              sg2im_stream_t stream);
+
+/* 2x2 average pool between channel slices (F.avg_pool2d, sg2im/crn.py:58-62,
+ * applied as a factor-2 cascade) and its backward:
+ * dfine[n,Y,X,c] (+)= dcoarse[n,Y/2,X/2,c] / 4  (accumulate=1 adds). */
+int sg2im_avgpool2_fwd(const float* x, int64_t x_cstride, int64_t x_coff,
+                       int64_t N, int64_t H, int64_t W, int64_t C,
+                       float* y, int64_t y_cstride, int64_t y_coff, sg2im_stream_t stream);
+int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int64_t dc_coff,
+                       int64_t N, int64_t H, int64_t W, int64_t C,
+                       float* dfine, int64_t df_cstride, int64_t df_coff, int accumulate,
+                       sg2im_stream_t stream);
+
+/* --------------------------------------------------------------- layout --
+ * Fused masks_to_layout / boxes_to_layout (sg2im/layout.py:30-162):
+ *   out[n,h,w,d] = sum_{o in image n, ascending o} vecs[o,d] * S_o(h,w),
+ *   S_o = bilinear sample (zeros padding, align_corners flag) of masks[o]
+ *   (MxM) at the box-local coordinate of pixel (h,w).  masks NULL => the
+ *   constant 8x8 ones "mask" of boxes_to_layout.  img_row_ptr/img_entries:
+ *   CSR image -> objects from sg2im_csr_build(obj_to_img, nroles=1).
+ * The (O,D,H,W) temporary of the reference never exists.  Channels
+ * [D, D+noise_c) of the output slice are filled from `noise` addressed with
+ * element strides (n,c,h,w) (model.py:164-169); noise NULL => untouched. */
+int sg2im_layout_fwd(const float* vecs, const float* boxes, const float* masks, int64_t M,
+                     const int32_t* img_row_ptr, const int32_t* img_entries,
+                     int64_t N, int64_t O, int64_t D, int64_t H, int64_t W,
+                     int align_corners,
+                     const float* noise, int64_t noise_c, int64_t nsn, int64_t nsc,
+                     int64_t nsh, int64_t nsw,
+                     float* out, int64_t out_cstride, sg2im_stream_t stream);
+/* dvecs[o,d] += sum_hw dout[n,h,w,d]*S_o(h,w);  dmasks[o,my,mx] += bilinear
+ * scatter of dS_o(h,w) = sum_d dout[n,h,w,d]*vecs[o,d].  Both zero-initialised
+ * by the caller; dmasks may be NULL. */
+int sg2im_layout_bwd(const float* dout, int64_t dout_cstride,
+                     const float* vecs, const float* boxes, const float* masks, int64_t M,
+                     const int64_t* obj_to_img, int64_t N, int64_t O, int64_t D,
+                     int64_t H, int64_t W, int align_corners,
+                     float* dvecs, float* dmasks, sg2im_stream_t stream);
+
+/* ----------------------------------------------------------------- crop --
+ * crop_bbox_batch (sg2im/bilinear.py:28-132,249-278): out[b,i,j,c] = bilinear
+ * sample (zeros padding) of feats[idx[b]] at X_j = (1-a_j)(2x0-1)+a_j(2x1-1),
+ * a = linspace(0,1,WW), Y_i likewise.  feats addressed with element strides;
+ * out NHWC (B,HH,WW,C).  No host sync, any object order. */
+int sg2im_crop_fwd(const float* feats, int64_t sfn, int64_t sfh, int64_t sfw, int64_t sfc,
+                   int64_t N, int64_t H, int64_t W, int64_t C,
+                   const float* boxes, const int64_t* idx, int64_t B, int64_t HH, int64_t WW,
+                   int align_corners, float* out, sg2im_stream_t stream);
+/* dfeats (N,H,W,C NHWC contiguous, zero-initialised) += scatter of dout. */
+int sg2im_crop_bwd(const float* dout, const float* boxes, const int64_t* idx,
+                   int64_t N, int64_t H, int64_t W, int64_t C, int64_t B, int64_t HH,
+                   int64_t WW, int align_corners, float* dfeats, sg2im_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SG2IM_B200_H_ */

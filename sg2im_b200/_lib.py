@@ -1,0 +1,86 @@
+"""ctypes binding of libsg2im_b200.so (the C-ABI in include/sg2im_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or
+``make -C sg2im_b200/csrc``).  There is no fallback: if the shared object is
+missing, or the device is not compute capability 10.x, every op raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsg2im_b200.so')
+
+_i64, _i32, _f32, _ptr, _int = (ctypes.c_int64, ctypes.c_int32, ctypes.c_float,
+                                ctypes.c_void_p, ctypes.c_int)
+
+# name -> argument ctypes, in the order of include/sg2im_b200.h
+SIGNATURES = {
+  'sg2im_abi_version': [],
+  'sg2im_device_ok': [],
+  'sg2im_csr_build': [_ptr, _i64, _i64, _int, _i64, _ptr, _ptr, _ptr],
+  'sg2im_triple_gather': [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr],
+  'sg2im_segment_sum': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64, _int, _ptr, _ptr],
+  'sg2im_conv_igemm': [_int, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                       _ptr, _ptr, _int, _int, _int, _int, _i64, _i64, _i64, _int, _f32,
+                       _ptr, _i64, _i64, _ptr],
+  'sg2im_conv_wgrad': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr,
+                       _int, _int, _int, _int, _i64, _i64, _i64, _ptr, _ptr],
+  'sg2im_colsum': [_ptr, _i64, _i64, _ptr, _ptr, _ptr],
+  'sg2im_act_bwd': [_ptr, _ptr, _f32, _i64, _ptr, _ptr],
+  'sg2im_bn_stats': [_ptr, _i64, _i64, _ptr, _ptr],
+  'sg2im_bn_finalize': [_ptr, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr,
+                        _ptr, _ptr, _ptr, _ptr],
+  'sg2im_scale_act_fwd': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _int, _ptr, _i64,
+                          _i64, _ptr],
+  'sg2im_scale_act_bwd_reduce': [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr,
+                                 _ptr, _f32, _int, _ptr, _ptr],
+  'sg2im_scale_act_bwd_apply': [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr,
+                                _ptr, _f32, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
+  'sg2im_avgpool2_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr],
+  'sg2im_avgpool2_bwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _ptr],
+  'sg2im_layout_fwd': [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
+                       _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
+  'sg2im_layout_bwd': [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64,
+                       _int, _ptr, _ptr, _ptr],
+  'sg2im_crop_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64,
+                     _i64, _i64, _int, _ptr, _ptr],
+  'sg2im_crop_bwd': [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _ptr,
+                     _ptr],
+}
+
+_lib = None
+
+
+def load():
+  """Load (once) and return the ctypes handle with prototypes set."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        'sg2im_b200: %s not found — build it with `python -c "import __graft_entry__ as g; '
+        'g.build()"` (there is no CPU or PyTorch fallback for the hot path)' % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, argtypes in SIGNATURES.items():
+    fn = getattr(lib, name)           # AttributeError if the symbol is missing
+    fn.argtypes = argtypes
+    fn.restype = _int
+  lib.sg2im_last_error_string.argtypes = []
+  lib.sg2im_last_error_string.restype = ctypes.c_char_p
+  _lib = lib
+  return lib
+
+
+def call(name, *args):
+  """Invoke an entry point; non-zero status -> RuntimeError with the library's
+  message (no silent fallback)."""
+  lib = load()
+  rc = getattr(lib, name)(*args)
+  if rc != 0:
+    msg = lib.sg2im_last_error_string().decode('utf-8', 'replace')
+    raise RuntimeError('%s failed (status %d): %s' % (name, rc, msg))
+
+
+# launch counter: bench.py reports how many of OUR kernels-launching entry
+# points ran inside the timed region
+launches = 0

@@ -1,0 +1,47 @@
+// Shared helpers for libsg2im_b200 (sm_100a).  Internal — the public surface is
+// include/sg2im_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "sg2im_b200.h"
+
+void sg2im_set_error(const char* fmt, ...);
+
+#define SG_ARG(cond)                                                          \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      sg2im_set_error("%s: invalid argument: %s", __func__, #cond);           \
+      return -1;                                                              \
+    }                                                                         \
+  } while (0)
+
+#define SG_LAUNCH_OK()                                                        \
+  do {                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                      \
+    if (e_ != cudaSuccess) {                                                  \
+      sg2im_set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e_)); \
+      return (int)e_;                                                         \
+    }                                                                         \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+static inline cudaStream_t as_stream(sg2im_stream_t s) { return (cudaStream_t)s; }
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// Bilinear sampling footprint of one normalised coordinate g in [-1,1] on an
+// axis of `size` texels (torch grid_sample, zeros padding): lower texel index
+// and the weight of the upper texel.
+__device__ __forceinline__ void bilinear_axis(float g, int size, int align_corners,
+                                              int& lo, float& w_hi) {
+  float pix = align_corners ? (g + 1.f) * 0.5f * (float)(size - 1)
+                            : ((g + 1.f) * (float)size - 1.f) * 0.5f;
+  float fl = floorf(pix);
+  // clamp far-out coordinates so the int conversion is defined; anything
+  // beyond [-2, size+1] samples only padding anyway
+  fl = fminf(fmaxf(fl, -2.f), (float)size + 1.f);
+  lo = (int)fl;
+  w_hi = pix - fl;
+  if (!(pix >= -2.f && pix <= (float)size + 1.f)) { lo = -2; w_hi = 0.f; }   // also NaN
+}

@@ -1,0 +1,393 @@
+// Train-mode BatchNorm statistics, the fused affine + LeakyReLU + nearest-x2
+// upsample + channel-slice write ("virtual concat"), their backward, the 2x2
+// average-pool cascade, bias-gradient column sums and the epilogue-activation
+// backward.  HBM-bound elementwise / reduction kernels (float4, coalesced on
+// the NHWC channel axis, fp64 cross-CTA accumulation).
+// Replaces nn.BatchNorm2d + nn.LeakyReLU + F.upsample + torch.cat +
+// F.avg_pool2d of sg2im/crn.py:41-47,58-63,107 and model.py:98-99.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RED_TX = 32, RED_TY = 8;
+
+// ---- per-channel sums over rows: out[c] += sum f(x), out[C+c] += sum g(x) ----
+// Functor F: (row m, channel c) -> (v0, v1).  Block = 32 channels x 8 row lanes.
+template <class F>
+__global__ void __launch_bounds__(RED_TX * RED_TY)
+colreduce_kernel(F f, int64_t M, int64_t C, int64_t rows_per_block, double* __restrict__ sums,
+                 int nout) {
+  __shared__ double sh[2][RED_TY][RED_TX];
+  int64_t c = (int64_t)blockIdx.x * RED_TX + threadIdx.x;
+  int64_t mb = (int64_t)blockIdx.y * rows_per_block;
+  int64_t me = mb + rows_per_block < M ? mb + rows_per_block : M;
+  double d0 = 0.0, d1 = 0.0;
+  if (c < C) {
+    float s0 = 0.f, s1 = 0.f;
+    int cnt = 0;
+    for (int64_t m = mb + threadIdx.y; m < me; m += RED_TY) {
+      float v0, v1;
+      f(m, c, v0, v1);
+      s0 += v0; s1 += v1;
+      if (++cnt == 32) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }
+    }
+    d0 += s0; d1 += s1;
+  }
+  sh[0][threadIdx.y][threadIdx.x] = d0;
+  sh[1][threadIdx.y][threadIdx.x] = d1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int y = 1; y < RED_TY; ++y) { d0 += sh[0][y][threadIdx.x]; d1 += sh[1][y][threadIdx.x]; }
+    atomicAdd(sums + c, d0);
+    if (nout > 1) atomicAdd(sums + C + c, d1);
+  }
+}
+
+struct StatsF {
+  const float* x; int64_t C;
+  __device__ void operator()(int64_t m, int64_t c, float& v0, float& v1) const {
+    float v = x[m * C + c];
+    v0 = v; v1 = v * v;
+  }
+};
+
+template <class F>
+int launch_colreduce(F f, int64_t M, int64_t C, double* sums, int nout, cudaStream_t st) {
+  int64_t cblocks = ceil_div64(C, RED_TX);
+  // ~8 waves of CTAs, at least 64 rows each
+  int64_t want = ceil_div64(148 * 8, cblocks);
+  int64_t rpb = ceil_div64(M, want);
+  if (rpb < 64) rpb = 64;
+  int64_t rblocks = ceil_div64(M, rpb);
+  if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
+  dim3 grid((unsigned)cblocks, (unsigned)rblocks);
+  colreduce_kernel<F><<<grid, dim3(RED_TX, RED_TY), 0, st>>>(f, M, C, rpb, sums, nout);
+  return 0;
+}
+
+__global__ void zero_doubles(double* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+__global__ void doubles_to_float(const double* p, float* o, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = (float)p[i];
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t count,
+                                   int64_t unbias_mult, int64_t C, const float* gamma,
+                                   const float* beta, float eps, float momentum, int training,
+                                   float* running_mean, float* running_var, float* scale,
+                                   float* shift, float* save) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double m = sums[c] / (double)count;
+    double var = sums[C + c] / (double)count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      double n = (double)count * (double)unbias_mult;
+      double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = 1.f / sqrtf(running_var[c] + eps);
+  }
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - mean * g * invstd;
+  save[c] = mean;
+  save[C + c] = invstd;
+}
+
+// ---- y[n,Y,X,coff+c] = leaky(x[n,Y/up,X/up,c]*scale+shift) -------------------
+template <int VEC>
+__global__ void scale_act_fwd_kernel(const float* __restrict__ x, int64_t N, int64_t H, int64_t W,
+                                     int64_t C, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, float slope, int up,
+                                     float* __restrict__ y, int64_t ycs, int64_t yco) {
+  int64_t cg = C / VEC;
+  int64_t Ho = H * up, Wo = W * up;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Ho * Wo * cg) return;
+  int64_t c = (i % cg) * VEC;
+  int64_t pix = i / cg;
+  int64_t X = pix % Wo;
+  int64_t t = pix / Wo;
+  int64_t Y = t % Ho;
+  int64_t n = t / Ho;
+  const float* xp = x + ((n * H + Y / up) * W + X / up) * C + c;
+  float* yp = y + pix * ycs + yco + c;
+  if (VEC == 4) {
+    float4 v = *reinterpret_cast<const float4*>(xp);
+    if (scale) {
+      float4 s = *reinterpret_cast<const float4*>(scale + c);
+      float4 b = *reinterpret_cast<const float4*>(shift + c);
+      v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y);
+      v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+    }
+    v.x = leaky(v.x, slope); v.y = leaky(v.y, slope);
+    v.z = leaky(v.z, slope); v.w = leaky(v.w, slope);
+    *reinterpret_cast<float4*>(yp) = v;
+  } else {
+    float v = xp[0];
+    if (scale) v = fmaf(v, scale[c], shift[c]);
+    yp[0] = leaky(v, slope);
+  }
+}
+
+// g = leaky'(pre) * sum_{up x up} dy   for input element (n,y,x,c)
+struct ActGrad {
+  const float* dy; int64_t dcs, dco;
+  const float* x; int64_t H, W, C;
+  const float* scale; const float* shift;
+  float slope; int up;
+  __device__ __forceinline__ float at(int64_t m, int64_t c, float& xv) const {
+    xv = x[m * C + c];
+    float pre = scale ? fmaf(xv, scale[c], shift[c]) : xv;
+    float d = pre > 0.f ? 1.f : slope;
+    float g;
+    if (up == 1) {
+      g = dy[m * dcs + dco + c];
+    } else {
+      int64_t xx = m % W; int64_t t = m / W; int64_t yy = t % H; int64_t n = t / H;
+      int64_t Wo = W * up;
+      g = 0.f;
+      for (int a = 0; a < up; ++a)
+        for (int b = 0; b < up; ++b)
+          g += dy[((n * H * up + yy * up + a) * Wo + xx * up + b) * dcs + dco + c];
+    }
+    return g * d;
+  }
+};
+
+struct BwdReduceF {
+  ActGrad ag; const float* save; int64_t C;
+  __device__ void operator()(int64_t m, int64_t c, float& v0, float& v1) const {
+    float xv;
+    float g = ag.at(m, c, xv);
+    float xhat = save ? (xv - save[c]) * save[C + c] : xv;
+    v0 = g; v1 = g * xhat;
+  }
+};
+
+__global__ void scale_act_bwd_apply_kernel(ActGrad ag, const float* __restrict__ save,
+                                           int64_t M, int64_t C, int training,
+                                           const double* __restrict__ sums,
+                                           float* __restrict__ dx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  int64_t m = i / C, c = i - m * C;
+  float xv;
+  float g = ag.at(m, c, xv);
+  float sc = ag.scale ? ag.scale[c] : 1.f;
+  float r;
+  if (training && save) {
+    float xhat = (xv - save[c]) * save[C + c];
+    float mg = (float)(sums[c] / (double)M);
+    float mgx = (float)(sums[C + c] / (double)M);
+    r = sc * (g - mg - xhat * mgx);
+  } else {
+    r = sc * g;
+  }
+  dx[i] = r;
+}
+
+__global__ void bn_param_grads(const double* __restrict__ sums, int64_t C, float* dgamma,
+                               float* dbeta) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+template <int VEC>
+__global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int64_t xcs, int64_t xco,
+                                    int64_t N, int64_t H, int64_t W, int64_t C,
+                                    float* __restrict__ y, int64_t ycs, int64_t yco) {
+  int64_t cg = C / VEC, Ho = H / 2, Wo = W / 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Ho * Wo * cg) return;
+  int64_t c = (i % cg) * VEC;
+  int64_t pix = i / cg;
+  int64_t X = pix % Wo; int64_t t = pix / Wo; int64_t Y = t % Ho; int64_t n = t / Ho;
+  const float* p00 = x + ((n * H + 2 * Y) * W + 2 * X) * xcs + xco + c;
+  const float* p10 = p00 + W * xcs;
+  float* yp = y + pix * ycs + yco + c;
+  if (VEC == 4) {
+    float4 a = *reinterpret_cast<const float4*>(p00);
+    float4 b = *reinterpret_cast<const float4*>(p00 + xcs);
+    float4 d = *reinterpret_cast<const float4*>(p10);
+    float4 e = *reinterpret_cast<const float4*>(p10 + xcs);
+    float4 r;
+    r.x = (a.x + b.x + d.x + e.x) * 0.25f; r.y = (a.y + b.y + d.y + e.y) * 0.25f;
+    r.z = (a.z + b.z + d.z + e.z) * 0.25f; r.w = (a.w + b.w + d.w + e.w) * 0.25f;
+    *reinterpret_cast<float4*>(yp) = r;
+  } else {
+    yp[0] = (p00[0] + p00[xcs] + p10[0] + p10[xcs]) * 0.25f;
+  }
+}
+
+template <int VEC>
+__global__ void avgpool2_bwd_kernel(const float* __restrict__ dc, int64_t dcs, int64_t dco,
+                                    int64_t N, int64_t H, int64_t W, int64_t C,
+                                    float* __restrict__ df, int64_t dfs, int64_t dfo, int acc) {
+  // (H, W) are the FINE dims
+  int64_t cg = C / VEC;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H * W * cg) return;
+  int64_t c = (i % cg) * VEC;
+  int64_t pix = i / cg;
+  int64_t X = pix % W; int64_t t = pix / W; int64_t Y = t % H; int64_t n = t / H;
+  const float* cp = dc + ((n * (H / 2) + Y / 2) * (W / 2) + X / 2) * dcs + dco + c;
+  float* fp = df + pix * dfs + dfo + c;
+  if (VEC == 4) {
+    float4 g = *reinterpret_cast<const float4*>(cp);
+    float4 r = make_float4(g.x * 0.25f, g.y * 0.25f, g.z * 0.25f, g.w * 0.25f);
+    if (acc) {
+      float4 o = *reinterpret_cast<const float4*>(fp);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    *reinterpret_cast<float4*>(fp) = r;
+  } else {
+    float r = cp[0] * 0.25f;
+    fp[0] = acc ? fp[0] + r : r;
+  }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                               float slope, int64_t n, float* __restrict__ dx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = y[i] > 0.f ? dy[i] : dy[i] * slope;
+}
+
+}  // namespace
+
+extern "C" int sg2im_bn_stats(const float* x, int64_t M, int64_t C, double* sums,
+                              sg2im_stream_t stream) {
+  SG_ARG(x && sums && M >= 1 && C >= 1);
+  StatsF f{x, C};
+  launch_colreduce(f, M, C, sums, 2, as_stream(stream));
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, double* scratch,
+                            sg2im_stream_t stream) {
+  SG_ARG(x && out && scratch && M >= 1 && C >= 1);
+  cudaStream_t st = as_stream(stream);
+  zero_doubles<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, C);
+  StatsF f{x, C};
+  launch_colreduce(f, M, C, scratch, 1, st);
+  doubles_to_float<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, out, C);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbias_mult, int64_t C,
+                                 const float* gamma, const float* beta, float eps, float momentum,
+                                 int training, float* running_mean, float* running_var,
+                                 float* scale, float* shift, float* save, sg2im_stream_t stream) {
+  SG_ARG(scale && shift && save && C >= 1 && count >= 1 && unbias_mult >= 1);
+  SG_ARG(training ? sums != nullptr : (running_mean && running_var));
+  bn_finalize_kernel<<<(unsigned)ceil_div64(C, 128), 128, 0, as_stream(stream)>>>(
+      sums, count, unbias_mult, C, gamma, beta, eps, momentum, training, running_mean,
+      running_var, scale, shift, save);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                                   const float* scale, const float* shift, float slope, int up,
+                                   float* y, int64_t y_cstride, int64_t y_coff,
+                                   sg2im_stream_t stream) {
+  SG_ARG(x && y && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
+  SG_ARG((scale == nullptr) == (shift == nullptr));
+  SG_ARG(y_coff >= 0 && y_cstride >= y_coff + C);
+  bool vec = (C % 4 == 0) && (y_cstride % 4 == 0) && (y_coff % 4 == 0) && aligned16(x) &&
+             aligned16(y) && (!scale || (aligned16(scale) && aligned16(shift)));
+  int64_t total = N * H * up * W * up * (C / (vec ? 4 : 1));
+  unsigned grid = (unsigned)ceil_div64(total, 256);
+  cudaStream_t st = as_stream(stream);
+  if (vec) scale_act_fwd_kernel<4><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+  else     scale_act_fwd_kernel<1><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, int64_t dy_coff,
+                                          const float* x, int64_t N, int64_t H, int64_t W,
+                                          int64_t C, const float* scale, const float* shift,
+                                          const float* save, float slope, int up, double* sums,
+                                          sg2im_stream_t stream) {
+  SG_ARG(dy && x && sums && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
+  BwdReduceF f{{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up}, save, C};
+  launch_colreduce(f, N * H * W, C, sums, 2, as_stream(stream));
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, int64_t dy_coff,
+                                         const float* x, int64_t N, int64_t H, int64_t W,
+                                         int64_t C, const float* scale, const float* shift,
+                                         const float* save, float slope, int up, int training,
+                                         const double* sums, float* dx, float* dgamma,
+                                         float* dbeta, sg2im_stream_t stream) {
+  SG_ARG(dy && x && dx && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
+  SG_ARG(!training || !save || sums);
+  cudaStream_t st = as_stream(stream);
+  ActGrad ag{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up};
+  int64_t M = N * H * W;
+  scale_act_bwd_apply_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(
+      ag, save, M, C, training, sums, dx);
+  if ((dgamma || dbeta) && sums)
+    bn_param_grads<<<(unsigned)ceil_div64(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_avgpool2_fwd(const float* x, int64_t x_cstride, int64_t x_coff,
+                                  int64_t N, int64_t H, int64_t W, int64_t C,
+                                  float* y, int64_t y_cstride, int64_t y_coff,
+                                  sg2im_stream_t stream) {
+  SG_ARG(x && y && N >= 1 && C >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0);
+  bool vec = (C % 4 == 0) && (x_cstride % 4 == 0) && (x_coff % 4 == 0) && (y_cstride % 4 == 0) &&
+             (y_coff % 4 == 0) && aligned16(x) && aligned16(y);
+  int64_t total = N * (H / 2) * (W / 2) * (C / (vec ? 4 : 1));
+  unsigned grid = (unsigned)ceil_div64(total, 256);
+  cudaStream_t st = as_stream(stream);
+  if (vec) avgpool2_fwd_kernel<4><<<grid, 256, 0, st>>>(x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
+  else     avgpool2_fwd_kernel<1><<<grid, 256, 0, st>>>(x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int64_t dc_coff,
+                                  int64_t N, int64_t H, int64_t W, int64_t C,
+                                  float* dfine, int64_t df_cstride, int64_t df_coff,
+                                  int accumulate, sg2im_stream_t stream) {
+  SG_ARG(dcoarse && dfine && N >= 1 && C >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0);
+  bool vec = (C % 4 == 0) && (dc_cstride % 4 == 0) && (dc_coff % 4 == 0) &&
+             (df_cstride % 4 == 0) && (df_coff % 4 == 0) && aligned16(dcoarse) && aligned16(dfine);
+  int64_t total = N * H * W * (C / (vec ? 4 : 1));
+  unsigned grid = (unsigned)ceil_div64(total, 256);
+  cudaStream_t st = as_stream(stream);
+  if (vec) avgpool2_bwd_kernel<4><<<grid, 256, 0, st>>>(dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
+  else     avgpool2_bwd_kernel<1><<<grid, 256, 0, st>>>(dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_act_bwd(const float* dy, const float* y, float slope, int64_t n, float* dx,
+                             sg2im_stream_t stream) {
+  SG_ARG(dy && y && dx && n >= 0);
+  if (n == 0) return 0;
+  act_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dy, y, slope, n, dx);
+  SG_LAUNCH_OK();
+  return 0;
+}

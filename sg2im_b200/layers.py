@@ -1,0 +1,353 @@
+"""Layer factories with the reference's surface (sg2im/layers.py): ``build_mlp``,
+``build_cnn``, ``get_normalization_2d``, ``get_activation`` and the small
+modules they return — same constructor arguments, same ``nn.Sequential``
+structure and therefore the same ``state_dict`` keys — whose forward passes run
+on the sm_100a kernels of libsg2im_b200.so.
+
+Callers see the reference's NCHW shapes; internally every 4-D activation is an
+NHWC tensor (a permuted view, i.e. torch ``channels_last`` memory), so no
+layout conversion kernels run between layers.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _to_nhwc(x):
+  """NCHW-shaped tensor (any strides) -> (N,H,W,C)-shaped view."""
+  return x.permute(0, 2, 3, 1)
+
+
+def _to_nchw(h):
+  return h.permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------
+# leaf modules: parameter containers identical to torch's, forward on our kernels
+# ----------------------------------------------------------------------------
+
+class Conv2d(nn.Conv2d):
+  """nn.Conv2d parameters (OIHW fp32 master weights); square stride/padding,
+  dilation 1, groups 1 — everything sg2im builds (layers.py:178, crn.py:41-45)."""
+
+  def _cfg(self):
+    if (self.dilation != (1, 1) or self.groups != 1 or self.stride[0] != self.stride[1]
+        or self.padding[0] != self.padding[1] or self.padding_mode != 'zeros'):
+      raise NotImplementedError('sg2im_b200.Conv2d: only square stride/zero padding, no '
+                                'dilation/groups (all the reference uses)')
+    return self.stride[0], self.padding[0]
+
+  def forward_nhwc(self, h, act=0, slope=0.0, in_ch=None):
+    stride, pad = self._cfg()
+    return ops.conv2d(h, self.weight, self.bias, stride, pad, act, slope, in_ch)
+
+  def forward(self, x):
+    return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
+
+
+class Linear(nn.Linear):
+  def forward_act(self, x, act=0, slope=0.0):
+    lead = x.shape[:-1]
+    y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, act, slope)
+    return y.view(*lead, self.out_features)
+
+  def forward(self, x):
+    return self.forward_act(x)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+  def forward_nhwc(self, h, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0):
+    return ops.bn_act(h, self, slope, up, unbias_mult, out, out_coff)
+
+  def forward(self, x):
+    return _to_nchw(self.forward_nhwc(_to_nhwc(x).contiguous()))
+
+
+class BatchNorm1d(nn.BatchNorm1d):
+  """(rows, C) batch norm for build_mlp(batch_norm='batch')."""
+
+  def forward_act(self, x, slope=1.0):
+    M, C = x.shape
+    return ops.bn_act(x.contiguous().view(M, 1, 1, C), self, slope).view(M, C)
+
+  def forward(self, x):
+    return self.forward_act(x)
+
+
+class LeakyReLU(nn.LeakyReLU):
+  def forward(self, x):
+    if x.dim() == 4:
+      return _to_nchw(ops.bn_act(_to_nhwc(x).contiguous(), None, self.negative_slope))
+    M = x.numel() // x.size(-1)
+    return ops.bn_act(x.contiguous().view(M, 1, 1, x.size(-1)), None,
+                      self.negative_slope).view(x.shape)
+
+
+class ReLU(nn.ReLU):
+  negative_slope = 0.0
+
+  def forward(self, x):
+    return LeakyReLU.forward(self, x)
+
+
+class Upsample(nn.Upsample):
+  """Nearest-neighbour integer upsampling (model.py:98, layers.py 'UX')."""
+
+  def _factor(self):
+    f = self.scale_factor
+    if self.mode != 'nearest' or f is None or int(f) != f:
+      raise NotImplementedError('sg2im_b200.Upsample: integer nearest upsampling only')
+    return int(f)
+
+  def forward(self, x):
+    return _to_nchw(ops.bn_act(_to_nhwc(x).contiguous(), None, 1.0, self._factor()))
+
+
+class GlobalAvgPool(nn.Module):
+  """sg2im/layers.py:83-86 (layout-agnostic form of view(N,C,-1).mean(2))."""
+
+  def forward(self, x):
+    return x.mean(dim=(2, 3))
+
+
+class Flatten(nn.Module):
+  def forward(self, x):
+    return x.reshape(x.size(0), -1)
+
+  def __repr__(self):
+    return 'Flatten()'
+
+
+class Unflatten(nn.Module):
+  def __init__(self, size):
+    super(Unflatten, self).__init__()
+    self.size = size
+
+  def forward(self, x):
+    return x.view(*self.size)
+
+  def __repr__(self):
+    return 'Unflatten(%s)' % ', '.join('%d' % d for d in self.size)
+
+
+class AvgPool2(nn.AvgPool2d):
+  """'P2' with pooling='avg' (layers.py:195-201)."""
+
+  def forward(self, x):
+    h = _to_nhwc(x).contiguous()
+    N, H, W, C = h.shape
+    return _to_nchw(_AvgPool2Fn.apply(h))
+
+
+class _AvgPool2Fn(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, h):
+    N, H, W, C = h.shape
+    out = torch.empty(N, H // 2, W // 2, C, dtype=h.dtype, device=h.device)
+    ops.avgpool2_fwd(h, 0, C, out, 0)
+    ctx.shape = h.shape
+    return out
+
+  @staticmethod
+  def backward(ctx, dy):
+    N, H, W, C = ctx.shape
+    dx = torch.empty(N, H, W, C, dtype=dy.dtype, device=dy.device)
+    ops.avgpool2_bwd(dy.contiguous(), 0, C, dx, 0, False)
+    return dx
+
+
+# ----------------------------------------------------------------------------
+# Sequential with peephole fusion
+# ----------------------------------------------------------------------------
+
+def _slope_of(m):
+  if isinstance(m, nn.LeakyReLU):
+    return m.negative_slope
+  if isinstance(m, nn.ReLU):
+    return 0.0
+  return None
+
+
+class FusedSequential(nn.Sequential):
+  """An nn.Sequential (same children, same state_dict keys) whose forward
+  walks the children with three fusions, each one kernel instead of two/three:
+    Conv2d|Linear -> ReLU|LeakyReLU      : activation in the GEMM epilogue
+    BatchNorm -> ReLU|LeakyReLU          : one normalise+activate pass
+    Upsample(x2) -> BatchNorm2d          : upsample folded into the BN apply
+  Unknown children fall back to their own forward (NCHW view in / out)."""
+
+  def forward(self, x):
+    mods = list(self)
+    four_d = x.dim() == 4
+    h = _to_nhwc(x) if four_d else x
+    i = 0
+    while i < len(mods):
+      m = mods[i]
+      nxt = mods[i + 1] if i + 1 < len(mods) else None
+      s = _slope_of(nxt) if nxt is not None else None
+      if isinstance(m, Conv2d) and four_d:
+        if s is not None:
+          h = m.forward_nhwc(h, 1, s); i += 2
+        else:
+          h = m.forward_nhwc(h); i += 1
+      elif isinstance(m, Linear) and not four_d:
+        if s is not None:
+          h = m.forward_act(h, 1, s); i += 2
+        else:
+          h = m.forward_act(h); i += 1
+      elif isinstance(m, BatchNorm2d) and four_d:
+        if s is not None:
+          h = m.forward_nhwc(h.contiguous(), s); i += 2
+        else:
+          h = m.forward_nhwc(h.contiguous()); i += 1
+      elif isinstance(m, BatchNorm1d) and not four_d:
+        if s is not None:
+          h = m.forward_act(h, s); i += 2
+        else:
+          h = m.forward_act(h); i += 1
+      elif isinstance(m, Upsample) and four_d and isinstance(nxt, BatchNorm2d):
+        f = m._factor()
+        h = nxt.forward_nhwc(h.contiguous(), 1.0, f, f * f); i += 2
+      elif isinstance(m, (Flatten, Unflatten)):
+        h = m(_to_nchw(h) if four_d else h)
+        four_d = h.dim() == 4
+        h = _to_nhwc(h) if four_d else h
+        i += 1
+      else:
+        y = m(_to_nchw(h) if four_d else h)
+        four_d = y.dim() == 4
+        h = _to_nhwc(y) if four_d else y
+        i += 1
+    return _to_nchw(h) if four_d else h
+
+
+# ----------------------------------------------------------------------------
+# factories (reference signatures)
+# ----------------------------------------------------------------------------
+
+def get_normalization_2d(channels, normalization):
+  """sg2im/layers.py:22-30."""
+  if normalization == 'instance':
+    raise NotImplementedError(
+        "sg2im_b200: normalization='instance' is outside the accelerated path "
+        "(scripts/train.py defaults to 'batch'); use 'batch' or 'none'")
+  elif normalization == 'batch':
+    return BatchNorm2d(channels)
+  elif normalization == 'none':
+    return None
+  else:
+    raise ValueError('Unrecognized normalization type "%s"' % normalization)
+
+
+def get_activation(name):
+  """sg2im/layers.py:33-46 — including its quirk: the reference reassigns
+  name = 'leakyrelu' before the lookup, so 'relu' also yields LeakyReLU (slope
+  0.01).  Reproduced for result compatibility."""
+  kwargs = {}
+  if name.lower().startswith('leakyrelu'):
+    if '-' in name:
+      kwargs = {'negative_slope': float(name.split('-')[1])}
+  return LeakyReLU(**kwargs)
+
+
+def _init_conv(layer, method):
+  if not isinstance(layer, nn.Conv2d) or method == 'default':
+    return
+  if method == 'kaiming-normal':
+    nn.init.kaiming_normal_(layer.weight)
+  elif method == 'kaiming-uniform':
+    nn.init.kaiming_uniform_(layer.weight)
+
+
+def _get_padding(K, mode):
+  """sg2im/layers.py:120-126."""
+  if mode == 'valid':
+    return 0
+  elif mode == 'same':
+    assert K % 2 == 1, 'Invalid kernel size %d for "same" padding' % K
+    return (K - 1) // 2
+
+
+def build_cnn(arch, normalization='batch', activation='relu', padding='same',
+              pooling='max', init='default'):
+  """sg2im/layers.py:129-213: architecture-string CNN builder.
+  IX / CK-X[-S] / UX / PX / FC-X-Y are built on the sm_100a kernels; 'R'
+  (residual blocks) and max pooling are outside the accelerated path (no
+  default architecture uses them) and raise NotImplementedError.
+  Returns (nn.Sequential, channels)."""
+  if isinstance(arch, str):
+    arch = arch.split(',')
+  cur_C = 3
+  if len(arch) > 0 and arch[0][0] == 'I':
+    cur_C = int(arch[0][1:])
+    arch = arch[1:]
+
+  first_conv = True
+  flat = False
+  layers = []
+  for i, s in enumerate(arch):
+    if s[0] == 'C':
+      if not first_conv:
+        layers.append(get_normalization_2d(cur_C, normalization))
+        layers.append(get_activation(activation))
+      first_conv = False
+      vals = [int(v) for v in s[1:].split('-')]
+      if len(vals) == 2:
+        K, next_C = vals
+        stride = 1
+      elif len(vals) == 3:
+        K, next_C, stride = vals
+      P = _get_padding(K, padding)
+      conv = Conv2d(cur_C, next_C, kernel_size=K, padding=P, stride=stride)
+      layers.append(conv)
+      _init_conv(layers[-1], init)
+      cur_C = next_C
+    elif s[0] == 'R':
+      raise NotImplementedError("sg2im_b200.build_cnn: residual blocks ('R') are outside the "
+                                'accelerated path')
+    elif s[0] == 'U':
+      layers.append(Upsample(scale_factor=int(s[1:]), mode='nearest'))
+    elif s[0] == 'P':
+      factor = int(s[1:])
+      if pooling == 'avg' and factor == 2:
+        layers.append(AvgPool2(kernel_size=2, stride=2))
+      else:
+        raise NotImplementedError("sg2im_b200.build_cnn: only 'P2' with pooling='avg' is "
+                                  'accelerated')
+    elif s[:2] == 'FC':
+      _, Din, Dout = s.split('-')
+      Din, Dout = int(Din), int(Dout)
+      if not flat:
+        layers.append(Flatten())
+      flat = True
+      layers.append(Linear(Din, Dout))
+      if i + 1 < len(arch):
+        layers.append(get_activation(activation))
+      cur_C = Dout
+    else:
+      raise ValueError('Invalid layer "%s"' % s)
+  layers = [layer for layer in layers if layer is not None]
+  for layer in layers:
+    print(layer)                                   # the reference prints them too (:211-212)
+  return FusedSequential(*layers), cur_C
+
+
+def build_mlp(dim_list, activation='relu', batch_norm='none',
+              dropout=0, final_nonlinearity=True):
+  """sg2im/layers.py:216-232."""
+  layers = []
+  for i in range(len(dim_list) - 1):
+    dim_in, dim_out = dim_list[i], dim_list[i + 1]
+    layers.append(Linear(dim_in, dim_out))
+    final_layer = (i == len(dim_list) - 2)
+    if not final_layer or final_nonlinearity:
+      if batch_norm == 'batch':
+        layers.append(BatchNorm1d(dim_out))
+      if activation == 'relu':
+        layers.append(ReLU())
+      elif activation == 'leakyrelu':
+        layers.append(LeakyReLU())
+    if dropout > 0:
+      layers.append(nn.Dropout(p=dropout))
+  return FusedSequential(*layers)

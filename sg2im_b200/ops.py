@@ -1,0 +1,516 @@
+"""Kernel wrappers and autograd Functions over the C-ABI (include/sg2im_b200.h).
+
+Internal tensor convention: activations are 4-D tensors of SHAPE (N, H, W, C)
+("NHWC"), fp32, normally contiguous; matrices are (rows, features).  The
+nn.Module mirror (layers.py etc.) presents the reference's NCHW shapes to
+callers by permuting views — no data movement.
+
+PyTorch here is plumbing only: allocation (caching allocator), stream choice,
+autograd graph bookkeeping.  Every arithmetic op of the hot path is a launch
+into libsg2im_b200.so; a non-CUDA tensor raises (no CPU fallback).
+"""
+import torch
+
+from . import _lib
+
+_call = _lib.call
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+  return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype=torch.float32, name='tensor'):
+  if not t.is_cuda:
+    raise RuntimeError('sg2im_b200: %s must be a CUDA tensor (the hot path has no CPU '
+                       'fallback; the CPU oracle lives in oracle/ for tests only)' % name)
+  if t.dtype != dtype:
+    raise RuntimeError('sg2im_b200: %s must be %s, got %s' % (name, dtype, t.dtype))
+  return t
+
+
+def _count(n=1):
+  _lib.launches += n
+
+
+# --------------------------------------------------------------------------
+# raw kernel wrappers (no autograd)
+# --------------------------------------------------------------------------
+
+def csr_build(idx, nroles, num_rows):
+  """idx: int64 (T,) for nroles=1 or (T,2) for nroles=2.  Returns
+  (row_ptr int32[R+1], entries int32[nroles*T])."""
+  _chk(idx, torch.int64, 'idx')
+  idx = idx.contiguous()
+  T = idx.size(0)
+  stride = 1 if idx.dim() == 1 else idx.size(1)
+  row_ptr = torch.empty(num_rows + 1, dtype=torch.int32, device=idx.device)
+  entries = torch.empty(max(nroles * T, 1), dtype=torch.int32, device=idx.device)
+  _call('sg2im_csr_build', _p(idx), T, stride, nroles, num_rows, _p(row_ptr), _p(entries),
+        _stream())
+  _count(3)
+  return row_ptr, entries
+
+
+def triple_gather(rows, mid, edges, Wm, row_ptr=None):
+  rows = _chk(rows).contiguous()
+  T, Wr = edges.size(0), rows.size(1)
+  if mid is not None:
+    mid = _chk(mid).contiguous()
+  out = torch.empty(T, 2 * Wr + Wm, dtype=torch.float32, device=rows.device)
+  _call('sg2im_triple_gather', _p(rows), _p(mid), _p(edges), T, Wr, Wm, _p(row_ptr), _p(out),
+        _stream())
+  _count()
+  return out
+
+
+def segment_sum(src, off0, off1, W, row_ptr, entries, num_rows, avg):
+  src = _chk(src).contiguous()
+  out = torch.empty(num_rows, W, dtype=torch.float32, device=src.device)
+  _call('sg2im_segment_sum', _p(src), src.size(1), off0, off1, W, _p(row_ptr), _p(entries),
+        num_rows, int(avg), _p(out), _stream())
+  _count()
+  return out
+
+
+def conv_out_size(h, k, s, p):
+  return (h + 2 * p - k) // s + 1
+
+
+def conv_igemm(mode, x, w_packed, bias, KH, KW, S, P, out_hw, Cout, act=0, slope=0.0,
+               out=None, out_coff=0):
+  """x: (N,Hin,Win,Cin) any strides.  Returns/writes (N,Hout,Wout,Cout[slice])."""
+  _chk(x)
+  N, Hin, Win, Cin = x.shape
+  Hout, Wout = out_hw
+  sn, sh, sw, sc = x.stride()
+  if out is None:
+    out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
+  cstride = out.size(3)
+  _call('sg2im_conv_igemm', mode, _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(w_packed),
+        _p(bias), KH, KW, S, P, Hout, Wout, Cout, int(act), float(slope), _p(out), cstride,
+        out_coff, _stream())
+  _count()
+  return out
+
+
+def conv_wgrad(x, dy, KH, KW, S, P):
+  """Returns dw packed (KH*KW*Cin, Cout)."""
+  _chk(x)
+  dy = _chk(dy).contiguous()
+  N, Hin, Win, Cin = x.shape
+  _, Hout, Wout, Cout = dy.shape
+  sn, sh, sw, sc = x.stride()
+  dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
+  _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
+        Hout, Wout, Cout, _p(dw), _stream())
+  _count()
+  return dw
+
+
+def colsum(x2d):
+  x2d = _chk(x2d).contiguous()
+  M, C = x2d.shape
+  out = torch.empty(C, dtype=torch.float32, device=x2d.device)
+  scratch = torch.empty(C, dtype=torch.float64, device=x2d.device)
+  _call('sg2im_colsum', _p(x2d), M, C, _p(out), _p(scratch), _stream())
+  _count(3)
+  return out
+
+
+def act_bwd(dy, y, slope):
+  dy = _chk(dy).contiguous()
+  dx = torch.empty_like(dy)
+  _call('sg2im_act_bwd', _p(dy), _p(y), float(slope), dy.numel(), _p(dx), _stream())
+  _count()
+  return dx
+
+
+def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum, eps,
+                   unbias_mult=1):
+  """Batch statistics of x (rows = all dims but the last) -> (scale, shift, save)."""
+  C = x.size(-1)
+  M = x.numel() // C
+  dev = x.device
+  scale = torch.empty(C, dtype=torch.float32, device=dev)
+  shift = torch.empty(C, dtype=torch.float32, device=dev)
+  save = torch.empty(2 * C, dtype=torch.float32, device=dev)
+  sums = None
+  if training:
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    _call('sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
+    _count()
+  _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, _p(gamma), _p(beta), float(eps),
+        float(momentum), int(training), _p(running_mean), _p(running_var), _p(scale), _p(shift),
+        _p(save), _stream())
+  _count()
+  return scale, shift, save
+
+
+def scale_act_fwd(x, scale, shift, slope, up, out=None, out_coff=0):
+  N, H, W, C = x.shape
+  if out is None:
+    out = torch.empty(N, H * up, W * up, C, dtype=torch.float32, device=x.device)
+  _call('sg2im_scale_act_fwd', _p(x), N, H, W, C, _p(scale), _p(shift), float(slope), up,
+        _p(out), out.size(3), out_coff, _stream())
+  _count()
+  return out
+
+
+def scale_act_bwd(dy, dy_coff, x, scale, shift, save, slope, up, training, want_param_grads):
+  """dy: (N,H*up,W*up,Ctot) contiguous, slice [dy_coff, dy_coff+C).  Returns
+  (dx, dgamma, dbeta)."""
+  N, H, W, C = x.shape
+  dev = x.device
+  sums = None
+  need_sums = (training and save is not None) or want_param_grads
+  if need_sums:
+    sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    _call('sg2im_scale_act_bwd_reduce', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C,
+          _p(scale), _p(shift), _p(save), float(slope), up, _p(sums), _stream())
+    _count()
+  dx = torch.empty_like(x)
+  dgamma = dbeta = None
+  if want_param_grads:
+    dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+  _call('sg2im_scale_act_bwd_apply', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C, _p(scale),
+        _p(shift), _p(save), float(slope), up, int(training), _p(sums), _p(dx), _p(dgamma),
+        _p(dbeta), _stream())
+  _count(2 if want_param_grads else 1)
+  return dx, dgamma, dbeta
+
+
+def avgpool2_fwd(x, x_coff, C, out, out_coff):
+  N, H, W, _ = x.shape
+  _call('sg2im_avgpool2_fwd', _p(x), x.size(3), x_coff, N, H, W, C, _p(out), out.size(3),
+        out_coff, _stream())
+  _count()
+
+
+def avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
+  N, H, W, _ = dfine.shape
+  _call('sg2im_avgpool2_bwd', _p(dcoarse), dcoarse.size(3), dc_coff, N, H, W, C, _p(dfine),
+        dfine.size(3), df_coff, int(accumulate), _stream())
+  _count()
+
+
+# --------------------------------------------------------------------------
+# weight packing (OIHW master parameters -> kernel layouts)
+# --------------------------------------------------------------------------
+
+def pack_conv_fwd(weight):
+  """OIHW -> (KH*KW*Cin, Cout) for mode 0."""
+  Co, Ci, KH, KW = weight.shape
+  return weight.permute(2, 3, 1, 0).reshape(KH * KW * Ci, Co).contiguous()
+
+
+def pack_conv_dgrad(weight):
+  """OIHW -> (KH*KW*Cout, Cin) for mode 1."""
+  Co, Ci, KH, KW = weight.shape
+  return weight.permute(2, 3, 0, 1).reshape(KH * KW * Co, Ci).contiguous()
+
+
+def unpack_conv_wgrad(dw, shape):
+  Co, Ci, KH, KW = shape
+  return dw.view(KH, KW, Ci, Co).permute(3, 2, 0, 1)
+
+
+# --------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------
+
+class Conv(torch.autograd.Function):
+  """y = act(conv(x, W) + b), NHWC.  weight is the OIHW master parameter.
+  ``in_ch``: use only the first in_ch input channels of the weight (the CRN's
+  first stage, whose extra input channel is identically zero)."""
+
+  @staticmethod
+  def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch):
+    _chk(weight, name='weight')
+    Co, Ci_w, KH, KW = weight.shape
+    Ci = Ci_w if in_ch is None else in_ch
+    assert x.size(3) == Ci, 'conv: input has %d channels, weight expects %d' % (x.size(3), Ci)
+    w_used = weight if Ci == Ci_w else weight[:, :Ci]
+    Hout = conv_out_size(x.size(1), KH, stride, pad)
+    Wout = conv_out_size(x.size(2), KW, stride, pad)
+    y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
+                   act, slope)
+    ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
+    ctx.save_for_backward(x, weight, y if act else None)
+    ctx.has_bias = bias is not None
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    stride, pad, act, slope, Ci, wshape = ctx.cfg
+    x, weight, y = ctx.saved_tensors
+    Co, Ci_w, KH, KW = wshape
+    dy = dy.contiguous()
+    if act:
+      dy = act_bwd(dy, y, slope)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+      w_used = weight if Ci == Ci_w else weight[:, :Ci]
+      dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
+                      (x.size(1), x.size(2)), Ci)
+    if ctx.needs_input_grad[1]:
+      dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
+      dw = unpack_conv_wgrad(dwp, (Co, Ci, KH, KW))
+      if Ci != Ci_w:
+        full = torch.zeros(wshape, dtype=dw.dtype, device=dw.device)
+        full[:, :Ci] = dw
+        dw = full
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      db = colsum(dy.view(-1, Co))
+    return dx, dw, db, None, None, None, None, None
+
+
+def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None):
+  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch)
+
+
+def linear(x2d, weight, bias, act=0, slope=0.0):
+  """nn.Linear (+ fused ReLU/LeakyReLU) as a 1x1 convolution over rows."""
+  M, K = x2d.shape
+  y = Conv.apply(x2d.reshape(M, 1, 1, K), weight.view(weight.size(0), K, 1, 1), bias,
+                 1, 0, act, slope, None)
+  return y.view(M, weight.size(0))
+
+
+class BNAct(torch.autograd.Function):
+  """y = up_x{up}( leaky_slope( BN(x) ) ) written into out[..., coff:coff+C]
+  (out=None -> fresh tensor).  BN optional (gamma None and no running stats ->
+  plain activation/upsample).  Train mode uses batch statistics and updates the
+  running buffers in place, like nn.BatchNorm2d."""
+
+  @staticmethod
+  def forward(ctx, x, gamma, beta, running_mean, running_var, use_bn, training, momentum, eps,
+              slope, up, unbias_mult, out, out_coff):
+    x = _chk(x).contiguous()
+    scale = shift = save = None
+    if use_bn:
+      scale, shift, save = bn_scale_shift(x, gamma, beta, running_mean, running_var, training,
+                                          momentum, eps, unbias_mult)
+    y = scale_act_fwd(x, scale, shift, slope, up, out, out_coff)
+    if out is not None:
+      ctx.mark_dirty(out)
+    ctx.cfg = (use_bn, training, slope, up, out_coff, out is not None)
+    ctx.save_for_backward(x, scale, shift, save)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    use_bn, training, slope, up, coff, sliced = ctx.cfg
+    x, scale, shift, save = ctx.saved_tensors
+    dy = dy.contiguous()
+    want_pg = use_bn and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+    dx, dgamma, dbeta = scale_act_bwd(dy, coff, x, scale, shift, save, slope, up,
+                                      training and use_bn, want_pg)
+    dout = dy if sliced else None
+    return (dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, dout, None)
+
+
+def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0):
+  """bn: an nn.BatchNorm2d-like module (weight, bias, running_mean, running_var,
+  training, momentum, eps, num_batches_tracked) or None."""
+  if bn is None:
+    return BNAct.apply(x, None, None, None, None, False, False, 0.0, 0.0, slope, up, 1, out,
+                       out_coff)
+  training = bn.training or bn.running_mean is None
+  if training and bn.num_batches_tracked is not None:
+    bn.num_batches_tracked.add_(1)
+  momentum = 0.1 if bn.momentum is None else bn.momentum
+  return BNAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, True, training,
+                     momentum, bn.eps, slope, up, unbias_mult, out, out_coff)
+
+
+class TripleGather(torch.autograd.Function):
+  """cur_t_vecs = cat([obj[s], pred, obj[o]], 1)   (sg2im/graph.py:77-82)."""
+
+  @staticmethod
+  def forward(ctx, obj_vecs, pred_vecs, edges, csr):
+    out = triple_gather(obj_vecs, pred_vecs, edges, pred_vecs.size(1))
+    ctx.csr = csr
+    ctx.dims = (obj_vecs.size(0), obj_vecs.size(1), pred_vecs.size(1))
+    return out
+
+  @staticmethod
+  def backward(ctx, dcur):
+    O, D, Dp = ctx.dims
+    row_ptr, entries = ctx.csr
+    dcur = dcur.contiguous()
+    dobj = segment_sum(dcur, 0, D + Dp, D, row_ptr, entries, O, False)
+    dpred = dcur[:, D:D + Dp]
+    return dobj, dpred, None, None
+
+
+class GraphPool(torch.autograd.Function):
+  """(pooled (O,H), new_p (T,Dout)) from new_t_vecs (T, 2H+Dout)
+  (sg2im/graph.py:85-114); bit-exact vs the CPU scatter_add order."""
+
+  @staticmethod
+  def forward(ctx, new_t, edges, csr, H, Dout, num_objs, avg):
+    row_ptr, entries = csr
+    pooled = segment_sum(new_t, 0, H + Dout, H, row_ptr, entries, num_objs, avg)
+    new_p = new_t[:, H:H + Dout].contiguous()
+    ctx.csr = csr
+    ctx.edges = edges
+    ctx.cfg = (H, Dout, avg)
+    return pooled, new_p
+
+  @staticmethod
+  def backward(ctx, dpooled, dnew_p):
+    H, Dout, avg = ctx.cfg
+    row_ptr, _ = ctx.csr
+    if dpooled is None:
+      dpooled = torch.zeros(row_ptr.numel() - 1, H, dtype=torch.float32, device=row_ptr.device)
+    dnew_t = triple_gather(dpooled, dnew_p, ctx.edges, Dout, row_ptr if avg else None)
+    return dnew_t, None, None, None, None, None, None
+
+
+class Layout(torch.autograd.Function):
+  """Fused masks_to_layout / boxes_to_layout (sg2im/layout.py:30-91) + the
+  noise concat of model.py:164-169.  Output (N,H,W,D+noise_c) NHWC."""
+
+  @staticmethod
+  def forward(ctx, vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners):
+    vecs = _chk(vecs).contiguous()
+    boxes = _chk(boxes).contiguous()
+    O, D = vecs.shape
+    M = 0
+    if masks is not None:
+      masks = _chk(masks.float() if masks.dtype != torch.float32 else masks).contiguous()
+      M = masks.size(1)
+    nc = 0 if noise is None else noise.size(1)
+    out = torch.empty(N, H, W, D + nc, dtype=torch.float32, device=vecs.device)
+    _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, out)
+    ctx.save_for_backward(vecs, boxes, masks, obj_to_img)
+    ctx.cfg = (N, H, W, M, align_corners)
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    vecs, boxes, masks, obj_to_img = ctx.saved_tensors
+    N, H, W, M, align = ctx.cfg
+    if ctx.needs_input_grad[1]:
+      raise NotImplementedError(
+          'sg2im_b200: gradient w.r.t. layout boxes is outside the accelerated training path '
+          '(scripts/train.py always passes boxes_gt, train.py:525-528)')
+    dout = dout.contiguous()
+    O, D = vecs.shape
+    dvecs = torch.zeros_like(vecs)
+    dmasks = None
+    if masks is not None and ctx.needs_input_grad[2]:
+      dmasks = torch.zeros_like(masks)
+    _call('sg2im_layout_bwd', _p(dout), dout.size(3), _p(vecs), _p(boxes), _p(masks), M,
+          _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
+    _count()
+    return dvecs, None, dmasks, None, None, None, None, None, None
+
+
+def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, out):
+  O, D = vecs.shape
+  M = 0 if masks is None else masks.size(1)
+  img_ptr, img_ent = csr_build(obj_to_img, 1, N)
+  nc = 0 if noise is None else noise.size(1)
+  ns = (0, 0, 0, 0) if noise is None else noise.stride()      # (n, c, h, w)
+  _call('sg2im_layout_fwd', _p(vecs), _p(boxes), _p(masks), M, _p(img_ptr), _p(img_ent), N, O,
+        D, H, W, int(align_corners), _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
+        out.size(3), _stream())
+  _count()
+
+
+class LayoutStack(torch.autograd.Function):
+  """Layout + the input buffers of every cascaded-refinement stage in one go.
+
+  Level k (k = 0 coarsest ... L-1 full resolution) is an NHWC buffer of
+  C + extras[k] channels, C = D + noise channels: the first C hold the layout
+  average-pooled by a 2x2 cascade (F.avg_pool2d, sg2im/crn.py:58-62; the
+  full-resolution level is written by the layout kernel itself), the trailing
+  ``extras[k]`` channels are left for the previous stage's upsampled features,
+  which BNAct later writes in place (the torch.cat of crn.py:63 never runs).
+  Backward folds the per-level layout gradients back down the cascade into the
+  finest level's buffer and runs the layout backward on that slice."""
+
+  @staticmethod
+  def forward(ctx, vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, extras):
+    vecs = _chk(vecs).contiguous()
+    boxes = _chk(boxes).contiguous()
+    if masks is not None:
+      masks = _chk(masks.float() if masks.dtype != torch.float32 else masks).contiguous()
+    D = vecs.size(1)
+    C = D + (0 if noise is None else noise.size(1))
+    L = len(extras)
+    dev = vecs.device
+    bufs = [None] * L
+    bufs[L - 1] = torch.empty(N, H, W, C + extras[L - 1], dtype=torch.float32, device=dev)
+    _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, bufs[L - 1])
+    for k in range(L - 2, -1, -1):
+      f = L - 1 - k
+      bufs[k] = torch.empty(N, H >> f, W >> f, C + extras[k], dtype=torch.float32, device=dev)
+      avgpool2_fwd(bufs[k + 1], 0, C, bufs[k], 0)
+    ctx.save_for_backward(vecs, boxes, masks, obj_to_img)
+    ctx.cfg = (N, H, W, C, align_corners)
+    return tuple(bufs)
+
+  @staticmethod
+  def backward(ctx, *douts):
+    vecs, boxes, masks, obj_to_img = ctx.saved_tensors
+    N, H, W, C, align = ctx.cfg
+    if ctx.needs_input_grad[1]:
+      raise NotImplementedError(
+          'sg2im_b200: gradient w.r.t. layout boxes is outside the accelerated training path '
+          '(scripts/train.py always passes boxes_gt, train.py:525-528)')
+    L = len(douts)
+    g = [d.contiguous() for d in douts]
+    # the stage gradients are private temporaries of this backward pass (fresh
+    # conv-dgrad outputs): accumulate the coarser levels into the finer in place
+    for k in range(1, L):
+      avgpool2_bwd(g[k - 1], 0, C, g[k], 0, True)
+    O, D = vecs.shape
+    M = 0 if masks is None else masks.size(1)
+    dvecs = torch.zeros_like(vecs)
+    dmasks = None
+    if masks is not None and ctx.needs_input_grad[2]:
+      dmasks = torch.zeros_like(masks)
+    _call('sg2im_layout_bwd', _p(g[L - 1]), g[L - 1].size(3), _p(vecs), _p(boxes), _p(masks), M,
+          _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
+    _count()
+    return dvecs, None, dmasks, None, None, None, None, None, None, None
+
+
+class Crop(torch.autograd.Function):
+  """crop_bbox_batch (sg2im/bilinear.py:28-132).  feats: (N,H,W,C)-shaped view
+  with any strides; returns (B,HH,WW,C) NHWC."""
+
+  @staticmethod
+  def forward(ctx, feats, boxes, idx, HH, WW, align_corners):
+    _chk(feats)
+    boxes = _chk(boxes).contiguous()
+    idx = _chk(idx, torch.int64, 'bbox_to_feats').contiguous()
+    N, H, W, C = feats.shape
+    B = boxes.size(0)
+    out = torch.empty(B, HH, WW, C, dtype=torch.float32, device=feats.device)
+    sn, sh, sw, sc = feats.stride()
+    _call('sg2im_crop_fwd', _p(feats), sn, sh, sw, sc, N, H, W, C, _p(boxes), _p(idx), B, HH, WW,
+          int(align_corners), _p(out), _stream())
+    _count()
+    ctx.save_for_backward(boxes, idx)
+    ctx.cfg = (N, H, W, C, HH, WW, align_corners)
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    boxes, idx = ctx.saved_tensors
+    N, H, W, C, HH, WW, align = ctx.cfg
+    dout = dout.contiguous()
+    dfeats = torch.zeros(N, H, W, C, dtype=torch.float32, device=dout.device)
+    _call('sg2im_crop_bwd', _p(dout), _p(boxes), _p(idx), N, H, W, C, boxes.size(0), HH, WW,
+          int(align), _p(dfeats), _stream())
+    _count()
+    return dfeats, None, None, None, None, None

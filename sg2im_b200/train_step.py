@@ -1,0 +1,211 @@
+"""One generator + object-discriminator + image-discriminator training
+iteration — the loop body of the reference's scripts/train.py:508-592 as a
+reusable object, plus the data-parallel plumbing the reference never had.
+
+Multi-GPU: one process per GPU, the batch sharded by image, no
+exchange in the forward pass (objects and triples never cross images),
+BatchNorm statistics rank-local, and exactly one collective per optimiser per
+iteration: an NCCL all-reduce (sum, then / world) of that network's flat fp32
+gradient bucket.  The non-finite-loss skip of train.py:552-555 is made
+collective (all-reduce MIN of the finite flag) so ranks cannot diverge.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .losses import get_gan_losses
+
+DEFAULT_ARGS = dict(                      # scripts/train.py:94-131
+    l1_pixel_loss_weight=1.0, bbox_pred_loss_weight=10.0,
+    predicate_pred_loss_weight=0.0, mask_loss_weight=0.0,
+    discriminator_loss_weight=0.01, d_obj_weight=1.0, d_img_weight=1.0,
+    ac_loss_weight=0.1, gan_loss_type='gan', learning_rate=1e-4)
+
+
+class FlatGrads(object):
+  """All gradients of one network in a single fp32 bucket: every parameter's
+  ``.grad`` is a view into ``flat``, so zeroing is one memset and the
+  data-parallel exchange is one all-reduce with no packing copies."""
+
+  def __init__(self, params):
+    self.params = [p for p in params if p.requires_grad]
+    total = sum(p.numel() for p in self.params)
+    dev = self.params[0].device
+    self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+    off = 0
+    for p in self.params:
+      n = p.numel()
+      p.grad = self.flat[off:off + n].view_as(p)
+      off += n
+
+  def zero(self):
+    self.flat.zero_()
+    # re-attach in case something replaced .grad (e.g. set_to_none)
+    off = 0
+    for p in self.params:
+      n = p.numel()
+      if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
+        p.grad = self.flat[off:off + n].view_as(p)
+      off += n
+
+  def all_reduce_mean(self, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+      world = dist.get_world_size(group)
+      if world > 1:
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.div_(world)
+
+
+def _all_finite(value, group=None):
+  """Collective version of train.py:552: every rank takes the same branch."""
+  ok = math.isfinite(value)
+  import torch.distributed as dist
+  if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32,
+                        device='cuda' if dist.get_backend(group) == 'nccl' else 'cpu')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    ok = bool(flag.item())
+  return ok
+
+
+class TrainStep(object):
+  def __init__(self, model, obj_discriminator, img_discriminator, args=None,
+               fused_adam=None, group=None):
+    a = dict(DEFAULT_ARGS)
+    if args is not None:
+      a.update(args if isinstance(args, dict) else
+               {k: getattr(args, k) for k in DEFAULT_ARGS if hasattr(args, k)})
+    self.args = a
+    self.model, self.d_obj, self.d_img = model, obj_discriminator, img_discriminator
+    self.group = group
+    self.gan_g_loss, self.gan_d_loss = get_gan_losses(a['gan_loss_type'])
+    dev = next(model.parameters()).device
+    if fused_adam is None:
+      fused_adam = dev.type == 'cuda'
+    kw = dict(lr=a['learning_rate'])
+    if fused_adam:
+      kw['fused'] = True
+    self.nets = {'g': model, 'd_obj': obj_discriminator, 'd_img': img_discriminator}
+    self.buckets, self.opts = {}, {}
+    for name, net in self.nets.items():
+      if net is None:
+        continue
+      self.buckets[name] = FlatGrads(net.parameters())
+      self.opts[name] = torch.optim.Adam(self.buckets[name].params, **kw)
+    self.skipped = 0
+
+  # -- loss assembly, scripts/train.py:387-412 + :539-550
+  def generator_losses(self, imgs, imgs_pred, boxes, boxes_pred, masks, masks_pred,
+                       predicates, predicate_scores):
+    a = self.args
+    losses = {}
+    total = torch.zeros(1, dtype=imgs.dtype, device=imgs.device)
+
+    def add(name, val, weight):
+      nonlocal total
+      val = val * weight
+      losses[name] = val
+      total = total + val
+
+    add('L1_pixel_loss', F.l1_loss(imgs_pred, imgs), a['l1_pixel_loss_weight'])
+    add('bbox_pred', F.mse_loss(boxes_pred, boxes), a['bbox_pred_loss_weight'])
+    if a['predicate_pred_loss_weight'] > 0:
+      add('predicate_pred', F.cross_entropy(predicate_scores, predicates),
+          a['predicate_pred_loss_weight'])
+    if a['mask_loss_weight'] > 0 and masks is not None and masks_pred is not None:
+      add('mask_loss', F.binary_cross_entropy(masks_pred, masks.float()),
+          a['mask_loss_weight'])
+    return total, losses
+
+  @staticmethod
+  def _freeze(net, frozen):
+    """The reference lets the generator's backward also produce (and then
+    discard) weight gradients of both discriminators; turning requires_grad off
+    for the G step skips those wgrads without changing any result."""
+    for p in net.parameters():
+      p.requires_grad_(not frozen)
+
+  def step(self, batch, noise=None):
+    """batch: the collate tuple (6 entries for VG, 7 with masks for COCO), on
+    the device.  Returns (losses dict of python floats, imgs_pred detached)."""
+    a = self.args
+    masks = None
+    if len(batch) == 6:
+      imgs, objs, boxes, triples, obj_to_img, _ = batch
+    elif len(batch) == 7:
+      imgs, objs, boxes, masks, triples, obj_to_img, _ = batch
+    else:
+      raise ValueError('batch must have 6 or 7 entries')
+    N = imgs.size(0)
+    predicates = triples[:, 1]
+
+    # ---------------- generator: train.py:524-560
+    imgs_pred, boxes_pred, masks_pred, predicate_scores = self.model(
+        objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, num_imgs=N, noise=noise)
+    total, losses = self.generator_losses(imgs, imgs_pred, boxes, boxes_pred, masks,
+                                          masks_pred, predicates, predicate_scores)
+    if self.d_obj is not None:
+      self._freeze(self.d_obj, True)
+      scores_fake, ac_loss = self.d_obj(imgs_pred, objs, boxes, obj_to_img)
+      losses['ac_loss'] = ac_loss * a['ac_loss_weight']
+      total = total + losses['ac_loss']
+      w = a['discriminator_loss_weight'] * a['d_obj_weight']
+      losses['g_gan_obj_loss'] = self.gan_g_loss(scores_fake) * w
+      total = total + losses['g_gan_obj_loss']
+    if self.d_img is not None:
+      self._freeze(self.d_img, True)
+      scores_fake = self.d_img(imgs_pred)
+      w = a['discriminator_loss_weight'] * a['d_img_weight']
+      losses['g_gan_img_loss'] = self.gan_g_loss(scores_fake) * w
+      total = total + losses['g_gan_img_loss']
+    losses['total_loss'] = total
+
+    keys = list(losses.keys())
+    vals = torch.stack([losses[k].reshape(()) for k in keys]).tolist()     # one D2H sync
+    out = dict(zip(keys, vals))
+    imgs_fake = imgs_pred.detach()
+    if not _all_finite(out['total_loss'], self.group):
+      print('WARNING: Got loss = NaN, not backpropping')
+      self.skipped += 1
+      for d in (self.d_obj, self.d_img):
+        if d is not None:
+          self._freeze(d, False)
+      return out, imgs_fake
+
+    self.buckets['g'].zero()
+    total.backward()
+    self.buckets['g'].all_reduce_mean(self.group)
+    self.opts['g'].step()
+
+    # ---------------- object discriminator: train.py:566-579
+    d_vals = {}
+    if self.d_obj is not None:
+      self._freeze(self.d_obj, False)
+      s_fake, ac_fake = self.d_obj(imgs_fake, objs, boxes, obj_to_img)
+      s_real, ac_real = self.d_obj(imgs, objs, boxes, obj_to_img)
+      d_obj_gan = self.gan_d_loss(s_real, s_fake)
+      d_total = d_obj_gan + ac_real + ac_fake
+      d_vals.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
+      self.buckets['d_obj'].zero()
+      d_total.backward()
+      self.buckets['d_obj'].all_reduce_mean(self.group)
+      self.opts['d_obj'].step()
+
+    # ---------------- image discriminator: train.py:581-592
+    if self.d_img is not None:
+      self._freeze(self.d_img, False)
+      s_fake = self.d_img(imgs_fake)
+      s_real = self.d_img(imgs)
+      d_img_gan = self.gan_d_loss(s_real, s_fake)
+      d_vals['d_img_gan_loss'] = d_img_gan
+      self.buckets['d_img'].zero()
+      d_img_gan.backward()
+      self.buckets['d_img'].all_reduce_mean(self.group)
+      self.opts['d_img'].step()
+
+    if d_vals:
+      dk = list(d_vals.keys())
+      out.update(zip(dk, torch.stack([d_vals[k].reshape(()).detach() for k in dk]).tolist()))
+    return out, imgs_fake

@@ -1,0 +1,141 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every
+symbol include/sg2im_b200.h declares, the module mirror has the reference's
+state_dict keys, the factories parse architectures, the synthetic batches
+have the collate format, and the product refuses to run without CUDA."""
+import contextlib
+import io
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def _quiet():
+  return contextlib.redirect_stdout(io.StringIO())
+
+
+def test_abi_exports_every_declared_symbol():
+  from sg2im_b200 import _lib
+  hdr = open(os.path.join(ROOT, 'include', 'sg2im_b200.h')).read()
+  declared = set(re.findall(r'\b(sg2im_[a-z0-9_]+)\s*\(', hdr))
+  declared.discard('sg2im_stream_t')
+  assert len(declared) >= 20
+  lib = _lib.load()
+  for name in sorted(declared):
+    assert hasattr(lib, name), 'missing export %s' % name
+  assert set(_lib.SIGNATURES) | {'sg2im_last_error_string'} == declared
+  assert lib.sg2im_abi_version() == 1
+  assert isinstance(lib.sg2im_last_error_string(), bytes)
+
+
+def test_invalid_argument_is_an_error_not_a_crash():
+  from sg2im_b200 import _lib
+  with pytest.raises(RuntimeError) as e:
+    _lib.call('sg2im_csr_build', None, 4, 2, 3, 5, None, None, None)     # nroles=3
+  assert 'sg2im_csr_build' in str(e.value)
+
+
+def test_no_cpu_fallback():
+  from sg2im_b200 import ops
+  with pytest.raises(RuntimeError):
+    ops.linear(torch.zeros(2, 4), torch.zeros(3, 4), None)
+
+
+def test_state_dict_keys_match_golden_reference_keys():
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  g = load_golden('train_step.pt')
+  with _quiet():
+    m = Sg2ImModel(vocab=g['vocab'], **g['kwargs'])
+    d_img = PatchDiscriminator(arch=g['arch'], padding='valid')
+    d_obj = AcCropDiscriminator(vocab=g['vocab'], arch=g['arch'], normalization='batch',
+                                activation='leakyrelu-0.2', padding='valid', object_size=16)
+  for net, sd in ((m, g['sd_g']), (d_img, g['sd_img']), (d_obj, g['sd_obj'])):
+    mine = net.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    for k in sd:
+      assert mine[k].shape == sd[k].shape, k
+    net.load_state_dict(sd)
+
+
+def test_default_state_dict_key_list():
+  """Key list spelled out in SURVEY.md §8(b)."""
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.synth import make_vocab
+  with _quiet():
+    m = Sg2ImModel(make_vocab(10, 5), image_size=(64, 64), embedding_dim=8, gconv_dim=8,
+                   gconv_hidden_dim=16, mask_size=16, layout_noise_dim=4,
+                   refinement_dims=(16, 8))
+  keys = set(m.state_dict().keys())
+  for k in ['obj_embeddings.weight', 'pred_embeddings.weight', 'gconv.net1.0.weight',
+            'gconv.net2.2.bias', 'gconv_net.gconvs.3.net1.2.weight', 'box_net.2.bias',
+            'mask_net.1.running_mean', 'mask_net.13.num_batches_tracked', 'mask_net.14.weight',
+            'mask_net.16.bias', 'rel_aux_net.0.weight',
+            'refinement_net.refinement_modules.0.net.0.weight',
+            'refinement_net.refinement_modules.1.net.4.running_var',
+            'refinement_net.output_conv.2.weight']:
+    assert k in keys, k
+  assert m.state_dict()['refinement_net.refinement_modules.0.net.0.weight'].shape == (16, 13, 3, 3)
+
+
+def test_activation_quirk_and_factories():
+  from sg2im_b200.layers import get_activation, build_cnn, build_mlp, get_normalization_2d
+  assert get_activation('relu').negative_slope == 0.01            # layers.py:39 quirk
+  assert get_activation('leakyrelu-0.2').negative_slope == 0.2
+  assert get_activation('leakyrelu').negative_slope == 0.01
+  assert get_normalization_2d(4, 'none') is None
+  with pytest.raises(ValueError):
+    get_normalization_2d(4, 'bogus')
+  with _quiet():
+    cnn, C = build_cnn('I5,C4-64-2,C4-128-2,C4-256-2', padding='valid')
+  assert C == 256
+  kinds = [type(l).__name__ for l in cnn]
+  assert kinds == ['Conv2d', 'BatchNorm2d', 'LeakyReLU', 'Conv2d', 'BatchNorm2d', 'LeakyReLU', 'Conv2d']
+  assert cnn[0].in_channels == 5 and cnn[0].stride == (2, 2) and cnn[0].padding == (0, 0)
+  with pytest.raises(ValueError):
+    with _quiet():
+      build_cnn('X3')
+  mlp = build_mlp([8, 16, 4])
+  assert [type(l).__name__ for l in mlp] == ['Linear', 'ReLU', 'Linear', 'ReLU']
+  assert [type(l).__name__ for l in build_mlp([8, 4], final_nonlinearity=False)] == ['Linear']
+
+
+def test_encode_scene_graphs_matches_reference_encoding():
+  import copy
+  from sg2im_b200.model import Sg2ImModel
+  g = load_golden('sheep.pt')
+  with _quiet():
+    m = Sg2ImModel(vocab=g['vocab'], **g['kwargs'])
+  enc = m.encode_scene_graphs(copy.deepcopy(g['scene_graphs']))
+  for a, b in zip(enc, g['encoded']):
+    assert torch.equal(a, b)
+  with pytest.raises(ValueError):
+    m.encode_scene_graphs({'objects': ['unicorn'], 'relationships': []})
+
+
+def test_synthetic_batch_format():
+  from sg2im_b200.synth import synth_config
+  (imgs, objs, boxes, triples, o2i, t2i), cfg = synth_config('vg128')
+  assert imgs.shape == (32, 3, 128, 128) and objs.shape == (320,) and triples.shape == (448, 3)
+  assert boxes.shape == (320, 4) and (boxes[:, 2:] > boxes[:, :2]).all()
+  assert torch.equal(o2i, torch.sort(o2i).values)
+  assert (objs.view(32, 10)[:, -1] == 0).all()                 # __image__ last per image
+  assert (o2i[triples[:, 0]] == o2i[triples[:, 2]]).all()      # triples never cross images
+  assert (o2i[triples[:, 0]] == t2i).all()
+  batch, cfg = synth_config('coco64')
+  assert len(batch) == 7 and batch[3].shape == (224, 16, 16) and batch[3].dtype == torch.int64
+  assert batch[4].shape == (384, 3)
+
+
+def test_losses_match_oracle():
+  from sg2im_b200 import losses
+  from oracle import sg2im_oracle as orc
+  torch.manual_seed(0)
+  r, f = torch.randn(5, 1), torch.randn(5, 1)
+  assert torch.allclose(losses.gan_g_loss(f), orc.gan_g_loss(f))
+  assert torch.allclose(losses.gan_d_loss(r, f), orc.gan_d_loss(r, f))
+  with pytest.raises(ValueError):
+    losses.get_gan_losses('nope')
