@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one sg2im generator + discriminator training
+iteration (scripts/train.py:508-592) per step, on synthetic scene-graph batches.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vg128]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference        # the CPU port of the reference, host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/sec with the batch
+resident in HBM; `e2e` = the same step through the public API with the batch in
+pinned host memory (H2D copies + loss read-back inside the timed region).
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'train-step images/sec at 128x128'
+UNIT = 'images/s'
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--workload', default='vg128')
+  ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: config)')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-e2e', action='store_true')
+  return ap.parse_args()
+
+
+def model_kwargs(cfg):
+  """scripts/train.py:94-131 defaults for the named workload."""
+  return dict(image_size=cfg['image_size'], embedding_dim=128, gconv_dim=128,
+              gconv_hidden_dim=512, gconv_num_layers=5,
+              refinement_dims=(1024, 512, 256, 128, 64), normalization='batch',
+              activation='leakyrelu-0.2', mask_size=16, layout_noise_dim=32)
+
+
+D_ARCH = 'C4-64-2,C4-128-2,C4-256-2'
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(hbm=p['hbm_gbs'], tf=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                src='measured (MEASURED_PEAKS.json, sustained)')
+  return dict(hbm=6650.0, tf=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(threading.Thread):
+  """SM clock + throttle reasons during the timed region (NVML, 200 ms)."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+    self._stop_evt = threading.Event()
+    self.ok = False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+      self.ok = True
+    except Exception:
+      pass
+
+  def run(self):
+    if not self.ok:
+      return
+    nv = self.nv
+    names = {
+        getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+        getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+        getattr(nv, 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake',
+    }
+    while not self._stop_evt.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      self._stop_evt.wait(0.2)
+
+  def finish(self):
+    self._stop_evt.set()
+    if self.is_alive():
+      self.join(timeout=2)
+    s = sorted(self.samples)
+    med = s[len(s) // 2] if s else None
+    return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+            'samples': len(s)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's step on the host cores
+# ----------------------------------------------------------------------------
+
+def cpu_reference_arm(cfg, steps, warmup, sample_imgs, budget_s=25.0):
+  """Times oracle.OracleTrainer (the torch-CPU restatement of
+  scripts/train.py:508-592, pinned against the unmodified reference by
+  tests/golden) on a bounded sample: `sample_imgs` images of the workload."""
+  from oracle import sg2im_oracle as orc
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  from sg2im_b200.synth import make_vocab, synth_batch
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  vocab = make_vocab(cfg['num_objs'], cfg['num_preds'])
+  torch.manual_seed(0)
+  with contextlib.redirect_stdout(io.StringIO()):
+    g = Sg2ImModel(vocab, **model_kwargs(cfg))            # parameter container only
+    d_img = PatchDiscriminator(D_ARCH, padding='valid')
+    d_obj = AcCropDiscriminator(vocab, D_ARCH, 'batch', 'leakyrelu-0.2', 32, 'valid')
+  tr = orc.OracleTrainer(g.state_dict(), d_obj.state_dict(), d_img.state_dict(),
+                         cfg['image_size'])
+  c = dict(cfg)
+  c['N'] = sample_imgs
+  H, W = cfg['image_size']
+  times = []
+  t_start = time.time()
+  for it in range(warmup + steps):
+    batch = synth_batch(seed=it, **c)
+    noise = torch.randn(sample_imgs, 32, H, W)
+    t0 = time.time()
+    tr.step(batch, noise)
+    dt = time.time() - t0
+    if it >= warmup:
+      times.append(dt)
+    if time.time() - t_start > budget_s and len(times) >= 1:
+      break
+  mean = sum(times) / len(times)
+  return dict(value=sample_imgs / mean, unit=UNIT, cores=cores, kind='port',
+              sample='%d timed full G+D steps (after %d warm-up) on %d of the %d images/GPU, '
+                     'torch CPU fp32, %d threads' % (len(times), min(warmup, it), sample_imgs,
+                                                     cfg['N'], cores),
+              ms_per_step=mean * 1e3)
+
+
+def run_reference(args, cfg):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  steps = max(1, min(args.steps, 3))
+  warm = 1 if args.warmup > 0 else 0
+  sample = min(cfg['N'], 8)
+  r = cpu_reference_arm(cfg, steps, warm, sample, budget_s=120.0)
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
+      'data': 'synthetic',
+      'config': {'workload': '%s_b%d' % (args.workload, cfg['N']),
+                 'note': 'CPU port of the reference step on host cores; bounded sample'},
+      'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+      'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+
+def run_b200(args, cfg):
+  import torch.distributed as dist
+  from sg2im_b200 import _lib, ops
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  from sg2im_b200.synth import make_vocab, synth_batch
+  from sg2im_b200.train_step import TrainStep
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  assert torch.cuda.is_available(), 'bench.py --impl b200 needs a GPU (no CPU fallback)'
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  _lib.load()
+  assert _lib.load().sg2im_device_ok() == 1
+
+  vocab = make_vocab(cfg['num_objs'], cfg['num_preds'])
+  torch.manual_seed(0)                                   # identical init on every rank
+  with contextlib.redirect_stdout(io.StringIO()):
+    model = Sg2ImModel(vocab, **model_kwargs(cfg)).to(dev)
+    d_img = PatchDiscriminator(D_ARCH, padding='valid').to(dev)
+    d_obj = AcCropDiscriminator(vocab, D_ARCH, 'batch', 'leakyrelu-0.2', 32, 'valid').to(dev)
+  step = TrainStep(model, d_obj, d_img)
+  torch.manual_seed(1234 + rank)                         # noise stream differs per rank
+
+  n_pool = 4
+  host = [[t.pin_memory() for t in synth_batch(seed=1000 * rank + i, **cfg)]
+          for i in range(n_pool)]
+  resident = [[t.to(dev) for t in b] for b in host]
+  h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+  def sync_all():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def timed(n_steps, from_host, profile=None):
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.PROFILE = profile
+    l0 = _lib.launches
+    e0.record()
+    last = None
+    for i in range(n_steps):
+      if from_host:
+        batch = [t.to(dev, non_blocking=True) for t in host[i % n_pool]]
+      else:
+        batch = resident[i % n_pool]
+      last, _ = step.step(batch)                         # reads the losses back (D2H)
+    e1.record()
+    sync_all()
+    ops.PROFILE = None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms, _lib.launches - l0, last
+
+  timed(args.warmup, False)                              # warm-up (untimed)
+  sampler = ClockSampler(local)
+  sampler.start()
+  prof = []
+  ms, launches, last = timed(args.steps, False, profile=prof)
+  clocks = sampler.finish()
+  e2e = None
+  if not args.no_e2e:
+    ms_e, _, last_e = timed(args.steps, True)
+    e2e = {'value': cfg['N'] * world * args.steps / (ms_e / 1e3), 'unit': UNIT,
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 * len(last_e),
+           'ms_per_step': ms_e / args.steps}
+
+  # ---- roofline of the dominant kernel family (conv implicit GEMM), live events
+  pk = peaks()
+  fam = {}
+  for name, flops, a, b in prof:
+    t = a.elapsed_time(b)
+    f = fam.setdefault(name, [0.0, 0.0, 0])
+    f[0] += flops; f[1] += t; f[2] += 1
+  roof = None
+  if fam:
+    conv_ms = sum(v[1] for v in fam.values())
+    conv_fl = sum(v[0] for v in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1][1])
+    ach = conv_fl / (conv_ms * 1e-3) / 1e12
+    roof = {'bound': 'tensor', 'kernel': 'conv implicit GEMM (fwd+dgrad+wgrad)',
+            'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf'],
+            'traffic': None, 'peak_source': pk['src'],
+            'share_of_step': conv_ms / ms,
+            'launches_per_step': sum(v[2] for v in fam.values()) / args.steps,
+            'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / args.steps,
+                              'launches_per_step': v[2] / args.steps} for k, v in fam.items()},
+            'top': top[0], 'math': ops.CONV_MATH}
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    r = cpu_reference_arm(cfg, steps=2, warmup=1, sample_imgs=min(cfg['N'], 8))
+    cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+
+  if rank == 0:
+    line = {
+        'metric': METRIC, 'value': cfg['N'] * world * args.steps / (ms / 1e3), 'unit': UNIT,
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': ops.CONV_MATH, 'data': 'synthetic',
+        'config': {'workload': '%s_b%d' % (args.workload, cfg['N']),
+                   'objs_per_gpu': int(resident[0][1].numel()),
+                   'triples_per_gpu': int(resident[0][-3].size(0)),
+                   'image_size': list(cfg['image_size']), 'global_batch': cfg['N'] * world,
+                   'parallelism': 'dp%d' % world,
+                   'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
+                         'no explicit flush'},
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
+        'cpu_baseline': cpu, 'last_losses': last,
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse()
+  from sg2im_b200.synth import CONFIGS
+  cfg = dict(CONFIGS[args.workload])
+  if args.batch:
+    cfg['N'] = args.batch
+  if args.impl == 'reference':
+    run_reference(args, cfg)
+  else:
+    run_b200(args, cfg)
+
+
+if __name__ == '__main__':
+  main()

@@ -37,6 +37,28 @@ def _count(n=1):
   _lib.launches += n
 
 
+# bench.py sets PROFILE to a list to time the conv kernels with CUDA events on
+# the launching stream: entries (kernel family, algorithmic flops, start, end)
+PROFILE = None
+CONV_MATH = 'fp32'          # arithmetic of the convolution path ('fp32' FFMA | 'tf32' tcgen05)
+
+
+class _prof(object):
+  def __init__(self, name, flops):
+    self.name, self.flops = name, flops
+
+  def __enter__(self):
+    if PROFILE is not None:
+      self.a = torch.cuda.Event(enable_timing=True)
+      self.b = torch.cuda.Event(enable_timing=True)
+      self.a.record()
+
+  def __exit__(self, *exc):
+    if PROFILE is not None:
+      self.b.record()
+      PROFILE.append((self.name, self.flops, self.a, self.b))
+
+
 # --------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # --------------------------------------------------------------------------
@@ -91,9 +113,11 @@ def conv_igemm(mode, x, w_packed, bias, KH, KW, S, P, out_hw, Cout, act=0, slope
   if out is None:
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
   cstride = out.size(3)
-  _call('sg2im_conv_igemm', mode, _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(w_packed),
-        _p(bias), KH, KW, S, P, Hout, Wout, Cout, int(act), float(slope), _p(out), cstride,
-        out_coff, _stream())
+  pix = N * Hout * Wout if mode == 0 else N * Hin * Win
+  with _prof('conv_fwd' if mode == 0 else 'conv_dgrad', 2.0 * pix * Cin * Cout * KH * KW):
+    _call('sg2im_conv_igemm', mode, _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(w_packed),
+          _p(bias), KH, KW, S, P, Hout, Wout, Cout, int(act), float(slope), _p(out), cstride,
+          out_coff, _stream())
   _count()
   return out
 
@@ -106,8 +130,9 @@ def conv_wgrad(x, dy, KH, KW, S, P):
   _, Hout, Wout, Cout = dy.shape
   sn, sh, sw, sc = x.stride()
   dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
-  _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
-        Hout, Wout, Cout, _p(dw), _stream())
+  with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW):
+    _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
+          Hout, Wout, Cout, _p(dw), _stream())
   _count()
   return dw
 

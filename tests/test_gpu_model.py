@@ -168,8 +168,8 @@ def test_generator_gradients_vs_oracle():
     if rg is None:
       assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
       continue
-    if rg.abs().max() < 1e-6:          # conv biases feeding BN: true gradient is 0
-      continue
+    if '.net.0.bias' in k or '.net.3.bias' in k:
+      continue      # conv bias feeding a train-mode BN: the true gradient is 0, both sides hold rounding noise
     e = rel_err(p.grad, rg)
     worst = max(worst, e)
     assert e < TOL, (k, e)
