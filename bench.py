@@ -37,6 +37,8 @@ def parse():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='vg128')
   ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: config)')
+  ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'],
+                  help='convolution arithmetic: tcgen05 TF32 (default) or exact-fp32 FFMA')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   return ap.parse_args()
@@ -201,6 +203,7 @@ def run_b200(args, cfg):
     dist.init_process_group('nccl', device_id=dev)
   _lib.load()
   assert _lib.load().sg2im_device_ok() == 1
+  ops.set_conv_math(args.math)
 
   vocab = make_vocab(cfg['num_objs'], cfg['num_preds'])
   torch.manual_seed(0)                                   # identical init on every rank

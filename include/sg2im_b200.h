@@ -87,6 +87,25 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
                      float* y, int64_t y_cstride, int64_t y_coff,
                      sg2im_stream_t stream);
 
+/* Tensor-core path (tcgen05.mma kind::tf32, TMA-staged NHWC tiles, TMEM
+ * accumulators): stride-1 convolution / Linear, TF32 multiply, fp32 accumulate.
+ *   y[n,oy,ox,co] = act(b[co] + sum_{ky,kx,ci} x[n,oy-P+ky,ox-P+kx,ci] *
+ *                                               w_tc[ky*KW+kx][co][ci])
+ * x is NHWC with pixel stride x_cstride floats (first Cin channels used);
+ * w_tc is packed [KH*KW][Cout][Cin].  The data gradient of a stride-1 conv is
+ * the same call with spatially flipped, channel-transposed weights and
+ * P' = K-1-P.  sg2im_conv_tc_supported() returns 1 when the shape tiles
+ * (S == 1, Cin % 4 == 0, Cout % 64 == 0, output width 1/2/4/8 or a multiple of
+ * 16, 128-pixel tiles); otherwise sg2im_conv_tc returns -2 and the caller uses
+ * sg2im_conv_igemm. */
+int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                            int64_t x_cstride, int KH, int KW, int S, int P,
+                            int64_t Cout, int64_t y_cstride, int64_t y_coff);
+int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
+                  int64_t Cin, const float* w_tc, const float* bias, int KH, int KW, int P,
+                  int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
+                  int64_t y_coff, sg2im_stream_t stream);
+
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
  * reduction over pixels is split across CTAs and combined with fp32 atomics). */

@@ -1,0 +1,435 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution, stride 1, NHWC fp32
+// in HBM, TF32 multiply / fp32 accumulate in TMEM.
+//
+//   D[pixel, co] = sum_{tap, ci} X[pixel + tap - P, ci] * Wt[tap][co][ci]
+//
+// * A operand: one TMA 4-D box (32 channels x BW x BH x BI pixels = 128 rows of
+//   128 B) per (tap, 32-channel block), fetched at the tap-shifted coordinate;
+//   the TMA unit zero-fills out-of-bounds pixels, which IS the conv padding, and
+//   lays rows out in the 128B-swizzled K-major form tcgen05 reads directly.
+// * B operand: weights pre-packed [tap][Cout][Cin] (K-major), 3-D TMA box.
+// * tcgen05.mma kind::tf32, M=128 x N=BN x K=8, one elected thread; fp32 data is
+//   consumed as-is (the tensor core ignores the low 13 mantissa bits), so there
+//   is no conversion pass and activations stay fp32 in HBM.
+// * Accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile
+//   i overlaps the MMAs of tile i+1; persistent CTAs, static tile striding.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
+//   epilogue (tcgen05.ld -> bias/LeakyReLU -> 128-bit global stores into the
+//   destination channel slice).
+// Replaces cuDNN's conv behind nn.Conv2d (sg2im/crn.py:41-45,80-82;
+// model.py:100) for the shapes that dominate the step.
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int KB_BYTES = 128;                 // 32 fp32 channels per k-block row
+constexpr int A_STAGE_BYTES = TILE_M * KB_BYTES;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  int N, Hout, Wout, Cin, Cout;
+  int KH, KW, P;
+  int BW, BH, BI;                  // tile = BI images x BH rows x BW cols (=128 pixels)
+  int tiles_w, tiles_h, tiles_n, n_tiles;   // n_tiles over Cout
+  int num_kb;                      // taps * ceil(Cin/32)
+  int cblocks;                     // ceil(Cin/32)
+  const float* bias;
+  int act; float slope;
+  float* y; long long y_cstride, y_coff;
+};
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();          // ~4 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled smem matrix descriptor (rows of 128 B, 8-row groups
+// 1024 B apart): start>>4 | LBO=1 (ignored for swizzled K-major) | SBO=1024>>4 |
+// version 1 (Blackwell) | layout SWIZZLE_128B (=2).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * KB_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;                     // 128 / 256 / 512
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256;
+  // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
+  // N>>3 at bit 17, M>>4 at bit 24
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                          // STAGES x 16 KB
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;              // STAGES x BN*128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                                       // [STAGES]
+  uint64_t* empty = bars + C::STAGES;                          // [STAGES]
+  uint64_t* tfull = bars + 2 * C::STAGES;                      // [2]
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n-tile over Cout fastest, so CTAs running together share A in L2)
+  auto decode = [&](int tile, int& nt, int& n0, int& y0, int& x0) {
+    nt = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    int tw = m % p.tiles_w; m /= p.tiles_w;
+    int th = m % p.tiles_h; m /= p.tiles_h;
+    n0 = m * p.BI; y0 = th * p.BH; x0 = tw * p.BW;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int nt, n0, y0, x0;
+        decode(tile, nt, n0, y0, x0);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          int ky = tap / p.KW, kx = tap - ky * p.KW;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], C::STAGE_BYTES);
+          tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full[s], cb * 32, x0 + kx - p.P,
+                      y0 + ky - p.P, n0);
+          tma_load_3d(sB + s * C::B_STAGE_BYTES, &tmB, &full[s], cb * 32, nt * BN, tap);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_desc(smem_u32(sA + s * A_STAGE_BYTES));
+          const uint64_t bdesc = make_desc(smem_u32(sB + s * C::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                      // 4 x (K=8 tf32 = 32 B) per 128 B row
+            tc_mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (kb | k) ? 1u : 0u);
+          tc_commit(&empty[s]);                            // frees the smem stage when the MMAs retire
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tfull[acc]);                            // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+    const int r = q * 32 + lane;                           // tile row = TMEM lane
+    const int img = r / (p.BH * p.BW);
+    const int hh = (r / p.BW) % p.BH, ww = r % p.BW;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int nt, n0, y0, x0;
+      decode(tile, nt, n0, y0, x0);
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const int n = n0 + img;
+      const bool valid = n < p.N;
+      float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
+                    p.y_coff + (long long)nt * BN;
+      const float* brow = p.bias ? p.bias + nt * BN : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tc_ld32(taddr + ch * 32, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (brow) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(brow + ch * 32 + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (p.act) {
+              o.x = leaky(o.x, p.slope); o.y = leaky(o.y, p.slope);
+              o.z = leaky(o.z, p.slope); o.w = leaky(o.w, p.slope);
+            }
+            *reinterpret_cast<float4*>(yrow + ch * 32 + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------- host side ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      sg2im_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  int grid = total < num_sms() ? total : num_sms();
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  return 0;
+}
+
+}  // namespace
+
+// Tile geometry for an output of Hout x Wout; returns false if it does not tile.
+static bool tc_geometry(long long Hout, long long Wout, int& BW, int& BH, int& BI) {
+  if (Wout >= 16) { if (Wout % 16) return false; BW = 16; }
+  else { if (Wout != 1 && Wout != 2 && Wout != 4 && Wout != 8) return false; BW = (int)Wout; }
+  int rem = TILE_M / BW;
+  if (Hout >= rem) { if (Hout % rem) return false; BH = rem; }
+  else { if (rem % Hout) return false; BH = (int)Hout; }
+  BI = rem / BH;
+  return true;
+}
+
+extern "C" int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                                       int64_t x_cstride, int KH, int KW, int S, int P,
+                                       int64_t Cout, int64_t y_cstride, int64_t y_coff) {
+  if (S != 1 || KH < 1 || KW < 1 || KH * KW > 64) return 0;
+  int64_t Hout = Hin + 2 * P - KH + 1, Wout = Win + 2 * P - KW + 1;
+  if (Hout < 1 || Wout < 1) return 0;
+  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 64) return 0;
+  if (y_cstride % 4 || y_coff % 4) return 0;
+  if (N > (1 << 24) || Hin > 32768 || Win > 32768) return 0;
+  int BW, BH, BI;
+  return tc_geometry(Hout, Wout, BW, BH, BI) ? 1 : 0;
+}
+
+extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                             int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
+                             int KH, int KW, int P, int64_t Cout, int act, float slope, float* y,
+                             int64_t y_cstride, int64_t y_coff, sg2im_stream_t stream) {
+  SG_ARG(x && w_tc && y);
+  if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Cout, y_cstride,
+                               y_coff)) {
+    sg2im_set_error("sg2im_conv_tc: unsupported shape (use sg2im_conv_igemm)");
+    return -2;
+  }
+  SG_ARG(aligned16(x) && aligned16(w_tc) && aligned16(y) && (!bias || aligned16(bias)));
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sg2im_set_error("sg2im_conv_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
+
+  TcParams p;
+  p.N = (int)N; p.Hout = (int)(Hin + 2 * P - KH + 1); p.Wout = (int)(Win + 2 * P - KW + 1);
+  p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
+  tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
+  p.tiles_w = p.Wout / p.BW; p.tiles_h = p.Hout / p.BH; p.tiles_n = (int)ceil_div64(N, p.BI);
+  int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // keep >= ~1 wave of tiles: small spatial problems prefer narrower N tiles
+  long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  while (BN > 64 && m_tiles * (Cout / BN) < num_sms()) BN >>= 1;
+  p.n_tiles = (int)(Cout / BN);
+  p.cblocks = (int)ceil_div64(Cin, 32);
+  p.num_kb = KH * KW * p.cblocks;
+  p.bias = bias; p.act = act; p.slope = slope;
+  p.y = y; p.y_cstride = y_cstride; p.y_coff = y_coff;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)Win * x_cstride * 4,
+                          (cuuint64_t)Hin * Win * x_cstride * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode A failed (%d)", (int)r); return -4; }
+  }
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(KH * KW)};
+    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_tc), gdim,
+                     gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode B failed (%d)", (int)r); return -4; }
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc = 0;
+  if (BN == 256) rc = launch<256>(tmA, tmB, p, st);
+  else if (BN == 128) rc = launch<128>(tmA, tmB, p, st);
+  else rc = launch<64>(tmA, tmB, p, st);
+  if (rc) return rc;
+  SG_LAUNCH_OK();
+  return 0;
+}

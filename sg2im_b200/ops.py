@@ -122,6 +122,72 @@ def conv_igemm(mode, x, w_packed, bias, KH, KW, S, P, out_hw, Cout, act=0, slope
   return out
 
 
+def set_conv_math(mode):
+  """'fp32': every convolution / Linear on the exact-fp32 FFMA kernels.
+  'tf32': stride-1 convolutions and Linears whose shape tiles run on the
+  tcgen05 tensor-core kernel (TF32 multiply, fp32 accumulate — the arithmetic
+  cuDNN uses for the reference under torch's default allow_tf32); everything
+  else stays on the FFMA kernels."""
+  global CONV_MATH
+  if mode not in ('fp32', 'tf32'):
+    raise ValueError("conv math must be 'fp32' or 'tf32'")
+  CONV_MATH = mode
+
+
+def _pixel_stride(x):
+  """Pixel stride (floats) if x is an NHWC channel-prefix view of a dense
+  buffer, else None."""
+  N, H, W, C = x.shape
+  if x.is_contiguous():
+    return C
+  if x.stride(3) != 1:
+    return None
+  cs = x.stride(2) if W > 1 else (x.stride(1) if H > 1 else x.stride(0))
+  ok = ((W == 1 or x.stride(2) == cs) and (H == 1 or x.stride(1) == W * cs)
+        and (N == 1 or x.stride(0) == H * W * cs) and cs >= C)
+  return cs if ok else None
+
+
+def conv_tc_ok(x, KH, KW, S, P, Cout, y_cstride=None, y_coff=0):
+  if CONV_MATH != 'tf32' or S != 1:
+    return False
+  cs = _pixel_stride(x)
+  if cs is None or x.data_ptr() % 16:
+    return False
+  N, H, W, C = x.shape
+  return bool(_lib.load().sg2im_conv_tc_supported(
+      N, H, W, C, cs, KH, KW, S, P, Cout, Cout if y_cstride is None else y_cstride, y_coff))
+
+
+def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
+            tag='conv_fwd_tc'):
+  """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
+  w_tc packed [KH*KW][Cout][Cin]."""
+  N, H, W, C = x.shape
+  cs = _pixel_stride(x)
+  Hout, Wout = H + 2 * P - KH + 1, W + 2 * P - KW + 1
+  if out is None:
+    out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW):
+    _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Cout, int(act),
+          float(slope), _p(out), out.size(3), out_coff, _stream())
+  _count()
+  return out
+
+
+def pack_tc_fwd(weight):
+  """OIHW -> [KH*KW][Cout][Cin]."""
+  Co, Ci, KH, KW = weight.shape
+  return weight.permute(2, 3, 0, 1).reshape(KH * KW, Co, Ci).contiguous()
+
+
+def pack_tc_dgrad(weight):
+  """OIHW -> [KH*KW (flipped)][Cin][Cout]: the data gradient of a stride-1 conv
+  is a conv of dY with the spatially flipped, channel-transposed filter."""
+  Co, Ci, KH, KW = weight.shape
+  return weight.flip(2, 3).permute(2, 3, 1, 0).reshape(KH * KW, Ci, Co).contiguous()
+
+
 def conv_wgrad(x, dy, KH, KW, S, P):
   """Returns dw packed (KH*KW*Cin, Cout)."""
   _chk(x)
@@ -263,8 +329,11 @@ class Conv(torch.autograd.Function):
     w_used = weight if Ci == Ci_w else weight[:, :Ci]
     Hout = conv_out_size(x.size(1), KH, stride, pad)
     Wout = conv_out_size(x.size(2), KW, stride, pad)
-    y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
-                   act, slope)
+    if conv_tc_ok(x, KH, KW, stride, pad, Co):
+      y = conv_tc(x, pack_tc_fwd(w_used), bias, KH, KW, pad, Co, act, slope)
+    else:
+      y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
+                     act, slope)
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.has_bias = bias is not None
@@ -281,8 +350,13 @@ class Conv(torch.autograd.Function):
     dx = dw = db = None
     if ctx.needs_input_grad[0]:
       w_used = weight if Ci == Ci_w else weight[:, :Ci]
-      dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
-                      (x.size(1), x.size(2)), Ci)
+      pad_t = KH - 1 - pad
+      if (KH == KW and pad_t >= 0 and dy.size(1) + 2 * pad_t - KH + 1 == x.size(1)
+          and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci)):
+        dx = conv_tc(dy, pack_tc_dgrad(w_used), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc')
+      else:
+        dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
+                        (x.size(1), x.size(2)), Ci)
     if ctx.needs_input_grad[1]:
       dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
       dw = unpack_conv_wgrad(dwp, (Co, Ci, KH, KW))

@@ -266,3 +266,90 @@ def test_crop_golden_and_backward():
   assert rel_err(out, g['crops']) < TOL
   out.backward(gy.to(d))
   assert rel_err(fd.grad, fr.grad) < TOL
+
+
+# ---------------------------------------------------------------------------
+# tcgen05 tensor-core convolution (TF32 multiply, fp32 accumulate)
+# ---------------------------------------------------------------------------
+
+def _tf32_exact(t):
+  """Zero the 13 low mantissa bits: values the tensor core consumes exactly."""
+  return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+TC_CASES = [
+    # N, H, W, Cin, Cout, K, P
+    (2, 16, 16, 32, 64, 3, 1),
+    (3, 8, 8, 160, 256, 3, 1),         # 8x8: two images per tile, ragged image count
+    (2, 32, 32, 96, 128, 3, 1),
+    (1, 64, 64, 64, 64, 3, 1),
+    (5, 4, 4, 128, 128, 3, 1),         # mask head sizes
+    (7, 2, 2, 128, 128, 3, 1),
+    (2, 16, 16, 288, 512, 3, 1),       # two N tiles
+    (448, 1, 1, 384, 512, 1, 0),       # Linear as a 1x1 convolution over rows
+    (70, 1, 1, 512, 1152, 1, 0),
+    (2, 16, 16, 64, 64, 1, 0),
+    (2, 32, 16, 36, 64, 3, 1),         # Cin not a multiple of 32 (TMA zero fill), H != W
+]
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P', TC_CASES)
+def test_conv_tc_forward_dgrad(N, H, W, Ci, Co, K, P):
+  """With TF32-exact operands every product is exact in fp32, so the tensor
+  core result must agree with the fp32 reference to accumulation-order level
+  (1e-5); with arbitrary fp32 operands the TF32 operand truncation bounds the
+  error at ~2^-10 relative per product (tolerance 3e-3 stated here)."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(Ci + 7 * Co + H)
+  x = torch.randn(N, Ci, H, W, generator=g)
+  w = torch.randn(Co, Ci, K, K, generator=g) * 0.1
+  b = torch.randn(Co, generator=g)
+  gy = torch.randn(N, Co, H + 2 * P - K + 1, W + 2 * P - K + 1, generator=g)
+  ops.set_conv_math('tf32')
+  try:
+    for exact in (True, False):
+      xx, ww, gg = (_tf32_exact(x), _tf32_exact(w), _tf32_exact(gy)) if exact else (x, w, gy)
+      xr, wr, br = xx.clone().requires_grad_(True), ww.clone().requires_grad_(True), b.clone().requires_grad_(True)
+      yr = F.leaky_relu(F.conv2d(xr, wr, br, padding=P), 0.2)
+      yr.backward(gg)
+      xd = xx.to(dev()).permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+      wd = ww.to(dev()).requires_grad_(True)
+      bd = b.to(dev()).requires_grad_(True)
+      assert ops.conv_tc_ok(xd, K, K, 1, P, Co), 'shape should take the tensor-core path'
+      y = ops.conv2d(xd, wd, bd, 1, P, 1, 0.2)
+      tol = 2e-5 if exact else 3e-3
+      assert rel_err(y.permute(0, 3, 1, 2), yr) < tol, ('fwd', exact)
+      y.backward(gg.to(dev()).permute(0, 2, 3, 1))
+      # dgrad runs on the tensor core as well (dY * act' is not TF32-exact -> looser)
+      assert rel_err(xd.grad.permute(0, 3, 1, 2), xr.grad) < 3e-3, ('dgrad', exact)
+      assert rel_err(wd.grad, wr.grad) < 3e-3
+      assert rel_err(bd.grad, br.grad) < 1e-4
+  finally:
+    ops.set_conv_math('fp32')
+
+
+def test_conv_tc_dgrad_exact_and_slice_output():
+  """dgrad with TF32-exact dY (no activation in between) is exact to 1e-5; and
+  the kernel writes into a channel slice of a wider buffer."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(3)
+  N, H, W, Ci, Co, K, P = 2, 16, 16, 64, 128, 3, 1
+  x = _tf32_exact(torch.randn(N, Ci, H, W, generator=g))
+  w = _tf32_exact(torch.randn(Co, Ci, K, K, generator=g) * 0.1)
+  gy = _tf32_exact(torch.randn(N, Co, H, W, generator=g))
+  xr = x.clone().requires_grad_(True)
+  yr = F.conv2d(xr, w, None, padding=P)
+  yr.backward(gy)
+  ops.set_conv_math('tf32')
+  try:
+    xd = x.to(dev()).permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    y = ops.conv2d(xd, w.to(dev()), None, 1, P)
+    assert rel_err(y.permute(0, 3, 1, 2), yr) < 2e-5
+    y.backward(gy.to(dev()).permute(0, 2, 3, 1))
+    assert rel_err(xd.grad.permute(0, 3, 1, 2), xr.grad) < 2e-5
+    buf = torch.zeros(N, H, W, 32 + Co + 8, device=dev())
+    ops.conv_tc(xd.detach(), ops.pack_tc_fwd(w.to(dev())), None, K, K, P, Co, out=buf, out_coff=32)
+    assert rel_err(buf[..., 32:32 + Co].permute(0, 3, 1, 2), yr) < 2e-5
+    assert float(buf[..., :32].abs().max()) == 0 and float(buf[..., 32 + Co:].abs().max()) == 0
+  finally:
+    ops.set_conv_math('fp32')
