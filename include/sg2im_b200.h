@@ -95,7 +95,7 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
  * w_tc is packed [KH*KW][Cout][Cin].  The data gradient of a stride-1 conv is
  * the same call with spatially flipped, channel-transposed weights and
  * P' = K-1-P.  sg2im_conv_tc_supported() returns 1 when the shape tiles
- * (S == 1, Cin % 4 == 0, Cout % 64 == 0, output width 1/2/4/8 or a multiple of
+ * (S == 1, Cin % 4 == 0, Cout % 32 == 0, output width 1/2/4/8 or a multiple of
  * 16, 128-pixel tiles); otherwise sg2im_conv_tc returns -2 and the caller uses
  * sg2im_conv_igemm. */
 int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,

@@ -262,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (nt * BN + ch * 32 >= p.Cout) break;              // partial last N tile (warp-uniform)
         float v[32];
         tc_ld32(taddr + ch * 32, v);
         if (valid) {
@@ -366,7 +367,7 @@ extern "C" int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int6
   if (S != 1 || KH < 1 || KW < 1 || KH * KW > 64) return 0;
   int64_t Hout = Hin + 2 * P - KH + 1, Wout = Win + 2 * P - KW + 1;
   if (Hout < 1 || Wout < 1) return 0;
-  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 64) return 0;
+  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 32) return 0;
   if (y_cstride % 4 || y_coff % 4) return 0;
   if (N > (1 << 24) || Hin > 32768 || Win > 32768) return 0;
   int BW, BH, BI;
@@ -392,11 +393,17 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
   tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
   p.tiles_w = p.Wout / p.BW; p.tiles_h = p.Hout / p.BH; p.tiles_n = (int)ceil_div64(N, p.BI);
-  int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
-  // keep >= ~1 wave of tiles: small spatial problems prefer narrower N tiles
+  // N tile: the widest of 256/128/64 whose padding waste (last tile may be
+  // partial: TMA zero-fills the missing weight rows, the epilogue skips the
+  // columns) stays under 1/8, then narrowed while there is less than a wave.
+  int BN = 64;
+  for (int cand = 256; cand >= 64; cand >>= 1) {
+    long long padded = ceil_div64(Cout, cand) * cand;
+    if ((padded - Cout) * 8 <= padded) { BN = cand; break; }
+  }
   long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-  while (BN > 64 && m_tiles * (Cout / BN) < num_sms()) BN >>= 1;
-  p.n_tiles = (int)(Cout / BN);
+  while (BN > 64 && m_tiles * ceil_div64(Cout, BN) < num_sms()) BN >>= 1;
+  p.n_tiles = (int)ceil_div64(Cout, BN);
   p.cblocks = (int)ceil_div64(Cin, 32);
   p.num_kb = KH * KW * p.cblocks;
   p.bias = bias; p.act = act; p.slope = slope;
