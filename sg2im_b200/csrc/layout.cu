@@ -45,29 +45,127 @@ __device__ __forceinline__ float grid_coord(int i, int size, float b0, float inv
   return (lin - b0) * inv * 2.f - 1.f;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256)
+// Forward, one CTA per (image, row, 32-pixel segment):
+//   phase 1  S[o][p] for the image's objects (chunks of LF_OBJ) and the 32 pixels
+//            — one bilinear mask sample per (object, pixel), not per channel;
+//   phase 2  out[p][c..c+3] += S[o][p] * vec[o][c..c+3] with vec staged in smem;
+//            threads walk (pixel, channel-group) so each pixel row is written as
+//            one contiguous run of float4 (coalesced 16 B stores).
+// Noise channels are transposed NCHW -> NHWC through a padded smem tile.
+constexpr int LF_PIX = 32, LF_OBJ = 16, LF_THREADS = 256, LF_MAXACC = 8;
+
+__global__ void __launch_bounds__(LF_THREADS)
 layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxes,
                   const float* __restrict__ masks, int M, const int32_t* __restrict__ img_ptr,
-                  const int32_t* __restrict__ img_ent, int64_t N, int64_t D, int64_t H, int64_t W,
-                  int align, const float* __restrict__ noise, int64_t noise_c, int64_t nsn,
+                  const int32_t* __restrict__ img_ent, int64_t N, int D, int H, int W,
+                  int align, const float* __restrict__ noise, int noise_c, int64_t nsn,
                   int64_t nsc, int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs) {
-  int64_t G = (D + (noise ? noise_c : 0)) / VEC;
+  extern __shared__ __align__(16) float lsm[];
+  float* sS = lsm;                               // [LF_OBJ][LF_PIX]
+  float* sV = lsm + LF_OBJ * LF_PIX;             // [LF_OBJ][D]
+  const int segs = (W + LF_PIX - 1) / LF_PIX;
+  int bid = blockIdx.x;
+  const int seg = bid % segs; bid /= segs;
+  const int h = bid % H;
+  const int64_t n = bid / H;
+  const int w0 = seg * LF_PIX;
+  const int npx = W - w0 < LF_PIX ? W - w0 : LF_PIX;
+  const int t = threadIdx.x;
+  const int G = D >> 2;                           // float4 groups per pixel (D % 4 == 0)
+  const int nout = npx * G;
+  float4 acc[LF_MAXACC];
+#pragma unroll
+  for (int k = 0; k < LF_MAXACC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int32_t ob = img_ptr[n], oe = img_ptr[n + 1];
+  for (int32_t c0 = ob; c0 < oe; c0 += LF_OBJ) {
+    const int nobj = oe - c0 < LF_OBJ ? oe - c0 : LF_OBJ;
+    __syncthreads();                              // previous chunk fully consumed
+    for (int i = t; i < nobj * LF_PIX; i += LF_THREADS) {
+      int ol = i / LF_PIX, pp = i - ol * LF_PIX;
+      float sv = 0.f;
+      if (pp < npx) {
+        int o = img_ent[c0 + ol] >> 1;
+        float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
+        float gx = grid_coord(w0 + pp, W, bx.x, 1.f / (bx.z - bx.x));
+        float gy = grid_coord(h, H, bx.y, 1.f / (bx.w - bx.y));
+        int xl, yl; float wx, wy;
+        sv = sample_mask(masks ? masks + (int64_t)o * M * M : nullptr, M, align, gx, gy, xl, yl,
+                         wx, wy);
+      }
+      sS[i] = sv;
+    }
+    for (int i = t; i < nobj * G; i += LF_THREADS) {
+      int ol = i / G, g = i - ol * G;
+      int o = img_ent[c0 + ol] >> 1;
+      reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(vecs + (int64_t)o * D + g * 4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LF_MAXACC; ++k) {
+      int idx = t + k * LF_THREADS;
+      if (idx < nout) {
+        int pp = idx / G, g = idx - pp * G;
+        float4 a = acc[k];
+        for (int ol = 0; ol < nobj; ++ol) {
+          float sv = sS[ol * LF_PIX + pp];
+          if (sv != 0.f) {
+            float4 v = reinterpret_cast<const float4*>(sV)[ol * G + g];
+            a.x += v.x * sv; a.y += v.y * sv; a.z += v.z * sv; a.w += v.w * sv;
+          }
+        }
+        acc[k] = a;
+      }
+    }
+  }
+  float* orow = out + ((n * H + h) * (int64_t)W + w0) * ocs;
+#pragma unroll
+  for (int k = 0; k < LF_MAXACC; ++k) {
+    int idx = t + k * LF_THREADS;
+    if (idx < nout) {
+      int pp = idx / G, g = idx - pp * G;
+      *reinterpret_cast<float4*>(orow + (int64_t)pp * ocs + g * 4) = acc[k];
+    }
+  }
+  if (noise) {
+    // coalesced read along w (NCHW), padded smem transpose, contiguous write per pixel
+    float* sN = lsm;                              // reuse: [LF_PIX][33] per 32-channel slab
+    for (int cb = 0; cb < noise_c; cb += 32) {
+      __syncthreads();
+      for (int i = t; i < 32 * LF_PIX; i += LF_THREADS) {
+        int c = i / LF_PIX, pp = i - c * LF_PIX;
+        if (cb + c < noise_c && pp < npx)
+          sN[pp * 33 + c] = noise[n * nsn + (int64_t)(cb + c) * nsc + (int64_t)h * nsh + (int64_t)(w0 + pp) * nsw];
+      }
+      __syncthreads();
+      for (int i = t; i < 32 * LF_PIX; i += LF_THREADS) {
+        int pp = i / 32, c = i - pp * 32;
+        if (cb + c < noise_c && pp < npx) orow[(int64_t)pp * ocs + D + cb + c] = sN[pp * 33 + c];
+      }
+    }
+  }
+}
+
+// Generic scalar fallback (D % 4 != 0): one thread per output element.
+__global__ void __launch_bounds__(256)
+layout_fwd_scalar_kernel(const float* __restrict__ vecs, const float* __restrict__ boxes,
+                         const float* __restrict__ masks, int M,
+                         const int32_t* __restrict__ img_ptr, const int32_t* __restrict__ img_ent,
+                         int64_t N, int64_t D, int64_t H, int64_t W, int align,
+                         const float* __restrict__ noise, int64_t noise_c, int64_t nsn, int64_t nsc,
+                         int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs) {
+  int64_t G = D + (noise ? noise_c : 0);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * H * W * G) return;
-  int64_t g = i % G;
+  int64_t c = i % G;
   int64_t pix = i / G;
   int w = (int)(pix % W);
   int64_t t = pix / W;
   int h = (int)(t % H);
   int64_t n = t / H;
-  int64_t c = g * VEC;
-  float acc[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  float acc = 0.f;
   if (c < D) {
-    int32_t b = img_ptr[n], e = img_ptr[n + 1];
-    for (int32_t k = b; k < e; ++k) {
+    for (int32_t k = img_ptr[n]; k < img_ptr[n + 1]; ++k) {
       int o = img_ent[k] >> 1;
       float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
       float gx = grid_coord(w, (int)W, bx.x, 1.f / (bx.z - bx.x));
@@ -75,25 +173,12 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxe
       int xl, yl; float wx, wy;
       float s = sample_mask(masks ? masks + (int64_t)o * M * M : nullptr, M, align, gx, gy, xl, yl,
                             wx, wy);
-      if (s != 0.f) {
-        const float* v = vecs + (int64_t)o * D + c;
-        if (VEC == 4) {
-          float4 vv = *reinterpret_cast<const float4*>(v);
-          acc[0] += vv.x * s; acc[1] += vv.y * s; acc[2] += vv.z * s; acc[3] += vv.w * s;
-        } else {
-          acc[0] += v[0] * s;
-        }
-      }
+      if (s != 0.f) acc += vecs[(int64_t)o * D + c] * s;
     }
   } else {
-    int64_t nc = c - D;
-    const float* np = noise + n * nsn + (int64_t)h * nsh + (int64_t)w * nsw;
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = np[(nc + j) * nsc];
+    acc = noise[n * nsn + (c - D) * nsc + (int64_t)h * nsh + (int64_t)w * nsw];
   }
-  float* op = out + pix * ocs + c;
-  if (VEC == 4) *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  else op[0] = acc[0];
+  out[pix * ocs + c] = acc;
 }
 
 // One CTA per (object, band of rows).  Each warp owns pixels of the band that
@@ -193,19 +278,25 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
   int64_t ctot = D + (noise ? noise_c : 0);
   SG_ARG(out_cstride >= ctot);
   SG_ARG(aligned16(boxes));
-  bool vec = (D % 4 == 0) && (ctot % 4 == 0) && (out_cstride % 4 == 0) && aligned16(vecs) &&
-             aligned16(out);
-  int64_t total = N * H * W * (ctot / (vec ? 4 : 1));
-  unsigned grid = (unsigned)ceil_div64(total, 256);
+  bool vec = (D % 4 == 0) && (out_cstride % 4 == 0) && aligned16(vecs) && aligned16(out) &&
+             (D / 4) * LF_PIX <= LF_MAXACC * LF_THREADS;
   cudaStream_t st = as_stream(stream);
-  if (vec)
-    layout_fwd_kernel<4><<<grid, 256, 0, st>>>(vecs, boxes, masks, (int)M, img_row_ptr, img_entries,
-                                               N, D, H, W, align_corners, noise, noise_c, nsn, nsc,
-                                               nsh, nsw, out, out_cstride);
-  else
-    layout_fwd_kernel<1><<<grid, 256, 0, st>>>(vecs, boxes, masks, (int)M, img_row_ptr, img_entries,
-                                               N, D, H, W, align_corners, noise, noise_c, nsn, nsc,
-                                               nsh, nsw, out, out_cstride);
+  if (vec) {
+    int segs = (int)ceil_div64(W, LF_PIX);
+    size_t smem = (size_t)(LF_OBJ * LF_PIX + LF_OBJ * D) * sizeof(float);
+    size_t need_noise = (size_t)LF_PIX * 33 * sizeof(float);
+    if (smem < need_noise) smem = need_noise;
+    unsigned grid = (unsigned)(N * H * segs);
+    layout_fwd_kernel<<<grid, LF_THREADS, smem, st>>>(vecs, boxes, masks, (int)M, img_row_ptr,
+                                                      img_entries, N, (int)D, (int)H, (int)W,
+                                                      align_corners, noise, (int)noise_c, nsn, nsc,
+                                                      nsh, nsw, out, out_cstride);
+  } else {
+    int64_t total = N * H * W * ctot;
+    layout_fwd_scalar_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+        vecs, boxes, masks, (int)M, img_row_ptr, img_entries, N, D, H, W, align_corners, noise,
+        noise_c, nsn, nsc, nsh, nsw, out, out_cstride);
+  }
   SG_LAUNCH_OK();
   return 0;
 }

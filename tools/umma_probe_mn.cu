@@ -76,10 +76,10 @@ probe(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorM
     if (threadIdx.x == 0) {
       uint32_t a_addr = smem_u32(sA) + cs.a_row * 128;
       uint32_t b_addr = smem_u32(sB) + cs.b_row * 128;
-      uint64_t atom = (uint64_t)((KROWS * 128) >> 4), grp = 64ull;
+      uint64_t atom = (uint64_t)((KROWS * 128) >> 4), grp = 32ull;   // K groups of 4 rows = 512 B
       uint64_t lbo = cs.swap_lbo_sbo ? grp : atom, sbo = cs.swap_lbo_sbo ? atom : grp;
-      uint64_t adesc = (uint64_t)((a_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
-      uint64_t bdesc = (uint64_t)((b_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+      uint64_t adesc = (uint64_t)((a_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (1ull << 61);   // layout SWIZZLE_128B_BASE32B
+      uint64_t bdesc = (uint64_t)((b_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (1ull << 61);   // layout SWIZZLE_128B_BASE32B
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                    ::"r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(0u) : "memory");
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
@@ -135,10 +135,10 @@ int main() {
   CUtensorMap tmA, tmB;
   {
     cuuint64_t gd[2] = {128, KROWS}; cuuint64_t gs[1] = {128 * 4}; cuuint32_t box[2] = {32, KROWS}; cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r) { printf("encode A %d\n", (int)r); return 1; }
     cuuint64_t gd2[2] = {BN, KROWS}; cuuint64_t gs2[1] = {BN * 4};
-    r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dB, gd2, gs2, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dB, gd2, gs2, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r) { printf("encode B %d\n", (int)r); return 1; }
   }
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
@@ -158,7 +158,7 @@ int main() {
         if (fabs(ref) > maxref) maxref = fabs(ref);
       }
     printf("MN-major  A rows %2d..  B rows %2d..  %s : max abs err %.3e (max |ref| %.2f)  %s\n", cs.a_row, cs.b_row,
-           cs.swap_lbo_sbo ? "LBO=1024,SBO=atom" : "LBO=atom,SBO=1024", maxerr, maxref, maxerr < 1e-3 ? "MATCH" : "differs");
+           cs.swap_lbo_sbo ? "LBO=512,SBO=atom" : "LBO=atom,SBO=512", maxerr, maxref, maxerr < 1e-3 ? "MATCH" : "differs");
   }
   return 0;
 }
