@@ -115,6 +115,20 @@ int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int6
                      int64_t Hout, int64_t Wout, int64_t Cout,
                      float* dw, sg2im_stream_t stream);
 
+/* Tensor-core weight gradient of a stride-1 'same' convolution or a Linear
+ * (tcgen05.mma kind::tf32, MN-major operands straight from NHWC, one smem halo
+ * tile serves all taps): dw[(ky*KW+kx)*Cin + ci][co] += sum_pix
+ * x[pix+tap-P, ci] * dy[pix, co]; dw zero-initialised by the caller (partial
+ * tiles are combined with vector atomics).  Supported when S == 1, K <= 3,
+ * Cin % 4 == 0, Cout % 32 == 0 and (K == 1: N*H*W % 32 == 0; K > 1: W % 8 == 0,
+ * H % 4 == 0, output size == input size); else -2 -> use sg2im_conv_wgrad. */
+int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                                  int64_t x_cstride, int KH, int KW, int S, int P,
+                                  int64_t Cout);
+int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
+                        int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Cout,
+                        float* dw, sg2im_stream_t stream);
+
 /* out[c] = sum_m x[m, c]  (bias gradient), fp64 accumulation; out zeroed by
  * the call. */
 int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out,

@@ -1,0 +1,334 @@
+// tcgen05 weight gradient of a stride-1 convolution (NHWC fp32 in HBM, TF32
+// multiply, fp32 accumulate in TMEM):
+//
+//   dW[tap][ci][co] += sum_pix X[pix + tap - P, ci] * dY[pix, co]
+//
+// GEMM view per tap: D[ci (M=128), co (N=BN)] over K = pixels.  Both operands
+// are "MN-major" exactly as NHWC stores them (a pixel row holds 32 consecutive
+// channels = one 128-byte swizzle row), so TMA boxes land in the layout
+// tcgen05 consumes (SWIZZLE_128B_ATOM_32B <-> UMMA layout SWIZZLE_128B_BASE32B,
+// the only MN-major layout for 32-bit operands) and no transpose ever runs.
+//
+// * Per pipeline stage one 8 x RH pixel tile: dY tile (32 px rows per 32-channel
+//   atom) and ONE X halo tile ((RH+KH-1) x (8+KW-1) pixels).  Every tap's A
+//   operand is the same halo tile read at a row-shifted start address
+//   ((h+ky)*(8+KW-1)+kx rows; tcgen05 swizzles on absolute smem address bits,
+//   verified by tools/umma_probe_mn.cu), so X is fetched once, not KH*KW times.
+// * Up to 512/BN taps accumulate side by side in TMEM (one [128 x BN] fp32
+//   block each); more taps = more passes over the pixel range.
+// * Work item = (ci tile, co tile, tap pass, pixel split); persistent CTAs; the
+//   epilogue adds the partial tile into dW with vector atomics (dW zeroed by
+//   the caller).
+// Replaces cuDNN's backward-filter behind nn.Conv2d / nn.Linear
+// (sg2im/crn.py:41-45,80-82; model.py:100; layers.py:221).
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int A_ATOM_BYTES = 8192;          // halo tile of one 32-channel atom, padded to 1 KB
+constexpr int B_ATOM_BYTES = 4096;          // 32 pixel rows x 128 B
+constexpr int A_STAGE = 4 * A_ATOM_BYTES;   // M = 128 channels = 4 atoms
+
+struct WgParams {
+  int Cin, Cout, KH, KW, P, taps;
+  int RH, pitch;                 // tile rows, halo row pitch (8 + KW - 1) in pixels
+  int tiles_w, tiles_h, total_ptiles;
+  int ci_tiles, co_tiles, passes, T, splits, per_split;
+  int a_bytes, b_atom_rows;      // bytes of one A atom box, pixel rows of a B atom (=8*RH)
+  float* dw;
+};
+
+// MN-major, SWIZZLE_128B_BASE32B descriptor: LBO = byte stride between 32-channel
+// atoms, SBO = 512 B (4 pixel rows), version 1, layout type 1.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+template <int BN>
+struct WCfg {
+  static constexpr int B_STAGE = (BN / 32) * B_ATOM_BYTES;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 5);
+  static constexpr int SMEM_BYTES = STAGES * STAGE + 1024 + 256;
+  // D=F32, A=B=TF32, both MN-major (bits 15,16), N>>3, M>>4
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                     const WgParams p) {
+  using C = WCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDY)) : "memory");
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& ci0, int& co0, int& pass, int& t0, int& t1) {
+    int ci = item % p.ci_tiles; item /= p.ci_tiles;
+    int co = item % p.co_tiles; item /= p.co_tiles;
+    pass = item % p.passes;
+    int split = item / p.passes;
+    ci0 = ci * 128; co0 = co * BN;
+    t0 = split * p.per_split;
+    t1 = t0 + p.per_split < p.total_ptiles ? t0 + p.per_split : p.total_ptiles;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int ci0, co0, pass, t0, t1;
+        decode(item, ci0, co0, pass, t0, t1);
+        int na = (p.Cin - ci0 + 31) / 32; if (na > 4) na = 4;
+        int nb = (p.Cout - co0 + 31) / 32; if (nb > BN / 32) nb = BN / 32;
+        const uint32_t bytes = (uint32_t)(na * p.a_bytes + nb * B_ATOM_BYTES);
+        for (int pt = t0; pt < t1; ++pt) {
+          int tw = pt % p.tiles_w;
+          int r = pt / p.tiles_w;
+          int th = r % p.tiles_h;
+          int n = r / p.tiles_h;
+          int x0 = tw * 8, y0 = th * p.RH;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], bytes);
+          uint8_t* sa = smem + s * C::STAGE;
+          uint8_t* sb = sa + A_STAGE;
+          for (int a = 0; a < na; ++a)
+            tma_load_4d(sa + a * A_ATOM_BYTES, &tmX, &full[s], ci0 + a * 32, x0 - p.P, y0 - p.P, n);
+          for (int b = 0; b < nb; ++b)
+            tma_load_4d(sb + b * B_ATOM_BYTES, &tmDY, &full[s], co0 + b * 32, x0, y0, n);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int ci0, co0, pass, t0, t1;
+        decode(item, ci0, co0, pass, t0, t1);
+        mbar_wait(tempty, acc_ph ^ 1);
+        tc_fence_after();
+        for (int pt = t0; pt < t1; ++pt) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE);
+          const uint32_t sb = sa + A_STAGE;
+          for (int tl = 0; tl < p.T; ++tl) {
+            int tap = pass * p.T + tl;
+            if (tap >= p.taps) break;
+            int ky = tap / p.KW, kx = tap - ky * p.KW;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(tl * BN);
+            for (int h = 0; h < p.RH; ++h) {
+              uint64_t adesc = make_desc_mn(sa + (uint32_t)(((h + ky) * p.pitch + kx) * 128), A_ATOM_BYTES);
+              uint64_t bdesc = make_desc_mn(sb + (uint32_t)(h * 1024), B_ATOM_BYTES);
+              tc_mma_tf32(d_tmem, adesc, bdesc, C::IDESC, (pt > t0 || h > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[s]);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(tfull);
+        acc_ph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> vector atomics into dW =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                           // ci row within the tile
+    uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int ci0, co0, pass, t0, t1;
+      decode(item, ci0, co0, pass, t0, t1);
+      mbar_wait(tfull, acc_ph);
+      tc_fence_after();
+      const int ci = ci0 + row;
+      const bool valid = ci < p.Cin;
+      for (int tl = 0; tl < p.T; ++tl) {
+        int tap = pass * p.T + tl;
+        if (tap >= p.taps) break;
+        float* drow = p.dw + ((long long)tap * p.Cin + ci) * p.Cout + co0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * BN);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          if (co0 + ch * 32 >= p.Cout) break;
+          float v[32];
+          tc_ld32(taddr + ch * 32, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(drow + ch * 32 + j),
+                        make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      acc_ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                 : "memory");
+  }
+}
+
+template <int BN>
+int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p, cudaStream_t st) {
+  using C = WCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      sg2im_set_error("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  int items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
+  int grid = items < num_sms() ? items : num_sms();
+  conv_wgrad_tc_kernel<BN><<<grid, WG_THREADS, C::SMEM_BYTES, st>>>(tmX, tmDY, p);
+  return 0;
+}
+
+// View (N,H,W) as the tiling grid (n, h, w) the kernel walks: a 1x1 "conv"
+// (Linear) has no spatial structure, so its pixels are re-viewed as rows of 8.
+bool wg_geometry(int64_t N, int64_t H, int64_t W, int KH, int KW, int64_t& gN, int64_t& gH,
+                 int64_t& gW, int& RH) {
+  if (KH == 1 && KW == 1) {
+    int64_t npix = N * H * W;
+    if (npix % 32) return false;
+    gN = 1; gH = npix / 8; gW = 8; RH = 4;
+    return gH < (1ll << 31);
+  }
+  if (W % 8 || H % 4) return false;
+  gN = N; gH = H; gW = W; RH = 4;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
+                                             int64_t x_cstride, int KH, int KW, int S, int P,
+                                             int64_t Cout) {
+  if (S != 1 || KH < 1 || KW < 1 || KH > 3 || KW > 3) return 0;
+  int64_t Hout = Hin + 2 * P - KH + 1, Wout = Win + 2 * P - KW + 1;
+  if (Hout < 1 || Wout < 1) return 0;
+  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 32) return 0;
+  if (KH == 1 && KW == 1 && (P != 0)) return 0;
+  if ((KH > 1 || KW > 1) && (Hout != Hin || Wout != Win)) return 0;   // 'same' convs only
+  int64_t gN, gH, gW; int RH;
+  return wg_geometry(N, Hout, Wout, KH, KW, gN, gH, gW, RH) ? 1 : 0;
+}
+
+extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                                   int64_t Win, int64_t Cin, const float* dy, int KH, int KW,
+                                   int P, int64_t Cout, float* dw, sg2im_stream_t stream) {
+  SG_ARG(x && dy && dw);
+  if (!sg2im_conv_wgrad_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Cout)) {
+    sg2im_set_error("sg2im_conv_wgrad_tc: unsupported shape (use sg2im_conv_wgrad)");
+    return -2;
+  }
+  SG_ARG(aligned16(x) && aligned16(dy) && aligned16(dw));
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sg2im_set_error("sg2im_conv_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
+  int64_t gN, gH, gW; int RH;
+  wg_geometry(N, Hin + 2 * P - KH + 1, Win + 2 * P - KW + 1, KH, KW, gN, gH, gW, RH);
+
+  WgParams p;
+  p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P; p.taps = KH * KW;
+  p.RH = RH; p.pitch = 8 + KW - 1;
+  p.tiles_w = (int)(gW / 8); p.tiles_h = (int)(gH / RH);
+  p.total_ptiles = (int)(gN * p.tiles_h * p.tiles_w);
+  int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  p.ci_tiles = (int)ceil_div64(Cin, 128);
+  p.co_tiles = (int)ceil_div64(Cout, BN);
+  p.passes = (int)ceil_div64((int64_t)p.taps * BN, 512);
+  p.T = (int)ceil_div64(p.taps, p.passes);
+  p.passes = (int)ceil_div64(p.taps, p.T);
+  long long base = (long long)p.ci_tiles * p.co_tiles * p.passes;
+  long long want = ceil_div64(3ll * num_sms(), base);
+  long long max_split = p.total_ptiles / 8 > 0 ? p.total_ptiles / 8 : 1;
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  p.per_split = (int)ceil_div64(p.total_ptiles, want);
+  p.splits = (int)ceil_div64(p.total_ptiles, p.per_split);
+  p.a_bytes = (RH + KH - 1) * p.pitch * 128;
+  p.b_atom_rows = 8 * RH;
+  p.dw = dw;
+
+  CUtensorMap tmX, tmDY;
+  {
+    // x viewed as (C, gW, gH, gN) pixels-of-8 rows; for K>1 this is the real NHWC tensor
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gN};
+    cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)gW * x_cstride * 4,
+                          (cuuint64_t)gH * gW * x_cstride * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.pitch, (cuuint32_t)(RH + KH - 1), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_wgrad_tc: encode X failed (%d)", (int)r); return -4; }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gN};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)gW * Cout * 4,
+                          (cuuint64_t)gH * gW * Cout * 4};
+    cuuint32_t box[4] = {32, 8, (cuuint32_t)RH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmDY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_wgrad_tc: encode dY failed (%d)", (int)r); return -4; }
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (BN == 256) rc = launch_wg<256>(tmX, tmDY, p, st);
+  else if (BN == 128) rc = launch_wg<128>(tmX, tmDY, p, st);
+  else rc = launch_wg<64>(tmX, tmDY, p, st);
+  if (rc) return rc;
+  SG_LAUNCH_OK();
+  return 0;
+}

@@ -196,6 +196,15 @@ def conv_wgrad(x, dy, KH, KW, S, P):
   _, Hout, Wout, Cout = dy.shape
   sn, sh, sw, sc = x.stride()
   dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
+  if CONV_MATH == 'tf32' and S == 1:
+    cs = _pixel_stride(x)
+    if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
+        N, Hin, Win, Cin, cs, KH, KW, S, P, Cout)):
+      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW):
+        _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Cout,
+              _p(dw), _stream())
+      _count()
+      return dw
   with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW):
     _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
           Hout, Wout, Cout, _p(dw), _stream())

@@ -174,3 +174,30 @@ def test_generator_gradients_vs_oracle():
     worst = max(worst, e)
     assert e < TOL, (k, e)
   print('worst param-grad rel err', worst)
+
+
+def test_training_iteration_tf32_tensor_core_path():
+  """Same two reference iterations with the convolutions on the tcgen05 TF32
+  kernels (forward, dgrad, wgrad).  TF32 operand truncation (2^-10 relative,
+  what cuDNN's default allow_tf32 path also does for the reference on GPU)
+  moves the losses by ~1e-3 relative; tolerance stated: 1e-2."""
+  from sg2im_b200 import ops
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  m, d_obj, d_img = _build_all(g)
+  ops.set_conv_math('tf32')
+  try:
+    step = TrainStep(m, d_obj, d_img)
+    batch = [t.to(dev()) for t in g['batch']]
+    kw = g['kwargs']
+    worst = 0.0
+    for it, seed in enumerate(g['noise_seeds']):
+      noise = _noise(seed, batch[0].size(0), kw['layout_noise_dim'], kw['image_size']).to(dev())
+      losses, _ = step.step(batch, noise=noise)
+      for k, v in g['losses'][it].items():
+        e = abs(losses[k] - v) / max(1.0, abs(v))
+        worst = max(worst, e)
+        assert e <= 1e-2, (it, k, losses[k], v)
+    print('worst loss deviation under tf32', worst)
+  finally:
+    ops.set_conv_math('fp32')

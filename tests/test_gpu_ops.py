@@ -292,6 +292,9 @@ TC_CASES = [
     (2, 32, 16, 36, 64, 3, 1),         # Cin not a multiple of 32 (TMA zero fill), H != W
     (2, 16, 16, 288, 64, 3, 1),        # dgrad output width 288 = 256 + 32: partial last N tile
     (1, 32, 32, 160, 96, 3, 1),        # Cout 96: partial N tile in the forward
+    (4, 64, 64, 64, 64, 3, 1),         # wgrad: several pixel splits, 5+4 tap passes
+    (1, 128, 128, 288, 64, 3, 1),      # CRN stage-4 conv1 shape (one image)
+    (2, 16, 16, 512, 256, 3, 1),       # wgrad: 4 ci tiles, 2 taps per pass
 ]
 
 
