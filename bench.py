@@ -41,6 +41,7 @@ def parse():
                   help='convolution arithmetic: tcgen05 TF32 (default) or exact-fp32 FFMA')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--shapes-out', default=None, help='write per-shape conv timings (JSON)')
   return ap.parse_args()
 
 
@@ -265,8 +266,11 @@ def run_b200(args, cfg):
   # ---- roofline of the dominant kernel family (conv implicit GEMM), live events
   pk = peaks()
   fam = {}
-  for name, flops, a, b in prof:
+  shapes = {}
+  for name, flops, a, b, shp in prof:
     t = a.elapsed_time(b)
+    sh = shapes.setdefault((name,) + tuple(shp or ()), [0.0, 0.0, 0])
+    sh[0] += flops; sh[1] += t; sh[2] += 1
     f = fam.setdefault(name, [0.0, 0.0, 0])
     f[0] += flops; f[1] += t; f[2] += 1
   roof = None
@@ -283,6 +287,13 @@ def run_b200(args, cfg):
             'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / args.steps,
                               'launches_per_step': v[2] / args.steps} for k, v in fam.items()},
             'top': top[0], 'math': ops.CONV_MATH}
+
+  if args.shapes_out and rank == 0:
+    rows = [{'kernel': k[0], 'shape(N,H,W,Cin,Cout,K,S)': list(k[1:]), 'ms_per_step': v[1] / args.steps,
+             'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'launches_per_step': v[2] / args.steps}
+            for k, v in shapes.items()]
+    rows.sort(key=lambda r: -r['ms_per_step'])
+    json.dump(rows, open(args.shapes_out, 'w'), indent=1)
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -91,20 +91,22 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
  * accumulators): stride-1 convolution / Linear, TF32 multiply, fp32 accumulate.
  *   y[n,oy,ox,co] = act(b[co] + sum_{ky,kx,ci} x[n,oy-P+ky,ox-P+kx,ci] *
  *                                               w_tc[ky*KW+kx][co][ci])
- * x is NHWC with pixel stride x_cstride floats (first Cin channels used);
- * w_tc is packed [KH*KW][Cout][Cin].  The data gradient of a stride-1 conv is
- * the same call with spatially flipped, channel-transposed weights and
- * P' = K-1-P.  sg2im_conv_tc_supported() returns 1 when the shape tiles
- * (S == 1, Cin % 4 == 0, Cout % 32 == 0, output width 1/2/4/8 or a multiple of
- * 16, 128-pixel tiles); otherwise sg2im_conv_tc returns -2 and the caller uses
- * sg2im_conv_igemm. */
+ * for oy < Hout, ox < Wout (Hout/Wout may be smaller than the natural output
+ * size).  x is NHWC with pixel stride x_cstride floats (first Cin channels
+ * used); w_tc is packed [KH*KW][Cout][Cin].  The data gradient of a stride-1
+ * conv is the same call with spatially flipped, channel-transposed weights
+ * and P' = K-1-P.  A KxK stride-2 'valid' conv (the discriminators) is the
+ * same call on the space-to-depth input (sg2im_s2d_fwd) with K/2 taps.
+ * sg2im_conv_tc_supported(): S == 1, Cin % 4 == 0, Cout % 4 == 0, 16-byte
+ * aligned slices; otherwise sg2im_conv_tc returns -2 (use sg2im_conv_igemm). */
 int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
                             int64_t x_cstride, int KH, int KW, int S, int P,
-                            int64_t Cout, int64_t y_cstride, int64_t y_coff);
+                            int64_t Hout, int64_t Wout, int64_t Cout, int64_t y_cstride,
+                            int64_t y_coff);
 int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                   int64_t Cin, const float* w_tc, const float* bias, int KH, int KW, int P,
-                  int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
-                  int64_t y_coff, sg2im_stream_t stream);
+                  int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope, float* y,
+                  int64_t y_cstride, int64_t y_coff, sg2im_stream_t stream);
 
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
@@ -115,19 +117,28 @@ int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int6
                      int64_t Hout, int64_t Wout, int64_t Cout,
                      float* dw, sg2im_stream_t stream);
 
-/* Tensor-core weight gradient of a stride-1 'same' convolution or a Linear
+/* Tensor-core weight gradient of a stride-1 convolution or a Linear
  * (tcgen05.mma kind::tf32, MN-major operands straight from NHWC, one smem halo
  * tile serves all taps): dw[(ky*KW+kx)*Cin + ci][co] += sum_pix
- * x[pix+tap-P, ci] * dy[pix, co]; dw zero-initialised by the caller (partial
- * tiles are combined with vector atomics).  Supported when S == 1, K <= 3,
- * Cin % 4 == 0, Cout % 32 == 0 and (K == 1: N*H*W % 32 == 0; K > 1: W % 8 == 0,
- * H % 4 == 0, output size == input size); else -2 -> use sg2im_conv_wgrad. */
+ * x[pix+tap-P, ci] * dy[pix, co] over the Hout x Wout outputs; dw
+ * zero-initialised by the caller (partial tiles are combined with vector
+ * atomics).  Supported when S == 1, K <= 3, Cin % 4 == 0, Cout % 32 == 0 (and
+ * N*H*W % 32 == 0 for K == 1); else -2 -> use sg2im_conv_wgrad. */
 int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
                                   int64_t x_cstride, int KH, int KW, int S, int P,
-                                  int64_t Cout);
+                                  int64_t Hout, int64_t Wout, int64_t Cout);
 int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
-                        int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Cout,
-                        float* dw, sg2im_stream_t stream);
+                        int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Hout,
+                        int64_t Wout, int64_t Cout, float* dw, sg2im_stream_t stream);
+
+/* Space-to-depth by 2 (and its adjoint): out[n, y/2, x/2, ((y&1)*2+(x&1))*C + c]
+ * = x[n,y,x,c], zero padded to even H, W.  x addressed with element strides.
+ * Turns the discriminators' 4x4 stride-2 'valid' convolutions
+ * (sg2im/layers.py:164-181, scripts/train.py:122-130) into 2x2 stride-1 ones. */
+int sg2im_s2d_fwd(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int64_t sxc,
+                  int64_t N, int64_t H, int64_t W, int64_t C, float* out, sg2im_stream_t stream);
+int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W, int64_t C, float* dx,
+                  sg2im_stream_t stream);
 
 /* out[c] = sum_m x[m, c]  (bias gradient), fp64 accumulation; out zeroed by
  * the call. */

@@ -168,7 +168,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const int n = n0 + img;
-      const bool valid = n < p.N;
+      const bool valid = n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
       float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
                     p.y_coff + (long long)nt * BN;
       const float* brow = p.bias ? p.bias + nt * BN : nullptr;
@@ -181,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
+            if (nt * BN + ch * 32 + j >= p.Cout) break;        // Cout % 4 == 0: whole float4s
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             if (brow) {
               float4 b = __ldg(reinterpret_cast<const float4*>(brow + ch * 32 + j));
@@ -233,37 +234,38 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
 
 }  // namespace
 
-// Tile geometry for an output of Hout x Wout; returns false if it does not tile.
-static bool tc_geometry(long long Hout, long long Wout, int& BW, int& BH, int& BI) {
-  if (Wout >= 16) { if (Wout % 16) return false; BW = 16; }
-  else { if (Wout != 1 && Wout != 2 && Wout != 4 && Wout != 8) return false; BW = (int)Wout; }
+// Tile geometry for an output of Hout x Wout: 128 pixels = BI images x BH rows x
+// BW cols, all powers of two; the last tile in each direction may be partial
+// (TMA reads past the edge are zero-filled or unused, the epilogue masks).
+static void tc_geometry(long long Hout, long long Wout, int& BW, int& BH, int& BI) {
+  BW = Wout > 8 ? 16 : (Wout > 4 ? 8 : (Wout > 2 ? 4 : (Wout > 1 ? 2 : 1)));
   int rem = TILE_M / BW;
-  if (Hout >= rem) { if (Hout % rem) return false; BH = rem; }
-  else { if (rem % Hout) return false; BH = (int)Hout; }
+  BH = 1;
+  while (BH < rem && BH < Hout) BH <<= 1;
   BI = rem / BH;
-  return true;
 }
 
 extern "C" int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
                                        int64_t x_cstride, int KH, int KW, int S, int P,
-                                       int64_t Cout, int64_t y_cstride, int64_t y_coff) {
-  if (S != 1 || KH < 1 || KW < 1 || KH * KW > 64) return 0;
-  int64_t Hout = Hin + 2 * P - KH + 1, Wout = Win + 2 * P - KW + 1;
-  if (Hout < 1 || Wout < 1) return 0;
-  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 32) return 0;
+                                       int64_t Hout, int64_t Wout, int64_t Cout,
+                                       int64_t y_cstride, int64_t y_coff) {
+  if (S != 1 || KH < 1 || KW < 1 || KH * KW > 64 || P < 0) return 0;
+  // any Hout/Wout: reads outside the input are zero-filled by TMA
+  if (Hout < 1 || Wout < 1 || Hout > 65536 || Wout > 65536) return 0;
+  if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 4) return 0;
   if (y_cstride % 4 || y_coff % 4) return 0;
   if (N > (1 << 24) || Hin > 32768 || Win > 32768) return 0;
-  int BW, BH, BI;
-  return tc_geometry(Hout, Wout, BW, BH, BI) ? 1 : 0;
+  return 1;
 }
 
 extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
                              int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
-                             int KH, int KW, int P, int64_t Cout, int act, float slope, float* y,
-                             int64_t y_cstride, int64_t y_coff, sg2im_stream_t stream) {
+                             int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
+                             int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
+                             sg2im_stream_t stream) {
   SG_ARG(x && w_tc && y);
-  if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Cout, y_cstride,
-                               y_coff)) {
+  if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
+                               y_cstride, y_coff)) {
     sg2im_set_error("sg2im_conv_tc: unsupported shape (use sg2im_conv_igemm)");
     return -2;
   }
@@ -272,10 +274,11 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
   if (!enc) { sg2im_set_error("sg2im_conv_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
 
   TcParams p;
-  p.N = (int)N; p.Hout = (int)(Hin + 2 * P - KH + 1); p.Wout = (int)(Win + 2 * P - KW + 1);
+  p.N = (int)N; p.Hout = (int)Hout; p.Wout = (int)Wout;
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
   tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
-  p.tiles_w = p.Wout / p.BW; p.tiles_h = p.Hout / p.BH; p.tiles_n = (int)ceil_div64(N, p.BI);
+  p.tiles_w = (int)ceil_div64(p.Wout, p.BW); p.tiles_h = (int)ceil_div64(p.Hout, p.BH);
+  p.tiles_n = (int)ceil_div64(N, p.BI);
   // N tile: the widest of 256/128/64 whose padding waste (last tile may be
   // partial: TMA zero-fills the missing weight rows, the epilogue skips the
   // columns) stays under 1/8, then narrowed while there is less than a wave.

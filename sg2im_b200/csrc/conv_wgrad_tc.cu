@@ -233,18 +233,20 @@ int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p
   return 0;
 }
 
-// View (N,H,W) as the tiling grid (n, h, w) the kernel walks: a 1x1 "conv"
-// (Linear) has no spatial structure, so its pixels are re-viewed as rows of 8.
-bool wg_geometry(int64_t N, int64_t H, int64_t W, int KH, int KW, int64_t& gN, int64_t& gH,
-                 int64_t& gW, int& RH) {
+// A 1x1 "conv" (Linear) has no spatial structure: its pixels are re-viewed as
+// rows of 8 (needs N*H*W % 32 == 0).  K > 1: the real (N, H, W) grids; partial
+// edge tiles are free because TMA zero-fills dY past the edge.
+struct WgGeom { int64_t xN, xH, xW, yN, yH, yW; };
+
+bool wg_geometry(int64_t N, int64_t Hin, int64_t Win, int64_t Hout, int64_t Wout, int KH, int KW,
+                 WgGeom& g) {
   if (KH == 1 && KW == 1) {
-    int64_t npix = N * H * W;
-    if (npix % 32) return false;
-    gN = 1; gH = npix / 8; gW = 8; RH = 4;
-    return gH < (1ll << 31);
+    int64_t npix = N * Hin * Win;
+    if (npix % 32 || Hout != Hin || Wout != Win) return false;
+    g.xN = g.yN = 1; g.xH = g.yH = npix / 8; g.xW = g.yW = 8;
+    return g.xH < (1ll << 31);
   }
-  if (W % 8 || H % 4) return false;
-  gN = N; gH = H; gW = W; RH = 4;
+  g.xN = g.yN = N; g.xH = Hin; g.xW = Win; g.yH = Hout; g.yW = Wout;
   return true;
 }
 
@@ -252,36 +254,36 @@ bool wg_geometry(int64_t N, int64_t H, int64_t W, int KH, int KW, int64_t& gN, i
 
 extern "C" int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
                                              int64_t x_cstride, int KH, int KW, int S, int P,
-                                             int64_t Cout) {
-  if (S != 1 || KH < 1 || KW < 1 || KH > 3 || KW > 3) return 0;
-  int64_t Hout = Hin + 2 * P - KH + 1, Wout = Win + 2 * P - KW + 1;
-  if (Hout < 1 || Wout < 1) return 0;
+                                             int64_t Hout, int64_t Wout, int64_t Cout) {
+  if (S != 1 || KH < 1 || KW < 1 || KH > 3 || KW > 3 || P < 0) return 0;
+  if (Hout < 1 || Wout < 1 || Hout > Hin + 2 * P - KH + 1 || Wout > Win + 2 * P - KW + 1) return 0;
   if (Cin % 4 || x_cstride % 4 || x_cstride < Cin || Cout % 32) return 0;
   if (KH == 1 && KW == 1 && (P != 0)) return 0;
-  if ((KH > 1 || KW > 1) && (Hout != Hin || Wout != Win)) return 0;   // 'same' convs only
-  int64_t gN, gH, gW; int RH;
-  return wg_geometry(N, Hout, Wout, KH, KW, gN, gH, gW, RH) ? 1 : 0;
+  WgGeom g;
+  return wg_geometry(N, Hin, Win, Hout, Wout, KH, KW, g) ? 1 : 0;
 }
 
 extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
                                    int64_t Win, int64_t Cin, const float* dy, int KH, int KW,
-                                   int P, int64_t Cout, float* dw, sg2im_stream_t stream) {
+                                   int P, int64_t Hout, int64_t Wout, int64_t Cout, float* dw,
+                                   sg2im_stream_t stream) {
   SG_ARG(x && dy && dw);
-  if (!sg2im_conv_wgrad_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Cout)) {
+  if (!sg2im_conv_wgrad_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout)) {
     sg2im_set_error("sg2im_conv_wgrad_tc: unsupported shape (use sg2im_conv_wgrad)");
     return -2;
   }
   SG_ARG(aligned16(x) && aligned16(dy) && aligned16(dw));
   EncodeTiledFn enc = get_encode();
   if (!enc) { sg2im_set_error("sg2im_conv_wgrad_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
-  int64_t gN, gH, gW; int RH;
-  wg_geometry(N, Hin + 2 * P - KH + 1, Win + 2 * P - KW + 1, KH, KW, gN, gH, gW, RH);
+  WgGeom g;
+  wg_geometry(N, Hin, Win, Hout, Wout, KH, KW, g);
+  const int RH = 4;
 
   WgParams p;
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P; p.taps = KH * KW;
   p.RH = RH; p.pitch = 8 + KW - 1;
-  p.tiles_w = (int)(gW / 8); p.tiles_h = (int)(gH / RH);
-  p.total_ptiles = (int)(gN * p.tiles_h * p.tiles_w);
+  p.tiles_w = (int)ceil_div64(g.yW, 8); p.tiles_h = (int)ceil_div64(g.yH, RH);
+  p.total_ptiles = (int)(g.yN * p.tiles_h * p.tiles_w);
   int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
   p.ci_tiles = (int)ceil_div64(Cin, 128);
   p.co_tiles = (int)ceil_div64(Cout, BN);
@@ -302,9 +304,9 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   CUtensorMap tmX, tmDY;
   {
     // x viewed as (C, gW, gH, gN) pixels-of-8 rows; for K>1 this is the real NHWC tensor
-    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gN};
-    cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)gW * x_cstride * 4,
-                          (cuuint64_t)gH * gW * x_cstride * 4};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)g.xW, (cuuint64_t)g.xH, (cuuint64_t)g.xN};
+    cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)g.xW * x_cstride * 4,
+                          (cuuint64_t)g.xH * g.xW * x_cstride * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)p.pitch, (cuuint32_t)(RH + KH - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
@@ -313,9 +315,9 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_wgrad_tc: encode X failed (%d)", (int)r); return -4; }
   }
   {
-    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gN};
-    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)gW * Cout * 4,
-                          (cuuint64_t)gH * gW * Cout * 4};
+    cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)g.yW, (cuuint64_t)g.yH, (cuuint64_t)g.yN};
+    cuuint64_t gstr[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)g.yW * Cout * 4,
+                          (cuuint64_t)g.yH * g.yW * Cout * 4};
     cuuint32_t box[4] = {32, 8, (cuuint32_t)RH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmDY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), gdim, gstr,

@@ -391,3 +391,51 @@ extern "C" int sg2im_act_bwd(const float* dy, const float* y, float slope, int64
   SG_LAUNCH_OK();
   return 0;
 }
+
+// ---------------------------------------------------------- space to depth ---
+namespace {
+__global__ void s2d_fwd_kernel(const float* __restrict__ x, int64_t sxn, int64_t sxh, int64_t sxw,
+                               int64_t sxc, int64_t N, int64_t H, int64_t W, int64_t C,
+                               float* __restrict__ out) {
+  int64_t H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H2 * W2 * 4 * C) return;
+  int64_t c = i % C; int64_t t = i / C;
+  int ph = (int)(t % 4); t /= 4;
+  int64_t x2 = t % W2; t /= W2;
+  int64_t y2 = t % H2; int64_t n = t / H2;
+  int64_t y = 2 * y2 + (ph >> 1), xx = 2 * x2 + (ph & 1);
+  out[i] = (y < H && xx < W) ? x[n * sxn + y * sxh + xx * sxw + c * sxc] : 0.f;
+}
+__global__ void s2d_bwd_kernel(const float* __restrict__ dout, int64_t N, int64_t H, int64_t W,
+                               int64_t C, float* __restrict__ dx) {
+  int64_t H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H * W * C) return;
+  int64_t c = i % C; int64_t t = i / C;
+  int64_t xx = t % W; t /= W;
+  int64_t y = t % H; int64_t n = t / H;
+  int ph = (int)((y & 1) * 2 + (xx & 1));
+  dx[i] = dout[(((n * H2 + y / 2) * W2 + xx / 2) * 4 + ph) * C + c];
+}
+}  // namespace
+
+extern "C" int sg2im_s2d_fwd(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int64_t sxc,
+                             int64_t N, int64_t H, int64_t W, int64_t C, float* out,
+                             sg2im_stream_t stream) {
+  SG_ARG(x && out && N >= 1 && H >= 1 && W >= 1 && C >= 1);
+  int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * 4 * C;
+  s2d_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+      x, sxn, sxh, sxw, sxc, N, H, W, C, out);
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W, int64_t C,
+                             float* dx, sg2im_stream_t stream) {
+  SG_ARG(dout && dx && N >= 1 && H >= 1 && W >= 1 && C >= 1);
+  int64_t total = N * H * W * C;
+  s2d_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
+  SG_LAUNCH_OK();
+  return 0;
+}

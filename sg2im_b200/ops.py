@@ -44,8 +44,8 @@ CONV_MATH = 'fp32'          # arithmetic of the convolution path ('fp32' FFMA | 
 
 
 class _prof(object):
-  def __init__(self, name, flops):
-    self.name, self.flops = name, flops
+  def __init__(self, name, flops, shape=None):
+    self.name, self.flops, self.shape = name, flops, shape
 
   def __enter__(self):
     if PROFILE is not None:
@@ -56,7 +56,7 @@ class _prof(object):
   def __exit__(self, *exc):
     if PROFILE is not None:
       self.b.record()
-      PROFILE.append((self.name, self.flops, self.a, self.b))
+      PROFILE.append((self.name, self.flops, self.a, self.b, self.shape))
 
 
 # --------------------------------------------------------------------------
@@ -114,7 +114,8 @@ def conv_igemm(mode, x, w_packed, bias, KH, KW, S, P, out_hw, Cout, act=0, slope
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
   cstride = out.size(3)
   pix = N * Hout * Wout if mode == 0 else N * Hin * Win
-  with _prof('conv_fwd' if mode == 0 else 'conv_dgrad', 2.0 * pix * Cin * Cout * KH * KW):
+  with _prof('conv_fwd' if mode == 0 else 'conv_dgrad', 2.0 * pix * Cin * Cout * KH * KW,
+             (N, Hin, Win, Cin, Cout, KH, S)):
     _call('sg2im_conv_igemm', mode, _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(w_packed),
           _p(bias), KH, KW, S, P, Hout, Wout, Cout, int(act), float(slope), _p(out), cstride,
           out_coff, _stream())
@@ -148,29 +149,32 @@ def _pixel_stride(x):
   return cs if ok else None
 
 
-def conv_tc_ok(x, KH, KW, S, P, Cout, y_cstride=None, y_coff=0):
+def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
   if CONV_MATH != 'tf32' or S != 1:
     return False
   cs = _pixel_stride(x)
   if cs is None or x.data_ptr() % 16:
     return False
   N, H, W, C = x.shape
+  Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
   return bool(_lib.load().sg2im_conv_tc_supported(
-      N, H, W, C, cs, KH, KW, S, P, Cout, Cout if y_cstride is None else y_cstride, y_coff))
+      N, H, W, C, cs, KH, KW, S, P, Hout, Wout, Cout, Cout if y_cstride is None else y_cstride,
+      y_coff))
 
 
 def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
-            tag='conv_fwd_tc'):
+            tag='conv_fwd_tc', out_hw=None):
   """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
-  w_tc packed [KH*KW][Cout][Cin]."""
+  w_tc packed [KH*KW][Cout][Cin]; out_hw: explicit output size (reads outside
+  the input are zero)."""
   N, H, W, C = x.shape
   cs = _pixel_stride(x)
-  Hout, Wout = H + 2 * P - KH + 1, W + 2 * P - KW + 1
+  Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
   if out is None:
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
-  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW):
-    _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Cout, int(act),
-          float(slope), _p(out), out.size(3), out_coff, _stream())
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
+    _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Hout, Wout,
+          Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _stream())
   _count()
   return out
 
@@ -199,13 +203,15 @@ def conv_wgrad(x, dy, KH, KW, S, P):
   if CONV_MATH == 'tf32' and S == 1:
     cs = _pixel_stride(x)
     if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
-        N, Hin, Win, Cin, cs, KH, KW, S, P, Cout)):
-      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW):
-        _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Cout,
-              _p(dw), _stream())
+        N, Hin, Win, Cin, cs, KH, KW, S, P, Hout, Wout, Cout)):
+      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
+                 (N, Hin, Win, Cin, Cout, KH, S)):
+        _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Hout, Wout,
+              Cout, _p(dw), _stream())
       _count()
       return dw
-  with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW):
+  with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
+             (N, Hin, Win, Cin, Cout, KH, S)):
     _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
           Hout, Wout, Cout, _p(dw), _stream())
   _count()
@@ -330,7 +336,7 @@ class Conv(torch.autograd.Function):
   first stage, whose extra input channel is identically zero)."""
 
   @staticmethod
-  def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch):
+  def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch, out_hw=None):
     _chk(weight, name='weight')
     Co, Ci_w, KH, KW = weight.shape
     Ci = Ci_w if in_ch is None else in_ch
@@ -338,8 +344,12 @@ class Conv(torch.autograd.Function):
     w_used = weight if Ci == Ci_w else weight[:, :Ci]
     Hout = conv_out_size(x.size(1), KH, stride, pad)
     Wout = conv_out_size(x.size(2), KW, stride, pad)
-    if conv_tc_ok(x, KH, KW, stride, pad, Co):
-      y = conv_tc(x, pack_tc_fwd(w_used), bias, KH, KW, pad, Co, act, slope)
+    if out_hw is not None:
+      # cropped output (space-to-depth route of the stride-2 convs): tensor-core only
+      assert out_hw[0] <= Hout and out_hw[1] <= Wout and conv_tc_ok(x, KH, KW, stride, pad, Co, out_hw)
+      Hout, Wout = out_hw
+    if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
+      y = conv_tc(x, pack_tc_fwd(w_used), bias, KH, KW, pad, Co, act, slope, out_hw=(Hout, Wout))
     else:
       y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
                      act, slope)
@@ -360,9 +370,10 @@ class Conv(torch.autograd.Function):
     if ctx.needs_input_grad[0]:
       w_used = weight if Ci == Ci_w else weight[:, :Ci]
       pad_t = KH - 1 - pad
-      if (KH == KW and pad_t >= 0 and dy.size(1) + 2 * pad_t - KH + 1 == x.size(1)
-          and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci)):
-        dx = conv_tc(dy, pack_tc_dgrad(w_used), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc')
+      if (KH == KW and pad_t >= 0 and stride == 1
+          and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
+        dx = conv_tc(dy, pack_tc_dgrad(w_used), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
+                     out_hw=(x.size(1), x.size(2)))
       else:
         dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
                         (x.size(1), x.size(2)), Ci)
@@ -375,10 +386,45 @@ class Conv(torch.autograd.Function):
         dw = full
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = colsum(dy.view(-1, Co))
-    return dx, dw, db, None, None, None, None, None
+    return dx, dw, db, None, None, None, None, None, None
+
+
+class S2D(torch.autograd.Function):
+  """Space-to-depth by 2 with zero padding to even size: (N,H,W,C) ->
+  (N,ceil(H/2),ceil(W/2),4C), channel = ((y&1)*2+(x&1))*C + c."""
+
+  @staticmethod
+  def forward(ctx, x):
+    _chk(x)
+    N, H, W, C = x.shape
+    out = torch.empty(N, (H + 1) // 2, (W + 1) // 2, 4 * C, dtype=torch.float32, device=x.device)
+    sn, sh, sw, sc = x.stride()
+    _call('sg2im_s2d_fwd', _p(x), sn, sh, sw, sc, N, H, W, C, _p(out), _stream())
+    _count()
+    ctx.shape = (N, H, W, C)
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    N, H, W, C = ctx.shape
+    dout = dout.contiguous()
+    dx = torch.empty(N, H, W, C, dtype=torch.float32, device=dout.device)
+    _call('sg2im_s2d_bwd', _p(dout), N, H, W, C, _p(dx), _stream())
+    _count()
+    return dx
 
 
 def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None):
+  if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
+      and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4):
+    # 4x4 stride-2 'valid' conv (the discriminators, scripts/train.py:122-130) ==
+    # 2x2 stride-1 conv on the space-to-depth input: runs on the tensor-core
+    # kernels (forward, dgrad, wgrad) with no strided gathers.
+    Co, C = weight.size(0), weight.size(1)
+    Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
+    xs = S2D.apply(x)
+    w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
+    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo))
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch)
 
 

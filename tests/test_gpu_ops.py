@@ -364,3 +364,43 @@ def test_conv_tc_dgrad_exact_and_slice_output():
     assert float(buf[..., :32].abs().max()) == 0 and float(buf[..., 32 + Co:].abs().max()) == 0
   finally:
     ops.set_conv_math('fp32')
+
+
+S2_CASES = [
+    # N, H, W, Cin, Cout  (4x4 stride-2 'valid' convs of the discriminators)
+    (2, 32, 32, 3, 64),        # first layer on crops: 12 s2d channels
+    (2, 15, 15, 64, 128),      # odd input size: zero-padded s2d, cropped output
+    (3, 6, 6, 128, 256),
+    (2, 63, 63, 64, 128),      # D_img layer 2 geometry
+    (2, 30, 30, 128, 256),
+    (5, 16, 20, 8, 32),        # H != W
+]
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co', S2_CASES)
+def test_conv_stride2_space_to_depth_route(N, H, W, Ci, Co):
+  """4x4/s2 conv == 2x2/s1 conv on the space-to-depth input, on the tensor-core
+  kernels (fwd, dgrad incl. the 12-channel image gradient, wgrad).  TF32-exact
+  operands -> 2e-5; also checks the NCHW-strided image input."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(H * 7 + Ci)
+  x = _tf32_exact(torch.randn(N, Ci, H, W, generator=g))
+  w = _tf32_exact(torch.randn(Co, Ci, 4, 4, generator=g) * 0.1)
+  b = torch.randn(Co, generator=g)
+  xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+  yr = F.conv2d(xr, wr, br, stride=2)
+  gy = _tf32_exact(torch.randn(yr.shape, generator=g))
+  yr.backward(gy)
+  ops.set_conv_math('tf32')
+  try:
+    xd = x.to(dev()).requires_grad_(True)                 # NCHW memory, viewed NHWC
+    wd, bd = w.to(dev()).requires_grad_(True), b.to(dev()).requires_grad_(True)
+    y = ops.conv2d(xd.permute(0, 2, 3, 1), wd, bd, 2, 0)
+    assert y.shape == (N, yr.size(2), yr.size(3), Co)
+    assert rel_err(y.permute(0, 3, 1, 2), yr) < 2e-5
+    y.backward(gy.to(dev()).permute(0, 2, 3, 1))
+    assert rel_err(xd.grad, xr.grad) < 2e-5
+    assert rel_err(wd.grad, wr.grad) < 2e-5
+    assert rel_err(bd.grad, br.grad) < 1e-4
+  finally:
+    ops.set_conv_math('fp32')
