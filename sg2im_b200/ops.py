@@ -416,7 +416,8 @@ class S2D(torch.autograd.Function):
 
 def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None):
   if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
-      and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4):
+      and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4
+      and weight.size(0) % 32 == 0):
     # 4x4 stride-2 'valid' conv (the discriminators, scripts/train.py:122-130) ==
     # 2x2 stride-1 conv on the space-to-depth input: runs on the tensor-core
     # kernels (forward, dgrad, wgrad) with no strided gathers.
