@@ -143,22 +143,32 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int ci0, co0, pass, t0, t1;
         decode(item, ci0, co0, pass, t0, t1);
+        const int tap0 = pass * p.T;
+        const int ntap = (p.taps - tap0) < p.T ? (p.taps - tap0) : p.T;
+        const int ky0 = tap0 / p.KW, kx0 = tap0 - ky0 * p.KW;
+        const uint32_t pitch16 = (uint32_t)p.pitch * 8u;
+        const uint64_t a_hi = make_desc_mn(0, A_ATOM_BYTES), b_hi = make_desc_mn(0, B_ATOM_BYTES);
         mbar_wait(tempty, acc_ph ^ 1);
         tc_fence_after();
         for (int pt = t0; pt < t1; ++pt) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C::STAGE);
-          const uint32_t sb = sa + A_STAGE;
-          for (int tl = 0; tl < p.T; ++tl) {
-            int tap = pass * p.T + tl;
-            if (tap >= p.taps) break;
-            int ky = tap / p.KW, kx = tap - ky * p.KW;
+          // descriptors differ only in the 14-bit start-address field: precomputed
+          // high words + 16-byte-unit offsets keep the single issuing thread ahead
+          // of the tensor pipe (one MMA per 32 cycles at N = 64)
+          const uint32_t sa16 = smem_u32(smem + s * C::STAGE) >> 4;
+          const uint32_t sb16 = sa16 + (A_STAGE >> 4);
+          const uint32_t first = (pt > t0) ? 1u : 0u;
+          int ky = ky0, kx = kx0;
+          for (int tl = 0; tl < ntap; ++tl) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(tl * BN);
-            for (int h = 0; h < p.RH; ++h) {
-              uint64_t adesc = make_desc_mn(sa + (uint32_t)(((h + ky) * p.pitch + kx) * 128), A_ATOM_BYTES);
-              uint64_t bdesc = make_desc_mn(sb + (uint32_t)(h * 1024), B_ATOM_BYTES);
-              tc_mma_tf32(d_tmem, adesc, bdesc, C::IDESC, (pt > t0 || h > 0) ? 1u : 0u);
+            const uint32_t a_tap = sa16 + (uint32_t)(ky * p.pitch + kx) * 8u;   // 128 B rows = 8 x 16 B
+            if (++kx == p.KW) { kx = 0; ++ky; }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {                    // RH == 4
+              uint64_t adesc = a_hi | (uint64_t)((a_tap + (uint32_t)h * pitch16) & 0x3FFF);
+              uint64_t bdesc = b_hi | (uint64_t)((sb16 + (uint32_t)h * 64u) & 0x3FFF);
+              tc_mma_tf32(d_tmem, adesc, bdesc, C::IDESC, (h > 0) ? 1u : first);
             }
           }
           tc_commit(&empty[s]);

@@ -215,9 +215,26 @@ layout_bwd_kernel(const float* __restrict__ dout, int64_t dcs, const float* __re
                   : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   int r1 = r0 + LB_ROWS < (int)H ? r0 + LB_ROWS : (int)H;
-  int npix = (r1 - r0) * (int)W;
+  // conservative pixel bounding box of the object's footprint (the bilinear
+  // support reaches at most one mask texel beyond the box); everything outside
+  // samples only padding and is skipped without touching memory
+  int w_lo = 0, w_hi = (int)W - 1, h_lo = r0, h_hi = r1 - 1;
+  {
+    float ww = bx.z - bx.x, hh = bx.w - bx.y;
+    float mg = 1.f / (float)(M > 1 ? M - 1 : 1);
+    if (ww > 0.f && hh > 0.f) {
+      float a = floorf((bx.x - mg * ww) * (float)(W - 1)) - 1.f, b = ceilf((bx.z + mg * ww) * (float)(W - 1)) + 1.f;
+      float c = floorf((bx.y - mg * hh) * (float)(H - 1)) - 1.f, d = ceilf((bx.w + mg * hh) * (float)(H - 1)) + 1.f;
+      if (a > (float)w_lo) w_lo = (int)fminf(a, (float)W);
+      if (b < (float)w_hi) w_hi = (int)fmaxf(b, -1.f);
+      if (c > (float)h_lo) h_lo = (int)fminf(c, (float)H);
+      if (d < (float)h_hi) h_hi = (int)fmaxf(d, -1.f);
+    }
+  }
+  const int bw = w_hi - w_lo + 1, bh = h_hi - h_lo + 1;
+  int npix = (bw > 0 && bh > 0) ? bw * bh : 0;
   for (int p = warp; p < npix; p += LB_WARPS) {
-    int h = r0 + p / (int)W, w = p % (int)W;
+    int h = h_lo + p / bw, w = w_lo + p % bw;
     float gx = grid_coord(w, (int)W, bx.x, inv_w);
     float gy = grid_coord(h, (int)H, bx.y, inv_h);
     int xl, yl; float wx, wy;

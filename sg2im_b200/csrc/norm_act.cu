@@ -43,11 +43,83 @@ colreduce_kernel(F f, int64_t M, int64_t C, int64_t rows_per_block, double* __re
   }
 }
 
+// float4 variant: thread = 4 consecutive channels, TX channel groups x (256/TX) row
+// lanes per block, 2 rows in flight per thread.  F4::at4(m, c, v0, v1).
+template <class F4>
+__global__ void __launch_bounds__(256)
+colreduce4_kernel(F4 f, int64_t M, int64_t C, int64_t rows_per_block, double* __restrict__ sums,
+                  int nout, int TX) {
+  __shared__ double sh[2][4][256];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
+  int64_t c = ((int64_t)blockIdx.x * TX + tx) * 4;
+  int64_t mb = (int64_t)blockIdx.y * rows_per_block;
+  int64_t me = mb + rows_per_block < M ? mb + rows_per_block : M;
+  double d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0};
+  if (c < C) {
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    int cnt = 0;
+    int64_t m = mb + ty;
+    for (; m + TY < me; m += 2 * TY) {
+      float4 a0, a1, b0, b1;
+      f.at4(m, c, a0, a1);
+      f.at4(m + TY, c, b0, b1);
+      s0.x += a0.x + b0.x; s0.y += a0.y + b0.y; s0.z += a0.z + b0.z; s0.w += a0.w + b0.w;
+      s1.x += a1.x + b1.x; s1.y += a1.y + b1.y; s1.z += a1.z + b1.z; s1.w += a1.w + b1.w;
+      if (++cnt == 16) {
+        d0[0] += s0.x; d0[1] += s0.y; d0[2] += s0.z; d0[3] += s0.w;
+        d1[0] += s1.x; d1[1] += s1.y; d1[2] += s1.z; d1[3] += s1.w;
+        s0 = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s0; cnt = 0;
+      }
+    }
+    if (m < me) {
+      float4 a0, a1;
+      f.at4(m, c, a0, a1);
+      s0.x += a0.x; s0.y += a0.y; s0.z += a0.z; s0.w += a0.w;
+      s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+    }
+    d0[0] += s0.x; d0[1] += s0.y; d0[2] += s0.z; d0[3] += s0.w;
+    d1[0] += s1.x; d1[1] += s1.y; d1[2] += s1.z; d1[3] += s1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sh[0][j][threadIdx.x] = d0[j]; sh[1][j][threadIdx.x] = d1[j]; }
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a = 0, b = 0;
+      for (int y = 0; y < TY; ++y) { a += sh[0][j][y * TX + tx]; b += sh[1][j][y * TX + tx]; }
+      atomicAdd(sums + c + j, a);
+      if (nout > 1) atomicAdd(sums + C + c + j, b);
+    }
+  }
+}
+
+template <class F4>
+int launch_colreduce4(F4 f, int64_t M, int64_t C, double* sums, int nout, cudaStream_t st) {
+  int64_t groups = C / 4;
+  int TX = 1;
+  while (TX < 32 && TX < groups) TX <<= 1;
+  int64_t cblocks = ceil_div64(groups, TX);
+  int TY = 256 / TX;
+  int64_t want = ceil_div64(148 * 8, cblocks);
+  int64_t rpb = ceil_div64(M, want);
+  if (rpb < 4 * TY) rpb = 4 * TY;
+  int64_t rblocks = ceil_div64(M, rpb);
+  if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
+  dim3 grid((unsigned)cblocks, (unsigned)rblocks);
+  colreduce4_kernel<F4><<<grid, 256, 0, st>>>(f, M, C, rpb, sums, nout, TX);
+  return 0;
+}
+
 struct StatsF {
   const float* x; int64_t C;
   __device__ void operator()(int64_t m, int64_t c, float& v0, float& v1) const {
     float v = x[m * C + c];
     v0 = v; v1 = v * v;
+  }
+  __device__ __forceinline__ void at4(int64_t m, int64_t c, float4& v0, float4& v1) const {
+    float4 v = *reinterpret_cast<const float4*>(x + m * C + c);
+    v0 = v; v1 = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
   }
 };
 
@@ -166,6 +238,35 @@ struct ActGrad {
   }
 };
 
+// float4 form of ActGrad::at (C, dcs, dco multiples of 4; 16-byte aligned bases)
+__device__ __forceinline__ float4 actgrad4(const ActGrad& a, int64_t m, int64_t c, float4& xv) {
+  xv = *reinterpret_cast<const float4*>(a.x + m * a.C + c);
+  float4 pre = xv;
+  if (a.scale) {
+    float4 s = *reinterpret_cast<const float4*>(a.scale + c);
+    float4 b = *reinterpret_cast<const float4*>(a.shift + c);
+    pre.x = fmaf(xv.x, s.x, b.x); pre.y = fmaf(xv.y, s.y, b.y);
+    pre.z = fmaf(xv.z, s.z, b.z); pre.w = fmaf(xv.w, s.w, b.w);
+  }
+  float4 g;
+  if (a.up == 1) {
+    g = *reinterpret_cast<const float4*>(a.dy + m * a.dcs + a.dco + c);
+  } else {
+    int64_t xx = m % a.W; int64_t t = m / a.W; int64_t yy = t % a.H; int64_t n = t / a.H;
+    int64_t Wo = a.W * a.up;
+    g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < a.up; ++i)
+      for (int j = 0; j < a.up; ++j) {
+        float4 d = *reinterpret_cast<const float4*>(
+            a.dy + ((n * a.H * a.up + yy * a.up + i) * Wo + xx * a.up + j) * a.dcs + a.dco + c);
+        g.x += d.x; g.y += d.y; g.z += d.z; g.w += d.w;
+      }
+  }
+  g.x *= pre.x > 0.f ? 1.f : a.slope; g.y *= pre.y > 0.f ? 1.f : a.slope;
+  g.z *= pre.z > 0.f ? 1.f : a.slope; g.w *= pre.w > 0.f ? 1.f : a.slope;
+  return g;
+}
+
 struct BwdReduceF {
   ActGrad ag; const float* save; int64_t C;
   __device__ void operator()(int64_t m, int64_t c, float& v0, float& v1) const {
@@ -174,7 +275,46 @@ struct BwdReduceF {
     float xhat = save ? (xv - save[c]) * save[C + c] : xv;
     v0 = g; v1 = g * xhat;
   }
+  __device__ __forceinline__ void at4(int64_t m, int64_t c, float4& v0, float4& v1) const {
+    float4 xv;
+    float4 g = actgrad4(ag, m, c, xv);
+    float4 xh = xv;
+    if (save) {
+      float4 mu = *reinterpret_cast<const float4*>(save + c);
+      float4 is = *reinterpret_cast<const float4*>(save + C + c);
+      xh.x = (xv.x - mu.x) * is.x; xh.y = (xv.y - mu.y) * is.y;
+      xh.z = (xv.z - mu.z) * is.z; xh.w = (xv.w - mu.w) * is.w;
+    }
+    v0 = g; v1 = make_float4(g.x * xh.x, g.y * xh.y, g.z * xh.z, g.w * xh.w);
+  }
 };
+
+__global__ void scale_act_bwd_apply4_kernel(ActGrad ag, const float* __restrict__ save,
+                                            int64_t M, int64_t C, int training,
+                                            const double* __restrict__ sums,
+                                            float* __restrict__ dx) {
+  int64_t cg = C / 4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * cg) return;
+  int64_t m = i / cg, c = (i - m * cg) * 4;
+  float4 xv;
+  float4 g = actgrad4(ag, m, c, xv);
+  float4 sc = ag.scale ? *reinterpret_cast<const float4*>(ag.scale + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float gv[4] = {g.x, g.y, g.z, g.w}, xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sc.x, sc.y, sc.z, sc.w};
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (training && save) {
+      float xhat = (xs[j] - save[c + j]) * save[C + c + j];
+      float mg = (float)(sums[c + j] / (double)M);
+      float mgx = (float)(sums[C + c + j] / (double)M);
+      r[j] = ss[j] * (gv[j] - mg - xhat * mgx);
+    } else {
+      r[j] = ss[j] * gv[j];
+    }
+  }
+  *reinterpret_cast<float4*>(dx + m * C + c) = make_float4(r[0], r[1], r[2], r[3]);
+}
 
 __global__ void scale_act_bwd_apply_kernel(ActGrad ag, const float* __restrict__ save,
                                            int64_t M, int64_t C, int training,
@@ -272,7 +412,8 @@ extern "C" int sg2im_bn_stats(const float* x, int64_t M, int64_t C, double* sums
                               sg2im_stream_t stream) {
   SG_ARG(x && sums && M >= 1 && C >= 1);
   StatsF f{x, C};
-  launch_colreduce(f, M, C, sums, 2, as_stream(stream));
+  if (C % 4 == 0 && aligned16(x)) launch_colreduce4(f, M, C, sums, 2, as_stream(stream));
+  else launch_colreduce(f, M, C, sums, 2, as_stream(stream));
   SG_LAUNCH_OK();
   return 0;
 }
@@ -283,7 +424,8 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
   cudaStream_t st = as_stream(stream);
   zero_doubles<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, C);
   StatsF f{x, C};
-  launch_colreduce(f, M, C, scratch, 1, st);
+  if (C % 4 == 0 && aligned16(x)) launch_colreduce4(f, M, C, scratch, 1, st);
+  else launch_colreduce(f, M, C, scratch, 1, st);
   doubles_to_float<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, out, C);
   SG_LAUNCH_OK();
   return 0;
@@ -327,7 +469,11 @@ extern "C" int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, i
                                           sg2im_stream_t stream) {
   SG_ARG(dy && x && sums && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
   BwdReduceF f{{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up}, save, C};
-  launch_colreduce(f, N * H * W, C, sums, 2, as_stream(stream));
+  bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
+             aligned16(x) && (!scale || (aligned16(scale) && aligned16(shift))) &&
+             (!save || aligned16(save));
+  if (vec) launch_colreduce4(f, N * H * W, C, sums, 2, as_stream(stream));
+  else launch_colreduce(f, N * H * W, C, sums, 2, as_stream(stream));
   SG_LAUNCH_OK();
   return 0;
 }
@@ -343,8 +489,14 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
   cudaStream_t st = as_stream(stream);
   ActGrad ag{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up};
   int64_t M = N * H * W;
-  scale_act_bwd_apply_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(
-      ag, save, M, C, training, sums, dx);
+  bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
+             aligned16(x) && aligned16(dx) && (!scale || (aligned16(scale) && aligned16(shift)));
+  if (vec)
+    scale_act_bwd_apply4_kernel<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, st>>>(
+        ag, save, M, C, training, sums, dx);
+  else
+    scale_act_bwd_apply_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(
+        ag, save, M, C, training, sums, dx);
   if ((dgamma || dbeta) && sums)
     bn_param_grads<<<(unsigned)ceil_div64(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
   SG_LAUNCH_OK();
@@ -407,6 +559,33 @@ __global__ void s2d_fwd_kernel(const float* __restrict__ x, int64_t sxn, int64_t
   int64_t y = 2 * y2 + (ph >> 1), xx = 2 * x2 + (ph & 1);
   out[i] = (y < H && xx < W) ? x[n * sxn + y * sxh + xx * sxw + c * sxc] : 0.f;
 }
+// float4 variants (C % 4 == 0, unit channel stride)
+__global__ void s2d_fwd4_kernel(const float* __restrict__ x, int64_t sxn, int64_t sxh, int64_t sxw,
+                                int64_t N, int64_t H, int64_t W, int64_t C, float* __restrict__ out) {
+  int64_t H2 = (H + 1) / 2, W2 = (W + 1) / 2, cg = C / 4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H2 * W2 * 4 * cg) return;
+  int64_t c = (i % cg) * 4; int64_t t = i / cg;
+  int ph = (int)(t % 4); t /= 4;
+  int64_t x2 = t % W2; t /= W2;
+  int64_t y2 = t % H2; int64_t n = t / H2;
+  int64_t y = 2 * y2 + (ph >> 1), xx = 2 * x2 + (ph & 1);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (y < H && xx < W) v = *reinterpret_cast<const float4*>(x + n * sxn + y * sxh + xx * sxw + c);
+  *reinterpret_cast<float4*>(out + (((n * H2 + y2) * W2 + x2) * 4 + ph) * C + c) = v;
+}
+__global__ void s2d_bwd4_kernel(const float* __restrict__ dout, int64_t N, int64_t H, int64_t W,
+                                int64_t C, float* __restrict__ dx) {
+  int64_t H2 = (H + 1) / 2, W2 = (W + 1) / 2, cg = C / 4;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * H * W * cg) return;
+  int64_t c = (i % cg) * 4; int64_t t = i / cg;
+  int64_t xx = t % W; t /= W;
+  int64_t y = t % H; int64_t n = t / H;
+  int ph = (int)((y & 1) * 2 + (xx & 1));
+  *reinterpret_cast<float4*>(dx + ((n * H + y) * W + xx) * C + c) =
+      *reinterpret_cast<const float4*>(dout + (((n * H2 + y / 2) * W2 + xx / 2) * 4 + ph) * C + c);
+}
 __global__ void s2d_bwd_kernel(const float* __restrict__ dout, int64_t N, int64_t H, int64_t W,
                                int64_t C, float* __restrict__ dx) {
   int64_t H2 = (H + 1) / 2, W2 = (W + 1) / 2;
@@ -425,8 +604,13 @@ extern "C" int sg2im_s2d_fwd(const float* x, int64_t sxn, int64_t sxh, int64_t s
                              sg2im_stream_t stream) {
   SG_ARG(x && out && N >= 1 && H >= 1 && W >= 1 && C >= 1);
   int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * 4 * C;
-  s2d_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
-      x, sxn, sxh, sxw, sxc, N, H, W, C, out);
+  if (sxc == 1 && C % 4 == 0 && sxn % 4 == 0 && sxh % 4 == 0 && sxw % 4 == 0 && aligned16(x) &&
+      aligned16(out))
+    s2d_fwd4_kernel<<<(unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream)>>>(
+        x, sxn, sxh, sxw, N, H, W, C, out);
+  else
+    s2d_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+        x, sxn, sxh, sxw, sxc, N, H, W, C, out);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -435,7 +619,10 @@ extern "C" int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W,
                              float* dx, sg2im_stream_t stream) {
   SG_ARG(dout && dx && N >= 1 && H >= 1 && W >= 1 && C >= 1);
   int64_t total = N * H * W * C;
-  s2d_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
+  if (C % 4 == 0 && aligned16(dout) && aligned16(dx))
+    s2d_bwd4_kernel<<<(unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
+  else
+    s2d_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
   SG_LAUNCH_OK();
   return 0;
 }
