@@ -18,6 +18,7 @@
 //   destination channel slice).
 // Replaces cuDNN's conv behind nn.Conv2d (sg2im/crn.py:41-45,80-82;
 // model.py:100) for the shapes that dominate the step.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace {
@@ -212,6 +213,230 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =============================================================================
+// Halo variant for KxK (K <= 3) stride-1 convs with narrow outputs (N tile 64):
+// the per-tap kernel above re-fetches every activation tile once per tap and
+// every weight tile once per pixel tile, which saturates the L2->SM fabric
+// (~10 TB/s, profiles/r01_prof_conv_tc_fwd.txt) long before the tensor pipe.
+// Here, per 32-channel block,
+//   * ONE TMA box brings the (16+KH-1) x (8+KW-1) pixel halo of an 8x16 tile;
+//     each tap's A operand is that tile at a row-shifted start address with an
+//     8-row-group stride of (8+KW-1) rows (tcgen05 swizzles on absolute smem
+//     address bits; shifted starts and SBO = 1280 B verified by
+//     tools/umma_probe.cu);
+//   * the KH*KW weight tiles are loaded once and reused by T = 4 pixel tiles
+//     whose accumulators sit side by side in TMEM (2 sets x 4 x 64 columns,
+//     so the epilogue of one group overlaps the MMAs of the next).
+// L2->SM bytes per MMA drop ~5x.  Warp roles: 0 = halo (A) producer, 1 = MMA
+// issuer + TMEM owner, 2 = weight (B) producer, 4-7 = epilogue.
+// =============================================================================
+constexpr int H_BN = 64, H_T = 4, H_BW = 8, H_BH = 16;
+constexpr int H_A_SLOT = 23 * 1024;           // 180 rows x 128 B = 23040, padded to 1 KB
+constexpr int H_A_SLOTS = 3;
+constexpr int H_B_TILE = H_BN * KB_BYTES;     // 8 KB
+constexpr int H_MAX_TAPS = 9;
+constexpr int H_THREADS = 256;
+constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512;
+
+struct HaloParams {
+  int N, Hout, Wout, Cin, Cout;
+  int KH, KW, P, taps, pitch;      // pitch = 8 + KW - 1 halo pixels per tile row
+  int tiles_w, tiles_h, ptiles;    // pixel tiles of 8 x 16
+  int groups, n_tiles, cblocks;    // groups of H_T pixel tiles; Cout tiles of 64
+  uint32_t a_bytes;                // bytes of one halo box
+  const float* bias;
+  int act; float slope;
+  float* y; long long y_cstride, y_coff;
+};
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + H_A_SLOTS * H_A_SLOT;                    // [2][taps][8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H_B_TILE);
+  uint64_t* a_full = bars;                    // [3]
+  uint64_t* a_empty = bars + 3;               // [3]
+  uint64_t* b_full = bars + 6;                // [2][9]
+  uint64_t* b_empty = bars + 6 + 18;          // [2][9]
+  uint64_t* tfull = bars + 6 + 36;            // [2]
+  uint64_t* tempty = bars + 6 + 38;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 40);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.groups * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (Cout tile, first pixel tile of the group)
+  auto decode = [&](int item, int& nt, int& pt0) {
+    nt = item % p.n_tiles;
+    pt0 = (item / p.n_tiles) * H_T;
+  };
+  auto tile_xy = [&](int pt, int& n, int& y0, int& x0) {
+    int tw = pt % p.tiles_w; int r = pt / p.tiles_w;
+    int th = r % p.tiles_h; n = r / p.tiles_h;            // n >= N for padding tiles: TMA zero-fills
+    y0 = th * H_BH; x0 = tw * H_BW;
+  };
+
+  if (warp == 0) {
+    // ===================== halo (A) producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int t = 0; t < H_T; ++t) {
+            int n, y0, x0;
+            tile_xy(pt0 + t, n, y0, x0);
+            mbar_wait(&a_empty[s], ph ^ 1);
+            mbar_expect_tx(&a_full[s], p.a_bytes);
+            tma_load_4d(sA + s * H_A_SLOT, &tmA, &a_full[s], cb * 32, x0 - p.P, y0 - p.P, n);
+            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight (B) producer =====================
+    if (lane == 0) {
+      uint32_t bcnt = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
+            mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
+            mbar_expect_tx(fb, H_B_TILE);
+            tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN, tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
+                                 ((uint32_t)(TILE_M >> 4) << 24);
+      // A: K-major SW128, 8-row groups `pitch` rows apart; B: dense K-major SW128
+      const uint64_t a_hi = (1ull << 16) | ((uint64_t)((p.pitch * 128) >> 4) << 32) | (1ull << 46) |
+                            (2ull << 61);
+      const uint64_t b_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      int s = 0; uint32_t ph = 0;
+      uint32_t bcnt = 0;
+      int aset = 0; uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        mbar_wait(&tempty[aset], acc_ph ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int t = 0; t < H_T; ++t) {
+            mbar_wait(&a_full[s], ph);
+            tc_fence_after();
+            const uint32_t a16 = smem_u32(sA + s * H_A_SLOT) >> 4;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
+            int ky = 0, kx = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+              if (t == 0) { mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph); tc_fence_after(); }
+              const uint32_t at = a16 + (uint32_t)(ky * p.pitch + kx) * 8u;
+              const uint32_t bt = smem_u32(sB + (set * H_MAX_TAPS + tap) * H_B_TILE) >> 4;
+              if (++kx == p.KW) { kx = 0; ++ky; }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_tf32(d_tmem, a_hi | (uint64_t)((at + 2 * k) & 0x3FFF),
+                            b_hi | (uint64_t)((bt + 2 * k) & 0x3FFF), IDESC, (cb | tap | k) ? 1u : 0u);
+              if (t == H_T - 1) tc_commit(&b_empty[set * H_MAX_TAPS + tap]);
+            }
+            tc_commit(&a_empty[s]);
+            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+        tc_commit(&tfull[aset]);
+        if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int hh = r >> 3, ww = r & 7;                      // 8-wide x 16-high tile
+    int aset = 0; uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      int nt, pt0;
+      decode(item, nt, pt0);
+      mbar_wait(&tfull[aset], acc_ph);
+      tc_fence_after();
+      const float* brow = p.bias ? p.bias + nt * H_BN : nullptr;
+      for (int t = 0; t < H_T; ++t) {
+        int n, y0, x0;
+        tile_xy(pt0 + t, n, y0, x0);
+        const bool valid = (pt0 + t) < p.ptiles && n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
+        float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
+                      p.y_coff + (long long)nt * H_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((aset * H_T + t) * H_BN);
+#pragma unroll 1
+        for (int ch = 0; ch < H_BN / 32; ++ch) {
+          if (nt * H_BN + ch * 32 >= p.Cout) break;
+          float v[32];
+          tc_ld32(taddr + ch * 32, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nt * H_BN + ch * 32 + j >= p.Cout) break;
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (brow) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(brow + ch * 32 + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (p.act) {
+                o.x = leaky(o.x, p.slope); o.y = leaky(o.y, p.slope);
+                o.z = leaky(o.z, p.slope); o.w = leaky(o.w, p.slope);
+              }
+              *reinterpret_cast<float4*>(yrow + ch * 32 + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[aset]);
+      if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------- host side ---
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
@@ -294,6 +519,59 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
   p.num_kb = KH * KW * p.cblocks;
   p.bias = bias; p.act = act; p.slope = slope;
   p.y = y; p.y_cstride = y_cstride; p.y_coff = y_coff;
+
+  // narrow outputs on real images: halo + weight-stationary kernel
+  if (KH * KW > 1 && KH <= 3 && KW <= 3 && Hout >= H_BH && Wout >= H_BW && BN <= 128 &&
+      getenv("SG2IM_NO_HALO") == nullptr) {
+    HaloParams h;
+    h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
+    h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
+    h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, H_BH);
+    h.ptiles = (int)(N * h.tiles_h * h.tiles_w);
+    h.groups = (int)ceil_div64(h.ptiles, H_T);
+    h.n_tiles = (int)ceil_div64(Cout, H_BN);
+    h.cblocks = (int)ceil_div64(Cin, 32);
+    h.a_bytes = (uint32_t)((H_BH + KH - 1) * h.pitch * 128);
+    h.bias = bias; h.act = act; h.slope = slope;
+    h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
+    CUtensorMap hA, hB;
+    {
+      cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
+      cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)Win * x_cstride * 4,
+                            (cuuint64_t)Hin * Win * x_cstride * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)h.pitch, (cuuint32_t)(H_BH + KH - 1), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&hA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
+    }
+    {
+      cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(KH * KW)};
+      cuuint64_t gstr[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
+      cuuint32_t box[3] = {32, (cuuint32_t)H_BN, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(&hB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_tc), gdim,
+                       gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo B failed (%d)", (int)r); return -4; }
+    }
+    static bool halo_attr = false;
+    if (!halo_attr) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+      if (e != cudaSuccess) {
+        sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
+      halo_attr = true;
+    }
+    int items = h.groups * h.n_tiles;
+    int grid = items < num_sms() ? items : num_sms();
+    conv_tc_halo_kernel<<<grid, H_THREADS, H_SMEM, as_stream(stream)>>>(hA, hB, h);
+    SG_LAUNCH_OK();
+    return 0;
+  }
 
   CUtensorMap tmA, tmB;
   {
