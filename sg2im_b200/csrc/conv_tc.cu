@@ -133,8 +133,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
+      const uint32_t d_hi = 64u | (1u << 14) | (2u << 29);          // SBO 1024 B, v1, SWIZZLE_128B
+      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
+      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
       int s = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -144,15 +148,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint64_t adesc = make_desc(smem_u32(sA + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_desc(smem_u32(sB + s * C::B_STAGE_BYTES));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)                      // 4 x (K=8 tf32 = 32 B) per 128 B row
-            tc_mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, C::IDESC, (kb | k) ? 1u : 0u);
-          tc_commit(&empty[s]);                            // frees the smem stage when the MMAs retire
+          const uint32_t at = sA16 + (uint32_t)s * (A_STAGE_BYTES >> 4);
+          const uint32_t bt = sB16 + (uint32_t)s * (C::B_STAGE_BYTES >> 4);
+          tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
+          tc_commit(&empty[s], leader);                    // frees the smem stage when the MMAs retire
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tfull[acc]);                            // accumulator complete -> epilogue
+        tc_commit(&tfull[acc], leader);                    // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -338,14 +343,18 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
                                  ((uint32_t)(TILE_M >> 4) << 24);
-      // A: K-major SW128, 8-row groups `pitch` rows apart; B: dense K-major SW128
-      const uint64_t a_hi = (1ull << 16) | ((uint64_t)((p.pitch * 128) >> 4) << 32) | (1ull << 46) |
-                            (2ull << 61);
-      const uint64_t b_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      // descriptor words: lo = start>>4 | LBO(=1)<<16, hi = SBO>>4 | version 1<<14 | SWIZZLE_128B<<29
+      // A: 8-row groups `pitch` rows apart (halo rows); B: dense (1024 B)
+      const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t b_hi = 64u | (1u << 14) | (2u << 29);
+      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
+      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
+      const uint32_t row_wrap = (uint32_t)(p.pitch - p.KW) * 8u;     // 16-byte units, row = 128 B
       int s = 0; uint32_t ph = 0;
       uint32_t bcnt = 0;
       int aset = 0; uint32_t acc_ph = 0;
@@ -354,28 +363,31 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
+          uint64_t* bf = &b_full[set * H_MAX_TAPS];
+          uint64_t* be = &b_empty[set * H_MAX_TAPS];
           for (int t = 0; t < H_T; ++t) {
             mbar_wait(&a_full[s], ph);
             tc_fence_after();
-            const uint32_t a16 = smem_u32(sA + s * H_A_SLOT) >> 4;
+            uint32_t at = sA16 + (uint32_t)s * (H_A_SLOT >> 4);
+            uint32_t bt = b_set;
             const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
-            int ky = 0, kx = 0;
+            int kx = 0;
             for (int tap = 0; tap < p.taps; ++tap) {
-              if (t == 0) { mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph); tc_fence_after(); }
-              const uint32_t at = a16 + (uint32_t)(ky * p.pitch + kx) * 8u;
-              const uint32_t bt = smem_u32(sB + (set * H_MAX_TAPS + tap) * H_B_TILE) >> 4;
-              if (++kx == p.KW) { kx = 0; ++ky; }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_tf32(d_tmem, a_hi | (uint64_t)((at + 2 * k) & 0x3FFF),
-                            b_hi | (uint64_t)((bt + 2 * k) & 0x3FFF), IDESC, (cb | tap | k) ? 1u : 0u);
-              if (t == H_T - 1) tc_commit(&b_empty[set * H_MAX_TAPS + tap]);
+              if (t == 0) { mbar_wait(&bf[tap], bph); tc_fence_after(); }
+              tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
+              if (t == H_T - 1) tc_commit(&be[tap], leader);
+              at += 8u; bt += (H_B_TILE >> 4);
+              if (++kx == p.KW) { kx = 0; at += row_wrap; }
             }
-            tc_commit(&a_empty[s]);
+            tc_commit(&a_empty[s], leader);
             if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
           }
         }
-        tc_commit(&tfull[aset]);
+        tc_commit(&tfull[aset], leader);
         if (++aset == 2) { aset = 0; acc_ph ^= 1; }
       }
     }

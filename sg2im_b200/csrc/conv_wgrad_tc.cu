@@ -136,8 +136,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
+      // MN-major SWIZZLE_128B_BASE32B: lo = start>>4 | (atom stride>>4)<<16, hi = SBO(512)>>4 | v1 | type 1
+      const uint32_t d_hi = 32u | (1u << 14) | (1u << 29);
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | ((uint32_t)(A_ATOM_BYTES >> 4) << 16);
+      const uint32_t b_lo0 = ((smem_u32(smem) + A_STAGE) >> 4) | ((uint32_t)(B_ATOM_BYTES >> 4) << 16);
+      const uint32_t pitch16 = (uint32_t)p.pitch * 8u;               // halo row pitch in 16-byte units
+      const uint32_t row_wrap = (uint32_t)(p.pitch - p.KW) * 8u;
       int s = 0; uint32_t ph = 0;
       uint32_t acc_ph = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -146,35 +153,31 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int tap0 = pass * p.T;
         const int ntap = (p.taps - tap0) < p.T ? (p.taps - tap0) : p.T;
         const int ky0 = tap0 / p.KW, kx0 = tap0 - ky0 * p.KW;
-        const uint32_t pitch16 = (uint32_t)p.pitch * 8u;
-        const uint64_t a_hi = make_desc_mn(0, A_ATOM_BYTES), b_hi = make_desc_mn(0, B_ATOM_BYTES);
+        const uint32_t tap_off0 = (uint32_t)(ky0 * p.pitch + kx0) * 8u;
         mbar_wait(tempty, acc_ph ^ 1);
         tc_fence_after();
         for (int pt = t0; pt < t1; ++pt) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          // descriptors differ only in the 14-bit start-address field: precomputed
-          // high words + 16-byte-unit offsets keep the single issuing thread ahead
-          // of the tensor pipe (one MMA per 32 cycles at N = 64)
-          const uint32_t sa16 = smem_u32(smem + s * C::STAGE) >> 4;
-          const uint32_t sb16 = sa16 + (A_STAGE >> 4);
           const uint32_t first = (pt > t0) ? 1u : 0u;
-          int ky = ky0, kx = kx0;
+          uint32_t at = a_lo0 + (uint32_t)s * (C::STAGE >> 4) + tap_off0;
+          const uint32_t bt = b_lo0 + (uint32_t)s * (C::STAGE >> 4);
+          uint32_t d_tmem = tmem_base;
+          int kx = kx0;
           for (int tl = 0; tl < ntap; ++tl) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(tl * BN);
-            const uint32_t a_tap = sa16 + (uint32_t)(ky * p.pitch + kx) * 8u;   // 128 B rows = 8 x 16 B
-            if (++kx == p.KW) { kx = 0; ++ky; }
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {                    // RH == 4
-              uint64_t adesc = a_hi | (uint64_t)((a_tap + (uint32_t)h * pitch16) & 0x3FFF);
-              uint64_t bdesc = b_hi | (uint64_t)((sb16 + (uint32_t)h * 64u) & 0x3FFF);
-              tc_mma_tf32(d_tmem, adesc, bdesc, C::IDESC, (h > 0) ? 1u : first);
-            }
+            // 4 output rows of 8 pixels (RH == 4): K = 8 pixels per MMA
+            tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, first, leader);
+            tc_mma_tf32_lh(d_tmem, at + pitch16, d_hi, bt + 64, d_hi, C::IDESC, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 2 * pitch16, d_hi, bt + 128, d_hi, C::IDESC, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 3 * pitch16, d_hi, bt + 192, d_hi, C::IDESC, 1u, leader);
+            d_tmem += BN;
+            at += 8u;
+            if (++kx == p.KW) { kx = 0; at += row_wrap; }
           }
-          tc_commit(&empty[s]);
+          tc_commit(&empty[s], leader);
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(tfull);
+        tc_commit(tfull, leader);
         acc_ph ^= 1;
       }
     }

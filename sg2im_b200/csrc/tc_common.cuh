@@ -62,19 +62,39 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+// The MMA-issuing warp runs CONVERGED (all 32 lanes execute the loops with
+// warp-uniform values); only the instruction itself is predicated on `leader`
+// (lane 0).  Issuing from a single-lane divergent region makes the compiler wrap
+// every UTCHMMA in an ELECT / BRA.U.ANY loop and serialises ~10 uniform-datapath
+// instructions per MMA, which costs more than the 32 cycles an N=64 TF32 MMA
+// takes on the tensor pipe.
+__device__ __forceinline__ void tc_commit(uint64_t* bar, uint32_t leader = 1u) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+  (void)leader;
+}
+// descriptors are passed as (lo, hi) words: hi is loop-invariant, lo = base + offset
+__device__ __forceinline__ void tc_mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  (void)leader;
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  tc_mma_tf32_lh(d_tmem, (uint32_t)adesc, (uint32_t)(adesc >> 32), (uint32_t)bdesc,
+                 (uint32_t)(bdesc >> 32), idesc, accumulate, 1u);   // whole warp must be converged
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
