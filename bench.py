@@ -39,6 +39,7 @@ def parse():
   ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: config)')
   ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'],
                   help='convolution arithmetic: tcgen05 TF32 (default) or exact-fp32 FFMA')
+  ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--shapes-out', default=None, help='write per-shape conv timings (JSON)')
@@ -212,7 +213,7 @@ def run_b200(args, cfg):
     model = Sg2ImModel(vocab, **model_kwargs(cfg)).to(dev)
     d_img = PatchDiscriminator(D_ARCH, padding='valid').to(dev)
     d_obj = AcCropDiscriminator(vocab, D_ARCH, 'batch', 'leakyrelu-0.2', 32, 'valid').to(dev)
-  step = TrainStep(model, d_obj, d_img)
+  step = TrainStep(model, d_obj, d_img, cuda_graph=not args.no_graph)
   torch.manual_seed(1234 + rank)                         # noise stream differs per rank
 
   n_pool = 4
@@ -231,31 +232,37 @@ def run_b200(args, cfg):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.PROFILE = profile
-    l0 = _lib.launches
+    l0, r0 = _lib.launches, step.replays
     e0.record()
     last = None
     for i in range(n_steps):
-      if from_host:
-        batch = [t.to(dev, non_blocking=True) for t in host[i % n_pool]]
+      if profile is not None:                            # per-kernel events need eager launches
+        last, _ = step._step_eager(resident[i % n_pool])
+      elif from_host and step.cuda_graph:
+        last, _ = step.step(host[i % n_pool])            # H2D into the graph's static inputs
+      elif from_host:
+        last, _ = step.step([t.to(dev, non_blocking=True) for t in host[i % n_pool]])
       else:
-        batch = resident[i % n_pool]
-      last, _ = step.step(batch)                         # reads the losses back (D2H)
+        last, _ = step.step(resident[i % n_pool])        # reads the losses back (D2H)
     e1.record()
     sync_all()
     ops.PROFILE = None
     ms = e0.elapsed_time(e1)
+    n_launch = (_lib.launches - l0) + (step.replays - r0) * step.launches_per_replay
     if world > 1:
       t = torch.tensor([ms], device=dev)
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms = float(t.item())
-    return ms, _lib.launches - l0, last
+    return ms, n_launch, last
 
-  timed(args.warmup, False)                              # warm-up (untimed)
+  timed(max(args.warmup, 5 if not args.no_graph else args.warmup), False)   # warm-up (untimed; incl. graph capture)
   sampler = ClockSampler(local)
   sampler.start()
-  prof = []
-  ms, launches, last = timed(args.steps, False, profile=prof)
+  ms, launches, last = timed(args.steps, False)
   clocks = sampler.finish()
+  prof = []
+  timed(min(args.steps, 3), False, profile=prof)         # same step, eager, kernels bracketed by events
+  prof_steps = min(args.steps, 3)
   e2e = None
   if not args.no_e2e:
     ms_e, _, last_e = timed(args.steps, True)
@@ -282,15 +289,15 @@ def run_b200(args, cfg):
     roof = {'bound': 'tensor', 'kernel': 'conv implicit GEMM (fwd+dgrad+wgrad)',
             'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf'],
             'traffic': None, 'peak_source': pk['src'],
-            'share_of_step': conv_ms / ms,
-            'launches_per_step': sum(v[2] for v in fam.values()) / args.steps,
-            'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / args.steps,
-                              'launches_per_step': v[2] / args.steps} for k, v in fam.items()},
+            'share_of_step': (conv_ms / prof_steps) / (ms / args.steps),
+            'launches_per_step': sum(v[2] for v in fam.values()) / prof_steps,
+            'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / prof_steps,
+                              'launches_per_step': v[2] / prof_steps} for k, v in fam.items()},
             'top': top[0], 'math': ops.CONV_MATH}
 
   if args.shapes_out and rank == 0:
-    rows = [{'kernel': k[0], 'shape(N,H,W,Cin,Cout,K,S)': list(k[1:]), 'ms_per_step': v[1] / args.steps,
-             'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'launches_per_step': v[2] / args.steps}
+    rows = [{'kernel': k[0], 'shape(N,H,W,Cin,Cout,K,S)': list(k[1:]), 'ms_per_step': v[1] / prof_steps,
+             'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'launches_per_step': v[2] / prof_steps}
             for k, v in shapes.items()]
     rows.sort(key=lambda r: -r['ms_per_step'])
     json.dump(rows, open(args.shapes_out, 'w'), indent=1)
@@ -310,7 +317,7 @@ def run_b200(args, cfg):
                    'objs_per_gpu': int(resident[0][1].numel()),
                    'triples_per_gpu': int(resident[0][-3].size(0)),
                    'image_size': list(cfg['image_size']), 'global_batch': cfg['N'] * world,
-                   'parallelism': 'dp%d' % world,
+                   'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph),
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
                          'no explicit flush'},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,

@@ -71,8 +71,18 @@ def _all_finite(value, group=None):
 
 
 class TrainStep(object):
+  """step(batch) runs one iteration.  cuda_graph=True: after `graph_warmup`
+  eager iterations the whole iteration (three forward/backward passes, gradient
+  all-reduces, three Adam steps — ~1500 kernel launches) is captured once per
+  batch-shape signature into a CUDA graph and replayed; inputs are copied into
+  static buffers, losses are read back after the replay.  Inside a graph there
+  can be no host decision, so the reference's "skip the iteration on a
+  non-finite loss" (train.py:552-555) becomes an on-device skip: the finite flag
+  (all-reduced across ranks) is handed to the fused Adam kernels as `found_inf`,
+  which leaves parameters, moments and step counts untouched."""
+
   def __init__(self, model, obj_discriminator, img_discriminator, args=None,
-               fused_adam=None, group=None):
+               fused_adam=None, group=None, cuda_graph=False, graph_warmup=3):
     a = dict(DEFAULT_ARGS)
     if args is not None:
       a.update(args if isinstance(args, dict) else
@@ -87,6 +97,15 @@ class TrainStep(object):
     kw = dict(lr=a['learning_rate'])
     if fused_adam:
       kw['fused'] = True
+    self.cuda_graph = bool(cuda_graph) and dev.type == 'cuda'
+    if self.cuda_graph:
+      kw['fused'] = True
+      kw['capturable'] = True
+    self.graph_warmup = graph_warmup
+    self._graphs = {}                     # shape signature -> captured state
+    self._eager_calls = 0
+    self.launches_per_replay = 0
+    self.replays = 0
     self.nets = {'g': model, 'd_obj': obj_discriminator, 'd_img': img_discriminator}
     self.buckets, self.opts = {}, {}
     for name, net in self.nets.items():
@@ -129,7 +148,123 @@ class TrainStep(object):
 
   def step(self, batch, noise=None):
     """batch: the collate tuple (6 entries for VG, 7 with masks for COCO), on
-    the device.  Returns (losses dict of python floats, imgs_pred detached)."""
+    the device (graph mode also accepts pinned host tensors: they are copied
+    into the static input buffers).  Returns (losses dict of python floats,
+    imgs_pred detached)."""
+    if self.cuda_graph:
+      return self._step_graphed(batch, noise)
+    return self._step_eager(batch, noise)
+
+  # ------------------------------------------------------------------ graph mode
+  def _step_graphed(self, batch, noise):
+    sig = tuple((tuple(t.shape), t.dtype) for t in batch) + (None if noise is None else tuple(noise.shape),)
+    st = self._graphs.get(sig)
+    dev = next(self.model.parameters()).device
+    if st is None:
+      if self._eager_calls < self.graph_warmup:
+        self._eager_calls += 1
+        return self._step_eager([t.to(dev, non_blocking=True) for t in batch], noise)
+      st = self._capture([t.to(dev) for t in batch], noise)
+      self._graphs[sig] = st
+    for dst, src in zip(st['batch'], batch):
+      dst.copy_(src, non_blocking=True)
+    if noise is not None:
+      st['noise'].copy_(noise, non_blocking=True)
+    st['graph'].replay()
+    self.replays += 1
+    vals = st['loss_vec'].tolist()                  # the one D2H sync per iteration
+    out = dict(zip(st['keys'], vals))
+    if not math.isfinite(out['total_loss']):
+      print('WARNING: Got loss = NaN, not backpropping')
+      self.skipped += 1
+    return out, st['imgs_fake']
+
+  def _capture(self, batch, noise):
+    dev = batch[0].device
+    static_batch = [t.clone() for t in batch]
+    static_noise = None if noise is None else noise.to(dev).clone()
+    found_inf = torch.zeros((), dtype=torch.float32, device=dev)
+    for opt in self.opts.values():
+      opt.grad_scale = None
+      opt.found_inf = found_inf
+    from . import _lib
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    l0 = _lib.launches
+    with torch.cuda.graph(graph):
+      losses, imgs_fake = self._body(static_batch, static_noise, found_inf)
+      keys = list(losses.keys())
+      loss_vec = torch.stack([losses[k].reshape(()).detach() for k in keys])
+    torch.cuda.synchronize()
+    self.launches_per_replay = _lib.launches - l0      # library launches inside one replay
+    return dict(graph=graph, batch=static_batch, noise=static_noise, keys=keys,
+                loss_vec=loss_vec, imgs_fake=imgs_fake)
+
+  def _body(self, batch, noise, found_inf):
+    """The whole iteration with no host synchronisation (graph-capturable)."""
+    a = self.args
+    masks = None
+    if len(batch) == 6:
+      imgs, objs, boxes, triples, obj_to_img, _ = batch
+    else:
+      imgs, objs, boxes, masks, triples, obj_to_img, _ = batch
+    N = imgs.size(0)
+    imgs_pred, boxes_pred, masks_pred, predicate_scores = self.model(
+        objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, num_imgs=N, noise=noise)
+    total, losses = self.generator_losses(imgs, imgs_pred, boxes, boxes_pred, masks,
+                                          masks_pred, triples[:, 1], predicate_scores)
+    if self.d_obj is not None:
+      self._freeze(self.d_obj, True)
+      scores_fake, ac_loss = self.d_obj(imgs_pred, objs, boxes, obj_to_img)
+      losses['ac_loss'] = ac_loss * a['ac_loss_weight']
+      total = total + losses['ac_loss']
+      losses['g_gan_obj_loss'] = self.gan_g_loss(scores_fake) * (
+          a['discriminator_loss_weight'] * a['d_obj_weight'])
+      total = total + losses['g_gan_obj_loss']
+    if self.d_img is not None:
+      self._freeze(self.d_img, True)
+      scores_fake = self.d_img(imgs_pred)
+      losses['g_gan_img_loss'] = self.gan_g_loss(scores_fake) * (
+          a['discriminator_loss_weight'] * a['d_img_weight'])
+      total = total + losses['g_gan_img_loss']
+    losses['total_loss'] = total
+    # on-device, collective finite flag -> fused Adam's found_inf
+    bad = (~torch.isfinite(total.detach().reshape(()))).to(torch.float32)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+      dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+    found_inf.copy_(bad)
+    imgs_fake = imgs_pred.detach()
+
+    self.buckets['g'].zero()
+    total.backward()
+    self.buckets['g'].all_reduce_mean(self.group)
+    self.opts['g'].step()
+
+    if self.d_obj is not None:
+      self._freeze(self.d_obj, False)
+      s_fake, ac_fake = self.d_obj(imgs_fake, objs, boxes, obj_to_img)
+      s_real, ac_real = self.d_obj(imgs, objs, boxes, obj_to_img)
+      d_obj_gan = self.gan_d_loss(s_real, s_fake)
+      losses.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
+      self.buckets['d_obj'].zero()
+      (d_obj_gan + ac_real + ac_fake).backward()
+      self.buckets['d_obj'].all_reduce_mean(self.group)
+      self.opts['d_obj'].step()
+    if self.d_img is not None:
+      self._freeze(self.d_img, False)
+      s_fake = self.d_img(imgs_fake)
+      s_real = self.d_img(imgs)
+      d_img_gan = self.gan_d_loss(s_real, s_fake)
+      losses['d_img_gan_loss'] = d_img_gan
+      self.buckets['d_img'].zero()
+      d_img_gan.backward()
+      self.buckets['d_img'].all_reduce_mean(self.group)
+      self.opts['d_img'].step()
+    return losses, imgs_fake
+
+  # ------------------------------------------------------------------ eager mode
+  def _step_eager(self, batch, noise=None):
     a = self.args
     masks = None
     if len(batch) == 6:

@@ -201,3 +201,31 @@ def test_training_iteration_tf32_tensor_core_path():
     print('worst loss deviation under tf32', worst)
   finally:
     ops.set_conv_math('fp32')
+
+
+def test_cuda_graph_step_matches_eager_step():
+  """TrainStep(cuda_graph=True): replayed iterations give the same losses and
+  parameters as eager iterations (same batches, same injected noise)."""
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  kw = g['kwargs']
+  batch = [t.to(dev()) for t in g['batch']]
+  N = batch[0].size(0)
+  runs = {}
+  for mode in (False, True):
+    m, d_obj, d_img = _build_all(g)
+    step = TrainStep(m, d_obj, d_img, cuda_graph=mode, graph_warmup=2)
+    hist = []
+    for it in range(6):
+      noise = _noise(900 + it, N, kw['layout_noise_dim'], kw['image_size']).to(dev())
+      losses, imgs = step.step(batch, noise=noise)
+      hist.append(losses)
+    runs[mode] = (hist, {k: v.detach().clone() for k, v in m.state_dict().items()})
+    if mode:
+      assert step.replays == 3 and step.launches_per_replay > 100
+  for it in range(6):
+    for k, v in runs[False][0][it].items():
+      assert abs(runs[True][0][it][k] - v) <= 2e-4 * max(1.0, abs(v)), (it, k)
+  for k, v in runs[False][1].items():
+    if v.dtype.is_floating_point:
+      assert (runs[True][1][k] - v).abs().max() < 1e-3, k
