@@ -140,6 +140,17 @@ int sg2im_s2d_fwd(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int64_t
 int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W, int64_t C, float* dx,
                   sg2im_stream_t stream);
 
+/* OIHW master weights <-> kernel layouts, smem-tiled (both sides coalesced).
+ * pack:   w[co][ci][t] (ci < cin_use of Cin) -> w_fwd[t][co][ci] (sg2im_conv_tc
+ *         forward) and/or w_dgrad[T-1-t][ci][co] (sg2im_conv_tc as data
+ *         gradient: flipped taps, channels swapped); either may be NULL.
+ * unpack: dw[t][ci][co] (sg2im_conv_wgrad[_tc] output) -> grad_oihw[co][ci][t]
+ *         (= or += when accumulate). */
+int sg2im_pack_weights(const float* w, int64_t Cout, int64_t Cin, int64_t cin_use, int64_t taps,
+                       float* w_fwd, float* w_dgrad, sg2im_stream_t stream);
+int sg2im_unpack_wgrad(const float* dw, int64_t Cout, int64_t Cin, int64_t cin_use, int64_t taps,
+                       float* grad_oihw, int accumulate, sg2im_stream_t stream);
+
 /* out[c] = sum_m x[m, c]  (bias gradient), fp64 accumulation; out zeroed by
  * the call. */
 int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out,

@@ -31,6 +31,8 @@ SIGNATURES = {
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,
                           _i64, _ptr, _ptr],
+  'sg2im_pack_weights': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr],
+  'sg2im_unpack_wgrad': [_ptr, _i64, _i64, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_s2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
   'sg2im_s2d_bwd': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr],
   'sg2im_conv_wgrad': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr,

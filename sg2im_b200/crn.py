@@ -102,9 +102,10 @@ class RefinementNetwork(nn.Module):
     a = None
     for i, mod in enumerate(mods):
       conv1, bn1, s1, conv2, bn2, s2 = mod.parts()
-      z1 = conv1.forward_nhwc(h, in_ch=C if i == 0 else None)
+      z1 = conv1.forward_nhwc(h, in_ch=C if i == 0 else None,
+                              feeds_bn=bn1 is not None and bn1.training)
       a1 = ops.bn_act(z1, bn1, s1)
-      z2 = conv2.forward_nhwc(a1)
+      z2 = conv2.forward_nhwc(a1, feeds_bn=bn2 is not None and bn2.training)
       if i + 1 < len(mods):
         # BN + LeakyReLU + nearest x2 upsample, written into the next stage's
         # buffer behind its layout channels (crn.py:107 + :63)

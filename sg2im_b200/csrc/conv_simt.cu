@@ -340,6 +340,41 @@ __global__ void __launch_bounds__(256, 2) conv_wgrad_kernel(WgradP p) {
   }
 }
 
+// 1x1 weight gradient with Cout <= 4 (RGB head 64->3, mask head 128->1, box head):
+// dw[ci][co] += sum_m x[m][ci] * dy[m][co].  HBM-bound on x: threads map to
+// channels (coalesced rows), 4+ pixel lanes per block, block reduce, one atomic
+// per (ci, co) per block.
+__global__ void __launch_bounds__(256)
+wgrad_skinny_kernel(const float* __restrict__ x, int64_t xs, int64_t M, int Cin,
+                    const float* __restrict__ dy, int Cout, int64_t rows_per_block,
+                    float* __restrict__ dw) {
+  __shared__ float red[4][256];
+  const int lanes = 256 / Cin > 0 ? 256 / Cin : 1;       // pixel lanes (Cin <= 256)
+  const int ci = threadIdx.x % Cin, pl = threadIdx.x / Cin;
+  int64_t mb = (int64_t)blockIdx.x * rows_per_block;
+  int64_t me = mb + rows_per_block < M ? mb + rows_per_block : M;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    for (int64_t m = mb + pl; m < me; m += lanes) {
+      float xv = x[m * xs + ci];
+      const float* d = dy + m * Cout;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < Cout) acc[j] = fmaf(xv, d[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[j][threadIdx.x] = (pl < lanes) ? acc[j] : 0.f;
+  __syncthreads();
+  if (pl == 0) {
+    for (int j = 0; j < Cout; ++j) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[j][l * Cin + ci];
+      atomicAdd(dw + (int64_t)ci * Cout + j, s);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t sxw,
@@ -393,6 +428,20 @@ extern "C" int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_
   SG_ARG(N >= 1 && Hin >= 1 && Win >= 1 && Cin >= 1 && Hout >= 1 && Wout >= 1 && Cout >= 1);
   SG_ARG(KH >= 1 && KW >= 1 && S >= 1 && P >= 0);
   SG_ARG((Hin + 2 * P - KH) / S + 1 == Hout && (Win + 2 * P - KW) / S + 1 == Wout);
+  if (KH == 1 && KW == 1 && S == 1 && P == 0 && Cout <= 4 && Cin <= 256 && sxc == 1 &&
+      (Hin * Win == 1 || (sxw * Win == sxh && sxh * Hin == sxn))) {
+    // pixels form one dense list of rows with stride sxw (or sxn when H = W = 1)
+    int64_t M = N * Hin * Win;
+    int64_t xs = (Hin * Win == 1) ? sxn : sxw;
+    int64_t blocks = 148 * 8;
+    int64_t rpb = ceil_div64(M, blocks);
+    if (rpb < 64) rpb = 64;
+    blocks = ceil_div64(M, rpb);
+    wgrad_skinny_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, xs, M, (int)Cin, dy,
+                                                                           (int)Cout, rpb, dw);
+    SG_LAUNCH_OK();
+    return 0;
+  }
   WgradP p;
   p.x = x; p.sxn = sxn; p.sxh = sxh; p.sxw = sxw; p.sxc = sxc;
   p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin; p.dy = dy;

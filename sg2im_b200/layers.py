@@ -38,9 +38,11 @@ class Conv2d(nn.Conv2d):
                                 'dilation/groups (all the reference uses)')
     return self.stride[0], self.padding[0]
 
-  def forward_nhwc(self, h, act=0, slope=0.0, in_ch=None):
+  def forward_nhwc(self, h, act=0, slope=0.0, in_ch=None, feeds_bn=False):
+    """feeds_bn: the output goes straight into a train-mode BatchNorm (its
+    bias gradient is identically zero and is not computed)."""
     stride, pad = self._cfg()
-    return ops.conv2d(h, self.weight, self.bias, stride, pad, act, slope, in_ch)
+    return ops.conv2d(h, self.weight, self.bias, stride, pad, act, slope, in_ch, feeds_bn)
 
   def forward(self, x):
     return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
@@ -190,7 +192,7 @@ class FusedSequential(nn.Sequential):
         if s is not None:
           h = m.forward_nhwc(h, 1, s); i += 2
         else:
-          h = m.forward_nhwc(h); i += 1
+          h = m.forward_nhwc(h, feeds_bn=isinstance(nxt, BatchNorm2d) and nxt.training); i += 1
       elif isinstance(m, Linear) and not four_d:
         if s is not None:
           h = m.forward_act(h, 1, s); i += 2

@@ -179,17 +179,40 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
   return out
 
 
-def pack_tc_fwd(weight):
-  """OIHW -> [KH*KW][Cout][Cin]."""
+def _pack(weight, cin_use, want_fwd):
+  weight = weight.contiguous()
   Co, Ci, KH, KW = weight.shape
-  return weight.permute(2, 3, 0, 1).reshape(KH * KW, Co, Ci).contiguous()
+  T = KH * KW
+  cu = Ci if cin_use is None else cin_use
+  if want_fwd and T == 1 and cu == Ci:
+    return weight.view(1, Co, Ci)                       # a Linear is already [1][Cout][Cin]
+  out = torch.empty((T, Co, cu) if want_fwd else (T, cu, Co), dtype=torch.float32,
+                    device=weight.device)
+  _call('sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(out) if want_fwd else None,
+        None if want_fwd else _p(out), _stream())
+  _count()
+  return out
 
 
-def pack_tc_dgrad(weight):
+def pack_tc_fwd(weight, cin_use=None):
+  """OIHW (first cin_use input channels) -> [KH*KW][Cout][Cin]."""
+  return _pack(weight, cin_use, True)
+
+
+def pack_tc_dgrad(weight, cin_use=None):
   """OIHW -> [KH*KW (flipped)][Cin][Cout]: the data gradient of a stride-1 conv
   is a conv of dY with the spatially flipped, channel-transposed filter."""
-  Co, Ci, KH, KW = weight.shape
-  return weight.flip(2, 3).permute(2, 3, 1, 0).reshape(KH * KW, Ci, Co).contiguous()
+  return _pack(weight, cin_use, False)
+
+
+def unpack_wgrad_oihw(dw, wshape, cin_use):
+  """dw [T][cin_use][Cout] -> OIHW gradient of the full weight (channels beyond
+  cin_use get zero)."""
+  Co, Ci, KH, KW = wshape
+  grad = (torch.zeros if cin_use != Ci else torch.empty)(wshape, dtype=torch.float32, device=dw.device)
+  _call('sg2im_unpack_wgrad', _p(dw), Co, Ci, cin_use, KH * KW, _p(grad), 0, _stream())
+  _count()
+  return grad
 
 
 def conv_wgrad(x, dy, KH, KW, S, P):
@@ -336,7 +359,8 @@ class Conv(torch.autograd.Function):
   first stage, whose extra input channel is identically zero)."""
 
   @staticmethod
-  def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch, out_hw=None):
+  def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch, out_hw=None,
+              zero_bias_grad=False):
     _chk(weight, name='weight')
     Co, Ci_w, KH, KW = weight.shape
     Ci = Ci_w if in_ch is None else in_ch
@@ -349,13 +373,15 @@ class Conv(torch.autograd.Function):
       assert out_hw[0] <= Hout and out_hw[1] <= Wout and conv_tc_ok(x, KH, KW, stride, pad, Co, out_hw)
       Hout, Wout = out_hw
     if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
-      y = conv_tc(x, pack_tc_fwd(w_used), bias, KH, KW, pad, Co, act, slope, out_hw=(Hout, Wout))
+      y = conv_tc(x, pack_tc_fwd(weight, Ci), bias, KH, KW, pad, Co, act, slope,
+                  out_hw=(Hout, Wout))
     else:
       y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
                      act, slope)
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.has_bias = bias is not None
+    ctx.zero_bias_grad = bool(zero_bias_grad)
     return y
 
   @staticmethod
@@ -372,21 +398,23 @@ class Conv(torch.autograd.Function):
       pad_t = KH - 1 - pad
       if (KH == KW and pad_t >= 0 and stride == 1
           and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
-        dx = conv_tc(dy, pack_tc_dgrad(w_used), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
+        dx = conv_tc(dy, pack_tc_dgrad(weight, Ci), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
                      out_hw=(x.size(1), x.size(2)))
       else:
         dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
                         (x.size(1), x.size(2)), Ci)
     if ctx.needs_input_grad[1]:
       dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
-      dw = unpack_conv_wgrad(dwp, (Co, Ci, KH, KW))
-      if Ci != Ci_w:
-        full = torch.zeros(wshape, dtype=dw.dtype, device=dw.device)
-        full[:, :Ci] = dw
-        dw = full
+      dw = unpack_wgrad_oihw(dwp, wshape, Ci)
     if ctx.has_bias and ctx.needs_input_grad[2]:
-      db = colsum(dy.view(-1, Co))
-    return dx, dw, db, None, None, None, None, None, None
+      if ctx.zero_bias_grad:
+        # this conv feeds a train-mode BatchNorm: d(loss)/d(bias) is identically
+        # zero (BN subtracts the batch mean); the reference accumulates rounding
+        # noise there.  Skip the full pass over dy.
+        db = torch.zeros(Co, dtype=torch.float32, device=dy.device)
+      else:
+        db = colsum(dy.view(-1, Co))
+    return dx, dw, db, None, None, None, None, None, None, None
 
 
 class S2D(torch.autograd.Function):
@@ -414,7 +442,7 @@ class S2D(torch.autograd.Function):
     return dx
 
 
-def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None):
+def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False):
   if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
       and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4
       and weight.size(0) % 32 == 0):
@@ -425,8 +453,8 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None):
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
     w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
-    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo))
-  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch)
+    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn)
+  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn)
 
 
 def linear(x2d, weight, bias, act=0, slope=0.0):
