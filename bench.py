@@ -323,9 +323,16 @@ def run_b200(args, cfg):
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
         'cpu_baseline': cpu, 'last_losses': last,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
   if world > 1:
-    dist.destroy_process_group()
+    # Leave without tearing NCCL down: destroying the process group while CUDA
+    # graphs that captured NCCL kernels are alive can block forever (seen on
+    # the 2-GPU box).  Everything is flushed; a final barrier keeps ranks in step.
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
