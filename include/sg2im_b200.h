@@ -97,6 +97,9 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
  * conv is the same call with spatially flipped, channel-transposed weights
  * and P' = K-1-P.  A KxK stride-2 'valid' conv (the discriminators) is the
  * same call on the space-to-depth input (sg2im_s2d_fwd) with K/2 taps.
+ * stats (optional, act == 0, Cout <= 1024): caller-zeroed double[2*Cout]; the
+ * epilogue adds the per-channel sum and sum of squares of the outputs — the
+ * batch statistics of the BatchNorm that follows, without a second pass.
  * sg2im_conv_tc_supported(): S == 1, Cin % 4 == 0, Cout % 4 == 0, 16-byte
  * aligned slices; otherwise sg2im_conv_tc returns -2 (use sg2im_conv_igemm). */
 int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
@@ -106,7 +109,7 @@ int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
 int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                   int64_t Cin, const float* w_tc, const float* bias, int KH, int KW, int P,
                   int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope, float* y,
-                  int64_t y_cstride, int64_t y_coff, sg2im_stream_t stream);
+                  int64_t y_cstride, int64_t y_coff, double* stats, sg2im_stream_t stream);
 
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the

@@ -102,16 +102,19 @@ class RefinementNetwork(nn.Module):
     a = None
     for i, mod in enumerate(mods):
       conv1, bn1, s1, conv2, bn2, s2 = mod.parts()
-      z1 = conv1.forward_nhwc(h, in_ch=C if i == 0 else None,
-                              feeds_bn=bn1 is not None and bn1.training)
-      a1 = ops.bn_act(z1, bn1, s1)
-      z2 = conv2.forward_nhwc(a1, feeds_bn=bn2 is not None and bn2.training)
+      fb1 = bn1 is not None and bn1.training
+      fb2 = bn2 is not None and bn2.training
+      st1 = ops.new_stats(conv1.out_channels, h.device) if fb1 else None
+      z1 = conv1.forward_nhwc(h, in_ch=C if i == 0 else None, feeds_bn=fb1, stats_out=st1)
+      a1 = ops.bn_act(z1, bn1, s1, sums=st1)
+      st2 = ops.new_stats(conv2.out_channels, h.device) if fb2 else None
+      z2 = conv2.forward_nhwc(a1, feeds_bn=fb2, stats_out=st2)
       if i + 1 < len(mods):
         # BN + LeakyReLU + nearest x2 upsample, written into the next stage's
         # buffer behind its layout channels (crn.py:107 + :63)
-        h = ops.bn_act(z2, bn2, s2, up=2, out=bufs[i + 1], out_coff=C)
+        h = ops.bn_act(z2, bn2, s2, up=2, out=bufs[i + 1], out_coff=C, sums=st2)
       else:
-        a = ops.bn_act(z2, bn2, s2)
+        a = ops.bn_act(z2, bn2, s2, sums=st2)
     oc = list(self.output_conv)
     t = oc[0].forward_nhwc(a, 1, oc[1].negative_slope)
     return oc[2].forward_nhwc(t)

@@ -38,6 +38,7 @@ struct TcParams {
   const float* bias;
   int act; float slope;
   float* y; long long y_cstride, y_coff;
+  double* stats;                   // optional [2*Cout] per-channel sum / sum of squares
 };
 
 using namespace tc;
@@ -56,7 +57,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;                     // 128 / 256 / 512
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 + 8192 /*BN partials*/;
   // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
   // N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC =
@@ -79,9 +80,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * C::STAGES;                      // [2]
   uint64_t* tempty = bars + 2 * C::STAGES + 2;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* s_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][1024]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -177,29 +181,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
       float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
                     p.y_coff + (long long)nt * BN;
-      const float* brow = p.bias ? p.bias + nt * BN : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         if (nt * BN + ch * 32 >= p.Cout) break;              // partial last N tile (warp-uniform)
         float v[32];
         tc_ld32(taddr + ch * 32, v);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nt * BN + ch * 32 + j >= p.Cout) break;        // Cout % 4 == 0: whole float4s
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (brow) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(brow + ch * 32 + j));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (p.act) {
-              o.x = leaky(o.x, p.slope); o.y = leaky(o.y, p.slope);
-              o.z = leaky(o.z, p.slope); o.w = leaky(o.w, p.slope);
-            }
-            *reinterpret_cast<float4*>(yrow + ch * 32 + j) = o;
-          }
-        }
+        epilogue_chunk(v, valid, nt * BN + ch * 32, p.Cout, p.bias, p.act, p.slope, yrow + ch * 32,
+                       p.stats ? s_part : nullptr, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -210,6 +199,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float a = s_part[c], b = s_part[1024 + c];
+      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -241,7 +236,7 @@ constexpr int H_A_SLOTS = 3;
 constexpr int H_B_TILE = H_BN * KB_BYTES;     // 8 KB
 constexpr int H_MAX_TAPS = 9;
 constexpr int H_THREADS = 256;
-constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512;
+constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512 + 8192;
 
 struct HaloParams {
   int N, Hout, Wout, Cin, Cout;
@@ -252,6 +247,7 @@ struct HaloParams {
   const float* bias;
   int act; float slope;
   float* y; long long y_cstride, y_coff;
+  double* stats;
 };
 
 __global__ void __launch_bounds__(H_THREADS, 1)
@@ -270,8 +266,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = bars + 6 + 36;            // [2]
   uint64_t* tempty = bars + 6 + 38;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 40);
+  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][1024]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.groups * p.n_tiles;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -402,7 +401,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       decode(item, nt, pt0);
       mbar_wait(&tfull[aset], acc_ph);
       tc_fence_after();
-      const float* brow = p.bias ? p.bias + nt * H_BN : nullptr;
       for (int t = 0; t < H_T; ++t) {
         int n, y0, x0;
         tile_xy(pt0 + t, n, y0, x0);
@@ -415,22 +413,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (nt * H_BN + ch * 32 >= p.Cout) break;
           float v[32];
           tc_ld32(taddr + ch * 32, v);
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (nt * H_BN + ch * 32 + j >= p.Cout) break;
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (brow) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(brow + ch * 32 + j));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (p.act) {
-                o.x = leaky(o.x, p.slope); o.y = leaky(o.y, p.slope);
-                o.z = leaky(o.z, p.slope); o.w = leaky(o.w, p.slope);
-              }
-              *reinterpret_cast<float4*>(yrow + ch * 32 + j) = o;
-            }
-          }
+          epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
+                         yrow + ch * 32, p.stats ? s_part : nullptr, lane);
         }
       }
       tc_fence_before();
@@ -442,6 +426,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float a = s_part[c], b = s_part[1024 + c];
+      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
@@ -499,7 +489,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                              int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
                              int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
                              int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
-                             sg2im_stream_t stream) {
+                             double* stats, sg2im_stream_t stream) {
   SG_ARG(x && w_tc && y);
   if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
                                y_cstride, y_coff)) {
@@ -507,10 +497,12 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
     return -2;
   }
   SG_ARG(aligned16(x) && aligned16(w_tc) && aligned16(y) && (!bias || aligned16(bias)));
+  SG_ARG(stats == nullptr || (Cout <= 1024 && act == 0));
   EncodeTiledFn enc = get_encode();
   if (!enc) { sg2im_set_error("sg2im_conv_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
 
   TcParams p;
+  p.stats = stats;
   p.N = (int)N; p.Hout = (int)Hout; p.Wout = (int)Wout;
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
   tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
@@ -546,6 +538,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
     h.a_bytes = (uint32_t)((H_BH + KH - 1) * h.pitch * 128);
     h.bias = bias; h.act = act; h.slope = slope;
     h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
+    h.stats = stats;
     CUtensorMap hA, hB;
     {
       cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};

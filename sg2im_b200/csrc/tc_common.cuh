@@ -114,6 +114,92 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 
 
+// Column sums across the 32 lanes of a warp for 32 per-lane values: lane j
+// returns sum over lanes of v[j] (31 shuffles via recursive halving instead of
+// 32 x 5 for independent butterflies).
+__device__ __forceinline__ float warp_colsum32(const float* v, int lane) {
+  float a[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float keep = up ? a[i + 8] : a[i], send = up ? a[i] : a[i + 8];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float keep = up ? a[i + 4] : a[i], send = up ? a[i] : a[i + 4];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float keep = up ? a[i + 2] : a[i], send = up ? a[i] : a[i + 2];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  {
+    const bool up = lane & 1;
+    float keep = up ? a[1] : a[0], send = up ? a[0] : a[1];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return a[0];
+}
+
+// Shared epilogue of the conv kernels: v[32] = accumulator chunk of one pixel ->
+// + bias -> (per-channel sum / sum of squares into the CTA's smem partials, for
+// the BatchNorm that follows) -> LeakyReLU -> 128-bit stores.
+__device__ __forceinline__ void epilogue_chunk(float* v, bool valid, int col0, int Cout,
+                                               const float* bias, int act, float slope,
+                                               float* yrow, float* s_part, int lane) {
+  const float* brow = bias ? bias + col0 : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    if (brow && col0 + j < Cout) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(brow + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (s_part) {
+    float sq[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (!valid) v[j] = 0.f;
+      sq[j] = v[j] * v[j];
+    }
+    float s1 = warp_colsum32(v, lane), s2 = warp_colsum32(sq, lane);
+    if (col0 + lane < Cout) {
+      atomicAdd(&s_part[col0 + lane], s1);
+      atomicAdd(&s_part[1024 + col0 + lane], s2);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j >= Cout) break;                       // Cout % 4 == 0: whole float4s
+      float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      if (act) {
+        o.x = leaky(o.x, slope); o.y = leaky(o.y, slope);
+        o.z = leaky(o.z, slope); o.w = leaky(o.w, slope);
+      }
+      *reinterpret_cast<float4*>(yrow + j) = o;
+    }
+  }
+}
+
 // host: driver entry point for tensor-map encoding (no link-time libcuda dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

@@ -38,11 +38,13 @@ class Conv2d(nn.Conv2d):
                                 'dilation/groups (all the reference uses)')
     return self.stride[0], self.padding[0]
 
-  def forward_nhwc(self, h, act=0, slope=0.0, in_ch=None, feeds_bn=False):
+  def forward_nhwc(self, h, act=0, slope=0.0, in_ch=None, feeds_bn=False, stats_out=None):
     """feeds_bn: the output goes straight into a train-mode BatchNorm (its
-    bias gradient is identically zero and is not computed)."""
+    bias gradient is identically zero and is not computed); stats_out receives
+    that BatchNorm's batch statistics from the conv epilogue."""
     stride, pad = self._cfg()
-    return ops.conv2d(h, self.weight, self.bias, stride, pad, act, slope, in_ch, feeds_bn)
+    return ops.conv2d(h, self.weight, self.bias, stride, pad, act, slope, in_ch, feeds_bn,
+                      stats_out)
 
   def forward(self, x):
     return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
@@ -51,16 +53,27 @@ class Conv2d(nn.Conv2d):
 class Linear(nn.Linear):
   def forward_act(self, x, act=0, slope=0.0):
     lead = x.shape[:-1]
-    y = ops.linear(x.reshape(-1, x.size(-1)), self.weight, self.bias, act, slope)
-    return y.view(*lead, self.out_features)
+    x2 = x.reshape(-1, x.size(-1))
+    nout = self.out_features
+    pad = (-nout) % 4
+    if pad and ops.CONV_MATH == 'tf32' and nout >= 32 and self.in_features % 4 == 0:
+      # e.g. the object classifier (1024 -> num_objects = 179): pad the output
+      # width to a multiple of 4 with zero rows so the GEMM and its data
+      # gradient run on the tensor-core kernel; the extra columns are sliced off
+      w = torch.nn.functional.pad(self.weight, (0, 0, 0, pad))
+      b = None if self.bias is None else torch.nn.functional.pad(self.bias, (0, pad))
+      y = ops.linear(x2, w, b, act, slope)[:, :nout]
+    else:
+      y = ops.linear(x2, self.weight, self.bias, act, slope)
+    return y.reshape(*lead, nout)
 
   def forward(self, x):
     return self.forward_act(x)
 
 
 class BatchNorm2d(nn.BatchNorm2d):
-  def forward_nhwc(self, h, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0):
-    return ops.bn_act(h, self, slope, up, unbias_mult, out, out_coff)
+  def forward_nhwc(self, h, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0, sums=None):
+    return ops.bn_act(h, self, slope, up, unbias_mult, out, out_coff, sums)
 
   def forward(self, x):
     return _to_nchw(self.forward_nhwc(_to_nhwc(x).contiguous()))
@@ -184,6 +197,7 @@ class FusedSequential(nn.Sequential):
     four_d = x.dim() == 4
     h = _to_nhwc(x) if four_d else x
     i = 0
+    sums = None                       # batch statistics handed from a conv to the BN after it
     while i < len(mods):
       m = mods[i]
       nxt = mods[i + 1] if i + 1 < len(mods) else None
@@ -192,7 +206,9 @@ class FusedSequential(nn.Sequential):
         if s is not None:
           h = m.forward_nhwc(h, 1, s); i += 2
         else:
-          h = m.forward_nhwc(h, feeds_bn=isinstance(nxt, BatchNorm2d) and nxt.training); i += 1
+          fb = isinstance(nxt, BatchNorm2d) and nxt.training
+          sums = ops.new_stats(m.out_channels, h.device) if fb else None
+          h = m.forward_nhwc(h, feeds_bn=fb, stats_out=sums); i += 1
       elif isinstance(m, Linear) and not four_d:
         if s is not None:
           h = m.forward_act(h, 1, s); i += 2
@@ -200,9 +216,10 @@ class FusedSequential(nn.Sequential):
           h = m.forward_act(h); i += 1
       elif isinstance(m, BatchNorm2d) and four_d:
         if s is not None:
-          h = m.forward_nhwc(h.contiguous(), s); i += 2
+          h = m.forward_nhwc(h.contiguous(), s, sums=sums); i += 2
         else:
-          h = m.forward_nhwc(h.contiguous()); i += 1
+          h = m.forward_nhwc(h.contiguous(), sums=sums); i += 1
+        sums = None
       elif isinstance(m, BatchNorm1d) and not four_d:
         if s is not None:
           h = m.forward_act(h, s); i += 2

@@ -163,7 +163,7 @@ def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
 
 
 def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
-            tag='conv_fwd_tc', out_hw=None):
+            tag='conv_fwd_tc', out_hw=None, stats=None):
   """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
   w_tc packed [KH*KW][Cout][Cin]; out_hw: explicit output size (reads outside
   the input are zero)."""
@@ -174,7 +174,7 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
   with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
     _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Hout, Wout,
-          Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _stream())
+          Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _p(stats), _stream())
   _count()
   return out
 
@@ -260,7 +260,7 @@ def act_bwd(dy, y, slope):
 
 
 def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum, eps,
-                   unbias_mult=1):
+                   unbias_mult=1, sums=None):
   """Batch statistics of x (rows = all dims but the last) -> (scale, shift, save)."""
   C = x.size(-1)
   M = x.numel() // C
@@ -268,8 +268,7 @@ def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum
   scale = torch.empty(C, dtype=torch.float32, device=dev)
   shift = torch.empty(C, dtype=torch.float32, device=dev)
   save = torch.empty(2 * C, dtype=torch.float32, device=dev)
-  sums = None
-  if training:
+  if training and sums is None:
     sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
     _call('sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
     _count()
@@ -360,7 +359,7 @@ class Conv(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch, out_hw=None,
-              zero_bias_grad=False):
+              zero_bias_grad=False, stats_out=None):
     _chk(weight, name='weight')
     Co, Ci_w, KH, KW = weight.shape
     Ci = Ci_w if in_ch is None else in_ch
@@ -372,12 +371,18 @@ class Conv(torch.autograd.Function):
       # cropped output (space-to-depth route of the stride-2 convs): tensor-core only
       assert out_hw[0] <= Hout and out_hw[1] <= Wout and conv_tc_ok(x, KH, KW, stride, pad, Co, out_hw)
       Hout, Wout = out_hw
+    fused_stats = stats_out is not None and act == 0 and Co <= 1024
     if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
       y = conv_tc(x, pack_tc_fwd(weight, Ci), bias, KH, KW, pad, Co, act, slope,
-                  out_hw=(Hout, Wout))
+                  out_hw=(Hout, Wout), stats=stats_out if fused_stats else None)
     else:
+      fused_stats = False
       y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
                      act, slope)
+    if stats_out is not None and not fused_stats:
+      # per-channel sum / sum of squares of the output for the BatchNorm that follows
+      _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
+      _count()
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.has_bias = bias is not None
@@ -414,7 +419,7 @@ class Conv(torch.autograd.Function):
         db = torch.zeros(Co, dtype=torch.float32, device=dy.device)
       else:
         db = colsum(dy.view(-1, Co))
-    return dx, dw, db, None, None, None, None, None, None, None
+    return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 class S2D(torch.autograd.Function):
@@ -442,7 +447,10 @@ class S2D(torch.autograd.Function):
     return dx
 
 
-def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False):
+def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False,
+           stats_out=None):
+  """stats_out: zeroed float64 [2*Cout]; receives the per-channel sum and sum of
+  squares of the output (fused into the tensor-core epilogue when possible)."""
   if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
       and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4
       and weight.size(0) % 32 == 0):
@@ -453,8 +461,8 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
     w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
-    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn)
-  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn)
+    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out)
+  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out)
 
 
 def linear(x2d, weight, bias, act=0, slope=0.0):
@@ -473,12 +481,12 @@ class BNAct(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, gamma, beta, running_mean, running_var, use_bn, training, momentum, eps,
-              slope, up, unbias_mult, out, out_coff):
+              slope, up, unbias_mult, out, out_coff, sums=None):
     x = _chk(x).contiguous()
     scale = shift = save = None
     if use_bn:
       scale, shift, save = bn_scale_shift(x, gamma, beta, running_mean, running_var, training,
-                                          momentum, eps, unbias_mult)
+                                          momentum, eps, unbias_mult, sums if training else None)
     y = scale_act_fwd(x, scale, shift, slope, up, out, out_coff)
     if out is not None:
       ctx.mark_dirty(out)
@@ -495,10 +503,11 @@ class BNAct(torch.autograd.Function):
     dx, dgamma, dbeta = scale_act_bwd(dy, coff, x, scale, shift, save, slope, up,
                                       training and use_bn, want_pg)
     dout = dy if sliced else None
-    return (dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, dout, None)
+    return (dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, dout, None,
+            None)
 
 
-def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0):
+def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0, sums=None):
   """bn: an nn.BatchNorm2d-like module (weight, bias, running_mean, running_var,
   training, momentum, eps, num_batches_tracked) or None."""
   if bn is None:
@@ -509,7 +518,11 @@ def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0):
     bn.num_batches_tracked.add_(1)
   momentum = 0.1 if bn.momentum is None else bn.momentum
   return BNAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, True, training,
-                     momentum, bn.eps, slope, up, unbias_mult, out, out_coff)
+                     momentum, bn.eps, slope, up, unbias_mult, out, out_coff, sums)
+
+
+def new_stats(channels, device):
+  return torch.zeros(2 * channels, dtype=torch.float64, device=device)
 
 
 class TripleGather(torch.autograd.Function):
