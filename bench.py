@@ -32,8 +32,8 @@ UNIT = 'images/s'
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=10)
-  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--steps', type=int, default=50)
+  ap.add_argument('--warmup', type=int, default=10)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='vg128')
   ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: config)')
@@ -67,7 +67,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-  """SM clock + throttle reasons during the timed region (NVML, 200 ms)."""
+  """SM clock + throttle reasons during the timed region (NVML, every 50 ms)."""
 
   def __init__(self, index):
     super().__init__(daemon=True)
@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(name)
       except Exception:
         pass
-      self._stop_evt.wait(0.2)
+      self._stop_evt.wait(0.05)
 
   def finish(self):
     self._stop_evt.set()
@@ -293,7 +293,13 @@ def run_b200(args, cfg):
             'launches_per_step': sum(v[2] for v in fam.values()) / prof_steps,
             'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / prof_steps,
                               'launches_per_step': v[2] / prof_steps} for k, v in fam.items()},
-            'top': top[0], 'math': ops.CONV_MATH}
+            'top': top[0], 'math': ops.CONV_MATH,
+            # the path multiplies in TF32, whose tensor-pipe rate is half the bf16 rate the
+            # measured peak was taken at: fraction against that halved figure as well
+            'peak_tf32_est': pk['tf'] / 2.0, 'frac_of_tf32_est': ach / (pk['tf'] / 2.0),
+            'note': 'achieved = algorithmic conv FLOPs / summed CUDA-event kernel time of the same '
+                    'step launched eagerly right after the timed (graph-replayed) region; traffic: '
+                    'see profiles/ (ncu --set full per kernel)'}
 
   if args.shapes_out and rank == 0:
     rows = [{'kernel': k[0], 'shape(N,H,W,Cin,Cout,K,S)': list(k[1:]), 'ms_per_step': v[1] / prof_steps,
