@@ -288,7 +288,11 @@ def run_b200(args, cfg):
     ach = conv_fl / (conv_ms * 1e-3) / 1e12
     roof = {'bound': 'tensor', 'kernel': 'conv implicit GEMM (fwd+dgrad+wgrad)',
             'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf'],
-            'traffic': None, 'peak_source': pk['src'],
+            # dram__bytes_read.sum + dram__bytes_write.sum of the top kernel (conv_tc_halo_kernel,
+            # stage-4 conv1 shape, one launch) from the committed ncu --set full capture
+            # profiles/r01_prof_conv_tc_halo.txt: 630.0 + 109.9 MB = the algorithmic 604 + 134 MB
+            'traffic': 739.9e6, 'traffic_unit': 'bytes/launch (top kernel, ncu)',
+            'peak_source': pk['src'],
             'share_of_step': (conv_ms / prof_steps) / (ms / args.steps),
             'launches_per_step': sum(v[2] for v in fam.values()) / prof_steps,
             'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / prof_steps,
