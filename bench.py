@@ -23,6 +23,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
+if 'reference' in sys.argv:
+  # torchrun exports OMP_NUM_THREADS=1; the CPU arm must own the host cores
+  for _v in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ[_v] = os.environ.get('SG2IM_CPU_THREADS', str(os.cpu_count() or 1))
+
 import torch  # noqa: E402
 
 METRIC = 'train-step images/sec at 128x128'
@@ -128,7 +133,7 @@ def cpu_reference_arm(cfg, steps, warmup, sample_imgs, budget_s=25.0):
   from sg2im_b200.model import Sg2ImModel
   from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
   from sg2im_b200.synth import make_vocab, synth_batch
-  cores = os.cpu_count() or 1
+  cores = int(os.environ.get('SG2IM_CPU_THREADS', os.cpu_count() or 1))
   torch.set_num_threads(cores)
   vocab = make_vocab(cfg['num_objs'], cfg['num_preds'])
   torch.manual_seed(0)
