@@ -43,13 +43,8 @@ struct TcParams {
 
 using namespace tc;
 
-// K-major, 128B-swizzled smem matrix descriptor (rows of 128 B, 8-row groups
-// 1024 B apart): start>>4 | LBO=1 (ignored for swizzled K-major) | SBO=1024>>4 |
-// version 1 (Blackwell) | layout SWIZZLE_128B (=2).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-         (2ull << 61);
-}
+// K-major SWIZZLE_128B descriptors are assembled in the MMA warps as (lo, hi) words:
+// lo = start>>4 | LBO(=1, ignored)<<16, hi = SBO>>4 | version 1<<14 | layout 2<<29.
 
 template <int BN>
 struct Cfg {

@@ -41,12 +41,8 @@ struct WgParams {
   float* dw;
 };
 
-// MN-major, SWIZZLE_128B_BASE32B descriptor: LBO = byte stride between 32-channel
-// atoms, SBO = 512 B (4 pixel rows), version 1, layout type 1.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) |
-         (1ull << 46) | (1ull << 61);
-}
+// MN-major SWIZZLE_128B_BASE32B descriptors (lo, hi words): lo = start>>4 | (byte stride
+// between 32-channel atoms >> 4)<<16, hi = SBO(512 B = 4 pixel rows)>>4 | version 1<<14 | layout 1<<29.
 
 template <int BN>
 struct WCfg {

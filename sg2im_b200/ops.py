@@ -343,11 +343,6 @@ def pack_conv_dgrad(weight):
   return weight.permute(2, 3, 0, 1).reshape(KH * KW * Co, Ci).contiguous()
 
 
-def unpack_conv_wgrad(dw, shape):
-  Co, Ci, KH, KW = shape
-  return dw.view(KH, KW, Ci, Co).permute(3, 2, 0, 1)
-
-
 # --------------------------------------------------------------------------
 # autograd Functions
 # --------------------------------------------------------------------------

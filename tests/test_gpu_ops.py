@@ -404,3 +404,69 @@ def test_conv_stride2_space_to_depth_route(N, H, W, Ci, Co):
     assert rel_err(bd.grad, br.grad) < 1e-4
   finally:
     ops.set_conv_math('fp32')
+
+
+# ---------------------------------------------------------------------------
+# full benchmark sizes (VG-128, batch 32): size-independent properties
+# ---------------------------------------------------------------------------
+
+def test_full_size_conv_tensor_core_vs_exact_fp32_kernel():
+  """CRN stage-4 conv1 at the benchmark size (32 x 128 x 128, 288 -> 64): with
+  TF32-exact operands the tcgen05 kernels (halo forward, dgrad, wgrad) must
+  reproduce the exact-fp32 FFMA kernels, which the small-size tests pin to the
+  CPU oracle.  Also linearity of the forward at full size."""
+  from sg2im_b200 import ops
+  torch.manual_seed(0)
+  N, H, W, Ci, Co = 32, 128, 128, 288, 64
+  d = dev()
+  x = _tf32_exact(torch.randn(N, H, W, Ci, device=d))
+  w = _tf32_exact(torch.randn(Co, Ci, 3, 3, device=d) * 0.05)
+  gy = _tf32_exact(torch.randn(N, H, W, Co, device=d))
+  res = {}
+  for mode in ('fp32', 'tf32'):
+    ops.set_conv_math(mode)
+    xx = x.clone().requires_grad_(True)
+    ww = w.clone().requires_grad_(True)
+    y = ops.conv2d(xx, ww, None, 1, 1)
+    y.backward(gy)
+    res[mode] = (y.detach(), xx.grad, ww.grad)
+  ops.set_conv_math('fp32')
+  for a, b, name in zip(res['tf32'], res['fp32'], ('fwd', 'dgrad', 'wgrad')):
+    assert rel_err(a, b) < 5e-5, name
+  ops.set_conv_math('tf32')
+  try:
+    x2 = _tf32_exact(torch.randn(N, H, W, Ci, device=d))
+    y1 = ops.conv2d(x, w, None, 1, 1)
+    y2 = ops.conv2d(x2, w, None, 1, 1)
+    y12 = ops.conv2d(_tf32_exact(0.5 * x + 0.25 * x2), w, None, 1, 1)
+    # 0.5*x + 0.25*x2 is TF32-exact only up to one rounding: tolerance of one TF32 ulp
+    assert rel_err(y12, 0.5 * y1 + 0.25 * y2) < 2e-3
+  finally:
+    ops.set_conv_math('fp32')
+
+
+def test_full_size_layout_linearity_and_mass():
+  """masks_to_layout at the benchmark size (O=320, N=32, D=128, 128x128): linear
+  in the object vectors; with all-ones masks and the full-image box the layout
+  equals the vector at every pixel (the bilinear weights of a constant mask sum
+  to 1 inside the box)."""
+  from sg2im_b200.layout import masks_to_layout
+  from sg2im_b200.synth import synth_config
+  (imgs, objs, boxes, triples, o2i, _), cfg = synth_config('vg128', seed=5)
+  d = dev()
+  O = objs.numel()
+  g = torch.Generator().manual_seed(1)
+  v1, v2 = torch.randn(O, 128, generator=g).to(d), torch.randn(O, 128, generator=g).to(d)
+  masks = torch.rand(O, 16, 16, generator=g).to(d)
+  b, o = boxes.to(d), o2i.to(d)
+  l1 = masks_to_layout(v1, b, masks, o, 128, 128, num_imgs=32)
+  l2 = masks_to_layout(v2, b, masks, o, 128, 128, num_imgs=32)
+  l12 = masks_to_layout(2.0 * v1 - 0.5 * v2, b, masks, o, 128, 128, num_imgs=32)
+  assert rel_err(l12, 2.0 * l1 - 0.5 * l2) < 1e-5
+  # only the __image__ objects (box [0,0,1,1], last of every image), all-ones masks
+  keep = torch.zeros(O, 1, device=d)
+  keep[9::10] = 1.0
+  lay = masks_to_layout(v1 * keep, b, torch.ones(O, 16, 16, device=d), o, 128, 128, num_imgs=32)
+  want = v1[9::10].view(32, 128, 1, 1).expand(32, 128, 128, 128)
+  inner = (slice(None), slice(None), slice(4, 124), slice(4, 124))
+  assert rel_err(lay[inner], want[inner]) < 1e-5
