@@ -178,21 +178,23 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t coun
 }
 
 // ---- y[n,Y,X,coff+c] = leaky(x[n,Y/up,X/up,c]*scale+shift) -------------------
-template <int VEC>
-__global__ void scale_act_fwd_kernel(const float* __restrict__ x, int64_t N, int64_t H, int64_t W,
-                                     int64_t C, const float* __restrict__ scale,
+// I = index type: uint32_t when every offset fits (64-bit integer division costs
+// >100 instructions per element and made these passes compute-bound)
+template <int VEC, typename I>
+__global__ void scale_act_fwd_kernel(const float* __restrict__ x, I N, I H, I W,
+                                     I C, const float* __restrict__ scale,
                                      const float* __restrict__ shift, float slope, int up,
-                                     float* __restrict__ y, int64_t ycs, int64_t yco) {
-  int64_t cg = C / VEC;
-  int64_t Ho = H * up, Wo = W * up;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                     float* __restrict__ y, I ycs, I yco) {
+  I cg = C / VEC;
+  I Ho = H * up, Wo = W * up;
+  I i = (I)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Ho * Wo * cg) return;
-  int64_t c = (i % cg) * VEC;
-  int64_t pix = i / cg;
-  int64_t X = pix % Wo;
-  int64_t t = pix / Wo;
-  int64_t Y = t % Ho;
-  int64_t n = t / Ho;
+  I c = (i % cg) * VEC;
+  I pix = i / cg;
+  I X = pix % Wo;
+  I t = pix / Wo;
+  I Y = t % Ho;
+  I n = t / Ho;
   const float* xp = x + ((n * H + Y / up) * W + X / up) * C + c;
   float* yp = y + pix * ycs + yco + c;
   if (VEC == 4) {
@@ -252,13 +254,15 @@ __device__ __forceinline__ float4 actgrad4(const ActGrad& a, int64_t m, int64_t 
   if (a.up == 1) {
     g = *reinterpret_cast<const float4*>(a.dy + m * a.dcs + a.dco + c);
   } else {
-    int64_t xx = m % a.W; int64_t t = m / a.W; int64_t yy = t % a.H; int64_t n = t / a.H;
+    // rows < 2^31 is guaranteed by the host for the float4 path: 32-bit division
+    uint32_t mm = (uint32_t)m, Wd = (uint32_t)a.W, Hd = (uint32_t)a.H;
+    uint32_t xx = mm % Wd; uint32_t t = mm / Wd; uint32_t yy = t % Hd; uint32_t n = t / Hd;
     int64_t Wo = a.W * a.up;
     g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < a.up; ++i)
       for (int j = 0; j < a.up; ++j) {
         float4 d = *reinterpret_cast<const float4*>(
-            a.dy + ((n * a.H * a.up + yy * a.up + i) * Wo + xx * a.up + j) * a.dcs + a.dco + c);
+            a.dy + (((int64_t)n * a.H * a.up + yy * a.up + i) * Wo + xx * a.up + j) * a.dcs + a.dco + c);
         g.x += d.x; g.y += d.y; g.z += d.z; g.w += d.w;
       }
   }
@@ -293,10 +297,12 @@ __global__ void scale_act_bwd_apply4_kernel(ActGrad ag, const float* __restrict_
                                             int64_t M, int64_t C, int training,
                                             const double* __restrict__ sums,
                                             float* __restrict__ dx) {
-  int64_t cg = C / 4;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * cg) return;
-  int64_t m = i / cg, c = (i - m * cg) * 4;
+  // host guarantees M * C < 2^31 on this path
+  uint32_t cg = (uint32_t)(C / 4);
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)M * cg) return;
+  uint32_t mrow = i / cg;
+  int64_t m = mrow, c = (int64_t)(i - mrow * cg) * 4;
   float4 xv;
   float4 g = actgrad4(ag, m, c, xv);
   float4 sc = ag.scale ? *reinterpret_cast<const float4*>(ag.scale + c) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -350,12 +356,14 @@ template <int VEC>
 __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int64_t xcs, int64_t xco,
                                     int64_t N, int64_t H, int64_t W, int64_t C,
                                     float* __restrict__ y, int64_t ycs, int64_t yco) {
-  int64_t cg = C / VEC, Ho = H / 2, Wo = W / 2;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * Ho * Wo * cg) return;
-  int64_t c = (i % cg) * VEC;
-  int64_t pix = i / cg;
-  int64_t X = pix % Wo; int64_t t = pix / Wo; int64_t Y = t % Ho; int64_t n = t / Ho;
+  // element counts < 2^31 (checked on the host): 32-bit index splitting
+  uint32_t cg = (uint32_t)(C / VEC), Ho = (uint32_t)(H / 2), Wo = (uint32_t)(W / 2);
+  uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= (uint32_t)N * Ho * Wo * cg) return;
+  int64_t c = (int64_t)(ii % cg) * VEC;
+  uint32_t pixu = ii / cg;
+  int64_t pix = pixu;
+  int64_t X = pixu % Wo; uint32_t tu = pixu / Wo; int64_t Y = tu % Ho; int64_t n = tu / Ho;
   const float* p00 = x + ((n * H + 2 * Y) * W + 2 * X) * xcs + xco + c;
   const float* p10 = p00 + W * xcs;
   float* yp = y + pix * ycs + yco + c;
@@ -378,12 +386,13 @@ __global__ void avgpool2_bwd_kernel(const float* __restrict__ dc, int64_t dcs, i
                                     int64_t N, int64_t H, int64_t W, int64_t C,
                                     float* __restrict__ df, int64_t dfs, int64_t dfo, int acc) {
   // (H, W) are the FINE dims
-  int64_t cg = C / VEC;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * H * W * cg) return;
-  int64_t c = (i % cg) * VEC;
-  int64_t pix = i / cg;
-  int64_t X = pix % W; int64_t t = pix / W; int64_t Y = t % H; int64_t n = t / H;
+  uint32_t cg = (uint32_t)(C / VEC);
+  uint32_t ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= (uint32_t)N * (uint32_t)H * (uint32_t)W * cg) return;
+  int64_t c = (int64_t)(ii % cg) * VEC;
+  uint32_t pixu = ii / cg;
+  int64_t pix = pixu;
+  int64_t X = pixu % (uint32_t)W; uint32_t tu = pixu / (uint32_t)W; int64_t Y = tu % (uint32_t)H; int64_t n = tu / (uint32_t)H;
   const float* cp = dc + ((n * (H / 2) + Y / 2) * (W / 2) + X / 2) * dcs + dco + c;
   float* fp = df + pix * dfs + dfo + c;
   if (VEC == 4) {
@@ -456,8 +465,14 @@ extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t
   int64_t total = N * H * up * W * up * (C / (vec ? 4 : 1));
   unsigned grid = (unsigned)ceil_div64(total, 256);
   cudaStream_t st = as_stream(stream);
-  if (vec) scale_act_fwd_kernel<4><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
-  else     scale_act_fwd_kernel<1><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+  bool small = N * H * up * W * up * y_cstride < (1ll << 31) && N * H * W * C < (1ll << 31);
+  typedef uint32_t U;
+  if (vec && small)
+    scale_act_fwd_kernel<4, U><<<grid, 256, 0, st>>>(x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff);
+  else if (vec)
+    scale_act_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+  else
+    scale_act_fwd_kernel<1, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -471,7 +486,7 @@ extern "C" int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, i
   BwdReduceF f{{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up}, save, C};
   bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
              aligned16(x) && (!scale || (aligned16(scale) && aligned16(shift))) &&
-             (!save || aligned16(save));
+             (!save || aligned16(save)) && N * H * W * C < (1ll << 31);
   if (vec) launch_colreduce4(f, N * H * W, C, sums, 2, as_stream(stream));
   else launch_colreduce(f, N * H * W, C, sums, 2, as_stream(stream));
   SG_LAUNCH_OK();
@@ -490,7 +505,8 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
   ActGrad ag{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up};
   int64_t M = N * H * W;
   bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
-             aligned16(x) && aligned16(dx) && (!scale || (aligned16(scale) && aligned16(shift)));
+             aligned16(x) && aligned16(dx) && (!scale || (aligned16(scale) && aligned16(shift))) &&
+             M * C < (1ll << 31);
   if (vec)
     scale_act_bwd_apply4_kernel<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, st>>>(
         ag, save, M, C, training, sums, dx);
@@ -508,6 +524,7 @@ extern "C" int sg2im_avgpool2_fwd(const float* x, int64_t x_cstride, int64_t x_c
                                   float* y, int64_t y_cstride, int64_t y_coff,
                                   sg2im_stream_t stream) {
   SG_ARG(x && y && N >= 1 && C >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0);
+  SG_ARG(N * H * W * C < (1ll << 31));
   bool vec = (C % 4 == 0) && (x_cstride % 4 == 0) && (x_coff % 4 == 0) && (y_cstride % 4 == 0) &&
              (y_coff % 4 == 0) && aligned16(x) && aligned16(y);
   int64_t total = N * (H / 2) * (W / 2) * (C / (vec ? 4 : 1));
@@ -524,6 +541,7 @@ extern "C" int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int6
                                   float* dfine, int64_t df_cstride, int64_t df_coff,
                                   int accumulate, sg2im_stream_t stream) {
   SG_ARG(dcoarse && dfine && N >= 1 && C >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0);
+  SG_ARG(N * H * W * C < (1ll << 31));
   bool vec = (C % 4 == 0) && (dc_cstride % 4 == 0) && (dc_coff % 4 == 0) &&
              (df_cstride % 4 == 0) && (df_coff % 4 == 0) && aligned16(dcoarse) && aligned16(dfine);
   int64_t total = N * H * W * (C / (vec ? 4 : 1));
