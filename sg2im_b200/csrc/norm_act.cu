@@ -59,19 +59,23 @@ colreduce4_kernel(F4 f, int64_t M, int64_t C, int64_t rows_per_block, double* __
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
     int cnt = 0;
     int64_t m = mb + ty;
-    for (; m + TY < me; m += 2 * TY) {
-      float4 a0, a1, b0, b1;
+    for (; m + 3 * TY < me; m += 4 * TY) {
+      float4 a0, a1, b0, b1, c0, c1, e0, e1;
       f.at4(m, c, a0, a1);
       f.at4(m + TY, c, b0, b1);
-      s0.x += a0.x + b0.x; s0.y += a0.y + b0.y; s0.z += a0.z + b0.z; s0.w += a0.w + b0.w;
-      s1.x += a1.x + b1.x; s1.y += a1.y + b1.y; s1.z += a1.z + b1.z; s1.w += a1.w + b1.w;
-      if (++cnt == 16) {
+      f.at4(m + 2 * TY, c, c0, c1);
+      f.at4(m + 3 * TY, c, e0, e1);
+      s0.x += (a0.x + b0.x) + (c0.x + e0.x); s0.y += (a0.y + b0.y) + (c0.y + e0.y);
+      s0.z += (a0.z + b0.z) + (c0.z + e0.z); s0.w += (a0.w + b0.w) + (c0.w + e0.w);
+      s1.x += (a1.x + b1.x) + (c1.x + e1.x); s1.y += (a1.y + b1.y) + (c1.y + e1.y);
+      s1.z += (a1.z + b1.z) + (c1.z + e1.z); s1.w += (a1.w + b1.w) + (c1.w + e1.w);
+      if (++cnt == 8) {
         d0[0] += s0.x; d0[1] += s0.y; d0[2] += s0.z; d0[3] += s0.w;
         d1[0] += s1.x; d1[1] += s1.y; d1[2] += s1.z; d1[3] += s1.w;
         s0 = make_float4(0.f, 0.f, 0.f, 0.f); s1 = s0; cnt = 0;
       }
     }
-    if (m < me) {
+    for (; m < me; m += TY) {
       float4 a0, a1;
       f.at4(m, c, a0, a1);
       s0.x += a0.x; s0.y += a0.y; s0.z += a0.z; s0.w += a0.w;
@@ -101,7 +105,10 @@ int launch_colreduce4(F4 f, int64_t M, int64_t C, double* sums, int nout, cudaSt
   while (TX < 32 && TX < groups) TX <<= 1;
   int64_t cblocks = ceil_div64(groups, TX);
   int TY = 256 / TX;
-  int64_t want = ceil_div64(148 * 8, cblocks);
+  // every block ends with 2*4*TX same-address fp64 atomics per channel group: with
+  // ~1200 blocks those serialised at the L2 (25 us per launch); ~2 blocks per SM keep
+  // HBM busy (4 independent 16-byte loads in flight per thread) with 4x fewer atomics
+  int64_t want = ceil_div64(148 * 2, cblocks);
   int64_t rpb = ceil_div64(M, want);
   if (rpb < 4 * TY) rpb = 4 * TY;
   int64_t rblocks = ceil_div64(M, rpb);
