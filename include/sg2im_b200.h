@@ -100,6 +100,9 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
  * stats (optional, act == 0, Cout <= 1024): caller-zeroed double[2*Cout]; the
  * epilogue adds the per-channel sum and sum of squares of the outputs — the
  * batch statistics of the BatchNorm that follows, without a second pass.
+ * round_out: write the outputs rounded to nearest TF32 (for outputs that feed another
+ * tensor-core op: the hardware truncates its fp32 operands, which biases products toward
+ * zero; RN-rounded operands are consumed exactly).
  * sg2im_conv_tc_supported(): S == 1, Cin % 4 == 0, Cout % 4 == 0, 16-byte
  * aligned slices; otherwise sg2im_conv_tc returns -2 (use sg2im_conv_igemm). */
 int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
@@ -109,7 +112,8 @@ int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
 int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                   int64_t Cin, const float* w_tc, const float* bias, int KH, int KW, int P,
                   int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope, float* y,
-                  int64_t y_cstride, int64_t y_coff, double* stats, sg2im_stream_t stream);
+                  int64_t y_cstride, int64_t y_coff, double* stats, int round_out,
+                  sg2im_stream_t stream);
 
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
@@ -150,7 +154,7 @@ int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W, int64_t C,
  * unpack: dw[t][ci][co] (sg2im_conv_wgrad[_tc] output) -> grad_oihw[co][ci][t]
  *         (= or += when accumulate). */
 int sg2im_pack_weights(const float* w, int64_t Cout, int64_t Cin, int64_t cin_use, int64_t taps,
-                       float* w_fwd, float* w_dgrad, sg2im_stream_t stream);
+                       float* w_fwd, float* w_dgrad, int round_tf32, sg2im_stream_t stream);
 int sg2im_unpack_wgrad(const float* dw, int64_t Cout, int64_t Cin, int64_t cin_use, int64_t taps,
                        float* grad_oihw, int accumulate, sg2im_stream_t stream);
 
@@ -176,7 +180,8 @@ int sg2im_act_bwd(const float* dy, const float* y, float slope, int64_t n,
  *              (unbias_mult = 4 when BN follows a x2 upsample: same mean/var,
  *              4x the elements).  training=0: scale/shift from running stats.
  *              save[0:C]=mean, save[C:2C]=invstd.  gamma/beta NULL => 1/0.
- * scale_act_fwd: y[n,Y,X,coff+c] = leaky(x[n,Y/up,X/up,c]*scale[c]+shift[c]);
+ * scale_act_fwd: y[n,Y,X,coff+c] = leaky(x[n,Y/up,X/up,c]*scale[c]+shift[c])
+ *              (rounded to nearest TF32 when round_tf32: the consumer is a tensor-core conv);
  *              scale NULL => identity affine; slope 1 => no activation.
  */
 int sg2im_bn_stats(const float* x, int64_t M, int64_t C, double* sums,
@@ -187,7 +192,7 @@ int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbias_mult, in
                       float* scale, float* shift, float* save, sg2im_stream_t stream);
 int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
                         const float* scale, const float* shift, float slope, int up,
-                        float* y, int64_t y_cstride, int64_t y_coff,
+                        float* y, int64_t y_cstride, int64_t y_coff, int round_tf32,
                         sg2im_stream_t stream);
 /* Backward of scale_act_fwd given dy on the (upsampled, sliced) output.
  * reduce: with g = leaky'(x*scale+shift) * sum_{up x up} dy,
@@ -234,7 +239,7 @@ int sg2im_layout_fwd(const float* vecs, const float* boxes, const float* masks, 
                      int align_corners,
                      const float* noise, int64_t noise_c, int64_t nsn, int64_t nsc,
                      int64_t nsh, int64_t nsw,
-                     float* out, int64_t out_cstride, sg2im_stream_t stream);
+                     float* out, int64_t out_cstride, int round_tf32, sg2im_stream_t stream);
 /* dvecs[o,d] += sum_hw dout[n,h,w,d]*S_o(h,w);  dmasks[o,my,mx] += bilinear
  * scatter of dS_o(h,w) = sum_d dout[n,h,w,d]*vecs[o,d].  Both zero-initialised
  * by the caller; dmasks may be NULL. */

@@ -26,12 +26,12 @@ SIGNATURES = {
   'sg2im_conv_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64, _i64,
                               _i64, _i64, _i64],
   'sg2im_conv_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _int, _int, _i64, _i64,
-                    _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _ptr],
+                    _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_conv_wgrad_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64,
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,
                           _i64, _ptr, _ptr],
-  'sg2im_pack_weights': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr],
+  'sg2im_pack_weights': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr],
   'sg2im_unpack_wgrad': [_ptr, _i64, _i64, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_s2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
   'sg2im_s2d_bwd': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr],
@@ -43,7 +43,7 @@ SIGNATURES = {
   'sg2im_bn_finalize': [_ptr, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr,
                         _ptr, _ptr, _ptr, _ptr],
   'sg2im_scale_act_fwd': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _int, _ptr, _i64,
-                          _i64, _ptr],
+                          _i64, _int, _ptr],
   'sg2im_scale_act_bwd_reduce': [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr,
                                  _ptr, _f32, _int, _ptr, _ptr],
   'sg2im_scale_act_bwd_apply': [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr,
@@ -51,7 +51,7 @@ SIGNATURES = {
   'sg2im_avgpool2_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr],
   'sg2im_avgpool2_bwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _ptr],
   'sg2im_layout_fwd': [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
-                       _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr],
+                       _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr],
   'sg2im_layout_bwd': [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64,
                        _int, _ptr, _ptr, _ptr],
   'sg2im_crop_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64,

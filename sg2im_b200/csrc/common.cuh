@@ -30,6 +30,16 @@ static inline cudaStream_t as_stream(sg2im_stream_t s) { return (cudaStream_t)s;
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// Round-to-nearest TF32 (10-bit mantissa, low 13 bits cleared).  The tensor core
+// TRUNCATES the fp32 words it is fed, which biases every product toward zero;
+// operands written through this are consumed exactly, so the only error left is
+// this unbiased rounding (what cuBLAS/cuDNN TF32 paths do with cvt.rna).
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
 // Bilinear sampling footprint of one normalised coordinate g in [-1,1] on an
 // axis of `size` texels (torch grid_sample, zeros padding): lower texel index
 // and the weight of the upper texel.

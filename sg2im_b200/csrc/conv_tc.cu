@@ -39,6 +39,7 @@ struct TcParams {
   int act; float slope;
   float* y; long long y_cstride, y_coff;
   double* stats;                   // optional [2*Cout] per-channel sum / sum of squares
+  int round_out;                   // write RN-TF32 values (output feeds another tensor-core op)
 };
 
 using namespace tc;
@@ -183,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
         tc_ld32(taddr + ch * 32, v);
         epilogue_chunk(v, valid, nt * BN + ch * 32, p.Cout, p.bias, p.act, p.slope, yrow + ch * 32,
-                       p.stats ? s_part : nullptr, lane);
+                       p.stats ? s_part : nullptr, lane, p.round_out);
       }
       tc_fence_before();
       __syncwarp();
@@ -243,6 +244,7 @@ struct HaloParams {
   int act; float slope;
   float* y; long long y_cstride, y_coff;
   double* stats;
+  int round_out;
 };
 
 __global__ void __launch_bounds__(H_THREADS, 1)
@@ -409,7 +411,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[32];
           tc_ld32(taddr + ch * 32, v);
           epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
-                         yrow + ch * 32, p.stats ? s_part : nullptr, lane);
+                         yrow + ch * 32, p.stats ? s_part : nullptr, lane, p.round_out);
         }
       }
       tc_fence_before();
@@ -484,7 +486,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                              int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
                              int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
                              int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
-                             double* stats, sg2im_stream_t stream) {
+                             double* stats, int round_out, sg2im_stream_t stream) {
   SG_ARG(x && w_tc && y);
   if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
                                y_cstride, y_coff)) {
@@ -497,7 +499,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
   if (!enc) { sg2im_set_error("sg2im_conv_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
 
   TcParams p;
-  p.stats = stats;
+  p.stats = stats; p.round_out = round_out;
   p.N = (int)N; p.Hout = (int)Hout; p.Wout = (int)Wout;
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
   tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
@@ -533,7 +535,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
     h.a_bytes = (uint32_t)((H_BH + KH - 1) * h.pitch * 128);
     h.bias = bias; h.act = act; h.slope = slope;
     h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
-    h.stats = stats;
+    h.stats = stats; h.round_out = round_out;
     CUtensorMap hA, hB;
     {
       cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};

@@ -59,7 +59,8 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxe
                   const float* __restrict__ masks, int M, const int32_t* __restrict__ img_ptr,
                   const int32_t* __restrict__ img_ent, int64_t N, int D, int H, int W,
                   int align, const float* __restrict__ noise, int noise_c, int64_t nsn,
-                  int64_t nsc, int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs) {
+                  int64_t nsc, int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs,
+                  int rnd) {
   extern __shared__ __align__(16) float lsm[];
   float* sS = lsm;                               // [LF_OBJ][LF_PIX]
   float* sV = lsm + LF_OBJ * LF_PIX;             // [LF_OBJ][D]
@@ -124,7 +125,9 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxe
     int idx = t + k * LF_THREADS;
     if (idx < nout) {
       int pp = idx / G, g = idx - pp * G;
-      *reinterpret_cast<float4*>(orow + (int64_t)pp * ocs + g * 4) = acc[k];
+      float4 o = acc[k];
+      if (rnd) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
+      *reinterpret_cast<float4*>(orow + (int64_t)pp * ocs + g * 4) = o;
     }
   }
   if (noise) {
@@ -140,7 +143,10 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxe
       __syncthreads();
       for (int i = t; i < 32 * LF_PIX; i += LF_THREADS) {
         int pp = i / 32, c = i - pp * 32;
-        if (cb + c < noise_c && pp < npx) orow[(int64_t)pp * ocs + D + cb + c] = sN[pp * 33 + c];
+        if (cb + c < noise_c && pp < npx) {
+          float v = sN[pp * 33 + c];
+          orow[(int64_t)pp * ocs + D + cb + c] = rnd ? tf32_rn(v) : v;
+        }
       }
     }
   }
@@ -286,7 +292,8 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
                                 int64_t N, int64_t O, int64_t D, int64_t H, int64_t W,
                                 int align_corners, const float* noise, int64_t noise_c,
                                 int64_t nsn, int64_t nsc, int64_t nsh, int64_t nsw,
-                                float* out, int64_t out_cstride, sg2im_stream_t stream) {
+                                float* out, int64_t out_cstride, int round_tf32,
+                                sg2im_stream_t stream) {
   SG_ARG(vecs && boxes && img_row_ptr && img_entries && out);
   SG_ARG(N >= 1 && O >= 1 && D >= 1 && H >= 1 && W >= 1);
   if (!masks) M = 8;
@@ -307,7 +314,7 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
     layout_fwd_kernel<<<grid, LF_THREADS, smem, st>>>(vecs, boxes, masks, (int)M, img_row_ptr,
                                                       img_entries, N, (int)D, (int)H, (int)W,
                                                       align_corners, noise, (int)noise_c, nsn, nsc,
-                                                      nsh, nsw, out, out_cstride);
+                                                      nsh, nsw, out, out_cstride, round_tf32);
   } else {
     int64_t total = N * H * W * ctot;
     layout_fwd_scalar_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(

@@ -191,7 +191,7 @@ template <int VEC, typename I>
 __global__ void scale_act_fwd_kernel(const float* __restrict__ x, I N, I H, I W,
                                      I C, const float* __restrict__ scale,
                                      const float* __restrict__ shift, float slope, int up,
-                                     float* __restrict__ y, I ycs, I yco) {
+                                     float* __restrict__ y, I ycs, I yco, int rnd) {
   I cg = C / VEC;
   I Ho = H * up, Wo = W * up;
   I i = (I)blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,11 +214,13 @@ __global__ void scale_act_fwd_kernel(const float* __restrict__ x, I N, I H, I W,
     }
     v.x = leaky(v.x, slope); v.y = leaky(v.y, slope);
     v.z = leaky(v.z, slope); v.w = leaky(v.w, slope);
+    if (rnd) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
     *reinterpret_cast<float4*>(yp) = v;
   } else {
     float v = xp[0];
     if (scale) v = fmaf(v, scale[c], shift[c]);
-    yp[0] = leaky(v, slope);
+    v = leaky(v, slope);
+    yp[0] = rnd ? tf32_rn(v) : v;
   }
 }
 
@@ -462,7 +464,7 @@ extern "C" int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbi
 
 extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
                                    const float* scale, const float* shift, float slope, int up,
-                                   float* y, int64_t y_cstride, int64_t y_coff,
+                                   float* y, int64_t y_cstride, int64_t y_coff, int round_tf32,
                                    sg2im_stream_t stream) {
   SG_ARG(x && y && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
   SG_ARG((scale == nullptr) == (shift == nullptr));
@@ -475,11 +477,11 @@ extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t
   bool small = N * H * up * W * up * y_cstride < (1ll << 31) && N * H * W * C < (1ll << 31);
   typedef uint32_t U;
   if (vec && small)
-    scale_act_fwd_kernel<4, U><<<grid, 256, 0, st>>>(x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff);
+    scale_act_fwd_kernel<4, U><<<grid, 256, 0, st>>>(x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff, round_tf32);
   else if (vec)
-    scale_act_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+    scale_act_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
   else
-    scale_act_fwd_kernel<1, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff);
+    scale_act_fwd_kernel<1, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
   SG_LAUNCH_OK();
   return 0;
 }

@@ -16,7 +16,7 @@ constexpr int PT = 32;          // 32 x 32 (co x ci) tile, all taps
 template <int TT>
 __global__ void __launch_bounds__(256)
 pack_oihw_kernel(const float* __restrict__ w, int Co, int Ci, int CiUse, int Trt,
-                 float* __restrict__ fwd, float* __restrict__ dgr) {
+                 float* __restrict__ fwd, float* __restrict__ dgr, int rnd) {
   extern __shared__ float sm[];                 // [PT co][PT * T + 1]
   const int T = TT ? TT : Trt;
   const int ld = PT * T + 1;
@@ -26,7 +26,10 @@ pack_oihw_kernel(const float* __restrict__ w, int Co, int Ci, int CiUse, int Trt
   // coalesced read: for each co a run of nci*T contiguous floats
   for (int i = threadIdx.x; i < PT * run; i += 256) {
     int c = i / run, r = i - c * run;
-    if (c < nco && r < nci * T) sm[c * ld + r] = w[((size_t)(co0 + c) * Ci + ci0) * T + r];
+    if (c < nco && r < nci * T) {
+      float v = w[((size_t)(co0 + c) * Ci + ci0) * T + r];
+      sm[c * ld + r] = rnd ? tf32_rn(v) : v;
+    }
   }
   __syncthreads();
   if (fwd) {
@@ -72,13 +75,13 @@ unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci, int CiUse, int
 
 template <int TT>
 void launch_pack(dim3 grid, size_t smem, cudaStream_t st, const float* w, int Co, int Ci, int cu,
-                 int T, float* f, float* d) {
+                 int T, float* f, float* d, int rnd) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(pack_oihw_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  pack_oihw_kernel<TT><<<grid, 256, smem, st>>>(w, Co, Ci, cu, T, f, d);
+  pack_oihw_kernel<TT><<<grid, 256, smem, st>>>(w, Co, Ci, cu, T, f, d, rnd);
 }
 template <int TT>
 void launch_unpack(dim3 grid, size_t smem, cudaStream_t st, const float* dw, int Co, int Ci, int cu,
@@ -93,7 +96,7 @@ void launch_unpack(dim3 grid, size_t smem, cudaStream_t st, const float* dw, int
 }  // namespace
 
 extern "C" int sg2im_pack_weights(const float* w, int64_t Cout, int64_t Cin, int64_t cin_use,
-                                  int64_t taps, float* w_fwd, float* w_dgrad,
+                                  int64_t taps, float* w_fwd, float* w_dgrad, int round_tf32,
                                   sg2im_stream_t stream) {
   SG_ARG(w && (w_fwd || w_dgrad));
   SG_ARG(Cout >= 1 && Cin >= 1 && cin_use >= 1 && cin_use <= Cin && taps >= 1 && taps <= 64);
@@ -102,11 +105,11 @@ extern "C" int sg2im_pack_weights(const float* w, int64_t Cout, int64_t Cin, int
   cudaStream_t st = as_stream(stream);
   int Co = (int)Cout, Ci = (int)Cin, cu = (int)cin_use, T = (int)taps;
   switch (T) {
-    case 1: launch_pack<1>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad); break;
-    case 4: launch_pack<4>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad); break;
-    case 9: launch_pack<9>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad); break;
-    case 16: launch_pack<16>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad); break;
-    default: launch_pack<0>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad); break;
+    case 1: launch_pack<1>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad, round_tf32); break;
+    case 4: launch_pack<4>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad, round_tf32); break;
+    case 9: launch_pack<9>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad, round_tf32); break;
+    case 16: launch_pack<16>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad, round_tf32); break;
+    default: launch_pack<0>(grid, smem, st, w, Co, Ci, cu, T, w_fwd, w_dgrad, round_tf32); break;
   }
   SG_LAUNCH_OK();
   return 0;

@@ -164,7 +164,8 @@ __device__ __forceinline__ float warp_colsum32(const float* v, int lane) {
 // the BatchNorm that follows) -> LeakyReLU -> 128-bit stores.
 __device__ __forceinline__ void epilogue_chunk(float* v, bool valid, int col0, int Cout,
                                                const float* bias, int act, float slope,
-                                               float* yrow, float* s_part, int lane) {
+                                               float* yrow, float* s_part, int lane,
+                                               int rnd = 0) {
   const float* brow = bias ? bias + col0 : nullptr;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -195,6 +196,7 @@ __device__ __forceinline__ void epilogue_chunk(float* v, bool valid, int col0, i
         o.x = leaky(o.x, slope); o.y = leaky(o.y, slope);
         o.z = leaky(o.z, slope); o.w = leaky(o.w, slope);
       }
+      if (rnd) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
       *reinterpret_cast<float4*>(yrow + j) = o;
     }
   }

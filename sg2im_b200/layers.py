@@ -51,7 +51,7 @@ class Conv2d(nn.Conv2d):
 
 
 class Linear(nn.Linear):
-  def forward_act(self, x, act=0, slope=0.0):
+  def forward_act(self, x, act=0, slope=0.0, round_out=False):
     lead = x.shape[:-1]
     x2 = x.reshape(-1, x.size(-1))
     nout = self.out_features
@@ -64,7 +64,7 @@ class Linear(nn.Linear):
       b = None if self.bias is None else torch.nn.functional.pad(self.bias, (0, pad))
       y = ops.linear(x2, w, b, act, slope)[:, :nout]
     else:
-      y = ops.linear(x2, self.weight, self.bias, act, slope)
+      y = ops.linear(x2, self.weight, self.bias, act, slope, round_out)
     return y.reshape(*lead, nout)
 
   def forward(self, x):
@@ -211,7 +211,9 @@ class FusedSequential(nn.Sequential):
           h = m.forward_nhwc(h, feeds_bn=fb, stats_out=sums); i += 1
       elif isinstance(m, Linear) and not four_d:
         if s is not None:
-          h = m.forward_act(h, 1, s); i += 2
+          # the next Linear of the MLP consumes this output on the tensor core
+          feeds_gemm = i + 2 < len(mods) and isinstance(mods[i + 2], Linear)
+          h = m.forward_act(h, 1, s, round_out=feeds_gemm); i += 2
         else:
           h = m.forward_act(h); i += 1
       elif isinstance(m, BatchNorm2d) and four_d:

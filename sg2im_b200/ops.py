@@ -163,7 +163,7 @@ def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
 
 
 def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
-            tag='conv_fwd_tc', out_hw=None, stats=None):
+            tag='conv_fwd_tc', out_hw=None, stats=None, round_out=False):
   """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
   w_tc packed [KH*KW][Cout][Cin]; out_hw: explicit output size (reads outside
   the input are zero)."""
@@ -174,7 +174,8 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
   with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
     _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Hout, Wout,
-          Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _p(stats), _stream())
+          Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _p(stats),
+          int(round_out), _stream())
   _count()
   return out
 
@@ -184,12 +185,10 @@ def _pack(weight, cin_use, want_fwd):
   Co, Ci, KH, KW = weight.shape
   T = KH * KW
   cu = Ci if cin_use is None else cin_use
-  if want_fwd and T == 1 and cu == Ci:
-    return weight.view(1, Co, Ci)                       # a Linear is already [1][Cout][Cin]
   out = torch.empty((T, Co, cu) if want_fwd else (T, cu, Co), dtype=torch.float32,
                     device=weight.device)
   _call('sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(out) if want_fwd else None,
-        None if want_fwd else _p(out), _stream())
+        None if want_fwd else _p(out), 1, _stream())     # RN-TF32: the tensor core would truncate
   _count()
   return out
 
@@ -284,7 +283,7 @@ def scale_act_fwd(x, scale, shift, slope, up, out=None, out_coff=0):
   if out is None:
     out = torch.empty(N, H * up, W * up, C, dtype=torch.float32, device=x.device)
   _call('sg2im_scale_act_fwd', _p(x), N, H, W, C, _p(scale), _p(shift), float(slope), up,
-        _p(out), out.size(3), out_coff, _stream())
+        _p(out), out.size(3), out_coff, int(CONV_MATH == 'tf32'), _stream())
   _count()
   return out
 
@@ -354,7 +353,7 @@ class Conv(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, weight, bias, stride, pad, act, slope, in_ch, out_hw=None,
-              zero_bias_grad=False, stats_out=None):
+              zero_bias_grad=False, stats_out=None, round_out=False):
     _chk(weight, name='weight')
     Co, Ci_w, KH, KW = weight.shape
     Ci = Ci_w if in_ch is None else in_ch
@@ -369,7 +368,8 @@ class Conv(torch.autograd.Function):
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
     if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
       y = conv_tc(x, pack_tc_fwd(weight, Ci), bias, KH, KW, pad, Co, act, slope,
-                  out_hw=(Hout, Wout), stats=stats_out if fused_stats else None)
+                  out_hw=(Hout, Wout), stats=stats_out if fused_stats else None,
+                  round_out=round_out)
     else:
       fused_stats = False
       y = conv_igemm(0, x, pack_conv_fwd(w_used), bias, KH, KW, stride, pad, (Hout, Wout), Co,
@@ -414,7 +414,7 @@ class Conv(torch.autograd.Function):
         db = torch.zeros(Co, dtype=torch.float32, device=dy.device)
       else:
         db = colsum(dy.view(-1, Co))
-    return dx, dw, db, None, None, None, None, None, None, None, None
+    return dx, dw, db, None, None, None, None, None, None, None, None, None
 
 
 class S2D(torch.autograd.Function):
@@ -460,11 +460,12 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out)
 
 
-def linear(x2d, weight, bias, act=0, slope=0.0):
-  """nn.Linear (+ fused ReLU/LeakyReLU) as a 1x1 convolution over rows."""
+def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
+  """nn.Linear (+ fused ReLU/LeakyReLU) as a 1x1 convolution over rows.
+  round_out: the output feeds another tensor-core GEMM (hand over RN-TF32 values)."""
   M, K = x2d.shape
   y = Conv.apply(x2d.reshape(M, 1, 1, K), weight.view(weight.size(0), K, 1, 1), bias,
-                 1, 0, act, slope, None)
+                 1, 0, act, slope, None, None, False, None, bool(round_out) and CONV_MATH == 'tf32')
   return y.view(M, weight.size(0))
 
 
@@ -604,7 +605,8 @@ class Layout(torch.autograd.Function):
     return dvecs, None, dmasks, None, None, None, None, None, None
 
 
-def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, out):
+def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, out,
+                   round_tf32=False):
   O, D = vecs.shape
   M = 0 if masks is None else masks.size(1)
   img_ptr, img_ent = csr_build(obj_to_img, 1, N)
@@ -612,7 +614,7 @@ def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners
   ns = (0, 0, 0, 0) if noise is None else noise.stride()      # (n, c, h, w)
   _call('sg2im_layout_fwd', _p(vecs), _p(boxes), _p(masks), M, _p(img_ptr), _p(img_ent), N, O,
         D, H, W, int(align_corners), _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
-        out.size(3), _stream())
+        out.size(3), int(round_tf32), _stream())
   _count()
 
 
@@ -640,7 +642,8 @@ class LayoutStack(torch.autograd.Function):
     dev = vecs.device
     bufs = [None] * L
     bufs[L - 1] = torch.empty(N, H, W, C + extras[L - 1], dtype=torch.float32, device=dev)
-    _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, bufs[L - 1])
+    _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, bufs[L - 1],
+                   round_tf32=CONV_MATH == 'tf32')
     for k in range(L - 2, -1, -1):
       f = L - 1 - k
       bufs[k] = torch.empty(N, H >> f, W >> f, C + extras[k], dtype=torch.float32, device=dev)
