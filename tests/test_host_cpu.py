@@ -139,3 +139,27 @@ def test_losses_match_oracle():
   assert torch.allclose(losses.gan_d_loss(r, f), orc.gan_d_loss(r, f))
   with pytest.raises(ValueError):
     losses.get_gan_losses('nope')
+
+
+def test_bench_reference_arm_contract():
+  """`bench.py --impl reference` (the CPU port of the reference step on the host
+  cores) prints one JSON line with the contract's keys; tiny workload so it runs
+  in seconds.  Under torchrun only rank 0 prints (covered by the same code path:
+  RANK != 0 returns immediately)."""
+  import json
+  import subprocess
+  import sys
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                        '--workload', 'tiny32', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+  assert out.returncode == 0, out.stderr[-2000:]
+  line = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+  assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['value'] > 0
+  assert line['higher_is_better'] is True and line['vs_baseline'] is None
+  assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+  assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['value'] == line['value']
+  env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                        '--workload', 'tiny32', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+  assert out.returncode == 0 and out.stdout.strip() == ''
