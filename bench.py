@@ -263,7 +263,9 @@ def run_b200(args, cfg):
       ms = float(t.item())
     return ms, n_launch, last
 
-  timed(max(args.warmup, 5 if not args.no_graph else args.warmup), False)   # warm-up (untimed; incl. graph capture)
+  if step.cuda_graph:
+    timed(4, False)                                      # setup: 3 eager iterations + graph capture
+  timed(args.warmup, False)                              # the W untimed warm-up steps
   sampler = ClockSampler(local)
   sampler.start()
   ms, launches, last = timed(args.steps, False)
@@ -336,6 +338,8 @@ def run_b200(args, cfg):
                    'triples_per_gpu': int(resident[0][-3].size(0)),
                    'image_size': list(cfg['image_size']), 'global_batch': cfg['N'] * world,
                    'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph),
+                   'setup': '4 untimed iterations before the warm-up (3 eager + CUDA-graph capture)'
+                            if step.cuda_graph else 'none',
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
                          'no explicit flush'},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
