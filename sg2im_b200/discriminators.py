@@ -1,82 +1,83 @@
-"""Image and object discriminators — reference surface of
-sg2im/discriminators.py (same constructor arguments, module tree and
-state_dict keys) on the sm_100a conv / crop kernels."""
-import torch
-import torch.nn as nn
-import torch.nn.functional as F
+"""Discriminators of the sg2im training step on the sm_100a kernels.
 
+Public surface (constructor arguments, forward signatures, module tree and
+therefore ``state_dict`` keys) is the reference's ``sg2im/discriminators.py``:
+
+  PatchDiscriminator(arch, ...)(x, layout=None)            -> feature map (N, C, h, w)
+  AcDiscriminator(vocab, arch, ...)(x, y)                  -> (real_scores, ac_loss)
+  AcCropDiscriminator(vocab, arch, ..., object_size)(imgs, objs, boxes, obj_to_img)
+
+The conv stacks come from ``layers.build_cnn`` (tcgen05 convolutions via the
+space-to-depth route for the 4x4 stride-2 layers, fused BatchNorm statistics /
+LeakyReLU), the per-object crops from the single-launch crop kernel.
+"""
+import torch
+from torch import nn
+from torch.nn.functional import cross_entropy
+
+from . import layers
 from .bilinear import crop_bbox_batch
-from .layers import GlobalAvgPool, Flatten, get_activation, build_cnn, Conv2d, Linear
+
+_HEAD_WIDTH = 1024          # width of the object discriminator's embedding (discriminators.py:62)
+
+
+def _conv_stack(arch, normalization, activation, padding, pooling):
+  """-> (FusedSequential, output channels); thin wrapper so both discriminators
+  build their trunk the same way."""
+  return layers.build_cnn(arch=arch, normalization=normalization, activation=activation,
+                          padding=padding, pooling=pooling)
 
 
 class PatchDiscriminator(nn.Module):
-  """sg2im/discriminators.py:25-45.  As in the reference, ``classifier`` is
-  constructed (it lives in the state_dict) but never applied by forward."""
+  """Image discriminator: a conv trunk whose whole output map is scored by the GAN
+  loss.  Like the reference (discriminators.py:40-45) a 1x1 ``classifier`` is
+  created — it is part of every checkpoint — but never applied."""
 
   def __init__(self, arch, normalization='batch', activation='leakyrelu-0.2',
-               padding='same', pooling='avg', input_size=(128, 128),
-               layout_dim=0):
-    super(PatchDiscriminator, self).__init__()
-    input_dim = 3 + layout_dim
-    arch = 'I%d,%s' % (input_dim, arch)
-    cnn_kwargs = {
-      'arch': arch,
-      'normalization': normalization,
-      'activation': activation,
-      'pooling': pooling,
-      'padding': padding,
-    }
-    self.cnn, output_dim = build_cnn(**cnn_kwargs)
-    self.classifier = Conv2d(output_dim, 1, kernel_size=1, stride=1)
+               padding='same', pooling='avg', input_size=(128, 128), layout_dim=0):
+    super().__init__()
+    trunk_arch = 'I%d,%s' % (3 + layout_dim, arch)           # RGB (+ optional layout channels)
+    self.cnn, width = _conv_stack(trunk_arch, normalization, activation, padding, pooling)
+    self.classifier = layers.Conv2d(width, 1, kernel_size=1, stride=1)
 
   def forward(self, x, layout=None):
-    if layout is not None:
-      x = torch.cat([x, layout], dim=1)
-    return self.cnn(x)
+    inp = x if layout is None else torch.cat([x, layout], dim=1)
+    return self.cnn(inp)
 
 
 class AcDiscriminator(nn.Module):
-  """sg2im/discriminators.py:48-75."""
+  """Auxiliary-classifier discriminator on object crops: trunk -> global average
+  pool -> Linear(D, 1024) -> {real/fake logit, object-class logits}."""
 
   def __init__(self, vocab, arch, normalization='none', activation='relu',
                padding='same', pooling='avg'):
-    super(AcDiscriminator, self).__init__()
+    super().__init__()
     self.vocab = vocab
-    cnn_kwargs = {
-      'arch': arch,
-      'normalization': normalization,
-      'activation': activation,
-      'pooling': pooling,
-      'padding': padding,
-    }
-    cnn, D = build_cnn(**cnn_kwargs)
-    self.cnn = nn.Sequential(cnn, GlobalAvgPool(), Linear(D, 1024))
-    num_objects = len(vocab['object_idx_to_name'])
-    self.real_classifier = Linear(1024, 1)
-    self.obj_classifier = Linear(1024, num_objects)
+    trunk, width = _conv_stack(arch, normalization, activation, padding, pooling)
+    # indices 0 / 2 of this Sequential carry parameters: keys cnn.0.*, cnn.2.*
+    self.cnn = nn.Sequential(trunk, layers.GlobalAvgPool(), layers.Linear(width, _HEAD_WIDTH))
+    self.real_classifier = layers.Linear(_HEAD_WIDTH, 1)
+    self.obj_classifier = layers.Linear(_HEAD_WIDTH, len(vocab['object_idx_to_name']))
 
   def forward(self, x, y):
-    if x.dim() == 3:
-      x = x[:, None]
-    vecs = self.cnn(x)
-    real_scores = self.real_classifier(vecs)
-    obj_scores = self.obj_classifier(vecs)
-    ac_loss = F.cross_entropy(obj_scores, y)
-    return real_scores, ac_loss
+    crops = x.unsqueeze(1) if x.dim() == 3 else x            # single-channel crops without a C axis
+    embedding = self.cnn(crops)
+    class_logits = self.obj_classifier(embedding)
+    return self.real_classifier(embedding), cross_entropy(class_logits, y)
 
 
 class AcCropDiscriminator(nn.Module):
-  """sg2im/discriminators.py:78-90."""
+  """Crops every object's box out of its image (bilinear, ``object_size`` square)
+  and scores the crops with an AcDiscriminator."""
 
   def __init__(self, vocab, arch, normalization='none', activation='relu',
                object_size=64, padding='same', pooling='avg'):
-    super(AcCropDiscriminator, self).__init__()
+    super().__init__()
     self.vocab = vocab
-    self.discriminator = AcDiscriminator(vocab, arch, normalization,
-                                         activation, padding, pooling)
     self.object_size = object_size
+    self.discriminator = AcDiscriminator(vocab, arch, normalization, activation, padding,
+                                         pooling)
 
   def forward(self, imgs, objs, boxes, obj_to_img):
-    crops = crop_bbox_batch(imgs, boxes, obj_to_img, self.object_size)
-    real_scores, ac_loss = self.discriminator(crops, objs)
-    return real_scores, ac_loss
+    object_crops = crop_bbox_batch(imgs, boxes, obj_to_img, self.object_size)
+    return self.discriminator(object_crops, objs)

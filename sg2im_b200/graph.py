@@ -30,24 +30,24 @@ class GraphCSR(object):
 
 
 class GraphTripleConv(nn.Module):
-  """A single layer of scene graph convolution (sg2im/graph.py:32-120)."""
+  """One scene-graph convolution layer (sg2im/graph.py:32-120): per triple an MLP
+  over [subject | predicate | object] produces candidate subject / object vectors
+  (hidden_dim wide) and the new predicate vector; candidates are pooled per
+  object; a second MLP maps the pooled vectors to the new object vectors."""
 
   def __init__(self, input_dim, output_dim=None, hidden_dim=512,
                pooling='avg', mlp_normalization='none'):
-    super(GraphTripleConv, self).__init__()
-    if output_dim is None:
-      output_dim = input_dim
-    self.input_dim = input_dim
-    self.output_dim = output_dim
-    self.hidden_dim = hidden_dim
+    super().__init__()
     assert pooling in ['sum', 'avg'], 'Invalid pooling "%s"' % pooling
-    self.pooling = pooling
-    net1_layers = [3 * input_dim, hidden_dim, 2 * hidden_dim + output_dim]
-    self.net1 = build_mlp(net1_layers, batch_norm=mlp_normalization)
-    self.net1.apply(_init_weights)
-    net2_layers = [hidden_dim, hidden_dim, output_dim]
-    self.net2 = build_mlp(net2_layers, batch_norm=mlp_normalization)
-    self.net2.apply(_init_weights)
+    self.input_dim = input_dim
+    self.output_dim = input_dim if output_dim is None else output_dim
+    self.hidden_dim, self.pooling = hidden_dim, pooling
+    widths = {'net1': [3 * input_dim, hidden_dim, 2 * hidden_dim + self.output_dim],
+              'net2': [hidden_dim, hidden_dim, self.output_dim]}
+    for name in ('net1', 'net2'):                  # registration order = state_dict order
+      mlp = build_mlp(widths[name], batch_norm=mlp_normalization)
+      mlp.apply(_init_weights)
+      setattr(self, name, mlp)
 
   def forward(self, obj_vecs, pred_vecs, edges, csr=None):
     """obj_vecs (O, Din), pred_vecs (T, Din), edges int64 (T, 2) ->

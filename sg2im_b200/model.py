@@ -12,6 +12,10 @@ from .layers import build_mlp, Conv2d, BatchNorm2d, Linear, Upsample, ReLU, Fuse
 
 
 class Sg2ImModel(nn.Module):
+  """Scene graph -> image generator.  Constructor keywords, sub-module names and
+  parameter shapes follow sg2im/model.py:30-92 (checkpoints are interchangeable);
+  unknown keywords only warn, as there."""
+
   def __init__(self, vocab, image_size=(64, 64), embedding_dim=64,
                gconv_dim=128, gconv_hidden_dim=512,
                gconv_pooling='avg', gconv_num_layers=5,
@@ -19,62 +23,50 @@ class Sg2ImModel(nn.Module):
                normalization='batch', activation='leakyrelu-0.2',
                mask_size=None, mlp_normalization='none', layout_noise_dim=0,
                **kwargs):
-    super(Sg2ImModel, self).__init__()
+    super().__init__()
+    if kwargs:
+      print('WARNING: Model got unexpected kwargs ', kwargs)
 
-    if len(kwargs) > 0:
-      print('WARNING: Model got unexpected kwargs ', kwargs)     # model.py:41-42
+    self.vocab, self.image_size, self.layout_noise_dim = vocab, image_size, layout_noise_dim
+    n_obj_classes = len(vocab['object_idx_to_name'])
+    n_predicates = len(vocab['pred_idx_to_name'])
 
-    self.vocab = vocab
-    self.image_size = image_size
-    self.layout_noise_dim = layout_noise_dim
+    # category / predicate embeddings (one spare object row, as in the reference)
+    self.obj_embeddings = nn.Embedding(n_obj_classes + 1, embedding_dim)
+    self.pred_embeddings = nn.Embedding(n_predicates, embedding_dim)
 
-    num_objs = len(vocab['object_idx_to_name'])
-    num_preds = len(vocab['pred_idx_to_name'])
-    self.obj_embeddings = nn.Embedding(num_objs + 1, embedding_dim)
-    self.pred_embeddings = nn.Embedding(num_preds, embedding_dim)
+    # graph convolution: first layer maps embedding_dim -> gconv_dim, the rest keep gconv_dim
+    shared = dict(hidden_dim=gconv_hidden_dim, pooling=gconv_pooling,
+                  mlp_normalization=mlp_normalization)
+    self.gconv = (Linear(embedding_dim, gconv_dim) if gconv_num_layers == 0 else
+                  GraphTripleConv(input_dim=embedding_dim, output_dim=gconv_dim, **shared)
+                  if gconv_num_layers > 0 else None)
+    self.gconv_net = (GraphTripleConvNet(input_dim=gconv_dim, num_layers=gconv_num_layers - 1,
+                                         **shared) if gconv_num_layers > 1 else None)
 
-    if gconv_num_layers == 0:
-      self.gconv = Linear(embedding_dim, gconv_dim)
-    elif gconv_num_layers > 0:
-      self.gconv = GraphTripleConv(input_dim=embedding_dim, output_dim=gconv_dim,
-                                   hidden_dim=gconv_hidden_dim, pooling=gconv_pooling,
-                                   mlp_normalization=mlp_normalization)
+    # per-object heads: box regressor, optional mask generator; auxiliary relation classifier
+    self.box_net = build_mlp([gconv_dim, gconv_hidden_dim, 4], batch_norm=mlp_normalization)
+    self.mask_net = (self._build_mask_net(n_obj_classes, gconv_dim, mask_size)
+                     if mask_size is not None and mask_size > 0 else None)
+    self.rel_aux_net = build_mlp([2 * embedding_dim + 8, gconv_hidden_dim, n_predicates],
+                                 batch_norm=mlp_normalization)
 
-    self.gconv_net = None
-    if gconv_num_layers > 1:
-      self.gconv_net = GraphTripleConvNet(input_dim=gconv_dim, hidden_dim=gconv_hidden_dim,
-                                          pooling=gconv_pooling,
-                                          num_layers=gconv_num_layers - 1,
-                                          mlp_normalization=mlp_normalization)
-
-    box_net_layers = [gconv_dim, gconv_hidden_dim, 4]
-    self.box_net = build_mlp(box_net_layers, batch_norm=mlp_normalization)
-
-    self.mask_net = None
-    if mask_size is not None and mask_size > 0:
-      self.mask_net = self._build_mask_net(num_objs, gconv_dim, mask_size)
-
-    rel_aux_layers = [2 * embedding_dim + 8, gconv_hidden_dim, num_preds]
-    self.rel_aux_net = build_mlp(rel_aux_layers, batch_norm=mlp_normalization)
-
+    # cascaded refinement network over the (layout ++ noise) canvas
     self.refinement_net = RefinementNetwork(
         dims=(gconv_dim + layout_noise_dim,) + tuple(refinement_dims),
         normalization=normalization, activation=activation)
 
   def _build_mask_net(self, num_objs, dim, mask_size):
-    """sg2im/model.py:94-106."""
-    output_dim = 1
-    layers, cur_size = [], 1
-    while cur_size < mask_size:
-      layers.append(Upsample(scale_factor=2, mode='nearest'))
-      layers.append(BatchNorm2d(dim))
-      layers.append(Conv2d(dim, dim, kernel_size=3, padding=1))
-      layers.append(ReLU())
-      cur_size *= 2
-    if cur_size != mask_size:
+    """1x1 -> mask_size x mask_size by repeated [nearest x2, BN, conv3x3, ReLU],
+    then a 1x1 conv to one channel (sg2im/model.py:94-106)."""
+    if mask_size & (mask_size - 1):
       raise ValueError('Mask size must be a power of 2')
-    layers.append(Conv2d(dim, output_dim, kernel_size=1))
-    return FusedSequential(*layers)
+    blocks = []
+    for _ in range(mask_size.bit_length() - 1):
+      blocks += [Upsample(scale_factor=2, mode='nearest'), BatchNorm2d(dim),
+                 Conv2d(dim, dim, kernel_size=3, padding=1), ReLU()]
+    blocks.append(Conv2d(dim, 1, kernel_size=1))
+    return FusedSequential(*blocks)
 
   def forward(self, objs, triples, obj_to_img=None,
               boxes_gt=None, masks_gt=None, num_imgs=None, noise=None):
@@ -138,36 +130,36 @@ class Sg2ImModel(nn.Module):
     return img, boxes_pred, masks_pred, rel_scores
 
   def encode_scene_graphs(self, scene_graphs):
-    """sg2im/model.py:173-227: JSON-style scene graphs -> (objs, triples,
-    obj_to_img) LongTensors on the model's device.  Like the reference, the
-    input dicts are modified in place (the __image__ object and its
-    __in_image__ relationships are appended)."""
-    if isinstance(scene_graphs, dict):
-      scene_graphs = [scene_graphs]
-    objs, triples, obj_to_img = [], [], []
-    obj_offset = 0
-    for i, sg in enumerate(scene_graphs):
-      sg['objects'].append('__image__')
-      image_idx = len(sg['objects']) - 1
-      for j in range(image_idx):
-        sg['relationships'].append([j, '__in_image__', image_idx])
-      for obj in sg['objects']:
-        obj_idx = self.vocab['object_name_to_idx'].get(obj, None)
-        if obj_idx is None:
-          raise ValueError('Object "%s" not in vocab' % obj)
-        objs.append(obj_idx)
-        obj_to_img.append(i)
-      for s, p, o in sg['relationships']:
-        pred_idx = self.vocab['pred_name_to_idx'].get(p, None)
-        if pred_idx is None:
-          raise ValueError('Relationship "%s" not in vocab' % p)
-        triples.append([s + obj_offset, pred_idx, o + obj_offset])
-      obj_offset += len(sg['objects'])
-    device = next(self.parameters()).device
-    objs = torch.tensor(objs, dtype=torch.int64, device=device)
-    triples = torch.tensor(triples, dtype=torch.int64, device=device)
-    obj_to_img = torch.tensor(obj_to_img, dtype=torch.int64, device=device)
-    return objs, triples, obj_to_img
+    """JSON-style scene graph(s) -> (objs, triples, obj_to_img) int64 tensors on the
+    model's device (sg2im/model.py:173-227).  Every graph gets a trailing
+    ``__image__`` object that every other object is ``__in_image__``; as in the
+    reference the input dictionaries are extended in place."""
+    graphs = [scene_graphs] if isinstance(scene_graphs, dict) else scene_graphs
+    obj_index = self.vocab['object_name_to_idx']
+    pred_index = self.vocab['pred_name_to_idx']
+    categories, owners, rows = [], [], []
+    base = 0
+    for img, graph in enumerate(graphs):
+      names, rels = graph['objects'], graph['relationships']
+      n_real = len(names)
+      names.append('__image__')
+      rels.extend([k, '__in_image__', n_real] for k in range(n_real))
+      for name in names:
+        if name not in obj_index:
+          raise ValueError('Object "%s" not in vocab' % name)
+        categories.append(obj_index[name])
+        owners.append(img)
+      for subj, pred, obj in rels:
+        if pred not in pred_index:
+          raise ValueError('Relationship "%s" not in vocab' % pred)
+        rows.append([base + subj, pred_index[pred], base + obj])
+      base += len(names)
+    where = next(self.parameters()).device
+
+    def as_long(values):
+      return torch.tensor(values, dtype=torch.int64, device=where)
+
+    return as_long(categories), as_long(rows), as_long(owners)
 
   def forward_json(self, scene_graphs):
     """sg2im/model.py:229-232."""

@@ -1,0 +1,143 @@
+"""Host-logic tests on CPU: the nn.Module mirror and the training iteration are
+replayed against the golden fixtures (outputs of the unmodified reference) with
+the CUDA op boundary swapped for its mathematical definition
+(tests/cpu_shim.py).  This pins the WIRING — slices, orders, buffers, which
+BatchNorm sees which tensor, loss assembly, optimiser plumbing — without a GPU;
+the kernels themselves are pinned by the `-m gpu` tests."""
+import contextlib
+import copy
+import io
+
+import torch
+
+from conftest import load_golden, rel_err
+from cpu_shim import cpu_ops
+
+TOL = 1e-5
+
+
+def _quiet():
+  return contextlib.redirect_stdout(io.StringIO())
+
+
+def _noise(seed, n, nd, hw):
+  torch.manual_seed(seed)
+  return torch.randn(n, nd, hw[0], hw[1])
+
+
+def _generator(g):
+  from sg2im_b200.model import Sg2ImModel
+  with _quiet():
+    m = Sg2ImModel(vocab=g['vocab'], **g['kwargs'])
+  m.load_state_dict(g['sd'] if 'sd' in g else g['sd_g'])
+  return m
+
+
+def test_generator_wiring_vg_coco_eval():
+  g = load_golden('generator.pt')
+  imgs, objs, boxes, triples, o2i, _ = g['batch']
+  kw = g['kwargs']
+  noise = _noise(g['noise_seed'], imgs.size(0), kw['layout_noise_dim'], kw['image_size'])
+  with cpu_ops():
+    m = _generator(g)
+    m.train()
+    out = m(objs, triples, o2i, boxes_gt=boxes, noise=noise)
+    for a, b, name in zip(out, g['out_vg'], ('img', 'boxes', 'masks', 'rel')):
+      assert rel_err(a, b) < TOL, name
+    sd = m.state_dict()
+    for k, v in g['running_after_vg'].items():
+      assert rel_err(sd[k], v) < TOL, k
+    assert int(sd['mask_net.1.num_batches_tracked']) == 1
+    m = _generator(g)
+    m.train()
+    out = m(objs, triples, o2i, boxes_gt=boxes, masks_gt=g['gt_masks'], noise=noise,
+            num_imgs=imgs.size(0))
+    for a, b in zip(out, g['out_coco']):
+      assert rel_err(a, b) < TOL
+    m = _generator(g)
+    m.eval()
+    with torch.no_grad():
+      out = m(objs, triples, o2i, noise=noise)
+    for a, b in zip(out, g['out_eval']):
+      assert rel_err(a, b) < TOL
+
+
+def test_forward_json_wiring_config1():
+  g = load_golden('sheep.pt')
+  kw = g['kwargs']
+  with cpu_ops():
+    m = _generator(g)
+    m.eval()
+    torch.manual_seed(g['noise_seed'])                  # forward_json draws the noise itself
+    with torch.no_grad():
+      out = m.forward_json(copy.deepcopy(g['scene_graphs']))
+  for a, b in zip(out, g['out']):
+    assert rel_err(a, b) < TOL
+  assert out[0].shape == (7, 3, 64, 64)
+
+
+def _discriminators(g):
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  with _quiet():
+    d_img = PatchDiscriminator(arch=g['arch'], normalization='batch',
+                               activation='leakyrelu-0.2', padding='valid')
+    d_obj = AcCropDiscriminator(vocab=g['vocab'], arch=g['arch'], normalization='batch',
+                                activation='leakyrelu-0.2', padding='valid',
+                                object_size=g['crop'])
+  d_img.load_state_dict(g['sd_img'])
+  d_obj.load_state_dict(g['sd_obj'])
+  return d_obj, d_img
+
+
+def test_discriminator_wiring():
+  from sg2im_b200.losses import gan_g_loss, gan_d_loss
+  g = load_golden('disc.pt')
+  imgs, objs, boxes, triples, o2i, _ = g['batch']
+  with cpu_ops():
+    d_obj, d_img = _discriminators(g)
+    s_real = d_img(imgs)
+    s_fake = d_img(g['fake'])
+    assert rel_err(s_real, g['img_scores_real']) < TOL
+    assert rel_err(s_fake, g['img_scores_fake']) < TOL
+    assert rel_err(gan_g_loss(s_fake), g['g_loss']) < TOL
+    assert rel_err(gan_d_loss(s_real, s_fake), g['d_loss']) < TOL
+    s_obj, ac = d_obj(imgs, objs, boxes, o2i)
+    assert rel_err(s_obj, g['obj_scores']) < TOL
+    assert rel_err(ac, g['ac_loss']) < TOL
+    # the never-applied classifier stays in the state_dict (discriminators.py:40-45)
+    assert 'classifier.weight' in d_img.state_dict()
+
+
+def test_training_iteration_wiring():
+  """scripts/train.py:508-592 flow of TrainStep (flat gradient buckets, frozen
+  discriminators during the generator step, loss weights, three Adam steps) vs
+  two iterations of the unmodified reference."""
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  kw = g['kwargs']
+  with cpu_ops():
+    m = _generator(g)
+    d_obj, d_img = _discriminators(g)
+    step = TrainStep(m, d_obj, d_img)
+    N = g['batch'][0].size(0)
+    for it, seed in enumerate(g['noise_seeds']):
+      noise = _noise(seed, N, kw['layout_noise_dim'], kw['image_size'])
+      losses, imgs_fake = step.step(g['batch'], noise=noise)
+      for k, v in g['losses'][it].items():
+        assert abs(losses[k] - v) <= 1e-5 * max(1.0, abs(v)), (it, k, losses[k], v)
+      assert imgs_fake.shape == (N, 3) + tuple(kw['image_size']) and not imgs_fake.requires_grad
+    # every parameter moved like the reference's (bias-before-BN entries are Adam noise there
+    # and exactly still here: allow 2 * lr)
+    for net, after in ((m, g['sd_g_after']), (d_obj, g['sd_obj_after']), (d_img, g['sd_img_after'])):
+      sd = net.state_dict()
+      for k, v in after.items():
+        if v.dtype.is_floating_point:
+          assert (sd[k] - v).abs().max() < 2.5e-4, k
+        else:
+          assert torch.equal(sd[k], v), k
+    # gradients live in one flat bucket per network
+    for name, bucket in step.buckets.items():
+      for p in bucket.params:
+        assert p.grad is not None and p.grad.data_ptr() >= bucket.flat.data_ptr()
+    # discriminators are trainable again after the step
+    assert all(p.requires_grad for p in d_obj.parameters())
