@@ -163,3 +163,41 @@ def test_bench_reference_arm_contract():
                         '--workload', 'tiny32', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
   assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_tensor_core_eligibility_rules():
+  """sg2im_conv_tc_supported / sg2im_conv_wgrad_tc_supported are pure host
+  functions: which shapes of the benchmark take the tcgen05 kernels."""
+  from sg2im_b200 import _lib
+  lib = _lib.load()
+  fwd = lib.sg2im_conv_tc_supported
+  wg = lib.sg2im_conv_wgrad_tc_supported
+  # args: N, Hin, Win, Cin, x_cstride, KH, KW, S, P, Hout, Wout, Cout, y_cstride, y_coff
+  assert fwd(32, 128, 128, 288, 288, 3, 3, 1, 1, 128, 128, 64, 64, 0) == 1      # CRN stage-4 conv1
+  assert fwd(32, 8, 8, 160, 160, 3, 3, 1, 1, 8, 8, 1024, 1024, 0) == 1          # stage 0 (zero channel dropped)
+  assert fwd(32, 8, 8, 161, 161, 3, 3, 1, 1, 8, 8, 1024, 1024, 0) == 0          # 161 channels: 644-byte pixel stride
+  assert fwd(448, 1, 1, 384, 384, 1, 1, 1, 0, 1, 1, 512, 512, 0) == 1           # gconv Linear as 1x1 conv
+  assert fwd(32, 32, 32, 256, 256, 2, 2, 1, 0, 30, 30, 128, 128, 0) == 1        # s2d discriminator conv, cropped output
+  assert fwd(32, 64, 64, 12, 12, 2, 2, 1, 0, 63, 63, 64, 64, 0) == 1            # first D layer on the s2d image
+  assert fwd(32, 128, 128, 64, 64, 1, 1, 1, 0, 128, 128, 3, 3, 0) == 0          # RGB head: Cout = 3
+  assert fwd(32, 128, 128, 3, 3, 4, 4, 2, 0, 63, 63, 64, 64, 0) == 0            # stride 2 itself is not taken
+  assert fwd(32, 64, 64, 128, 128, 3, 3, 1, 1, 64, 64, 128, 288, 160) == 1      # write into a channel slice
+  assert fwd(32, 64, 64, 128, 128, 3, 3, 1, 1, 64, 64, 128, 288, 162) == 0      # misaligned slice offset
+  # args: N, Hin, Win, Cin, x_cstride, KH, KW, S, P, Hout, Wout, Cout
+  assert wg(32, 128, 128, 288, 288, 3, 3, 1, 1, 128, 128, 64) == 1
+  assert wg(448, 1, 1, 384, 384, 1, 1, 1, 0, 1, 1, 512) == 1                    # 448 rows: multiple of 32
+  assert wg(70, 1, 1, 512, 512, 1, 1, 1, 0, 1, 1, 1152) == 0                    # 70 rows: FFMA kernel
+  assert wg(32, 32, 32, 256, 256, 2, 2, 1, 0, 30, 30, 128) == 1                 # s2d conv, ragged 30x30 output
+  assert wg(32, 128, 128, 64, 64, 1, 1, 1, 0, 128, 128, 3) == 0                 # Cout = 3 -> skinny kernel
+  assert wg(32, 16, 16, 64, 64, 5, 5, 1, 2, 16, 16, 64) == 0                    # K > 3
+
+
+def test_unsupported_tensor_core_call_is_refused_without_a_device():
+  from sg2im_b200 import _lib
+  import ctypes
+  buf = (ctypes.c_float * 64)()
+  ptr = ctypes.addressof(buf)
+  with pytest.raises(RuntimeError) as e:
+    _lib.call('sg2im_conv_tc', ptr, 161, 1, 4, 4, 161, ptr, None, 3, 3, 1, 4, 4, 64, 0, 0.0, ptr, 64, 0,
+              None, 0, None)
+  assert 'unsupported shape' in str(e.value)
