@@ -1,0 +1,131 @@
+"""Live cross-checks against the UNMODIFIED reference imported from
+/root/reference (present only in the build container; skipped elsewhere):
+
+  * the oracle (oracle/sg2im_oracle.py) vs the reference on configurations the
+    golden fixtures do not cover (layer counts, mask sizes, 'none'
+    normalisation, activation strings, no masks, no noise);
+  * the nn.Module mirror (sg2im_b200.*) under the CPU op shim vs the reference,
+    same configurations — same state_dict loaded into both.
+"""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from conftest import rel_err
+from refimport import have_reference, import_reference
+
+pytestmark = pytest.mark.skipif(not have_reference(), reason='reference tree not mounted')
+
+TOL = 1e-5
+
+CONFIGS = [
+    dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=1,
+         refinement_dims=(16,), mask_size=4, layout_noise_dim=0, image_size=(16, 16)),
+    dict(embedding_dim=8, gconv_dim=16, gconv_hidden_dim=16, gconv_num_layers=2,
+         refinement_dims=(16, 8, 8), mask_size=None, layout_noise_dim=4, image_size=(32, 32)),
+    dict(embedding_dim=12, gconv_dim=12, gconv_hidden_dim=24, gconv_num_layers=4,
+         refinement_dims=(24, 16, 8, 8), mask_size=16, layout_noise_dim=8, image_size=(32, 64),
+         normalization='none', activation='relu'),
+    dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=0,
+         refinement_dims=(8, 8), mask_size=8, layout_noise_dim=4, image_size=(16, 16),
+         gconv_pooling='sum', activation='leakyrelu'),
+]
+
+
+def _quiet():
+  return contextlib.redirect_stdout(io.StringIO())
+
+
+def _batch(H, W, seed):
+  from sg2im_b200.synth import synth_batch
+  return synth_batch(N=3, objs_per_img=4, rels_per_img=3, image_size=(H, W), num_objs=7,
+                     num_preds=4, seed=seed)
+
+
+@pytest.mark.parametrize('idx', range(len(CONFIGS)))
+def test_generator_oracle_and_mirror_vs_live_reference(idx):
+  import_reference()
+  from sg2im.model import Sg2ImModel as RefModel
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.synth import make_vocab
+  from oracle import sg2im_oracle as orc
+  from cpu_shim import cpu_ops
+  kw = dict(CONFIGS[idx])
+  H, W = kw['image_size']
+  vocab = make_vocab(7, 4)
+  torch.manual_seed(100 + idx)
+  with _quiet():
+    ref = RefModel(vocab=vocab, **kw)
+    mine = Sg2ImModel(vocab=vocab, **kw)
+  with torch.no_grad():
+    ref.box_net[2].bias.copy_(torch.tensor([0.1, 0.15, 0.6, 0.7]))      # finite predicted boxes
+  sd = {k: v.clone() for k, v in ref.state_dict().items()}
+  assert list(mine.state_dict().keys()) == list(sd.keys())
+  mine.load_state_dict(sd)
+  imgs, objs, boxes, triples, o2i, _ = _batch(H, W, seed=idx)
+  nd = kw['layout_noise_dim']
+  for training, use_gt in ((True, True), (False, False)):
+    ref.train(training)
+    mine.train(training)
+    ref.load_state_dict(sd)
+    mine.load_state_dict(sd)
+    torch.manual_seed(7)
+    noise = torch.randn(3, nd, H, W) if nd > 0 else None
+    torch.manual_seed(7)                                 # the reference draws the same noise itself
+    out_ref = ref(objs, triples, o2i, boxes_gt=boxes if use_gt else None)
+    out_orc = orc.generator_forward(
+        {k: v.clone() for k, v in sd.items()}, (H, W), objs, triples, o2i,
+        boxes_gt=boxes if use_gt else None, noise=noise, training=training,
+        activation=kw.get('activation', 'leakyrelu-0.2'),
+        normalization=kw.get('normalization', 'batch'),
+        gconv_pooling=kw.get('gconv_pooling', 'avg'), num_imgs=3)
+    with cpu_ops():
+      out_mine = mine(objs, triples, o2i, boxes_gt=boxes if use_gt else None, noise=noise,
+                      num_imgs=3)
+    for r, o, m in zip(out_ref, out_orc, out_mine):
+      if r is None:
+        assert o is None and m is None
+        continue
+      assert rel_err(o, r) < TOL
+      assert rel_err(m, r) < TOL
+    if training:
+      for k, v in ref.state_dict().items():
+        if 'running' in k or 'num_batches' in k:
+          assert rel_err(mine.state_dict()[k].float(), v.float()) < TOL, k
+
+
+@pytest.mark.parametrize('arch,norm,pad', [('C4-8-2,C4-16-2,C4-16-2', 'batch', 'valid'),
+                                          ('C3-8,C3-8-2', 'none', 'same'),
+                                          ('C4-8-2', 'batch', 'valid')])
+def test_discriminators_mirror_vs_live_reference(arch, norm, pad):
+  import_reference()
+  from sg2im.discriminators import PatchDiscriminator as RefP, AcCropDiscriminator as RefA
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  from sg2im_b200.synth import make_vocab
+  from oracle import sg2im_oracle as orc
+  from cpu_shim import cpu_ops
+  vocab = make_vocab(7, 4)
+  torch.manual_seed(5)
+  with _quiet():
+    rp = RefP(arch=arch, normalization=norm, activation='leakyrelu-0.2', padding=pad)
+    ra = RefA(vocab=vocab, arch=arch, normalization=norm, activation='leakyrelu-0.2',
+              padding=pad, object_size=32)
+    mp = PatchDiscriminator(arch=arch, normalization=norm, activation='leakyrelu-0.2', padding=pad)
+    ma = AcCropDiscriminator(vocab=vocab, arch=arch, normalization=norm,
+                             activation='leakyrelu-0.2', padding=pad, object_size=32)
+  assert list(mp.state_dict().keys()) == list(rp.state_dict().keys())
+  assert list(ma.state_dict().keys()) == list(ra.state_dict().keys())
+  mp.load_state_dict(rp.state_dict())
+  ma.load_state_dict(ra.state_dict())
+  imgs, objs, boxes, triples, o2i, _ = _batch(32, 32, seed=3)
+  with cpu_ops():
+    assert rel_err(mp(imgs), rp(imgs)) < TOL
+    s_m, ac_m = ma(imgs, objs, boxes, o2i)
+  s_r, ac_r = ra(imgs, objs, boxes, o2i)
+  assert rel_err(s_m, s_r) < TOL and rel_err(ac_m, ac_r) < TOL
+  out = orc.patch_discriminator({k: v.clone() for k, v in mp.state_dict().items()}, imgs, arch,
+                                normalization=norm, padding=pad, training=True)
+  # the oracle sees the running stats AFTER the two forwards above; outputs in train mode do not depend on them
+  assert rel_err(out, rp(imgs)) < TOL
