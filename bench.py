@@ -55,7 +55,8 @@ def model_kwargs(cfg):
   """scripts/train.py:94-131 defaults for the named workload."""
   return dict(image_size=cfg['image_size'], embedding_dim=128, gconv_dim=128,
               gconv_hidden_dim=512, gconv_num_layers=5,
-              refinement_dims=(1024, 512, 256, 128, 64), normalization='batch',
+              refinement_dims=tuple(cfg.get('refinement_dims', (1024, 512, 256, 128, 64))),
+              normalization='batch',
               activation='leakyrelu-0.2', mask_size=16, layout_noise_dim=32)
 
 

@@ -29,6 +29,11 @@ CONFIGS = {
                  masks=True, num_objs=184, num_preds=7),
   'vg128': dict(N=32, objs_per_img=9, rels_per_img=5, image_size=(128, 128),
                 masks=False, num_objs=179, num_preds=46),
+  # VG-256: the reference ships no 256x256 recipe; SURVEY.md §8(d) assumes one extra refinement
+  # stage (dims 1024,512,256,128,64,32), batch 16 per GPU
+  'vg256': dict(N=16, objs_per_img=9, rels_per_img=5, image_size=(256, 256),
+                masks=False, num_objs=179, num_preds=46,
+                refinement_dims=(1024, 512, 256, 128, 64, 32)),
   'dense128': dict(N=64, objs_per_img=32, rels_per_img=32, image_size=(128, 128),
                    masks=False, num_objs=179, num_preds=46),
   'tiny32': dict(N=4, objs_per_img=3, rels_per_img=2, image_size=(32, 32),
@@ -38,6 +43,7 @@ CONFIGS = {
 
 def synth_batch(N, objs_per_img, rels_per_img, image_size, num_objs, num_preds,
                 masks=False, mask_size=16, seed=0, **_):
+  """Returns the collate tuple (CPU tensors); extra config keys are ignored."""
   g = torch.Generator().manual_seed(seed)
   H, W = image_size
   R = objs_per_img
