@@ -263,6 +263,21 @@ int sg2im_crop_bwd(const float* dout, const float* boxes, const int64_t* idx,
                    int64_t N, int64_t H, int64_t W, int64_t C, int64_t B, int64_t HH,
                    int64_t WW, int align_corners, float* dfeats, sg2im_stream_t stream);
 
+/* ------------------------------------------------------------ deprocess --
+ * imagenet_deprocess_batch (sg2im/data/utils.py:32-67; callers
+ * scripts/train.py:365-366, scripts/run_model.py:70): per element
+ * v = x/inv_std[c] - neg_mean[c]; if rescale, v = (v-lo)/(hi-lo) with lo/hi the
+ * min/max of v over the whole image n; byte = trunc(clamp(255 v, 0, 255)).
+ * imgs and out are addressed with ELEMENT strides (n, c, h, w), so the NCHW
+ * view of an NHWC buffer and either output order work.  inv_std, neg_mean:
+ * device float[C].  minmax: device scratch uint32[2N] (rescale only; written
+ * by the call).  fp32 IEEE arithmetic in the reference's order: identical bytes. */
+int sg2im_deprocess(const float* imgs, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                    int64_t N, int64_t C, int64_t H, int64_t W,
+                    const float* inv_std, const float* neg_mean, int rescale,
+                    uint32_t* minmax, uint8_t* out, int64_t on, int64_t oc, int64_t oh,
+                    int64_t ow, sg2im_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

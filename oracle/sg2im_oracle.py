@@ -153,25 +153,27 @@ def pool_samples(samples, obj_to_img, num_imgs):
   return out.scatter_add(0, idx, samples)
 
 
-def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W, num_imgs):
+def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W, num_imgs, align_corners=False):
   """sg2im/layout.py:66-91 (grid_sample defaults under torch>=1.3:
-  bilinear, zeros padding, align_corners=False — SURVEY.md §0.5)."""
+  bilinear, zeros padding, align_corners=False — SURVEY.md §0.5;
+  align_corners=True is the torch-0.4 convention the published checkpoints
+  were trained under)."""
   O, D = vecs.size()
   M = masks.size(1)
   grid = boxes_to_grid(boxes, H, W)
   img_in = vecs.view(O, D, 1, 1) * masks.float().view(O, 1, M, M)
   sampled = F.grid_sample(img_in, grid, mode='bilinear', padding_mode='zeros',
-                          align_corners=False)
+                          align_corners=align_corners)
   return pool_samples(sampled, obj_to_img, num_imgs)
 
 
-def boxes_to_layout(vecs, boxes, obj_to_img, H, W, num_imgs):
+def boxes_to_layout(vecs, boxes, obj_to_img, H, W, num_imgs, align_corners=False):
   """sg2im/layout.py:30-63: same warp with a constant 8x8 "mask" of ones."""
   O, D = vecs.size()
   grid = boxes_to_grid(boxes, H, W)
   img_in = vecs.view(O, D, 1, 1).expand(O, D, 8, 8)
   sampled = F.grid_sample(img_in, grid, mode='bilinear', padding_mode='zeros',
-                          align_corners=False)
+                          align_corners=align_corners)
   return pool_samples(sampled, obj_to_img, num_imgs)
 
 
@@ -346,7 +348,7 @@ def patch_discriminator(sd, x, arch, normalization='batch',
   return disc_cnn(sd, 'cnn', x, arch, normalization, activation, padding, training)
 
 
-def crop_bbox_batch(feats, bbox, bbox_to_feats, HH, WW=None):
+def crop_bbox_batch(feats, bbox, bbox_to_feats, HH, WW=None, align_corners=False):
   """sg2im/bilinear.py:28-43 -> :69-100 -> :103-132 -> :249-278.  For box b:
   X = (1-a)*(2*x0-1) + a*(2*x1-1), a = linspace(0,1,WW) (tensor_linspace's
   start_w*start + end_w*end form), Y likewise; bilinear grid_sample of
@@ -366,7 +368,7 @@ def crop_bbox_batch(feats, bbox, bbox_to_feats, HH, WW=None):
   Y = (wy0 * y0.view(B, 1) + wy1 * y1.view(B, 1)).view(B, HH, 1).expand(B, HH, WW)
   grid = torch.stack([X, Y], dim=3)
   return F.grid_sample(feats[bbox_to_feats], grid, mode='bilinear',
-                       padding_mode='zeros', align_corners=False)
+                       padding_mode='zeros', align_corners=align_corners)
 
 
 def ac_crop_discriminator(sd, imgs, objs, boxes, obj_to_img, arch, object_size,

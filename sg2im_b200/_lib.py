@@ -58,6 +58,8 @@ SIGNATURES = {
                      _i64, _i64, _int, _ptr, _ptr],
   'sg2im_crop_bwd': [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _ptr,
                      _ptr],
+  'sg2im_deprocess': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int,
+                      _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
 }
 
 _lib = None

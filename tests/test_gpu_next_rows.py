@@ -1,0 +1,129 @@
+"""GPU parity tests for the rows NEXT to the training step:
+de-normalisation kernel, validation pass, staged batch upload, and the
+align_corners=True (torch-0.4 checkpoint) sampling convention.
+
+STATUS: written after round 1's GPU budget was spent — the code under test is
+compile-checked and its host logic is covered on CPU (tests/test_validation_cpu.py,
+tests/test_batching_cpu.py), but these tests have NOT yet run on a B200.  They
+are therefore opt-in (SG2IM_RUN_UNVERIFIED=1) so the default `-m gpu` suite
+reports only kernels that have been validated on hardware; the switch goes away
+once they have passed there.
+"""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get('SG2IM_RUN_UNVERIFIED') != '1',
+                       reason='not yet validated on hardware; set SG2IM_RUN_UNVERIFIED=1'),
+]
+
+TOL = 1e-4
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+def test_deprocess_bytes_identical_to_reference():
+  from sg2im_b200.images import imagenet_deprocess_batch
+  g = load_golden('aux.pt')['deprocess']
+  x = g['imgs'].to(dev())
+  out = imagenet_deprocess_batch(x)
+  assert out.device.type == 'cpu' and out.dtype == torch.uint8
+  assert torch.equal(out, g['rescaled'])
+  assert torch.equal(imagenet_deprocess_batch(x, rescale=False), g['plain'])
+  # the generator hands out an NCHW view of an NHWC buffer: read in place
+  view = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+  assert torch.equal(imagenet_deprocess_batch(view), g['rescaled'])
+  nhwc = imagenet_deprocess_batch(view, device_out=True, channels_last=True)
+  assert nhwc.is_cuda and torch.equal(nhwc.cpu().permute(0, 3, 1, 2), g['rescaled'])
+
+
+def test_deprocess_full_size_properties():
+  from sg2im_b200.images import imagenet_deprocess_batch
+  from oracle import validation_oracle as vorc
+  x = torch.randn(32, 3, 128, 128, generator=torch.Generator().manual_seed(3))
+  out = imagenet_deprocess_batch(x.to(dev()))
+  assert torch.equal(out, vorc.imagenet_deprocess_batch(x))
+  flat = out.view(32, -1)
+  assert bool((flat.min(dim=1).values == 0).all()) and bool((flat.max(dim=1).values == 255).all())
+  with pytest.raises(RuntimeError):
+    imagenet_deprocess_batch(x)                        # CPU tensor: refused
+
+
+@pytest.mark.parametrize('name', ['check_vg', 'check_coco'])
+def test_check_model_matches_reference(name):
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.validate import check_model
+  from sg2im_b200 import ops
+  ops.set_conv_math('fp32')
+  g = load_golden('aux.pt')[name]
+  with contextlib.redirect_stdout(io.StringIO()):
+    model = Sg2ImModel(vocab=g['vocab'], **g['kwargs'])
+  model.load_state_dict(g['sd'])
+  model.to(dev()).train()
+  mean_losses, samples, batch_data, avg_iou = check_model(g['args'], 0, g['loader'], model)
+  for k, v in g['mean_losses'].items():
+    assert abs(mean_losses[k] - v) <= 1e-4 * max(1.0, abs(v)), k
+  assert abs(float(avg_iou) - float(g['avg_iou'])) < 1e-5
+  assert torch.equal(samples['gt_img'], g['samples']['gt_img'])
+  for k in ('gt_box_gt_mask', 'gt_box_pred_mask', 'pred_box_pred_mask'):
+    d = (samples[k].int() - g['samples'][k].int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.01, k
+  assert rel_err(batch_data['boxes_pred'], g['batch_data']['boxes_pred']) < TOL
+  sd = model.state_dict()
+  for k, v in g['bn_after'].items():
+    assert rel_err(sd[k].float(), v.float()) < TOL, k
+
+
+def test_staged_batch_upload():
+  from sg2im_b200 import batching
+  from sg2im_b200.synth import synth_batch
+  imgs, objs, boxes, triples, o2i, t2i = synth_batch(N=3, objs_per_img=4, rels_per_img=2,
+                                                     image_size=(16, 16), num_objs=9, num_preds=5)
+  samples = batching.uncollate((imgs, objs, boxes, triples, o2i, t2i))
+  staged = batching.collate(samples, pin=True)
+  assert staged.floats.is_pinned() and staged.ints.is_pinned()
+  on_dev = staged.to(dev())
+  torch.cuda.synchronize()
+  for a, b in zip(on_dev, (imgs, objs, boxes, triples, o2i, t2i)):
+    assert a.is_cuda and torch.equal(a.cpu(), b)
+
+
+def test_align_corners_true_layout_and_crop():
+  """torch-0.4 sampling convention for the published checkpoints."""
+  from sg2im_b200 import layout as L
+  from sg2im_b200.bilinear import crop_bbox_batch
+  from oracle import sg2im_oracle as orc
+  g = load_golden('aux.pt')['align_corners']
+  lay, crp = load_golden('layout.pt'), load_golden('crop.pt')
+  d = dev()
+  L.ALIGN_CORNERS = True
+  try:
+    m = L.masks_to_layout(lay['rvecs'].to(d), lay['rboxes'].to(d), lay['rmasks'].to(d),
+                          lay['robj_to_img'].to(d), 24, 40)
+    b = L.boxes_to_layout(lay['vecs'].to(d), lay['boxes'].to(d), lay['obj_to_img'].to(d), 24, 20)
+    c = crop_bbox_batch(crp['feats'].to(d), crp['boxes'].to(d), crp['bbox_to_feats'].to(d), 6, 7)
+    assert rel_err(m, g['masks']) < TOL and rel_err(b, g['boxes']) < TOL
+    assert rel_err(c, g['crops']) < TOL
+    # gradients against the oracle under the same convention
+    vecs = lay['rvecs'].clone().requires_grad_(True)
+    masks = lay['rmasks'].clone().requires_grad_(True)
+    ref = orc.masks_to_layout(vecs, lay['rboxes'], masks, lay['robj_to_img'], 24, 40, 3,
+                              align_corners=True)
+    gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    ref.backward(gy)
+    vd = lay['rvecs'].to(d).requires_grad_(True)
+    md = lay['rmasks'].to(d).requires_grad_(True)
+    out = L.masks_to_layout(vd, lay['rboxes'].to(d), md, lay['robj_to_img'].to(d), 24, 40, num_imgs=3)
+    out.backward(gy.to(d))
+    assert rel_err(vd.grad, vecs.grad) < TOL and rel_err(md.grad, masks.grad) < TOL
+  finally:
+    L.ALIGN_CORNERS = False
