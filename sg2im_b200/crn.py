@@ -15,6 +15,39 @@ from .layers import (get_normalization_2d, get_activation, Conv2d, BatchNorm2d,
                      FusedSequential, _to_nhwc, _to_nchw)
 
 
+# Inference: fold an eval-mode BatchNorm into the convolution before it
+# (w' = w * g/sqrt(var+eps), b' = (b - mean) * g/sqrt(var+eps) + beta) so that
+# conv -> BN -> LeakyReLU is ONE kernel (activation in the conv epilogue) and the
+# only elementwise pass left per stage is the x2 upsample into the next stage's
+# buffer.  Off until it has been timed and parity-checked on hardware
+# (tests/test_gpu_next_rows.py); the wiring is covered on CPU.
+FOLD_EVAL_BN = False
+
+
+def _can_fold(bn):
+  return (FOLD_EVAL_BN and bn is not None and not bn.training
+          and bn.running_mean is not None)
+
+
+def _folded(conv, bn):
+  scale = torch.rsqrt(bn.running_var + bn.eps)
+  if bn.weight is not None:
+    scale = scale * bn.weight
+  w = conv.weight * scale.view(-1, 1, 1, 1)
+  b = -bn.running_mean if conv.bias is None else conv.bias - bn.running_mean
+  b = b * scale
+  if bn.bias is not None:
+    b = b + bn.bias
+  return w, b
+
+
+def _conv_bn_act(conv, bn, slope, h, in_ch, round_out):
+  """act(BN_eval(conv(h))) as one convolution with folded parameters."""
+  stride, pad = conv._cfg()
+  w, b = _folded(conv, bn)
+  return ops.conv2d(h, w, b, stride, pad, 1, slope, in_ch, round_out=round_out)
+
+
 class RefinementModule(nn.Module):
   """sg2im/crn.py:35-65."""
 
@@ -102,6 +135,15 @@ class RefinementNetwork(nn.Module):
     a = None
     for i, mod in enumerate(mods):
       conv1, bn1, s1, conv2, bn2, s2 = mod.parts()
+      if _can_fold(bn1) and _can_fold(bn2):
+        last = i + 1 == len(mods)
+        a1 = _conv_bn_act(conv1, bn1, s1, h, C if i == 0 else None, True)
+        a2 = _conv_bn_act(conv2, bn2, s2, a1, None, last)
+        if last:
+          a = a2
+        else:
+          h = ops.bn_act(a2, None, 1.0, up=2, out=bufs[i + 1], out_coff=C)
+        continue
       fb1 = bn1 is not None and bn1.training
       fb2 = bn2 is not None and bn2.training
       st1 = ops.new_stats(conv1.out_channels, h.device) if fb1 else None

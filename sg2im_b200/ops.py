@@ -443,9 +443,12 @@ class S2D(torch.autograd.Function):
 
 
 def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False,
-           stats_out=None):
+           stats_out=None, round_out=False):
   """stats_out: zeroed float64 [2*Cout]; receives the per-channel sum and sum of
-  squares of the output (fused into the tensor-core epilogue when possible)."""
+  squares of the output (fused into the tensor-core epilogue when possible).
+  round_out: the output is consumed directly by another tensor-core op (no
+  normalise/activate pass in between that would round it): write RN-TF32 values."""
+  round_out = bool(round_out) and CONV_MATH == 'tf32'
   if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
       and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4
       and weight.size(0) % 32 == 0):
@@ -456,8 +459,10 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
     w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
-    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out)
-  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out)
+    return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
+                      round_out)
+  return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out,
+                    round_out)
 
 
 def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):

@@ -23,7 +23,7 @@ def _leaky(x, slope):
 
 
 def _conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False,
-            stats_out=None):
+            stats_out=None, round_out=False):
   w = weight if in_ch is None else weight[:, :in_ch]
   y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride=stride, padding=pad)
   if stats_out is not None:

@@ -127,3 +127,32 @@ def test_align_corners_true_layout_and_crop():
     assert rel_err(vd.grad, vecs.grad) < TOL and rel_err(md.grad, masks.grad) < TOL
   finally:
     L.ALIGN_CORNERS = False
+
+
+@pytest.mark.parametrize('math', ['fp32', 'tf32'])
+def test_eval_bn_folding_sheep(math):
+  """Inference with eval-mode BatchNorm folded into the convolutions
+  (crn.FOLD_EVAL_BN) against the reference's config-1 outputs."""
+  import copy
+  from sg2im_b200 import crn, ops
+  from sg2im_b200.model import Sg2ImModel
+  s = load_golden('sheep.pt')
+  ops.set_conv_math(math)
+  crn.FOLD_EVAL_BN = True
+  try:
+    with contextlib.redirect_stdout(io.StringIO()):
+      m = Sg2ImModel(vocab=s['vocab'], **s['kwargs'])
+    m.load_state_dict(s['sd'] if 'sd' in s else s['sd_g'])
+    m.to(dev()).eval()
+    kw = s['kwargs']
+    torch.manual_seed(s['noise_seed'])
+    noise = torch.randn(7, kw['layout_noise_dim'], 64, 64)
+    objs, triples, o2i = m.encode_scene_graphs(copy.deepcopy(s['scene_graphs']))
+    with torch.no_grad():
+      out = m(objs, triples, o2i, noise=noise.to(dev()))
+    tol = TOL if math == 'fp32' else 1e-2
+    for a, b in zip(out, s['out']):
+      assert rel_err(a, b) < tol
+  finally:
+    crn.FOLD_EVAL_BN = False
+    ops.set_conv_math('fp32')

@@ -141,3 +141,58 @@ def test_training_iteration_wiring():
         assert p.grad is not None and p.grad.data_ptr() >= bucket.flat.data_ptr()
     # discriminators are trainable again after the step
     assert all(p.requires_grad for p in d_obj.parameters())
+
+
+def test_eval_bn_folding_wiring():
+  """Inference path: eval-mode BatchNorm folded into the preceding convolution
+  (crn.FOLD_EVAL_BN) reproduces the reference's eval outputs; train mode is
+  untouched by the switch."""
+  from sg2im_b200 import crn
+  g = load_golden('generator.pt')
+  imgs, objs, boxes, triples, o2i, _ = g['batch']
+  kw = g['kwargs']
+  noise = _noise(g['noise_seed'], imgs.size(0), kw['layout_noise_dim'], kw['image_size'])
+  s = load_golden('sheep.pt')
+  crn.FOLD_EVAL_BN = True
+  try:
+    with cpu_ops():
+      m = _generator(g)
+      # make the running statistics non-trivial so the fold is actually exercised
+      for name, buf in m.named_buffers():
+        if name.endswith('running_mean'):
+          buf.copy_(torch.linspace(-0.3, 0.4, buf.numel()))
+        elif name.endswith('running_var'):
+          buf.copy_(torch.linspace(0.5, 1.7, buf.numel()))
+      m.eval()
+      with torch.no_grad():
+        folded = m(objs, triples, o2i, noise=noise)
+        crn.FOLD_EVAL_BN = False
+        plain = m(objs, triples, o2i, noise=noise)
+        crn.FOLD_EVAL_BN = True
+      for a, b in zip(folded, plain):
+        assert rel_err(a, b) < TOL
+      assert not torch.equal(folded[0], plain[0])           # a different op order did run
+      # train mode ignores the switch (batch statistics cannot be folded)
+      m.train()
+      out = m(objs, triples, o2i, boxes_gt=boxes, noise=noise)
+      m2 = _generator(g)
+      for name, buf in m2.named_buffers():
+        if name.endswith('running_mean'):
+          buf.copy_(torch.linspace(-0.3, 0.4, buf.numel()))
+        elif name.endswith('running_var'):
+          buf.copy_(torch.linspace(0.5, 1.7, buf.numel()))
+      m2.train()
+      crn.FOLD_EVAL_BN = False
+      ref = m2(objs, triples, o2i, boxes_gt=boxes, noise=noise)
+      assert torch.equal(out[0], ref[0])
+      # config 1 (figure_6_sheep.json through forward_json) with folding on
+      crn.FOLD_EVAL_BN = True
+      ms = _generator(s)
+      ms.eval()
+      torch.manual_seed(s['noise_seed'])
+      with torch.no_grad():
+        out = ms.forward_json(copy.deepcopy(s['scene_graphs']))
+      for a, b in zip(out, s['out']):
+        assert rel_err(a, b) < TOL
+  finally:
+    crn.FOLD_EVAL_BN = False
