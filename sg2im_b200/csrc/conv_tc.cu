@@ -515,6 +515,11 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
   }
   long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
   while (BN > 64 && m_tiles * ceil_div64(Cout, BN) < num_sms()) BN >>= 1;
+  // tuning aid (tools/prof_conv.py): SG2IM_TC_BN=64|128|256 pins the N tile
+  if (const char* e = getenv("SG2IM_TC_BN")) {
+    int forced = atoi(e);
+    if (forced == 64 || forced == 128 || forced == 256) BN = forced;
+  }
   p.n_tiles = (int)ceil_div64(Cout, BN);
   p.cblocks = (int)ceil_div64(Cin, 32);
   p.num_kb = KH * KW * p.cblocks;
