@@ -5,7 +5,23 @@
 // the NHWC channel axis, fp64 cross-CTA accumulation).
 // Replaces nn.BatchNorm2d + nn.LeakyReLU + F.upsample + torch.cat +
 // F.avg_pool2d of sg2im/crn.py:41-47,58-63,107 and model.py:98-99.
+#include <cstdlib>
 #include "common.cuh"
+
+// second-generation BatchNorm-backward kernels (norm_act_v2.cu), opt-in until
+// they have been validated and timed on hardware
+int sg2im_bn_bwd_reduce_v2(const float* dy, int64_t dcs, int64_t dco, const float* x, int64_t N,
+                           int64_t H, int64_t W, int64_t C, const float* scale, const float* shift,
+                           const float* save, float slope, int up, double* sums, cudaStream_t st);
+int sg2im_bn_bwd_apply_v2(const float* dy, int64_t dcs, int64_t dco, const float* x, int64_t N,
+                          int64_t H, int64_t W, int64_t C, const float* scale, const float* shift,
+                          const float* save, float slope, int up, const double* sums, float* dx,
+                          cudaStream_t st);
+
+static bool bn_bwd_v2_enabled() {
+  const char* e = getenv("SG2IM_BNBWD_V2");          // read per call: tests toggle it in-process
+  return e && e[0] == '1';
+}
 
 namespace {
 
@@ -496,7 +512,10 @@ extern "C" int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, i
   bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
              aligned16(x) && (!scale || (aligned16(scale) && aligned16(shift))) &&
              (!save || aligned16(save)) && N * H * W * C < (1ll << 31);
-  if (vec) launch_colreduce4(f, N * H * W, C, sums, 2, as_stream(stream));
+  if (vec && scale && shift && save && (up == 1 || up == 2) && bn_bwd_v2_enabled())
+    sg2im_bn_bwd_reduce_v2(dy, dy_cstride, dy_coff, x, N, H, W, C, scale, shift, save, slope, up,
+                           sums, as_stream(stream));
+  else if (vec) launch_colreduce4(f, N * H * W, C, sums, 2, as_stream(stream));
   else launch_colreduce(f, N * H * W, C, sums, 2, as_stream(stream));
   SG_LAUNCH_OK();
   return 0;
@@ -516,7 +535,11 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
   bool vec = (C % 4 == 0) && (dy_cstride % 4 == 0) && (dy_coff % 4 == 0) && aligned16(dy) &&
              aligned16(x) && aligned16(dx) && (!scale || (aligned16(scale) && aligned16(shift))) &&
              M * C < (1ll << 31);
-  if (vec)
+  if (vec && training && scale && shift && save && aligned16(save) && sums &&
+      (up == 1 || up == 2) && bn_bwd_v2_enabled())
+    sg2im_bn_bwd_apply_v2(dy, dy_cstride, dy_coff, x, N, H, W, C, scale, shift, save, slope, up,
+                          sums, dx, st);
+  else if (vec)
     scale_act_bwd_apply4_kernel<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, st>>>(
         ag, save, M, C, training, sums, dx);
   else

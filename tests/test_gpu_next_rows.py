@@ -156,3 +156,51 @@ def test_eval_bn_folding_sheep(math):
   finally:
     crn.FOLD_EVAL_BN = False
     ops.set_conv_math('fp32')
+
+
+@pytest.mark.parametrize('N,H,W,C,up,extra', [
+    (4, 16, 16, 64, 1, 0), (4, 16, 16, 64, 2, 40), (2, 8, 8, 1024, 2, 160), (3, 5, 7, 12, 1, 0),
+    (32, 64, 64, 128, 2, 160), (32, 128, 128, 64, 1, 0)])
+def test_bn_backward_v2_matches_v1_and_torch(N, H, W, C, up, extra):
+  """Second-generation BatchNorm+LeakyReLU(+x2 upsample) backward kernels
+  (csrc/norm_act_v2.cu, SG2IM_BNBWD_V2=1) against the first generation and, for
+  the small cases, against torch autograd on the CPU."""
+  import torch.nn as nn
+  import torch.nn.functional as F
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(N * 1000 + C)
+  x = torch.randn(N, H, W, C, generator=g)
+  gy = torch.randn(N, H * up, W * up, C + extra, generator=g)
+  gy[..., :extra] = 0                                  # only the written slice carries gradient
+
+  def run(v2):
+    if v2:
+      os.environ['SG2IM_BNBWD_V2'] = '1'
+    else:
+      os.environ.pop('SG2IM_BNBWD_V2', None)
+    try:
+      bn = nn.BatchNorm2d(C).to(dev())
+      with torch.no_grad():
+        bn.weight.copy_(torch.linspace(0.5, 1.5, C)); bn.bias.copy_(torch.linspace(-0.2, 0.3, C))
+      xd = x.to(dev()).requires_grad_(True)
+      out = torch.zeros(N, H * up, W * up, C + extra, device=dev()) if extra else None
+      y = ops.bn_act(xd, bn, 0.2, up=up, out=out, out_coff=extra)
+      y.backward(gy.to(dev()))
+      return xd.grad.cpu(), bn.weight.grad.cpu(), bn.bias.grad.cpu()
+    finally:
+      os.environ.pop('SG2IM_BNBWD_V2', None)
+
+  a, b = run(False), run(True)
+  for u, v in zip(a, b):
+    assert rel_err(v, u) < 1e-5
+  if N * H * W * C <= 1 << 20:
+    bn = nn.BatchNorm2d(C)
+    with torch.no_grad():
+      bn.weight.copy_(torch.linspace(0.5, 1.5, C)); bn.bias.copy_(torch.linspace(-0.2, 0.3, C))
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.leaky_relu(bn(xr), 0.2)
+    if up > 1:
+      yr = F.interpolate(yr, scale_factor=up, mode='nearest')
+    yr.backward(gy[..., extra:].permute(0, 3, 1, 2))
+    assert rel_err(b[0], xr.grad.permute(0, 2, 3, 1)) < TOL
+    assert rel_err(b[1], bn.weight.grad) < TOL and rel_err(b[2], bn.bias.grad) < TOL
