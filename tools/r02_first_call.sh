@@ -1,0 +1,33 @@
+#!/bin/bash
+# First GPU call of round 2 (run under gpurun from the repo root):
+#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+# 1. hardware validation of everything written after round 1's GPU budget ran out
+# 2. A/B of the opt-in kernels on the default bench
+# 3. tile sweep of the conv kernel over the step's shapes
+# Every step is bounded by its own timeout and writes under gpurun_out/.
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+echo "== unverified GPU tests" | tee gpurun_out/r02_first.log
+SG2IM_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_next_rows.py -q -m gpu -x \
+    >> gpurun_out/r02_first.log 2>&1
+echo "exit $?" >> gpurun_out/r02_first.log
+echo "== bench default" >> gpurun_out/r02_first.log
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_default.json 2>> gpurun_out/r02_first.log
+echo "== bench BN backward v2" >> gpurun_out/r02_first.log
+SG2IM_BNBWD_V2=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_bnv2.json 2>> gpurun_out/r02_first.log
+echo "== conv tile sweep" >> gpurun_out/r02_first.log
+timeout 300 python tools/sweep_conv.py --out gpurun_out/r02_sweep_conv.json >> gpurun_out/r02_first.log 2>&1
+echo "== kernel table (BN v2)" >> gpurun_out/r02_first.log
+SG2IM_BNBWD_V2=1 timeout 300 python tools/kernel_table.py > gpurun_out/r02_kernel_table_bnv2.txt 2>> gpurun_out/r02_first.log
+tail -5 gpurun_out/r02_first.log
+for f in gpurun_out/r02_bench_default.json gpurun_out/r02_bench_bnv2.json; do
+  python - "$f" <<'PY'
+import json, sys
+try:
+  d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+  print(sys.argv[1], d['value'], d['unit'], d['ms_per_step'], 'ms')
+except Exception as e:
+  print(sys.argv[1], 'unreadable:', e)
+PY
+done
