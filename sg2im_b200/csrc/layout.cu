@@ -6,7 +6,13 @@
 // per channel and the warp factorises.
 // HBM-bound: forward writes N*H*W*(D+noise) floats once, backward reads the
 // output gradient inside each object's box once.
+#include <cstdlib>
 #include "common.cuh"
+
+int sg2im_layout_bwd_v2(const float* dout, int64_t dcs, const float* vecs, const float* boxes,
+                        const float* masks, int64_t M, const int64_t* obj_to_img, int64_t N,
+                        int64_t O, int64_t D, int64_t H, int64_t W, int align, float* dvecs,
+                        float* dmasks, cudaStream_t st);
 
 namespace {
 
@@ -341,11 +347,166 @@ extern "C" int sg2im_layout_bwd(const float* dout, int64_t dout_cstride, const f
   }
   SG_ARG(dout_cstride % 4 == 0 && dout_cstride >= D && aligned16(dout) && aligned16(vecs) &&
          aligned16(boxes));
+  const char* v2 = getenv("SG2IM_LAYOUT_V2");           // read per call: tests toggle it in-process
+  if (v2 && v2[0] == '1' && ceil_div64(H, 8) <= 65535 && ceil_div64(W, 32) <= 65535 &&
+      H * W < (1ll << 31)) {
+    sg2im_layout_bwd_v2(dout, dout_cstride, vecs, boxes, masks, M, obj_to_img, N, O, D, H, W,
+                        align_corners, dvecs, dmasks, as_stream(stream));
+    SG_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)O, (unsigned)ceil_div64(H, LB_ROWS));
   size_t smem = (size_t)(M * M + LB_WARPS * D) * sizeof(float);
   layout_bwd_kernel<<<grid, LB_WARPS * 32, smem, as_stream(stream)>>>(
       dout, dout_cstride, vecs, boxes, masks, (int)M, obj_to_img, N, D, H, W, align_corners, dvecs,
       dmasks);
   SG_LAUNCH_OK();
+  return 0;
+}
+
+// =============================================================================
+// Second-generation layout backward (opt-in: SG2IM_LAYOUT_V2=1 until validated on
+// hardware).  Same mathematics as layout_bwd_kernel; restructured because the
+// first generation is latency-bound and unbalanced (0.44 ms for ~0.45 GB of
+// reads, profiles/r01_kernel_table_tf32.txt): there, one CTA owns an object x
+// 8-row band however wide the object is (the `__image__` object of every image
+// makes 10 % of the CTAs carry >90 % of the pixels), and every warp walks its
+// pixels one at a time (one 512 B load in flight, then a 5-step shuffle chain).
+// Here
+//   * a CTA owns an object x (8 rows x 32 columns) tile, so work per CTA is
+//     bounded and the big objects spread over 4x more CTAs;
+//   * a warp owns one row of the tile: each LANE evaluates the bilinear mask
+//     sample of one of the 32 pixels once (instead of every lane recomputing
+//     it for every pixel), a ballot marks the pixels whose footprint touches
+//     the mask, and the row is consumed four pixels per iteration with their
+//     dout loads issued together.
+// =============================================================================
+namespace {
+
+constexpr int L2_ROWS = 8, L2_COLS = 32, L2_GROUP = 4;
+
+__global__ void __launch_bounds__(L2_ROWS * 32)
+layout_bwd_v2_kernel(const float* __restrict__ dout, int64_t dcs, const float* __restrict__ vecs,
+                     const float* __restrict__ boxes, const float* __restrict__ masks, int M,
+                     const int64_t* __restrict__ obj_to_img, int64_t N, int D, int H, int W,
+                     int align, float* __restrict__ dvecs, float* __restrict__ dmasks) {
+  extern __shared__ __align__(16) float sm[];   // [L2_ROWS][D] dvec partials + [M*M] dmask
+  float* sdv = sm;
+  float* sdm = sm + L2_ROWS * D;
+  const int o = blockIdx.x;
+  const int h = blockIdx.y * L2_ROWS + (threadIdx.x >> 5);      // this warp's image row
+  const int w = blockIdx.z * L2_COLS + (threadIdx.x & 31);      // this lane's pixel (sampling phase)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = obj_to_img[o];
+  if (n < 0 || n >= N) return;                                   // CTA-uniform
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
+  const float* mk = masks ? masks + (int64_t)o * M * M : nullptr;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) sdm[i] = 0.f;
+  __syncthreads();
+
+  // lane owns channels j*128 + lane*4 .. +3 (D % 4 == 0, D <= 128*LB_MAXJ: host-checked)
+  bool cv[LB_MAXJ];
+  float4 vv[LB_MAXJ], acc[LB_MAXJ];
+#pragma unroll
+  for (int j = 0; j < LB_MAXJ; ++j) {
+    cv[j] = j * 128 + lane * 4 < D;
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    vv[j] = cv[j] ? *reinterpret_cast<const float4*>(vecs + (int64_t)o * D + j * 128 + lane * 4)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // phase 1: lane = pixel.  Bilinear footprint of (h, w) in the object's mask.
+  int xl = -2, yl = -2; float wx = 0.f, wy = 0.f, s = 0.f;
+  bool touch = false;
+  if (h < H && w < W) {
+    float gx = grid_coord(w, W, bx.x, 1.f / (bx.z - bx.x));
+    float gy = grid_coord(h, H, bx.y, 1.f / (bx.w - bx.y));
+    s = sample_mask(mk, M, align, gx, gy, xl, yl, wx, wy);
+    touch = (xl >= -1 && xl < M) && (yl >= -1 && yl < M);        // else: padding only
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, touch);
+
+  // phase 2: lane = 4 channels.  Four pixels per iteration.
+  if (active) {
+    const float* drow = dout + ((n * H + h) * (int64_t)W + (int64_t)blockIdx.z * L2_COLS) * dcs +
+                        lane * 4;
+    for (int p0 = 0; p0 < L2_COLS; p0 += L2_GROUP) {
+      const unsigned grp = (active >> p0) & ((1u << L2_GROUP) - 1u);
+      if (!grp) continue;                                        // warp-uniform
+      float4 d[L2_GROUP][LB_MAXJ];
+#pragma unroll
+      for (int q = 0; q < L2_GROUP; ++q) {
+        const bool on = (grp >> q) & 1u;
+#pragma unroll
+        for (int j = 0; j < LB_MAXJ; ++j)
+          d[q][j] = (on && cv[j]) ? *reinterpret_cast<const float4*>(drow + (int64_t)(p0 + q) * dcs + j * 128)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float dot[L2_GROUP];
+#pragma unroll
+      for (int q = 0; q < L2_GROUP; ++q) {
+        const float sq = __shfl_sync(0xffffffffu, s, p0 + q);
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < LB_MAXJ; ++j) {
+          t += d[q][j].x * vv[j].x + d[q][j].y * vv[j].y + d[q][j].z * vv[j].z + d[q][j].w * vv[j].w;
+          acc[j].x += d[q][j].x * sq; acc[j].y += d[q][j].y * sq;
+          acc[j].z += d[q][j].z * sq; acc[j].w += d[q][j].w * sq;
+        }
+        dot[q] = t;
+      }
+      if (dmasks) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+          for (int q = 0; q < L2_GROUP; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], off);
+        }
+        // lanes 0..15: pixel q = lane/4, mask corner = lane%4
+        const int q = (lane >> 2) & (L2_GROUP - 1), corner = lane & 3;
+        const int src = p0 + q;
+        const int pxl = __shfl_sync(0xffffffffu, xl, src), pyl = __shfl_sync(0xffffffffu, yl, src);
+        const float pwx = __shfl_sync(0xffffffffu, wx, src), pwy = __shfl_sync(0xffffffffu, wy, src);
+        float dq = dot[0];
+#pragma unroll
+        for (int k = 1; k < L2_GROUP; ++k) dq = (q == k) ? dot[k] : dq;
+        if (lane < 4 * L2_GROUP && ((grp >> q) & 1u)) {
+          const int cx = pxl + (corner & 1), cy = pyl + (corner >> 1);
+          const float wgt = ((corner & 1) ? pwx : 1.f - pwx) * ((corner >> 1) ? pwy : 1.f - pwy);
+          if (cx >= 0 && cx < M && cy >= 0 && cy < M) atomicAdd(&sdm[cy * M + cx], wgt * dq);
+        }
+      }
+    }
+  }
+
+  // cross-warp reduction of dvec, then one atomic per channel per CTA
+#pragma unroll
+  for (int j = 0; j < LB_MAXJ; ++j)
+    if (cv[j]) *reinterpret_cast<float4*>(&sdv[warp * D + j * 128 + lane * 4]) = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float t = 0.f;
+    for (int wv = 0; wv < L2_ROWS; ++wv) t += sdv[wv * D + c];
+    if (t != 0.f) atomicAdd(dvecs + (int64_t)o * D + c, t);
+  }
+  if (dmasks) {
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+      float t = sdm[i];
+      if (t != 0.f) atomicAdd(dmasks + (int64_t)o * M * M + i, t);
+    }
+  }
+}
+
+}  // namespace
+
+// preconditions checked by sg2im_layout_bwd
+int sg2im_layout_bwd_v2(const float* dout, int64_t dcs, const float* vecs, const float* boxes,
+                        const float* masks, int64_t M, const int64_t* obj_to_img, int64_t N,
+                        int64_t O, int64_t D, int64_t H, int64_t W, int align, float* dvecs,
+                        float* dmasks, cudaStream_t st) {
+  dim3 grid((unsigned)O, (unsigned)ceil_div64(H, L2_ROWS), (unsigned)ceil_div64(W, L2_COLS));
+  size_t smem = (size_t)(M * M + L2_ROWS * D) * sizeof(float);
+  layout_bwd_v2_kernel<<<grid, L2_ROWS * 32, smem, st>>>(dout, dcs, vecs, boxes, masks, (int)M,
+                                                         obj_to_img, N, (int)D, (int)H, (int)W,
+                                                         align, dvecs, dmasks);
   return 0;
 }

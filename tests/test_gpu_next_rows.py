@@ -204,3 +204,56 @@ def test_bn_backward_v2_matches_v1_and_torch(N, H, W, C, up, extra):
     yr.backward(gy[..., extra:].permute(0, 3, 1, 2))
     assert rel_err(b[0], xr.grad.permute(0, 2, 3, 1)) < TOL
     assert rel_err(b[1], bn.weight.grad) < TOL and rel_err(b[2], bn.bias.grad) < TOL
+
+
+@pytest.mark.parametrize('O,N,D,M,H,W,with_masks', [
+    (12, 3, 16, 8, 24, 20, True), (40, 4, 128, 16, 64, 64, True), (40, 4, 128, 16, 64, 64, False),
+    (320, 32, 128, 16, 128, 128, True), (7, 2, 256, 5, 9, 37, True)])
+def test_layout_backward_v2(O, N, D, M, H, W, with_masks):
+  """Tiled layout backward (SG2IM_LAYOUT_V2=1) against the first generation and,
+  for the small cases, the oracle's autograd."""
+  from sg2im_b200 import layout as L
+  from oracle import sg2im_oracle as orc
+  g = torch.Generator().manual_seed(O + D)
+  vecs = torch.randn(O, D, generator=g)
+  xy = torch.rand(O, 2, generator=g) * 0.6
+  boxes = torch.cat([xy, xy + torch.rand(O, 2, generator=g) * 0.35 + 0.1], 1)
+  o2i = torch.sort(torch.randint(0, N, (O,), generator=g)).values
+  boxes[-1] = torch.tensor([0., 0., 1., 1.])
+  boxes[0] = torch.tensor([0.2, 0.3, 0.2, 0.5])           # degenerate width: contributes nothing
+  masks = torch.rand(O, M, M, generator=g) if with_masks else None
+  gy = torch.randn(N, D, H, W, generator=g)
+  d = dev()
+
+  def run(v2):
+    if v2:
+      os.environ['SG2IM_LAYOUT_V2'] = '1'
+    else:
+      os.environ.pop('SG2IM_LAYOUT_V2', None)
+    try:
+      vd = vecs.to(d).requires_grad_(True)
+      if with_masks:
+        md = masks.to(d).requires_grad_(True)
+        out = L.masks_to_layout(vd, boxes.to(d), md, o2i.to(d), H, W, num_imgs=N)
+      else:
+        md = None
+        out = L.boxes_to_layout(vd, boxes.to(d), o2i.to(d), H, W, num_imgs=N)
+      out.backward(gy.to(d))
+      return vd.grad.cpu(), (md.grad.cpu() if md is not None else None)
+    finally:
+      os.environ.pop('SG2IM_LAYOUT_V2', None)
+
+  a, b = run(False), run(True)
+  assert rel_err(b[0], a[0]) < 1e-5
+  if with_masks:
+    assert rel_err(b[1], a[1]) < 1e-5
+  if O <= 64:
+    vr = vecs.clone().requires_grad_(True)
+    if with_masks:
+      mr = masks.clone().requires_grad_(True)
+      ref = orc.masks_to_layout(vr, boxes, mr, o2i, H, W, N)
+    else:
+      ref = orc.boxes_to_layout(vr, boxes, o2i, H, W, N)
+    torch.nan_to_num(ref, nan=0.0).backward(gy)
+    if torch.isfinite(vr.grad).all():
+      assert rel_err(b[0], vr.grad) < TOL
