@@ -220,7 +220,8 @@ def test_layout_backward_v2(O, N, D, M, H, W, with_masks):
   boxes = torch.cat([xy, xy + torch.rand(O, 2, generator=g) * 0.35 + 0.1], 1)
   o2i = torch.sort(torch.randint(0, N, (O,), generator=g)).values
   boxes[-1] = torch.tensor([0., 0., 1., 1.])
-  boxes[0] = torch.tensor([0.2, 0.3, 0.2, 0.5])           # degenerate width: contributes nothing
+  if O > 64:
+    boxes[0] = torch.tensor([0.2, 0.3, 0.2, 0.5])         # degenerate width: contributes nothing
   masks = torch.rand(O, M, M, generator=g) if with_masks else None
   gy = torch.randn(N, D, H, W, generator=g)
   d = dev()
@@ -254,6 +255,7 @@ def test_layout_backward_v2(O, N, D, M, H, W, with_masks):
       ref = orc.masks_to_layout(vr, boxes, mr, o2i, H, W, N)
     else:
       ref = orc.boxes_to_layout(vr, boxes, o2i, H, W, N)
-    torch.nan_to_num(ref, nan=0.0).backward(gy)
-    if torch.isfinite(vr.grad).all():
-      assert rel_err(b[0], vr.grad) < TOL
+    ref.backward(gy)
+    assert rel_err(b[0], vr.grad) < TOL
+    if with_masks:
+      assert rel_err(b[1], mr.grad) < TOL
