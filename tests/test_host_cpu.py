@@ -201,3 +201,33 @@ def test_unsupported_tensor_core_call_is_refused_without_a_device():
     _lib.call('sg2im_conv_tc', ptr, 161, 1, 4, 4, 161, ptr, None, 3, 3, 1, 4, 4, 64, 0, 0.0, ptr, 64, 0,
               None, 0, None)
   assert 'unsupported shape' in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+  """oracle/ is test infrastructure: no module of the shipped package may import it
+  (statically: no import statement; dynamically: importing every product module
+  leaves `oracle` out of sys.modules)."""
+  import ast
+  import glob
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  files = sorted(glob.glob(os.path.join(root, 'sg2im_b200', '*.py')))
+  assert len(files) > 10
+  for path in files:
+    tree = ast.parse(open(path).read(), path)
+    for node in ast.walk(tree):
+      names = []
+      if isinstance(node, ast.Import):
+        names = [a.name for a in node.names]
+      elif isinstance(node, ast.ImportFrom):
+        names = [node.module or '']
+      for n in names:
+        assert n.split('.')[0] != 'oracle', '%s imports %s' % (path, n)
+  mods = [os.path.splitext(os.path.basename(f))[0] for f in files if not f.endswith('__init__.py')]
+  code = ('import sys, importlib\n'
+          'for m in %r: importlib.import_module("sg2im_b200." + m)\n'
+          'bad = [m for m in sys.modules if m == "oracle" or m.startswith("oracle.")]\n'
+          'assert not bad, bad\n' % (mods,))
+  subprocess.check_call([sys.executable, '-c', code], cwd=root)
