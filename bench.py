@@ -45,6 +45,8 @@ def parse():
   ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'],
                   help='convolution arithmetic: tcgen05 TF32 (default) or exact-fp32 FFMA')
   ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
+  ap.add_argument('--adam', default='torch', choices=['torch', 'flat'],
+                  help="'flat': one sg2im_adam_flat kernel per optimiser (opt-in until validated on hardware)")
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--shapes-out', default=None, help='write per-shape conv timings (JSON)')
@@ -222,7 +224,8 @@ def run_b200(args, cfg):
     model = Sg2ImModel(vocab, **model_kwargs(cfg)).to(dev)
     d_img = PatchDiscriminator(D_ARCH, padding='valid').to(dev)
     d_obj = AcCropDiscriminator(vocab, D_ARCH, 'batch', 'leakyrelu-0.2', 32, 'valid').to(dev)
-  step = TrainStep(model, d_obj, d_img, cuda_graph=not args.no_graph)
+  step = TrainStep(model, d_obj, d_img, cuda_graph=not args.no_graph,
+                   fused_adam='flat' if args.adam == 'flat' else None)
   torch.manual_seed(1234 + rank)                         # noise stream differs per rank
 
   n_pool = 4

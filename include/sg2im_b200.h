@@ -278,6 +278,18 @@ int sg2im_deprocess(const float* imgs, int64_t sn, int64_t sc, int64_t sh, int64
                     uint32_t* minmax, uint8_t* out, int64_t on, int64_t oc, int64_t oh,
                     int64_t ow, sg2im_stream_t stream);
 
+/* ------------------------------------------------------------ optimiser --
+ * torch.optim.Adam (scripts/train.py:426,436,443; steps at :560,579,592) over
+ * one flat fp32 bucket: params/grads/exp_avg/exp_avg_sq are four arrays of n
+ * floats (16-byte aligned).  `step`: device float holding the step count,
+ * incremented by the call; `found_inf` (device float, may be NULL): nonzero
+ * skips the update AND the increment (the collective non-finite-loss skip of
+ * train.py:552-555 inside a CUDA graph).  amsgrad=False, maximize=False,
+ * weight_decay = L2 added to the gradient. */
+int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float* step, const float* found_inf, sg2im_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,6 +326,21 @@ def avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
   _count()
 
 
+def adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
+              found_inf=None):
+  """One Adam update of a flat fp32 bucket in place (torch.optim.Adam arithmetic);
+  `step` is a 0-dim device float incremented by the call, `found_inf` (0-dim
+  device float or None) nonzero skips update and increment."""
+  for t in (params, grads, exp_avg, exp_avg_sq):
+    _chk(t)
+    if not t.is_contiguous() or t.numel() != params.numel():
+      raise RuntimeError('sg2im_b200: adam_flat needs four contiguous buffers of equal length')
+  _call('sg2im_adam_flat', _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(),
+        float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), _p(step),
+        _p(found_inf), _stream())
+  _count(2)
+
+
 # --------------------------------------------------------------------------
 # weight packing (OIHW master parameters -> kernel layouts)
 # --------------------------------------------------------------------------

@@ -28,26 +28,26 @@ class FlatGrads(object):
   ``.grad`` is a view into ``flat``, so zeroing is one memset and the
   data-parallel exchange is one all-reduce with no packing copies."""
 
-  def __init__(self, params):
+  def __init__(self, params, align=1):
+    """align: every parameter's slice starts at a multiple of `align` elements
+    (FlatAdam lays the parameters out the same way and needs 16-byte aligned
+    weights/biases for the kernels: align=4); padding stays zero."""
     self.params = [p for p in params if p.requires_grad]
-    total = sum(p.numel() for p in self.params)
-    dev = self.params[0].device
-    self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-    off = 0
+    self.offsets, off = [], 0
     for p in self.params:
-      n = p.numel()
-      p.grad = self.flat[off:off + n].view_as(p)
-      off += n
+      self.offsets.append(off)
+      off += -(-p.numel() // align) * align
+    dev = self.params[0].device
+    self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+    for p, o in zip(self.params, self.offsets):
+      p.grad = self.flat[o:o + p.numel()].view_as(p)
 
   def zero(self):
     self.flat.zero_()
     # re-attach in case something replaced .grad (e.g. set_to_none)
-    off = 0
-    for p in self.params:
-      n = p.numel()
-      if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
-        p.grad = self.flat[off:off + n].view_as(p)
-      off += n
+    for p, o in zip(self.params, self.offsets):
+      if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
+        p.grad = self.flat[o:o + p.numel()].view_as(p)
 
   def all_reduce_mean(self, group=None):
     import torch.distributed as dist
@@ -56,6 +56,42 @@ class FlatGrads(object):
       if world > 1:
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.div_(world)
+
+
+class FlatAdam(object):
+  """Adam over one flat bucket per network: the parameters are
+  re-pointed into a flat fp32 buffer laid out like the FlatGrads bucket, the two
+  moments are flat too, and one update is one streaming kernel
+  (``sg2im_adam_flat``) instead of torch.optim.Adam's multi-tensor launches.
+  Same arithmetic and defaults as torch.optim.Adam (amsgrad=False); the step
+  count lives on the device and ``found_inf`` (0-dim device float, nonzero =
+  skip) makes it usable inside a CUDA graph.  ``state_dict`` keys and values of
+  the network are untouched (parameters stay ``nn.Parameter``s of the same
+  shape; only their storage moves)."""
+
+  def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    self.bucket = bucket
+    self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+    flat = bucket.flat
+    self.flat_params = torch.zeros_like(flat)
+    with torch.no_grad():
+      for p, o in zip(bucket.params, bucket.offsets):
+        if o % 4:
+          raise ValueError('FlatAdam needs FlatGrads(align=4)')
+        dst = self.flat_params[o:o + p.numel()].view_as(p)
+        dst.copy_(p)
+        p.data = dst
+    self.exp_avg = torch.zeros_like(flat)
+    self.exp_avg_sq = torch.zeros_like(flat)
+    self.step_count = torch.zeros((), dtype=torch.float32, device=flat.device)
+    self.found_inf = None            # set by the graph path, like torch's capturable Adam
+    self.grad_scale = None
+
+  def step(self):
+    from . import ops
+    ops.adam_flat(self.flat_params, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
+                  self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                  self.weight_decay, self.found_inf)
 
 
 def _all_finite(value, group=None):
@@ -95,7 +131,7 @@ class TrainStep(object):
     if fused_adam is None:
       fused_adam = dev.type == 'cuda'
     kw = dict(lr=a['learning_rate'])
-    if fused_adam:
+    if fused_adam and fused_adam != 'flat':
       kw['fused'] = True
     self.cuda_graph = bool(cuda_graph) and dev.type == 'cuda'
     if self.cuda_graph:
@@ -111,8 +147,13 @@ class TrainStep(object):
     for name, net in self.nets.items():
       if net is None:
         continue
-      self.buckets[name] = FlatGrads(net.parameters())
-      self.opts[name] = torch.optim.Adam(self.buckets[name].params, **kw)
+      if fused_adam == 'flat':
+        # one streaming kernel per optimiser over flat parameter / moment buckets
+        self.buckets[name] = FlatGrads(net.parameters(), align=4)
+        self.opts[name] = FlatAdam(self.buckets[name], lr=a['learning_rate'])
+      else:
+        self.buckets[name] = FlatGrads(net.parameters())
+        self.opts[name] = torch.optim.Adam(self.buckets[name].params, **kw)
     self.skipped = 0
 
   # -- loss assembly, scripts/train.py:387-412 + :539-550

@@ -120,11 +120,30 @@ def _graph_pool(new_t, edges, csr, H, Dout, num_objs, avg):
   return pooled, new_t[:, H:H + Dout]
 
 
+def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
+               found_inf=None):
+  """Mathematical definition of sg2im_adam_flat (csrc/adam.cu), torch/optim/adam.py
+  single-tensor arithmetic, in place."""
+  if found_inf is not None and float(found_inf) != 0.0:
+    return
+  with torch.no_grad():
+    step += 1
+    t = float(step)
+    g = grads if weight_decay == 0 else grads + weight_decay * params
+    exp_avg.add_((g - exp_avg) * (1 - beta1))
+    exp_avg_sq.mul_(beta2).add_((1 - beta2) * g * g)
+    bc1 = 1 - beta1 ** t
+    bc2_sqrt = (1 - beta2 ** t) ** 0.5
+    denom = exp_avg_sq.sqrt() / bc2_sqrt + eps
+    params.sub_((lr / bc1) * (exp_avg / denom))
+
+
 @contextlib.contextmanager
 def cpu_ops():
   from sg2im_b200 import ops
   saved = {}
   repl = dict(conv2d=_conv2d, linear=_linear, bn_act=_bn_act, new_stats=_new_stats,
+              adam_flat=_adam_flat,
               csr_build=lambda idx, nroles, num_rows: (None, None),
               LayoutStack=_Apply(_layout_stack), Layout=_Apply(_layout), Crop=_Apply(_crop),
               TripleGather=_Apply(_triple_gather), GraphPool=_Apply(_graph_pool))

@@ -259,3 +259,61 @@ def test_layout_backward_v2(O, N, D, M, H, W, with_masks):
     assert rel_err(b[0], vr.grad) < TOL
     if with_masks:
       assert rel_err(b[1], mr.grad) < TOL
+
+
+def test_flat_adam_kernel_matches_torch_adam():
+  """sg2im_adam_flat (csrc/adam.cu) vs torch.optim.Adam on the device, incl. a
+  bucket whose length is not a multiple of 4 and the found_inf skip."""
+  from sg2im_b200 import ops
+  for n in (1027, 4096, 28135695 // 7):
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().to(dev()).requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().to(dev())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros((), device=dev())
+    for it in range(4):
+      grad = torch.randn(n, generator=g).to(dev())
+      ref.grad = grad.clone()
+      opt.step()
+      ops.adam_flat(p, grad, m, v, step, 1e-3, 0.9, 0.999, 1e-8)
+      assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (n, it)
+    assert float(step) == 4
+    before = p.clone()
+    ops.adam_flat(p, grad, m, v, step, 1e-3, 0.9, 0.999, 1e-8, found_inf=torch.ones((), device=dev()))
+    torch.cuda.synchronize()
+    assert torch.equal(p, before) and float(step) == 4
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_train_step_with_flat_adam(graph):
+  from sg2im_b200 import ops
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  from sg2im_b200.train_step import TrainStep
+  ops.set_conv_math('fp32')
+  g = load_golden('train_step.pt')
+  kw = g['kwargs']
+  with contextlib.redirect_stdout(io.StringIO()):
+    m = Sg2ImModel(vocab=g['vocab'], **kw)
+    d_img = PatchDiscriminator(arch=g['arch'], normalization='batch', activation='leakyrelu-0.2',
+                               padding='valid')
+    d_obj = AcCropDiscriminator(vocab=g['vocab'], arch=g['arch'], normalization='batch',
+                                activation='leakyrelu-0.2', padding='valid', object_size=g['crop'])
+  m.load_state_dict(g['sd_g']); d_img.load_state_dict(g['sd_img']); d_obj.load_state_dict(g['sd_obj'])
+  for net in (m, d_img, d_obj):
+    net.to(dev())
+  step = TrainStep(m, d_obj, d_img, fused_adam='flat', cuda_graph=graph, graph_warmup=0)
+  batch = [t.to(dev()) for t in g['batch']]
+  N = batch[0].size(0)
+  for it, seed in enumerate(g['noise_seeds']):
+    torch.manual_seed(seed)
+    noise = torch.randn(N, kw['layout_noise_dim'], *kw['image_size']).to(dev())
+    losses, _ = step.step(batch, noise=noise)
+    for k, v in g['losses'][it].items():
+      assert abs(losses[k] - v) <= 1e-3 * max(1.0, abs(v)), (it, k, losses[k], v)
+  sd = m.state_dict()
+  for k, v in g['sd_g_after'].items():
+    if v.dtype.is_floating_point:
+      assert (sd[k].cpu() - v).abs().max() < 2.5e-4, k

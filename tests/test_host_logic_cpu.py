@@ -196,3 +196,76 @@ def test_eval_bn_folding_wiring():
         assert rel_err(a, b) < TOL
   finally:
     crn.FOLD_EVAL_BN = False
+
+
+def test_flat_adam_matches_torch_adam():
+  """FlatAdam (one flat bucket, sg2im_adam_flat arithmetic) tracks
+  torch.optim.Adam over several steps, keeps state_dict keys/shapes, pads
+  odd-sized parameters to 16 bytes, and skips on found_inf."""
+  from sg2im_b200.train_step import FlatGrads, FlatAdam
+  torch.manual_seed(3)
+  def net():
+    torch.manual_seed(5)
+    return torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 1))
+  a, b = net(), net()
+  keys = list(a.state_dict().keys())
+  opt_ref = torch.optim.Adam(a.parameters(), lr=1e-2)
+  with cpu_ops():
+    bucket = FlatGrads(b.parameters(), align=4)
+    opt = FlatAdam(bucket, lr=1e-2)
+    assert all(o % 4 == 0 for o in bucket.offsets)
+    assert bucket.flat.numel() == sum(-(-p.numel() // 4) * 4 for p in b.parameters())
+    assert list(b.state_dict().keys()) == keys
+    for it in range(6):
+      x = torch.randn(11, 7)
+      opt_ref.zero_grad()
+      a(x).pow(2).mean().backward()
+      opt_ref.step()
+      bucket.zero()
+      b(x).pow(2).mean().backward()
+      opt.step()
+      for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7), it
+    assert float(opt.step_count) == 6
+    # parameters are views of the flat bucket; the padding never moves
+    for p, o in zip(bucket.params, bucket.offsets):
+      assert p.data_ptr() == opt.flat_params.data_ptr() + 4 * o
+    used = torch.zeros_like(opt.flat_params, dtype=torch.bool)
+    for p, o in zip(bucket.params, bucket.offsets):
+      used[o:o + p.numel()] = True
+    assert bool((opt.flat_params[~used] == 0).all())
+    # found_inf: nothing moves, the step count stays
+    before = opt.flat_params.clone()
+    opt.found_inf = torch.ones(())
+    opt.step()
+    assert torch.equal(opt.flat_params, before) and float(opt.step_count) == 6
+    # state round trip still works on the re-pointed parameters
+    b.load_state_dict(a.state_dict())
+    for pa, pb in zip(a.parameters(), b.parameters()):
+      assert torch.equal(pa, pb)
+    assert bucket.params[0].data_ptr() == opt.flat_params.data_ptr()
+
+
+def test_training_iteration_with_flat_adam():
+  """TrainStep(fused_adam='flat') reproduces the reference's two iterations like
+  the torch.optim.Adam configuration does."""
+  from sg2im_b200.train_step import TrainStep, FlatAdam
+  g = load_golden('train_step.pt')
+  kw = g['kwargs']
+  with cpu_ops():
+    m = _generator(g)
+    d_obj, d_img = _discriminators(g)
+    step = TrainStep(m, d_obj, d_img, fused_adam='flat')
+    assert all(isinstance(o, FlatAdam) for o in step.opts.values())
+    N = g['batch'][0].size(0)
+    for it, seed in enumerate(g['noise_seeds']):
+      noise = _noise(seed, N, kw['layout_noise_dim'], kw['image_size'])
+      losses, _ = step.step(g['batch'], noise=noise)
+      for k, v in g['losses'][it].items():
+        assert abs(losses[k] - v) <= 1e-5 * max(1.0, abs(v)), (it, k, losses[k], v)
+    for net, after in ((m, g['sd_g_after']), (d_obj, g['sd_obj_after']), (d_img, g['sd_img_after'])):
+      sd = net.state_dict()
+      assert list(sd.keys()) == list(after.keys())
+      for k, v in after.items():
+        if v.dtype.is_floating_point:
+          assert (sd[k] - v).abs().max() < 2.5e-4, k
