@@ -304,7 +304,7 @@ def test_train_step_with_flat_adam(graph):
   m.load_state_dict(g['sd_g']); d_img.load_state_dict(g['sd_img']); d_obj.load_state_dict(g['sd_obj'])
   for net in (m, d_img, d_obj):
     net.to(dev())
-  step = TrainStep(m, d_obj, d_img, fused_adam='flat', cuda_graph=graph, graph_warmup=0)
+  step = TrainStep(m, d_obj, d_img, fused_adam='flat', cuda_graph=graph, graph_warmup=1)
   batch = [t.to(dev()) for t in g['batch']]
   N = batch[0].size(0)
   for it, seed in enumerate(g['noise_seeds']):
