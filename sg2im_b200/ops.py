@@ -180,17 +180,30 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
   return out
 
 
-def _pack(weight, cin_use, want_fwd):
+def _pack(weight, cin_use, want_fwd, want_dgrad=None):
+  """One launch of sg2im_pack_weights; returns the requested layout, or the pair
+  (fwd, dgrad) when both are requested (weights read once)."""
+  if want_dgrad is None:
+    want_dgrad = not want_fwd
   weight = weight.contiguous()
   Co, Ci, KH, KW = weight.shape
   T = KH * KW
   cu = Ci if cin_use is None else cin_use
-  out = torch.empty((T, Co, cu) if want_fwd else (T, cu, Co), dtype=torch.float32,
-                    device=weight.device)
-  _call('sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(out) if want_fwd else None,
-        None if want_fwd else _p(out), 1, _stream())     # RN-TF32: the tensor core would truncate
+  dev = weight.device
+  f = torch.empty((T, Co, cu), dtype=torch.float32, device=dev) if want_fwd else None
+  d = torch.empty((T, cu, Co), dtype=torch.float32, device=dev) if want_dgrad else None
+  _call('sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(f), _p(d), 1,
+        _stream())                                        # RN-TF32: the tensor core would truncate
   _count()
-  return out
+  if want_fwd and want_dgrad:
+    return f, d
+  return f if want_fwd else d
+
+
+# Training: pack the forward AND the data-gradient operand layouts in the forward
+# pass with one launch (the weights are read once; the dgrad copy is kept for the
+# backward pass) instead of one launch per pass.  Off until timed on hardware.
+PACK_BOTH = False
 
 
 def pack_tc_fwd(weight, cin_use=None):
@@ -381,8 +394,14 @@ class Conv(torch.autograd.Function):
       assert out_hw[0] <= Hout and out_hw[1] <= Wout and conv_tc_ok(x, KH, KW, stride, pad, Co, out_hw)
       Hout, Wout = out_hw
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
+    w_dgrad = None
     if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
-      y = conv_tc(x, pack_tc_fwd(weight, Ci), bias, KH, KW, pad, Co, act, slope,
+      if (PACK_BOTH and ctx.needs_input_grad[0] and KH == KW and stride == 1
+          and KH - 1 - pad >= 0):
+        w_fwd, w_dgrad = _pack(weight, Ci, True, True)
+      else:
+        w_fwd = pack_tc_fwd(weight, Ci)
+      y = conv_tc(x, w_fwd, bias, KH, KW, pad, Co, act, slope,
                   out_hw=(Hout, Wout), stats=stats_out if fused_stats else None,
                   round_out=round_out)
     else:
@@ -394,6 +413,7 @@ class Conv(torch.autograd.Function):
       _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
+    ctx.w_dgrad = w_dgrad                       # packed in the forward pass (PACK_BOTH) or None
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.has_bias = bias is not None
     ctx.zero_bias_grad = bool(zero_bias_grad)
@@ -413,7 +433,8 @@ class Conv(torch.autograd.Function):
       pad_t = KH - 1 - pad
       if (KH == KW and pad_t >= 0 and stride == 1
           and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
-        dx = conv_tc(dy, pack_tc_dgrad(weight, Ci), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
+        w_dgrad = ctx.w_dgrad if ctx.w_dgrad is not None else pack_tc_dgrad(weight, Ci)
+        dx = conv_tc(dy, w_dgrad, None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
                      out_hw=(x.size(1), x.size(2)))
       else:
         dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,

@@ -317,3 +317,30 @@ def test_train_step_with_flat_adam(graph):
   for k, v in g['sd_g_after'].items():
     if v.dtype.is_floating_point:
       assert (sd[k].cpu() - v).abs().max() < 2.5e-4, k
+
+
+def test_pack_both_layouts_in_one_launch():
+  """ops.PACK_BOTH: forward + data-gradient operand layouts from one pack launch
+  give bit-identical results to the two-launch default."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(4, 16, 16, 64, generator=g).to(dev())
+    w = (torch.randn(96, 64, 3, 3, generator=g) * 0.05).to(dev())
+    b = torch.randn(96, generator=g).to(dev())
+    gy = torch.randn(4, 16, 16, 96, generator=g).to(dev())
+    outs = []
+    for both in (False, True):
+      ops.PACK_BOTH = both
+      xd, wd = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+      l0 = ops._lib.launches
+      y = ops.conv2d(xd, wd, b, 1, 1, 1, 0.2)
+      y.backward(gy)
+      outs.append((y.detach(), xd.grad, wd.grad, ops._lib.launches - l0))
+    for a, c in zip(outs[0][:3], outs[1][:3]):
+      assert torch.equal(a, c)
+    assert outs[1][3] == outs[0][3] - 1                  # one pack launch fewer
+  finally:
+    ops.PACK_BOTH = False
+    ops.set_conv_math('fp32')
