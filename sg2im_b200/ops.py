@@ -9,6 +9,8 @@ PyTorch here is plumbing only: allocation (caching allocator), stream choice,
 autograd graph bookkeeping.  Every arithmetic op of the hot path is a launch
 into libsg2im_b200.so; a non-CUDA tensor raises (no CPU fallback).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -203,7 +205,7 @@ def _pack(weight, cin_use, want_fwd, want_dgrad=None):
 # Training: pack the forward AND the data-gradient operand layouts in the forward
 # pass with one launch (the weights are read once; the dgrad copy is kept for the
 # backward pass) instead of one launch per pass.  Off until timed on hardware.
-PACK_BOTH = False
+PACK_BOTH = os.environ.get('SG2IM_PACK_BOTH') == '1'
 
 
 def pack_tc_fwd(weight, cin_use=None):
