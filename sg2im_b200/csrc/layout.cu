@@ -13,6 +13,11 @@ int sg2im_layout_bwd_v2(const float* dout, int64_t dcs, const float* vecs, const
                         const float* masks, int64_t M, const int64_t* obj_to_img, int64_t N,
                         int64_t O, int64_t D, int64_t H, int64_t W, int align, float* dvecs,
                         float* dmasks, cudaStream_t st);
+int sg2im_layout_fwd_v2(const float* vecs, const float* boxes, const float* masks, int64_t M,
+                        const int32_t* img_ptr, const int32_t* img_ent, int64_t N, int64_t D,
+                        int64_t H, int64_t W, int align, const float* noise, int64_t noise_c,
+                        int64_t nsn, int64_t nsc, int64_t nsh, int64_t nsw, float* out, int64_t ocs,
+                        int rnd, cudaStream_t st);
 
 namespace {
 
@@ -311,6 +316,13 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
   bool vec = (D % 4 == 0) && (out_cstride % 4 == 0) && aligned16(vecs) && aligned16(out) &&
              (D / 4) * LF_PIX <= LF_MAXACC * LF_THREADS;
   cudaStream_t st = as_stream(stream);
+  const char* v2 = getenv("SG2IM_LAYOUT_V2");            // read per call: tests toggle it in-process
+  if (vec && v2 && v2[0] == '1' && D <= 1024 && N * ceil_div64(H, 4) < (1ll << 31)) {
+    sg2im_layout_fwd_v2(vecs, boxes, masks, M, img_row_ptr, img_entries, N, D, H, W, align_corners,
+                        noise, noise_c, nsn, nsc, nsh, nsw, out, out_cstride, round_tf32, st);
+    SG_LAUNCH_OK();
+    return 0;
+  }
   if (vec) {
     int segs = (int)ceil_div64(W, LF_PIX);
     size_t smem = (size_t)(LF_OBJ * LF_PIX + LF_OBJ * D) * sizeof(float);
@@ -497,6 +509,182 @@ layout_bwd_v2_kernel(const float* __restrict__ dout, int64_t dcs, const float* _
 }
 
 }  // namespace
+
+// =============================================================================
+// Second-generation layout forward (opt-in: SG2IM_LAYOUT_V2=1).  The first
+// generation launches one CTA per (image, row, 32-pixel segment) = 16 384 CTAs
+// at VG-128, and each of them walks the same dependent chain of global loads
+// (image -> object list -> boxes / mask texels / vectors) before it can write
+// 20 KB: 0.26 ms for 0.4 GB (profiles/r01_kernel_table_tf32.txt).  Here a CTA
+// owns an (image, 4-row band): the image's object data (boxes, vectors, masks
+// up to 16x16) is staged in shared memory ONCE, then the band's 32-pixel
+// segments are produced from shared memory only; the noise channels of a
+// segment are fetched into registers before the segment's arithmetic starts.
+// Images with more than 16 objects take further passes that accumulate into the
+// output (read-modify-write); TF32 rounding is applied by the last pass only.
+// =============================================================================
+namespace {
+
+constexpr int F2_ROWS = 4, F2_OBJ = 16, F2_MAXM = 16, F2_THREADS = 256, F2_MAXACC = 8;
+constexpr int F2_NOISE_PER_THREAD = (32 * LF_PIX) / F2_THREADS;   // noise slab of 32 channels x 32 px
+
+__global__ void __launch_bounds__(F2_THREADS)
+layout_fwd_v2_kernel(const float* __restrict__ vecs, const float* __restrict__ boxes,
+                     const float* __restrict__ masks, int M, const int32_t* __restrict__ img_ptr,
+                     const int32_t* __restrict__ img_ent, int D, int H, int W, int align,
+                     const float* __restrict__ noise, int noise_c, int64_t nsn, int64_t nsc,
+                     int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs, int rnd) {
+  extern __shared__ __align__(16) float f2sm[];
+  float* sV = f2sm;                               // [F2_OBJ][D]
+  float* sS = sV + F2_OBJ * D;                    // [F2_OBJ][LF_PIX]
+  float* sN = sS + F2_OBJ * LF_PIX;               // [LF_PIX][33] noise transpose tile
+  float* sM = sN + LF_PIX * 33;                   // [F2_OBJ][M*M] when M <= F2_MAXM
+  __shared__ float4 sBox[F2_OBJ];
+  __shared__ int sObj[F2_OBJ];
+  const int bands = (H + F2_ROWS - 1) / F2_ROWS;
+  const int band = blockIdx.x % bands;
+  const int64_t n = blockIdx.x / bands;
+  const int h0 = band * F2_ROWS;
+  const int h1 = h0 + F2_ROWS < H ? h0 + F2_ROWS : H;
+  const int segs = (W + LF_PIX - 1) / LF_PIX;
+  const int t = threadIdx.x;
+  const int G = D >> 2;
+  const bool mask_in_smem = masks != nullptr && M <= F2_MAXM;
+  const int32_t ob = img_ptr[n], oe = img_ptr[n + 1];
+  const int32_t npass = oe > ob ? (oe - ob + F2_OBJ - 1) / F2_OBJ : 1;   // an empty image still writes zeros
+
+  for (int32_t pass = 0; pass < npass; ++pass) {
+    const int32_t c0 = ob + pass * F2_OBJ;
+    const int nobj = oe - c0 < F2_OBJ ? (oe - c0 > 0 ? oe - c0 : 0) : F2_OBJ;
+    const bool first = pass == 0, last = pass == npass - 1;
+    __syncthreads();                              // previous pass fully consumed
+    if (t < nobj) {
+      int o = img_ent[c0 + t] >> 1;
+      sObj[t] = o;
+      sBox[t] = *reinterpret_cast<const float4*>(boxes + (int64_t)o * 4);
+    }
+    __syncthreads();
+    for (int i = t; i < nobj * G; i += F2_THREADS) {
+      int ol = i / G, g = i - ol * G;
+      reinterpret_cast<float4*>(sV)[i] =
+          *reinterpret_cast<const float4*>(vecs + (int64_t)sObj[ol] * D + g * 4);
+    }
+    if (mask_in_smem) {
+      const int MM = M * M;
+      for (int i = t; i < nobj * MM; i += F2_THREADS) {
+        int ol = i / MM, r = i - ol * MM;
+        sM[i] = masks[(int64_t)sObj[ol] * MM + r];
+      }
+    }
+    __syncthreads();
+
+    for (int h = h0; h < h1; ++h) {
+      for (int seg = 0; seg < segs; ++seg) {
+        const int w0 = seg * LF_PIX;
+        const int npx = W - w0 < LF_PIX ? W - w0 : LF_PIX;
+        // noise of this segment (first 32-channel slab) into registers before anything else
+        float nz[F2_NOISE_PER_THREAD];
+        if (noise && first) {
+#pragma unroll
+          for (int k = 0; k < F2_NOISE_PER_THREAD; ++k) {
+            int i = t + k * F2_THREADS;
+            int c = i / LF_PIX, pp = i - c * LF_PIX;
+            nz[k] = (c < noise_c && pp < npx)
+                        ? noise[n * nsn + (int64_t)c * nsc + (int64_t)h * nsh + (int64_t)(w0 + pp) * nsw]
+                        : 0.f;
+          }
+        }
+        // phase 1: S[o][p], one bilinear mask sample per (object, pixel)
+        for (int i = t; i < nobj * LF_PIX; i += F2_THREADS) {
+          int ol = i / LF_PIX, pp = i - ol * LF_PIX;
+          float sv = 0.f;
+          if (pp < npx) {
+            float4 bx = sBox[ol];
+            float gx = grid_coord(w0 + pp, W, bx.x, 1.f / (bx.z - bx.x));
+            float gy = grid_coord(h, H, bx.y, 1.f / (bx.w - bx.y));
+            int xl, yl; float wx, wy;
+            const float* mk = !masks ? nullptr
+                              : (mask_in_smem ? sM + ol * M * M : masks + (int64_t)sObj[ol] * M * M);
+            sv = sample_mask(mk, M, align, gx, gy, xl, yl, wx, wy);
+          }
+          sS[i] = sv;
+        }
+        __syncthreads();
+        // phase 2: out[p][c..c+3] (+)= sum_o S[o][p] * vec[o][c..c+3]
+        float* orow = out + ((n * H + h) * (int64_t)W + w0) * ocs;
+        const int nout = npx * G;
+#pragma unroll
+        for (int k = 0; k < F2_MAXACC; ++k) {
+          int idx = t + k * F2_THREADS;
+          if (idx < nout) {
+            int pp = idx / G, g = idx - pp * G;
+            float4* dst = reinterpret_cast<float4*>(orow + (int64_t)pp * ocs + g * 4);
+            float4 a = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *dst;
+            for (int ol = 0; ol < nobj; ++ol) {
+              float sv = sS[ol * LF_PIX + pp];
+              if (sv != 0.f) {
+                float4 v = reinterpret_cast<const float4*>(sV)[ol * G + g];
+                a.x += v.x * sv; a.y += v.y * sv; a.z += v.z * sv; a.w += v.w * sv;
+              }
+            }
+            if (rnd && last) { a.x = tf32_rn(a.x); a.y = tf32_rn(a.y); a.z = tf32_rn(a.z); a.w = tf32_rn(a.w); }
+            *dst = a;
+          }
+        }
+        if (noise && first) {
+          // NCHW -> NHWC through a padded tile; slabs beyond the first 32 channels are fetched here
+          for (int cb = 0; cb < noise_c; cb += 32) {
+#pragma unroll
+            for (int k = 0; k < F2_NOISE_PER_THREAD; ++k) {
+              int i = t + k * F2_THREADS;
+              int c = i / LF_PIX, pp = i - c * LF_PIX;
+              float v = nz[k];
+              if (cb > 0)
+                v = (cb + c < noise_c && pp < npx)
+                        ? noise[n * nsn + (int64_t)(cb + c) * nsc + (int64_t)h * nsh + (int64_t)(w0 + pp) * nsw]
+                        : 0.f;
+              sN[pp * 33 + c] = v;
+            }
+            __syncthreads();
+            for (int i = t; i < 32 * LF_PIX; i += F2_THREADS) {
+              int pp = i / 32, c = i - pp * 32;
+              if (cb + c < noise_c && pp < npx) {
+                float v = sN[pp * 33 + c];
+                orow[(int64_t)pp * ocs + D + cb + c] = rnd ? tf32_rn(v) : v;
+              }
+            }
+            __syncthreads();                      // sN (and sS) free for the next slab / segment
+          }
+        } else {
+          __syncthreads();                        // sS free for the next segment
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// preconditions checked by sg2im_layout_fwd (float4 path)
+int sg2im_layout_fwd_v2(const float* vecs, const float* boxes, const float* masks, int64_t M,
+                        const int32_t* img_ptr, const int32_t* img_ent, int64_t N, int64_t D,
+                        int64_t H, int64_t W, int align, const float* noise, int64_t noise_c,
+                        int64_t nsn, int64_t nsc, int64_t nsh, int64_t nsw, float* out, int64_t ocs,
+                        int rnd, cudaStream_t st) {
+  const bool stage_masks = masks != nullptr && M <= F2_MAXM;
+  size_t smem = (size_t)(F2_OBJ * D + F2_OBJ * LF_PIX + LF_PIX * 33 +
+                         (stage_masks ? F2_OBJ * M * M : 0)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(layout_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  int64_t bands = ceil_div64(H, F2_ROWS);
+  layout_fwd_v2_kernel<<<(unsigned)(N * bands), F2_THREADS, smem, st>>>(
+      vecs, boxes, masks, (int)M, img_ptr, img_ent, (int)D, (int)H, (int)W, align, noise,
+      (int)noise_c, nsn, nsc, nsh, nsw, out, ocs, rnd);
+  return 0;
+}
 
 // preconditions checked by sg2im_layout_bwd
 int sg2im_layout_bwd_v2(const float* dout, int64_t dcs, const float* vecs, const float* boxes,

@@ -344,3 +344,44 @@ def test_pack_both_layouts_in_one_launch():
   finally:
     ops.PACK_BOTH = False
     ops.set_conv_math('fp32')
+
+
+@pytest.mark.parametrize('O,N,D,M,H,W,nc', [
+    (12, 3, 16, 8, 24, 20, 0), (40, 4, 128, 16, 64, 64, 32), (320, 32, 128, 16, 128, 128, 32),
+    (45, 2, 128, 16, 32, 32, 40), (9, 3, 64, 0, 16, 48, 5), (7, 2, 256, 20, 9, 37, 0)])
+def test_layout_forward_v2_bit_identical(O, N, D, M, H, W, nc):
+  """Band-resident layout forward (SG2IM_LAYOUT_V2=1): same summation order as the
+  first generation, so the outputs must be bit-identical — incl. images with more
+  than 16 objects (several passes), no masks (M=0), masks too large for shared
+  memory (M=20) and noise channels."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(O * 7 + D)
+  vecs = torch.randn(O, D, generator=g).to(dev())
+  xy = torch.rand(O, 2, generator=g) * 0.6
+  boxes = torch.cat([xy, xy + torch.rand(O, 2, generator=g) * 0.35 + 0.1], 1).to(dev())
+  o2i = torch.sort(torch.randint(0, N, (O,), generator=g)).values
+  if O == 45:
+    o2i = torch.cat([torch.zeros(40, dtype=torch.int64), torch.ones(5, dtype=torch.int64)])
+  o2i = o2i.to(dev())
+  masks = torch.rand(O, M, M, generator=g).to(dev()) if M else None
+  noise = torch.randn(N, nc, H, W, generator=g).to(dev()) if nc else None
+  outs = []
+  for v2 in (False, True):
+    if v2:
+      os.environ['SG2IM_LAYOUT_V2'] = '1'
+    else:
+      os.environ.pop('SG2IM_LAYOUT_V2', None)
+    try:
+      for math in ('fp32', 'tf32'):
+        ops.set_conv_math(math)                            # tf32: the stack variant rounds its output
+        outs.append(ops.Layout.apply(vecs, boxes, masks, o2i, N, H, W, noise, False))
+        extras = [0, 8]
+        if H % 2 == 0 and W % 2 == 0:
+          outs.append(ops.LayoutStack.apply(vecs, boxes, masks, o2i, N, H, W, noise, False, extras)[1]
+                      [..., :D + nc].contiguous())
+    finally:
+      os.environ.pop('SG2IM_LAYOUT_V2', None)
+      ops.set_conv_math('fp32')
+  half = len(outs) // 2
+  for a, b in zip(outs[:half], outs[half:]):
+    assert torch.equal(a, b)
