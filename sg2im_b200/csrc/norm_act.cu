@@ -18,6 +18,15 @@ int sg2im_bn_bwd_apply_v2(const float* dy, int64_t dcs, int64_t dco, const float
                           const float* save, float slope, int up, const double* sums, float* dx,
                           cudaStream_t st);
 
+int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                           const float* scale, const float* shift, float slope, int up, float* y,
+                           int64_t ycs, int64_t yco, int rnd, cudaStream_t st);
+
+static bool bn_fwd_v2_enabled() {
+  const char* e = getenv("SG2IM_BNFWD_V2");
+  return e && e[0] == '1';
+}
+
 static bool bn_bwd_v2_enabled() {
   const char* e = getenv("SG2IM_BNBWD_V2");          // read per call: tests toggle it in-process
   return e && e[0] == '1';
@@ -492,7 +501,10 @@ extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t
   cudaStream_t st = as_stream(stream);
   bool small = N * H * up * W * up * y_cstride < (1ll << 31) && N * H * W * C < (1ll << 31);
   typedef uint32_t U;
-  if (vec && small)
+  if (vec && small && (up == 1 || up == 2) && bn_fwd_v2_enabled())
+    sg2im_scale_act_fwd_v2(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32,
+                           st);
+  else if (vec && small)
     scale_act_fwd_kernel<4, U><<<grid, 256, 0, st>>>(x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff, round_tf32);
   else if (vec)
     scale_act_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);

@@ -282,3 +282,78 @@ int sg2im_bn_bwd_apply_v2(const float* dy, int64_t dcs, int64_t dco, const float
                                                     slope, (uint32_t)M, (uint32_t)rpb, sums, dx, TX);
   return 0;
 }
+
+// ---------------------------------------------------------------- forward ---
+// y[n, Y, X, yco + c] = leaky(x[n, Y/UP, X/UP, c] * scale[c] + shift[c])   (UP in {1, 2})
+// First generation: one OUTPUT float4 per thread, i.e. every input element is
+// fetched UP*UP times and each output pays eight 32-bit divisions.  Here a thread
+// owns an INPUT float4 (x is contiguous: element i of the float4 stream), computes
+// it once and writes the UP*UP replicas; four elements per thread are in flight.
+// Opt-in with SG2IM_BNFWD_V2=1 (norm_act.cu) until validated on hardware.
+namespace {
+
+template <int UP>
+__global__ void __launch_bounds__(256)
+scale_act_fwd_v2_kernel(const float* __restrict__ x, uint32_t total /* float4s */, uint32_t W,
+                        uint32_t C, const float* __restrict__ scale,
+                        const float* __restrict__ shift, float slope, float* __restrict__ y,
+                        uint32_t ycs, uint32_t yco, int rnd) {
+  constexpr int ILP = 4;
+  const uint32_t cg = C >> 2;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i0 < total; i0 += ILP * stride) {
+    float4 v[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) {
+      uint32_t i = i0 + k * stride;
+      v[k] = i < total ? ld4(x + (size_t)i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) {
+      uint32_t i = i0 + k * stride;
+      if (i >= total) continue;
+      const uint32_t m = i / cg, c = (i - m * cg) * 4;
+      float4 r = v[k];
+      if (scale) {
+        float4 s = ld4(scale + c), b = ld4(shift + c);
+        r.x = fmaf(r.x, s.x, b.x); r.y = fmaf(r.y, s.y, b.y);
+        r.z = fmaf(r.z, s.z, b.z); r.w = fmaf(r.w, s.w, b.w);
+      }
+      r.x = leaky(r.x, slope); r.y = leaky(r.y, slope); r.z = leaky(r.z, slope); r.w = leaky(r.w, slope);
+      if (rnd) { r.x = tf32_rn(r.x); r.y = tf32_rn(r.y); r.z = tf32_rn(r.z); r.w = tf32_rn(r.w); }
+      if (UP == 1) {
+        *reinterpret_cast<float4*>(y + (size_t)m * ycs + yco + c) = r;
+      } else {
+        const uint32_t xx = m % W, t = m / W;            // t = n*H + yy
+        float* p = y + ((size_t)t * 4u * W + 2u * xx) * ycs + yco + c;
+        const size_t row = (size_t)2u * W * ycs;
+        *reinterpret_cast<float4*>(p) = r;
+        *reinterpret_cast<float4*>(p + ycs) = r;
+        *reinterpret_cast<float4*>(p + row) = r;
+        *reinterpret_cast<float4*>(p + row + ycs) = r;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// Preconditions (checked by sg2im_scale_act_fwd): float4 path eligible, up in {1, 2},
+// N*H*W*C < 2^31, y_cstride < 2^31.
+int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                           const float* scale, const float* shift, float slope, int up, float* y,
+                           int64_t ycs, int64_t yco, int rnd, cudaStream_t st) {
+  const int64_t total = N * H * W * (C / 4);
+  int64_t blocks = ceil_div64(total, 256 * 4);
+  if (blocks < 1) blocks = 1;
+  if (up == 1)
+    scale_act_fwd_v2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, (uint32_t)total, (uint32_t)W,
+                                                                 (uint32_t)C, scale, shift, slope, y,
+                                                                 (uint32_t)ycs, (uint32_t)yco, rnd);
+  else
+    scale_act_fwd_v2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, (uint32_t)total, (uint32_t)W,
+                                                                 (uint32_t)C, scale, shift, slope, y,
+                                                                 (uint32_t)ycs, (uint32_t)yco, rnd);
+  return 0;
+}

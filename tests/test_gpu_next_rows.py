@@ -385,3 +385,38 @@ def test_layout_forward_v2_bit_identical(O, N, D, M, H, W, nc):
   half = len(outs) // 2
   for a, b in zip(outs[:half], outs[half:]):
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('N,H,W,C,up,extra,use_bn', [
+    (4, 16, 16, 64, 1, 0, True), (4, 16, 16, 64, 2, 40, True), (2, 8, 8, 1024, 2, 160, True),
+    (3, 5, 7, 12, 1, 0, False), (3, 5, 7, 12, 2, 4, False), (32, 64, 64, 128, 2, 160, True)])
+def test_scale_act_forward_v2_bit_identical(N, H, W, C, up, extra, use_bn):
+  """Input-stationary BN-apply + LeakyReLU + x2 upsample forward (SG2IM_BNFWD_V2=1):
+  same per-element operations as the first generation => identical bits."""
+  import torch.nn as nn
+  from sg2im_b200 import ops
+  x = torch.randn(N, H, W, C, generator=torch.Generator().manual_seed(C + up)).to(dev())
+  outs = []
+  for v2 in (False, True):
+    if v2:
+      os.environ['SG2IM_BNFWD_V2'] = '1'
+    else:
+      os.environ.pop('SG2IM_BNFWD_V2', None)
+    try:
+      for math in ('fp32', 'tf32'):
+        ops.set_conv_math(math)
+        bn = None
+        if use_bn:
+          bn = nn.BatchNorm2d(C).to(dev())
+          with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, C)); bn.bias.copy_(torch.linspace(-0.2, 0.3, C))
+        out = torch.full((N, H * up, W * up, C + extra), 7.0, device=dev()) if extra else None
+        with torch.no_grad():
+          outs.append(ops.bn_act(x, bn, 0.2, up=up, out=out, out_coff=extra).clone())
+    finally:
+      os.environ.pop('SG2IM_BNFWD_V2', None)
+      ops.set_conv_math('fp32')
+  for a, b in zip(outs[:2], outs[2:]):
+    assert torch.equal(a, b)
+  if extra:
+    assert bool((outs[2][..., :extra] == 7.0).all())       # channels in front of the slice untouched
