@@ -22,6 +22,8 @@ int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int6
                            const float* scale, const float* shift, float slope, int up, float* y,
                            int64_t ycs, int64_t yco, int rnd, cudaStream_t st);
 
+int sg2im_colsum_small(const float* x, int64_t M, int64_t C, float* out, cudaStream_t st);
+
 static bool bn_fwd_v2_enabled() {
   const char* e = getenv("SG2IM_BNFWD_V2");
   return e && e[0] == '1';
@@ -465,6 +467,14 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
                             sg2im_stream_t stream) {
   SG_ARG(x && out && scratch && M >= 1 && C >= 1);
   cudaStream_t st = as_stream(stream);
+  {
+    const char* e = getenv("SG2IM_COLSUM_V2");            // read per call: tests toggle it in-process
+    if (e && e[0] == '1' && M <= 8192 && M * C < (1ll << 31)) {
+      sg2im_colsum_small(x, M, C, out, st);
+      SG_LAUNCH_OK();
+      return 0;
+    }
+  }
   zero_doubles<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, C);
   StatsF f{x, C};
   if (C % 4 == 0 && aligned16(x)) launch_colreduce4(f, M, C, scratch, 1, st);

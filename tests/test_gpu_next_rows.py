@@ -420,3 +420,19 @@ def test_scale_act_forward_v2_bit_identical(N, H, W, C, up, extra, use_bn):
     assert torch.equal(a, b)
   if extra:
     assert bool((outs[2][..., :extra] == 7.0).all())       # channels in front of the slice untouched
+
+
+@pytest.mark.parametrize('M,C', [(448, 1152), (320, 128), (1, 5), (8192, 64), (37, 179), (9000, 32)])
+def test_colsum_small_kernel(M, C):
+  """Single-launch column sum for the small GEMMs' bias gradients (SG2IM_COLSUM_V2=1)."""
+  from sg2im_b200 import ops
+  x = torch.randn(M, C, generator=torch.Generator().manual_seed(M + C))
+  ref = x.double().sum(dim=0).float()
+  os.environ['SG2IM_COLSUM_V2'] = '1'
+  try:
+    got = ops.colsum(x.to(dev())).cpu()
+  finally:
+    os.environ.pop('SG2IM_COLSUM_V2', None)
+  base = ops.colsum(x.to(dev())).cpu()
+  assert torch.allclose(got, ref, rtol=1e-6, atol=1e-5)
+  assert torch.allclose(base, ref, rtol=1e-6, atol=1e-5)
