@@ -9,7 +9,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 echo "== unverified GPU tests" | tee gpurun_out/r02_first.log
-SG2IM_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_next_rows.py -q -m gpu -x \
+SG2IM_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_next_rows.py -q -m gpu -rf \
     >> gpurun_out/r02_first.log 2>&1
 echo "exit $?" >> gpurun_out/r02_first.log
 echo "== bench default" >> gpurun_out/r02_first.log
