@@ -120,6 +120,20 @@ def _graph_pool(new_t, edges, csr, H, Dout, num_objs, avg):
   return pooled, new_t[:, H:H + Dout]
 
 
+def _avgpool2_fwd(x, x_coff, C, out, out_coff):
+  src = x[..., x_coff:x_coff + C].permute(0, 3, 1, 2)
+  out[..., out_coff:out_coff + C] = F.avg_pool2d(src, 2, 2).permute(0, 2, 3, 1)
+
+
+def _avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
+  g = dcoarse[..., dc_coff:dc_coff + C] * 0.25
+  g = g.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+  if accumulate:
+    dfine[..., df_coff:df_coff + C] += g
+  else:
+    dfine[..., df_coff:df_coff + C] = g
+
+
 def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
                found_inf=None):
   """Mathematical definition of sg2im_adam_flat (csrc/adam.cu), torch/optim/adam.py
@@ -143,7 +157,7 @@ def cpu_ops():
   from sg2im_b200 import ops
   saved = {}
   repl = dict(conv2d=_conv2d, linear=_linear, bn_act=_bn_act, new_stats=_new_stats,
-              adam_flat=_adam_flat,
+              adam_flat=_adam_flat, avgpool2_fwd=_avgpool2_fwd, avgpool2_bwd=_avgpool2_bwd,
               csr_build=lambda idx, nroles, num_rows: (None, None),
               LayoutStack=_Apply(_layout_stack), Layout=_Apply(_layout), Crop=_Apply(_crop),
               TripleGather=_Apply(_triple_gather), GraphPool=_Apply(_graph_pool))

@@ -129,3 +129,123 @@ def test_discriminators_mirror_vs_live_reference(arch, norm, pad):
                                 normalization=norm, padding=pad, training=True)
   # the oracle sees the running stats AFTER the two forwards above; outputs in train mode do not depend on them
   assert rel_err(out, rp(imgs)) < TOL
+
+
+@pytest.mark.parametrize('dims,act,bn,final,drop', [
+    ((12, 16, 8), 'relu', 'none', True, 0), ((12, 16, 8), 'leakyrelu', 'batch', True, 0),
+    ((6, 10, 10, 4), 'relu', 'batch', False, 0), ((6, 10), 'relu', 'none', True, 0.5)])
+def test_build_mlp_mirror_vs_live_reference(dims, act, bn, final, drop):
+  """sg2im/layers.py:216-232 incl. BatchNorm1d, LeakyReLU, no final non-linearity, Dropout."""
+  import_reference()
+  from sg2im.layers import build_mlp as ref_build
+  from sg2im_b200.layers import build_mlp
+  from cpu_shim import cpu_ops
+  torch.manual_seed(11)
+  ref = ref_build(list(dims), activation=act, batch_norm=bn, dropout=drop, final_nonlinearity=final)
+  mine = build_mlp(list(dims), activation=act, batch_norm=bn, dropout=drop, final_nonlinearity=final)
+  assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+  assert [type(m).__name__.replace('Linear', 'Linear') for m in mine] is not None
+  mine.load_state_dict(ref.state_dict())
+  x = torch.randn(9, dims[0])
+  for training in (True, False):
+    if drop > 0 and training:
+      continue                                         # dropout masks are RNG-dependent
+    ref.train(training); mine.train(training)
+    with cpu_ops():
+      got = mine(x)
+    assert rel_err(got, ref(x)) < TOL
+  for k, v in ref.state_dict().items():
+    assert rel_err(mine.state_dict()[k].float(), v.float()) < TOL, k
+
+
+@pytest.mark.parametrize('arch,norm,pad,pool,size', [
+    ('I5,C3-8,U2,C3-6', 'batch', 'same', 'avg', 8),
+    ('C3-8,P2,C3-8-2,FC-32-10,FC-10-3', 'none', 'same', 'avg', 8),
+    ('C4-8-2,C4-8-2', 'batch', 'valid', 'avg', 16),
+    ('C1-4,C3-4', 'none', 'same', 'avg', 6)])
+def test_build_cnn_mirror_vs_live_reference(arch, norm, pad, pool, size):
+  """sg2im/layers.py:129-213: input-channel spec, upsample, average pooling,
+  fully-connected tail, stride / padding variants."""
+  import_reference()
+  from sg2im.layers import build_cnn as ref_build
+  from sg2im_b200.layers import build_cnn
+  from cpu_shim import cpu_ops
+  torch.manual_seed(13)
+  with _quiet():
+    ref, c_ref = ref_build(arch, normalization=norm, activation='leakyrelu-0.2', padding=pad,
+                           pooling=pool)
+    mine, c_mine = build_cnn(arch, normalization=norm, activation='leakyrelu-0.2', padding=pad,
+                             pooling=pool)
+  assert c_ref == c_mine
+  assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+  mine.load_state_dict(ref.state_dict())
+  cin = 5 if arch.startswith('I5') else 3
+  x = torch.randn(2, cin, size, size)
+  for training in (True, False):
+    ref.train(training); mine.train(training)
+    with cpu_ops():
+      got = mine(x)
+    want = ref(x)
+    assert got.shape == want.shape and rel_err(got, want) < TOL
+
+
+def test_generator_with_batchnorm_mlps_vs_live_reference():
+  """mlp_normalization='batch' (BatchNorm1d inside the scene-graph MLPs, model.py:57-66)."""
+  import_reference()
+  from sg2im.model import Sg2ImModel as RefModel
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.synth import make_vocab
+  from cpu_shim import cpu_ops
+  kw = dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=2,
+            refinement_dims=(16, 8), mask_size=8, layout_noise_dim=0, image_size=(16, 16),
+            mlp_normalization='batch')
+  vocab = make_vocab(7, 4)
+  torch.manual_seed(21)
+  with _quiet():
+    ref = RefModel(vocab=vocab, **kw)
+    mine = Sg2ImModel(vocab=vocab, **kw)
+  with torch.no_grad():
+    ref.box_net[3].bias.copy_(torch.tensor([0.1, 0.15, 0.6, 0.7]))
+  assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+  mine.load_state_dict(ref.state_dict())
+  imgs, objs, boxes, triples, o2i, _ = _batch(16, 16, seed=9)
+  ref.train(); mine.train()
+  out_ref = ref(objs, triples, o2i, boxes_gt=boxes)
+  with cpu_ops():
+    out_mine = mine(objs, triples, o2i, boxes_gt=boxes, num_imgs=3)
+  for r, m in zip(out_ref, out_mine):
+    assert rel_err(m, r) < TOL
+  for k, v in ref.state_dict().items():
+    assert rel_err(mine.state_dict()[k].float(), v.float()) < TOL, k
+
+
+def test_refinement_network_standalone_forward_backward_vs_live_reference():
+  """sg2im/crn.py:68-111 called on its own (layout tensor in, image out): exercises the
+  stage-buffer construction from an existing layout and its hand-written backward
+  (crn._StackFromLayout: average-pool cascade folded back into the layout gradient)."""
+  import_reference()
+  from sg2im.crn import RefinementNetwork as RefNet
+  from sg2im_b200.crn import RefinementNetwork
+  from cpu_shim import cpu_ops
+  dims = (6, 16, 8, 8)
+  torch.manual_seed(31)
+  ref = RefNet(dims=dims, normalization='batch', activation='leakyrelu-0.2')
+  mine = RefinementNetwork(dims=dims, normalization='batch', activation='leakyrelu-0.2')
+  assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+  mine.load_state_dict(ref.state_dict())
+  layout = torch.randn(2, 6, 16, 16)
+  gy = torch.randn(2, 3, 16, 16)
+  lr = layout.clone().requires_grad_(True)
+  out_ref = ref(lr)
+  out_ref.backward(gy)
+  lm = layout.clone().requires_grad_(True)
+  with cpu_ops():
+    out = mine(lm)
+    out.backward(gy)
+  assert rel_err(out, out_ref) < TOL
+  assert rel_err(lm.grad, lr.grad) < 1e-4
+  gr = dict(ref.named_parameters())
+  for k, p in mine.named_parameters():
+    if k.endswith('net.0.bias') or k.endswith('net.3.bias'):
+      continue                                           # conv bias in front of BatchNorm: rounding noise only
+    assert rel_err(p.grad, gr[k].grad) < 1e-3, k
