@@ -21,7 +21,12 @@
 //   the caller).
 // Replaces cuDNN's backward-filter behind nn.Conv2d / nn.Linear
 // (sg2im/crn.py:41-45,80-82; model.py:100; layers.py:221).
+#include <cstdlib>
 #include "tc_common.cuh"
+
+// cluster / TMA-multicast variant (conv_wgrad_tc_mc.cu), opt-in with SG2IM_WGRAD_MC=1
+int sg2im_wgrad_mc_launch(const CUtensorMap* tmX, const CUtensorMap* tmDY, const int* f, float* dw,
+                          int BN, cudaStream_t st);
 
 using namespace tc;
 
@@ -294,6 +299,12 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   p.tiles_w = (int)ceil_div64(g.yW, 8); p.tiles_h = (int)ceil_div64(g.yH, RH);
   p.total_ptiles = (int)(g.yN * p.tiles_h * p.tiles_w);
   int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  // read per call: tests toggle it in-process.  The cluster variant always uses N = 64 tiles:
+  // 2 tap passes x ceil(Cout/64) co tiles share one X stream (cluster of 2 or 4), the fewest
+  // L2->SM bytes per accumulator column
+  const char* mc_env = getenv("SG2IM_WGRAD_MC");
+  const bool mc = mc_env && mc_env[0] == '1';
+  if (mc) BN = 64;
   p.ci_tiles = (int)ceil_div64(Cin, 128);
   p.co_tiles = (int)ceil_div64(Cout, BN);
   p.passes = (int)ceil_div64((int64_t)p.taps * BN, 512);
@@ -336,6 +347,15 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   }
   cudaStream_t st = as_stream(stream);
   int rc;
+  {
+    if (mc) {
+      const int f[16] = {p.Cin, p.Cout, p.KH, p.KW, p.P, p.taps, p.RH, p.pitch, p.tiles_w, p.tiles_h,
+                         p.total_ptiles, p.ci_tiles, p.co_tiles, p.passes, p.T, p.a_bytes};
+      rc = sg2im_wgrad_mc_launch(&tmX, &tmDY, f, dw, BN, st);
+      if (rc == 0) { SG_LAUNCH_OK(); return 0; }
+      if (rc > 0) return rc;                               // -1: shape forms no cluster -> plain kernel
+    }
+  }
   if (BN == 256) rc = launch_wg<256>(tmX, tmDY, p, st);
   else if (BN == 128) rc = launch_wg<128>(tmX, tmDY, p, st);
   else rc = launch_wg<64>(tmX, tmDY, p, st);

@@ -436,3 +436,39 @@ def test_colsum_small_kernel(M, C):
   base = ops.colsum(x.to(dev())).cpu()
   assert torch.allclose(got, ref, rtol=1e-6, atol=1e-5)
   assert torch.allclose(base, ref, rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K', [
+    (4, 16, 16, 64, 64, 3), (2, 16, 16, 160, 128, 3), (2, 8, 8, 96, 256, 3), (4, 32, 32, 288, 64, 3),
+    (2, 16, 24, 64, 192, 3), (3, 9, 11, 32, 64, 3), (32, 1, 1, 128, 128, 1), (4, 15, 15, 64, 64, 2)])
+def test_wgrad_cluster_multicast_matches_single_cta(N, H, W, Ci, Co, K):
+  """Cluster / TMA-multicast weight gradient (SG2IM_WGRAD_MC=1) vs the single-CTA kernel
+  (same MMAs, same split-K atomics: agreement to fp32 accumulation-order noise) and vs fp64."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(N + Ci + Co)
+    def tf32(t):                                           # operands the tensor core consumes exactly
+      return (t.view(torch.int32) & ~0x1fff).view(torch.float32)
+    P = 1 if K == 3 else 0
+    x = tf32(torch.randn(N, H, W, Ci, generator=g)).to(dev())
+    Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+    dy = tf32(torch.randn(N, Ho, Wo, Co, generator=g)).to(dev())
+    outs = []
+    for mc in (False, True):
+      if mc:
+        os.environ['SG2IM_WGRAD_MC'] = '1'
+      else:
+        os.environ.pop('SG2IM_WGRAD_MC', None)
+      try:
+        outs.append(ops.conv_wgrad(x, dy, K, K, 1, P).clone())
+      finally:
+        os.environ.pop('SG2IM_WGRAD_MC', None)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Co, Ci, K, K),
+                                      dy.permute(0, 3, 1, 2).double(), padding=P)
+    ref = ref.permute(2, 3, 1, 0).reshape(K * K * Ci, Co).float()
+    assert rel_err(outs[0], ref) < 2e-5
+    assert rel_err(outs[1], ref) < 2e-5
+  finally:
+    ops.set_conv_math('fp32')
