@@ -76,13 +76,13 @@ extern "C" int sg2im_adam_flat(float* params, const float* grads, float* exp_avg
   SG_ARG(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq));
   SG_ARG(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f);
   cudaStream_t st = as_stream(stream);
-  adam_tick_kernel<<<1, 1, 0, st>>>(step, found_inf);
+  SG_LAUNCH(adam_tick_kernel, 1, 1, 0, st, step, found_inf);
   if (n > 0) {
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
     const int64_t cap = 148 * 16;                       // grid-stride beyond ~2 waves of 8 CTAs/SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<(unsigned)blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
+    SG_LAUNCH(adam_flat_kernel, (unsigned)blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, lr,
                                                        beta1, beta2, eps, weight_decay, step,
                                                        found_inf);
   }

@@ -1,9 +1,27 @@
 // Shared helpers for libsg2im_b200 (sm_100a).  Internal — the public surface is
 // include/sg2im_b200.h.
 #pragma once
+#ifdef SG2IM_EMUL
+// tests/emul/cuda_emul.h: host-side SIMT emulation of the CUDA builtins — lets the CPU test
+// suite execute the non-tensor-core kernel sources themselves (test infrastructure only)
+#include "cuda_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "sg2im_b200.h"
+
+// Kernel launch and dynamic shared memory spelled so that the same source also builds for the
+// emulation harness; under nvcc these expand to the plain CUDA forms.
+#ifdef SG2IM_EMUL
+#define SG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emul_launch(dim3(grid), (unsigned)(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
+#define SG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul_dynamic_smem())
+#else
+#define SG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define SG_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 void sg2im_set_error(const char* fmt, ...);
 
@@ -15,6 +33,9 @@ void sg2im_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+#ifdef SG2IM_EMUL
+#define SG_LAUNCH_OK() do { } while (0)
+#else
 #define SG_LAUNCH_OK()                                                        \
   do {                                                                        \
     cudaError_t e_ = cudaGetLastError();                                      \
@@ -23,6 +44,7 @@ void sg2im_set_error(const char* fmt, ...);
       return (int)e_;                                                         \
     }                                                                         \
   } while (0)
+#endif
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
@@ -36,7 +58,13 @@ __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? 
 // this unbiased rounding (what cuBLAS/cuDNN TF32 paths do with cvt.rna).
 __device__ __forceinline__ float tf32_rn(float v) {
   uint32_t u;
+#ifdef SG2IM_EMUL
+  u = __float_as_uint(v);                     // cvt.rna: nearest, ties away from zero (magnitude)
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
+  u &= ~0x1fffu;
+#else
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+#endif
   return __uint_as_float(u);
 }
 

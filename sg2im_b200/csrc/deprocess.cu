@@ -117,18 +117,18 @@ extern "C" int sg2im_deprocess(const float* imgs, int64_t sn, int64_t sc, int64_
   cudaStream_t st = as_stream(stream);
   const int64_t per = C * H * W;
   if (rescale) {
-    deprocess_init_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, st>>>(minmax, N);
+    SG_LAUNCH(deprocess_init_kernel, (unsigned)ceil_div64(N, 128), 128, 0, st, minmax, N);
     int64_t want = ceil_div64(148 * 8, N);               // ~8 CTAs per SM over the whole batch
     int64_t fit = ceil_div64(per, 256 * 4);
     unsigned bx = (unsigned)(want < fit ? want : fit);
     if (bx < 1) bx = 1;
     dim3 grid(bx, (unsigned)N);
-    deprocess_minmax_kernel<<<grid, 256, 0, st>>>(imgs, sn, sc, sh, sw, (int)C, (int)H, (int)W,
+    SG_LAUNCH(deprocess_minmax_kernel, grid, 256, 0, st, imgs, sn, sc, sh, sw, (int)C, (int)H, (int)W,
                                                   inv_std, neg_mean, minmax);
   }
   const int64_t total = N * per;
   SG_ARG(ceil_div64(total, 256) <= 0x7fffffff);
-  deprocess_map_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+  SG_LAUNCH(deprocess_map_kernel, (unsigned)ceil_div64(total, 256), 256, 0, st, 
       imgs, sn, sc, sh, sw, N, (int)C, (int)H, (int)W, inv_std, neg_mean, minmax, rescale, out, on,
       oc, oh, ow);
   SG_LAUNCH_OK();

@@ -72,7 +72,7 @@ layout_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ boxe
                   int align, const float* __restrict__ noise, int noise_c, int64_t nsn,
                   int64_t nsc, int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs,
                   int rnd) {
-  extern __shared__ __align__(16) float lsm[];
+  SG_DYN_SMEM(float, lsm);
   float* sS = lsm;                               // [LF_OBJ][LF_PIX]
   float* sV = lsm + LF_OBJ * LF_PIX;             // [LF_OBJ][D]
   const int segs = (W + LF_PIX - 1) / LF_PIX;
@@ -170,7 +170,7 @@ layout_fwd_scalar_kernel(const float* __restrict__ vecs, const float* __restrict
                          const int32_t* __restrict__ img_ptr, const int32_t* __restrict__ img_ent,
                          int64_t N, int64_t D, int64_t H, int64_t W, int align,
                          const float* __restrict__ noise, int64_t noise_c, int64_t nsn, int64_t nsc,
-                         int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs) {
+                         int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs, int rnd) {
   int64_t G = D + (noise ? noise_c : 0);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * H * W * G) return;
@@ -195,7 +195,7 @@ layout_fwd_scalar_kernel(const float* __restrict__ vecs, const float* __restrict
   } else {
     acc = noise[n * nsn + (c - D) * nsc + (int64_t)h * nsh + (int64_t)w * nsw];
   }
-  out[pix * ocs + c] = acc;
+  out[pix * ocs + c] = rnd ? tf32_rn(acc) : acc;
 }
 
 // One CTA per (object, band of rows).  Each warp owns pixels of the band that
@@ -208,7 +208,7 @@ layout_bwd_kernel(const float* __restrict__ dout, int64_t dcs, const float* __re
                   const float* __restrict__ boxes, const float* __restrict__ masks, int M,
                   const int64_t* __restrict__ obj_to_img, int64_t N, int64_t D, int64_t H,
                   int64_t W, int align, float* __restrict__ dvecs, float* __restrict__ dmasks) {
-  extern __shared__ __align__(16) float sm[];   // [LB_WARPS][D] dvec partials + [M*M] dmask
+  SG_DYN_SMEM(float, sm);   // [LB_WARPS][D] dvec partials + [M*M] dmask
   float* sdv = sm;
   float* sdm = sm + LB_WARPS * D;
   const int o = blockIdx.x;
@@ -329,15 +329,15 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
     size_t need_noise = (size_t)LF_PIX * 33 * sizeof(float);
     if (smem < need_noise) smem = need_noise;
     unsigned grid = (unsigned)(N * H * segs);
-    layout_fwd_kernel<<<grid, LF_THREADS, smem, st>>>(vecs, boxes, masks, (int)M, img_row_ptr,
+    SG_LAUNCH(layout_fwd_kernel, grid, LF_THREADS, smem, st, vecs, boxes, masks, (int)M, img_row_ptr,
                                                       img_entries, N, (int)D, (int)H, (int)W,
                                                       align_corners, noise, (int)noise_c, nsn, nsc,
                                                       nsh, nsw, out, out_cstride, round_tf32);
   } else {
     int64_t total = N * H * W * ctot;
-    layout_fwd_scalar_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+    SG_LAUNCH(layout_fwd_scalar_kernel, (unsigned)ceil_div64(total, 256), 256, 0, st, 
         vecs, boxes, masks, (int)M, img_row_ptr, img_entries, N, D, H, W, align_corners, noise,
-        noise_c, nsn, nsc, nsh, nsw, out, out_cstride);
+        noise_c, nsn, nsc, nsh, nsw, out, out_cstride, round_tf32);
   }
   SG_LAUNCH_OK();
   return 0;
@@ -369,7 +369,7 @@ extern "C" int sg2im_layout_bwd(const float* dout, int64_t dout_cstride, const f
   }
   dim3 grid((unsigned)O, (unsigned)ceil_div64(H, LB_ROWS));
   size_t smem = (size_t)(M * M + LB_WARPS * D) * sizeof(float);
-  layout_bwd_kernel<<<grid, LB_WARPS * 32, smem, as_stream(stream)>>>(
+  SG_LAUNCH(layout_bwd_kernel, grid, LB_WARPS * 32, smem, as_stream(stream), 
       dout, dout_cstride, vecs, boxes, masks, (int)M, obj_to_img, N, D, H, W, align_corners, dvecs,
       dmasks);
   SG_LAUNCH_OK();
@@ -402,7 +402,7 @@ layout_bwd_v2_kernel(const float* __restrict__ dout, int64_t dcs, const float* _
                      const float* __restrict__ boxes, const float* __restrict__ masks, int M,
                      const int64_t* __restrict__ obj_to_img, int64_t N, int D, int H, int W,
                      int align, float* __restrict__ dvecs, float* __restrict__ dmasks) {
-  extern __shared__ __align__(16) float sm[];   // [L2_ROWS][D] dvec partials + [M*M] dmask
+  SG_DYN_SMEM(float, sm);   // [L2_ROWS][D] dvec partials + [M*M] dmask
   float* sdv = sm;
   float* sdm = sm + L2_ROWS * D;
   const int o = blockIdx.x;
@@ -534,7 +534,7 @@ layout_fwd_v2_kernel(const float* __restrict__ vecs, const float* __restrict__ b
                      const int32_t* __restrict__ img_ent, int D, int H, int W, int align,
                      const float* __restrict__ noise, int noise_c, int64_t nsn, int64_t nsc,
                      int64_t nsh, int64_t nsw, float* __restrict__ out, int64_t ocs, int rnd) {
-  extern __shared__ __align__(16) float f2sm[];
+  SG_DYN_SMEM(float, f2sm);
   float* sV = f2sm;                               // [F2_OBJ][D]
   float* sS = sV + F2_OBJ * D;                    // [F2_OBJ][LF_PIX]
   float* sN = sS + F2_OBJ * LF_PIX;               // [LF_PIX][33] noise transpose tile
@@ -674,13 +674,15 @@ int sg2im_layout_fwd_v2(const float* vecs, const float* boxes, const float* mask
   const bool stage_masks = masks != nullptr && M <= F2_MAXM;
   size_t smem = (size_t)(F2_OBJ * D + F2_OBJ * LF_PIX + LF_PIX * 33 +
                          (stage_masks ? F2_OBJ * M * M : 0)) * sizeof(float);
+#ifndef SG2IM_EMUL
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(layout_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
+#endif
   int64_t bands = ceil_div64(H, F2_ROWS);
-  layout_fwd_v2_kernel<<<(unsigned)(N * bands), F2_THREADS, smem, st>>>(
+  SG_LAUNCH(layout_fwd_v2_kernel, (unsigned)(N * bands), F2_THREADS, smem, st, 
       vecs, boxes, masks, (int)M, img_ptr, img_ent, (int)D, (int)H, (int)W, align, noise,
       (int)noise_c, nsn, nsc, nsh, nsw, out, ocs, rnd);
   return 0;
@@ -693,7 +695,7 @@ int sg2im_layout_bwd_v2(const float* dout, int64_t dcs, const float* vecs, const
                         float* dmasks, cudaStream_t st) {
   dim3 grid((unsigned)O, (unsigned)ceil_div64(H, L2_ROWS), (unsigned)ceil_div64(W, L2_COLS));
   size_t smem = (size_t)(M * M + L2_ROWS * D) * sizeof(float);
-  layout_bwd_v2_kernel<<<grid, L2_ROWS * 32, smem, st>>>(dout, dcs, vecs, boxes, masks, (int)M,
+  SG_LAUNCH(layout_bwd_v2_kernel, grid, L2_ROWS * 32, smem, st, dout, dcs, vecs, boxes, masks, (int)M,
                                                          obj_to_img, N, (int)D, (int)H, (int)W,
                                                          align, dvecs, dmasks);
   return 0;

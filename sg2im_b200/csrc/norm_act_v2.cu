@@ -245,11 +245,11 @@ int sg2im_bn_bwd_reduce_v2(const float* dy, int64_t dcs, int64_t dco, const floa
   if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
   dim3 grid((unsigned)cblocks, (unsigned)rblocks);
   if (up == 1)
-    bn_bwd_reduce_v2_kernel<1><<<grid, 256, 0, st>>>(dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
+    SG_LAUNCH(bn_bwd_reduce_v2_kernel<1>, grid, 256, 0, st, dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
                                                      (uint32_t)W, (uint32_t)C, scale, shift, save,
                                                      slope, (uint32_t)M, (uint32_t)rpb, sums, TX);
   else
-    bn_bwd_reduce_v2_kernel<2><<<grid, 256, 0, st>>>(dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
+    SG_LAUNCH(bn_bwd_reduce_v2_kernel<2>, grid, 256, 0, st, dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
                                                      (uint32_t)W, (uint32_t)C, scale, shift, save,
                                                      slope, (uint32_t)M, (uint32_t)rpb, sums, TX);
   return 0;
@@ -273,11 +273,11 @@ int sg2im_bn_bwd_apply_v2(const float* dy, int64_t dcs, int64_t dco, const float
   if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
   dim3 grid((unsigned)cblocks, (unsigned)rblocks);
   if (up == 1)
-    bn_bwd_apply_v2_kernel<1><<<grid, 256, 0, st>>>(dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
+    SG_LAUNCH(bn_bwd_apply_v2_kernel<1>, grid, 256, 0, st, dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
                                                     (uint32_t)W, (uint32_t)C, scale, shift, save,
                                                     slope, (uint32_t)M, (uint32_t)rpb, sums, dx, TX);
   else
-    bn_bwd_apply_v2_kernel<2><<<grid, 256, 0, st>>>(dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
+    SG_LAUNCH(bn_bwd_apply_v2_kernel<2>, grid, 256, 0, st, dy, (uint32_t)dcs, (uint32_t)dco, x, (uint32_t)H,
                                                     (uint32_t)W, (uint32_t)C, scale, shift, save,
                                                     slope, (uint32_t)M, (uint32_t)rpb, sums, dx, TX);
   return 0;
@@ -348,11 +348,11 @@ int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int6
   int64_t blocks = ceil_div64(total, 256 * 4);
   if (blocks < 1) blocks = 1;
   if (up == 1)
-    scale_act_fwd_v2_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, (uint32_t)total, (uint32_t)W,
+    SG_LAUNCH(scale_act_fwd_v2_kernel<1>, (unsigned)blocks, 256, 0, st, x, (uint32_t)total, (uint32_t)W,
                                                                  (uint32_t)C, scale, shift, slope, y,
                                                                  (uint32_t)ycs, (uint32_t)yco, rnd);
   else
-    scale_act_fwd_v2_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, (uint32_t)total, (uint32_t)W,
+    SG_LAUNCH(scale_act_fwd_v2_kernel<2>, (unsigned)blocks, 256, 0, st, x, (uint32_t)total, (uint32_t)W,
                                                                  (uint32_t)C, scale, shift, slope, y,
                                                                  (uint32_t)ycs, (uint32_t)yco, rnd);
   return 0;
@@ -394,6 +394,6 @@ colsum_small_kernel(const float* __restrict__ x, uint32_t M, uint32_t C, float* 
 }  // namespace
 
 int sg2im_colsum_small(const float* x, int64_t M, int64_t C, float* out, cudaStream_t st) {
-  colsum_small_kernel<<<(unsigned)ceil_div64(C, 32), 256, 0, st>>>(x, (uint32_t)M, (uint32_t)C, out);
+  SG_LAUNCH(colsum_small_kernel, (unsigned)ceil_div64(C, 32), 256, 0, st, x, (uint32_t)M, (uint32_t)C, out);
   return 0;
 }

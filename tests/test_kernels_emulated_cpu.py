@@ -1,0 +1,275 @@
+"""The non-tensor-core kernel SOURCES executed on the CPU.
+
+`tests/emul/cuda_emul.h` is a host-side SIMT emulation of the CUDA builtins (one OS
+thread per CUDA thread of a block, real barriers for __syncthreads / shuffles /
+ballots, atomics under a lock).  With -DSG2IM_EMUL the very files nvcc compiles
+(`csrc/layout.cu`, `norm_act_v2.cu`, `adam.cu`, `deprocess.cu` — kernels AND their host
+launchers: grid sizing, tiling, dispatch on SG2IM_*_V2) build with g++ and run here
+against the oracle / torch.  This pins index arithmetic, tiling, masking and reduction
+logic of kernels that have not run on hardware yet, and cross-checks
+the emulator itself on the hardware-validated first-generation layout kernels.
+It does not model the tensor-core / TMA kernels, memory ordering or timing.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT, load_golden, rel_err
+
+pytestmark = pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++ (C++20)')
+
+_i64, _f32, _int, _ptr = ctypes.c_int64, ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+
+
+@pytest.fixture(scope='module')
+def lib(tmp_path_factory):
+  out = tmp_path_factory.mktemp('emul') / 'libemul.so'
+  src = sorted(str(p) for p in (__import__('pathlib').Path(ROOT) / 'tests' / 'emul').glob('emul_*.cpp'))
+  cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-DSG2IM_EMUL',
+         '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
+         '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')] + src + ['-o', str(out)]
+  subprocess.check_call(cmd)
+  L = ctypes.CDLL(str(out))
+  L.sg2im_layout_fwd.argtypes = [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
+                                 _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr]
+  L.sg2im_layout_bwd.argtypes = [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64,
+                                 _int, _ptr, _ptr, _ptr]
+  L.emul_bn_bwd_reduce_v2.argtypes = [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                      _f32, _int, _ptr]
+  L.emul_bn_bwd_apply_v2.argtypes = [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                     _f32, _int, _ptr, _ptr]
+  L.emul_scale_act_fwd_v2.argtypes = [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _int, _ptr, _i64,
+                                      _i64, _int]
+  L.emul_colsum_small.argtypes = [_ptr, _i64, _i64, _ptr]
+  L.sg2im_adam_flat.argtypes = [_ptr, _ptr, _ptr, _ptr, _i64, _f32, _f32, _f32, _f32, _f32, _ptr, _ptr,
+                                _ptr]
+  L.sg2im_deprocess.argtypes = [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int,
+                                _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]
+  L.emul_last_error.restype = ctypes.c_char_p
+  L.emul_blocks_run.restype = ctypes.c_ulonglong
+  return L
+
+
+def _p(t):
+  return None if t is None else t.data_ptr()
+
+
+def _ok(lib, rc):
+  assert rc == 0, lib.emul_last_error()
+
+
+@pytest.fixture
+def v2_env():
+  keys = ('SG2IM_LAYOUT_V2',)
+  yield lambda on: [os.environ.__setitem__(k, '1') if on else os.environ.pop(k, None) for k in keys]
+  for k in keys:
+    os.environ.pop(k, None)
+
+
+def _scene(O, N, D, M, seed, crowded=False):
+  g = torch.Generator().manual_seed(seed)
+  vecs = torch.randn(O, D, generator=g)
+  xy = torch.rand(O, 2, generator=g) * 0.6
+  boxes = torch.cat([xy, xy + torch.rand(O, 2, generator=g) * 0.35 + 0.1], 1)
+  boxes[-1] = torch.tensor([0., 0., 1., 1.])
+  if crowded:                                             # > 16 objects in image 0: several passes
+    o2i = torch.cat([torch.zeros(O - 2, dtype=torch.int64), torch.full((2,), N - 1, dtype=torch.int64)])
+  else:
+    o2i = torch.sort(torch.randint(0, N, (O,), generator=g)).values
+  masks = torch.rand(O, M, M, generator=g) if M else None
+  counts = torch.bincount(o2i, minlength=N)
+  row_ptr = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)]).to(torch.int32)
+  entries = (torch.arange(O, dtype=torch.int32) * 2).contiguous()    # objects are grouped by image
+  return vecs, boxes, masks, o2i, row_ptr, entries
+
+
+LAYOUT_CASES = [  # O, N, D, M, H, W, noise channels, crowded
+    (6, 2, 8, 5, 8, 16, 0, False), (9, 3, 16, 8, 12, 40, 5, False), (20, 2, 8, 4, 6, 8, 3, True),
+    (5, 2, 12, 0, 8, 8, 0, False), (4, 1, 8, 20, 8, 36, 33, False),
+    (5, 2, 6, 4, 6, 10, 2, False)]            # D % 4 != 0: the scalar fallback kernel
+
+
+@pytest.mark.parametrize('case', LAYOUT_CASES)
+@pytest.mark.parametrize('gen', [1, 2])
+def test_layout_forward_sources_on_cpu(lib, v2_env, case, gen):
+  """csrc/layout.cu forward: first generation (validated on the B200 — here it validates the
+  emulator) and second generation (band-resident, not yet run on hardware) vs the oracle."""
+  from oracle import sg2im_oracle as orc
+  O, N, D, M, H, W, nc, crowded = case
+  vecs, boxes, masks, o2i, row_ptr, entries = _scene(O, N, D, M, seed=O + W, crowded=crowded)
+  noise = torch.randn(N, nc, H, W, generator=torch.Generator().manual_seed(1)) if nc else None
+  ref = (orc.masks_to_layout(vecs, boxes, masks, o2i, H, W, N) if M
+         else orc.boxes_to_layout(vecs, boxes, o2i, H, W, N))
+  if nc:
+    ref = torch.cat([ref, noise], dim=1)
+  ref = ref.permute(0, 2, 3, 1)
+  # trailing channels of a wider buffer stay untouched; pixel stride a multiple of 4 floats so
+  # that D % 4 == 0 cases take the float4 kernels
+  extra = 4 + (-(D + nc)) % 4
+  out = torch.full((N, H, W, D + nc + extra), 7.0)
+  ns = noise.stride() if nc else (0, 0, 0, 0)
+  v2_env(gen == 2)
+  b0 = lib.emul_blocks_run()
+  _ok(lib, lib.sg2im_layout_fwd(_p(vecs), _p(boxes), _p(masks), M, _p(row_ptr), _p(entries), N, O, D,
+                                H, W, 0, _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
+                                out.size(3), 0, None))
+  if D % 4 == 0:                                          # the generation asked for really ran
+    segs = -(-W // 32)
+    assert lib.emul_blocks_run() - b0 == (N * -(-H // 4) if gen == 2 else N * H * segs)
+  assert rel_err(out[..., :D + nc], ref) < 1e-5
+  assert bool((out[..., D + nc:] == 7.0).all())
+  # TF32-rounded variant: every value has its 13 low mantissa bits clear and is within 2^-11 relative
+  out_r = torch.zeros(N, H, W, D + nc + extra)
+  _ok(lib, lib.sg2im_layout_fwd(_p(vecs), _p(boxes), _p(masks), M, _p(row_ptr), _p(entries), N, O, D,
+                                H, W, 0, _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out_r),
+                                out_r.size(3), 1, None))
+  out_r = out_r[..., :D + nc].contiguous()
+  assert int((out_r.view(torch.int32) & 0x1fff).abs().max()) == 0
+  assert float((out_r - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -11 + 1e-6
+
+
+@pytest.mark.parametrize('case', LAYOUT_CASES[:4])
+@pytest.mark.parametrize('gen', [1, 2])
+def test_layout_backward_sources_on_cpu(lib, v2_env, case, gen):
+  from oracle import sg2im_oracle as orc
+  O, N, D, M, H, W, nc, crowded = case
+  vecs, boxes, masks, o2i, _, _ = _scene(O, N, D, M, seed=O + W, crowded=crowded)
+  vr = vecs.clone().requires_grad_(True)
+  mr = masks.clone().requires_grad_(True) if M else None
+  ref = (orc.masks_to_layout(vr, boxes, mr, o2i, H, W, N) if M
+         else orc.boxes_to_layout(vr, boxes, o2i, H, W, N))
+  gy = torch.randn(N, H, W, D + 4, generator=torch.Generator().manual_seed(2))   # wider buffer: dcs > D
+  ref.backward(gy[..., :D].permute(0, 3, 1, 2))
+  dvecs = torch.zeros(O, D)
+  dmasks = torch.zeros(O, M, M) if M else None
+  v2_env(gen == 2)
+  b0 = lib.emul_blocks_run()
+  _ok(lib, lib.sg2im_layout_bwd(_p(gy), gy.size(3), _p(vecs), _p(boxes), _p(masks), M, _p(o2i), N, O, D,
+                                H, W, 0, _p(dvecs), _p(dmasks), None))
+  assert lib.emul_blocks_run() - b0 == O * -(-H // 8) * (-(-W // 32) if gen == 2 else 1)
+  assert rel_err(dvecs, vr.grad) < 1e-4
+  if M:
+    assert rel_err(dmasks, mr.grad) < 1e-4
+
+
+def _bn_case(N, H, W, C, up, extra, seed):
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(N, H, W, C, generator=g)
+  gamma = torch.linspace(0.5, 1.5, C)
+  beta = torch.linspace(-0.2, 0.3, C)
+  gy = torch.randn(N, H * up, W * up, C + extra, generator=g)
+  mean = x.reshape(-1, C).mean(0)
+  var = x.reshape(-1, C).var(0, unbiased=False)
+  invstd = torch.rsqrt(var + 1e-5)
+  scale = (gamma * invstd).contiguous()
+  shift = (beta - mean * gamma * invstd).contiguous()
+  save = torch.cat([mean, invstd]).contiguous()
+  return x, gamma, beta, gy, scale, shift, save
+
+
+BN_CASES = [(2, 8, 8, 16, 1, 0), (2, 4, 6, 12, 2, 8), (1, 16, 16, 64, 2, 32), (3, 5, 7, 4, 1, 4),
+            (2, 8, 8, 132, 1, 0)]
+
+
+@pytest.mark.parametrize('N,H,W,C,up,extra', BN_CASES)
+def test_bn_backward_v2_source_on_cpu(lib, N, H, W, C, up, extra):
+  """csrc/norm_act_v2.cu reduce + apply (and their launch geometry) vs torch autograd of
+  BatchNorm(train) -> LeakyReLU -> nearest x`up` -> channel slice of a wider buffer."""
+  x, gamma, beta, gy, scale, shift, save = _bn_case(N, H, W, C, up, extra, seed=C + up)
+  xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+  y = F.leaky_relu(F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5), 0.2)
+  if up > 1:
+    y = F.interpolate(y, scale_factor=up, mode='nearest')
+  y.backward(gy[..., extra:].permute(0, 3, 1, 2))
+  sums = torch.zeros(2 * C, dtype=torch.float64)
+  _ok(lib, lib.emul_bn_bwd_reduce_v2(_p(gy), gy.size(3), extra, _p(x), N, H, W, C, _p(scale), _p(shift),
+                                     _p(save), 0.2, up, _p(sums)))
+  # sums = (d loss / d beta, d loss / d gamma)
+  assert rel_err(sums[:C].float(), br.grad) < 1e-5
+  assert rel_err(sums[C:].float(), gr.grad) < 1e-5
+  dx = torch.full((N, H, W, C), float('nan'))
+  _ok(lib, lib.emul_bn_bwd_apply_v2(_p(gy), gy.size(3), extra, _p(x), N, H, W, C, _p(scale), _p(shift),
+                                    _p(save), 0.2, up, _p(sums), _p(dx)))
+  assert bool(torch.isfinite(dx).all())                    # every element written
+  assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 1e-4
+
+
+@pytest.mark.parametrize('N,H,W,C,up,extra', BN_CASES)
+@pytest.mark.parametrize('affine', [True, False])
+def test_scale_act_forward_v2_source_on_cpu(lib, N, H, W, C, up, extra, affine):
+  x, _, _, _, scale, shift, _ = _bn_case(N, H, W, C, up, extra, seed=C)
+  pre = x * scale + shift if affine else x
+  ref = F.leaky_relu(pre, 0.2)
+  if up > 1:
+    ref = ref.repeat_interleave(up, dim=1).repeat_interleave(up, dim=2)
+  y = torch.full((N, H * up, W * up, C + extra), 7.0)
+  _ok(lib, lib.emul_scale_act_fwd_v2(_p(x), N, H, W, C, _p(scale) if affine else None,
+                                     _p(shift) if affine else None, 0.2, up, _p(y), y.size(3), extra, 0))
+  assert rel_err(y[..., extra:], ref) < 1e-6
+  assert bool((y[..., :extra] == 7.0).all())
+
+
+@pytest.mark.parametrize('M,C', [(448, 100), (1, 5), (37, 179), (300, 32)])
+def test_colsum_small_source_on_cpu(lib, M, C):
+  x = torch.randn(M, C, generator=torch.Generator().manual_seed(M))
+  out = torch.full((C,), float('nan'))
+  _ok(lib, lib.emul_colsum_small(_p(x), M, C, _p(out)))
+  assert torch.allclose(out, x.double().sum(0).float(), rtol=1e-6, atol=1e-5)
+
+
+def test_adam_flat_source_on_cpu(lib):
+  """csrc/adam.cu vs torch.optim.Adam: several steps, a length that is not a multiple of 4
+  (scalar tail), weight decay, and the found_inf skip (no update, no step increment)."""
+  for n, wd in ((1027, 0.0), (4096, 0.0), (515, 0.01)):
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2, weight_decay=wd)
+    p, m, v = p0.clone(), torch.zeros(n), torch.zeros(n)
+    step = torch.zeros(())
+    for it in range(5):
+      grad = torch.randn(n, generator=g)
+      ref.grad = grad.clone()
+      opt.step()
+      _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
+                                   _p(step), None, None))
+      assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (n, it)
+    assert float(step) == 5
+    before = p.clone()
+    inf = torch.ones(())
+    _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
+                                 _p(step), _p(inf), None))
+    assert torch.equal(p, before) and float(step) == 5
+
+
+def test_deprocess_source_on_cpu_bit_exact(lib):
+  """csrc/deprocess.cu against the bytes of the reference's imagenet_deprocess_batch."""
+  g = load_golden('aux.pt')['deprocess']
+  x = g['imgs']
+  N, C, H, W = x.shape
+  inv_std = torch.tensor([1.0 / s for s in (0.229, 0.224, 0.225)], dtype=torch.float32)
+  neg_mean = torch.tensor([-m for m in (0.485, 0.456, 0.406)], dtype=torch.float32)
+  views = {'nchw': x, 'nhwc-backed': x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)}
+  for name, src in views.items():
+    for rescale, want in ((1, g['rescaled']), (0, g['plain'])):
+      out = torch.zeros(N, C, H, W, dtype=torch.uint8)
+      mm = torch.zeros(2 * N, dtype=torch.int32)
+      sn, sc, sh, sw = src.stride()
+      on, oc, oh, ow = out.stride()
+      _ok(lib, lib.sg2im_deprocess(_p(src), sn, sc, sh, sw, N, C, H, W, _p(inv_std), _p(neg_mean),
+                                   rescale, _p(mm), _p(out), on, oc, oh, ow, None))
+      assert torch.equal(out, want), (name, rescale)
+  # channels-last output
+  out = torch.zeros(N, H, W, C, dtype=torch.uint8)
+  mm = torch.zeros(2 * N, dtype=torch.int32)
+  sn, sc, sh, sw = x.stride()
+  on, oh, ow, oc = out.stride()
+  _ok(lib, lib.sg2im_deprocess(_p(x), sn, sc, sh, sw, N, C, H, W, _p(inv_std), _p(neg_mean), 1,
+                               _p(mm), _p(out), on, oc, oh, ow, None))
+  assert torch.equal(out.permute(0, 3, 1, 2), g['rescaled'])
