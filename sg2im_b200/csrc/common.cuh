@@ -15,7 +15,7 @@
 // emulation harness; under nvcc these expand to the plain CUDA forms.
 #ifdef SG2IM_EMUL
 #define SG_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  emul_launch(dim3(grid), (unsigned)(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
+  emul_launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
 #define SG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul_dynamic_smem())
 #else
 #define SG_LAUNCH(kernel, grid, block, smem, stream, ...) \

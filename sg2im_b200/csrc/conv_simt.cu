@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) conv_igemm_kernel(ConvP p) {
 // Cout <= 4 forward: thread per output pixel, weights (K x 4, zero padded) in
 // shared memory.  Memory-bound on x.
 __global__ void __launch_bounds__(256) conv_skinny_kernel(ConvP p) {
-  extern __shared__ __align__(16) float ws[];            // [K][4]
+  SG_DYN_SMEM(float, ws);            // [K][4]
   const int64_t K = (int64_t)p.KH * p.KW * p.Cin;
   for (int64_t i = threadIdx.x; i < K * 4; i += blockDim.x) {
     int64_t k = i >> 2; int j = (int)(i & 3);
@@ -409,11 +409,11 @@ extern "C" int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t s
   int64_t K = (int64_t)KH * KW * Cin;
   if (mode == 0 && Cout <= 4 && K * 16 <= 48 * 1024) {
     unsigned grid = (unsigned)ceil_div64(p.M, 256);
-    conv_skinny_kernel<<<grid, 256, (size_t)(K * 16), st>>>(p);
+    SG_LAUNCH(conv_skinny_kernel, grid, 256, (size_t)(K * 16), st, p);
   } else {
     dim3 grid((unsigned)ceil_div64(p.M, BM), (unsigned)ceil_div64(Cout, BN));
-    if (mode == 0) conv_igemm_kernel<0><<<grid, 256, 0, st>>>(p);
-    else           conv_igemm_kernel<1><<<grid, 256, 0, st>>>(p);
+    if (mode == 0) SG_LAUNCH(conv_igemm_kernel<0>, grid, 256, 0, st, p);
+    else           SG_LAUNCH(conv_igemm_kernel<1>, grid, 256, 0, st, p);
   }
   SG_LAUNCH_OK();
   return 0;
@@ -437,7 +437,7 @@ extern "C" int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_
     int64_t rpb = ceil_div64(M, blocks);
     if (rpb < 64) rpb = 64;
     blocks = ceil_div64(M, rpb);
-    wgrad_skinny_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, xs, M, (int)Cin, dy,
+    SG_LAUNCH(wgrad_skinny_kernel, (unsigned)blocks, 256, 0, as_stream(stream), x, xs, M, (int)Cin, dy,
                                                                            (int)Cout, rpb, dw);
     SG_LAUNCH_OK();
     return 0;
@@ -461,7 +461,7 @@ extern "C" int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_
   p.m_per_split = ceil_div64(ceil_div64(p.M, split), BK) * BK;
   split = ceil_div64(p.M, p.m_per_split);
   dim3 grid((unsigned)(KH * KW * p.ci_tiles), (unsigned)ceil_div64(Cout, BN), (unsigned)split);
-  conv_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
+  SG_LAUNCH(conv_wgrad_kernel, grid, 256, 0, as_stream(stream), p);
   SG_LAUNCH_OK();
   return 0;
 }

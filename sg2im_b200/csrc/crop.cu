@@ -86,7 +86,7 @@ extern "C" int sg2im_crop_fwd(const float* feats, int64_t sfn, int64_t sfh, int6
   SG_ARG(aligned16(boxes));
   if (B == 0) return 0;
   int64_t total = B * HH * WW;
-  crop_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+  SG_LAUNCH(crop_fwd_kernel, (unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream), 
       feats, sfn, sfh, sfw, sfc, N, (int)H, (int)W, (int)C, boxes, idx, B, (int)HH, (int)WW,
       align_corners, out);
   SG_LAUNCH_OK();
@@ -102,7 +102,7 @@ extern "C" int sg2im_crop_bwd(const float* dout, const float* boxes, const int64
   SG_ARG(aligned16(boxes));
   if (B == 0) return 0;
   int64_t total = B * HH * WW;
-  crop_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+  SG_LAUNCH(crop_bwd_kernel, (unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream), 
       dout, boxes, idx, N, (int)H, (int)W, (int)C, B, (int)HH, (int)WW, align_corners, dfeats);
   SG_LAUNCH_OK();
   return 0;

@@ -136,9 +136,9 @@ extern "C" int sg2im_csr_build(const int64_t* idx, int64_t T, int64_t idx_stride
   cudaStream_t st = as_stream(stream);
   const int warps = 8;
   unsigned grid = (unsigned)ceil_div64(R, warps);
-  csr_scan_rows<0><<<grid, warps * 32, 0, st>>>(idx, T, idx_stride, nroles, R, row_ptr, entries);
-  csr_scan_counts<<<1, 1024, 0, st>>>(row_ptr, R);
-  csr_scan_rows<1><<<grid, warps * 32, 0, st>>>(idx, T, idx_stride, nroles, R, row_ptr, entries);
+  SG_LAUNCH(csr_scan_rows<0>, grid, warps * 32, 0, st, idx, T, idx_stride, nroles, R, row_ptr, entries);
+  SG_LAUNCH(csr_scan_counts, 1, 1024, 0, st, row_ptr, R);
+  SG_LAUNCH(csr_scan_rows<1>, grid, warps * 32, 0, st, idx, T, idx_stride, nroles, R, row_ptr, entries);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -154,8 +154,8 @@ extern "C" int sg2im_triple_gather(const float* rows, const float* mid, const in
              (mid == nullptr || aligned16(mid));
   int64_t total = T * (2 * Wr + Wm) / (vec ? 4 : 1);
   unsigned grid = (unsigned)ceil_div64(total, 256);
-  if (vec) triple_gather_kernel<4><<<grid, 256, 0, st>>>(rows, mid, edges, T, Wr, Wm, row_ptr, out);
-  else     triple_gather_kernel<1><<<grid, 256, 0, st>>>(rows, mid, edges, T, Wr, Wm, row_ptr, out);
+  if (vec) SG_LAUNCH(triple_gather_kernel<4>, grid, 256, 0, st, rows, mid, edges, T, Wr, Wm, row_ptr, out);
+  else     SG_LAUNCH(triple_gather_kernel<1>, grid, 256, 0, st, rows, mid, edges, T, Wr, Wm, row_ptr, out);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -170,8 +170,8 @@ extern "C" int sg2im_segment_sum(const float* src, int64_t src_stride, int64_t o
              aligned16(src) && aligned16(out);
   int64_t total = R * W / (vec ? 4 : 1);
   unsigned grid = (unsigned)ceil_div64(total, 128);
-  if (vec) segment_sum_kernel<4><<<grid, 128, 0, st>>>(src, src_stride, off0, off1, W, row_ptr, entries, R, avg, out);
-  else     segment_sum_kernel<1><<<grid, 128, 0, st>>>(src, src_stride, off0, off1, W, row_ptr, entries, R, avg, out);
+  if (vec) SG_LAUNCH(segment_sum_kernel<4>, grid, 128, 0, st, src, src_stride, off0, off1, W, row_ptr, entries, R, avg, out);
+  else     SG_LAUNCH(segment_sum_kernel<1>, grid, 128, 0, st, src, src_stride, off0, off1, W, row_ptr, entries, R, avg, out);
   SG_LAUNCH_OK();
   return 0;
 }

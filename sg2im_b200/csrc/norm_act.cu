@@ -141,7 +141,7 @@ int launch_colreduce4(F4 f, int64_t M, int64_t C, double* sums, int nout, cudaSt
   int64_t rblocks = ceil_div64(M, rpb);
   if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
   dim3 grid((unsigned)cblocks, (unsigned)rblocks);
-  colreduce4_kernel<F4><<<grid, 256, 0, st>>>(f, M, C, rpb, sums, nout, TX);
+  SG_LAUNCH(colreduce4_kernel<F4>, grid, 256, 0, st, f, M, C, rpb, sums, nout, TX);
   return 0;
 }
 
@@ -167,7 +167,7 @@ int launch_colreduce(F f, int64_t M, int64_t C, double* sums, int nout, cudaStre
   int64_t rblocks = ceil_div64(M, rpb);
   if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
   dim3 grid((unsigned)cblocks, (unsigned)rblocks);
-  colreduce_kernel<F><<<grid, dim3(RED_TX, RED_TY), 0, st>>>(f, M, C, rpb, sums, nout);
+  SG_LAUNCH(colreduce_kernel<F>, grid, dim3(RED_TX, RED_TY), 0, st, f, M, C, rpb, sums, nout);
   return 0;
 }
 
@@ -475,11 +475,11 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
       return 0;
     }
   }
-  zero_doubles<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, C);
+  SG_LAUNCH(zero_doubles, (unsigned)ceil_div64(C, 256), 256, 0, st, scratch, C);
   StatsF f{x, C};
   if (C % 4 == 0 && aligned16(x)) launch_colreduce4(f, M, C, scratch, 1, st);
   else launch_colreduce(f, M, C, scratch, 1, st);
-  doubles_to_float<<<(unsigned)ceil_div64(C, 256), 256, 0, st>>>(scratch, out, C);
+  SG_LAUNCH(doubles_to_float, (unsigned)ceil_div64(C, 256), 256, 0, st, scratch, out, C);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -490,7 +490,7 @@ extern "C" int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbi
                                  float* scale, float* shift, float* save, sg2im_stream_t stream) {
   SG_ARG(scale && shift && save && C >= 1 && count >= 1 && unbias_mult >= 1);
   SG_ARG(training ? sums != nullptr : (running_mean && running_var));
-  bn_finalize_kernel<<<(unsigned)ceil_div64(C, 128), 128, 0, as_stream(stream)>>>(
+  SG_LAUNCH(bn_finalize_kernel, (unsigned)ceil_div64(C, 128), 128, 0, as_stream(stream), 
       sums, count, unbias_mult, C, gamma, beta, eps, momentum, training, running_mean,
       running_var, scale, shift, save);
   SG_LAUNCH_OK();
@@ -515,11 +515,11 @@ extern "C" int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t
     sg2im_scale_act_fwd_v2(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32,
                            st);
   else if (vec && small)
-    scale_act_fwd_kernel<4, U><<<grid, 256, 0, st>>>(x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff, round_tf32);
+    SG_LAUNCH((scale_act_fwd_kernel<4, U>), grid, 256, 0, st, x, (U)N, (U)H, (U)W, (U)C, scale, shift, slope, up, y, (U)y_cstride, (U)y_coff, round_tf32);
   else if (vec)
-    scale_act_fwd_kernel<4, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
+    SG_LAUNCH((scale_act_fwd_kernel<4, int64_t>), grid, 256, 0, st, x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
   else
-    scale_act_fwd_kernel<1, int64_t><<<grid, 256, 0, st>>>(x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
+    SG_LAUNCH((scale_act_fwd_kernel<1, int64_t>), grid, 256, 0, st, x, N, H, W, C, scale, shift, slope, up, y, y_cstride, y_coff, round_tf32);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -562,13 +562,13 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
     sg2im_bn_bwd_apply_v2(dy, dy_cstride, dy_coff, x, N, H, W, C, scale, shift, save, slope, up,
                           sums, dx, st);
   else if (vec)
-    scale_act_bwd_apply4_kernel<<<(unsigned)ceil_div64(M * (C / 4), 256), 256, 0, st>>>(
+    SG_LAUNCH(scale_act_bwd_apply4_kernel, (unsigned)ceil_div64(M * (C / 4), 256), 256, 0, st, 
         ag, save, M, C, training, sums, dx);
   else
-    scale_act_bwd_apply_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(
+    SG_LAUNCH(scale_act_bwd_apply_kernel, (unsigned)ceil_div64(M * C, 256), 256, 0, st, 
         ag, save, M, C, training, sums, dx);
   if ((dgamma || dbeta) && sums)
-    bn_param_grads<<<(unsigned)ceil_div64(C, 128), 128, 0, st>>>(sums, C, dgamma, dbeta);
+    SG_LAUNCH(bn_param_grads, (unsigned)ceil_div64(C, 128), 128, 0, st, sums, C, dgamma, dbeta);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -584,8 +584,8 @@ extern "C" int sg2im_avgpool2_fwd(const float* x, int64_t x_cstride, int64_t x_c
   int64_t total = N * (H / 2) * (W / 2) * (C / (vec ? 4 : 1));
   unsigned grid = (unsigned)ceil_div64(total, 256);
   cudaStream_t st = as_stream(stream);
-  if (vec) avgpool2_fwd_kernel<4><<<grid, 256, 0, st>>>(x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
-  else     avgpool2_fwd_kernel<1><<<grid, 256, 0, st>>>(x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
+  if (vec) SG_LAUNCH(avgpool2_fwd_kernel<4>, grid, 256, 0, st, x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
+  else     SG_LAUNCH(avgpool2_fwd_kernel<1>, grid, 256, 0, st, x, x_cstride, x_coff, N, H, W, C, y, y_cstride, y_coff);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -601,8 +601,8 @@ extern "C" int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int6
   int64_t total = N * H * W * (C / (vec ? 4 : 1));
   unsigned grid = (unsigned)ceil_div64(total, 256);
   cudaStream_t st = as_stream(stream);
-  if (vec) avgpool2_bwd_kernel<4><<<grid, 256, 0, st>>>(dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
-  else     avgpool2_bwd_kernel<1><<<grid, 256, 0, st>>>(dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
+  if (vec) SG_LAUNCH(avgpool2_bwd_kernel<4>, grid, 256, 0, st, dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
+  else     SG_LAUNCH(avgpool2_bwd_kernel<1>, grid, 256, 0, st, dcoarse, dc_cstride, dc_coff, N, H, W, C, dfine, df_cstride, df_coff, accumulate);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -611,7 +611,7 @@ extern "C" int sg2im_act_bwd(const float* dy, const float* y, float slope, int64
                              sg2im_stream_t stream) {
   SG_ARG(dy && y && dx && n >= 0);
   if (n == 0) return 0;
-  act_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(dy, y, slope, n, dx);
+  SG_LAUNCH(act_bwd_kernel, (unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream), dy, y, slope, n, dx);
   SG_LAUNCH_OK();
   return 0;
 }
@@ -678,10 +678,10 @@ extern "C" int sg2im_s2d_fwd(const float* x, int64_t sxn, int64_t sxh, int64_t s
   int64_t total = N * ((H + 1) / 2) * ((W + 1) / 2) * 4 * C;
   if (sxc == 1 && C % 4 == 0 && sxn % 4 == 0 && sxh % 4 == 0 && sxw % 4 == 0 && aligned16(x) &&
       aligned16(out))
-    s2d_fwd4_kernel<<<(unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream)>>>(
+    SG_LAUNCH(s2d_fwd4_kernel, (unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream), 
         x, sxn, sxh, sxw, N, H, W, C, out);
   else
-    s2d_fwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(
+    SG_LAUNCH(s2d_fwd_kernel, (unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream), 
         x, sxn, sxh, sxw, sxc, N, H, W, C, out);
   SG_LAUNCH_OK();
   return 0;
@@ -692,9 +692,9 @@ extern "C" int sg2im_s2d_bwd(const float* dout, int64_t N, int64_t H, int64_t W,
   SG_ARG(dout && dx && N >= 1 && H >= 1 && W >= 1 && C >= 1);
   int64_t total = N * H * W * C;
   if (C % 4 == 0 && aligned16(dout) && aligned16(dx))
-    s2d_bwd4_kernel<<<(unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
+    SG_LAUNCH(s2d_bwd4_kernel, (unsigned)ceil_div64(total / 4, 256), 256, 0, as_stream(stream), dout, N, H, W, C, dx);
   else
-    s2d_bwd_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(dout, N, H, W, C, dx);
+    SG_LAUNCH(s2d_bwd_kernel, (unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream), dout, N, H, W, C, dx);
   SG_LAUNCH_OK();
   return 0;
 }

@@ -17,7 +17,7 @@ template <int TT>
 __global__ void __launch_bounds__(256)
 pack_oihw_kernel(const float* __restrict__ w, int Co, int Ci, int CiUse, int Trt,
                  float* __restrict__ fwd, float* __restrict__ dgr, int rnd) {
-  extern __shared__ float sm[];                 // [PT co][PT * T + 1]
+  SG_DYN_SMEM(float, sm);                 // [PT co][PT * T + 1]
   const int T = TT ? TT : Trt;
   const int ld = PT * T + 1;
   const int co0 = blockIdx.y * PT, ci0 = blockIdx.x * PT;
@@ -52,7 +52,7 @@ template <int TT>
 __global__ void __launch_bounds__(256)
 unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci, int CiUse, int Trt,
                     float* __restrict__ grad, int accumulate) {
-  extern __shared__ float sm[];
+  SG_DYN_SMEM(float, sm);
   const int T = TT ? TT : Trt;
   const int ld = PT * T + 1;
   const int co0 = blockIdx.y * PT, ci0 = blockIdx.x * PT;
@@ -76,22 +76,26 @@ unpack_wgrad_kernel(const float* __restrict__ dw, int Co, int Ci, int CiUse, int
 template <int TT>
 void launch_pack(dim3 grid, size_t smem, cudaStream_t st, const float* w, int Co, int Ci, int cu,
                  int T, float* f, float* d, int rnd) {
+#ifndef SG2IM_EMUL
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(pack_oihw_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  pack_oihw_kernel<TT><<<grid, 256, smem, st>>>(w, Co, Ci, cu, T, f, d, rnd);
+#endif
+  SG_LAUNCH(pack_oihw_kernel<TT>, grid, 256, smem, st, w, Co, Ci, cu, T, f, d, rnd);
 }
 template <int TT>
 void launch_unpack(dim3 grid, size_t smem, cudaStream_t st, const float* dw, int Co, int Ci, int cu,
                    int T, float* g, int acc) {
+#ifndef SG2IM_EMUL
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(unpack_wgrad_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  unpack_wgrad_kernel<TT><<<grid, 256, smem, st>>>(dw, Co, Ci, cu, T, g, acc);
+#endif
+  SG_LAUNCH(unpack_wgrad_kernel<TT>, grid, 256, smem, st, dw, Co, Ci, cu, T, g, acc);
 }
 }  // namespace
 

@@ -37,7 +37,7 @@ struct dim3 {
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 namespace emul {
 
@@ -58,8 +58,10 @@ inline std::mutex& atomic_lock() { static std::mutex m; return m; }
 inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
-static inline unsigned emul_lane() { return threadIdx.x & 31u; }
-static inline unsigned emul_warp() { return threadIdx.x >> 5; }
+// linear thread id inside the block (x fastest, like the hardware's warp packing)
+static inline unsigned emul_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+static inline unsigned emul_lane() { return emul_tid() & 31u; }
+static inline unsigned emul_warp() { return emul_tid() >> 5; }
 
 static inline void __syncthreads() { emul::current()->block_bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
@@ -73,9 +75,9 @@ static inline T emul_shfl_from(T v, unsigned src_lane) {
   emul::Block* b = emul::current();
   uint32_t bits;
   std::memcpy(&bits, &v, 4);
-  b->xch[threadIdx.x] = bits;
+  b->xch[emul_tid()] = bits;
   b->warp_bar[emul_warp()]->arrive_and_wait();
-  uint32_t got = b->xch[(threadIdx.x & ~31u) + (src_lane & 31u)];
+  uint32_t got = b->xch[(emul_tid() & ~31u) + (src_lane & 31u)];
   b->warp_bar[emul_warp()]->arrive_and_wait();      // slots free for the next exchange
   T out;
   std::memcpy(&out, &got, 4);
@@ -85,10 +87,11 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return 
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emul_shfl_from(v, emul_lane() ^ (unsigned)m); }
 static inline unsigned __ballot_sync(unsigned, bool pred) {
   emul::Block* b = emul::current();
-  b->xch[threadIdx.x] = pred ? 1u : 0u;
+  b->xch[emul_tid()] = pred ? 1u : 0u;
   b->warp_bar[emul_warp()]->arrive_and_wait();
   unsigned m = 0;
-  for (unsigned l = 0; l < 32; ++l) m |= (b->xch[(threadIdx.x & ~31u) + l] & 1u) << l;
+  const unsigned lanes = std::min(32u, b->nthreads - (emul_tid() & ~31u));
+  for (unsigned l = 0; l < lanes; ++l) m |= (b->xch[(emul_tid() & ~31u) + l] & 1u) << l;
   b->warp_bar[emul_warp()]->arrive_and_wait();
   return m;
 }
@@ -106,6 +109,11 @@ static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
   uint32_t old = *p; *p = std::max(old, v); return old;
 }
 
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline float __fadd_rn(float a, float b) { return a + b; }       // no contraction on the host build
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 using std::min;
@@ -113,8 +121,9 @@ using std::max;
 
 // Run `body` (a call of the kernel with its arguments bound) for every thread of every block.
 // Threads that return early simply drop out of the block barrier, like exited CUDA threads.
-static inline void emul_launch(dim3 grid, unsigned nthreads, size_t dyn_smem_bytes,
+static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
                                const std::function<void()>& body) {
+  const unsigned nthreads = block.x * block.y * block.z;
   emul::Block blk;
   blk.nthreads = nthreads;
   blk.xch.assign(nthreads, 0);
@@ -135,9 +144,9 @@ static inline void emul_launch(dim3 grid, unsigned nthreads, size_t dyn_smem_byt
         th.reserve(nthreads);
         for (unsigned t = 0; t < nthreads; ++t)
           th.emplace_back([&, t]() {
-            threadIdx = uint3{t, 0, 0};
+            threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
             blockIdx = uint3{bx, by, bz};
-            blockDim = dim3(nthreads, 1, 1);
+            blockDim = block;
             gridDim = grid;
             body();
             blk.block_bar->arrive_and_drop();

@@ -273,3 +273,204 @@ def test_deprocess_source_on_cpu_bit_exact(lib):
   _ok(lib, lib.sg2im_deprocess(_p(x), sn, sc, sh, sw, N, C, H, W, _p(inv_std), _p(neg_mean), 1,
                                _p(mm), _p(out), on, oc, oh, ow, None))
   assert torch.equal(out.permute(0, 3, 1, 2), g['rescaled'])
+
+
+# ---------------------------------------------------------------------------
+# First-generation kernels (graph, crop, pack, norm/act, exact-fp32 convolutions): these HAVE
+# run on the B200 (tests/test_gpu_*.py); executing their sources here puts the same parity
+# checks into the CPU suite and validates the emulator against hardware-proven code.
+# ---------------------------------------------------------------------------
+
+@pytest.fixture(scope='module')
+def api(lib):
+  from sg2im_b200._lib import SIGNATURES
+  for name, sig in SIGNATURES.items():
+    if hasattr(lib, name):
+      getattr(lib, name).argtypes = sig
+  return lib
+
+
+@pytest.mark.parametrize('T,O,H,D,avg', [(10, 7, 16, 8, True), (448, 320, 32, 8, True),
+                                         (33, 5, 6, 3, False), (64, 9, 12, 4, True)])
+def test_graph_kernels_source_on_cpu_bit_exact(api, T, O, H, D, avg):
+  """csrc/graph.cu: CSR build (ballot / popc compaction) + ordered segment sum must equal the
+  CPU scatter_add of the reference's pooling BIT FOR BIT (sg2im/graph.py:85-114)."""
+  from oracle import sg2im_oracle as orc
+  g = torch.Generator().manual_seed(T)
+  edges = torch.randint(0, O, (T, 2), generator=g)
+  edges[:, 0] = torch.where(edges[:, 0] == O - 1, torch.zeros(()).long(), edges[:, 0])   # leave a row unused
+  new_t = torch.randn(T, 2 * H + D, generator=g)
+  row_ptr = torch.zeros(O + 1, dtype=torch.int32)
+  entries = torch.zeros(2 * T, dtype=torch.int32)
+  _ok(api, api.sg2im_csr_build(_p(edges), T, 2, 2, O, _p(row_ptr), _p(entries), None))
+  counts = torch.bincount(edges.reshape(-1), minlength=O)
+  assert torch.equal(row_ptr[1:].long() - row_ptr[:-1].long(), counts)
+  pooled = torch.full((O, H), float('nan'))
+  _ok(api, api.sg2im_segment_sum(_p(new_t), new_t.size(1), 0, H + D, H, _p(row_ptr), _p(entries), O,
+                                 int(avg), _p(pooled), None))
+  ref = orc.graph_pool(new_t, edges, O, H, D, 'avg' if avg else 'sum')
+  assert torch.equal(pooled, ref)
+  # forward gather cat([obj[s], pred, obj[o]])
+  obj, pred = torch.randn(O, H, generator=g), torch.randn(T, D, generator=g)
+  out = torch.empty(T, 2 * H + D)
+  _ok(api, api.sg2im_triple_gather(_p(obj), _p(pred), _p(edges), T, H, D, None, _p(out), None))
+  assert torch.equal(out, torch.cat([obj[edges[:, 0]], pred, obj[edges[:, 1]]], dim=1))
+
+
+def test_crop_kernels_source_on_cpu(api):
+  from oracle import sg2im_oracle as orc
+  g = load_golden('crop.pt')
+  feats, boxes, idx = g['feats'], g['boxes'], g['bbox_to_feats']
+  N, C, H, W = feats.shape
+  B, HH = boxes.size(0), 8
+  nhwc = feats.permute(0, 2, 3, 1)                       # strided view of the NCHW fixture
+  sn, sh, sw, sc = nhwc.stride()
+  out = torch.empty(B, HH, HH, C)
+  _ok(api, api.sg2im_crop_fwd(_p(feats), sn, sh, sw, sc, N, H, W, C, _p(boxes), _p(idx), B, HH, HH, 0,
+                              _p(out), None))
+  assert rel_err(out.permute(0, 3, 1, 2), g['crops']) < 1e-5
+  fr = feats.clone().requires_grad_(True)
+  ref = orc.crop_bbox_batch(fr, boxes, idx, HH)
+  gy = torch.randn(B, HH, HH, C, generator=torch.Generator().manual_seed(1))
+  ref.backward(gy.permute(0, 3, 1, 2))
+  dfeats = torch.zeros(N, H, W, C)
+  _ok(api, api.sg2im_crop_bwd(_p(gy), _p(boxes), _p(idx), N, H, W, C, B, HH, HH, 0, _p(dfeats), None))
+  assert rel_err(dfeats.permute(0, 3, 1, 2), fr.grad) < 1e-5
+
+
+@pytest.mark.parametrize('Co,Ci,cu,K', [(40, 36, 36, 3), (33, 64, 32, 3), (8, 12, 12, 1), (16, 8, 8, 2),
+                                        (5, 7, 7, 5)])
+def test_pack_kernels_source_on_cpu(api, Co, Ci, cu, K):
+  T = K * K
+  w = torch.randn(Co, Ci, K, K, generator=torch.Generator().manual_seed(Co))
+  fwd, dgr = torch.empty(T, Co, cu), torch.empty(T, cu, Co)
+  _ok(api, api.sg2im_pack_weights(_p(w), Co, Ci, cu, T, _p(fwd), _p(dgr), 0, None))
+  ws = w[:, :cu].reshape(Co, cu, T)
+  assert torch.equal(fwd, ws.permute(2, 0, 1))
+  assert torch.equal(dgr, ws.flip(2).permute(2, 1, 0))
+  # round-to-nearest TF32 variant, one layout at a time (what ops._pack does)
+  fr = torch.empty(T, Co, cu)
+  _ok(api, api.sg2im_pack_weights(_p(w), Co, Ci, cu, T, _p(fr), None, 1, None))
+  assert int((fr.view(torch.int32) & 0x1fff).abs().max()) == 0
+  assert float((fr - fwd).abs().max()) <= float(fwd.abs().max()) * 2.0 ** -11
+  # unpack: wgrad layout -> OIHW, with and without accumulation, partial channel use
+  dw = torch.randn(T, cu, Co, generator=torch.Generator().manual_seed(1))
+  grad = torch.zeros(Co, Ci, K, K)
+  _ok(api, api.sg2im_unpack_wgrad(_p(dw), Co, Ci, cu, T, _p(grad), 0, None))
+  want = torch.zeros(Co, Ci, T)
+  want[:, :cu] = dw.permute(2, 1, 0)
+  assert torch.equal(grad.view(Co, Ci, T), want)
+  _ok(api, api.sg2im_unpack_wgrad(_p(dw), Co, Ci, cu, T, _p(grad), 1, None))
+  assert torch.equal(grad.view(Co, Ci, T), 2 * want)
+
+
+@pytest.mark.parametrize('N,H,W,C,up,extra', [(2, 8, 8, 16, 1, 0), (2, 4, 6, 12, 2, 8), (3, 5, 7, 5, 1, 3)])
+def test_norm_act_kernels_source_on_cpu(api, N, H, W, C, up, extra):
+  """csrc/norm_act.cu: batch statistics, finalize (running stats), the fused
+  BN+LeakyReLU+upsample+slice forward and its backward (generic kernels)."""
+  g = torch.Generator().manual_seed(C)
+  x = torch.randn(N, H, W, C, generator=g)
+  gamma, beta = torch.linspace(0.5, 1.5, C), torch.linspace(-0.2, 0.3, C)
+  M = N * H * W
+  sums = torch.zeros(2 * C, dtype=torch.float64)
+  _ok(api, api.sg2im_bn_stats(_p(x), M, C, _p(sums), None))
+  assert torch.allclose(sums[:C], x.double().reshape(M, C).sum(0), rtol=1e-6, atol=1e-6)
+  rm, rv = torch.zeros(C), torch.ones(C)
+  scale, shift, save = torch.empty(C), torch.empty(C), torch.empty(2 * C)
+  _ok(api, api.sg2im_bn_finalize(_p(sums), M, 1, C, _p(gamma), _p(beta), 1e-5, 0.1, 1, _p(rm), _p(rv),
+                                 _p(scale), _p(shift), _p(save), None))
+  bn = torch.nn.BatchNorm2d(C)
+  with torch.no_grad():
+    bn.weight.copy_(gamma); bn.bias.copy_(beta)
+  xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  y = F.leaky_relu(bn(xr), 0.2)
+  if up > 1:
+    y = F.interpolate(y, scale_factor=up, mode='nearest')
+  assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+  out = torch.full((N, H * up, W * up, C + extra), 7.0)
+  _ok(api, api.sg2im_scale_act_fwd(_p(x), N, H, W, C, _p(scale), _p(shift), 0.2, up, _p(out),
+                                   out.size(3), extra, 0, None))
+  assert rel_err(out[..., extra:], y.permute(0, 2, 3, 1)) < 1e-5
+  assert bool((out[..., :extra] == 7.0).all())
+  gy = torch.randn(N, H * up, W * up, C + extra, generator=g)
+  y.backward(gy[..., extra:].permute(0, 3, 1, 2))
+  bs = torch.zeros(2 * C, dtype=torch.float64)
+  _ok(api, api.sg2im_scale_act_bwd_reduce(_p(gy), gy.size(3), extra, _p(x), N, H, W, C, _p(scale),
+                                          _p(shift), _p(save), 0.2, up, _p(bs), None))
+  dx, dg, db = torch.empty(N, H, W, C), torch.empty(C), torch.empty(C)
+  _ok(api, api.sg2im_scale_act_bwd_apply(_p(gy), gy.size(3), extra, _p(x), N, H, W, C, _p(scale),
+                                         _p(shift), _p(save), 0.2, up, 1, _p(bs), _p(dx), _p(dg), _p(db),
+                                         None))
+  assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 1e-4
+  assert rel_err(dg, bn.weight.grad) < 1e-5 and rel_err(db, bn.bias.grad) < 1e-5
+
+
+def test_pool_s2d_act_colsum_sources_on_cpu(api):
+  g = torch.Generator().manual_seed(4)
+  x = torch.randn(2, 8, 6, 12, generator=g)
+  out = torch.full((2, 4, 3, 16), 7.0)
+  _ok(api, api.sg2im_avgpool2_fwd(_p(x), 12, 4, 2, 8, 6, 8, _p(out), 16, 4, None))   # channels 4..11 -> 4..11
+  ref = F.avg_pool2d(x[..., 4:12].permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+  assert rel_err(out[..., 4:12], ref) < 1e-6 and bool((out[..., :4] == 7.0).all())
+  dfine = torch.ones(2, 8, 6, 12)
+  dco = torch.randn(2, 4, 3, 16, generator=g)
+  _ok(api, api.sg2im_avgpool2_bwd(_p(dco), 16, 4, 2, 8, 6, 8, _p(dfine), 12, 4, 1, None))
+  up = (dco[..., 4:12] * 0.25).repeat_interleave(2, 1).repeat_interleave(2, 2)
+  assert rel_err(dfine[..., 4:12], 1 + up) < 1e-6 and bool((dfine[..., :4] == 1).all())
+  # space-to-depth (odd sizes are zero-padded) and back
+  xs = torch.randn(2, 7, 5, 4, generator=g)
+  s2d = torch.empty(2, 4, 3, 16)
+  sn, sh, sw, sc = xs.stride()
+  _ok(api, api.sg2im_s2d_fwd(_p(xs), sn, sh, sw, sc, 2, 7, 5, 4, _p(s2d), None))
+  pad = F.pad(xs, (0, 0, 0, 1, 0, 1))
+  want = pad.view(2, 4, 2, 3, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(2, 4, 3, 16)
+  assert torch.equal(s2d, want)
+  back = torch.empty(2, 7, 5, 4)
+  _ok(api, api.sg2im_s2d_bwd(_p(s2d), 2, 7, 5, 4, _p(back), None))
+  assert torch.equal(back, xs)
+  # activation backward and bias-gradient column sum
+  yv, dy = torch.randn(50, 7, generator=g), torch.randn(50, 7, generator=g)
+  dxv = torch.empty(50, 7)
+  _ok(api, api.sg2im_act_bwd(_p(dy), _p(yv), 0.2, 350, _p(dxv), None))
+  assert torch.equal(dxv, torch.where(yv > 0, dy, dy * 0.2))
+  cs, scratch = torch.empty(7), torch.empty(7, dtype=torch.float64)
+  _ok(api, api.sg2im_colsum(_p(dy), 50, 7, _p(cs), _p(scratch), None))
+  assert torch.allclose(cs, dy.double().sum(0).float(), rtol=1e-6, atol=1e-6)
+
+
+CONV_CASES = [  # N, H, W, Ci, Co, K, S, P, act
+    (2, 6, 6, 5, 7, 3, 1, 1, 1), (1, 9, 8, 4, 6, 4, 2, 0, 0), (3, 1, 1, 20, 9, 1, 1, 0, 1),
+    (1, 10, 10, 3, 130, 3, 1, 1, 0), (2, 5, 5, 8, 3, 1, 1, 0, 0)]
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,S,P,act', CONV_CASES)
+def test_exact_fp32_conv_sources_on_cpu(api, N, H, W, Ci, Co, K, S, P, act):
+  """csrc/conv_simt.cu (forward, data gradient, weight gradient, skinny variants) vs torch."""
+  g = torch.Generator().manual_seed(Ci * Co)
+  x = torch.randn(N, Ci, H, W, generator=g)             # NCHW storage, addressed through strides
+  w = torch.randn(Co, Ci, K, K, generator=g) * 0.2
+  b = torch.randn(Co, generator=g)
+  xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+  pre = F.conv2d(xr, wr, b, stride=S, padding=P)
+  ref = F.leaky_relu(pre, 0.2) if act else pre
+  Ho, Wo = ref.shape[2], ref.shape[3]
+  nhwc = x.permute(0, 2, 3, 1)
+  sn, sh, sw, sc = nhwc.stride()
+  wf = w.permute(2, 3, 1, 0).reshape(K * K * Ci, Co).contiguous()
+  y = torch.full((N, Ho, Wo, Co + 2), 7.0)
+  _ok(api, api.sg2im_conv_igemm(0, _p(x), sn, sh, sw, sc, N, H, W, Ci, _p(wf), _p(b), K, K, S, P, Ho, Wo,
+                                Co, act, 0.2, _p(y), Co + 2, 2, None))
+  assert rel_err(y[..., 2:], ref.permute(0, 2, 3, 1)) < 1e-5
+  assert bool((y[..., :2] == 7.0).all())
+  gy = torch.randn(N, Ho, Wo, Co, generator=g)
+  pre.backward(gy.permute(0, 3, 1, 2))
+  wd = w.permute(2, 3, 0, 1).reshape(K * K * Co, Ci).contiguous()
+  dx = torch.empty(N, H, W, Ci)
+  gs = gy.stride()
+  _ok(api, api.sg2im_conv_igemm(1, _p(gy), gs[0], gs[1], gs[2], gs[3], N, Ho, Wo, Co, _p(wd), None, K, K,
+                                S, P, H, W, Ci, 0, 0.0, _p(dx), Ci, 0, None))
+  assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 1e-5
+  dw = torch.zeros(K * K * Ci, Co)
+  _ok(api, api.sg2im_conv_wgrad(_p(x), sn, sh, sw, sc, N, H, W, Ci, _p(gy), K, K, S, P, Ho, Wo, Co,
+                                _p(dw), None))
+  assert rel_err(dw, wr.grad.permute(2, 3, 1, 0).reshape(K * K * Ci, Co)) < 1e-5
