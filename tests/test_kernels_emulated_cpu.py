@@ -33,6 +33,9 @@ def lib(tmp_path_factory):
   cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-DSG2IM_EMUL',
          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
          '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')] + src + ['-o', str(out)]
+  # e.g. SG2IM_EMUL_CXXFLAGS='-g -fsanitize=address,alignment,bounds' with LD_PRELOAD=libasan.so
+  # (memcheck of the kernel sources) or '-g -fsanitize=thread' with LD_PRELOAD=libtsan.so (racecheck)
+  cmd[1:1] = os.environ.get('SG2IM_EMUL_CXXFLAGS', '').split()
   subprocess.check_call(cmd)
   L = ctypes.CDLL(str(out))
   L.sg2im_layout_fwd.argtypes = [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
