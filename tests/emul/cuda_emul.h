@@ -1,8 +1,14 @@
 // TEST INFRASTRUCTURE ONLY — a host-side SIMT emulation of the CUDA builtins the
 // non-tensor-core kernels of sg2im_b200/csrc use, so that the KERNEL SOURCES THEMSELVES
 // (compiled by g++ with -DSG2IM_EMUL) can be executed on the CPU and checked against the
-// oracle without a GPU: one OS thread per CUDA thread of a block, blocks run one after
-// another, __syncthreads / warp shuffles / ballots as real barriers, atomics under a lock.
+// oracle without a GPU.  Two execution models behind the same builtins:
+//   default               every CUDA thread of a block is a cooperative fiber (ucontext) of ONE OS
+//                         thread; __syncthreads / warp shuffles / ballots yield to the next fiber
+//                         until the barrier completes.  Fast and deterministic.
+//   -DSG2IM_EMUL_THREADS  one OS thread per CUDA thread with real barriers and locked atomics:
+//                         true concurrency, for the sanitizer runs (tools/emul_sanitize.sh; TSan
+//                         then sees missing-barrier races, ASan sees out-of-bounds accesses).
+// Blocks run one after another in both models.
 // It checks index arithmetic, tiling, masking and reduction logic of the exact source that
 // nvcc compiles; it does not model memory ordering, timing or the tensor-core / TMA paths.
 #pragma once
@@ -18,6 +24,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#ifndef SG2IM_EMUL_THREADS
+#include <ucontext.h>
+#endif
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
@@ -40,7 +49,26 @@ struct dim3 {
 #define __align__(n) __attribute__((aligned(n)))
 
 namespace emul {
+inline unsigned long long& blocks_run() { static unsigned long long n = 0; return n; }   // test introspection
+inline std::mutex& atomic_lock() { static std::mutex m; return m; }
+}  // namespace emul
 
+#ifdef SG2IM_EMUL_THREADS
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+#else
+inline uint3 threadIdx, blockIdx;                       // one OS thread: plain globals, set per fiber
+inline dim3 blockDim, gridDim;
+#endif
+
+// linear thread id inside the block (x fastest, like the hardware's warp packing)
+static inline unsigned emul_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+static inline unsigned emul_lane() { return emul_tid() & 31u; }
+static inline unsigned emul_warp() { return emul_tid() >> 5; }
+
+#ifdef SG2IM_EMUL_THREADS
+// ------------------------------------------------------------------ OS-thread model
+namespace emul {
 struct Block {
   unsigned nthreads = 0;
   std::unique_ptr<std::barrier<>> block_bar;
@@ -48,25 +76,65 @@ struct Block {
   std::vector<uint32_t> xch;            // one exchange slot per thread (shuffles / ballots)
   std::vector<unsigned char> dyn_smem;
 };
-
 inline Block*& current() { static Block* b = nullptr; return b; }
-inline unsigned long long& blocks_run() { static unsigned long long n = 0; return n; }   // test introspection
-inline std::mutex& atomic_lock() { static std::mutex m; return m; }
-
+inline void block_sync() { current()->block_bar->arrive_and_wait(); }
+inline void warp_sync() { current()->warp_bar[emul_warp()]->arrive_and_wait(); }
 }  // namespace emul
-
-inline thread_local uint3 threadIdx, blockIdx;
-inline thread_local dim3 blockDim, gridDim;
-
-// linear thread id inside the block (x fastest, like the hardware's warp packing)
-static inline unsigned emul_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
-static inline unsigned emul_lane() { return emul_tid() & 31u; }
-static inline unsigned emul_warp() { return emul_tid() >> 5; }
-
-static inline void __syncthreads() { emul::current()->block_bar->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {
-  emul::current()->warp_bar[emul_warp()]->arrive_and_wait();
+#else
+// ------------------------------------------------------------------ fiber model
+namespace emul {
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  uint3 tid;
+  bool done = false;
+};
+struct Block {
+  unsigned nthreads = 0;
+  std::vector<Fiber> fibers;
+  ucontext_t main_ctx;
+  unsigned cur = 0;
+  unsigned alive = 0, arrived = 0;
+  unsigned long long gen = 0;
+  std::vector<unsigned> w_alive, w_arrived;
+  std::vector<unsigned long long> w_gen;
+  std::vector<uint32_t> xch;
+  std::vector<unsigned char> dyn_smem;
+  const std::function<void()>* body = nullptr;
+};
+inline Block*& current() { static Block* b = nullptr; return b; }
+inline void yield() { Block* b = current(); swapcontext(&b->fibers[b->cur].ctx, &b->main_ctx); }
+inline void block_sync() {
+  Block* b = current();
+  const unsigned long long g = b->gen;
+  if (++b->arrived == b->alive) { b->arrived = 0; ++b->gen; return; }
+  while (b->gen == g) yield();
 }
+inline void warp_sync() {
+  Block* b = current();
+  const unsigned w = emul_warp();
+  const unsigned long long g = b->w_gen[w];
+  if (++b->w_arrived[w] == b->w_alive[w]) { b->w_arrived[w] = 0; ++b->w_gen[w]; return; }
+  while (b->w_gen[w] == g) yield();
+}
+inline void fiber_exit_bookkeeping() {
+  // an exited thread no longer takes part in barriers; complete any barrier it was the last missing of
+  Block* b = current();
+  const unsigned w = b->cur >> 5;
+  if (--b->alive > 0 && b->arrived == b->alive) { b->arrived = 0; ++b->gen; }
+  if (--b->w_alive[w] > 0 && b->w_arrived[w] == b->w_alive[w]) { b->w_arrived[w] = 0; ++b->w_gen[w]; }
+}
+inline void trampoline() {
+  Block* b = current();
+  (*b->body)();
+  b->fibers[b->cur].done = true;
+  fiber_exit_bookkeeping();
+}
+}  // namespace emul
+#endif
+
+static inline void __syncthreads() { emul::block_sync(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emul::warp_sync(); }
 static inline void* emul_dynamic_smem() { return emul::current()->dyn_smem.data(); }
 
 template <class T>
@@ -76,9 +144,9 @@ static inline T emul_shfl_from(T v, unsigned src_lane) {
   uint32_t bits;
   std::memcpy(&bits, &v, 4);
   b->xch[emul_tid()] = bits;
-  b->warp_bar[emul_warp()]->arrive_and_wait();
+  emul::warp_sync();
   uint32_t got = b->xch[(emul_tid() & ~31u) + (src_lane & 31u)];
-  b->warp_bar[emul_warp()]->arrive_and_wait();      // slots free for the next exchange
+  emul::warp_sync();                                   // slots free for the next exchange
   T out;
   std::memcpy(&out, &got, 4);
   return out;
@@ -88,11 +156,11 @@ template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { retur
 static inline unsigned __ballot_sync(unsigned, bool pred) {
   emul::Block* b = emul::current();
   b->xch[emul_tid()] = pred ? 1u : 0u;
-  b->warp_bar[emul_warp()]->arrive_and_wait();
+  emul::warp_sync();
   unsigned m = 0;
   const unsigned lanes = std::min(32u, b->nthreads - (emul_tid() & ~31u));
   for (unsigned l = 0; l < lanes; ++l) m |= (b->xch[(emul_tid() & ~31u) + l] & 1u) << l;
-  b->warp_bar[emul_warp()]->arrive_and_wait();
+  emul::warp_sync();
   return m;
 }
 
@@ -120,38 +188,98 @@ using std::min;
 using std::max;
 
 // Run `body` (a call of the kernel with its arguments bound) for every thread of every block.
-// Threads that return early simply drop out of the block barrier, like exited CUDA threads.
+// Threads that return early stop taking part in that block's barriers, like exited CUDA threads.
+#ifdef SG2IM_EMUL_THREADS
 static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
                                const std::function<void()>& body) {
   const unsigned nthreads = block.x * block.y * block.z;
+  if (nthreads == 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
   emul::Block blk;
   blk.nthreads = nthreads;
   blk.xch.assign(nthreads, 0);
   blk.dyn_smem.assign(dyn_smem_bytes + 64, 0);
   emul::current() = &blk;
   const unsigned nwarps = (nthreads + 31) / 32;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        ++emul::blocks_run();
-        blk.block_bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)nthreads);
-        blk.warp_bar.clear();
-        for (unsigned w = 0; w < nwarps; ++w) {
-          unsigned lanes = std::min(32u, nthreads - w * 32);
-          blk.warp_bar.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)lanes));
-        }
-        std::vector<std::thread> th;
-        th.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-          th.emplace_back([&, t]() {
-            threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            blockIdx = uint3{bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
-            body();
-            blk.block_bar->arrive_and_drop();
-          });
-        for (auto& x : th) x.join();
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  auto arm = [&]() {                                   // fresh barriers for the next block
+    blk.block_bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)nthreads);
+    blk.warp_bar.clear();
+    for (unsigned w = 0; w < nwarps; ++w) {
+      unsigned lanes = std::min(32u, nthreads - w * 32);
+      blk.warp_bar.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)lanes));
+    }
+  };
+  arm();
+  std::barrier<> turn((std::ptrdiff_t)nthreads);       // all threads, between blocks
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      blockDim = block;
+      gridDim = grid;
+      for (unsigned long long b = 0; b < nblocks; ++b) {
+        blockIdx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y),
+                         (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+        body();
+        blk.block_bar->arrive_and_drop();              // done with this block's barrier
+        turn.arrive_and_wait();                        // everyone finished block b
+        if (t == 0) { ++emul::blocks_run(); if (b + 1 < nblocks) arm(); }
+        turn.arrive_and_wait();                        // barriers re-armed
       }
+    });
+  for (auto& x : th) x.join();
   emul::current() = nullptr;
 }
+#else
+static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
+                               const std::function<void()>& body) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  if (nthreads == 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+  static emul::Block blk;                              // fiber stacks are reused across launches
+  constexpr size_t STACK = 256 * 1024;
+  if (blk.fibers.size() < nthreads) blk.fibers.resize(nthreads);
+  for (unsigned t = 0; t < nthreads; ++t)
+    if (blk.fibers[t].stack.size() != STACK) blk.fibers[t].stack.resize(STACK);
+  blk.nthreads = nthreads;
+  blk.xch.assign(nthreads, 0);
+  blk.dyn_smem.assign(dyn_smem_bytes + 64, 0);
+  blk.body = &body;
+  const unsigned nwarps = (nthreads + 31) / 32;
+  emul::current() = &blk;
+  blockDim = block;
+  gridDim = grid;
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  for (unsigned long long b = 0; b < nblocks; ++b) {
+    const uint3 bid = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y),
+                            (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+    blk.alive = nthreads; blk.arrived = 0;
+    blk.w_alive.assign(nwarps, 0); blk.w_arrived.assign(nwarps, 0); blk.w_gen.assign(nwarps, 0);
+    for (unsigned t = 0; t < nthreads; ++t) {
+      emul::Fiber& f = blk.fibers[t];
+      f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      f.done = false;
+      ++blk.w_alive[t >> 5];
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack.data();
+      f.ctx.uc_stack.ss_size = f.stack.size();
+      f.ctx.uc_link = &blk.main_ctx;
+      makecontext(&f.ctx, (void (*)())emul::trampoline, 0);
+    }
+    unsigned remaining = nthreads;
+    while (remaining) {
+      for (unsigned t = 0; t < nthreads; ++t) {
+        emul::Fiber& f = blk.fibers[t];
+        if (f.done) continue;
+        blk.cur = t;
+        threadIdx = f.tid;
+        blockIdx = bid;
+        swapcontext(&blk.main_ctx, &f.ctx);
+        if (f.done) --remaining;
+      }
+    }
+    ++emul::blocks_run();
+  }
+  emul::current() = nullptr;
+}
+#endif

