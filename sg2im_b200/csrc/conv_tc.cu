@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using C = Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
+  SG_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* sA = smem;                                          // STAGES x 16 KB
@@ -84,20 +84,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_alloc(tmem_slot, (uint32_t)C::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -203,9 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    tc_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
   }
 }
 
@@ -250,7 +243,7 @@ struct HaloParams {
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  SG_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -270,20 +263,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
     for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_alloc(tmem_slot, 512u);
   }
   tc_fence_before();
   __syncthreads();
@@ -431,8 +419,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
-                 : "memory");
+    tc_dealloc(tmem_base, 512u);
   }
 }
 
@@ -440,6 +427,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
+#ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>,
@@ -450,9 +438,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
     }
     attr_set = true;
   }
+#endif
   int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  SG_LAUNCH(conv_tc_kernel<BN>, grid, NUM_THREADS, C::SMEM_BYTES, st, tmA, tmB, p);
   return 0;
 }
 
@@ -563,6 +552,7 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo B failed (%d)", (int)r); return -4; }
     }
+#ifndef SG2IM_EMUL
     static bool halo_attr = false;
     if (!halo_attr) {
       cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel,
@@ -573,9 +563,10 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
       }
       halo_attr = true;
     }
+#endif
     int items = h.groups * h.n_tiles;
     int grid = items < num_sms() ? items : num_sms();
-    conv_tc_halo_kernel<<<grid, H_THREADS, H_SMEM, as_stream(stream)>>>(hA, hB, h);
+    SG_LAUNCH(conv_tc_halo_kernel, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
     SG_LAUNCH_OK();
     return 0;
   }

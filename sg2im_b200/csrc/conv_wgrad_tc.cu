@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const WgParams p) {
   using C = WCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
+  SG_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
@@ -78,20 +78,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int total_items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDY)) : "memory");
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
     for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_alloc(tmem_slot, 512u);
   }
   tc_fence_before();
   __syncthreads();
@@ -223,14 +218,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
-                 : "memory");
+    tc_dealloc(tmem_base, 512u);
   }
 }
 
 template <int BN>
 int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p, cudaStream_t st) {
   using C = WCfg<BN>;
+#ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>,
@@ -241,9 +236,10 @@ int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p
     }
     attr_set = true;
   }
+#endif
   int items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
   int grid = items < num_sms() ? items : num_sms();
-  conv_wgrad_tc_kernel<BN><<<grid, WG_THREADS, C::SMEM_BYTES, st>>>(tmX, tmDY, p);
+  SG_LAUNCH(conv_wgrad_tc_kernel<BN>, grid, WG_THREADS, C::SMEM_BYTES, st, tmX, tmDY, p);
   return 0;
 }
 

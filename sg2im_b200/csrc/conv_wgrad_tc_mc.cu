@@ -54,42 +54,12 @@ struct MCfg {
                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
-               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load multicast to the CTAs in `mask`: data and complete_tx land at the same
-// smem / mbarrier offsets in every destination CTA
-__device__ __forceinline__ void tma_load_4d_mc(void* smem, const CUtensorMap* map, uint64_t* bar,
-                                               uint16_t mask, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(smem)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3)
-      : "memory");
-}
-// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
-
 template <int BN, int CS>
 __global__ void __launch_bounds__(MC_THREADS, 1)
 conv_wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmX,
                         const __grid_constant__ CUtensorMap tmDY, const McParams p) {
   using C = MCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
+  SG_DYN_SMEM(uint8_t, smem_raw);
   // dynamic smem starts at the same offset in every CTA of the launch; the 1 KB round-up is
   // therefore identical too, which the multicast (same-offset) addressing relies on
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -107,22 +77,17 @@ conv_wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmX,
   const int total_items = p.ci_tiles * p.splits * p.subgroups;      // per cluster
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDY)) : "memory");
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full[i], 1); mbar_init(&empty_b[i], 1); mbar_init(&empty_a[i], CS);
     }
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tc_alloc(tmem_slot, 512u);
   }
   tc_fence_before();
   __syncthreads();
@@ -260,14 +225,22 @@ conv_wgrad_tc_mc_kernel(const __grid_constant__ CUtensorMap tmX,
   cluster_sync_all();                              // peers may still signal this CTA's barriers until here
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
-                 : "memory");
+    tc_dealloc(tmem_base, 512u);
   }
 }
 
 template <int BN, int CS>
 int launch_mc(const CUtensorMap& tmX, const CUtensorMap& tmDY, const McParams& p, cudaStream_t st) {
   using C = MCfg<BN>;
+  const int items = p.ci_tiles * p.splits * p.subgroups;
+#ifdef SG2IM_EMUL
+  int max_clusters = num_sms() / CS;
+  int nclusters = items < max_clusters ? items : max_clusters;
+  emul_launch_cluster(CS, dim3((unsigned)(nclusters * CS)), dim3(MC_THREADS), (size_t)C::SMEM_BYTES,
+                      [=]() { conv_wgrad_tc_mc_kernel<BN, CS>(tmX, tmDY, p); });
+  (void)st;
+  return 0;
+#else
   auto kern = conv_wgrad_tc_mc_kernel<BN, CS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -278,7 +251,6 @@ int launch_mc(const CUtensorMap& tmX, const CUtensorMap& tmDY, const McParams& p
     }
     attr_set = true;
   }
-  const int items = p.ci_tiles * p.splits * p.subgroups;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -303,6 +275,7 @@ int launch_mc(const CUtensorMap& tmX, const CUtensorMap& tmDY, const McParams& p
     return (int)e;
   }
   return 0;
+#endif
 }
 
 }  // namespace

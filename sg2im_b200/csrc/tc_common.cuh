@@ -5,6 +5,11 @@
 #include <mutex>
 #include "common.cuh"
 
+#ifdef SG2IM_EMUL
+// tests/emul/tc_emul.h: a FUNCTIONAL model of the TMA / mbarrier / tcgen05 / TMEM / cluster
+// primitives below (test infrastructure; calibrated on the hardware-validated kernels)
+#include "tc_emul.h"
+#else
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -114,6 +119,63 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 
 
+// --- setup / teardown pieces the kernels share
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// make freshly initialised mbarriers visible to the async proxy (TMA / tcgen05.commit)
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// whole warp: allocate `ncols` TMEM columns (base address written to *slot), give up the permit
+__device__ __forceinline__ void tc_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t base, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols)
+               : "memory");
+}
+// --- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\t"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load multicast to the CTAs in `mask`: data and complete_tx land at the same
+// smem / mbarrier offsets in every destination CTA
+__device__ __forceinline__ void tma_load_4d_mc(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                               uint16_t mask, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+}  // namespace tc
+#endif  // !SG2IM_EMUL
+
+namespace tc {
+
 // Column sums across the 32 lanes of a warp for 32 per-lane values: lane j
 // returns sum over lanes of v[j] (31 shuffles via recursive halving instead of
 // 32 x 5 for independent butterflies).
@@ -208,6 +270,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+#ifdef SG2IM_EMUL
+inline EncodeTiledFn get_encode() { return &emul_tensor_map_encode_tiled; }
+inline int num_sms() { return 148; }
+#else
 inline EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
@@ -232,5 +298,6 @@ inline int num_sms() {
   }
   return n;
 }
+#endif
 
 }  // namespace tc

@@ -50,6 +50,7 @@ struct dim3 {
 
 namespace emul {
 inline unsigned long long& blocks_run() { static unsigned long long n = 0; return n; }   // test introspection
+inline unsigned long long& cluster_blocks_run() { static unsigned long long n = 0; return n; }
 inline std::mutex& atomic_lock() { static std::mutex m; return m; }
 }  // namespace emul
 
@@ -82,28 +83,46 @@ inline void warp_sync() { current()->warp_bar[emul_warp()]->arrive_and_wait(); }
 }  // namespace emul
 #else
 // ------------------------------------------------------------------ fiber model
+#include <unordered_map>
 namespace emul {
+struct MBar {                          // functional mbarrier (tests/emul/tc_emul.h)
+  uint32_t init_count = 0, pending = 0, phase = 0;
+  long long tx = 0;
+  bool inited = false;
+};
 struct Fiber {
   ucontext_t ctx;
   std::vector<char> stack;
   uint3 tid;
+  unsigned block = 0;                  // index of its CTA inside the gang
   bool done = false;
 };
-struct Block {
-  unsigned nthreads = 0;
-  std::vector<Fiber> fibers;
-  ucontext_t main_ctx;
-  unsigned cur = 0;
+struct Block {                         // one CTA
+  unsigned nthreads = 0, rank = 0;
+  uint3 bid;
   unsigned alive = 0, arrived = 0;
   unsigned long long gen = 0;
   std::vector<unsigned> w_alive, w_arrived;
   std::vector<unsigned long long> w_gen;
   std::vector<uint32_t> xch;
-  std::vector<unsigned char> dyn_smem;
+  std::vector<unsigned char> smem_store;
+  unsigned char* smem = nullptr;       // 1024-byte aligned
+  size_t smem_bytes = 0;
+  std::unordered_map<uint32_t, MBar> mbar;   // keyed by shared-memory offset
+  std::vector<float> tmem;             // [128 lanes][512 columns], allocated on first use
+};
+struct Gang {                          // the CTAs that run concurrently: one block, or one cluster
+  std::vector<Block> blocks;
+  std::vector<Fiber> fibers;
+  ucontext_t main_ctx;
+  unsigned cur = 0;
+  unsigned c_alive = 0, c_arrived = 0;
+  unsigned long long c_gen = 0;
   const std::function<void()>* body = nullptr;
 };
-inline Block*& current() { static Block* b = nullptr; return b; }
-inline void yield() { Block* b = current(); swapcontext(&b->fibers[b->cur].ctx, &b->main_ctx); }
+inline Gang*& gang() { static Gang* g = nullptr; return g; }
+inline Block* current() { Gang* g = gang(); return &g->blocks[g->fibers[g->cur].block]; }
+inline void yield() { Gang* g = gang(); swapcontext(&g->fibers[g->cur].ctx, &g->main_ctx); }
 inline void block_sync() {
   Block* b = current();
   const unsigned long long g = b->gen;
@@ -117,17 +136,25 @@ inline void warp_sync() {
   if (++b->w_arrived[w] == b->w_alive[w]) { b->w_arrived[w] = 0; ++b->w_gen[w]; return; }
   while (b->w_gen[w] == g) yield();
 }
+inline void cluster_sync() {
+  Gang* G = gang();
+  const unsigned long long g = G->c_gen;
+  if (++G->c_arrived == G->c_alive) { G->c_arrived = 0; ++G->c_gen; return; }
+  while (G->c_gen == g) yield();
+}
 inline void fiber_exit_bookkeeping() {
   // an exited thread no longer takes part in barriers; complete any barrier it was the last missing of
+  Gang* G = gang();
   Block* b = current();
-  const unsigned w = b->cur >> 5;
+  const unsigned w = (G->cur % b->nthreads) >> 5;
   if (--b->alive > 0 && b->arrived == b->alive) { b->arrived = 0; ++b->gen; }
   if (--b->w_alive[w] > 0 && b->w_arrived[w] == b->w_alive[w]) { b->w_arrived[w] = 0; ++b->w_gen[w]; }
+  if (--G->c_alive > 0 && G->c_arrived == G->c_alive) { G->c_arrived = 0; ++G->c_gen; }
 }
 inline void trampoline() {
-  Block* b = current();
-  (*b->body)();
-  b->fibers[b->cur].done = true;
+  Gang* G = gang();
+  (*G->body)();
+  G->fibers[G->cur].done = true;
   fiber_exit_bookkeeping();
 }
 }  // namespace emul
@@ -135,7 +162,11 @@ inline void trampoline() {
 
 static inline void __syncthreads() { emul::block_sync(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emul::warp_sync(); }
+#ifdef SG2IM_EMUL_THREADS
 static inline void* emul_dynamic_smem() { return emul::current()->dyn_smem.data(); }
+#else
+static inline void* emul_dynamic_smem() { return emul::current()->smem; }
+#endif
 
 template <class T>
 static inline T emul_shfl_from(T v, unsigned src_lane) {
@@ -232,54 +263,72 @@ static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
   emul::current() = nullptr;
 }
 #else
-static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
-                               const std::function<void()>& body) {
+// `cluster` consecutive blocks (along x) run concurrently as one gang; cluster == 1 is a plain launch.
+static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, size_t dyn_smem_bytes,
+                                       const std::function<void()>& body) {
   const unsigned nthreads = block.x * block.y * block.z;
   if (nthreads == 0 || grid.x == 0 || grid.y == 0 || grid.z == 0) return;
-  static emul::Block blk;                              // fiber stacks are reused across launches
+  static emul::Gang G;                                 // fiber stacks are reused across launches
   constexpr size_t STACK = 256 * 1024;
-  if (blk.fibers.size() < nthreads) blk.fibers.resize(nthreads);
-  for (unsigned t = 0; t < nthreads; ++t)
-    if (blk.fibers[t].stack.size() != STACK) blk.fibers[t].stack.resize(STACK);
-  blk.nthreads = nthreads;
-  blk.xch.assign(nthreads, 0);
-  blk.dyn_smem.assign(dyn_smem_bytes + 64, 0);
-  blk.body = &body;
+  const unsigned nfib = cluster * nthreads;
+  if (G.fibers.size() < nfib) G.fibers.resize(nfib);
+  for (unsigned f = 0; f < nfib; ++f)
+    if (G.fibers[f].stack.size() != STACK) G.fibers[f].stack.resize(STACK);
+  G.blocks.resize(cluster);
+  G.body = &body;
   const unsigned nwarps = (nthreads + 31) / 32;
-  emul::current() = &blk;
+  emul::gang() = &G;
   blockDim = block;
   gridDim = grid;
   const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
-  for (unsigned long long b = 0; b < nblocks; ++b) {
-    const uint3 bid = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y),
-                            (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
-    blk.alive = nthreads; blk.arrived = 0;
-    blk.w_alive.assign(nwarps, 0); blk.w_arrived.assign(nwarps, 0); blk.w_gen.assign(nwarps, 0);
-    for (unsigned t = 0; t < nthreads; ++t) {
-      emul::Fiber& f = blk.fibers[t];
-      f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-      f.done = false;
-      ++blk.w_alive[t >> 5];
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack.data();
-      f.ctx.uc_stack.ss_size = f.stack.size();
-      f.ctx.uc_link = &blk.main_ctx;
-      makecontext(&f.ctx, (void (*)())emul::trampoline, 0);
-    }
-    unsigned remaining = nthreads;
-    while (remaining) {
+  for (unsigned long long b0 = 0; b0 < nblocks; b0 += cluster) {
+    G.c_alive = nfib; G.c_arrived = 0;
+    for (unsigned r = 0; r < cluster; ++r) {
+      emul::Block& blk = G.blocks[r];
+      const unsigned long long b = b0 + r;
+      blk.nthreads = nthreads; blk.rank = r;
+      blk.bid = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y),
+                      (unsigned)(b / ((unsigned long long)grid.x * grid.y))};
+      blk.alive = nthreads; blk.arrived = 0;
+      blk.w_alive.assign(nwarps, 0); blk.w_arrived.assign(nwarps, 0); blk.w_gen.assign(nwarps, 0);
+      blk.xch.assign(nthreads, 0);
+      blk.smem_store.assign(dyn_smem_bytes + 2048, 0);
+      blk.smem = reinterpret_cast<unsigned char*>(
+          (reinterpret_cast<uintptr_t>(blk.smem_store.data()) + 1023) & ~(uintptr_t)1023);
+      blk.smem_bytes = dyn_smem_bytes;
+      blk.mbar.clear();
       for (unsigned t = 0; t < nthreads; ++t) {
-        emul::Fiber& f = blk.fibers[t];
-        if (f.done) continue;
-        blk.cur = t;
-        threadIdx = f.tid;
-        blockIdx = bid;
-        swapcontext(&blk.main_ctx, &f.ctx);
-        if (f.done) --remaining;
+        emul::Fiber& f = G.fibers[r * nthreads + t];
+        f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+        f.block = r;
+        f.done = false;
+        ++blk.w_alive[t >> 5];
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_link = &G.main_ctx;
+        makecontext(&f.ctx, (void (*)())emul::trampoline, 0);
       }
     }
-    ++emul::blocks_run();
+    unsigned remaining = nfib;
+    while (remaining) {
+      for (unsigned f = 0; f < nfib; ++f) {
+        emul::Fiber& fb = G.fibers[f];
+        if (fb.done) continue;
+        G.cur = f;
+        threadIdx = fb.tid;
+        blockIdx = G.blocks[fb.block].bid;
+        swapcontext(&G.main_ctx, &fb.ctx);
+        if (fb.done) --remaining;
+      }
+    }
+    emul::blocks_run() += cluster;
+    if (cluster > 1) emul::cluster_blocks_run() += cluster;
   }
-  emul::current() = nullptr;
+  emul::gang() = nullptr;
+}
+static inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem_bytes,
+                               const std::function<void()>& body) {
+  emul_launch_cluster(1, grid, block, dyn_smem_bytes, body);
 }
 #endif

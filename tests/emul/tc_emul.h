@@ -1,0 +1,262 @@
+// TEST INFRASTRUCTURE ONLY — a FUNCTIONAL model of the Blackwell primitives the tensor-core
+// kernels use (csrc/tc_common.cuh wrappers): TMA tiled loads with shared-memory swizzle and
+// out-of-bounds zero fill, mbarriers (arrive / expect_tx / complete_tx / parity wait),
+// tcgen05.alloc / mma kind::tf32 (K-major and MN-major shared-memory descriptors) / commit /
+// ld, TMEM, and thread-block clusters (rank, barrier, multicast TMA, multicast commit).
+// Everything completes immediately (no asynchrony, no timing); the point is to execute the
+// kernels' OWN control flow, pipeline protocol, descriptor arithmetic and indexing on the CPU.
+//
+// The model encodes this repository's understanding of the hardware (probed on the B200 with
+// tools/umma_probe*.cu, see profiles/README.md) and is CALIBRATED by the kernels that are proven
+// on hardware: conv_tc / conv_tc_halo / conv_wgrad_tc must reproduce correct convolutions under
+// it (tests/test_tc_kernels_emulated_cpu.py) before it is used to exercise kernels that have not
+// run on hardware yet (conv_wgrad_tc_mc).  Facts the model relies on:
+//   * the 128-byte swizzles are XORs on ABSOLUTE shared-memory address bits (so row-shifted
+//     operand start addresses stay consistent with what TMA wrote);
+//   * K-major SWIZZLE_128B operand, tf32: element (row r, k) at start + (r/8)*SBO + (r%8)*128 + 4k;
+//   * MN-major SWIZZLE_128B_BASE32B operand, tf32: element (mn, k) at
+//     start + (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + 4*(mn%32);
+//   * tcgen05.mma kind::tf32 ignores the 13 low mantissa bits of its operands, accumulates fp32;
+//   * accumulator D[row][col] lives at TMEM lane `row`, column `d_tmem.col + col`.
+// Only the exact XOR pattern of SWIZZLE_128B_ATOM_32B is an assumption; it cancels out because
+// producer (TMA) and consumer (MMA) use the same function.
+#pragma once
+#ifdef SG2IM_EMUL_THREADS
+#error "the tensor-core model needs the fiber execution model (no -DSG2IM_EMUL_THREADS)"
+#endif
+#include <cstdio>
+
+#define __grid_constant__
+
+static inline long long clock64() { static long long t = 0; return t += 1000; }
+[[noreturn]] static inline void __trap() {
+  std::fprintf(stderr, "emulated kernel: __trap() (an mbarrier wait never completed)\n");
+  std::abort();
+}
+static inline float4 atomicAdd(float4* p, float4 v) {
+  float4 old = *p;
+  p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+  return old;
+}
+
+namespace emul {
+constexpr uint32_t SMEM_VA = 0x400;                      // shared window base (1 KB aligned)
+struct TMap {                                            // lives inside the 128-byte CUtensorMap
+  void* gptr;
+  uint32_t rank, swizzle;
+  uint64_t dim[5];
+  uint64_t stride[5];                                    // bytes; stride[0] = element size
+  uint32_t box[5];
+};
+static_assert(sizeof(TMap) <= sizeof(CUtensorMap), "descriptor does not fit");
+
+inline uint32_t va_of(const Block* b, const void* p) {
+  return (uint32_t)(reinterpret_cast<const unsigned char*>(p) - b->smem) + SMEM_VA;
+}
+inline unsigned char* host_of(Block* b, uint32_t va) { return b->smem + (va - SMEM_VA); }
+inline uint32_t swz128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+inline uint32_t swz128_atom32(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }
+inline float tf32_trunc(float f) {
+  uint32_t u; std::memcpy(&u, &f, 4); u &= ~0x1fffu; std::memcpy(&f, &u, 4); return f;
+}
+inline MBar& bar_at(Block* b, uint32_t va) { return b->mbar[va]; }
+inline void bar_check_complete(MBar& m) {
+  if (m.inited && m.pending == 0 && m.tx == 0) { m.phase ^= 1u; m.pending = m.init_count; }
+}
+inline void bar_arrive(Block* b, uint32_t va) {
+  MBar& m = bar_at(b, va);
+  if (!m.inited || m.pending == 0) { std::fprintf(stderr, "emul: arrive on bad mbarrier %x\n", va); std::abort(); }
+  --m.pending;
+  bar_check_complete(m);
+}
+inline void bar_complete_tx(Block* b, uint32_t va, long long bytes) {
+  MBar& m = bar_at(b, va);
+  m.tx -= bytes;
+  bar_check_complete(m);
+}
+// copy one TMA box into CTA `b` at shared address dst_va (swizzled), signal its barrier
+inline void tma_box(Block* b, uint32_t dst_va, const TMap& t, uint32_t bar_va, const int* c) {
+  if (t.stride[0] != 4 || t.box[0] * 4 != 128) { std::fprintf(stderr, "emul: TMA box must be 32 floats wide\n"); std::abort(); }
+  long long bytes = 0;
+  const uint32_t b1 = t.rank > 1 ? t.box[1] : 1, b2 = t.rank > 2 ? t.box[2] : 1, b3 = t.rank > 3 ? t.box[3] : 1;
+  for (uint32_t i3 = 0; i3 < b3; ++i3)
+    for (uint32_t i2 = 0; i2 < b2; ++i2)
+      for (uint32_t i1 = 0; i1 < b1; ++i1) {
+        const uint32_t row = (i3 * b2 + i2) * b1 + i1;
+        long long g1 = t.rank > 1 ? (long long)c[1] + i1 : 0, g2 = t.rank > 2 ? (long long)c[2] + i2 : 0,
+                  g3 = t.rank > 3 ? (long long)c[3] + i3 : 0;
+        const bool row_in = g1 >= 0 && (t.rank < 2 || g1 < (long long)t.dim[1]) && g2 >= 0 &&
+                            (t.rank < 3 || g2 < (long long)t.dim[2]) && g3 >= 0 &&
+                            (t.rank < 4 || g3 < (long long)t.dim[3]);
+        for (uint32_t i0 = 0; i0 < t.box[0]; ++i0) {
+          const long long g0 = (long long)c[0] + i0;
+          float v = 0.f;
+          if (row_in && g0 >= 0 && g0 < (long long)t.dim[0]) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(t.gptr) + g0 * 4 +
+                                       (t.rank > 1 ? g1 * (long long)t.stride[1] : 0) +
+                                       (t.rank > 2 ? g2 * (long long)t.stride[2] : 0) +
+                                       (t.rank > 3 ? g3 * (long long)t.stride[3] : 0);
+            std::memcpy(&v, src, 4);
+          }
+          uint32_t a = dst_va + row * 128u + i0 * 4u;
+          a = t.swizzle == (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B ? swz128(a)
+              : t.swizzle == (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B ? swz128_atom32(a) : a;
+          if (a - SMEM_VA + 4 > b->smem_bytes) { std::fprintf(stderr, "emul: TMA write outside shared memory\n"); std::abort(); }
+          std::memcpy(host_of(b, a), &v, 4);
+          bytes += 4;
+        }
+      }
+  bar_complete_tx(b, bar_va, bytes);
+}
+}  // namespace emul
+
+// cuTensorMapEncodeTiled stand-in (tc::get_encode under SG2IM_EMUL)
+static inline CUresult emul_tensor_map_encode_tiled(
+    CUtensorMap* map, CUtensorMapDataType dtype, cuuint32_t rank, void* gaddr, const cuuint64_t* gdim,
+    const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t* estride, CUtensorMapInterleave,
+    CUtensorMapSwizzle swizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  if (dtype != CU_TENSOR_MAP_DATA_TYPE_FLOAT32 || rank < 1 || rank > 5) return CUDA_ERROR_INVALID_VALUE;
+  if ((reinterpret_cast<uintptr_t>(gaddr) & 15) != 0) return CUDA_ERROR_INVALID_VALUE;
+  emul::TMap t{};
+  t.gptr = gaddr; t.rank = rank; t.swizzle = (uint32_t)swizzle;
+  t.stride[0] = 4;
+  for (uint32_t i = 0; i < rank; ++i) {
+    t.dim[i] = gdim[i]; t.box[i] = box[i];
+    if (estride[i] != 1 || box[i] == 0 || box[i] > 256) return CUDA_ERROR_INVALID_VALUE;
+    if (i > 0) {
+      t.stride[i] = gstride[i - 1];
+      if (gstride[i - 1] % 16) return CUDA_ERROR_INVALID_VALUE;     // the driver's rule
+    }
+  }
+  std::memset(map, 0, sizeof(*map));
+  std::memcpy(map, &t, sizeof(t));
+  return CUDA_SUCCESS;
+}
+
+namespace tc {
+using emul::Block;
+
+static inline uint32_t smem_u32(const void* p) { return emul::va_of(emul::current(), p); }
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
+  emul::MBar& m = emul::bar_at(emul::current(), smem_u32(bar));
+  m = emul::MBar{};
+  m.init_count = m.pending = count; m.inited = true;
+}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {          // arrive.expect_tx
+  Block* b = emul::current();
+  emul::MBar& m = emul::bar_at(b, smem_u32(bar));
+  m.tx += bytes;
+  emul::bar_arrive(b, smem_u32(bar));
+}
+static inline void mbar_arrive(uint64_t* bar) { emul::bar_arrive(emul::current(), smem_u32(bar)); }
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  emul::MBar& m = emul::bar_at(emul::current(), smem_u32(bar));
+  if (!m.inited) { std::fprintf(stderr, "emul: wait on uninitialised mbarrier\n"); std::abort(); }
+  if (m.phase != parity) return true;                   // the phase with this parity has completed
+  emul::yield();
+  return false;
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > 50000000LL) __trap();                 // a protocol bug must fail, never hang
+}
+static inline void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  emul::TMap t; std::memcpy(&t, map, sizeof(t));
+  const int c[4] = {c0, c1, c2, c3};
+  emul::tma_box(emul::current(), smem_u32(smem), t, smem_u32(bar), c);
+}
+static inline void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  emul::TMap t; std::memcpy(&t, map, sizeof(t));
+  const int c[4] = {c0, c1, c2, 0};
+  emul::tma_box(emul::current(), smem_u32(smem), t, smem_u32(bar), c);
+}
+static inline void tma_load_4d_mc(void* smem, const CUtensorMap* map, uint64_t* bar, uint16_t mask,
+                                  int c0, int c1, int c2, int c3) {
+  emul::TMap t; std::memcpy(&t, map, sizeof(t));
+  const int c[4] = {c0, c1, c2, c3};
+  emul::Gang* G = emul::gang();
+  const uint32_t dst = smem_u32(smem), bv = smem_u32(bar);
+  for (unsigned r = 0; r < G->blocks.size(); ++r)
+    if (mask & (1u << r)) emul::tma_box(&G->blocks[r], dst, t, bv, c);
+}
+static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline void mbar_fence_init() {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+
+static inline void tc_alloc(uint32_t* slot, uint32_t ncols) {                // whole warp calls it
+  Block* b = emul::current();
+  if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) { std::fprintf(stderr, "emul: bad TMEM column count\n"); std::abort(); }
+  if (b->tmem.empty()) b->tmem.assign(128 * 512, 0.f);
+  *slot = 0;                                             // lane 0, column 0
+}
+static inline void tc_dealloc(uint32_t, uint32_t) {}
+static inline void tc_commit(uint64_t* bar, uint32_t = 1u) {                 // converged warp, one arrive
+  if (emul_lane() == 0) emul::bar_arrive(emul::current(), smem_u32(bar));
+}
+static inline void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  if (emul_lane() != 0) return;
+  emul::Gang* G = emul::gang();
+  const uint32_t bv = smem_u32(bar);
+  for (unsigned r = 0; r < G->blocks.size(); ++r)
+    if (mask & (1u << r)) emul::bar_arrive(&G->blocks[r], bv);
+}
+
+// tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words
+static inline void tc_mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t) {
+  if (emul_lane() != 0) return;                           // elect.sync: one lane issues
+  Block* blk = emul::current();
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  if (M != 128 || N < 8 || N > 256 || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u) {
+    std::fprintf(stderr, "emul: unsupported instruction descriptor %x\n", idesc); std::abort();
+  }
+  auto elem = [&](uint32_t lo, uint32_t hi, bool mn_major, int idx, int k) -> float {
+    const uint32_t start = (lo & 0x3fffu) << 4, lbo = ((lo >> 16) & 0x3fffu) << 4, sbo = (hi & 0x3fffu) << 4;
+    const uint32_t layout = (hi >> 29) & 7u;
+    uint32_t a;
+    if (!mn_major) {
+      if (layout != 2u) { std::fprintf(stderr, "emul: K-major operand must be SWIZZLE_128B\n"); std::abort(); }
+      a = emul::swz128(start + (uint32_t)(idx >> 3) * sbo + (uint32_t)(idx & 7) * 128u + (uint32_t)k * 4u);
+    } else {
+      if (layout != 1u) { std::fprintf(stderr, "emul: MN-major tf32 operand must be SWIZZLE_128B_BASE32B\n"); std::abort(); }
+      a = emul::swz128_atom32(start + (uint32_t)(idx >> 5) * lbo + (uint32_t)(k >> 2) * sbo +
+                              (uint32_t)(k & 3) * 128u + (uint32_t)(idx & 31) * 4u);
+    }
+    if (a < emul::SMEM_VA || a - emul::SMEM_VA + 4 > blk->smem_bytes) { std::fprintf(stderr, "emul: MMA operand read outside shared memory\n"); std::abort(); }
+    float v; std::memcpy(&v, emul::host_of(blk, a), 4);
+    return emul::tf32_trunc(v);
+  };
+  const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xffffu;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emul: accumulator outside TMEM\n"); std::abort(); }
+  float A[128][8], B[256][8];
+  for (int m = 0; m < M; ++m) for (int k = 0; k < 8; ++k) A[m][k] = elem(a_lo, a_hi, a_mn, m, k);
+  for (int n = 0; n < N; ++n) for (int k = 0; k < 8; ++k) B[n][k] = elem(b_lo, b_hi, b_mn, n, k);
+  for (int m = 0; m < M; ++m) {
+    float* drow = &blk->tmem[(size_t)m * 512 + col0];
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? drow[n] : 0.f;
+      for (int k = 0; k < 8; ++k) acc += A[m][k] * B[n][k];
+      drow[n] = acc;
+    }
+  }
+}
+static inline void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  tc_mma_tf32_lh(d_tmem, (uint32_t)adesc, (uint32_t)(adesc >> 32), (uint32_t)bdesc, (uint32_t)(bdesc >> 32), idesc, accumulate, 1u);
+}
+// tcgen05.ld.32x32b.x32: lane i of the warp reads TMEM lane (base + i), 32 consecutive columns
+static inline void tc_ld32(uint32_t taddr, float* v) {
+  Block* b = emul::current();
+  const uint32_t lane = (taddr >> 16) + emul_lane(), col = taddr & 0xffffu;
+  if (lane >= 128 || col + 32 > 512 || (emul_warp() & 3u) != ((taddr >> 16) >> 5)) {
+    std::fprintf(stderr, "emul: tcgen05.ld outside the warp's TMEM lane quadrant\n"); std::abort();
+  }
+  for (int i = 0; i < 32; ++i) v[i] = b->tmem[(size_t)lane * 512 + col + i];
+}
+
+static inline uint32_t cluster_rank() { return emul::current()->rank; }
+static inline void cluster_sync_all() { emul::cluster_sync(); }
+}  // namespace tc

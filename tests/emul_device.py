@@ -4,10 +4,11 @@ against the kernel sources compiled for the host (tests/emul/, -DSG2IM_EMUL).
 
 ``with emulated_device(): ...`` swaps the loaded library handle for the emulation build and
 relaxes the two device checks of the op layer (`_chk`'s is_cuda test, the CUDA stream lookup);
-nothing else of the product is touched.  Only the exact-fp32 configuration can run this way — the
-tcgen05 / TMA kernels have no host build: with `ops.set_conv_math('tf32')` any convolution that
-would take them fails loudly (missing symbol), while the flag's other effect (RN-TF32 rounding in
-the layout / BN-apply kernels) is emulated.
+nothing else of the product is touched.  When the CUDA headers are present (HAVE_TC) the
+tensor-core kernels are part of the host build too — they execute against the functional
+TMA / mbarrier / tcgen05 / TMEM / cluster model of tests/emul/tc_emul.h, so `set_conv_math('tf32')`
+(the benchmarked configuration) runs end to end; without them a convolution that would take the
+tensor-core path fails loudly (missing symbol).
 """
 import contextlib
 import ctypes
@@ -18,6 +19,9 @@ import tempfile
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = next((d for d in (os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include'),
+                             '/usr/local/cuda/include') if os.path.exists(os.path.join(d, 'cuda.h'))), None)
+HAVE_TC = CUDA_INC is not None
 _built = {}
 
 
@@ -30,7 +34,13 @@ def build_lib():
   src = sorted(glob.glob(os.path.join(ROOT, 'tests', 'emul', 'emul_*.cpp')))
   cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-DSG2IM_EMUL',
          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
-         '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')] + src + ['-o', out]
+         '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')]
+  if CUDA_INC is not None:
+    # with the CUDA headers (cuda.h: CUtensorMap) the tensor-core kernels build too, against the
+    # functional tcgen05 / TMA / cluster model of tests/emul/tc_emul.h
+    src += sorted(glob.glob(os.path.join(ROOT, 'tests', 'emul', 'emultc_*.cpp')))
+    cmd += ['-I', CUDA_INC]
+  cmd += src + ['-o', out]
   cmd[1:1] = os.environ.get('SG2IM_EMUL_CXXFLAGS', '').split()
   subprocess.check_call(cmd)
   _built['path'] = out

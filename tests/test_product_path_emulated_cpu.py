@@ -22,6 +22,16 @@ def emul(monkeypatch):
   cpu = lambda: torch.device('cpu')                      # noqa: E731
   monkeypatch.setattr(G, 'dev', cpu)
   monkeypatch.setattr(O, 'dev', cpu)
+  # the GPU tests write `t.to(dev()).requires_grad_(True)`: on a GPU `.to` copies, here it would
+  # alias the fixture tensor (and turn later `.clone()`s into non-leaves).  Make `.to(device)` copy.
+  orig_to = torch.Tensor.to
+
+  def to_copying(self, *a, **k):
+    out = orig_to(self, *a, **k)
+    if out is self and a and isinstance(a[0], torch.device):
+      out = out.clone()
+    return out
+  monkeypatch.setattr(torch.Tensor, 'to', to_copying)
   with emulated_device() as lib:
     yield lib
 
@@ -69,15 +79,32 @@ def test_layout_and_crop(emul):
   O.test_crop_golden_and_backward()
 
 
-def test_the_emulated_device_has_no_tensor_core_kernels(emul):
-  """A convolution that would take the tcgen05 path fails loudly here: no silent stand-in."""
-  from sg2im_b200 import ops
-  ops.set_conv_math('tf32')
-  try:
-    with pytest.raises(AttributeError):
-      ops.conv2d(torch.zeros(1, 8, 8, 32), torch.zeros(32, 32, 3, 3), None, 1, 1)
-  finally:
-    ops.set_conv_math('fp32')
+# ---- the benchmarked configuration: tcgen05 TF32 convolutions (functional tensor-core model)
+from emul_device import HAVE_TC  # noqa: E402
+
+needs_tc = pytest.mark.skipif(not HAVE_TC, reason='needs the CUDA headers (cuda.h) for the tensor-core host build')
+
+
+@needs_tc
+def test_training_iteration_on_the_tensor_core_path(emul):
+  G.test_training_iteration_tf32_tensor_core_path()
+
+
+@needs_tc
+def test_generator_tf32_error_vs_fp32_reference(emul):
+  G.test_generator_forward_tf32_error_vs_fp32_reference()
+
+
+@needs_tc
+@pytest.mark.parametrize('case', [0, 3, 6])
+def test_tensor_core_conv_forward_dgrad_through_the_op_layer(emul, case):
+  O.test_conv_tc_forward_dgrad(*O.TC_CASES[case])
+
+
+@needs_tc
+def test_tensor_core_dgrad_slices_and_stride2_route(emul):
+  O.test_conv_tc_dgrad_exact_and_slice_output()
+  O.test_conv_stride2_space_to_depth_route(*O.S2_CASES[0])
 
 
 # ---- the staged rows / second-generation kernels of DESIGN.md §7a, same treatment: the opt-in
@@ -119,3 +146,11 @@ def test_layout_v2_through_the_op_layer(emul_next):
 def test_colsum_v2_and_flat_adam_through_the_op_layer(emul_next):
   R.test_colsum_small_kernel(37, 179)
   R.test_train_step_with_flat_adam(False)
+
+
+@needs_tc
+def test_staged_tensor_core_switches_through_the_op_layer(emul_next):
+  R.test_pack_both_layouts_in_one_launch()
+  R.test_wgrad_cluster_multicast_matches_single_cta(4, 16, 16, 64, 64, 3)
+  R.test_wgrad_cluster_multicast_matches_single_cta(2, 16, 24, 64, 192, 3)
+  R.test_eval_bn_folding_sheep('tf32')
