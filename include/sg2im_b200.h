@@ -115,6 +115,21 @@ int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int
                   int64_t y_cstride, int64_t y_coff, double* stats, int round_out,
                   sg2im_stream_t stream);
 
+/* The same convolution with the weights taken straight from the WEIGHT-GRADIENT layout
+ * w_kcc[tap][row][col] (rows = the conv weight's input channels, cols = its output channels —
+ * what sg2im_conv_wgrad_tc writes), so that master weights kept in that layout need no
+ * pack / unpack pass:
+ *   dgrad == 0  forward: Cin rows used of w_rows_full, Cout == cols (B operand MN-major);
+ *   dgrad != 0  data gradient of that conv: call with x = dY, Cin = cols, Cout = rows used,
+ *               P' = K-1-P; the kernel flips the tap index itself.
+ * w_rows_full = row pitch of one tap (>= rows used: the CRN's first stage uses a channel prefix).
+ * Opt-in: validated so far only under the functional tensor-core model of the CPU test suite. */
+int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
+                      int64_t Cin, const float* w_kcc, int64_t w_rows_full, int dgrad,
+                      const float* bias, int KH, int KW, int P, int64_t Hout, int64_t Wout,
+                      int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
+                      int64_t y_coff, double* stats, int round_out, sg2im_stream_t stream);
+
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
  * reduction over pixels is split across CTAs and combined with fp32 atomics). */

@@ -27,6 +27,8 @@ SIGNATURES = {
                               _i64, _i64, _i64],
   'sg2im_conv_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _int, _int, _i64, _i64,
                     _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
+  'sg2im_conv_tc_kcc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr, _int, _int, _int,
+                        _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_conv_wgrad_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64,
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,

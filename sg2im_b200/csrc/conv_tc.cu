@@ -60,7 +60,16 @@ struct Cfg {
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 };
 
-template <int BN>
+// WMODE selects where the B operand (weights) comes from:
+//   0  packed [tap][Cout][Cin] (K-major; sg2im_pack_weights)                — the validated default
+//   1  FORWARD straight from the weight-gradient layout [tap][Cin][Cout]: B is MN-major
+//      (32-co atoms of 32 ci rows, SWIZZLE_128B_BASE32B like the wgrad kernel's operands)
+//   2  DATA GRADIENT straight from the same layout [tap][Cin_w][Cout_w]: conv-Cin = Cout_w is
+//      contiguous => K-major as in mode 0, only the tap index is flipped
+// Modes 1/2 remove every pack / unpack pass when the master weights live in that layout
+// (DESIGN.md §7b); they are opt-in (sg2im_conv_tc_kcc) and so far only run under the functional
+// tensor-core model of tests/emul/tc_emul.h.
+template <int BN, int WMODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
@@ -122,7 +131,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full[s], C::STAGE_BYTES);
           tma_load_4d(sA + s * A_STAGE_BYTES, &tmA, &full[s], cb * 32, x0 + kx - p.P,
                       y0 + ky - p.P, n0);
-          tma_load_3d(sB + s * C::B_STAGE_BYTES, &tmB, &full[s], cb * 32, nt * BN, tap);
+          if constexpr (WMODE == 1) {
+#pragma unroll
+            for (int a = 0; a < BN / 32; ++a)
+              tma_load_3d(sB + s * C::B_STAGE_BYTES + a * 4096, &tmB, &full[s], nt * BN + a * 32,
+                          cb * 32, tap);
+          } else {
+            tma_load_3d(sB + s * C::B_STAGE_BYTES, &tmB, &full[s], cb * 32, nt * BN,
+                        WMODE == 2 ? p.KH * p.KW - 1 - tap : tap);
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -145,10 +162,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t at = sA16 + (uint32_t)s * (A_STAGE_BYTES >> 4);
           const uint32_t bt = sB16 + (uint32_t)s * (C::B_STAGE_BYTES >> 4);
+          if constexpr (WMODE == 1) {
+            // B MN-major: atoms of 32 co (LBO = 4 KB apart), 8 ci rows = 1 KB per K step
+            constexpr uint32_t IDESC_MN = C::IDESC | (1u << 16);
+            const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);         // SBO 512 B, SWIZZLE_128B_BASE32B
+            const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
+            tc_mma_tf32_lh(d_tmem, at, d_hi, btm, bm_hi, IDESC_MN, kb ? 1u : 0u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 2, d_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 4, d_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 6, d_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
+          } else {
           tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
           tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
           tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
           tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
+          }
           tc_commit(&empty[s], leader);                    // frees the smem stage when the MMAs retire
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -240,6 +268,7 @@ struct HaloParams {
   int round_out;
 };
 
+template <int WMODE>                              // weight source, see conv_tc_kernel
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p) {
@@ -321,7 +350,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
             mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
             mbar_expect_tx(fb, H_B_TILE);
-            tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN, tap);
+            if constexpr (WMODE == 1) {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, nt * H_BN, cb * 32, tap);
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE + 4096, &tmB, fb, nt * H_BN + 32,
+                          cb * 32, tap);
+            } else {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN,
+                          WMODE == 2 ? p.taps - 1 - tap : tap);
+            }
           }
         }
       }
@@ -359,10 +395,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int kx = 0;
             for (int tap = 0; tap < p.taps; ++tap) {
               if (t == 0) { mbar_wait(&bf[tap], bph); tc_fence_after(); }
+              if constexpr (WMODE == 1) {
+                constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
+                const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
+                const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
+                tc_mma_tf32_lh(d_tmem, at, a_hi, btm, bm_hi, IDESC_MN, (cb | tap) ? 1u : 0u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 2, a_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
+              } else {
               tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
               tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
               tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
               tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
+              }
               if (t == H_T - 1) tc_commit(&be[tap], leader);
               at += 8u; bt += (H_B_TILE >> 4);
               if (++kx == p.KW) { kx = 0; at += row_wrap; }
@@ -424,13 +470,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------- host side ---
-template <int BN>
+template <int BN, int WMODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WMODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -441,11 +487,38 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
 #endif
   int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  SG_LAUNCH(conv_tc_kernel<BN>, grid, NUM_THREADS, C::SMEM_BYTES, st, tmA, tmB, p);
+  SG_LAUNCH((conv_tc_kernel<BN, WMODE>), grid, NUM_THREADS, C::SMEM_BYTES, st, tmA, tmB, p);
   return 0;
 }
 
 }  // namespace
+
+// Tensor map of the B operand for the three weight sources (see conv_tc_kernel).
+static int encode_weights(tc::EncodeTiledFn enc, CUtensorMap* map, const float* w, int64_t Cin,
+                          int64_t Cout, int taps, int BN, int wmode, int64_t w_rows_full) {
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (wmode == 0) {                       // [taps][Cout][Cin]
+    gdim[0] = (cuuint64_t)Cin; gdim[1] = (cuuint64_t)Cout;
+    gstr[0] = (cuuint64_t)Cin * 4; gstr[1] = (cuuint64_t)Cout * Cin * 4;
+  } else if (wmode == 1) {                // [taps][rows = Cin][cols = Cout], cols contiguous, MN-major atoms
+    gdim[0] = (cuuint64_t)Cout; gdim[1] = (cuuint64_t)Cin;
+    gstr[0] = (cuuint64_t)Cout * 4; gstr[1] = (cuuint64_t)w_rows_full * Cout * 4;
+    box[1] = 32;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  } else {                                // [taps][rows = conv Cout][cols = conv Cin], K-major
+    gdim[0] = (cuuint64_t)Cin; gdim[1] = (cuuint64_t)Cout;
+    gstr[0] = (cuuint64_t)Cin * 4; gstr[1] = (cuuint64_t)w_rows_full * Cin * 4;
+  }
+  gdim[2] = (cuuint64_t)taps;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode B failed (%d)", (int)r); return -4; }
+  return 0;
+}
 
 // Tile geometry for an output of Hout x Wout: 128 pixels = BI images x BH rows x
 // BW cols, all powers of two; the last tile in each direction may be partial
@@ -471,11 +544,16 @@ extern "C" int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int6
   return 1;
 }
 
-extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
-                             int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
-                             int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
-                             int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
-                             double* stats, int round_out, sg2im_stream_t stream) {
+// wmode 0: w_tc packed [taps][Cout][Cin].  wmode 1 / 2: w_tc is the weight-gradient layout
+// [taps][w_rows][w_cols] of the conv's weight (rows = its input channels, cols = its output
+// channels; w_rows_full >= rows actually used = row pitch of a tap): 1 = forward (Cin rows used,
+// Cout == w_cols), 2 = data gradient (conv-Cin == w_cols, conv-Cout rows used).
+static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                        int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
+                        int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
+                        int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
+                        double* stats, int round_out, sg2im_stream_t stream, int wmode,
+                        int64_t w_rows_full) {
   SG_ARG(x && w_tc && y);
   if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
                                y_cstride, y_coff)) {
@@ -542,21 +620,16 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
     }
-    {
-      cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(KH * KW)};
-      cuuint64_t gstr[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
-      cuuint32_t box[3] = {32, (cuuint32_t)H_BN, 1};
-      cuuint32_t estr[3] = {1, 1, 1};
-      CUresult r = enc(&hB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_tc), gdim,
-                       gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo B failed (%d)", (int)r); return -4; }
-    }
+    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full)) return rc;
 #ifndef SG2IM_EMUL
     static bool halo_attr = false;
     if (!halo_attr) {
-      cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel,
+      cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<0>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
       if (e != cudaSuccess) {
         sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
@@ -566,7 +639,9 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
 #endif
     int items = h.groups * h.n_tiles;
     int grid = items < num_sms() ? items : num_sms();
-    SG_LAUNCH(conv_tc_halo_kernel, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
+    if (wmode == 1) SG_LAUNCH(conv_tc_halo_kernel<1>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
+    else if (wmode == 2) SG_LAUNCH(conv_tc_halo_kernel<2>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
+    else SG_LAUNCH(conv_tc_halo_kernel<0>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
     SG_LAUNCH_OK();
     return 0;
   }
@@ -583,22 +658,40 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode A failed (%d)", (int)r); return -4; }
   }
-  {
-    cuuint64_t gdim[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(KH * KW)};
-    cuuint64_t gstr[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout * Cin * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w_tc), gdim,
-                     gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode B failed (%d)", (int)r); return -4; }
-  }
+  if (int rc = encode_weights(enc, &tmB, w_tc, Cin, Cout, KH * KW, BN, wmode, w_rows_full)) return rc;
   cudaStream_t st = as_stream(stream);
   int rc = 0;
-  if (BN == 256) rc = launch<256>(tmA, tmB, p, st);
-  else if (BN == 128) rc = launch<128>(tmA, tmB, p, st);
-  else rc = launch<64>(tmA, tmB, p, st);
+  if (wmode == 1) {
+    rc = BN == 256 ? launch<256, 1>(tmA, tmB, p, st) : BN == 128 ? launch<128, 1>(tmA, tmB, p, st)
+                                                                   : launch<64, 1>(tmA, tmB, p, st);
+  } else if (wmode == 2) {
+    rc = BN == 256 ? launch<256, 2>(tmA, tmB, p, st) : BN == 128 ? launch<128, 2>(tmA, tmB, p, st)
+                                                                   : launch<64, 2>(tmA, tmB, p, st);
+  } else if (BN == 256) rc = launch<256, 0>(tmA, tmB, p, st);
+  else if (BN == 128) rc = launch<128, 0>(tmA, tmB, p, st);
+  else rc = launch<64, 0>(tmA, tmB, p, st);
   if (rc) return rc;
   SG_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                             int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
+                             int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
+                             int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
+                             double* stats, int round_out, sg2im_stream_t stream) {
+  return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_tc, bias, KH, KW, P, Hout, Wout, Cout, act,
+                      slope, y, y_cstride, y_coff, stats, round_out, stream, 0, 0);
+}
+
+extern "C" int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                                 int64_t Win, int64_t Cin, const float* w_kcc, int64_t w_rows_full,
+                                 int dgrad, const float* bias, int KH, int KW, int P, int64_t Hout,
+                                 int64_t Wout, int64_t Cout, int act, float slope, float* y,
+                                 int64_t y_cstride, int64_t y_coff, double* stats, int round_out,
+                                 sg2im_stream_t stream) {
+  SG_ARG(w_rows_full >= (dgrad ? Cout : Cin));
+  return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_kcc, bias, KH, KW, P, Hout, Wout, Cout, act,
+                      slope, y, y_cstride, y_coff, stats, round_out, stream, dgrad ? 2 : 1,
+                      w_rows_full);
 }

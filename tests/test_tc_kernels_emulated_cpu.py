@@ -147,3 +147,45 @@ def test_cluster_multicast_weight_gradient_kernel(lib, env, N, H, W, Ci, Co, K):
     assert lib.emul_cluster_blocks_run() > c0              # the cluster kernel really ran
   else:
     assert lib.emul_cluster_blocks_run() == c0             # odd: plain kernel (documented fallback)
+
+
+KCC_CASES = [  # N, H, W, Ci, Co, K, P, Ci_full, env
+    (1, 8, 8, 32, 64, 3, 1, 32, {}),                           # per-tap kernel
+    (2, 16, 16, 32, 64, 3, 1, 32, {}),                         # halo kernel
+    (2, 16, 16, 64, 96, 3, 1, 64, {'SG2IM_NO_HALO': 1}),       # ragged N tile
+    (1, 16, 8, 72, 36, 3, 1, 80, {}),                          # channel prefix of wider weights, ragged
+    (4, 1, 1, 64, 128, 1, 0, 64, {}),                          # Linear
+    (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 256}),
+    (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 128}),
+    (2, 15, 15, 48, 32, 2, 0, 48, {})]
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P,Cf,e', KCC_CASES)
+def test_convolution_straight_from_the_weight_gradient_layout(lib, env, N, H, W, Ci, Co, K, P, Cf, e):
+  """sg2im_conv_tc_kcc (WMODE 1: forward with an MN-major B operand; WMODE 2: data gradient with
+  the tap flip in the TMA coordinate) — weights in [tap][Cin][Cout], no pack pass.  Not yet run on
+  hardware; executed here under the model calibrated by the tests above."""
+  env(**e)
+  g = torch.Generator().manual_seed(Ci * 3 + Co)
+  T = K * K
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w_full = _tf32(torch.randn(Co, Cf, K, K, generator=g) * 0.1)       # OIHW with Cf >= Ci input channels
+  w = w_full[:, :Ci]
+  b = torch.randn(Co, generator=g)
+  kcc = w_full.permute(2, 3, 1, 0).reshape(T, Cf, Co).contiguous()    # [tap][ci][co]: the wgrad layout
+  Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+  y = torch.full((N, Ho, Wo, Co + 4), 7.0)
+  lib.sg2im_conv_tc_kcc.argtypes = __import__('sg2im_b200._lib', fromlist=['x']).SIGNATURES['sg2im_conv_tc_kcc']
+  assert lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kcc), Cf, 0, _p(b), K, K, P, Ho, Wo, Co, 1, 0.2,
+                               _p(y), Co + 4, 4, None, 0, None) == 0, lib.emul_last_error()
+  xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  pre = F.conv2d(xr, w, b, padding=P)
+  assert rel_err(y[..., 4:], F.leaky_relu(pre, 0.2).permute(0, 2, 3, 1)) < 2e-6
+  assert bool((y[..., :4] == 7.0).all())
+  # data gradient from the very same weight buffer
+  gy = _tf32(torch.randn(N, Ho, Wo, Co, generator=g))
+  pre.backward(gy.permute(0, 3, 1, 2))
+  dx = torch.empty(N, H, W, Ci)
+  assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kcc), Cf, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
+                               0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
+  assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-6
