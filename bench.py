@@ -47,6 +47,9 @@ def parse():
   ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
   ap.add_argument('--adam', default='torch', choices=['torch', 'flat'],
                   help="'flat': one sg2im_adam_flat kernel per optimiser (opt-in until validated on hardware)")
+  ap.add_argument('--weights', default='oihw', choices=['oihw', 'kcc'],
+                  help="'kcc': conv / linear weights stored in the weight-gradient layout, no pack / unpack "
+                       'passes (opt-in until validated on hardware)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--shapes-out', default=None, help='write per-shape conv timings (JSON)')
@@ -225,7 +228,7 @@ def run_b200(args, cfg):
     d_img = PatchDiscriminator(D_ARCH, padding='valid').to(dev)
     d_obj = AcCropDiscriminator(vocab, D_ARCH, 'batch', 'leakyrelu-0.2', 32, 'valid').to(dev)
   step = TrainStep(model, d_obj, d_img, cuda_graph=not args.no_graph,
-                   fused_adam='flat' if args.adam == 'flat' else None)
+                   fused_adam='flat' if args.adam == 'flat' else None, weights=args.weights)
   torch.manual_seed(1234 + rank)                         # noise stream differs per rank
 
   n_pool = 4

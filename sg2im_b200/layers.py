@@ -172,6 +172,25 @@ class _AvgPool2Fn(torch.autograd.Function):
     return dx
 
 
+def to_kcc_(module):
+  """Re-store every Conv2d / Linear weight of `module` tap-major with the output channel
+  fastest ([KH][KW][Cin][Cout]; Linear: [in][out]) — the layout the tensor-core weight-gradient
+  kernel writes and `sg2im_conv_tc_kcc` reads in place, so a training step needs no weight
+  pack / unpack pass (ops.ConvKCC).  The parameters keep their OIHW / (out, in) SHAPE as
+  permuted views: `state_dict` keys, shapes and values are unchanged, `load_state_dict`
+  copies into the new storage.  Opt-in (TrainStep(weights='kcc')); validated so far under
+  the functional tensor-core model of the CPU suite only.  Returns `module`."""
+  with torch.no_grad():
+    for m in module.modules():
+      if isinstance(m, nn.Conv2d):
+        store = m.weight.detach().permute(2, 3, 1, 0).contiguous()
+        m.weight.data = store.permute(3, 2, 0, 1)
+      elif isinstance(m, nn.Linear):
+        store = m.weight.detach().t().contiguous()
+        m.weight.data = store.t()
+  return module
+
+
 # ----------------------------------------------------------------------------
 # Sequential with peephole fusion
 # ----------------------------------------------------------------------------

@@ -455,6 +455,90 @@ class Conv(torch.autograd.Function):
     return dx, dw, db, None, None, None, None, None, None, None, None, None
 
 
+def is_kcc(weight):
+  """True if an OIHW-shaped (or (out, in)) weight is stored tap-major / input-channel /
+  output-channel fastest — the layout the weight-gradient kernel writes and
+  sg2im_conv_tc_kcc reads (layers.to_kcc_ puts the parameters there)."""
+  if weight.dim() == 2:
+    return weight.size(0) > 1 and weight.stride(0) == 1 and weight.t().is_contiguous()
+  return (weight.dim() == 4 and weight.stride(0) == 1
+          and weight.permute(2, 3, 1, 0).is_contiguous())
+
+
+def conv_tc_kcc(x, w_kcc, rows_full, dgrad, bias, KH, KW, P, Cout, act=0, slope=0.0, out_hw=None,
+                stats=None, round_out=False, tag='conv_fwd_tc'):
+  """Tensor-core stride-1 convolution with the weights read in place from the
+  weight-gradient layout w_kcc [KH*KW][rows_full][cols] (sg2im_conv_tc_kcc)."""
+  N, H, W, C = x.shape
+  cs = _pixel_stride(x)
+  Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
+  out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
+    _call('sg2im_conv_tc_kcc', _p(x), cs, N, H, W, C, _p(w_kcc), rows_full, int(dgrad), _p(bias), KH,
+          KW, P, Hout, Wout, Cout, int(act), float(slope), _p(out), Cout, 0, _p(stats),
+          int(round_out), _stream())
+  _count()
+  return out
+
+
+class ConvKCC(torch.autograd.Function):
+  """y = act(conv(x, W) + b) on the tensor-core kernels with W given as w_kcc
+  (T, Ci_w, Co) — the weight-gradient layout — so that neither the forward, nor the
+  data gradient, nor the weight gradient needs a layout pass: the forward reads it
+  MN-major, the data gradient K-major with the tap index flipped, and the weight
+  gradient kernel's output IS the gradient w.r.t. w_kcc.  Stride 1, tf32 only;
+  `in_ch` < Ci_w uses a channel prefix (the CRN's first stage)."""
+
+  @staticmethod
+  def forward(ctx, x, w_kcc, bias, KH, KW, pad, act, slope, in_ch, out_hw, zero_bias_grad,
+              stats_out, round_out):
+    T, Ci_w, Co = w_kcc.shape
+    Ci = Ci_w if in_ch is None else in_ch
+    assert T == KH * KW and x.size(3) == Ci and w_kcc.is_contiguous()
+    Hout = x.size(1) + 2 * pad - KH + 1 if out_hw is None else out_hw[0]
+    Wout = x.size(2) + 2 * pad - KW + 1 if out_hw is None else out_hw[1]
+    fused_stats = stats_out is not None and act == 0 and Co <= 1024
+    y = conv_tc_kcc(x, w_kcc, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
+                    stats_out if fused_stats else None, round_out)
+    if stats_out is not None and not fused_stats:
+      _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
+      _count()
+    ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
+    ctx.save_for_backward(x, w_kcc, y if act else None)
+    ctx.has_bias = bias is not None
+    ctx.zero_bias_grad = bool(zero_bias_grad)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    KH, KW, pad, act, slope, Ci, Ci_w, Co = ctx.cfg
+    x, w_kcc, y = ctx.saved_tensors
+    dy = dy.contiguous()
+    if act:
+      dy = act_bwd(dy, y, slope)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+      pad_t = KH - 1 - pad
+      if (KH == KW and pad_t >= 0
+          and conv_tc_ok(dy, KH, KW, 1, pad_t, Ci, (x.size(1), x.size(2)))):
+        dx = conv_tc_kcc(dy, w_kcc, Ci_w, 1, None, KH, KW, pad_t, Ci, out_hw=(x.size(1), x.size(2)),
+                         tag='conv_dgrad_tc')
+      else:
+        wd = w_kcc[:, :Ci].permute(0, 2, 1).reshape(KH * KW * Co, Ci).contiguous()   # exact-fp32 kernel
+        dx = conv_igemm(1, dy, wd, None, KH, KW, 1, pad, (x.size(1), x.size(2)), Ci)
+    if ctx.needs_input_grad[1]:
+      dwp = conv_wgrad(x, dy, KH, KW, 1, pad)                # (T*Ci, Co): already the w_kcc layout
+      if Ci == Ci_w:
+        dw = dwp.view(KH * KW, Ci_w, Co)
+      else:
+        dw = torch.zeros(KH * KW, Ci_w, Co, dtype=torch.float32, device=dwp.device)
+        dw[:, :Ci] = dwp.view(KH * KW, Ci, Co)
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+      db = (torch.zeros(Co, dtype=torch.float32, device=dy.device) if ctx.zero_bias_grad
+            else colsum(dy.view(-1, Co)))
+    return (dx, dw, db) + (None,) * 10
+
+
 class S2D(torch.autograd.Function):
   """Space-to-depth by 2 with zero padding to even size: (N,H,W,C) ->
   (N,ceil(H/2),ceil(W/2),4C), channel = ((y&1)*2+(x&1))*C + c."""
@@ -480,6 +564,15 @@ class S2D(torch.autograd.Function):
     return dx
 
 
+def _kcc_view(weight):
+  """(T, Ci, Co) view of a weight stored in the weight-gradient layout (zero-copy,
+  differentiable: the gradient flows back through the view ops with matching strides)."""
+  if weight.dim() == 2:
+    return weight.t().unsqueeze(0)
+  Co, Ci, KH, KW = weight.shape
+  return weight.permute(2, 3, 1, 0).reshape(KH * KW, Ci, Co)
+
+
 def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds_bn=False,
            stats_out=None, round_out=False):
   """stats_out: zeroed float64 [2*Cout]; receives the per-channel sum and sum of
@@ -487,18 +580,31 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
   round_out: the output is consumed directly by another tensor-core op (no
   normalise/activate pass in between that would round it): write RN-TF32 values."""
   round_out = bool(round_out) and CONV_MATH == 'tf32'
+  Co, C, KH, KW = weight.shape
+  kcc = CONV_MATH == 'tf32' and is_kcc(weight)
   if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
-      and weight.size(2) == 4 and weight.size(3) == 4 and x.size(1) >= 4 and x.size(2) >= 4
-      and weight.size(0) % 32 == 0):
+      and KH == 4 and KW == 4 and x.size(1) >= 4 and x.size(2) >= 4 and Co % 32 == 0):
     # 4x4 stride-2 'valid' conv (the discriminators, scripts/train.py:122-130) ==
     # 2x2 stride-1 conv on the space-to-depth input: runs on the tensor-core
     # kernels (forward, dgrad, wgrad) with no strided gathers.
-    Co, C = weight.size(0), weight.size(1)
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
+    if kcc:
+      # [ky][kx][c][co] -> [(ty,tx)][(py,px,c)][co]: one small copy, no pack pass
+      w2 = weight.permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
+      w2 = w2.reshape(4, 4 * C, Co)
+      if conv_tc_ok(xs, 2, 2, 1, 0, Co, (Ho, Wo)):
+        return ConvKCC.apply(xs, w2, bias, 2, 2, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
+                             round_out)
     w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
     return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
                       round_out)
+  if kcc and stride == 1:
+    Ci = C if in_ch is None else in_ch
+    Hout, Wout = conv_out_size(x.size(1), KH, 1, pad), conv_out_size(x.size(2), KW, 1, pad)
+    if conv_tc_ok(x, KH, KW, 1, pad, Co, (Hout, Wout)) and x.size(3) == Ci:
+      return ConvKCC.apply(x, _kcc_view(weight), bias, KH, KW, pad, act, slope, in_ch, None, feeds_bn,
+                           stats_out, round_out)
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out,
                     round_out)
 
@@ -507,8 +613,14 @@ def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
   """nn.Linear (+ fused ReLU/LeakyReLU) as a 1x1 convolution over rows.
   round_out: the output feeds another tensor-core GEMM (hand over RN-TF32 values)."""
   M, K = x2d.shape
-  y = Conv.apply(x2d.reshape(M, 1, 1, K), weight.view(weight.size(0), K, 1, 1), bias,
-                 1, 0, act, slope, None, None, False, None, bool(round_out) and CONV_MATH == 'tf32')
+  rnd = bool(round_out) and CONV_MATH == 'tf32'
+  x4 = x2d.reshape(M, 1, 1, K)
+  if CONV_MATH == 'tf32' and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
+    y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd)
+  else:
+    w4 = weight.reshape(weight.size(0), K, 1, 1) if not weight.is_contiguous() else \
+        weight.view(weight.size(0), K, 1, 1)
+    y = Conv.apply(x4, w4, bias, 1, 0, act, slope, None, None, False, None, rnd)
   return y.view(M, weight.size(0))
 
 

@@ -40,14 +40,19 @@ class FlatGrads(object):
     dev = self.params[0].device
     self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
     for p, o in zip(self.params, self.offsets):
-      p.grad = self.flat[o:o + p.numel()].view_as(p)
+      p.grad = self._slot(p, o)
+
+  def _slot(self, p, o):
+    """The parameter's slice of the bucket with the parameter's own strides (parameters stored
+    in a permuted layout, layers.to_kcc_, get gradients in the same layout)."""
+    return self.flat[o:o + p.numel()].as_strided(p.shape, p.stride())
 
   def zero(self):
     self.flat.zero_()
     # re-attach in case something replaced .grad (e.g. set_to_none)
     for p, o in zip(self.params, self.offsets):
       if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
-        p.grad = self.flat[o:o + p.numel()].view_as(p)
+        p.grad = self._slot(p, o)
 
   def all_reduce_mean(self, group=None):
     import torch.distributed as dist
@@ -78,7 +83,7 @@ class FlatAdam(object):
       for p, o in zip(bucket.params, bucket.offsets):
         if o % 4:
           raise ValueError('FlatAdam needs FlatGrads(align=4)')
-        dst = self.flat_params[o:o + p.numel()].view_as(p)
+        dst = self.flat_params[o:o + p.numel()].as_strided(p.shape, p.stride())
         dst.copy_(p)
         p.data = dst
     self.exp_avg = torch.zeros_like(flat)
@@ -118,7 +123,7 @@ class TrainStep(object):
   which leaves parameters, moments and step counts untouched."""
 
   def __init__(self, model, obj_discriminator, img_discriminator, args=None,
-               fused_adam=None, group=None, cuda_graph=False, graph_warmup=3):
+               fused_adam=None, group=None, cuda_graph=False, graph_warmup=3, weights='oihw'):
     a = dict(DEFAULT_ARGS)
     if args is not None:
       a.update(args if isinstance(args, dict) else
@@ -143,6 +148,14 @@ class TrainStep(object):
     self.launches_per_replay = 0
     self.replays = 0
     self.nets = {'g': model, 'd_obj': obj_discriminator, 'd_img': img_discriminator}
+    if weights == 'kcc':
+      # conv / linear weights re-stored in the weight-gradient layout: no pack / unpack passes
+      from .layers import to_kcc_
+      for net in self.nets.values():
+        if net is not None:
+          to_kcc_(net)
+    elif weights != 'oihw':
+      raise ValueError("weights must be 'oihw' or 'kcc'")
     self.buckets, self.opts = {}, {}
     for name, net in self.nets.items():
       if net is None:

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -25,6 +26,7 @@
 #include <thread>
 #include <vector>
 #ifndef SG2IM_EMUL_THREADS
+#include <csetjmp>
 #include <ucontext.h>
 #endif
 
@@ -91,11 +93,12 @@ struct MBar {                          // functional mbarrier (tests/emul/tc_emu
   bool inited = false;
 };
 struct Fiber {
-  ucontext_t ctx;
+  ucontext_t ctx;                      // first entry only (makecontext); afterwards jmp_buf switches,
+  jmp_buf jb;                          // which skip swapcontext's signal-mask system call
   std::vector<char> stack;
   uint3 tid;
   unsigned block = 0;                  // index of its CTA inside the gang
-  bool done = false;
+  bool started = false, done = false;
 };
 struct Block {                         // one CTA
   unsigned nthreads = 0, rank = 0;
@@ -115,6 +118,7 @@ struct Gang {                          // the CTAs that run concurrently: one bl
   std::vector<Block> blocks;
   std::vector<Fiber> fibers;
   ucontext_t main_ctx;
+  jmp_buf main_jb;
   unsigned cur = 0;
   unsigned c_alive = 0, c_arrived = 0;
   unsigned long long c_gen = 0;
@@ -122,7 +126,10 @@ struct Gang {                          // the CTAs that run concurrently: one bl
 };
 inline Gang*& gang() { static Gang* g = nullptr; return g; }
 inline Block* current() { Gang* g = gang(); return &g->blocks[g->fibers[g->cur].block]; }
-inline void yield() { Gang* g = gang(); swapcontext(&g->fibers[g->cur].ctx, &g->main_ctx); }
+inline void yield() {
+  Gang* g = gang();
+  if (!_setjmp(g->fibers[g->cur].jb)) _longjmp(g->main_jb, 1);
+}
 inline void block_sync() {
   Block* b = current();
   const unsigned long long g = b->gen;
@@ -152,10 +159,17 @@ inline void fiber_exit_bookkeeping() {
   if (--G->c_alive > 0 && G->c_arrived == G->c_alive) { G->c_arrived = 0; ++G->c_gen; }
 }
 inline void trampoline() {
-  Gang* G = gang();
-  (*G->body)();
-  G->fibers[G->cur].done = true;
-  fiber_exit_bookkeeping();
+  // a fiber lives for the whole process: it runs one CUDA thread of block after block, launch
+  // after launch (no per-block context creation, hence no per-block system calls)
+  for (;;) {
+    Gang* G = gang();
+    (*G->body)();
+    G = gang();
+    Fiber& me = G->fibers[G->cur];
+    me.done = true;
+    fiber_exit_bookkeeping();
+    if (!_setjmp(me.jb)) _longjmp(G->main_jb, 1);      // parked until the next block
+  }
 }
 }  // namespace emul
 #endif
@@ -271,7 +285,8 @@ static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, 
   static emul::Gang G;                                 // fiber stacks are reused across launches
   constexpr size_t STACK = 256 * 1024;
   const unsigned nfib = cluster * nthreads;
-  if (G.fibers.size() < nfib) G.fibers.resize(nfib);
+  if (G.fibers.empty()) G.fibers.resize(4096);         // never reallocated: live fibers hold pointers into it
+  if (nfib > G.fibers.size()) { std::fprintf(stderr, "emul: more than %zu threads per gang\n", G.fibers.size()); std::abort(); }
   for (unsigned f = 0; f < nfib; ++f)
     if (G.fibers[f].stack.size() != STACK) G.fibers[f].stack.resize(STACK);
   G.blocks.resize(cluster);
@@ -303,11 +318,13 @@ static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, 
         f.block = r;
         f.done = false;
         ++blk.w_alive[t >> 5];
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
-        f.ctx.uc_link = &G.main_ctx;
-        makecontext(&f.ctx, (void (*)())emul::trampoline, 0);
+        if (!f.started) {                                // created once per process
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack.data();
+          f.ctx.uc_stack.ss_size = f.stack.size();
+          f.ctx.uc_link = nullptr;
+          makecontext(&f.ctx, (void (*)())emul::trampoline, 0);
+        }
       }
     }
     unsigned remaining = nfib;
@@ -318,7 +335,11 @@ static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, 
         G.cur = f;
         threadIdx = fb.tid;
         blockIdx = G.blocks[fb.block].bid;
-        swapcontext(&G.main_ctx, &fb.ctx);
+        if (!_setjmp(G.main_jb)) {
+          if (fb.started) _longjmp(fb.jb, 1);
+          fb.started = true;
+          setcontext(&fb.ctx);                           // first entry: onto the fiber's own stack
+        }
         if (fb.done) --remaining;
       }
     }

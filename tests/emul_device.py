@@ -32,7 +32,7 @@ def build_lib():
   import glob
   out = os.path.join(tempfile.mkdtemp(prefix='sg2im_emul_'), 'libemul.so')
   src = sorted(glob.glob(os.path.join(ROOT, 'tests', 'emul', 'emul_*.cpp')))
-  cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-DSG2IM_EMUL',
+  cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-Wno-psabi', '-U_FORTIFY_SOURCE', '-DSG2IM_EMUL',
          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
          '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')]
   if CUDA_INC is not None:

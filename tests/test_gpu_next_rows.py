@@ -477,3 +477,42 @@ def test_wgrad_cluster_multicast_matches_single_cta(N, H, W, Ci, Co, K):
     assert rel_err(outs[1], ref) < 2e-5
   finally:
     ops.set_conv_math('fp32')
+
+
+@pytest.mark.parametrize('adam,graph', [(None, False), ('flat', False), (None, True)])
+def test_train_step_with_weights_in_the_gradient_layout(adam, graph):
+  """TrainStep(weights='kcc') on the tensor-core path: forward reads [KH][KW][Cin][Cout] weights
+  MN-major, dgrad K-major with flipped taps, wgrad lands in place — no pack / unpack kernels."""
+  from sg2im_b200 import ops
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.discriminators import PatchDiscriminator, AcCropDiscriminator
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  kw = g['kwargs']
+  with contextlib.redirect_stdout(io.StringIO()):
+    m = Sg2ImModel(vocab=g['vocab'], **kw)
+    d_img = PatchDiscriminator(arch=g['arch'], normalization='batch', activation='leakyrelu-0.2',
+                               padding='valid')
+    d_obj = AcCropDiscriminator(vocab=g['vocab'], arch=g['arch'], normalization='batch',
+                                activation='leakyrelu-0.2', padding='valid', object_size=g['crop'])
+  m.load_state_dict(g['sd_g']); d_img.load_state_dict(g['sd_img']); d_obj.load_state_dict(g['sd_obj'])
+  for net in (m, d_img, d_obj):
+    net.to(dev())
+  ops.set_conv_math('tf32')
+  try:
+    step = TrainStep(m, d_obj, d_img, weights='kcc', fused_adam=adam, cuda_graph=graph, graph_warmup=1)
+    batch = [t.to(dev()) for t in g['batch']]
+    N = batch[0].size(0)
+    for it, seed in enumerate(g['noise_seeds']):
+      torch.manual_seed(seed)
+      noise = torch.randn(N, kw['layout_noise_dim'], *kw['image_size']).to(dev())
+      losses, _ = step.step(batch, noise=noise)
+      for k, v in g['losses'][it].items():
+        assert abs(losses[k] - v) / max(1.0, abs(v)) <= 1e-2, (it, k, losses[k], v)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g['sd_g_after'].keys())
+    for k, v in g['sd_g_after'].items():
+      if v.dtype.is_floating_point:
+        assert (sd[k].cpu() - v).abs().max() < 2e-3, k
+  finally:
+    ops.set_conv_math('fp32')

@@ -30,7 +30,7 @@ _i64, _f32, _int, _ptr = ctypes.c_int64, ctypes.c_float, ctypes.c_int, ctypes.c_
 def lib(tmp_path_factory):
   out = tmp_path_factory.mktemp('emul') / 'libemul.so'
   src = sorted(str(p) for p in (__import__('pathlib').Path(ROOT) / 'tests' / 'emul').glob('emul_*.cpp'))
-  cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-DSG2IM_EMUL',
+  cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-Wno-psabi', '-U_FORTIFY_SOURCE', '-DSG2IM_EMUL',
          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
          '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')] + src + ['-o', str(out)]
   # e.g. SG2IM_EMUL_CXXFLAGS='-g -fsanitize=address,alignment,bounds' with LD_PRELOAD=libasan.so

@@ -154,3 +154,50 @@ def test_staged_tensor_core_switches_through_the_op_layer(emul_next):
   R.test_wgrad_cluster_multicast_matches_single_cta(4, 16, 16, 64, 64, 3)
   R.test_wgrad_cluster_multicast_matches_single_cta(2, 16, 24, 64, 192, 3)
   R.test_eval_bn_folding_sheep('tf32')
+
+
+@needs_tc
+@pytest.mark.parametrize('adam', [None, 'flat'])
+def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
+  """TrainStep(weights='kcc'): conv / linear weights stored [KH][KW][Cin][Cout]; forward reads them
+  MN-major, the data gradient K-major with flipped taps, the weight gradient lands in the same
+  layout — no pack / unpack kernels run — and the losses track the reference like the packed
+  tf32 configuration (tolerance of test_training_iteration_tf32_tensor_core_path).  state_dict
+  keys / shapes / values stay those of the reference."""
+  from sg2im_b200 import ops, _lib
+  from sg2im_b200.train_step import TrainStep
+  g = G.load_golden('train_step.pt')
+  m, d_obj, d_img = G._build_all(g)
+  ops.set_conv_math('tf32')
+  try:
+    step = TrainStep(m, d_obj, d_img, weights='kcc', fused_adam=adam)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g['sd_g'].keys())
+    for k, v in g['sd_g'].items():
+      assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+    calls = []
+    real_call = _lib.call
+    _lib.call = lambda name, *a: (calls.append(name), real_call(name, *a))[1]
+    ops._call = _lib.call
+    try:
+      kw = g['kwargs']
+      for it, seed in enumerate(g['noise_seeds']):
+        noise = G._noise(seed, g['batch'][0].size(0), kw['layout_noise_dim'], kw['image_size'])
+        losses, _ = step.step(g['batch'], noise=noise)
+        for k, v in g['losses'][it].items():
+          assert abs(losses[k] - v) / max(1.0, abs(v)) <= 1e-2, (it, k, losses[k], v)
+    finally:
+      _lib.call = real_call
+      ops._call = real_call
+    # every tensor-core convolution read its weights in place: no pack pass at all, and unpack only
+    # for the (tiny-model) convolutions that stay on the exact-fp32 kernels (38 per iteration with
+    # packed weights, 14 here; none of the benchmark model's convolutions are in that class)
+    assert calls.count('sg2im_conv_tc_kcc') >= 2 * 51 and 'sg2im_conv_tc' not in calls
+    assert 'sg2im_pack_weights' not in calls
+    assert calls.count('sg2im_unpack_wgrad') <= 2 * 14
+    after = m.state_dict()
+    for k, v in g['sd_g_after'].items():
+      if v.dtype.is_floating_point:
+        assert (after[k] - v).abs().max() < 2e-3, k
+  finally:
+    ops.set_conv_math('fp32')
