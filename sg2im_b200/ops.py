@@ -229,14 +229,20 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   return grad
 
 
-def conv_wgrad(x, dy, KH, KW, S, P):
-  """Returns dw packed (KH*KW*Cin, Cout)."""
+def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
+  """Returns dw packed (KH*KW*Cin, Cout).  accumulate_into: a contiguous buffer of that size
+  the kernels ADD into (they combine partial tiles with atomics anyway) instead of a fresh
+  zeroed one — e.g. the parameter's slice of the flat gradient bucket."""
   _chk(x)
   dy = _chk(dy).contiguous()
   N, Hin, Win, Cin = x.shape
   _, Hout, Wout, Cout = dy.shape
   sn, sh, sw, sc = x.stride()
-  dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
+  if accumulate_into is not None:
+    assert accumulate_into.is_contiguous() and accumulate_into.numel() == KH * KW * Cin * Cout
+    dw = accumulate_into.view(KH * KW * Cin, Cout)
+  else:
+    dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
   if CONV_MATH == 'tf32' and S == 1:
     cs = _pixel_stride(x)
     if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
@@ -491,7 +497,7 @@ class ConvKCC(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w_kcc, bias, KH, KW, pad, act, slope, in_ch, out_hw, zero_bias_grad,
-              stats_out, round_out):
+              stats_out, round_out, grad_into=None):
     T, Ci_w, Co = w_kcc.shape
     Ci = Ci_w if in_ch is None else in_ch
     assert T == KH * KW and x.size(3) == Ci and w_kcc.is_contiguous()
@@ -507,6 +513,8 @@ class ConvKCC(torch.autograd.Function):
     ctx.save_for_backward(x, w_kcc, y if act else None)
     ctx.has_bias = bias is not None
     ctx.zero_bias_grad = bool(zero_bias_grad)
+    # the (T, Ci_w, Co) view of the parameter's slot in the flat gradient bucket, or None
+    ctx.grad_into = grad_into if (grad_into is not None and Ci == Ci_w) else None
     return y
 
   @staticmethod
@@ -526,7 +534,11 @@ class ConvKCC(torch.autograd.Function):
       else:
         wd = w_kcc[:, :Ci].permute(0, 2, 1).reshape(KH * KW * Co, Ci).contiguous()   # exact-fp32 kernel
         dx = conv_igemm(1, dy, wd, None, KH, KW, 1, pad, (x.size(1), x.size(2)), Ci)
-    if ctx.needs_input_grad[1]:
+    if ctx.needs_input_grad[1] and ctx.grad_into is not None:
+      # the weight-gradient kernel adds straight into the gradient bucket: no temporary, no zero
+      # fill, no autograd accumulation kernel (the returned gradient is None)
+      conv_wgrad(x, dy, KH, KW, 1, pad, accumulate_into=ctx.grad_into)
+    elif ctx.needs_input_grad[1]:
       dwp = conv_wgrad(x, dy, KH, KW, 1, pad)                # (T*Ci, Co): already the w_kcc layout
       if Ci == Ci_w:
         dw = dwp.view(KH * KW, Ci_w, Co)
@@ -536,7 +548,7 @@ class ConvKCC(torch.autograd.Function):
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = (torch.zeros(Co, dtype=torch.float32, device=dy.device) if ctx.zero_bias_grad
             else colsum(dy.view(-1, Co)))
-    return (dx, dw, db) + (None,) * 10
+    return (dx, dw, db) + (None,) * 11
 
 
 class S2D(torch.autograd.Function):
@@ -562,6 +574,20 @@ class S2D(torch.autograd.Function):
     _call('sg2im_s2d_bwd', _p(dout), N, H, W, C, _p(dx), _stream())
     _count()
     return dx
+
+
+# Training with flat gradient buckets (train_step.FlatGrads) in the kcc weight layout: let the
+# weight-gradient kernels accumulate directly into the parameter's .grad slot.  Switched on by
+# TrainStep(weights='kcc'); off for plain autograd use (hooks / create_graph expect returned grads).
+DIRECT_WGRAD = False
+
+
+def _grad_slot(weight):
+  g = weight.grad
+  if DIRECT_WGRAD and g is not None and weight.requires_grad and g.shape == weight.shape \
+      and g.stride() == weight.stride() and is_kcc(g):
+    return _kcc_view(g)
+  return None
 
 
 def _kcc_view(weight):
@@ -604,7 +630,7 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Hout, Wout = conv_out_size(x.size(1), KH, 1, pad), conv_out_size(x.size(2), KW, 1, pad)
     if conv_tc_ok(x, KH, KW, 1, pad, Co, (Hout, Wout)) and x.size(3) == Ci:
       return ConvKCC.apply(x, _kcc_view(weight), bias, KH, KW, pad, act, slope, in_ch, None, feeds_bn,
-                           stats_out, round_out)
+                           stats_out, round_out, _grad_slot(weight))
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out,
                     round_out)
 
@@ -616,7 +642,8 @@ def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
   rnd = bool(round_out) and CONV_MATH == 'tf32'
   x4 = x2d.reshape(M, 1, 1, K)
   if CONV_MATH == 'tf32' and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
-    y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd)
+    y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd,
+                      _grad_slot(weight))
   else:
     w4 = weight.reshape(weight.size(0), K, 1, 1) if not weight.is_contiguous() else \
         weight.view(weight.size(0), K, 1, 1)

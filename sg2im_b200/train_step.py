@@ -150,12 +150,14 @@ class TrainStep(object):
     self.nets = {'g': model, 'd_obj': obj_discriminator, 'd_img': img_discriminator}
     if weights == 'kcc':
       # conv / linear weights re-stored in the weight-gradient layout: no pack / unpack passes
+      from . import ops
       from .layers import to_kcc_
       for net in self.nets.values():
         if net is not None:
           to_kcc_(net)
     elif weights != 'oihw':
       raise ValueError("weights must be 'oihw' or 'kcc'")
+    self.weights = weights
     self.buckets, self.opts = {}, {}
     for name, net in self.nets.items():
       if net is None:
@@ -165,7 +167,8 @@ class TrainStep(object):
         self.buckets[name] = FlatGrads(net.parameters(), align=4)
         self.opts[name] = FlatAdam(self.buckets[name], lr=a['learning_rate'])
       else:
-        self.buckets[name] = FlatGrads(net.parameters())
+        # kcc: the weight-gradient kernels write float4 atomics straight into the slots
+        self.buckets[name] = FlatGrads(net.parameters(), align=4 if weights == 'kcc' else 1)
         self.opts[name] = torch.optim.Adam(self.buckets[name].params, **kw)
     self.skipped = 0
 
@@ -205,9 +208,16 @@ class TrainStep(object):
     the device (graph mode also accepts pinned host tensors: they are copied
     into the static input buffers).  Returns (losses dict of python floats,
     imgs_pred detached)."""
-    if self.cuda_graph:
-      return self._step_graphed(batch, noise)
-    return self._step_eager(batch, noise)
+    from . import ops
+    prev = ops.DIRECT_WGRAD
+    # kcc: the weight-gradient kernels accumulate in place in the flat gradient buckets
+    ops.DIRECT_WGRAD = self.weights == 'kcc'
+    try:
+      if self.cuda_graph:
+        return self._step_graphed(batch, noise)
+      return self._step_eager(batch, noise)
+    finally:
+      ops.DIRECT_WGRAD = prev
 
   # ------------------------------------------------------------------ graph mode
   def _step_graphed(self, batch, noise):

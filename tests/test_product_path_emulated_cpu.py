@@ -192,6 +192,7 @@ def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
     # every tensor-core convolution read its weights in place: no pack pass at all, and unpack only
     # for the (tiny-model) convolutions that stay on the exact-fp32 kernels (38 per iteration with
     # packed weights, 14 here; none of the benchmark model's convolutions are in that class)
+    assert ops.DIRECT_WGRAD is False                       # only on inside TrainStep.step
     assert calls.count('sg2im_conv_tc_kcc') >= 2 * 51 and 'sg2im_conv_tc' not in calls
     assert 'sg2im_pack_weights' not in calls
     assert calls.count('sg2im_unpack_wgrad') <= 2 * 14
