@@ -300,10 +300,15 @@ int sg2im_deprocess(const float* imgs, int64_t sn, int64_t sc, int64_t sh, int64
  * incremented by the call; `found_inf` (device float, may be NULL): nonzero
  * skips the update AND the increment (the collective non-finite-loss skip of
  * train.py:552-555 inside a CUDA graph).  amsgrad=False, maximize=False,
- * weight_decay = L2 added to the gradient. */
+ * weight_decay = L2 added to the gradient.  rounded_out (may be NULL): also write the updated
+ * parameters rounded to nearest TF32 — the copy the tensor-core kernels read when the weights
+ * live in the weight-gradient layout (the hardware would truncate the fp32 master). */
 int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                    float* step, const float* found_inf, sg2im_stream_t stream);
+                    float* step, const float* found_inf, float* rounded_out,
+                    sg2im_stream_t stream);
+/* y[i] = x[i] rounded to nearest TF32 (initialises that copy). */
+int sg2im_round_tf32(const float* x, int64_t n, float* y, sg2im_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,8 @@ __global__ void adam_tick_kernel(float* step, const float* found_inf) {
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                 float wd, const float* __restrict__ step, const float* __restrict__ found_inf) {
+                 float wd, const float* __restrict__ step, const float* __restrict__ found_inf,
+                 float* __restrict__ rounded) {
   if (found_inf && *found_inf != 0.f) return;
   const float t = *step;
   // bias corrections in double like the host-side reference implementation
@@ -51,6 +52,9 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
       pa[j] = pa[j] - step_size * (ma[j] / denom);
     }
     reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    if (rounded)                                       // RN-TF32 shadow the tensor-core kernels read
+      reinterpret_cast<float4*>(rounded)[i] =
+          make_float4(tf32_rn(pa[0]), tf32_rn(pa[1]), tf32_rn(pa[2]), tf32_rn(pa[3]));
     reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
   }
@@ -62,18 +66,36 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
       float vj = b2 * v[i] + (1.f - b2) * gj * gj;
       m[i] = mj; v[i] = vj;
       p[i] = p[i] - step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+      if (rounded) rounded[i] = tf32_rn(p[i]);
     }
   }
 }
 
+__global__ void __launch_bounds__(256)
+round_tf32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = tf32_rn(x[i]);
+}
+
 }  // namespace
+
+extern "C" int sg2im_round_tf32(const float* x, int64_t n, float* y, sg2im_stream_t stream) {
+  SG_ARG(x && y && n >= 0);
+  if (n == 0) return 0;
+  int64_t blocks = ceil_div64(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  SG_LAUNCH(round_tf32_kernel, (unsigned)blocks, 256, 0, as_stream(stream), x, n, y);
+  SG_LAUNCH_OK();
+  return 0;
+}
 
 extern "C" int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                int64_t n, float lr, float beta1, float beta2, float eps,
                                float weight_decay, float* step, const float* found_inf,
-                               sg2im_stream_t stream) {
+                               float* rounded_out, sg2im_stream_t stream) {
   SG_ARG(params && grads && exp_avg && exp_avg_sq && step && n >= 0);
   SG_ARG(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq));
+  SG_ARG(rounded_out == nullptr || aligned16(rounded_out));
   SG_ARG(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f);
   cudaStream_t st = as_stream(stream);
   SG_LAUNCH(adam_tick_kernel, 1, 1, 0, st, step, found_inf);
@@ -84,7 +106,7 @@ extern "C" int sg2im_adam_flat(float* params, const float* grads, float* exp_avg
     if (blocks < 1) blocks = 1;
     SG_LAUNCH(adam_flat_kernel, (unsigned)blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, lr,
                                                        beta1, beta2, eps, weight_decay, step,
-                                                       found_inf);
+                                                       found_inf, rounded_out);
   }
   SG_LAUNCH_OK();
   return 0;

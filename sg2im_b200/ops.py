@@ -347,18 +347,26 @@ def avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
   _count()
 
 
+def round_tf32(src, dst):
+  """dst[i] = src[i] rounded to nearest TF32 (flat contiguous buffers)."""
+  _chk(src); _chk(dst)
+  _call('sg2im_round_tf32', _p(src), src.numel(), _p(dst), _stream())
+  _count()
+
+
 def adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
-              found_inf=None):
+              found_inf=None, shadow=None):
   """One Adam update of a flat fp32 bucket in place (torch.optim.Adam arithmetic);
   `step` is a 0-dim device float incremented by the call, `found_inf` (0-dim
-  device float or None) nonzero skips update and increment."""
+  device float or None) nonzero skips update and increment; `shadow` (or None)
+  receives the updated parameters rounded to nearest TF32."""
   for t in (params, grads, exp_avg, exp_avg_sq):
     _chk(t)
     if not t.is_contiguous() or t.numel() != params.numel():
       raise RuntimeError('sg2im_b200: adam_flat needs four contiguous buffers of equal length')
   _call('sg2im_adam_flat', _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(),
         float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), _p(step),
-        _p(found_inf), _stream())
+        _p(found_inf), _p(shadow), _stream())
   _count(2)
 
 
@@ -497,20 +505,25 @@ class ConvKCC(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w_kcc, bias, KH, KW, pad, act, slope, in_ch, out_hw, zero_bias_grad,
-              stats_out, round_out, grad_into=None):
+              stats_out, round_out, grad_into=None, w_read=None):
     T, Ci_w, Co = w_kcc.shape
+    if w_read is not None:
+      # RN-TF32 shadow of the same weights (FlatAdam keeps it current): what the kernels read
+      assert w_read.shape == w_kcc.shape and w_read.is_contiguous()
+    else:
+      w_read = w_kcc
     Ci = Ci_w if in_ch is None else in_ch
     assert T == KH * KW and x.size(3) == Ci and w_kcc.is_contiguous()
     Hout = x.size(1) + 2 * pad - KH + 1 if out_hw is None else out_hw[0]
     Wout = x.size(2) + 2 * pad - KW + 1 if out_hw is None else out_hw[1]
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
-    y = conv_tc_kcc(x, w_kcc, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
+    y = conv_tc_kcc(x, w_read, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
                     stats_out if fused_stats else None, round_out)
     if stats_out is not None and not fused_stats:
       _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
-    ctx.save_for_backward(x, w_kcc, y if act else None)
+    ctx.save_for_backward(x, w_read, y if act else None)
     ctx.has_bias = bias is not None
     ctx.zero_bias_grad = bool(zero_bias_grad)
     # the (T, Ci_w, Co) view of the parameter's slot in the flat gradient bucket, or None
@@ -548,7 +561,7 @@ class ConvKCC(torch.autograd.Function):
     if ctx.has_bias and ctx.needs_input_grad[2]:
       db = (torch.zeros(Co, dtype=torch.float32, device=dy.device) if ctx.zero_bias_grad
             else colsum(dy.view(-1, Co)))
-    return (dx, dw, db) + (None,) * 11
+    return (dx, dw, db) + (None,) * 12
 
 
 class S2D(torch.autograd.Function):
@@ -590,6 +603,11 @@ def _grad_slot(weight):
   return None
 
 
+def _shadow(weight):
+  sh = getattr(weight, '_tc_shadow', None)
+  return None if sh is None else _kcc_view(sh)
+
+
 def _kcc_view(weight):
   """(T, Ci, Co) view of a weight stored in the weight-gradient layout (zero-copy,
   differentiable: the gradient flows back through the view ops with matching strides)."""
@@ -620,8 +638,13 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
       w2 = weight.permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
       w2 = w2.reshape(4, 4 * C, Co)
       if conv_tc_ok(xs, 2, 2, 1, 0, Co, (Ho, Wo)):
+        sh = getattr(weight, '_tc_shadow', None)
+        w2r = None
+        if sh is not None:
+          w2r = sh.detach().permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
+          w2r = w2r.reshape(4, 4 * C, Co)
         return ConvKCC.apply(xs, w2, bias, 2, 2, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
-                             round_out)
+                             round_out, None, w2r)
     w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
     return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
                       round_out)
@@ -630,7 +653,7 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Hout, Wout = conv_out_size(x.size(1), KH, 1, pad), conv_out_size(x.size(2), KW, 1, pad)
     if conv_tc_ok(x, KH, KW, 1, pad, Co, (Hout, Wout)) and x.size(3) == Ci:
       return ConvKCC.apply(x, _kcc_view(weight), bias, KH, KW, pad, act, slope, in_ch, None, feeds_bn,
-                           stats_out, round_out, _grad_slot(weight))
+                           stats_out, round_out, _grad_slot(weight), _shadow(weight))
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out,
                     round_out)
 
@@ -643,7 +666,7 @@ def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
   x4 = x2d.reshape(M, 1, 1, K)
   if CONV_MATH == 'tf32' and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
     y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd,
-                      _grad_slot(weight))
+                      _grad_slot(weight), _shadow(weight))
   else:
     w4 = weight.reshape(weight.size(0), K, 1, 1) if not weight.is_contiguous() else \
         weight.view(weight.size(0), K, 1, 1)

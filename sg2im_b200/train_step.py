@@ -74,7 +74,11 @@ class FlatAdam(object):
   the network are untouched (parameters stay ``nn.Parameter``s of the same
   shape; only their storage moves)."""
 
-  def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+  def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, shadow=False):
+    """shadow: keep a round-to-nearest-TF32 copy of the parameters (written by the same kernel)
+    and hang each parameter's view of it on the parameter as `_tc_shadow` — what the tensor-core
+    kernels read when the weights live in the weight-gradient layout (ops.ConvKCC); call
+    refresh_shadow() after loading a state_dict."""
     self.bucket = bucket
     self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
     flat = bucket.flat
@@ -91,12 +95,23 @@ class FlatAdam(object):
     self.step_count = torch.zeros((), dtype=torch.float32, device=flat.device)
     self.found_inf = None            # set by the graph path, like torch's capturable Adam
     self.grad_scale = None
+    self.shadow = None
+    if shadow:
+      self.shadow = torch.zeros_like(flat)
+      for p, o in zip(bucket.params, bucket.offsets):
+        p._tc_shadow = self.shadow[o:o + p.numel()].as_strided(p.shape, p.stride())
+      self.refresh_shadow()
+
+  def refresh_shadow(self):
+    if self.shadow is not None:
+      from . import ops
+      ops.round_tf32(self.flat_params, self.shadow)
 
   def step(self):
     from . import ops
     ops.adam_flat(self.flat_params, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
                   self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                  self.weight_decay, self.found_inf)
+                  self.weight_decay, self.found_inf, self.shadow)
 
 
 def _all_finite(value, group=None):
@@ -165,7 +180,8 @@ class TrainStep(object):
       if fused_adam == 'flat':
         # one streaming kernel per optimiser over flat parameter / moment buckets
         self.buckets[name] = FlatGrads(net.parameters(), align=4)
-        self.opts[name] = FlatAdam(self.buckets[name], lr=a['learning_rate'])
+        self.opts[name] = FlatAdam(self.buckets[name], lr=a['learning_rate'],
+                                   shadow=weights == 'kcc')
       else:
         # kcc: the weight-gradient kernels write float4 atomics straight into the slots
         self.buckets[name] = FlatGrads(net.parameters(), align=4 if weights == 'kcc' else 1)

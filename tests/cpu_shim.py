@@ -134,8 +134,14 @@ def _avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
     dfine[..., df_coff:df_coff + C] = g
 
 
+def _round_tf32(src, dst):
+  u = src.view(torch.int32)
+  finite = (u & 0x7f800000) != 0x7f800000
+  dst.copy_(torch.where(finite, (u + 0x1000) & ~0x1fff, u & ~0x1fff).view(torch.float32))
+
+
 def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
-               found_inf=None):
+               found_inf=None, shadow=None):
   """Mathematical definition of sg2im_adam_flat (csrc/adam.cu), torch/optim/adam.py
   single-tensor arithmetic, in place."""
   if found_inf is not None and float(found_inf) != 0.0:
@@ -150,6 +156,8 @@ def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, 
     bc2_sqrt = (1 - beta2 ** t) ** 0.5
     denom = exp_avg_sq.sqrt() / bc2_sqrt + eps
     params.sub_((lr / bc1) * (exp_avg / denom))
+    if shadow is not None:
+      _round_tf32(params, shadow)
 
 
 @contextlib.contextmanager
@@ -157,7 +165,7 @@ def cpu_ops():
   from sg2im_b200 import ops
   saved = {}
   repl = dict(conv2d=_conv2d, linear=_linear, bn_act=_bn_act, new_stats=_new_stats,
-              adam_flat=_adam_flat, avgpool2_fwd=_avgpool2_fwd, avgpool2_bwd=_avgpool2_bwd,
+              adam_flat=_adam_flat, round_tf32=_round_tf32, avgpool2_fwd=_avgpool2_fwd, avgpool2_bwd=_avgpool2_bwd,
               csr_build=lambda idx, nroles, num_rows: (None, None),
               LayoutStack=_Apply(_layout_stack), Layout=_Apply(_layout), Crop=_Apply(_crop),
               TripleGather=_Apply(_triple_gather), GraphPool=_Apply(_graph_pool))

@@ -50,7 +50,7 @@ def lib(tmp_path_factory):
                                       _i64, _int]
   L.emul_colsum_small.argtypes = [_ptr, _i64, _i64, _ptr]
   L.sg2im_adam_flat.argtypes = [_ptr, _ptr, _ptr, _ptr, _i64, _f32, _f32, _f32, _f32, _f32, _ptr, _ptr,
-                                _ptr]
+                                _ptr, _ptr]
   L.sg2im_deprocess.argtypes = [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int,
                                 _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]
   L.emul_last_error.restype = ctypes.c_char_p
@@ -240,14 +240,18 @@ def test_adam_flat_source_on_cpu(lib):
       grad = torch.randn(n, generator=g)
       ref.grad = grad.clone()
       opt.step()
+      shadow = torch.full((n,), float('nan'))
       _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
-                                   _p(step), None, None))
+                                   _p(step), None, _p(shadow), None))
       assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (n, it)
+      # the RN-TF32 shadow: low 13 mantissa bits clear, within half a TF32 ulp of the master
+      assert int((shadow.view(torch.int32) & 0x1fff).abs().max()) == 0
+      assert bool(((shadow - p).abs() <= p.abs() * 2.0 ** -11 + 1e-30).all())
     assert float(step) == 5
     before = p.clone()
     inf = torch.ones(())
     _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
-                                 _p(step), _p(inf), None))
+                                 _p(step), _p(inf), None, None))
     assert torch.equal(p, before) and float(step) == 5
 
 
