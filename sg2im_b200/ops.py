@@ -645,7 +645,8 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
           w2r = w2r.reshape(4, 4 * C, Co)
         return ConvKCC.apply(xs, w2, bias, 2, 2, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
                              round_out, None, w2r)
-    w2 = weight.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
+    wc = weight if weight.is_contiguous() else weight.contiguous()
+    w2 = wc.view(Co, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Co, 4 * C, 2, 2)
     return Conv.apply(xs, w2, bias, 1, 0, act, slope, None, (Ho, Wo), feeds_bn, stats_out,
                       round_out)
   if kcc and stride == 1:
