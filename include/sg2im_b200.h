@@ -307,6 +307,12 @@ int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* ex
                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                     float* step, const float* found_inf, float* rounded_out,
                     sg2im_stream_t stream);
+/* dx = dy * leaky'(y) and db[c] += sum_m dx[m,c] in one pass (the activation backward of a
+ * conv+bias+LeakyReLU epilogue and its bias gradient, layers.py:39 / crn.py:43-47; autograd
+ * derives both in the reference).  db is accumulated into: zeroed buffer or gradient slot.
+ * C % 4 == 0, 16-byte aligned. */
+int sg2im_act_bwd_colsum(const float* dy, const float* y, float slope, int64_t M, int64_t C,
+                         float* dx, float* db, sg2im_stream_t stream);
 /* y[i] = x[i] rounded to nearest TF32 (initialises that copy). */
 int sg2im_round_tf32(const float* x, int64_t n, float* y, sg2im_stream_t stream);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
   'sg2im_adam_flat': [_ptr, _ptr, _ptr, _ptr, _i64, _f32, _f32, _f32, _f32, _f32, _ptr, _ptr,
                       _ptr, _ptr],
   'sg2im_round_tf32': [_ptr, _i64, _ptr, _ptr],
+  'sg2im_act_bwd_colsum': [_ptr, _ptr, _f32, _i64, _i64, _ptr, _ptr, _ptr],
 }
 
 _lib = None

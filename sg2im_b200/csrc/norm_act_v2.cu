@@ -397,3 +397,71 @@ int sg2im_colsum_small(const float* x, int64_t M, int64_t C, float* out, cudaStr
   SG_LAUNCH(colsum_small_kernel, (unsigned)ceil_div64(C, 32), 256, 0, st, x, (uint32_t)M, (uint32_t)C, out);
   return 0;
 }
+
+// -------------------------------------------- activation backward + bias gradient ---
+// dx = dy * leaky'(y)  AND  db[c] += sum_m dx[m, c]  in ONE pass over dy (the generic path is
+// act_bwd followed by the three-launch colsum, i.e. two passes over the gradient and four
+// launches).  db is ACCUMULATED into (float atomics of per-CTA fp64 partials): pass a zeroed
+// buffer, or the bias' slot of the flat gradient bucket.  Opt-in (ops.FUSE_ACT_BWD).
+namespace {
+
+__global__ void __launch_bounds__(256)
+act_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope,
+                      uint32_t M, uint32_t C, uint32_t rows_per_block, float* __restrict__ dx,
+                      float* __restrict__ db, int TX) {
+  __shared__ double sh[4][256];
+  const uint32_t tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
+  const uint32_t c = (blockIdx.x * TX + tx) * 4;
+  const uint32_t mb = blockIdx.y * rows_per_block;
+  const uint32_t me = min(mb + rows_per_block, M);
+  double d[4] = {0, 0, 0, 0};
+  if (c < C) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    for (uint32_t m = mb + ty; m < me; m += TY) {
+      const size_t o = (size_t)m * C + c;
+      float4 g = ld4(dy + o), yy = ld4(y + o);
+      g.x *= yy.x > 0.f ? 1.f : slope; g.y *= yy.y > 0.f ? 1.f : slope;
+      g.z *= yy.z > 0.f ? 1.f : slope; g.w *= yy.w > 0.f ? 1.f : slope;
+      *reinterpret_cast<float4*>(dx + o) = g;
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+      if (++cnt == 32) {
+        d[0] += s.x; d[1] += s.y; d[2] += s.z; d[3] += s.w;
+        s = make_float4(0.f, 0.f, 0.f, 0.f); cnt = 0;
+      }
+    }
+    d[0] += s.x; d[1] += s.y; d[2] += s.z; d[3] += s.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sh[j][threadIdx.x] = d[j];
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double a = 0;
+      for (uint32_t r = 0; r < TY; ++r) a += sh[j][r * TX + tx];
+      atomicAdd(db + c + j, (float)a);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sg2im_act_bwd_colsum(const float* dy, const float* y, float slope, int64_t M, int64_t C,
+                                    float* dx, float* db, sg2im_stream_t stream) {
+  SG_ARG(dy && y && dx && db && M >= 1 && C >= 4 && C % 4 == 0 && M * C < (1ll << 31));
+  SG_ARG(aligned16(dy) && aligned16(y) && aligned16(dx));
+  int TX; int64_t cblocks;
+  tile_channels(C, TX, cblocks);
+  const int TY = 256 / TX;
+  int64_t want = ceil_div64(148 * 4, cblocks);
+  int64_t rpb = ceil_div64(M, want);
+  if (rpb < (int64_t)4 * TY) rpb = (int64_t)4 * TY;
+  int64_t rblocks = ceil_div64(M, rpb);
+  if (rblocks > 65535) { rblocks = 65535; rpb = ceil_div64(M, rblocks); rblocks = ceil_div64(M, rpb); }
+  dim3 grid((unsigned)cblocks, (unsigned)rblocks);
+  SG_LAUNCH(act_bwd_colsum_kernel, grid, 256, 0, as_stream(stream), dy, y, slope, (uint32_t)M,
+            (uint32_t)C, (uint32_t)rpb, dx, db, TX);
+  SG_LAUNCH_OK();
+  return 0;
+}

@@ -279,6 +279,31 @@ def act_bwd(dy, y, slope):
   return dx
 
 
+# One pass for the activation backward and the bias gradient of a conv+bias+LeakyReLU epilogue
+# (instead of act_bwd + the three-launch colsum), accumulating straight into the bias' slot of the
+# flat gradient bucket inside TrainStep (DIRECT_WGRAD).  Off until timed on hardware.
+FUSE_ACT_BWD = os.environ.get('SG2IM_ACTBWD_FUSED') == '1'
+
+
+def act_bwd_bias(dy, y, slope, bias):
+  """Returns (dx, db) like act_bwd + colsum.  db is None when it was accumulated directly into
+  bias.grad (the caller then returns no bias gradient to autograd)."""
+  C = dy.size(-1)
+  if not (FUSE_ACT_BWD and C % 4 == 0 and dy.numel() < (1 << 31)):
+    dx = act_bwd(dy, y, slope)
+    return dx, colsum(dx.view(-1, C))
+  dy = _chk(dy).contiguous()
+  dx = torch.empty_like(dy)
+  g = bias.grad if bias is not None else None
+  direct = (DIRECT_WGRAD and g is not None and g.is_contiguous() and g.numel() == C
+            and g.data_ptr() % 4 == 0)
+  db = g if direct else torch.zeros(C, dtype=torch.float32, device=dy.device)
+  _call('sg2im_act_bwd_colsum', _p(dy), _p(y), float(slope), dy.numel() // C, C, _p(dx), _p(db),
+        _stream())
+  _count()
+  return dx, (None if direct else db)
+
+
 def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum, eps,
                    unbias_mult=1, sums=None):
   """Batch statistics of x (rows = all dims but the last) -> (scale, shift, save)."""
@@ -431,6 +456,7 @@ class Conv(torch.autograd.Function):
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
     ctx.w_dgrad = w_dgrad                       # packed in the forward pass (PACK_BOTH) or None
     ctx.save_for_backward(x, weight, y if act else None)
+    ctx.bias_ref = bias                         # the Parameter itself (its .grad slot), not a saved value
     ctx.has_bias = bias is not None
     ctx.zero_bias_grad = bool(zero_bias_grad)
     return y
@@ -441,9 +467,14 @@ class Conv(torch.autograd.Function):
     x, weight, y = ctx.saved_tensors
     Co, Ci_w, KH, KW = wshape
     dy = dy.contiguous()
-    if act:
-      dy = act_bwd(dy, y, slope)
     dx = dw = db = None
+    db_done = False
+    if act:
+      if FUSE_ACT_BWD and ctx.has_bias and ctx.needs_input_grad[2] and not ctx.zero_bias_grad:
+        dy, db = act_bwd_bias(dy, y, slope, ctx.bias_ref)
+        db_done = True
+      else:
+        dy = act_bwd(dy, y, slope)
     if ctx.needs_input_grad[0]:
       w_used = weight if Ci == Ci_w else weight[:, :Ci]
       pad_t = KH - 1 - pad
@@ -458,7 +489,7 @@ class Conv(torch.autograd.Function):
     if ctx.needs_input_grad[1]:
       dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
       dw = unpack_wgrad_oihw(dwp, wshape, Ci)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
+    if ctx.has_bias and ctx.needs_input_grad[2] and not db_done:
       if ctx.zero_bias_grad:
         # this conv feeds a train-mode BatchNorm: d(loss)/d(bias) is identically
         # zero (BN subtracts the batch mean); the reference accumulates rounding
@@ -524,6 +555,7 @@ class ConvKCC(torch.autograd.Function):
       _count()
     ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
     ctx.save_for_backward(x, w_read, y if act else None)
+    ctx.bias_ref = bias
     ctx.has_bias = bias is not None
     ctx.zero_bias_grad = bool(zero_bias_grad)
     # the (T, Ci_w, Co) view of the parameter's slot in the flat gradient bucket, or None
@@ -535,9 +567,14 @@ class ConvKCC(torch.autograd.Function):
     KH, KW, pad, act, slope, Ci, Ci_w, Co = ctx.cfg
     x, w_kcc, y = ctx.saved_tensors
     dy = dy.contiguous()
-    if act:
-      dy = act_bwd(dy, y, slope)
     dx = dw = db = None
+    db_done = False
+    if act:
+      if FUSE_ACT_BWD and ctx.has_bias and ctx.needs_input_grad[2] and not ctx.zero_bias_grad:
+        dy, db = act_bwd_bias(dy, y, slope, ctx.bias_ref)
+        db_done = True
+      else:
+        dy = act_bwd(dy, y, slope)
     if ctx.needs_input_grad[0]:
       pad_t = KH - 1 - pad
       if (KH == KW and pad_t >= 0
@@ -558,7 +595,7 @@ class ConvKCC(torch.autograd.Function):
       else:
         dw = torch.zeros(KH * KW, Ci_w, Co, dtype=torch.float32, device=dwp.device)
         dw[:, :Ci] = dwp.view(KH * KW, Ci, Co)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
+    if ctx.has_bias and ctx.needs_input_grad[2] and not db_done:
       db = (torch.zeros(Co, dtype=torch.float32, device=dy.device) if ctx.zero_bias_grad
             else colsum(dy.view(-1, Co)))
     return (dx, dw, db) + (None,) * 12

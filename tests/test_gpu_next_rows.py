@@ -516,3 +516,21 @@ def test_train_step_with_weights_in_the_gradient_layout(adam, graph):
         assert (sd[k].cpu() - v).abs().max() < 2e-3, k
   finally:
     ops.set_conv_math('fp32')
+
+
+def test_fused_activation_backward_bias_gradient():
+  """sg2im_act_bwd_colsum (SG2IM_ACTBWD_FUSED=1) vs act_bwd + colsum."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(5)
+  for M, C in ((1000, 64), (37, 132), (32 * 128 * 128, 64)):
+    dy, y = torch.randn(M, C, generator=g).to(dev()), torch.randn(M, C, generator=g).to(dev())
+    ref_dx = ops.act_bwd(dy, y, 0.2)
+    ref_db = ops.colsum(ref_dx)
+    bias = torch.zeros(C, device=dev(), requires_grad=True)
+    ops.FUSE_ACT_BWD = True
+    try:
+      dx, db = ops.act_bwd_bias(dy, y, 0.2, bias)
+    finally:
+      ops.FUSE_ACT_BWD = False
+    assert torch.equal(dx, ref_dx)
+    assert torch.allclose(db, ref_db, rtol=1e-4, atol=1e-3)

@@ -481,3 +481,16 @@ def test_exact_fp32_conv_sources_on_cpu(api, N, H, W, Ci, Co, K, S, P, act):
   _ok(api, api.sg2im_conv_wgrad(_p(x), sn, sh, sw, sc, N, H, W, Ci, _p(gy), K, K, S, P, Ho, Wo, Co,
                                 _p(dw), None))
   assert rel_err(dw, wr.grad.permute(2, 3, 1, 0).reshape(K * K * Ci, Co)) < 1e-5
+
+
+@pytest.mark.parametrize('M,C', [(50, 8), (1000, 64), (37, 132), (4096, 4)])
+def test_act_backward_with_bias_gradient_source_on_cpu(api, M, C):
+  """csrc/norm_act_v2.cu act_bwd_colsum: dx = dy * leaky'(y) and db += column sums in one pass."""
+  g = torch.Generator().manual_seed(M + C)
+  dy, y = torch.randn(M, C, generator=g), torch.randn(M, C, generator=g)
+  dx = torch.full((M, C), float('nan'))
+  db = torch.full((C,), 2.0)                              # accumulated INTO
+  _ok(api, api.sg2im_act_bwd_colsum(_p(dy), _p(y), 0.2, M, C, _p(dx), _p(db), None))
+  want = torch.where(y > 0, dy, dy * 0.2)
+  assert torch.equal(dx, want)
+  assert torch.allclose(db - 2.0, want.double().sum(0).float(), rtol=1e-5, atol=1e-4)

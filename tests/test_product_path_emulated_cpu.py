@@ -202,3 +202,44 @@ def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
         assert (after[k] - v).abs().max() < 2e-3, k
   finally:
     ops.set_conv_math('fp32')
+
+
+@needs_tc
+def test_fused_activation_backward_and_direct_bias_gradients(emul):
+  """ops.FUSE_ACT_BWD inside TrainStep(weights='kcc'): the bias gradients of conv+bias+LeakyReLU
+  layers accumulate straight into the flat bucket from the activation-backward pass — losses and
+  parameters after two iterations are those of the unfused configuration."""
+  from sg2im_b200 import ops, _lib
+  from sg2im_b200.train_step import TrainStep
+  g = G.load_golden('train_step.pt')
+  results = []
+  for fused in (False, True):
+    m, d_obj, d_img = G._build_all(g)
+    ops.set_conv_math('tf32')
+    ops.FUSE_ACT_BWD = fused
+    calls = []
+    real_call = _lib.call
+    _lib.call = lambda name, *a: (calls.append(name), real_call(name, *a))[1]
+    ops._call = _lib.call
+    try:
+      step = TrainStep(m, d_obj, d_img, weights='kcc', fused_adam='flat')
+      kw = g['kwargs']
+      losses = []
+      for it, seed in enumerate(g['noise_seeds']):
+        noise = G._noise(seed, g['batch'][0].size(0), kw['layout_noise_dim'], kw['image_size'])
+        losses.append(step.step(g['batch'], noise=noise)[0])
+    finally:
+      _lib.call = real_call
+      ops._call = real_call
+      ops.FUSE_ACT_BWD = False
+      ops.set_conv_math('fp32')
+    results.append((losses, {k: v.clone() for k, v in m.state_dict().items()}, calls))
+  (l0, sd0, c0), (l1, sd1, c1) = results
+  for a, b in zip(l0, l1):
+    for k in a:
+      assert abs(a[k] - b[k]) <= 1e-5 * max(1.0, abs(a[k])), k
+  for k, v in sd0.items():
+    if v.dtype.is_floating_point:
+      assert (sd1[k] - v).abs().max() < 1e-5, k
+  assert c1.count('sg2im_act_bwd_colsum') > 0 and c1.count('sg2im_act_bwd') < c0.count('sg2im_act_bwd')
+  assert c1.count('sg2im_colsum') < c0.count('sg2im_colsum')

@@ -29,8 +29,10 @@ SG2IM_PACK_BOTH=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02
 echo "== bench weights in the gradient layout (no pack / unpack)" >> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline --weights kcc > gpurun_out/r02_bench_kcc.json 2>> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_flatadam.json 2>> gpurun_out/r02_first.log
+echo "== bench fused activation backward + bias gradient (kcc, flat Adam)" >> gpurun_out/r02_first.log
+SG2IM_ACTBWD_FUSED=1 timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_actbwd.json 2>> gpurun_out/r02_first.log
 echo "== bench all opt-ins" >> gpurun_out/r02_first.log
-SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 SG2IM_LAYOUT_V2=1 SG2IM_PACK_BOTH=1 SG2IM_COLSUM_V2=1 timeout 300 python bench.py --no-cpu-baseline --adam flat --weights kcc > gpurun_out/r02_bench_all.json 2>> gpurun_out/r02_first.log
+SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 SG2IM_LAYOUT_V2=1 SG2IM_PACK_BOTH=1 SG2IM_COLSUM_V2=1 SG2IM_ACTBWD_FUSED=1 SG2IM_WGRAD_MC=1 timeout 300 python bench.py --no-cpu-baseline --adam flat --weights kcc > gpurun_out/r02_bench_all.json 2>> gpurun_out/r02_first.log
 echo "== conv tile sweep" >> gpurun_out/r02_first.log
 timeout 300 python tools/sweep_conv.py --out gpurun_out/r02_sweep_conv.json >> gpurun_out/r02_first.log 2>&1
 echo "== kernel table (BN v2)" >> gpurun_out/r02_first.log
