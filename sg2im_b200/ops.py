@@ -596,8 +596,12 @@ class ConvKCC(torch.autograd.Function):
         dw = torch.zeros(KH * KW, Ci_w, Co, dtype=torch.float32, device=dwp.device)
         dw[:, :Ci] = dwp.view(KH * KW, Ci, Co)
     if ctx.has_bias and ctx.needs_input_grad[2] and not db_done:
-      db = (torch.zeros(Co, dtype=torch.float32, device=dy.device) if ctx.zero_bias_grad
-            else colsum(dy.view(-1, Co)))
+      if ctx.zero_bias_grad:
+        # exact zero (conv feeds a train-mode BatchNorm).  With the flat gradient bucket zeroed at
+        # the start of the step there is nothing to add: skip the fill and the accumulate kernel
+        db = None if DIRECT_WGRAD else torch.zeros(Co, dtype=torch.float32, device=dy.device)
+      else:
+        db = colsum(dy.view(-1, Co))
     return (dx, dw, db) + (None,) * 12
 
 
