@@ -16,6 +16,12 @@ from emul_device import emulated_device
 
 pytestmark = pytest.mark.skipif(shutil.which('g++') is None, reason='needs g++ (C++20)')
 
+import os  # noqa: E402
+# the longest variants (each repeats full training iterations under emulation) only run with
+# SG2IM_FULL_EMUL=1, to keep the default CPU suite around three minutes
+full = pytest.mark.skipif(os.environ.get('SG2IM_FULL_EMUL') != '1',
+                          reason='long emulated variant: set SG2IM_FULL_EMUL=1')
+
 
 @pytest.fixture
 def emul(monkeypatch):
@@ -143,8 +149,12 @@ def test_layout_v2_through_the_op_layer(emul_next):
   R.test_layout_forward_v2_bit_identical(45, 2, 128, 16, 32, 32, 40)
 
 
-def test_colsum_v2_and_flat_adam_through_the_op_layer(emul_next):
+def test_colsum_v2_through_the_op_layer(emul_next):
   R.test_colsum_small_kernel(37, 179)
+
+
+@full
+def test_flat_adam_training_iterations_fp32(emul_next):
   R.test_train_step_with_flat_adam(False)
 
 
@@ -157,7 +167,7 @@ def test_staged_tensor_core_switches_through_the_op_layer(emul_next):
 
 
 @needs_tc
-@pytest.mark.parametrize('adam', [None, 'flat'])
+@pytest.mark.parametrize('adam', [pytest.param(None, marks=full), 'flat'])
 def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
   """TrainStep(weights='kcc'): conv / linear weights stored [KH][KW][Cin][Cout]; forward reads them
   MN-major, the data gradient K-major with flipped taps, the weight gradient lands in the same
@@ -204,6 +214,7 @@ def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
     ops.set_conv_math('fp32')
 
 
+@full
 @needs_tc
 def test_fused_activation_backward_and_direct_bias_gradients(emul):
   """ops.FUSE_ACT_BWD inside TrainStep(weights='kcc'): the bias gradients of conv+bias+LeakyReLU
