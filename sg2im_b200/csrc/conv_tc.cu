@@ -230,6 +230,187 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// Cluster / TMA-multicast variant of conv_tc_kernel (opt-in: SG2IM_CONV_MC=1; DERIVED TEXTUALLY from the
+// kernel above, which stays byte-identical): the CS CTAs of a thread-block cluster take the CS
+// consecutive Cout tiles of one pixel tile in lockstep; rank 0 fetches every activation (A) tile
+// once and TMA-multicasts it into all of them, each CTA fetches only its own weight tile.  Same
+// protocol as conv_wgrad_tc_mc.cu: full[s] counts A (multicast) + own B bytes; `empty` is the
+// local release, empty_a[s] (count CS, rank 0's copy) collects every CTA's release of the A half
+// through a multicast tcgen05.commit; cluster barriers after init and before exit.  Meant for the
+// small-spatial / wide-channel stages where the per-tap kernel re-fetches A once per Cout tile.
+template <int BN, int WMODE, int CS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  using C = Cfg<BN>;
+  SG_DYN_SMEM(uint8_t, smem_raw);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                          // STAGES x 16 KB
+  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;              // STAGES x BN*128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                                       // [STAGES]
+  uint64_t* empty = bars + C::STAGES;                          // [STAGES]
+  uint64_t* tfull = bars + 2 * C::STAGES;                      // [2]
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* empty_a = bars + 2 * C::STAGES + 5;                // [STAGES]: A-half releases, used on rank 0
+  float* s_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][1024]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  // work unit = the CS tiles of a cluster: same pixels, CS consecutive Cout tiles (n_tiles % CS == 0)
+  const uint32_t rank = cluster_rank();
+  const int unit0 = (int)blockIdx.x / CS, unit_step = (int)gridDim.x / CS, units = total_tiles / CS;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&empty_a[i], CS);
+    }
+    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tc_alloc(tmem_slot, (uint32_t)C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                              // every CTA's barriers exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n-tile over Cout fastest, so CTAs running together share A in L2)
+  auto decode = [&](int tile, int& nt, int& n0, int& y0, int& x0) {
+    nt = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    int tw = m % p.tiles_w; m /= p.tiles_w;
+    int th = m % p.tiles_h; m /= p.tiles_h;
+    n0 = m * p.BI; y0 = th * p.BH; x0 = tw * p.BW;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int unit = unit0; unit < units; unit += unit_step) {
+        int nt, n0, y0, x0;
+        decode(unit * CS + (int)rank, nt, n0, y0, x0);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          int ky = tap / p.KW, kx = tap - ky * p.KW;
+          mbar_wait(&empty[s], ph ^ 1);                      // own MMAs released the stage
+          if (rank == 0) mbar_wait(&empty_a[s], ph ^ 1);     // ... and every peer's released the A half
+          mbar_expect_tx(&full[s], C::STAGE_BYTES);
+          if (rank == 0)
+            tma_load_4d_mc(sA + s * A_STAGE_BYTES, &tmA, &full[s], (uint16_t)((1u << CS) - 1u), cb * 32,
+                           x0 + kx - p.P, y0 + ky - p.P, n0);
+          if constexpr (WMODE == 1) {
+#pragma unroll
+            for (int a = 0; a < BN / 32; ++a)
+              tma_load_3d(sB + s * C::B_STAGE_BYTES + a * 4096, &tmB, &full[s], nt * BN + a * 32,
+                          cb * 32, tap);
+          } else {
+            tma_load_3d(sB + s * C::B_STAGE_BYTES, &tmB, &full[s], cb * 32, nt * BN,
+                        WMODE == 2 ? p.KH * p.KW - 1 - tap : tap);
+          }
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
+      const uint32_t d_hi = 64u | (1u << 14) | (2u << 29);          // SBO 1024 B, v1, SWIZZLE_128B
+      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
+      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
+      int s = 0; uint32_t ph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      for (int unit = unit0; unit < units; unit += unit_step) {
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t at = sA16 + (uint32_t)s * (A_STAGE_BYTES >> 4);
+          const uint32_t bt = sB16 + (uint32_t)s * (C::B_STAGE_BYTES >> 4);
+          if constexpr (WMODE == 1) {
+            // B MN-major: atoms of 32 co (LBO = 4 KB apart), 8 ci rows = 1 KB per K step
+            constexpr uint32_t IDESC_MN = C::IDESC | (1u << 16);
+            const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);         // SBO 512 B, SWIZZLE_128B_BASE32B
+            const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
+            tc_mma_tf32_lh(d_tmem, at, d_hi, btm, bm_hi, IDESC_MN, kb ? 1u : 0u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 2, d_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 4, d_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 6, d_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
+          } else {
+          tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
+          tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
+          }
+          tc_commit(&empty[s], leader);                    // frees the smem stage when the MMAs retire
+          tc_commit_mc(&empty_a[s], (uint16_t)1);          // A half: tell rank 0
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tfull[acc], leader);                    // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+    const int r = q * 32 + lane;                           // tile row = TMEM lane
+    const int img = r / (p.BH * p.BW);
+    const int hh = (r / p.BW) % p.BH, ww = r % p.BW;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int unit = unit0; unit < units; unit += unit_step) {
+      int nt, n0, y0, x0;
+      decode(unit * CS + (int)rank, nt, n0, y0, x0);
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const int n = n0 + img;
+      const bool valid = n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
+      float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
+                    p.y_coff + (long long)nt * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        if (nt * BN + ch * 32 >= p.Cout) break;              // partial last N tile (warp-uniform)
+        float v[32];
+        tc_ld32(taddr + ch * 32, v);
+        epilogue_chunk(v, valid, nt * BN + ch * 32, p.Cout, p.bias, p.act, p.slope, yrow + ch * 32,
+                       p.stats ? s_part : nullptr, lane, p.round_out);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float a = s_part[c], b = s_part[1024 + c];
+      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
+    }
+  }
+  cluster_sync_all();                              // peers may still signal this CTA's barriers until here
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
+  }
+}
+
+
 // =============================================================================
 // Halo variant for KxK (K <= 3) stride-1 convs with narrow outputs (N tile 64):
 // the per-tap kernel above re-fetches every activation tile once per tap and
@@ -470,9 +651,59 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------- host side ---
+template <int BN, int WMODE, int CS>
+int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  const int units = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles / CS;
+#ifdef SG2IM_EMUL
+  int nclusters = units < num_sms() / CS ? units : num_sms() / CS;
+  emul_launch_cluster(CS, dim3((unsigned)(nclusters * CS)), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES,
+                      [=]() { conv_tc_mc_kernel<BN, WMODE, CS>(tmA, tmB, p); });
+  (void)st;
+  return 0;
+#else
+  auto kern = conv_tc_mc_kernel<BN, WMODE, CS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      sg2im_set_error("conv_tc (cluster): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)(num_sms() / CS * CS));
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+    (void)cudaGetLastError();
+    max_clusters = num_sms() / CS / 2 > 0 ? num_sms() / CS / 2 : 1;
+  }
+  int nclusters = units < max_clusters ? units : max_clusters;
+  cfg.gridDim = dim3((unsigned)(nclusters * CS));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) {
+    sg2im_set_error("conv_tc (cluster): launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+#endif
+}
+
 template <int BN, int WMODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
+  if (const char* mc = getenv("SG2IM_CONV_MC")) {          // read per call: tests toggle it in-process
+    if (mc[0] == '1' && p.n_tiles % 4 == 0) return launch_mc<BN, WMODE, 4>(tmA, tmB, p, st);
+    if (mc[0] == '1' && p.n_tiles % 2 == 0) return launch_mc<BN, WMODE, 2>(tmA, tmB, p, st);
+  }
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {

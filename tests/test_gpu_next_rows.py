@@ -534,3 +534,30 @@ def test_fused_activation_backward_bias_gradient():
       ops.FUSE_ACT_BWD = False
     assert torch.equal(dx, ref_dx)
     assert torch.allclose(db, ref_db, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co', [(32, 8, 8, 1024, 1024), (32, 8, 8, 160, 1024), (4, 8, 8, 64, 256)])
+def test_conv_cluster_multicast_matches_default(N, H, W, Ci, Co):
+  """conv_tc_mc_kernel (SG2IM_CONV_MC=1) vs the single-CTA per-tap kernel: same MMAs in the same
+  order => identical bits."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dev())
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(dev())
+    wt = ops.pack_tc_fwd(w)
+    outs = []
+    for mc in (False, True):
+      if mc:
+        os.environ['SG2IM_CONV_MC'] = '1'
+      else:
+        os.environ.pop('SG2IM_CONV_MC', None)
+      try:
+        outs.append(ops.conv_tc(x, wt, None, 3, 3, 1, Co).clone())
+      finally:
+        os.environ.pop('SG2IM_CONV_MC', None)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+  finally:
+    ops.set_conv_math('fp32')

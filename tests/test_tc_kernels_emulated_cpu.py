@@ -56,7 +56,7 @@ def _tf32(t):
 
 @pytest.fixture
 def env():
-  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC')
+  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC')
   def set_(**kw):
     for k in keys:
       os.environ.pop(k, None)
@@ -189,3 +189,50 @@ def test_convolution_straight_from_the_weight_gradient_layout(lib, env, N, H, W,
   assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kcc), Cf, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
                                0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
   assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-6
+
+
+MC_FWD_CASES = [  # N, H, W, Ci, Co, K, P, env  (per-tap kernel, even number of Cout tiles)
+    (2, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 64}),              # 4 Cout tiles -> clusters of 4
+    (2, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 128}),             # 2 Cout tiles -> clusters of 2
+    (3, 8, 8, 96, 512, 3, 1, {'SG2IM_TC_BN': 256}),             # ragged image count, N tile 256
+    (8, 1, 1, 128, 384, 1, 0, {'SG2IM_TC_BN': 64}),             # Linear, 6 tiles -> clusters of 2
+    (2, 16, 16, 32, 128, 3, 1, {'SG2IM_NO_HALO': 1, 'SG2IM_TC_BN': 64}),
+    (40, 4, 4, 64, 128, 3, 1, {'SG2IM_TC_BN': 64})]             # many pixel tiles: persistent loop, phase wraps
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P,e', MC_FWD_CASES)
+@pytest.mark.parametrize('kcc', [False, True])
+def test_cluster_multicast_forward_kernel(lib, env, N, H, W, Ci, Co, K, P, e, kcc):
+  """conv_tc_mc_kernel (SG2IM_CONV_MC=1; not yet run on hardware): rank 0 multicasts the activation
+  tile to the CS CTAs that own consecutive Cout tiles.  Packed weights and, with kcc, the in-place
+  weight-gradient layout (forward MN-major B and data gradient with flipped taps)."""
+  env(SG2IM_CONV_MC=1, **e)
+  g = torch.Generator().manual_seed(Ci + Co + N)
+  T = K * K
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w = _tf32(torch.randn(Co, Ci, K, K, generator=g) * 0.1)
+  b = torch.randn(Co, generator=g)
+  Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+  y = torch.empty(N, Ho, Wo, Co)
+  c0 = lib.emul_cluster_blocks_run()
+  if kcc:
+    kw = w.permute(2, 3, 1, 0).reshape(T, Ci, Co).contiguous()
+    lib.sg2im_conv_tc_kcc.argtypes = __import__('sg2im_b200._lib', fromlist=['x']).SIGNATURES['sg2im_conv_tc_kcc']
+    rc = lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kw), Ci, 0, _p(b), K, K, P, Ho, Wo, Co, 0, 0.0,
+                               _p(y), Co, 0, None, 0, None)
+  else:
+    wt = w.permute(2, 3, 0, 1).reshape(T, Co, Ci).contiguous()
+    rc = lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), _p(b), K, K, P, Ho, Wo, Co, 0, 0.0, _p(y), Co,
+                           0, None, 0, None)
+  assert rc == 0, lib.emul_last_error()
+  assert lib.emul_cluster_blocks_run() > c0                # the cluster kernel really ran
+  xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  ref = F.conv2d(xr, w, b, padding=P)
+  assert rel_err(y, ref.permute(0, 2, 3, 1)) < 2e-6
+  if kcc and Ci % 64 == 0:                                 # data gradient: Cout_dgrad = Ci tiles must pair up
+    gy = _tf32(torch.randn(N, Ho, Wo, Co, generator=g))
+    ref.backward(gy.permute(0, 3, 1, 2))
+    dx = torch.empty(N, H, W, Ci)
+    assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kw), Ci, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
+                                 0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
+    assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-6
