@@ -3,8 +3,8 @@ training iteration (round-2 tuning aid; not part of the library).
 
 For every distinct forward / data-gradient shape recorded in
 profiles/r01_tf32_conv_shapes_v2.json, time sg2im_conv_tc with the N tile pinned
-to 64 / 128 / 256 (SG2IM_TC_BN) and with the halo kernel on / off (SG2IM_NO_HALO),
-next to the built-in heuristic.  CUDA events, 3 warm-up + 10 timed launches,
+to 64 / 128 / 256 (SG2IM_TC_BN), with the halo kernel on / off (SG2IM_NO_HALO) and with the
+cluster-multicast per-tap kernel (SG2IM_CONV_MC), next to the built-in heuristic.  CUDA events, 3 warm-up + 10 timed launches,
 input larger than L2 or L2 flushed between launches is NOT attempted here: this
 is a relative comparison of variants on identical inputs.
 
@@ -57,8 +57,11 @@ def main():
   args = ap.parse_args()
   dev = torch.device('cuda:0')
   ops.set_conv_math('tf32')
-  variants = [('auto', None, False), ('bn64', '64', False), ('bn128', '128', False),
-              ('bn256', '256', False), ('nohalo', None, True), ('nohalo128', '128', True)]
+  # (name, SG2IM_TC_BN, SG2IM_NO_HALO, SG2IM_CONV_MC)
+  variants = [('auto', None, False, False), ('bn64', '64', False, False), ('bn128', '128', False, False),
+              ('bn256', '256', False, False), ('nohalo', None, True, False), ('nohalo128', '128', True, False),
+              ('mc', None, True, True), ('mc64', '64', True, True), ('mc128', '128', True, True),
+              ('mc256', '256', True, True)]
   results = []
   for (N, H, W, Ci, Co, K, S), ref_ms in shapes()[:args.top]:
     torch.manual_seed(0)
@@ -68,17 +71,19 @@ def main():
     out_hw = (H + 2 * P - K + 1, W + 2 * P - K + 1)
     flops = 2.0 * N * out_hw[0] * out_hw[1] * Ci * Co * K * K
     row = {'shape': [N, H, W, Ci, Co, K], 'r01_us': ref_ms * 1e3}
-    for name, bn, nohalo in variants:
-      os.environ.pop('SG2IM_TC_BN', None)
-      os.environ.pop('SG2IM_NO_HALO', None)
+    for name, bn, nohalo, mc in variants:
+      for k in ('SG2IM_TC_BN', 'SG2IM_NO_HALO', 'SG2IM_CONV_MC'):
+        os.environ.pop(k, None)
       if bn:
         os.environ['SG2IM_TC_BN'] = bn
       if nohalo:
         os.environ['SG2IM_NO_HALO'] = '1'
+      if mc:
+        os.environ['SG2IM_CONV_MC'] = '1'
       us = time_one(x, w, K, P, Co, out_hw)
       row[name] = {'us': us, 'tflops': flops / us / 1e6}
-    os.environ.pop('SG2IM_TC_BN', None)
-    os.environ.pop('SG2IM_NO_HALO', None)
+    for k in ('SG2IM_TC_BN', 'SG2IM_NO_HALO', 'SG2IM_CONV_MC'):
+      os.environ.pop(k, None)
     best = min(variants, key=lambda v: row[v[0]]['us'])[0]
     row['best'] = best
     results.append(row)
