@@ -344,7 +344,8 @@ def run_b200(args, cfg):
                    'objs_per_gpu': int(resident[0][1].numel()),
                    'triples_per_gpu': int(resident[0][-3].size(0)),
                    'image_size': list(cfg['image_size']), 'global_batch': cfg['N'] * world,
-                   'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph),
+                   'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph), 'adam': args.adam, 'weights': args.weights,
+                   'switches': sorted(k for k in os.environ if k.startswith('SG2IM_') and os.environ[k] == '1'),
                    'setup': '4 untimed iterations before the warm-up (3 eager + CUDA-graph capture)'
                             if step.cuda_graph else 'none',
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
