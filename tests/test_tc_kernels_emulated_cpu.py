@@ -32,7 +32,7 @@ def lib(tmp_path_factory):
   from sg2im_b200._lib import SIGNATURES
   out = tmp_path_factory.mktemp('emultc') / 'libemul_tc.so'
   src = sorted(glob.glob(os.path.join(ROOT, 'tests', 'emul', 'emul*.cpp')))
-  subprocess.check_call(['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-Wno-psabi', '-U_FORTIFY_SOURCE', '-DSG2IM_EMUL',
+  subprocess.check_call(['g++'] + os.environ.get('SG2IM_EMUL_CXXFLAGS', '').split() + ['-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-Wno-psabi', '-U_FORTIFY_SOURCE', '-DSG2IM_EMUL',
                          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
                          '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc'), '-I', CUDA_INC] + src +
                         ['-o', str(out)])

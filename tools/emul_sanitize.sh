@@ -17,3 +17,7 @@ SG2IM_EMUL_CXXFLAGS='-g -DSG2IM_EMUL_THREADS -fsanitize=thread' LD_PRELOAD=$TSAN
   TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 log_path=/tmp/sg2im_tsan" \
   python -m pytest tests/test_kernels_emulated_cpu.py -q -p no:cacheprovider | tail -2
 echo "race reports: $(cat /tmp/sg2im_tsan.* 2>/dev/null | grep -c 'WARNING: ThreadSanitizer')"
+echo "== tensor-core kernels (functional model, fibers): alignment,bounds"
+SG2IM_EMUL_CXXFLAGS='-g -fsanitize=alignment,bounds -fno-sanitize-recover=alignment,bounds' \
+  LD_PRELOAD=$(g++ -print-file-name=libubsan.so) \
+  python -m pytest tests/test_tc_kernels_emulated_cpu.py -q -x -p no:cacheprovider | tail -2
