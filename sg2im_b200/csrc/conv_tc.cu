@@ -447,6 +447,7 @@ struct HaloParams {
   float* y; long long y_cstride, y_coff;
   double* stats;
   int round_out;
+  int ti;                          // images per pixel tile (small-image variant only)
 };
 
 template <int WMODE>                              // weight source, see conv_tc_kernel
@@ -650,6 +651,225 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =============================================================================
+// Small-image halo variant (opt-in: SG2IM_HALO_SMALL=1; DERIVED TEXTUALLY from conv_tc_halo_kernel,
+// which stays byte-identical).  The halo kernel needs 16 output rows per tile, so 8x8 (and smaller)
+// feature maps — the first CRN stage with 1024 channels, the 8x8 mask-head layer — fall back to the
+// per-tap kernel, which re-fetches every activation tile once per tap and per Cout tile.  Here a
+// tile is TI images x (16 / TI) rows x 8 columns: the TMA box is taken from a tensor map whose
+// dimensions are ordered (C, W, N, H), so the halo rows of the TI images land INTERLEAVED in shared
+// memory (row = (y * TI + image) * pitch + x) and the 8-row groups of the A operand keep one
+// uniform stride (pitch rows) exactly as before; a filter row further down is TI halo rows away.
+// Two A slots of 26 KB instead of three of 23 KB keep the kernel inside the shared-memory budget.
+// =============================================================================
+constexpr int HS_A_SLOT = 26 * 1024;          // (16/TI + 2) x TI x 10 rows x 128 B <= 25.6 KB for TI = 2
+constexpr int HS_A_SLOTS = 2;
+constexpr int HS_SMEM = HS_A_SLOTS * HS_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512 + 8192;
+
+template <int WMODE>
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv_tc_halo_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const HaloParams p) {
+  SG_DYN_SMEM(uint8_t, smem_raw);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + HS_A_SLOTS * HS_A_SLOT;                    // [2][taps][8 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H_B_TILE);
+  uint64_t* a_full = bars;                    // [3]
+  uint64_t* a_empty = bars + 3;               // [3]
+  uint64_t* b_full = bars + 6;                // [2][9]
+  uint64_t* b_empty = bars + 6 + 18;          // [2][9]
+  uint64_t* tfull = bars + 6 + 36;            // [2]
+  uint64_t* tempty = bars + 6 + 38;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 40);
+  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][1024]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.groups * p.n_tiles;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < HS_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tc_alloc(tmem_slot, 512u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (Cout tile, first pixel tile of the group)
+  auto decode = [&](int item, int& nt, int& pt0) {
+    nt = item % p.n_tiles;
+    pt0 = (item / p.n_tiles) * H_T;
+  };
+  // a pixel tile = TI images x TH rows x 8 columns (TI * TH == 16); n = first image of the group
+  const int TI = p.ti, TH = H_BH / p.ti;
+  auto tile_xy = [&](int pt, int& n, int& y0, int& x0) {
+    int tw = pt % p.tiles_w; int r = pt / p.tiles_w;
+    int th = r % p.tiles_h; n = (r / p.tiles_h) * TI;     // n >= N for padding tiles: TMA zero-fills
+    y0 = th * TH; x0 = tw * H_BW;
+  };
+
+  if (warp == 0) {
+    // ===================== halo (A) producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int t = 0; t < H_T; ++t) {
+            int n, y0, x0;
+            tile_xy(pt0 + t, n, y0, x0);
+            mbar_wait(&a_empty[s], ph ^ 1);
+            mbar_expect_tx(&a_full[s], p.a_bytes);
+            tma_load_4d(sA + s * HS_A_SLOT, &tmA, &a_full[s], cb * 32, x0 - p.P, n, y0 - p.P);
+            if (++s == HS_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight (B) producer =====================
+    if (lane == 0) {
+      uint32_t bcnt = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
+            mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
+            mbar_expect_tx(fb, H_B_TILE);
+            if constexpr (WMODE == 1) {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, nt * H_BN, cb * 32, tap);
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE + 4096, &tmB, fb, nt * H_BN + 32,
+                          cb * 32, tap);
+            } else {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN,
+                          WMODE == 2 ? p.taps - 1 - tap : tap);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
+                                 ((uint32_t)(TILE_M >> 4) << 24);
+      // descriptor words: lo = start>>4 | LBO(=1)<<16, hi = SBO>>4 | version 1<<14 | SWIZZLE_128B<<29
+      // A: 8-row groups `pitch` rows apart (halo rows); B: dense (1024 B)
+      const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t b_hi = 64u | (1u << 14) | (2u << 29);
+      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
+      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
+      const uint32_t row_wrap = (uint32_t)(p.ti * p.pitch - p.KW) * 8u;   // next ky: TI interleaved halo rows down
+      int s = 0; uint32_t ph = 0;
+      uint32_t bcnt = 0;
+      int aset = 0; uint32_t acc_ph = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        mbar_wait(&tempty[aset], acc_ph ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
+          uint64_t* bf = &b_full[set * H_MAX_TAPS];
+          uint64_t* be = &b_empty[set * H_MAX_TAPS];
+          for (int t = 0; t < H_T; ++t) {
+            mbar_wait(&a_full[s], ph);
+            tc_fence_after();
+            uint32_t at = sA16 + (uint32_t)s * (HS_A_SLOT >> 4);
+            uint32_t bt = b_set;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
+            int kx = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+              if (t == 0) { mbar_wait(&bf[tap], bph); tc_fence_after(); }
+              if constexpr (WMODE == 1) {
+                constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
+                const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
+                const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
+                tc_mma_tf32_lh(d_tmem, at, a_hi, btm, bm_hi, IDESC_MN, (cb | tap) ? 1u : 0u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 2, a_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
+              } else {
+              tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
+              tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
+              }
+              if (t == H_T - 1) tc_commit(&be[tap], leader);
+              at += 8u; bt += (H_B_TILE >> 4);
+              if (++kx == p.KW) { kx = 0; at += row_wrap; }
+            }
+            tc_commit(&a_empty[s], leader);
+            if (++s == HS_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+        tc_commit(&tfull[aset], leader);
+        if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int hh = (r >> 3) / TI, img = (r >> 3) % TI, ww = r & 7;   // row group g = y * TI + image
+    int aset = 0; uint32_t acc_ph = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      int nt, pt0;
+      decode(item, nt, pt0);
+      mbar_wait(&tfull[aset], acc_ph);
+      tc_fence_after();
+      for (int t = 0; t < H_T; ++t) {
+        int n, y0, x0;
+        tile_xy(pt0 + t, n, y0, x0);
+        const bool valid = (pt0 + t) < p.ptiles && (n + img) < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
+        float* yrow = p.y + (((long long)(n + img) * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
+                      p.y_coff + (long long)nt * H_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((aset * H_T + t) * H_BN);
+#pragma unroll 1
+        for (int ch = 0; ch < H_BN / 32; ++ch) {
+          if (nt * H_BN + ch * 32 >= p.Cout) break;
+          float v[32];
+          tc_ld32(taddr + ch * 32, v);
+          epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
+                         yrow + ch * 32, p.stats ? s_part : nullptr, lane, p.round_out);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[aset]);
+      if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float a = s_part[c], b = s_part[1024 + c];
+      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, 512u);
+  }
+}
+
+
 // ------------------------------------------------------------- host side ---
 template <int BN, int WMODE, int CS>
 int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
@@ -825,9 +1045,66 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
   p.y = y; p.y_cstride = y_cstride; p.y_coff = y_coff;
 
   // narrow outputs on real images: halo + weight-stationary kernel
+  // 8-row feature maps (CRN stage 0, 8x8 mask-head layer): two images per tile, opt-in
+  if (const char* hs = getenv("SG2IM_HALO_SMALL")) {
+    if (hs[0] == '1' && KH * KW > 1 && KH <= 3 && KW <= 3 && Hout > 4 && Hout <= 8 && N >= 2) {
+      HaloParams h;
+      const int TI = 2, TH = H_BH / TI;
+      h.ti = TI;
+      h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
+      h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
+      h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, TH);
+      h.ptiles = (int)(ceil_div64(N, TI) * h.tiles_h * h.tiles_w);
+      h.groups = (int)ceil_div64(h.ptiles, H_T);
+      h.n_tiles = (int)ceil_div64(Cout, H_BN);
+      h.cblocks = (int)ceil_div64(Cin, 32);
+      h.a_bytes = (uint32_t)((TH + KH - 1) * TI * h.pitch * 128);
+      h.bias = bias; h.act = act; h.slope = slope;
+      h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
+      h.stats = stats; h.round_out = round_out;
+      CUtensorMap hA, hB;
+      {
+        // dimensions ordered (C, W, N, H): the TI images' halo rows interleave in shared memory
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)N, (cuuint64_t)Hin};
+        cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)Hin * Win * x_cstride * 4,
+                              (cuuint64_t)Win * x_cstride * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)h.pitch, (cuuint32_t)TI, (cuuint32_t)(TH + KH - 1)};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&hA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode small-halo A failed (%d)", (int)r); return -4; }
+      }
+      if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full)) return rc;
+#ifndef SG2IM_EMUL
+      static bool small_attr = false;
+      if (!small_attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<0>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
+        if (e == cudaSuccess)
+          e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
+        if (e != cudaSuccess) {
+          sg2im_set_error("conv_tc_halo_small: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+          return (int)e;
+        }
+        small_attr = true;
+      }
+#endif
+      int items = h.groups * h.n_tiles;
+      int grid = items < num_sms() ? items : num_sms();
+      if (wmode == 1) SG_LAUNCH(conv_tc_halo_small_kernel<1>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
+      else if (wmode == 2) SG_LAUNCH(conv_tc_halo_small_kernel<2>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
+      else SG_LAUNCH(conv_tc_halo_small_kernel<0>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
+      SG_LAUNCH_OK();
+      return 0;
+    }
+  }
   if (KH * KW > 1 && KH <= 3 && KW <= 3 && Hout >= H_BH && Wout >= H_BW && BN <= 128 &&
       getenv("SG2IM_NO_HALO") == nullptr) {
     HaloParams h;
+    h.ti = 1;
     h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
     h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
     h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, H_BH);

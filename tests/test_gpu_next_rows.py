@@ -561,3 +561,38 @@ def test_conv_cluster_multicast_matches_default(N, H, W, Ci, Co):
     assert torch.equal(outs[0], outs[1])
   finally:
     ops.set_conv_math('fp32')
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co', [(32, 8, 8, 1024, 1024), (32, 8, 8, 160, 1024), (5, 8, 8, 64, 96),
+                                         (32, 8, 8, 128, 64)])
+def test_small_image_halo_matches_default(N, H, W, Ci, Co):
+  """conv_tc_halo_small_kernel (SG2IM_HALO_SMALL=1) vs the default dispatch on 8-row feature maps:
+  the same TF32 products, accumulated channel-block-major instead of tap-major (the per-tap kernel
+  serves these shapes by default), so agreement is to fp32 summation order, not bitwise; forward with
+  packed weights, forward and data gradient with in-place weights."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dev())
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(dev())
+    gy = torch.randn(N, H, W, Co, generator=g).to(dev())
+    wt = ops.pack_tc_fwd(w)
+    kcc = w.permute(2, 3, 1, 0).contiguous()
+    ops.round_tf32(kcc, kcc)
+    outs = []
+    for small in (False, True):
+      os.environ.pop('SG2IM_HALO_SMALL', None)
+      if small:
+        os.environ['SG2IM_HALO_SMALL'] = '1'
+      try:
+        outs.append((ops.conv_tc(x, wt, None, 3, 3, 1, Co).clone(),
+                     ops.conv_tc_kcc(x, kcc, Ci, False, None, 3, 3, 1, Co).clone(),
+                     ops.conv_tc_kcc(gy, kcc, Ci, True, None, 3, 3, 1, Ci).clone()))
+      finally:
+        os.environ.pop('SG2IM_HALO_SMALL', None)
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+      assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max())
+  finally:
+    ops.set_conv_math('fp32')

@@ -56,7 +56,7 @@ def _tf32(t):
 
 @pytest.fixture
 def env():
-  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC')
+  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL')
   def set_(**kw):
     for k in keys:
       os.environ.pop(k, None)
@@ -230,6 +230,60 @@ def test_cluster_multicast_forward_kernel(lib, env, N, H, W, Ci, Co, K, P, e, kc
   ref = F.conv2d(xr, w, b, padding=P)
   assert rel_err(y, ref.permute(0, 2, 3, 1)) < 2e-6
   if kcc and Ci % 64 == 0:                                 # data gradient: Cout_dgrad = Ci tiles must pair up
+    gy = _tf32(torch.randn(N, Ho, Wo, Co, generator=g))
+    ref.backward(gy.permute(0, 3, 1, 2))
+    dx = torch.empty(N, H, W, Ci)
+    assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kw), Ci, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
+                                 0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
+    assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-6
+
+
+SMALL_CASES = [  # N, H, W, Ci, Co, K, P
+    (4, 8, 8, 64, 64, 3, 1), (5, 8, 8, 96, 160, 3, 1),       # odd image count: last tile half empty
+    (2, 8, 8, 40, 36, 3, 1), (6, 6, 7, 32, 64, 3, 1),        # ragged channels; Hout = 6 rows, W = 7
+    (3, 8, 20, 32, 64, 3, 1), (4, 9, 9, 32, 32, 2, 0),       # wide rows (3 column tiles); 2x2 taps -> 8x8 out
+    (2, 10, 10, 64, 64, 3, 0)]                               # valid conv: 8x8 output from 10x10
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P', SMALL_CASES)
+@pytest.mark.parametrize('kcc', [False, True])
+def test_small_image_halo_kernel(lib, env, N, H, W, Ci, Co, K, P, kcc):
+  """conv_tc_halo_small_kernel (SG2IM_HALO_SMALL=1; not yet run on hardware): two images per tile
+  through a (C, W, N, H)-ordered tensor map, interleaved halo rows, uniform descriptor stride."""
+  env(SG2IM_HALO_SMALL=1)
+  g = torch.Generator().manual_seed(Ci + Co + N + H)
+  T = K * K
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w = _tf32(torch.randn(Co, Ci, K, K, generator=g) * 0.1)
+  b = torch.randn(Co, generator=g)
+  Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+  assert 4 < Ho <= 8
+  y = torch.full((N, Ho, Wo, Co + 4), 7.0)
+  stats = torch.zeros(2 * Co, dtype=torch.float64)
+  if kcc:
+    kw = w.permute(2, 3, 1, 0).reshape(T, Ci, Co).contiguous()
+    lib.sg2im_conv_tc_kcc.argtypes = __import__('sg2im_b200._lib', fromlist=['x']).SIGNATURES['sg2im_conv_tc_kcc']
+    rc = lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kw), Ci, 0, _p(b), K, K, P, Ho, Wo, Co, 0, 0.0,
+                               _p(y), Co + 4, 4, _p(stats), 0, None)
+  else:
+    wt = w.permute(2, 3, 0, 1).reshape(T, Co, Ci).contiguous()
+    rc = lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), _p(b), K, K, P, Ho, Wo, Co, 0, 0.0, _p(y),
+                           Co + 4, 4, _p(stats), 0, None)
+  assert rc == 0, lib.emul_last_error()
+  xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+  ref = F.conv2d(xr, w, b, padding=P)
+  assert rel_err(y[..., 4:], ref.permute(0, 2, 3, 1)) < 2e-6
+  assert bool((y[..., :4] == 7.0).all())
+  assert torch.allclose(stats[:Co], ref.double().sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+  # the same shape on the default (per-tap) kernels: same products, different summation order
+  env()
+  y0 = torch.empty(N, Ho, Wo, Co)
+  wt = w.permute(2, 3, 0, 1).reshape(T, Co, Ci).contiguous()
+  assert lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), _p(b), K, K, P, Ho, Wo, Co, 0, 0.0, _p(y0), Co, 0,
+                           None, 0, None) == 0
+  assert rel_err(y[..., 4:], y0) < 2e-6
+  if kcc and K - 1 - P >= 0 and 4 < H <= 8:                 # data gradient also lands on 8-row maps
+    env(SG2IM_HALO_SMALL=1)
     gy = _tf32(torch.randn(N, Ho, Wo, Co, generator=g))
     ref.backward(gy.permute(0, 3, 1, 2))
     dx = torch.empty(N, H, W, Ci)

@@ -16,7 +16,7 @@ import torch.nn.functional as F  # noqa: E402
 from emul_device import build_lib  # noqa: E402
 from sg2im_b200._lib import SIGNATURES  # noqa: E402
 
-KEYS = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC')
+KEYS = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL')
 
 
 def tf32(t):
@@ -53,6 +53,10 @@ def main():
     if rng.random() < 0.4: env['SG2IM_TC_BN'] = rng.choice(['64', '128', '256'])
     if rng.random() < 0.5: env['SG2IM_CONV_MC'] = '1'
     if rng.random() < 0.5: env['SG2IM_WGRAD_MC'] = '1'
+    if rng.random() < 0.5:                                 # two-image halo tiles: 5..8 output rows, N >= 2
+      env['SG2IM_HALO_SMALL'] = '1'
+      if K > 1:
+        H, N = rng.randint(5, 8) + K - 1 - 2 * P, rng.randint(2, 7)
     for k in KEYS:
       os.environ.pop(k, None)
     os.environ.update(env)

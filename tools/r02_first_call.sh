@@ -26,6 +26,8 @@ echo "== bench wgrad cluster multicast" >> gpurun_out/r02_first.log
 SG2IM_WGRAD_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_wgradmc.json 2>> gpurun_out/r02_first.log
 echo "== bench forward cluster multicast" >> gpurun_out/r02_first.log
 SG2IM_CONV_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_convmc.json 2>> gpurun_out/r02_first.log
+echo "== bench small-image halo kernel (8-row maps)" >> gpurun_out/r02_first.log
+SG2IM_HALO_SMALL=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halosmall.json 2>> gpurun_out/r02_first.log
 echo "== bench pack-both" >> gpurun_out/r02_first.log
 SG2IM_PACK_BOTH=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_packboth.json 2>> gpurun_out/r02_first.log
 echo "== bench weights in the gradient layout (no pack / unpack)" >> gpurun_out/r02_first.log
