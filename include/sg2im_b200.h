@@ -293,6 +293,26 @@ int sg2im_deprocess(const float* imgs, int64_t sn, int64_t sc, int64_t sh, int64
                     uint32_t* minmax, uint8_t* out, int64_t on, int64_t oc, int64_t oh,
                     int64_t ow, sg2im_stream_t stream);
 
+/* ------------------------------------------------------------ relations --
+ * COCO scene-graph synthesis for a collated batch (sg2im/data/coco.py:294-356 per sample +
+ * the index offsets of coco_collate_fn, coco.py:400-407).  Objects are grouped by image with the
+ * __image__ object last in every image: obj_off[N+1] / trip_off[N+1] are the per-image object and
+ * triple offsets, obj_to_img[O] the image of every object.  Per real object i of an image with at
+ * least two real objects (trip_off says so: the image owns 2*n_real triples, else n_real):
+ * partner[i] = the GLOBAL index of the randomly chosen other object, swap[i] = 0 -> (i, p, partner),
+ * 1 -> (partner, p, i) — the host draws both from Python's `random` in the reference's call order.
+ * p from the boxes (surrounding / inside, strict inequalities) else from the sector of the
+ * difference of the masked centroids (mask value 1; empty mask -> box centre).
+ * pred_ids: HOST int64[7] = ids of left of, right of, above, below, inside, surrounding,
+ * __in_image__.  centers: device scratch float[2*O] (written).  Outputs triples (T,3) int64 with
+ * global object indices and triple_to_img (T): per image first the geometric triples in object
+ * order, then (i, __in_image__, image object) for every real object. */
+int sg2im_coco_relations(const float* boxes, const int64_t* masks, int64_t MH, int64_t MW,
+                         const int64_t* obj_off, const int64_t* trip_off, const int64_t* obj_to_img,
+                         const int64_t* partner, const uint8_t* swap, int64_t O,
+                         const int64_t* pred_ids, float* centers, int64_t* triples,
+                         int64_t* triple_to_img, sg2im_stream_t stream);
+
 /* ------------------------------------------------------------ optimiser --
  * torch.optim.Adam (scripts/train.py:426,436,443; steps at :560,579,592) over
  * one flat fp32 bucket: params/grads/exp_avg/exp_avg_sq are four arrays of n

@@ -5,4 +5,5 @@ legs; never from ``sg2im_b200`` (tests/test_host_cpu.py checks that the product
 package has no import of it).
   sg2im_oracle       generator + discriminators + training iteration
   validation_oracle  de-normalisation, box IoU, the validation pass
+  relations_oracle   COCO scene-graph synthesis of one sample
 """

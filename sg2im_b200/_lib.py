@@ -66,6 +66,8 @@ SIGNATURES = {
                       _ptr, _ptr],
   'sg2im_round_tf32': [_ptr, _i64, _ptr, _ptr],
   'sg2im_act_bwd_colsum': [_ptr, _ptr, _f32, _i64, _i64, _ptr, _ptr, _ptr],
+  'sg2im_coco_relations': [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr,
+                           _ptr, _ptr],
 }
 
 _lib = None

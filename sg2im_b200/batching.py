@@ -163,3 +163,84 @@ def uncollate(batch):
     t[:, 0::2] -= base                       # columns 0 (subject) and 2 (object)
     out.append((img, o, b, t))
   return out
+
+
+# --------------------------------------------------------------------------
+# COCO scene-graph synthesis for a whole batch (sg2im/data/coco.py:294-356)
+# --------------------------------------------------------------------------
+COCO_PREDICATES = ('left of', 'right of', 'above', 'below', 'inside', 'surrounding', '__in_image__')
+
+
+def coco_relation_draws(obj_counts, include_relationships=True, rng=None):
+  """The random part of the reference's graph synthesis, on the host.  obj_counts: objects
+  per image INCLUDING the trailing __image__ object.  For every image with at least two real
+  objects, per real object in order: ``other = random.choice(the other real objects)`` then
+  ``random.random() > 0.5`` keeps (cur, other) as (subject, object) — the same two calls in
+  the same order as coco.py:319-327, so with the same seed and sample order the draws are the
+  reference's.  Returns (partner int64 [O] of GLOBAL indices, -1 where unused; swap uint8 [O],
+  1 = the partner is the subject; obj_off int64 [N+1]; trip_off int64 [N+1])."""
+  import random as _random
+  rng = _random if rng is None else rng
+  O = int(sum(obj_counts))
+  partner = [-1] * O
+  swap = [0] * O
+  obj_off, trip_off = [0], [0]
+  for c in obj_counts:
+    c = int(c)
+    if c < 1:
+      raise ValueError('every image needs its __image__ object')
+    base, n_real = obj_off[-1], c - 1
+    n_rel = n_real if (include_relationships and n_real > 1) else 0
+    for pos in range(n_rel):
+      k = rng.randrange(n_real - 1)
+      partner[base + pos] = base + (k if k < pos else k + 1)
+      swap[base + pos] = 0 if rng.random() > 0.5 else 1
+    obj_off.append(base + c)
+    trip_off.append(trip_off[-1] + n_rel + n_real)
+  return (torch.tensor(partner, dtype=torch.int64), torch.tensor(swap, dtype=torch.uint8),
+          torch.tensor(obj_off, dtype=torch.int64), torch.tensor(trip_off, dtype=torch.int64))
+
+
+def coco_relations(boxes, masks, obj_counts, vocab, include_relationships=True, rng=None,
+                   device=None):
+  """Scene graphs of a collated COCO batch in two kernel launches (sg2im_coco_relations).
+
+  boxes (O,4) float32 and masks (O,M,M) int64 of all objects of the batch, grouped by image
+  with the __image__ object last in each (what coco.py:286-292 builds per sample and
+  coco_collate_fn concatenates); host tensors are uploaded (two copies), device tensors are
+  used in place.  Returns (triples (T,3) int64 with batch-global object indices, triple_to_img
+  (T,), obj_to_img (O,)) on the device — the three graph members of the collate tuple
+  (coco.py:411-418).  Per image the triple order is the reference's: geometric triples in
+  object order, then the __in_image__ triples."""
+  from . import _lib, ops
+  if device is None:
+    device = boxes.device if boxes.is_cuda else torch.device('cuda')
+  partner, swap, obj_off, trip_off = coco_relation_draws(obj_counts, include_relationships, rng)
+  O, T = int(obj_off[-1]), int(trip_off[-1])
+  if boxes.shape != (O, 4) or masks.dim() != 3 or masks.size(0) != O:
+    raise ValueError('coco_relations: boxes %s / masks %s do not match %d objects'
+                     % (tuple(boxes.shape), tuple(masks.shape), O))
+  if masks.dtype != torch.int64 or boxes.dtype != torch.float32:
+    raise ValueError('coco_relations: boxes float32 and masks int64 expected (coco.py:291-292)')
+  names = vocab['pred_name_to_idx']
+  pred_ids = torch.tensor([names[p] for p in COCO_PREDICATES], dtype=torch.int64)   # host array
+  counts = torch.as_tensor([int(c) for c in obj_counts], dtype=torch.int64)
+  # one staging buffer for the five small index arrays
+  obj_to_img_h = torch.repeat_interleave(torch.arange(counts.numel(), dtype=torch.int64), counts)
+  ints = torch.cat([obj_off, trip_off, obj_to_img_h, partner]).to(device, non_blocking=True)
+  n1 = obj_off.numel()
+  d_obj_off, d_trip_off = ints[:n1], ints[n1:2 * n1]
+  d_obj_to_img, d_partner = ints[2 * n1:2 * n1 + O], ints[2 * n1 + O:]
+  d_swap = swap.to(device, non_blocking=True)
+  boxes = ops._chk(boxes.to(device, non_blocking=True).contiguous(), name='boxes')
+  masks = ops._chk(masks.to(device, non_blocking=True).contiguous(), dtype=torch.int64, name='masks')
+  centers = torch.empty(max(O, 1), 2, dtype=torch.float32, device=device)
+  triples = torch.empty(T, 3, dtype=torch.int64, device=device)
+  triple_to_img = torch.empty(T, dtype=torch.int64, device=device)
+  if T == 0:                                           # only __image__ objects: nothing to write
+    return triples, triple_to_img, d_obj_to_img
+  _lib.call('sg2im_coco_relations', boxes.data_ptr(), masks.data_ptr(), masks.size(1), masks.size(2),
+            d_obj_off.data_ptr(), d_trip_off.data_ptr(), d_obj_to_img.data_ptr(), d_partner.data_ptr(),
+            d_swap.data_ptr(), O, pred_ids.data_ptr(), centers.data_ptr(), triples.data_ptr(),
+            triple_to_img.data_ptr(), ops._stream())
+  return triples, triple_to_img, d_obj_to_img

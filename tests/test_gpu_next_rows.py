@@ -596,3 +596,46 @@ def test_small_image_halo_matches_default(N, H, W, Ci, Co):
       assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max())
   finally:
     ops.set_conv_math('fp32')
+
+
+def test_coco_relations_match_the_reference_samples_and_scale():
+  """sg2im_coco_relations (COCO scene-graph synthesis): the reference's own
+  samples (tests/golden/coco_rel.pt) collated into one batch, against the pinned oracle; then a
+  training-size batch (32 images x 7 objects) checked through properties."""
+  import random
+  from oracle import relations_oracle as RO
+  from sg2im_b200 import batching
+  d = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'coco_rel.pt'))
+  names = d['pred_names']
+  idx = {n: i for i, n in enumerate(names)}
+  vocab = {'object_name_to_idx': {'__image__': 0}, 'pred_name_to_idx': idx}
+  for mask_size in (16, 5):
+    samples = [s for s in d['samples'] if s['masks'].size(1) == mask_size]
+    rng = random.Random(4)
+    want, base = [], 0
+    for s in samples:
+      t, _ = RO.sample_triples(s['objs'], s['boxes'], s['masks'].long(), idx, rng=rng)
+      want += [[a + base, p, b + base] for a, p, b in t]
+      base += s['objs'].numel()
+    boxes = torch.cat([s['boxes'] for s in samples])
+    masks = torch.cat([s['masks'].long() for s in samples])
+    counts = [s['objs'].numel() for s in samples]
+    triples, t2i, o2i = batching.coco_relations(boxes, masks, counts, vocab, rng=random.Random(4), device=dev())
+    assert triples.device == dev() or triples.device.type == dev().type
+    assert torch.equal(triples.cpu(), torch.tensor(want))   # golden margins are >= 3e-2
+    assert torch.equal(t2i.cpu(), torch.repeat_interleave(
+        torch.arange(len(counts)), torch.tensor([2 * (c - 1) if c > 2 else c - 1 for c in counts])))
+  # training-size batch: structure of the table
+  g = torch.Generator().manual_seed(0)
+  N, c = 32, 7
+  xy = torch.rand(N * c, 2, generator=g) * 0.6
+  boxes = torch.cat([xy, xy + torch.rand(N * c, 2, generator=g) * 0.4], 1)
+  masks = (torch.rand(N * c, 16, 16, generator=g) < 0.5).long()
+  triples, t2i, o2i = batching.coco_relations(boxes.to(dev()), masks.to(dev()), [c] * N, vocab,
+                                              rng=random.Random(1), device=dev())
+  triples, t2i, o2i = triples.cpu(), t2i.cpu(), o2i.cpu()
+  assert triples.shape == (N * 2 * (c - 1), 3)
+  assert torch.equal(o2i[triples[:, 0]], t2i) and torch.equal(o2i[triples[:, 2]], t2i)   # never across images
+  in_img = triples[:, 1] == idx['__in_image__']
+  assert int(in_img.sum()) == N * (c - 1) and bool((triples[in_img, 2] % c == c - 1).all())
+  assert bool((triples[~in_img, 0] != triples[~in_img, 2]).all())
