@@ -639,3 +639,37 @@ def test_coco_relations_match_the_reference_samples_and_scale():
   in_img = triples[:, 1] == idx['__in_image__']
   assert int(in_img.sum()) == N * (c - 1) and bool((triples[in_img, 2] % c == c - 1).all())
   assert bool((triples[~in_img, 0] != triples[~in_img, 2]).all())
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Cf,Co,K,P', [
+    (32, 8, 8, 160, 1184, 1024, 3, 1),      # CRN stage 0 conv 1: channel prefix of a wider weight, per-tap kernel
+    (8, 32, 32, 256, 256, 256, 3, 1),       # BN=128/256 per-tap tiles
+    (4, 128, 128, 288, 288, 64, 3, 1),      # halo kernel (weight-stationary)
+    (4, 64, 64, 96, 96, 128, 2, 0),         # 2x2 taps (the space-to-depth discriminator convs)
+    (448, 1, 1, 384, 384, 512, 1, 0),       # linear layer as a 1x1 convolution
+])
+def test_conv_from_weight_gradient_layout_matches_packed(N, H, W, Ci, Cf, Co, K, P):
+  """sg2im_conv_tc_kcc (WMODE 1 forward: MN-major B operand; WMODE 2 data gradient: tap flip) vs
+  the validated kernels on packed weights.  Same A operand, same products, same accumulation
+  order => identical bits; the weights are RN-TF32 in both."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(Ci + Co + K)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dev())
+    w_full = (torch.randn(Co, Cf, K, K, generator=g) * 0.05).to(dev())
+    b = torch.randn(Co, generator=g).to(dev())
+    Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+    gy = torch.randn(N, Ho, Wo, Co, generator=g).to(dev())
+    kcc = w_full.permute(2, 3, 1, 0).reshape(K * K, Cf, Co).contiguous()
+    ops.round_tf32(kcc, kcc)
+    y_ref = ops.conv_tc(x, ops.pack_tc_fwd(w_full, Ci), b, K, K, P, Co, 1, 0.2)
+    y = ops.conv_tc_kcc(x, kcc, Cf, False, b, K, K, P, Co, 1, 0.2)
+    assert torch.equal(y, y_ref)
+    if K - 1 - P >= 0:
+      dx_ref = ops.conv_tc(gy, ops.pack_tc_dgrad(w_full, Ci), None, K, K, K - 1 - P, Ci, out_hw=(H, W))
+      dx = ops.conv_tc_kcc(gy, kcc, Cf, True, None, K, K, K - 1 - P, Ci, out_hw=(H, W))
+      assert torch.equal(dx, dx_ref)
+    torch.cuda.synchronize()
+  finally:
+    ops.set_conv_math('fp32')

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2 (run under gpurun from the repo root):
-#   gpurun --timeout 2400 -- 'bash tools/r02_first_call.sh'      (about 25 GPU-minutes)
+#   gpurun --timeout 2700 -- 'bash tools/r02_first_call.sh'      (about 25-30 GPU-minutes)
 # 1. hardware validation of everything written after round 1's GPU budget ran out
 # 2. A/B of the opt-in kernels on the default bench
 # 3. tile sweep of the conv kernel over the step's shapes
@@ -8,10 +8,25 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-echo "== unverified GPU tests" | tee gpurun_out/r02_first.log
-SG2IM_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_next_rows.py -q -m gpu -rf \
-    >> gpurun_out/r02_first.log 2>&1
-echo "exit $?" >> gpurun_out/r02_first.log
+LOG=gpurun_out/r02_first.log
+: > $LOG
+# each group of not-yet-run kernels in its own process and under its own timeout: a kernel that
+# hangs or faults on hardware takes down only its group, and its A/B bench below is skipped
+group() {   # name, timeout, -k expression
+  echo "== tests: $1" >> $LOG
+  SG2IM_RUN_UNVERIFIED=1 timeout "$2" python -m pytest tests/test_gpu_next_rows.py -q -m gpu -rf -k "$3" >> $LOG 2>&1
+  local rc=$?
+  echo "exit $rc ($1)" >> $LOG
+  eval "RC_$1=$rc"
+}
+group rows 600 "deprocess or check_model or staged_batch or align_corners or eval_bn or coco_relations"
+group simt 600 "bn_backward_v2 or layout_backward_v2 or layout_forward_v2 or scale_act_forward_v2 or colsum or pack_both or flat_adam_kernel or fused_activation"
+group kcc 300 "conv_from_weight_gradient_layout"
+group wgradmc 300 "wgrad_cluster_multicast"
+group convmc 300 "conv_cluster_multicast"
+group halosmall 300 "small_image_halo"
+group steps 600 "train_step_with"
+grep -E "^exit|passed|failed" $LOG
 echo "== bench default" >> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_default.json 2>> gpurun_out/r02_first.log
 echo "== bench BN backward v2" >> gpurun_out/r02_first.log
@@ -23,20 +38,27 @@ SG2IM_LAYOUT_V2=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02
 echo "== bench flat Adam" >> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline --adam flat > gpurun_out/r02_bench_flatadam.json 2>> gpurun_out/r02_first.log
 echo "== bench wgrad cluster multicast" >> gpurun_out/r02_first.log
-SG2IM_WGRAD_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_wgradmc.json 2>> gpurun_out/r02_first.log
+[ "$RC_wgradmc" = 0 ] && SG2IM_WGRAD_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_wgradmc.json 2>> gpurun_out/r02_first.log
 echo "== bench forward cluster multicast" >> gpurun_out/r02_first.log
-SG2IM_CONV_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_convmc.json 2>> gpurun_out/r02_first.log
+[ "$RC_convmc" = 0 ] && SG2IM_CONV_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_convmc.json 2>> gpurun_out/r02_first.log
 echo "== bench small-image halo kernel (8-row maps)" >> gpurun_out/r02_first.log
-SG2IM_HALO_SMALL=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halosmall.json 2>> gpurun_out/r02_first.log
+[ "$RC_halosmall" = 0 ] && SG2IM_HALO_SMALL=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halosmall.json 2>> gpurun_out/r02_first.log
 echo "== bench pack-both" >> gpurun_out/r02_first.log
 SG2IM_PACK_BOTH=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_packboth.json 2>> gpurun_out/r02_first.log
 echo "== bench weights in the gradient layout (no pack / unpack)" >> gpurun_out/r02_first.log
-timeout 300 python bench.py --no-cpu-baseline --weights kcc > gpurun_out/r02_bench_kcc.json 2>> gpurun_out/r02_first.log
-timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_flatadam.json 2>> gpurun_out/r02_first.log
+[ "$RC_kcc" = 0 ] && timeout 300 python bench.py --no-cpu-baseline --weights kcc > gpurun_out/r02_bench_kcc.json 2>> gpurun_out/r02_first.log
+[ "$RC_kcc" = 0 ] && timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_flatadam.json 2>> gpurun_out/r02_first.log
 echo "== bench fused activation backward + bias gradient (kcc, flat Adam)" >> gpurun_out/r02_first.log
-SG2IM_ACTBWD_FUSED=1 timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_actbwd.json 2>> gpurun_out/r02_first.log
+[ "$RC_kcc" = 0 ] && SG2IM_ACTBWD_FUSED=1 timeout 300 python bench.py --no-cpu-baseline --weights kcc --adam flat > gpurun_out/r02_bench_kcc_actbwd.json 2>> gpurun_out/r02_first.log
 echo "== bench all opt-ins" >> gpurun_out/r02_first.log
-SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 SG2IM_LAYOUT_V2=1 SG2IM_PACK_BOTH=1 SG2IM_COLSUM_V2=1 SG2IM_ACTBWD_FUSED=1 SG2IM_WGRAD_MC=1 timeout 300 python bench.py --no-cpu-baseline --adam flat --weights kcc > gpurun_out/r02_bench_all.json 2>> gpurun_out/r02_first.log
+ALL="SG2IM_PACK_BOTH=1"
+[ "$RC_simt" = 0 ] && ALL="$ALL SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 SG2IM_LAYOUT_V2=1 SG2IM_COLSUM_V2=1 SG2IM_ACTBWD_FUSED=1"
+[ "$RC_wgradmc" = 0 ] && ALL="$ALL SG2IM_WGRAD_MC=1"
+[ "$RC_halosmall" = 0 ] && ALL="$ALL SG2IM_HALO_SMALL=1"
+ARGS="--adam flat"
+[ "$RC_kcc" = 0 ] && [ "$RC_steps" = 0 ] && ARGS="$ARGS --weights kcc"
+echo "all: $ALL $ARGS" >> gpurun_out/r02_first.log
+env $ALL timeout 300 python bench.py --no-cpu-baseline $ARGS > gpurun_out/r02_bench_all.json 2>> gpurun_out/r02_first.log
 echo "== conv tile sweep" >> gpurun_out/r02_first.log
 timeout 300 python tools/sweep_conv.py --out gpurun_out/r02_sweep_conv.json >> gpurun_out/r02_first.log 2>&1
 echo "== kernel table (BN v2)" >> gpurun_out/r02_first.log
