@@ -27,6 +27,11 @@ group convmc 300 "conv_cluster_multicast"
 group halosmall 300 "small_image_halo"
 group steps 600 "train_step_with"
 grep -E "^exit|passed|failed" $LOG
+echo "== tcgen05 issue-rate probe" >> $LOG
+(timeout 120 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I sg2im_b200/csrc \
+   -o /tmp/umma_rate_probe tools/umma_rate_probe.cu -lcuda && timeout 60 /tmp/umma_rate_probe) \
+   > gpurun_out/r02_umma_rate.txt 2>&1
+echo "exit $?" >> $LOG
 echo "== bench default" >> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_default.json 2>> gpurun_out/r02_first.log
 echo "== bench BN backward v2" >> gpurun_out/r02_first.log
