@@ -34,6 +34,7 @@ struct Case {
   int b_mode;       // 0: K-major dense   1: MN-major (SBO 512, atoms 4 KB apart)
   int accs;         // accumulators cycled through (1, 2, 4)
   int iters;        // MMAs issued
+  int m;            // M: 128 (the kernels) or 64 (weights as the A operand: D^T = W X^T)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -60,7 +61,7 @@ rate_kernel(const Case* cases, int ncases, long long* cycles) {
     for (int c = 0; c < ncases; ++c) {
       const Case cs = cases[c];
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(cs.n >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24) | (cs.a_mode == 2 ? (1u << 15) : 0u) |
+                             ((uint32_t)(cs.m >> 4) << 24) | (cs.a_mode == 2 ? (1u << 15) : 0u) |
                              (cs.b_mode == 1 ? (1u << 16) : 0u);
       // A descriptor (lo, hi)
       uint32_t a_lo = (smem_u32(sA) >> 4), a_hi;
@@ -106,16 +107,18 @@ int main() {
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   std::vector<Case> cases;
   const int IT = 4096;
-  for (int n : {64, 128, 256}) cases.push_back({n, 0, 0, 1, IT});          // K-major dense, one accumulator
-  cases.push_back({64, 1, 0, 1, IT});                                      // halo A addressing
-  cases.push_back({64, 0, 0, 2, IT});                                      // alternate accumulators
-  cases.push_back({64, 0, 0, 4, IT});
-  cases.push_back({64, 1, 0, 4, IT});
-  cases.push_back({128, 0, 0, 2, IT});
-  for (int n : {64, 128, 256}) cases.push_back({n, 0, 1, 1, IT});          // MN-major B (kcc forward)
-  cases.push_back({64, 1, 1, 1, IT});                                      // halo A + MN-major B
-  for (int n : {64, 128, 256}) cases.push_back({n, 2, 1, 1, IT});          // weight gradient operands
-  cases.push_back({256, 2, 1, 2, IT});
+  for (int n : {64, 128, 256}) cases.push_back({n, 0, 0, 1, IT, 128});          // K-major dense, one accumulator
+  cases.push_back({64, 1, 0, 1, IT, 128});                                      // halo A addressing
+  cases.push_back({64, 0, 0, 2, IT, 128});                                      // alternate accumulators
+  cases.push_back({64, 0, 0, 4, IT, 128});
+  cases.push_back({64, 1, 0, 4, IT, 128});
+  cases.push_back({128, 0, 0, 2, IT, 128});
+  for (int n : {64, 128, 256}) cases.push_back({n, 0, 1, 1, IT, 128});          // MN-major B (kcc forward)
+  cases.push_back({64, 1, 1, 1, IT, 128});                                      // halo A + MN-major B
+  for (int n : {64, 128, 256}) cases.push_back({n, 2, 1, 1, IT, 128});          // weight gradient operands
+  cases.push_back({256, 2, 1, 2, IT, 128});
+  for (int n : {64, 128, 256}) cases.push_back({n, 0, 0, 1, IT, 64});      // M = 64: half the rows per MMA
+  cases.push_back({256, 0, 0, 2, IT, 64});
   const int nc = (int)cases.size();
   Case* d_cases; long long* d_cyc;
   CK(cudaMalloc(&d_cases, nc * sizeof(Case)));
@@ -132,13 +135,13 @@ int main() {
   CK(cudaMemcpy(cyc.data(), d_cyc, cyc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
   const char* am[] = {"K-major dense", "K-major halo (SBO 1280, shifted)", "MN-major"};
   const char* bm[] = {"K-major", "MN-major"};
-  printf("%d SMs, %d MMAs (128 x N x 8, tf32) per case; cycles per MMA: median over SMs [min, max]; "
-         "math floor = N/2 cycles\n", sms, IT);
+  printf("%d SMs, %d MMAs (M x N x 8, tf32) per case; cycles per MMA: median over SMs [min, max]; "
+         "math floor at M = 128: N/2 cycles\n", sms, IT);
   for (int c = 0; c < nc; ++c) {
     std::vector<double> v;
     for (int b = 0; b < sms; ++b) v.push_back((double)cyc[(size_t)b * nc + c] / cases[c].iters);
     std::sort(v.begin(), v.end());
-    printf("N=%3d  A: %-34s B: %-9s accumulators %d : %6.1f  [%6.1f, %6.1f]\n", cases[c].n,
+    printf("M=%3d N=%3d  A: %-34s B: %-9s accumulators %d : %6.1f  [%6.1f, %6.1f]\n", cases[c].m, cases[c].n,
            am[cases[c].a_mode], bm[cases[c].b_mode], cases[c].accs, v[v.size() / 2], v.front(), v.back());
   }
   return 0;
