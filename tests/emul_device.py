@@ -35,9 +35,10 @@ def build_lib():
   cmd = ['g++', '-std=c++20', '-O1', '-pthread', '-shared', '-fPIC', '-Wno-psabi', '-U_FORTIFY_SOURCE', '-DSG2IM_EMUL',
          '-I', os.path.join(ROOT, 'tests', 'emul'), '-I', os.path.join(ROOT, 'include'),
          '-I', os.path.join(ROOT, 'sg2im_b200', 'csrc')]
-  if CUDA_INC is not None:
+  if CUDA_INC is not None and '-DSG2IM_EMUL_THREADS' not in os.environ.get('SG2IM_EMUL_CXXFLAGS', ''):
     # with the CUDA headers (cuda.h: CUtensorMap) the tensor-core kernels build too, against the
-    # functional tcgen05 / TMA / cluster model of tests/emul/tc_emul.h
+    # functional tcgen05 / TMA / cluster model of tests/emul/tc_emul.h (fiber execution model only:
+    # the OS-thread model used for the ASan / TSan runs builds the SIMT kernels alone)
     src += sorted(glob.glob(os.path.join(ROOT, 'tests', 'emul', 'emultc_*.cpp')))
     cmd += ['-I', CUDA_INC]
   cmd += src + ['-o', out]
