@@ -32,6 +32,11 @@ echo "== tcgen05 issue-rate probe" >> $LOG
    -o /tmp/umma_rate_probe tools/umma_rate_probe.cu -lcuda && timeout 60 /tmp/umma_rate_probe) \
    > gpurun_out/r02_umma_rate.txt 2>&1
 echo "exit $?" >> $LOG
+echo "== CTA-pair (cta_group::2) semantics + rate probe" >> $LOG
+(timeout 120 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I sg2im_b200/csrc \
+   -o /tmp/umma_2cta_probe tools/umma_2cta_probe.cu -lcuda && timeout 60 /tmp/umma_2cta_probe) \
+   > gpurun_out/r02_umma_2cta.txt 2>&1
+echo "exit $?" >> $LOG
 echo "== bench default" >> gpurun_out/r02_first.log
 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_default.json 2>> gpurun_out/r02_first.log
 echo "== bench BN backward v2" >> gpurun_out/r02_first.log
