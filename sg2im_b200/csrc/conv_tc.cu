@@ -869,8 +869,304 @@ conv_tc_halo_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 }
 
+// =============================================================================
+// CTA-pair halo variant (opt-in: SG2IM_HALO_PAIR=1; DERIVED TEXTUALLY from conv_tc_halo_kernel, which
+// stays byte-identical; NOT yet run on hardware — built on the cta_group::2 semantics that
+// tools/umma_2cta_probe.cu is there to pin).  Motivation: the N = 64 kernels run at ~63 cycles per
+// 128 x 64 x 8 MMA against 32 cycles of math, i.e. bound by the shared-memory operand feed (4 KB of
+// A + 2 KB of B per MMA, profiles/r01_prof_conv_tc_halo.txt).  Two CTAs of a cluster work as one
+// M = 256 tile: each keeps its own group of H_T pixel tiles (own halo tiles, own accumulators, own
+// epilogue — all as in the single-CTA kernel) but loads only HALF of every weight tile; rank 0
+// issues tcgen05.mma.cta_group::2, which reads A from both CTAs and the two B halves.
+// Per SM: 5 KB instead of 6 KB of operands per MMA, half the weight traffic from L2.
+// Protocol on top of the single-CTA one:
+//   * rank 1's warp 1 (idle otherwise) relays "my A tile / B half has landed" to rank 0's
+//     a_peer / b_peer barriers (remote mbarrier arrive);
+//   * slot releases and accumulator-ready signals are multicast commits to both CTAs;
+//   * rank 1's epilogue warps release the accumulators on rank 0's tempty (count 8);
+//   * cluster barriers after init and before TMEM is freed.
+// =============================================================================
+constexpr int H2_B_TILE = (H_BN / 2) * KB_BYTES;     // this CTA's 32 of the 64 weight columns: 4 KB
+constexpr int H2_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H2_B_TILE + 1024 + 1024 + 8192;
+
+template <int WMODE>
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const HaloParams p) {
+  SG_DYN_SMEM(uint8_t, smem_raw);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + H_A_SLOTS * H_A_SLOT;                    // [2][taps][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H2_B_TILE);
+  uint64_t* a_full = bars;                    // [3]
+  uint64_t* a_empty = bars + 3;               // [3]
+  uint64_t* b_full = bars + 6;                // [2][9]
+  uint64_t* b_empty = bars + 6 + 18;          // [2][9]
+  uint64_t* tfull = bars + 6 + 36;            // [2]
+  uint64_t* tempty = bars + 6 + 38;           // [2]   used on rank 0: 4 local + 4 remote epilogue warps
+  uint64_t* a_peer = bars + 6 + 40;           // [3]   used on rank 0: rank 1's A tile has landed
+  uint64_t* b_peer = bars + 6 + 43;           // [2][9] used on rank 0: rank 1's B half has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 61);
+  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [2][1024]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  // work unit = (Cout tile, PAIR of pixel-tile groups); rank r owns group 2 * gp + r (a group past
+  // the end is all padding: TMA zero-fills, the epilogue masks)
+  const int gpairs = (p.groups + 1) / 2;
+  const int total = gpairs * p.n_tiles;
+  const int unit0 = (int)blockIdx.x / 2, unit_step = (int)gridDim.x / 2;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_peer[i], 1); }
+    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&b_peer[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tc_alloc2(tmem_slot, 512u);                     // warp 1 of BOTH CTAs
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // both CTAs' barriers exist before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& nt, int& pt0) {
+    nt = item % p.n_tiles;
+    pt0 = ((item / p.n_tiles) * 2 + (int)rank) * H_T;
+  };
+  auto tile_xy = [&](int pt, int& n, int& y0, int& x0) {
+    int tw = pt % p.tiles_w; int r = pt / p.tiles_w;
+    int th = r % p.tiles_h; n = r / p.tiles_h;            // n >= N for padding tiles: TMA zero-fills
+    y0 = th * H_BH; x0 = tw * H_BW;
+  };
+
+  if (warp == 0) {
+    // ===================== halo (A) producer: this CTA's own pixel tiles =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int item = unit0; item < total; item += unit_step) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int t = 0; t < H_T; ++t) {
+            int n, y0, x0;
+            tile_xy(pt0 + t, n, y0, x0);
+            mbar_wait(&a_empty[s], ph ^ 1);
+            mbar_expect_tx(&a_full[s], p.a_bytes);
+            tma_load_4d(sA + s * H_A_SLOT, &tmA, &a_full[s], cb * 32, x0 - p.P, y0 - p.P, n);
+            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight (B) producer: columns 32 * rank .. + 32 of the tile =====================
+    if (lane == 0) {
+      uint32_t bcnt = 0;
+      for (int item = unit0; item < total; item += unit_step) {
+        int nt, pt0;
+        decode(item, nt, pt0);
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
+            mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
+            mbar_expect_tx(fb, H2_B_TILE);
+            if constexpr (WMODE == 1) {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H2_B_TILE, &tmB, fb, nt * H_BN + (int)rank * 32,
+                          cb * 32, tap);
+            } else {
+              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H2_B_TILE, &tmB, fb, cb * 32,
+                          nt * H_BN + (int)rank * 32, WMODE == 2 ? p.taps - 1 - tap : tap);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== rank 1: relay "landed" to rank 0 (whole warp walks the loops, lane 0 signals) ==
+    {
+      int s = 0; uint32_t ph = 0;
+      uint32_t bcnt = 0;
+      for (int item = unit0; item < total; item += unit_step) {
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int t = 0; t < H_T; ++t) {
+            mbar_wait(&a_full[s], ph);
+            if (lane == 0) mbar_arrive_cluster(&a_peer[s], 0u);
+            if (t == 0) {
+              for (int tap = 0; tap < p.taps; ++tap) {
+                mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
+                if (lane == 0) mbar_arrive_cluster(&b_peer[set * H_MAX_TAPS + tap], 0u);
+              }
+            }
+            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== rank 0: pair-MMA issuer (converged warp, lane 0 issues) =====================
+    {
+      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
+                                 ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t b_hi = 64u | (1u << 14) | (2u << 29);
+      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
+      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
+      const uint32_t row_wrap = (uint32_t)(p.pitch - p.KW) * 8u;     // 16-byte units, row = 128 B
+      int s = 0; uint32_t ph = 0;
+      uint32_t bcnt = 0;
+      int aset = 0; uint32_t acc_ph = 0;
+      for (int item = unit0; item < total; item += unit_step) {
+        mbar_wait(&tempty[aset], acc_ph ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
+          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H2_B_TILE >> 4);
+          uint64_t* bf = &b_full[set * H_MAX_TAPS];
+          uint64_t* bp = &b_peer[set * H_MAX_TAPS];
+          uint64_t* be = &b_empty[set * H_MAX_TAPS];
+          for (int t = 0; t < H_T; ++t) {
+            mbar_wait(&a_full[s], ph);
+            mbar_wait(&a_peer[s], ph);
+            tc_fence_after();
+            uint32_t at = sA16 + (uint32_t)s * (H_A_SLOT >> 4);
+            uint32_t bt = b_set;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
+            int kx = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+              if (t == 0) { mbar_wait(&bf[tap], bph); mbar_wait(&bp[tap], bph); tc_fence_after(); }
+              if constexpr (WMODE == 1) {
+                constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
+                const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
+                const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
+                tc_mma2_tf32_lh(d_tmem, at, a_hi, btm, bm_hi, IDESC_MN, (cb | tap) ? 1u : 0u);
+                tc_mma2_tf32_lh(d_tmem, at + 2, a_hi, btm + 64, bm_hi, IDESC_MN, 1u);
+                tc_mma2_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u);
+                tc_mma2_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u);
+              } else {
+                tc_mma2_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u);
+                tc_mma2_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u);
+                tc_mma2_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u);
+                tc_mma2_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u);
+              }
+              if (t == H_T - 1) tc_commit2_mc(&be[tap], (uint16_t)3);
+              at += 8u; bt += (H2_B_TILE >> 4);
+              if (++kx == p.KW) { kx = 0; at += row_wrap; }
+            }
+            tc_commit2_mc(&a_empty[s], (uint16_t)3);
+            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
+          }
+        }
+        tc_commit2_mc(&tfull[aset], (uint16_t)3);
+        if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7): this CTA's own accumulators =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int hh = r >> 3, ww = r & 7;                      // 8-wide x 16-high tile
+    int aset = 0; uint32_t acc_ph = 0;
+    for (int item = unit0; item < total; item += unit_step) {
+      int nt, pt0;
+      decode(item, nt, pt0);
+      mbar_wait(&tfull[aset], acc_ph);
+      tc_fence_after();
+      for (int t = 0; t < H_T; ++t) {
+        int n, y0, x0;
+        tile_xy(pt0 + t, n, y0, x0);
+        const bool valid = (pt0 + t) < p.ptiles && n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
+        float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
+                      p.y_coff + (long long)nt * H_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((aset * H_T + t) * H_BN);
+#pragma unroll 1
+        for (int ch = 0; ch < H_BN / 32; ++ch) {
+          if (nt * H_BN + ch * 32 >= p.Cout) break;
+          float v[32];
+          tc_ld32(taddr + ch * 32, v);
+          epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
+                         yrow + ch * 32, p.stats ? s_part : nullptr, lane, p.round_out);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[aset]); else mbar_arrive_cluster(&tempty[aset], 0u);
+      }
+      if (++aset == 2) { aset = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float a = s_part[c], b = s_part[1024 + c];
+      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
+    }
+  }
+  cluster_sync_all();                               // the peer may still signal / be read until here
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc2(tmem_base, 512u);
+  }
+}
+
 
 // ------------------------------------------------------------- host side ---
+template <int WMODE>
+int launch_halo_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& h, cudaStream_t st) {
+  const int units = ((h.groups + 1) / 2) * h.n_tiles;
+#ifdef SG2IM_EMUL
+  int nclusters = units < num_sms() / 2 ? units : num_sms() / 2;
+  emul_launch_cluster(2, dim3((unsigned)(nclusters * 2)), dim3(H_THREADS), (size_t)H2_SMEM,
+                      [=]() { conv_tc_halo_pair_kernel<WMODE>(tmA, tmB, h); });
+  (void)st;
+  return 0;
+#else
+  auto kern = conv_tc_halo_pair_kernel<WMODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM);
+    if (e != cudaSuccess) {
+      sg2im_set_error("conv_tc_halo_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(H_THREADS);
+  cfg.dynamicSmemBytes = H2_SMEM;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.gridDim = dim3((unsigned)(num_sms() / 2 * 2));
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+    (void)cudaGetLastError();
+    max_clusters = num_sms() / 4 > 0 ? num_sms() / 4 : 1;
+  }
+  int nclusters = units < max_clusters ? units : max_clusters;
+  cfg.gridDim = dim3((unsigned)(nclusters * 2));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, h);
+  if (e != cudaSuccess) {
+    sg2im_set_error("conv_tc_halo_pair: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+#endif
+}
+
 template <int BN, int WMODE, int CS>
 int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -1127,6 +1423,15 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
+    }
+    if (const char* hp = getenv("SG2IM_HALO_PAIR")) {
+      if (hp[0] == '1') {
+        // CTA pairs (cta_group::2): every CTA loads 32 of the 64 columns of each weight tile
+        if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN / 2, wmode, w_rows_full)) return rc;
+        return wmode == 1 ? launch_halo_pair<1>(hA, hB, h, as_stream(stream))
+             : wmode == 2 ? launch_halo_pair<2>(hA, hB, h, as_stream(stream))
+                          : launch_halo_pair<0>(hA, hB, h, as_stream(stream));
+      }
     }
     if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full)) return rc;
 #ifndef SG2IM_EMUL

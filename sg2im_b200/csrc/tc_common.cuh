@@ -171,6 +171,49 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// --- CTA pair (cta_group::2): M = 256 across two SMs that share the B tile (each supplies half of
+// its columns).  Semantics to be pinned on hardware by tools/umma_2cta_probe.cu.
+__device__ __forceinline__ void tc_alloc2(uint32_t* slot, uint32_t ncols) {      // warp 0 of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc2(uint32_t base, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+// converged warp of the even-ranked CTA, one elected lane issues
+__device__ __forceinline__ void tc_mma2_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                                uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// arrive (release, cluster scope) on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
 }  // namespace tc
 #endif  // !SG2IM_EMUL
 
@@ -272,7 +315,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 #ifdef SG2IM_EMUL
 inline EncodeTiledFn get_encode() { return &emul_tensor_map_encode_tiled; }
-inline int num_sms() { return 148; }
+inline int num_sms() {                       // SG2IM_EMUL_SMS: small grids make the persistent loops iterate
+  const char* e = getenv("SG2IM_EMUL_SMS");
+  return e && atoi(e) > 0 ? atoi(e) : 148;
+}
 #else
 inline EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;

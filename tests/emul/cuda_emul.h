@@ -125,6 +125,10 @@ struct Gang {                          // the CTAs that run concurrently: one bl
   const std::function<void()>* body = nullptr;
 };
 inline Gang*& gang() { static Gang* g = nullptr; return g; }
+// optional hooks of a device model layered on top (tc_emul.h: asynchronous TMA / tensor pipe):
+// called once per scheduler sweep over the gang's fibers, and when the gang has finished
+inline void (*&sweep_hook())() { static void (*h)() = nullptr; return h; }
+inline void (*&drain_hook())() { static void (*h)() = nullptr; return h; }
 inline Block* current() { Gang* g = gang(); return &g->blocks[g->fibers[g->cur].block]; }
 inline void yield() {
   Gang* g = gang();
@@ -329,6 +333,7 @@ static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, 
     }
     unsigned remaining = nfib;
     while (remaining) {
+      if (emul::sweep_hook()) emul::sweep_hook()();
       for (unsigned f = 0; f < nfib; ++f) {
         emul::Fiber& fb = G.fibers[f];
         if (fb.done) continue;
@@ -343,6 +348,7 @@ static inline void emul_launch_cluster(unsigned cluster, dim3 grid, dim3 block, 
         if (fb.done) --remaining;
       }
     }
+    if (emul::drain_hook()) emul::drain_hook()();
     emul::blocks_run() += cluster;
     if (cluster > 1) emul::cluster_blocks_run() += cluster;
   }

@@ -3,8 +3,10 @@
 // out-of-bounds zero fill, mbarriers (arrive / expect_tx / complete_tx / parity wait),
 // tcgen05.alloc / mma kind::tf32 (K-major and MN-major shared-memory descriptors) / commit /
 // ld, TMEM, and thread-block clusters (rank, barrier, multicast TMA, multicast commit).
-// Everything completes immediately (no asynchrony, no timing); the point is to execute the
-// kernels' OWN control flow, pipeline protocol, descriptor arithmetic and indexing on the CPU.
+// The point is to execute the kernels' OWN control flow, pipeline protocol, descriptor arithmetic
+// and indexing on the CPU.  No timing; asynchrony is modelled (see `AsyncState` below): loads and
+// tensor-pipe work complete some scheduler sweeps after they are issued, in-flight TMA destinations
+// are poisoned, so missing waits and early slot releases produce wrong numbers.
 //
 // The model encodes this repository's understanding of the hardware (probed on the B200 with
 // tools/umma_probe*.cu, see profiles/README.md) and is CALIBRATED by the kernels that are proven
@@ -25,6 +27,10 @@
 #error "the tensor-core model needs the fiber execution model (no -DSG2IM_EMUL_THREADS)"
 #endif
 #include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <functional>
+#include <vector>
 
 #define __grid_constant__
 
@@ -74,8 +80,63 @@ inline void bar_complete_tx(Block* b, uint32_t va, long long bytes) {
   m.tx -= bytes;
   bar_check_complete(m);
 }
+// ---- asynchrony (SG2IM_EMUL_ASYNC=<sweeps>, default 3; 0 = everything completes at issue).
+// A TMA load poisons its destination with NaNs when it is ISSUED and delivers data + complete_tx a
+// few scheduler sweeps later (pseudo-random per load, so loads also complete out of order); MMAs and
+// commits go through an in-order queue per CTA and read their shared-memory operands when they
+// EXECUTE.  A consumer that does not wait for `full`, a producer that refills a slot before the
+// MMAs reading it have been committed (`empty`), an epilogue that reads TMEM before the commit —
+// all of them now compute with NaNs / stale data and fail the comparison instead of passing by luck
+// of the cooperative schedule.
+struct AsyncOp { unsigned long long ready; std::function<void()> fn; };
+struct AsyncState {
+  unsigned long long now = 0;
+  int delay = -1;
+  uint32_t lcg = 12345u;
+  std::vector<AsyncOp> tma;                            // complete individually, in any order
+  std::deque<AsyncOp> pipe[16];                        // tensor pipe of CTA `rank`: in order
+};
+inline AsyncState& async() { static AsyncState s; return s; }
+inline void async_tick() {
+  AsyncState& A = async();
+  ++A.now;
+  for (size_t i = 0; i < A.tma.size();) {
+    if (A.tma[i].ready <= A.now) { auto fn = std::move(A.tma[i].fn); A.tma.erase(A.tma.begin() + (long)i); fn(); }
+    else ++i;
+  }
+  for (auto& q : A.pipe)
+    while (!q.empty() && q.front().ready <= A.now) { auto fn = std::move(q.front().fn); q.pop_front(); fn(); }
+}
+inline void async_drain() {
+  AsyncState& A = async();
+  if (!A.tma.empty()) { std::fprintf(stderr, "emul: a CTA exited with a TMA load still in flight\n"); std::abort(); }
+  for (auto& q : A.pipe) { while (!q.empty()) { auto fn = std::move(q.front().fn); q.pop_front(); fn(); } }
+}
+inline int async_delay() {
+  AsyncState& A = async();
+  if (A.delay < 0) {
+    const char* e = std::getenv("SG2IM_EMUL_ASYNC");
+    A.delay = e ? std::atoi(e) : 3;
+    if (A.delay > 0) { sweep_hook() = &async_tick; drain_hook() = &async_drain; }
+  }
+  return A.delay;
+}
+inline unsigned long long async_when(int spread) {      // now + delay + pseudo-random 0..spread-1
+  AsyncState& A = async();
+  A.lcg = A.lcg * 1664525u + 1013904223u;
+  return A.now + (unsigned long long)A.delay + (spread > 1 ? (A.lcg >> 16) % (unsigned)spread : 0u);
+}
+inline void pipe_push(unsigned rank, std::function<void()> fn) {
+  if (async_delay() <= 0) { fn(); return; }
+  // adversarial schedule: SG2IM_EMUL_SLOW_PIPE=<sweeps> makes the tensor pipes of CTAs of rank >= 1 lag (a
+  // multicasting producer that does not collect every peer's release then overwrites operands in use)
+  const char* sp = std::getenv("SG2IM_EMUL_SLOW_PIPE");
+  const unsigned long long lag = (sp && rank >= 1) ? (unsigned long long)std::atoi(sp) : 0ull;
+  async().pipe[rank & 15].push_back(AsyncOp{async_when(1) + lag, std::move(fn)});
+}
+
 // copy one TMA box into CTA `b` at shared address dst_va (swizzled), signal its barrier
-inline void tma_box(Block* b, uint32_t dst_va, const TMap& t, uint32_t bar_va, const int* c) {
+inline void tma_box_now(Block* b, uint32_t dst_va, const TMap& t, uint32_t bar_va, const int* c, bool poison) {
   if (t.stride[0] != 4 || t.box[0] * 4 != 128) { std::fprintf(stderr, "emul: TMA box must be 32 floats wide\n"); std::abort(); }
   long long bytes = 0;
   const uint32_t b1 = t.rank > 1 ? t.box[1] : 1, b2 = t.rank > 2 ? t.box[2] : 1, b3 = t.rank > 3 ? t.box[3] : 1;
@@ -102,11 +163,27 @@ inline void tma_box(Block* b, uint32_t dst_va, const TMap& t, uint32_t bar_va, c
           a = t.swizzle == (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B ? swz128(a)
               : t.swizzle == (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B ? swz128_atom32(a) : a;
           if (a - SMEM_VA + 4 > b->smem_bytes) { std::fprintf(stderr, "emul: TMA write outside shared memory\n"); std::abort(); }
-          std::memcpy(host_of(b, a), &v, 4);
+          if (poison) { const uint32_t nan = 0x7fc0deadu; std::memcpy(host_of(b, a), &nan, 4); }
+          else std::memcpy(host_of(b, a), &v, 4);
           bytes += 4;
         }
       }
-  bar_complete_tx(b, bar_va, bytes);
+  if (!poison) bar_complete_tx(b, bar_va, bytes);
+}
+inline void tma_box(Block* b, uint32_t dst_va, const TMap& t, uint32_t bar_va, const int* c) {
+  if (async_delay() <= 0) { tma_box_now(b, dst_va, t, bar_va, c, false); return; }
+  tma_box_now(b, dst_va, t, bar_va, c, true);           // the destination is undefined from now on ...
+  const int c4[4] = {c[0], c[1], c[2], c[3]};
+  // loads into the higher-ranked CTAs of a cluster land later (SG2IM_EMUL_ASYNC_SKEW sweeps per rank,
+  // default 6): a CTA that consumes a peer's shared memory without having been told that the
+  // peer's load completed reads the poison
+  static const int skew = std::getenv("SG2IM_EMUL_ASYNC_SKEW") ? std::atoi(std::getenv("SG2IM_EMUL_ASYNC_SKEW")) : 6;
+  // adversarial schedules for cluster kernels (tests sweep them): SG2IM_EMUL_ASYNC_SLOW3D=<sweeps> delays
+  // the rank-3 tensor-map loads (the weight tiles) into CTAs of rank >= 1 further
+  const char* s3 = std::getenv("SG2IM_EMUL_ASYNC_SLOW3D");
+  const unsigned long long slow3d = (s3 && t.rank == 3 && b->rank >= 1) ? (unsigned long long)std::atoi(s3) : 0ull;
+  async().tma.push_back(AsyncOp{async_when(3) + (unsigned long long)(skew * (int)b->rank) + slow3d,
+                                [=]() { tma_box_now(b, dst_va, t, bar_va, c4, false); }});
 }
 }  // namespace emul
 
@@ -193,48 +270,55 @@ static inline void tc_alloc(uint32_t* slot, uint32_t ncols) {                // 
   *slot = 0;                                             // lane 0, column 0
 }
 static inline void tc_dealloc(uint32_t, uint32_t) {}
+// commits arrive once every MMA issued before them by this CTA has executed (in-order pipe)
 static inline void tc_commit(uint64_t* bar, uint32_t = 1u) {                 // converged warp, one arrive
-  if (emul_lane() == 0) emul::bar_arrive(emul::current(), smem_u32(bar));
+  if (emul_lane() != 0) return;
+  Block* b = emul::current();
+  const uint32_t bv = smem_u32(bar);
+  emul::pipe_push(b->rank, [=]() { emul::bar_arrive(b, bv); });
 }
 static inline void tc_commit_mc(uint64_t* bar, uint16_t mask) {
   if (emul_lane() != 0) return;
   emul::Gang* G = emul::gang();
   const uint32_t bv = smem_u32(bar);
-  for (unsigned r = 0; r < G->blocks.size(); ++r)
-    if (mask & (1u << r)) emul::bar_arrive(&G->blocks[r], bv);
+  emul::pipe_push(emul::current()->rank, [=]() {
+    for (unsigned r = 0; r < G->blocks.size(); ++r)
+      if (mask & (1u << r)) emul::bar_arrive(&G->blocks[r], bv);
+  });
 }
 
-// tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words
-static inline void tc_mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t) {
-  if (emul_lane() != 0) return;                           // elect.sync: one lane issues
-  Block* blk = emul::current();
+// one operand element through a shared-memory matrix descriptor, read from `blk`'s shared memory
+static inline float emul_desc_elem(Block* blk, uint32_t lo, uint32_t hi, bool mn_major, int idx, int k) {
+  const uint32_t start = (lo & 0x3fffu) << 4, lbo = ((lo >> 16) & 0x3fffu) << 4, sbo = (hi & 0x3fffu) << 4;
+  const uint32_t layout = (hi >> 29) & 7u;
+  uint32_t a;
+  if (!mn_major) {
+    if (layout != 2u) { std::fprintf(stderr, "emul: K-major operand must be SWIZZLE_128B\n"); std::abort(); }
+    a = emul::swz128(start + (uint32_t)(idx >> 3) * sbo + (uint32_t)(idx & 7) * 128u + (uint32_t)k * 4u);
+  } else {
+    if (layout != 1u) { std::fprintf(stderr, "emul: MN-major tf32 operand must be SWIZZLE_128B_BASE32B\n"); std::abort(); }
+    a = emul::swz128_atom32(start + (uint32_t)(idx >> 5) * lbo + (uint32_t)(k >> 2) * sbo +
+                            (uint32_t)(k & 3) * 128u + (uint32_t)(idx & 31) * 4u);
+  }
+  if (a < emul::SMEM_VA || a - emul::SMEM_VA + 4 > blk->smem_bytes) { std::fprintf(stderr, "emul: MMA operand read outside shared memory\n"); std::abort(); }
+  float v; std::memcpy(&v, emul::host_of(blk, a), 4);
+  return emul::tf32_trunc(v);
+}
+
+// tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words: what the tensor pipe does
+// when the instruction EXECUTES (operands are read from shared memory then, not at issue)
+static inline void emul_mma1(Block* blk, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
   const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
   if (M != 128 || N < 8 || N > 256 || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u) {
     std::fprintf(stderr, "emul: unsupported instruction descriptor %x\n", idesc); std::abort();
   }
-  auto elem = [&](uint32_t lo, uint32_t hi, bool mn_major, int idx, int k) -> float {
-    const uint32_t start = (lo & 0x3fffu) << 4, lbo = ((lo >> 16) & 0x3fffu) << 4, sbo = (hi & 0x3fffu) << 4;
-    const uint32_t layout = (hi >> 29) & 7u;
-    uint32_t a;
-    if (!mn_major) {
-      if (layout != 2u) { std::fprintf(stderr, "emul: K-major operand must be SWIZZLE_128B\n"); std::abort(); }
-      a = emul::swz128(start + (uint32_t)(idx >> 3) * sbo + (uint32_t)(idx & 7) * 128u + (uint32_t)k * 4u);
-    } else {
-      if (layout != 1u) { std::fprintf(stderr, "emul: MN-major tf32 operand must be SWIZZLE_128B_BASE32B\n"); std::abort(); }
-      a = emul::swz128_atom32(start + (uint32_t)(idx >> 5) * lbo + (uint32_t)(k >> 2) * sbo +
-                              (uint32_t)(k & 3) * 128u + (uint32_t)(idx & 31) * 4u);
-    }
-    if (a < emul::SMEM_VA || a - emul::SMEM_VA + 4 > blk->smem_bytes) { std::fprintf(stderr, "emul: MMA operand read outside shared memory\n"); std::abort(); }
-    float v; std::memcpy(&v, emul::host_of(blk, a), 4);
-    return emul::tf32_trunc(v);
-  };
   const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xffffu;
   if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emul: accumulator outside TMEM\n"); std::abort(); }
   float A[128][8], B[256][8];
-  for (int m = 0; m < M; ++m) for (int k = 0; k < 8; ++k) A[m][k] = elem(a_lo, a_hi, a_mn, m, k);
-  for (int n = 0; n < N; ++n) for (int k = 0; k < 8; ++k) B[n][k] = elem(b_lo, b_hi, b_mn, n, k);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < 8; ++k) A[m][k] = emul_desc_elem(blk, a_lo, a_hi, a_mn, m, k);
+  for (int n = 0; n < N; ++n) for (int k = 0; k < 8; ++k) B[n][k] = emul_desc_elem(blk, b_lo, b_hi, b_mn, n, k);
   for (int m = 0; m < M; ++m) {
     float* drow = &blk->tmem[(size_t)m * 512 + col0];
     for (int n = 0; n < N; ++n) {
@@ -244,12 +328,79 @@ static inline void tc_mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
     }
   }
 }
+
+// ---- CTA pair (cta_group::2).  ASSUMED semantics (CUTLASS's 2x1SM atoms; to be pinned on hardware
+// by tools/umma_2cta_probe.cu before any kernel built on them is trusted): M = 256, the SAME
+// descriptors are applied to both CTAs' shared memory; CTA r of the pair supplies rows
+// 128r..128r+127 of A and columns (N/2)r..(N/2)(r+1)-1 of B (its descriptor addresses an N/2-wide
+// tile); the accumulator rows 128r.. land in CTA r's TMEM at the same lane / column address.
+// Issued by the even-ranked CTA only.
+static inline void tc_mma_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t) {
+  if (emul_lane() != 0) return;                           // elect.sync: one lane issues
+  Block* blk = emul::current();
+  emul::pipe_push(blk->rank, [=]() { emul_mma1(blk, d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); });
+}
+static inline void emul_mma2(emul::Gang* G, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if (G->blocks.size() != 2) { std::fprintf(stderr, "emul: cta_group::2 MMA needs a cluster of 2, issued by rank 0\n"); std::abort(); }
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  if (M != 256 || N < 16 || N > 256 || (N & 15) || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u) {
+    std::fprintf(stderr, "emul: unsupported pair instruction descriptor %x\n", idesc); std::abort();
+  }
+  const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xffffu;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emul: accumulator outside TMEM\n"); std::abort(); }
+  static float B[256][8];
+  for (int n = 0; n < N; ++n) {
+    Block* src = &G->blocks[n < N / 2 ? 0 : 1];
+    for (int k = 0; k < 8; ++k) B[n][k] = emul_desc_elem(src, b_lo, b_hi, b_mn, n % (N / 2), k);
+  }
+  for (int r = 0; r < 2; ++r) {
+    Block* blk = &G->blocks[r];
+    if (blk->tmem.empty()) { std::fprintf(stderr, "emul: pair MMA before both CTAs allocated TMEM\n"); std::abort(); }
+    for (int m = 0; m < 128; ++m) {
+      float a[8];
+      for (int k = 0; k < 8; ++k) a[k] = emul_desc_elem(blk, a_lo, a_hi, a_mn, m, k);
+      float* drow = &blk->tmem[(size_t)m * 512 + col0];
+      for (int n = 0; n < N; ++n) {
+        float acc = accumulate ? drow[n] : 0.f;
+        for (int k = 0; k < 8; ++k) acc += a[k] * B[n][k];
+        drow[n] = acc;
+      }
+    }
+  }
+}
+static inline void tc_mma2_tf32_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                   uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if (emul_lane() != 0) return;
+  emul::Gang* G = emul::gang();
+  if (emul::current()->rank != 0) { std::fprintf(stderr, "emul: cta_group::2 MMA issued by rank 1\n"); std::abort(); }
+  emul::pipe_push(0, [=]() { emul_mma2(G, d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); });
+}
+static inline void tc_alloc2(uint32_t* slot, uint32_t ncols) { tc_alloc(slot, ncols); }   // warp 0 of both CTAs
+static inline void tc_dealloc2(uint32_t, uint32_t) {}
+static inline void tc_commit2_mc(uint64_t* bar, uint16_t mask) { tc_commit_mc(bar, mask); }
+// mbarrier.arrive on the barrier at this offset in CTA `rank` of the cluster (mapa + shared::cluster)
+static inline void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  emul::Gang* G = emul::gang();
+  if (rank >= G->blocks.size()) { std::fprintf(stderr, "emul: remote arrive outside the cluster\n"); std::abort(); }
+  emul::bar_arrive(&G->blocks[rank], smem_u32(bar));
+}
 static inline void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   tc_mma_tf32_lh(d_tmem, (uint32_t)adesc, (uint32_t)(adesc >> 32), (uint32_t)bdesc, (uint32_t)(bdesc >> 32), idesc, accumulate, 1u);
 }
 // tcgen05.ld.32x32b.x32: lane i of the warp reads TMEM lane (base + i), 32 consecutive columns
 static inline void tc_ld32(uint32_t taddr, float* v) {
   Block* b = emul::current();
+  // adversarial schedule: SG2IM_EMUL_SLOW_EPILOGUE=<sweeps> makes the epilogue warps of CTAs of rank >= 1
+  // lag (an MMA issuer that does not wait for a peer's epilogue then overwrites live accumulators)
+  if (b->rank >= 1 && emul::async_delay() > 0) {
+    static int lag = -1;
+    const char* e = std::getenv("SG2IM_EMUL_SLOW_EPILOGUE");
+    lag = e ? std::atoi(e) : 0;
+    for (int i = 0; i < lag; ++i) emul::yield();
+  }
   const uint32_t lane = (taddr >> 16) + emul_lane(), col = taddr & 0xffffu;
   if (lane >= 128 || col + 32 > 512 || (emul_warp() & 3u) != ((taddr >> 16) >> 5)) {
     std::fprintf(stderr, "emul: tcgen05.ld outside the warp's TMEM lane quadrant\n"); std::abort();

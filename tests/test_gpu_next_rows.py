@@ -673,3 +673,41 @@ def test_conv_from_weight_gradient_layout_matches_packed(N, H, W, Ci, Cf, Co, K,
     torch.cuda.synchronize()
   finally:
     ops.set_conv_math('fp32')
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co', [(32, 128, 128, 288, 64), (32, 128, 128, 64, 64), (32, 64, 64, 416, 128),
+                                         (3, 16, 24, 40, 96)])
+def test_cta_pair_halo_matches_single_cta(N, H, W, Ci, Co):
+  """conv_tc_halo_pair_kernel (SG2IM_HALO_PAIR=1: tcgen05 cta_group::2, two CTAs as one M = 256 tile that
+  share every weight tile) vs the validated single-CTA halo kernel: same products in the same order
+  => identical bits.  Forward on packed weights with fused statistics, forward and data gradient on
+  in-place weights.  Run tools/umma_2cta_probe.cu first: it pins the operand placement this kernel
+  assumes."""
+  from sg2im_b200 import ops
+  ops.set_conv_math('tf32')
+  try:
+    g = torch.Generator().manual_seed(Ci + Co)
+    x = torch.randn(N, H, W, Ci, generator=g).to(dev())
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * 0.05).to(dev())
+    gy = torch.randn(N, H, W, Co, generator=g).to(dev())
+    wt = ops.pack_tc_fwd(w)
+    kcc = w.permute(2, 3, 1, 0).contiguous()
+    ops.round_tf32(kcc, kcc)
+    outs = []
+    for pair in (False, True):
+      os.environ.pop('SG2IM_HALO_PAIR', None)
+      if pair:
+        os.environ['SG2IM_HALO_PAIR'] = '1'
+      try:
+        st = ops.new_stats(Co, x.device)
+        outs.append((ops.conv_tc(x, wt, None, 3, 3, 1, Co, stats=st).clone(), st.clone(),
+                     ops.conv_tc_kcc(x, kcc, Ci, False, None, 3, 3, 1, Co).clone(),
+                     ops.conv_tc_kcc(gy, kcc, Ci, True, None, 3, 3, 1, Ci).clone()))
+      finally:
+        os.environ.pop('SG2IM_HALO_PAIR', None)
+    torch.cuda.synchronize()
+    (y0, s0, f0, d0), (y1, s1, f1, d1) = outs
+    assert torch.equal(y0, y1) and torch.equal(f0, f1) and torch.equal(d0, d1)
+    assert torch.allclose(s0, s1, rtol=1e-6, atol=1e-4)       # atomics in another order
+  finally:
+    ops.set_conv_math('fp32')

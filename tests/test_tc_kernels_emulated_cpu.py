@@ -56,7 +56,8 @@ def _tf32(t):
 
 @pytest.fixture
 def env():
-  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL')
+  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL', 'SG2IM_HALO_PAIR',
+          'SG2IM_EMUL_ASYNC_SLOW3D', 'SG2IM_EMUL_SLOW_EPILOGUE', 'SG2IM_EMUL_SMS', 'SG2IM_EMUL_SLOW_PIPE')
   def set_(**kw):
     for k in keys:
       os.environ.pop(k, None)
@@ -290,3 +291,109 @@ def test_small_image_halo_kernel(lib, env, N, H, W, Ci, Co, K, P, kcc):
     assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kw), Ci, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
                                  0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
     assert rel_err(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-6
+
+
+PAIR_CASES = [  # N, H, W, Ci, Co, K, P
+    (1, 16, 16, 32, 64, 3, 1),      # 2 pixel tiles: one (half-padded) group per... one pair, rank 1 all padding
+    (2, 32, 16, 64, 64, 3, 1),      # 8 tiles = 2 groups = exactly one pair
+    (3, 16, 24, 40, 96, 3, 1),      # 9 tiles -> 3 groups (odd): last pair half padding; ragged channels, 2 Cout tiles
+    (5, 48, 8, 96, 128, 3, 1),      # several units per cluster (persistent loop), 2 weight sets in flight
+    (2, 17, 9, 32, 64, 2, 0),       # 2x2 taps, partial edge tiles
+]
+
+
+# adversarial schedules of the asynchronous model (tests/emul/tc_emul.h): the peer's weight loads land
+# late / the peer's epilogue lags, so a missing cross-CTA wait shows up as wrong numbers
+# (SG2IM_EMUL_SMS=2: one cluster runs every work unit, so accumulator sets and weight sets are reused)
+SCHEDULES = [{}, {'SG2IM_EMUL_ASYNC_SLOW3D': 60, 'SG2IM_EMUL_SMS': 2}, {'SG2IM_EMUL_SLOW_EPILOGUE': 40, 'SG2IM_EMUL_SMS': 2}]
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P', PAIR_CASES)
+@pytest.mark.parametrize('kcc', [False, True])
+@pytest.mark.parametrize('sched', SCHEDULES, ids=['plain', 'slow-weights', 'slow-epilogue'])
+def test_cta_pair_halo_kernel(lib, env, N, H, W, Ci, Co, K, P, kcc, sched):
+  """conv_tc_halo_pair_kernel (SG2IM_HALO_PAIR=1; not yet run on hardware): two CTAs as one M = 256
+  tile under the ASSUMED cta_group::2 semantics of the model (tools/umma_2cta_probe.cu pins them on
+  hardware): own pixel tiles and accumulators per CTA, half of every weight tile each, relay /
+  multicast-commit / remote-release protocol.  Same products in the same order as the single-CTA
+  halo kernel => identical bits."""
+  g = torch.Generator().manual_seed(Ci + Co + N + H)
+  T = K * K
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w = _tf32(torch.randn(Co, Ci, K, K, generator=g) * 0.1)
+  b = torch.randn(Co, generator=g)
+  Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+  wt = w.permute(2, 3, 0, 1).reshape(T, Co, Ci).contiguous()
+  kw = w.permute(2, 3, 1, 0).reshape(T, Ci, Co).contiguous()
+  lib.sg2im_conv_tc_kcc.argtypes = __import__('sg2im_b200._lib', fromlist=['x']).SIGNATURES['sg2im_conv_tc_kcc']
+
+  def run(pair):
+    env(**(dict(sched, SG2IM_HALO_PAIR=1) if pair else {}))
+    y = torch.full((N, Ho, Wo, Co + 4), 7.0)
+    stats = torch.zeros(2 * Co, dtype=torch.float64)
+    if kcc:
+      rc = lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kw), Ci, 0, _p(b), K, K, P, Ho, Wo, Co, 1, 0.2,
+                                 _p(y), Co + 4, 4, None, 1, None)      # fused LeakyReLU, RN-TF32 outputs
+    else:
+      rc = lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), _p(b), K, K, P, Ho, Wo, Co, 0, 0.0, _p(y),
+                             Co + 4, 4, _p(stats), 0, None)      # fused BatchNorm statistics
+    assert rc == 0, lib.emul_last_error()
+    return y, stats
+
+  y, stats = run(True)
+  y0, stats0 = run(False)
+  assert torch.equal(y, y0)
+  assert torch.allclose(stats, stats0, rtol=1e-6, atol=1e-5)      # smem / global atomics in another order
+  ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=P)
+  if kcc:
+    ref = F.leaky_relu(ref, 0.2)
+  assert rel_err(y[..., 4:], ref.permute(0, 2, 3, 1)) < (2e-3 if kcc else 2e-6)   # kcc case writes RN-TF32 outputs
+  assert bool((y[..., :4] == 7.0).all())
+  if kcc and K - 1 - P >= 0:
+    gy = _tf32(torch.randn(N, Ho, Wo, Co, generator=g))
+    outs = []
+    for pair in (True, False):
+      env(**(dict(sched, SG2IM_HALO_PAIR=1) if pair else {}))
+      dx = torch.empty(N, H, W, Ci)
+      assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kw), Ci, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
+                                   0.0, _p(dx), Ci, 0, None, 0, None) == 0, lib.emul_last_error()
+      outs.append(dx)
+    assert torch.equal(outs[0], outs[1])
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv2d(xr, w, None, padding=P).backward(gy.permute(0, 3, 1, 2))
+    assert rel_err(outs[0], xr.grad.permute(0, 2, 3, 1)) < 2e-6
+
+
+ADVERSARIAL = [{'SG2IM_EMUL_ASYNC_SLOW3D': 60}, {'SG2IM_EMUL_SLOW_EPILOGUE': 40}, {'SG2IM_EMUL_SLOW_PIPE': 25}]
+
+
+@pytest.mark.parametrize('sched', ADVERSARIAL, ids=['slow-weights', 'slow-epilogue', 'slow-peer-pipe'])
+def test_cluster_kernels_under_adversarial_schedules(lib, env, sched):
+  """The cluster-multicast kernels and the CTA-pair kernel once more with ONE cluster doing all the
+  work (SG2IM_EMUL_SMS: pipeline slots, accumulator sets and barrier phases are reused many times)
+  while the asynchronous model makes the peer CTAs' loads, tensor pipes or epilogues lag."""
+  # cluster weight gradient: clusters of 2 (co tiles x tap passes), 4 SMs -> 2 clusters
+  env(SG2IM_WGRAD_MC=1, SG2IM_EMUL_SMS=4, **sched)
+  dw, ref = _wgrad(lib, 4, 32, 16, 96, 64, 3)
+  assert rel_err(dw, ref) < 2e-6
+  # cluster forward: 4 Cout tiles of 64 -> one cluster of 4 runs every pixel tile
+  env(SG2IM_CONV_MC=1, SG2IM_TC_BN=64, SG2IM_EMUL_SMS=4, **sched)
+  g = torch.Generator().manual_seed(3)
+  N, H, W, Ci, Co = 20, 4, 4, 64, 256
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w = _tf32(torch.randn(Co, Ci, 3, 3, generator=g) * 0.1)
+  wt = w.permute(2, 3, 0, 1).reshape(9, Co, Ci).contiguous()
+  y = torch.empty(N, H, W, Co)
+  assert lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), None, 3, 3, 1, H, W, Co, 0, 0.0, _p(y), Co, 0,
+                           None, 0, None) == 0, lib.emul_last_error()
+  assert rel_err(y, F.conv2d(x.permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1)) < 2e-6
+  # CTA pair: one pair runs 6 work units
+  env(SG2IM_HALO_PAIR=1, SG2IM_EMUL_SMS=2, **sched)
+  N, H, W, Ci, Co = 6, 32, 16, 64, 128
+  x = _tf32(torch.randn(N, H, W, Ci, generator=g))
+  w = _tf32(torch.randn(Co, Ci, 3, 3, generator=g) * 0.1)
+  wt = w.permute(2, 3, 0, 1).reshape(9, Co, Ci).contiguous()
+  y = torch.empty(N, H, W, Co)
+  assert lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), None, 3, 3, 1, H, W, Co, 0, 0.0, _p(y), Co, 0,
+                           None, 0, None) == 0, lib.emul_last_error()
+  assert rel_err(y, F.conv2d(x.permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1)) < 2e-6

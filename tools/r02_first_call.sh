@@ -25,6 +25,7 @@ group kcc 300 "conv_from_weight_gradient_layout"
 group wgradmc 300 "wgrad_cluster_multicast"
 group convmc 300 "conv_cluster_multicast"
 group halosmall 300 "small_image_halo"
+group halopair 300 "cta_pair_halo"
 group steps 600 "train_step_with"
 grep -E "^exit|passed|failed" $LOG
 echo "== tcgen05 issue-rate probe" >> $LOG
@@ -53,6 +54,8 @@ echo "== bench forward cluster multicast" >> gpurun_out/r02_first.log
 [ "$RC_convmc" = 0 ] && SG2IM_CONV_MC=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_convmc.json 2>> gpurun_out/r02_first.log
 echo "== bench small-image halo kernel (8-row maps)" >> gpurun_out/r02_first.log
 [ "$RC_halosmall" = 0 ] && SG2IM_HALO_SMALL=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halosmall.json 2>> gpurun_out/r02_first.log
+echo "== bench CTA-pair halo kernel (cta_group::2)" >> gpurun_out/r02_first.log
+[ "$RC_halopair" = 0 ] && SG2IM_HALO_PAIR=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halopair.json 2>> gpurun_out/r02_first.log
 echo "== bench pack-both" >> gpurun_out/r02_first.log
 SG2IM_PACK_BOTH=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_packboth.json 2>> gpurun_out/r02_first.log
 echo "== bench weights in the gradient layout (no pack / unpack)" >> gpurun_out/r02_first.log
@@ -65,6 +68,7 @@ ALL="SG2IM_PACK_BOTH=1"
 [ "$RC_simt" = 0 ] && ALL="$ALL SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 SG2IM_LAYOUT_V2=1 SG2IM_COLSUM_V2=1 SG2IM_ACTBWD_FUSED=1"
 [ "$RC_wgradmc" = 0 ] && ALL="$ALL SG2IM_WGRAD_MC=1"
 [ "$RC_halosmall" = 0 ] && ALL="$ALL SG2IM_HALO_SMALL=1"
+[ "$RC_halopair" = 0 ] && ALL="$ALL SG2IM_HALO_PAIR=1"
 ARGS="--adam flat"
 [ "$RC_kcc" = 0 ] && [ "$RC_steps" = 0 ] && ARGS="$ARGS --weights kcc"
 echo "all: $ALL $ARGS" >> gpurun_out/r02_first.log

@@ -57,11 +57,11 @@ def main():
   args = ap.parse_args()
   dev = torch.device('cuda:0')
   ops.set_conv_math('tf32')
-  # (name, SG2IM_TC_BN, SG2IM_NO_HALO, SG2IM_CONV_MC); 'small' = SG2IM_HALO_SMALL (8-row maps only)
+  # (name, SG2IM_TC_BN, SG2IM_NO_HALO, SG2IM_CONV_MC); 'small' = SG2IM_HALO_SMALL (8-row maps only), 'pair' = SG2IM_HALO_PAIR (halo shapes only)
   variants = [('auto', None, False, False), ('bn64', '64', False, False), ('bn128', '128', False, False),
               ('bn256', '256', False, False), ('nohalo', None, True, False), ('nohalo128', '128', True, False),
               ('mc', None, True, True), ('mc64', '64', True, True), ('mc128', '128', True, True),
-              ('mc256', '256', True, True), ('small', 'small', False, False)]
+              ('mc256', '256', True, True), ('small', 'small', False, False), ('pair', 'pair', False, False)]
   results = []
   for (N, H, W, Ci, Co, K, S), ref_ms in shapes()[:args.top]:
     torch.manual_seed(0)
@@ -75,8 +75,11 @@ def main():
       for k in ('SG2IM_TC_BN', 'SG2IM_NO_HALO', 'SG2IM_CONV_MC'):
         os.environ.pop(k, None)
       os.environ.pop('SG2IM_HALO_SMALL', None)
+      os.environ.pop('SG2IM_HALO_PAIR', None)
       if bn == 'small':
         os.environ['SG2IM_HALO_SMALL'] = '1'
+      elif bn == 'pair':
+        os.environ['SG2IM_HALO_PAIR'] = '1'
       elif bn:
         os.environ['SG2IM_TC_BN'] = bn
       if nohalo:
@@ -85,7 +88,7 @@ def main():
         os.environ['SG2IM_CONV_MC'] = '1'
       us = time_one(x, w, K, P, Co, out_hw)
       row[name] = {'us': us, 'tflops': flops / us / 1e6}
-    for k in ('SG2IM_TC_BN', 'SG2IM_NO_HALO', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL'):
+    for k in ('SG2IM_TC_BN', 'SG2IM_NO_HALO', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL', 'SG2IM_HALO_PAIR'):
       os.environ.pop(k, None)
     best = min(variants, key=lambda v: row[v[0]]['us'])[0]
     row['best'] = best
