@@ -1127,6 +1127,7 @@ int launch_halo_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloP
   const int units = ((h.groups + 1) / 2) * h.n_tiles;
 #ifdef SG2IM_EMUL
   int nclusters = units < num_sms() / 2 ? units : num_sms() / 2;
+  if (nclusters < 1) nclusters = 1;
   emul_launch_cluster(2, dim3((unsigned)(nclusters * 2)), dim3(H_THREADS), (size_t)H2_SMEM,
                       [=]() { conv_tc_halo_pair_kernel<WMODE>(tmA, tmB, h); });
   (void)st;
@@ -1173,6 +1174,7 @@ int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
   const int units = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles / CS;
 #ifdef SG2IM_EMUL
   int nclusters = units < num_sms() / CS ? units : num_sms() / CS;
+  if (nclusters < 1) nclusters = 1;
   emul_launch_cluster(CS, dim3((unsigned)(nclusters * CS)), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES,
                       [=]() { conv_tc_mc_kernel<BN, WMODE, CS>(tmA, tmB, p); });
   (void)st;

@@ -236,6 +236,7 @@ int launch_mc(const CUtensorMap& tmX, const CUtensorMap& tmDY, const McParams& p
 #ifdef SG2IM_EMUL
   int max_clusters = num_sms() / CS;
   int nclusters = items < max_clusters ? items : max_clusters;
+  if (nclusters < 1) nclusters = 1;
   emul_launch_cluster(CS, dim3((unsigned)(nclusters * CS)), dim3(MC_THREADS), (size_t)C::SMEM_BYTES,
                       [=]() { conv_wgrad_tc_mc_kernel<BN, CS>(tmX, tmDY, p); });
   (void)st;

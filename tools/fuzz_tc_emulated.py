@@ -16,7 +16,8 @@ import torch.nn.functional as F  # noqa: E402
 from emul_device import build_lib  # noqa: E402
 from sg2im_b200._lib import SIGNATURES  # noqa: E402
 
-KEYS = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL')
+KEYS = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_WGRAD_MC', 'SG2IM_CONV_MC', 'SG2IM_HALO_SMALL', 'SG2IM_HALO_PAIR',
+        'SG2IM_EMUL_SMS', 'SG2IM_EMUL_ASYNC_SLOW3D', 'SG2IM_EMUL_SLOW_EPILOGUE', 'SG2IM_EMUL_SLOW_PIPE')
 
 
 def tf32(t):
@@ -57,6 +58,16 @@ def main():
       env['SG2IM_HALO_SMALL'] = '1'
       if K > 1:
         H, N = rng.randint(5, 8) + K - 1 - 2 * P, rng.randint(2, 7)
+    if rng.random() < 0.4:                                 # CTA pairs (halo shapes: >= 16 rows, >= 8 columns)
+      env['SG2IM_HALO_PAIR'] = '1'
+      if K > 1 and rng.random() < 0.7:
+        H, W = rng.randint(16, 40) + K - 1 - 2 * P, rng.randint(8, 20) + K - 1 - 2 * P
+    if rng.random() < 0.5:                                 # few SMs: persistent loops iterate; adversarial schedules
+      env['SG2IM_EMUL_SMS'] = rng.choice(['2', '4', '8'])
+      r = rng.random()
+      if r < 0.25: env['SG2IM_EMUL_ASYNC_SLOW3D'] = '60'
+      elif r < 0.5: env['SG2IM_EMUL_SLOW_EPILOGUE'] = '40'
+      elif r < 0.75: env['SG2IM_EMUL_SLOW_PIPE'] = '25'
     for k in KEYS:
       os.environ.pop(k, None)
     os.environ.update(env)
