@@ -68,6 +68,32 @@ def model_kwargs(cfg):
 D_ARCH = 'C4-64-2,C4-128-2,C4-256-2'
 
 
+def hbm_table(entries, steps, peak_gbs, step_ms):
+  """Per entry point: algorithmic bytes / summed CUDA-event time of its launches in `steps` eager
+  steps -> achieved GB/s and fraction of the measured HBM copy bandwidth.  Small launches are
+  latency-bound (a few microseconds whatever the bytes): `us_per_launch` says which rows those are."""
+  fam = {}
+  for name, nbytes, a, b in entries:
+    f = fam.setdefault(name.replace('sg2im_', ''), [0.0, 0.0, 0])
+    f[0] += nbytes; f[1] += a.elapsed_time(b); f[2] += 1
+  rows = {}
+  for k, (nb, t_ms, n) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+    gbs = nb / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+    rows[k] = {'gbs': round(gbs, 1), 'frac': round(gbs / peak_gbs, 4),
+               'ms_per_step': round(t_ms / steps, 4), 'mb_per_step': round(nb / steps / 1e6, 2),
+               'launches_per_step': n / steps, 'us_per_launch': round(1e3 * t_ms / max(n, 1), 2)}
+  tot_ms = sum(v[1] for v in fam.values()) / steps
+  tot_b = sum(v[0] for v in fam.values()) / steps
+  return {'unit': 'GB/s', 'peak': peak_gbs, 'bound': 'hbm',
+          'achieved': round(tot_b / (tot_ms * 1e-3) / 1e9, 1) if tot_ms > 0 else 0.0,
+          'frac': round(tot_b / (tot_ms * 1e-3) / 1e9 / peak_gbs, 4) if tot_ms > 0 else 0.0,
+          'ms_per_step': round(tot_ms, 4), 'share_of_step': round(tot_ms / step_ms, 4),
+          'by_kernel': rows,
+          'note': 'algorithmic bytes (each operand read or written once) / CUDA-event time of the '
+                  'launches in an eager step after the timed region; frac against the measured copy '
+                  'bandwidth'}
+
+
 def peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -243,15 +269,16 @@ def run_b200(args, cfg):
       dist.barrier()
       torch.cuda.synchronize()
 
-  def timed(n_steps, from_host, profile=None):
+  def timed(n_steps, from_host, profile=None, profile_hbm=None):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.PROFILE = profile
+    ops.PROFILE_HBM = profile_hbm
     l0, r0 = _lib.launches, step.replays
     e0.record()
     last = None
     for i in range(n_steps):
-      if profile is not None:                            # per-kernel events need eager launches
+      if profile is not None or profile_hbm is not None:  # per-kernel events need eager launches
         last, _ = step._step_eager(resident[i % n_pool])
       elif from_host and step.cuda_graph:
         last, _ = step.step(host[i % n_pool])            # H2D into the graph's static inputs
@@ -262,6 +289,7 @@ def run_b200(args, cfg):
     e1.record()
     sync_all()
     ops.PROFILE = None
+    ops.PROFILE_HBM = None
     ms = e0.elapsed_time(e1)
     n_launch = (_lib.launches - l0) + (step.replays - r0) * step.launches_per_replay
     if world > 1:
@@ -322,6 +350,20 @@ def run_b200(args, cfg):
                     'step launched eagerly right after the timed (graph-replayed) region; traffic: '
                     'see profiles/ (ncu --set full per kernel)'}
 
+  # ---- the HBM-bound kernels (graph gather / pooling, layout warp, crops, normalise / activate
+  # passes, layout conversions): the same eager step once more with THOSE launches bracketed by
+  # events; algorithmic bytes (every operand once) / event time, against the measured copy
+  # bandwidth.  Last GPU work of the run and single-process only: it cannot disturb a number above.
+  hbm = None
+  if world == 1:
+    try:
+      hprof = []
+      timed(prof_steps, False, profile_hbm=hprof)
+      hbm = hbm_table(hprof, prof_steps, pk['hbm'], ms / args.steps)
+    except Exception as e:                               # instrumentation only: never fail the run
+      ops.PROFILE_HBM = None
+      hbm = {'error': repr(e)[:200]}
+
   if args.shapes_out and rank == 0:
     rows = [{'kernel': k[0], 'shape(N,H,W,Cin,Cout,K,S)': list(k[1:]), 'ms_per_step': v[1] / prof_steps,
              'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'launches_per_step': v[2] / prof_steps}
@@ -351,6 +393,7 @@ def run_b200(args, cfg):
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
                          'no explicit flush'},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
+        'hbm_kernels': hbm,
         'cpu_baseline': cpu, 'last_losses': last,
     }
     print(json.dumps(line), flush=True)

@@ -61,6 +61,27 @@ class _prof(object):
       PROFILE.append((self.name, self.flops, self.a, self.b, self.shape))
 
 
+# bench.py sets PROFILE_HBM to a list to time the HBM-bound kernels (graph gather / pooling,
+# layout warp, crops, normalise / activate passes, layout conversions) the same way: entries
+# (entry point, ALGORITHMIC bytes of the launch — every operand read or written once —, start, end)
+PROFILE_HBM = None
+
+
+def _event():
+  return torch.cuda.Event(enable_timing=True)
+
+
+def _call_b(nbytes, name, *args):
+  """_call, bracketed by CUDA events on the launching stream while bench.py profiles."""
+  if PROFILE_HBM is None:
+    return _call(name, *args)
+  a, b = _event(), _event()
+  a.record()
+  _call(name, *args)
+  b.record()
+  PROFILE_HBM.append((name, float(nbytes), a, b))
+
+
 # --------------------------------------------------------------------------
 # raw kernel wrappers (no autograd)
 # --------------------------------------------------------------------------
@@ -86,8 +107,9 @@ def triple_gather(rows, mid, edges, Wm, row_ptr=None):
   if mid is not None:
     mid = _chk(mid).contiguous()
   out = torch.empty(T, 2 * Wr + Wm, dtype=torch.float32, device=rows.device)
-  _call('sg2im_triple_gather', _p(rows), _p(mid), _p(edges), T, Wr, Wm, _p(row_ptr), _p(out),
-        _stream())
+  _call_b(8 * T * (2 * Wr + Wm) + 16 * T,
+          'sg2im_triple_gather', _p(rows), _p(mid), _p(edges), T, Wr, Wm, _p(row_ptr), _p(out),
+          _stream())
   _count()
   return out
 
@@ -95,8 +117,9 @@ def triple_gather(rows, mid, edges, Wm, row_ptr=None):
 def segment_sum(src, off0, off1, W, row_ptr, entries, num_rows, avg):
   src = _chk(src).contiguous()
   out = torch.empty(num_rows, W, dtype=torch.float32, device=src.device)
-  _call('sg2im_segment_sum', _p(src), src.size(1), off0, off1, W, _p(row_ptr), _p(entries),
-        num_rows, int(avg), _p(out), _stream())
+  _call_b(4 * W * (entries.numel() + num_rows) + 4 * entries.numel(),
+          'sg2im_segment_sum', _p(src), src.size(1), off0, off1, W, _p(row_ptr), _p(entries),
+          num_rows, int(avg), _p(out), _stream())
   _count()
   return out
 
@@ -194,8 +217,9 @@ def _pack(weight, cin_use, want_fwd, want_dgrad=None):
   dev = weight.device
   f = torch.empty((T, Co, cu), dtype=torch.float32, device=dev) if want_fwd else None
   d = torch.empty((T, cu, Co), dtype=torch.float32, device=dev) if want_dgrad else None
-  _call('sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(f), _p(d), 1,
-        _stream())                                        # RN-TF32: the tensor core would truncate
+  _call_b(4 * T * Co * cu * (1 + int(want_fwd) + int(want_dgrad)),
+          'sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(f), _p(d), 1,
+          _stream())                                        # RN-TF32: the tensor core would truncate
   _count()
   if want_fwd and want_dgrad:
     return f, d
@@ -224,7 +248,8 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   cin_use get zero)."""
   Co, Ci, KH, KW = wshape
   grad = (torch.zeros if cin_use != Ci else torch.empty)(wshape, dtype=torch.float32, device=dw.device)
-  _call('sg2im_unpack_wgrad', _p(dw), Co, Ci, cin_use, KH * KW, _p(grad), 0, _stream())
+  _call_b(4 * (dw.numel() + grad.numel()),
+          'sg2im_unpack_wgrad', _p(dw), Co, Ci, cin_use, KH * KW, _p(grad), 0, _stream())
   _count()
   return grad
 
@@ -274,7 +299,8 @@ def colsum(x2d):
 def act_bwd(dy, y, slope):
   dy = _chk(dy).contiguous()
   dx = torch.empty_like(dy)
-  _call('sg2im_act_bwd', _p(dy), _p(y), float(slope), dy.numel(), _p(dx), _stream())
+  _call_b(12 * dy.numel(),
+          'sg2im_act_bwd', _p(dy), _p(y), float(slope), dy.numel(), _p(dx), _stream())
   _count()
   return dx
 
@@ -315,7 +341,7 @@ def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum
   save = torch.empty(2 * C, dtype=torch.float32, device=dev)
   if training and sums is None:
     sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
-    _call('sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
+    _call_b(4 * M * C, 'sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
     _count()
   _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, _p(gamma), _p(beta), float(eps),
         float(momentum), int(training), _p(running_mean), _p(running_var), _p(scale), _p(shift),
@@ -328,8 +354,9 @@ def scale_act_fwd(x, scale, shift, slope, up, out=None, out_coff=0):
   N, H, W, C = x.shape
   if out is None:
     out = torch.empty(N, H * up, W * up, C, dtype=torch.float32, device=x.device)
-  _call('sg2im_scale_act_fwd', _p(x), N, H, W, C, _p(scale), _p(shift), float(slope), up,
-        _p(out), out.size(3), out_coff, int(CONV_MATH == 'tf32'), _stream())
+  _call_b(4 * x.numel() * (1 + up * up),
+          'sg2im_scale_act_fwd', _p(x), N, H, W, C, _p(scale), _p(shift), float(slope), up,
+          _p(out), out.size(3), out_coff, int(CONV_MATH == 'tf32'), _stream())
   _count()
   return out
 
@@ -343,32 +370,36 @@ def scale_act_bwd(dy, dy_coff, x, scale, shift, save, slope, up, training, want_
   need_sums = (training and save is not None) or want_param_grads
   if need_sums:
     sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
-    _call('sg2im_scale_act_bwd_reduce', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C,
-          _p(scale), _p(shift), _p(save), float(slope), up, _p(sums), _stream())
+    _call_b(4 * x.numel() * (1 + up * up),
+            'sg2im_scale_act_bwd_reduce', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C,
+            _p(scale), _p(shift), _p(save), float(slope), up, _p(sums), _stream())
     _count()
   dx = torch.empty_like(x)
   dgamma = dbeta = None
   if want_param_grads:
     dgamma = torch.empty(C, dtype=torch.float32, device=dev)
     dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-  _call('sg2im_scale_act_bwd_apply', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C, _p(scale),
-        _p(shift), _p(save), float(slope), up, int(training), _p(sums), _p(dx), _p(dgamma),
-        _p(dbeta), _stream())
+  _call_b(4 * x.numel() * (2 + up * up),
+          'sg2im_scale_act_bwd_apply', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C, _p(scale),
+          _p(shift), _p(save), float(slope), up, int(training), _p(sums), _p(dx), _p(dgamma),
+          _p(dbeta), _stream())
   _count(2 if want_param_grads else 1)
   return dx, dgamma, dbeta
 
 
 def avgpool2_fwd(x, x_coff, C, out, out_coff):
   N, H, W, _ = x.shape
-  _call('sg2im_avgpool2_fwd', _p(x), x.size(3), x_coff, N, H, W, C, _p(out), out.size(3),
-        out_coff, _stream())
+  _call_b(5 * N * H * W * C,
+          'sg2im_avgpool2_fwd', _p(x), x.size(3), x_coff, N, H, W, C, _p(out), out.size(3),
+          out_coff, _stream())
   _count()
 
 
 def avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
   N, H, W, _ = dfine.shape
-  _call('sg2im_avgpool2_bwd', _p(dcoarse), dcoarse.size(3), dc_coff, N, H, W, C, _p(dfine),
-        dfine.size(3), df_coff, int(accumulate), _stream())
+  _call_b((9 if accumulate else 5) * N * H * W * C,
+          'sg2im_avgpool2_bwd', _p(dcoarse), dcoarse.size(3), dc_coff, N, H, W, C, _p(dfine),
+          dfine.size(3), df_coff, int(accumulate), _stream())
   _count()
 
 
@@ -451,7 +482,7 @@ class Conv(torch.autograd.Function):
                      act, slope)
     if stats_out is not None and not fused_stats:
       # per-channel sum / sum of squares of the output for the BatchNorm that follows
-      _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
+      _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
     ctx.w_dgrad = w_dgrad                       # packed in the forward pass (PACK_BOTH) or None
@@ -551,7 +582,7 @@ class ConvKCC(torch.autograd.Function):
     y = conv_tc_kcc(x, w_read, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
                     stats_out if fused_stats else None, round_out)
     if stats_out is not None and not fused_stats:
-      _call('sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
+      _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
     ctx.save_for_backward(x, w_read, y if act else None)
@@ -615,7 +646,8 @@ class S2D(torch.autograd.Function):
     N, H, W, C = x.shape
     out = torch.empty(N, (H + 1) // 2, (W + 1) // 2, 4 * C, dtype=torch.float32, device=x.device)
     sn, sh, sw, sc = x.stride()
-    _call('sg2im_s2d_fwd', _p(x), sn, sh, sw, sc, N, H, W, C, _p(out), _stream())
+    _call_b(4 * (x.numel() + out.numel()),
+            'sg2im_s2d_fwd', _p(x), sn, sh, sw, sc, N, H, W, C, _p(out), _stream())
     _count()
     ctx.shape = (N, H, W, C)
     return out
@@ -625,7 +657,8 @@ class S2D(torch.autograd.Function):
     N, H, W, C = ctx.shape
     dout = dout.contiguous()
     dx = torch.empty(N, H, W, C, dtype=torch.float32, device=dout.device)
-    _call('sg2im_s2d_bwd', _p(dout), N, H, W, C, _p(dx), _stream())
+    _call_b(4 * (dx.numel() + dout.numel()),
+            'sg2im_s2d_bwd', _p(dout), N, H, W, C, _p(dx), _stream())
     _count()
     return dx
 
@@ -846,8 +879,9 @@ class Layout(torch.autograd.Function):
     dmasks = None
     if masks is not None and ctx.needs_input_grad[2]:
       dmasks = torch.zeros_like(masks)
-    _call('sg2im_layout_bwd', _p(dout), dout.size(3), _p(vecs), _p(boxes), _p(masks), M,
-          _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
+    _call_b(4 * N * H * W * D + 8 * O * D,
+            'sg2im_layout_bwd', _p(dout), dout.size(3), _p(vecs), _p(boxes), _p(masks), M,
+            _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
     _count()
     return dvecs, None, dmasks, None, None, None, None, None, None
 
@@ -859,9 +893,10 @@ def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners
   img_ptr, img_ent = csr_build(obj_to_img, 1, N)
   nc = 0 if noise is None else noise.size(1)
   ns = (0, 0, 0, 0) if noise is None else noise.stride()      # (n, c, h, w)
-  _call('sg2im_layout_fwd', _p(vecs), _p(boxes), _p(masks), M, _p(img_ptr), _p(img_ent), N, O,
-        D, H, W, int(align_corners), _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
-        out.size(3), int(round_tf32), _stream())
+  _call_b(4 * N * H * W * (out.size(3) + nc) + 4 * O * D,
+          'sg2im_layout_fwd', _p(vecs), _p(boxes), _p(masks), M, _p(img_ptr), _p(img_ent), N, O,
+          D, H, W, int(align_corners), _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
+          out.size(3), int(round_tf32), _stream())
   _count()
 
 
@@ -919,8 +954,9 @@ class LayoutStack(torch.autograd.Function):
     dmasks = None
     if masks is not None and ctx.needs_input_grad[2]:
       dmasks = torch.zeros_like(masks)
-    _call('sg2im_layout_bwd', _p(g[L - 1]), g[L - 1].size(3), _p(vecs), _p(boxes), _p(masks), M,
-          _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
+    _call_b(4 * N * H * W * D + 8 * O * D,
+            'sg2im_layout_bwd', _p(g[L - 1]), g[L - 1].size(3), _p(vecs), _p(boxes), _p(masks), M,
+            _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
     _count()
     return dvecs, None, dmasks, None, None, None, None, None, None, None
 
@@ -938,8 +974,9 @@ class Crop(torch.autograd.Function):
     B = boxes.size(0)
     out = torch.empty(B, HH, WW, C, dtype=torch.float32, device=feats.device)
     sn, sh, sw, sc = feats.stride()
-    _call('sg2im_crop_fwd', _p(feats), sn, sh, sw, sc, N, H, W, C, _p(boxes), _p(idx), B, HH, WW,
-          int(align_corners), _p(out), _stream())
+    _call_b(4 * (N * H * W * C + out.numel()),
+            'sg2im_crop_fwd', _p(feats), sn, sh, sw, sc, N, H, W, C, _p(boxes), _p(idx), B, HH, WW,
+            int(align_corners), _p(out), _stream())
     _count()
     ctx.save_for_backward(boxes, idx)
     ctx.cfg = (N, H, W, C, HH, WW, align_corners)
@@ -951,7 +988,8 @@ class Crop(torch.autograd.Function):
     N, H, W, C, HH, WW, align = ctx.cfg
     dout = dout.contiguous()
     dfeats = torch.zeros(N, H, W, C, dtype=torch.float32, device=dout.device)
-    _call('sg2im_crop_bwd', _p(dout), _p(boxes), _p(idx), N, H, W, C, boxes.size(0), HH, WW,
-          int(align), _p(dfeats), _stream())
+    _call_b(4 * (dfeats.numel() + dout.numel()),
+            'sg2im_crop_bwd', _p(dout), _p(boxes), _p(idx), N, H, W, C, boxes.size(0), HH, WW,
+            int(align), _p(dfeats), _stream())
     _count()
     return dfeats, None, None, None, None, None

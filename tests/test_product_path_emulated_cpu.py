@@ -254,3 +254,50 @@ def test_fused_activation_backward_and_direct_bias_gradients(emul):
       assert (sd1[k] - v).abs().max() < 1e-5, k
   assert c1.count('sg2im_act_bwd_colsum') > 0 and c1.count('sg2im_act_bwd') < c0.count('sg2im_act_bwd')
   assert c1.count('sg2im_colsum') < c0.count('sg2im_colsum')
+
+
+class _FakeEvent(object):
+  """Stands in for torch.cuda.Event while bench.py's per-kernel profiling hooks run on the CPU."""
+  clock = [0.0]
+
+  def record(self):
+    _FakeEvent.clock[0] += 0.001
+    self.t = _FakeEvent.clock[0]
+
+  def elapsed_time(self, other):
+    return other.t - self.t
+
+
+def test_hbm_kernel_profiling_hooks_of_the_benchmark(emul, monkeypatch):
+  """bench.py's `hbm_kernels` table: every HBM-bound entry point is launched through ops._call_b
+  with its algorithmic byte count.  Run the reference's training iterations (on the tensor-core
+  host build where it exists: adds space-to-depth and weight packing) with the hooks
+  ON and the CUDA events stubbed: every byte expression evaluates, results are unchanged (the test
+  bodies still compare against the reference), and bench.hbm_table digests the entries."""
+  import sys
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  import bench
+  from sg2im_b200 import ops
+  monkeypatch.setattr(ops, '_event', _FakeEvent)
+  entries = []
+  monkeypatch.setattr(ops, 'PROFILE_HBM', entries)
+  if HAVE_TC:
+    G.test_training_iteration_tf32_tensor_core_path()
+    O.test_conv_stride2_space_to_depth_route(*O.S2_CASES[0])
+  else:
+    G.test_two_training_iterations_match_reference()
+  monkeypatch.setattr(ops, 'PROFILE_HBM', None)
+  seen = {e[0] for e in entries}
+  want = {'sg2im_triple_gather', 'sg2im_segment_sum', 'sg2im_layout_fwd', 'sg2im_layout_bwd',
+          'sg2im_crop_fwd', 'sg2im_crop_bwd', 'sg2im_scale_act_fwd', 'sg2im_scale_act_bwd_reduce',
+          'sg2im_scale_act_bwd_apply', 'sg2im_bn_stats', 'sg2im_act_bwd', 'sg2im_avgpool2_fwd',
+          'sg2im_avgpool2_bwd'}
+  if HAVE_TC:
+    want |= {'sg2im_s2d_fwd', 'sg2im_s2d_bwd', 'sg2im_pack_weights', 'sg2im_unpack_wgrad'}
+  assert want <= seen, sorted(want - seen)
+  assert all(nbytes > 0 for _, nbytes, _, _ in entries)
+  tab = bench.hbm_table(entries, 2, 6572.9, 10.0)
+  assert tab['bound'] == 'hbm' and set(tab['by_kernel']) == {s.replace('sg2im_', '') for s in seen}
+  assert all(r['gbs'] > 0 and r['launches_per_step'] > 0 for r in tab['by_kernel'].values())
+  import json
+  json.dumps(tab)
