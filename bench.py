@@ -343,6 +343,11 @@ def run_b200(args, cfg):
             'by_kernel': {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12, 'ms_per_step': v[1] / prof_steps,
                               'launches_per_step': v[2] / prof_steps} for k, v in fam.items()},
             'top': top[0], 'math': ops.CONV_MATH,
+            # the dozen most expensive (kernel, shape) rows of the step: (N,H,W,Cin,Cout,K,S)
+            'by_shape': [{'kernel': k[0], 'shape': list(k[1:]), 'ms_per_step': round(v[1] / prof_steps, 4),
+                          'tflops': round(v[0] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else 0.0,
+                          'launches_per_step': v[2] / prof_steps}
+                         for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:12]],
             # the path multiplies in TF32, whose tensor-pipe rate is half the bf16 rate the
             # measured peak was taken at: fraction against that halved figure as well
             'peak_tf32_est': pk['tf'] / 2.0, 'frac_of_tf32_est': ach / (pk['tf'] / 2.0),
