@@ -238,6 +238,17 @@ int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int64_t dc_coff
                        float* dfine, int64_t df_cstride, int64_t df_coff, int accumulate,
                        sg2im_stream_t stream);
 
+/* Non-overlapping pooling, NHWC contiguous: nn.MaxPool2d / nn.AvgPool2d(kernel_size = stride =
+ * factor) as built by build_cnn's 'PX' token (sg2im/layers.py:195-201).  mode 0 = average,
+ * 1 = max (ties: first element in row-major window order, like ATen).  y is
+ * (N, H/factor, W/factor, C) (floor: trailing rows / columns are dropped); the backward writes
+ * every element of the covered region of dx (N,H,W,C) — the caller zeroes dx when H or W is not a
+ * multiple of factor.  x is read only for mode 1 (arg-max re-derived). */
+int sg2im_pool2d_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C, int factor,
+                     int mode, float* y, sg2im_stream_t stream);
+int sg2im_pool2d_bwd(const float* dy, const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
+                     int factor, int mode, float* dx, sg2im_stream_t stream);
+
 /* --------------------------------------------------------------- layout --
  * Fused masks_to_layout / boxes_to_layout (sg2im/layout.py:30-162):
  *   out[n,h,w,d] = sum_{o in image n, ascending o} vecs[o,d] * S_o(h,w),

@@ -198,6 +198,15 @@ def mask_net(sd, prefix, obj_vecs, training):
   return x.squeeze(1).sigmoid()
 
 
+def instancenorm2d(x, eps=1e-5):
+  """nn.InstanceNorm2d with torch's defaults, what get_normalization_2d('instance') builds
+  (sg2im/layers.py:24): per (image, channel) mean and BIASED variance over H*W, no affine
+  parameters, no running statistics (so the same in train and eval mode)."""
+  mean = x.mean(dim=(2, 3), keepdim=True)
+  var = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True)
+  return (x - mean) / torch.sqrt(var + eps)
+
+
 def refinement_module(sd, prefix, layout, feats, slope, normalization, training):
   """sg2im/crn.py:54-65 (+ layer list :40-52)."""
   HH, H = layout.size(2), feats.size(2)
@@ -205,16 +214,18 @@ def refinement_module(sd, prefix, layout, feats, slope, normalization, training)
     factor = HH // H
     layout = F.avg_pool2d(layout, kernel_size=factor, stride=factor)
   x = torch.cat([layout, feats], dim=1)            # layout channels FIRST
-  if normalization == 'batch':
+  if normalization in ('batch', 'instance'):         # the norm module occupies a Sequential slot
     conv_idx, bn_idx = (0, 3), (1, 4)
   elif normalization == 'none':
     conv_idx, bn_idx = (0, 2), (None, None)
   else:
-    raise ValueError('oracle covers normalization in {batch, none}')
+    raise ValueError('oracle covers normalization in {batch, instance, none}')
   for ci, bi in zip(conv_idx, bn_idx):
     x = F.conv2d(x, sd['%s.net.%d.weight' % (prefix, ci)],
                  sd['%s.net.%d.bias' % (prefix, ci)], padding=1)
-    if bi is not None:
+    if normalization == 'instance':
+      x = instancenorm2d(x)
+    elif bi is not None:
       x = batchnorm2d(sd, '%s.net.%d' % (prefix, bi), x, training)
     x = F.leaky_relu(x, slope)
   return x
@@ -329,8 +340,11 @@ def disc_cnn(sd, prefix, x, arch, normalization, activation, padding, training):
       if normalization == 'batch':
         x = batchnorm2d(sd, '%s.%d' % (prefix, idx), x, training)
         idx += 1
+      elif normalization == 'instance':
+        x = instancenorm2d(x)
+        idx += 1
       elif normalization != 'none':
-        raise ValueError('oracle covers normalization in {batch, none}')
+        raise ValueError('oracle covers normalization in {batch, instance, none}')
       x = F.leaky_relu(x, slope)
       idx += 1
     P = 0 if padding == 'valid' else (K - 1) // 2

@@ -11,8 +11,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import (get_normalization_2d, get_activation, Conv2d, BatchNorm2d,
-                     FusedSequential, _to_nhwc, _to_nchw)
+from .layers import (get_normalization_2d, get_activation, Conv2d, BatchNorm2d, InstanceNorm2d,
+                     FusedSequential, norm_act, _to_nhwc, _to_nchw)
 
 
 # Inference: fold an eval-mode BatchNorm into the convolution before it
@@ -25,7 +25,7 @@ FOLD_EVAL_BN = False
 
 
 def _can_fold(bn):
-  return (FOLD_EVAL_BN and bn is not None and not bn.training
+  return (FOLD_EVAL_BN and isinstance(bn, BatchNorm2d) and not bn.training
           and bn.running_mean is not None)
 
 
@@ -70,10 +70,11 @@ class RefinementModule(nn.Module):
     self.input_dim = input_dim
 
   def parts(self):
-    """(conv1, bn1|None, slope1, conv2, bn2|None, slope2)."""
+    """(conv1, norm1|None, slope1, conv2, norm2|None, slope2); norm = BatchNorm2d or
+    InstanceNorm2d."""
     mods = list(self.net)
     convs = [m for m in mods if isinstance(m, Conv2d)]
-    bns = [m for m in mods if isinstance(m, BatchNorm2d)] or [None, None]
+    bns = [m for m in mods if isinstance(m, (BatchNorm2d, InstanceNorm2d))] or [None, None]
     acts = [m for m in mods if isinstance(m, nn.LeakyReLU)]
     return convs[0], bns[0], acts[0].negative_slope, convs[1], bns[1], acts[1].negative_slope
 
@@ -144,19 +145,19 @@ class RefinementNetwork(nn.Module):
         else:
           h = ops.bn_act(a2, None, 1.0, up=2, out=bufs[i + 1], out_coff=C)
         continue
-      fb1 = bn1 is not None and bn1.training
-      fb2 = bn2 is not None and bn2.training
+      fb1 = isinstance(bn1, BatchNorm2d) and bn1.training
+      fb2 = isinstance(bn2, BatchNorm2d) and bn2.training
       st1 = ops.new_stats(conv1.out_channels, h.device) if fb1 else None
       z1 = conv1.forward_nhwc(h, in_ch=C if i == 0 else None, feeds_bn=fb1, stats_out=st1)
-      a1 = ops.bn_act(z1, bn1, s1, sums=st1)
+      a1 = norm_act(z1, bn1, s1, sums=st1)
       st2 = ops.new_stats(conv2.out_channels, h.device) if fb2 else None
       z2 = conv2.forward_nhwc(a1, feeds_bn=fb2, stats_out=st2)
       if i + 1 < len(mods):
         # BN + LeakyReLU + nearest x2 upsample, written into the next stage's
         # buffer behind its layout channels (crn.py:107 + :63)
-        h = ops.bn_act(z2, bn2, s2, up=2, out=bufs[i + 1], out_coff=C, sums=st2)
+        h = norm_act(z2, bn2, s2, up=2, out=bufs[i + 1], out_coff=C, sums=st2)
       else:
-        a = ops.bn_act(z2, bn2, s2, sums=st2)
+        a = norm_act(z2, bn2, s2, sums=st2)
     oc = list(self.output_conv)
     t = oc[0].forward_nhwc(a, 1, oc[1].negative_slope)
     return oc[2].forward_nhwc(t)

@@ -79,6 +79,36 @@ class BatchNorm2d(nn.BatchNorm2d):
     return _to_nchw(self.forward_nhwc(_to_nhwc(x).contiguous()))
 
 
+class InstanceNorm2d(nn.InstanceNorm2d):
+  """get_normalization_2d('instance') (sg2im/layers.py:24): torch's defaults — no affine
+  parameters, no running statistics, instance statistics in train AND eval mode, biased variance,
+  eps 1e-5; nothing in the state_dict.  Per image this is exactly the train-mode BatchNorm
+  arithmetic over that image's H*W rows with gamma = 1, beta = 0, so it runs on the same
+  statistics / finalize / normalise-activate(-upsample) kernels, one image per launch set."""
+
+  def forward_nhwc(self, h, slope=1.0, up=1, out=None, out_coff=0):
+    if self.affine or self.track_running_stats:
+      raise NotImplementedError('sg2im_b200.InstanceNorm2d: torch defaults only (what '
+                                'get_normalization_2d builds)')
+    h = h.contiguous()
+    y = torch.cat([ops.bn_act(h[n:n + 1], self, slope, up) for n in range(h.size(0))], 0)
+    if out is None:
+      return y
+    out[..., out_coff:out_coff + y.size(3)] = y
+    return out
+
+  def forward(self, x):
+    return _to_nchw(self.forward_nhwc(_to_nhwc(x)))
+
+
+def norm_act(h, norm, slope=1.0, up=1, out=None, out_coff=0, sums=None):
+  """leaky_slope(norm(h)) (+ nearest upsample, optionally written into a channel slice of `out`)
+  for norm = BatchNorm2d | InstanceNorm2d | None."""
+  if isinstance(norm, InstanceNorm2d):
+    return norm.forward_nhwc(h, slope, up, out, out_coff)
+  return ops.bn_act(h, norm, slope, up, 1, out, out_coff, sums)
+
+
 class BatchNorm1d(nn.BatchNorm1d):
   """(rows, C) batch norm for build_mlp(batch_norm='batch')."""
 
@@ -153,6 +183,33 @@ class AvgPool2(nn.AvgPool2d):
     h = _to_nhwc(x).contiguous()
     N, H, W, C = h.shape
     return _to_nchw(_AvgPool2Fn.apply(h))
+
+
+def _pool_factor(m):
+  """kernel_size = stride = f, no padding / dilation / ceil mode: what build_cnn builds."""
+  as2 = lambda v: (v, v) if isinstance(v, int) else tuple(v)            # noqa: E731
+  k, st = as2(m.kernel_size), as2(m.stride if m.stride is not None else m.kernel_size)
+  ok = (k[0] == k[1] and st == k and as2(m.padding) == (0, 0) and not m.ceil_mode
+        and as2(getattr(m, 'dilation', 1)) == (1, 1)
+        and getattr(m, 'divisor_override', None) is None and not getattr(m, 'return_indices', False))
+  if not ok:
+    raise NotImplementedError('sg2im_b200: pooling with kernel_size = stride, no padding only '
+                              "(what build_cnn's 'PX' builds)")
+  return int(k[0])
+
+
+class AvgPool2d(nn.AvgPool2d):
+  """'PX' with pooling='avg' (layers.py:198-199), any factor."""
+
+  def forward(self, x):
+    return _to_nchw(ops.Pool2d.apply(_to_nhwc(x), _pool_factor(self), 0))
+
+
+class MaxPool2d(nn.MaxPool2d):
+  """'PX' with pooling='max' (layers.py:196-197; build_cnn's default pooling)."""
+
+  def forward(self, x):
+    return _to_nchw(ops.Pool2d.apply(_to_nhwc(x), _pool_factor(self), 1))
 
 
 class _AvgPool2Fn(torch.autograd.Function):
@@ -241,6 +298,11 @@ class FusedSequential(nn.Sequential):
         else:
           h = m.forward_nhwc(h.contiguous(), sums=sums); i += 1
         sums = None
+      elif isinstance(m, InstanceNorm2d) and four_d:
+        if s is not None:
+          h = m.forward_nhwc(h, s); i += 2
+        else:
+          h = m.forward_nhwc(h); i += 1
       elif isinstance(m, BatchNorm1d) and not four_d:
         if s is not None:
           h = m.forward_act(h, s); i += 2
@@ -269,9 +331,7 @@ class FusedSequential(nn.Sequential):
 def get_normalization_2d(channels, normalization):
   """sg2im/layers.py:22-30."""
   if normalization == 'instance':
-    raise NotImplementedError(
-        "sg2im_b200: normalization='instance' is outside the accelerated path "
-        "(scripts/train.py defaults to 'batch'); use 'batch' or 'none'")
+    return InstanceNorm2d(channels)
   elif normalization == 'batch':
     return BatchNorm2d(channels)
   elif normalization == 'none':
@@ -309,13 +369,49 @@ def _get_padding(K, mode):
     return (K - 1) // 2
 
 
+class ResidualBlock(nn.Module):
+  """sg2im/layers.py:89-117, quirks included: `self.net` is evaluated TWICE per forward
+  (:115-116; the first result is discarded, but train-mode BatchNorm running statistics and
+  `num_batches_tracked` advance twice), and with padding 0 the shortcut is the EMPTY slice
+  x[:, :, 0:-0, 0:-0] (:112-114), so a 'valid' residual block fails in the addition exactly like
+  the reference's.  Same children / state_dict keys (net.0 .. net.5)."""
+
+  def __init__(self, channels, normalization='batch', activation='relu',
+               padding='same', kernel_size=3, init='default'):
+    super(ResidualBlock, self).__init__()
+    K = kernel_size
+    P = _get_padding(K, padding)
+    C = channels
+    self.padding = P
+    layers = [
+      get_normalization_2d(C, normalization),
+      get_activation(activation),
+      Conv2d(C, C, kernel_size=K, padding=P),
+      get_normalization_2d(C, normalization),
+      get_activation(activation),
+      Conv2d(C, C, kernel_size=K, padding=P),
+    ]
+    layers = [layer for layer in layers if layer is not None]
+    for layer in layers:
+      _init_conv(layer, method=init)
+    self.net = FusedSequential(*layers)
+
+  def forward(self, x):
+    P = self.padding
+    shortcut = x
+    if P == 0:
+      shortcut = x[:, :, P:-P, P:-P]
+    if self.training and any(isinstance(m, nn.BatchNorm2d) for m in self.net):
+      with torch.no_grad():
+        self.net(x)                  # the reference's discarded first evaluation (side effects only)
+    return shortcut + self.net(x)
+
+
 def build_cnn(arch, normalization='batch', activation='relu', padding='same',
               pooling='max', init='default'):
   """sg2im/layers.py:129-213: architecture-string CNN builder.
-  IX / CK-X[-S] / UX / PX / FC-X-Y are built on the sm_100a kernels; 'R'
-  (residual blocks) and max pooling are outside the accelerated path (no
-  default architecture uses them) and raise NotImplementedError.
-  Returns (nn.Sequential, channels)."""
+  Every token — IX / CK-X[-S] / R / UX / PX (max or average) / FC-X-Y — is built from modules
+  whose forward and backward run on the sm_100a kernels.  Returns (nn.Sequential, channels)."""
   if isinstance(arch, str):
     arch = arch.split(',')
   cur_C = 3
@@ -344,17 +440,22 @@ def build_cnn(arch, normalization='batch', activation='relu', padding='same',
       _init_conv(layers[-1], init)
       cur_C = next_C
     elif s[0] == 'R':
-      raise NotImplementedError("sg2im_b200.build_cnn: residual blocks ('R') are outside the "
-                                'accelerated path')
+      norm = 'none' if first_conv else normalization
+      res = ResidualBlock(cur_C, normalization=norm, activation=activation,
+                          padding=padding, init=init)
+      layers.append(res)
+      first_conv = False
     elif s[0] == 'U':
       layers.append(Upsample(scale_factor=int(s[1:]), mode='nearest'))
     elif s[0] == 'P':
       factor = int(s[1:])
       if pooling == 'avg' and factor == 2:
         layers.append(AvgPool2(kernel_size=2, stride=2))
-      else:
-        raise NotImplementedError("sg2im_b200.build_cnn: only 'P2' with pooling='avg' is "
-                                  'accelerated')
+      elif pooling == 'avg':
+        layers.append(AvgPool2d(kernel_size=factor, stride=factor))
+      elif pooling == 'max':
+        layers.append(MaxPool2d(kernel_size=factor, stride=factor))
+      # any other pooling string: the reference leaves `pool` unbound (layers.py:196-201)
     elif s[:2] == 'FC':
       _, Din, Dout = s.split('-')
       Din, Dout = int(Din), int(Dout)

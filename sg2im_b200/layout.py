@@ -18,26 +18,39 @@ def _num_imgs(obj_to_img, num_imgs):
   return int(obj_to_img.max().item()) + 1
 
 
+def _pooling_weights(vecs, obj_to_img, N, pooling):
+  """_pool_samples (sg2im/layout.py:131-162): 'sum', or 'avg' = the per-image sum divided by
+  clamp(number of objects of the image, 1).  The layout is linear in the object vectors, so the
+  division is applied to the (O, D) vectors (each by its image's count) instead of to the
+  (N, D, H, W) result: same value up to the last rounding, no extra pass over the layout.  The
+  reference prints the counts in 'avg' mode (:156); so does this."""
+  if pooling == 'sum':
+    return vecs
+  if pooling != 'avg':
+    raise ValueError('Invalid pooling "%s"' % pooling)
+  counts = torch.bincount(obj_to_img, minlength=N).to(vecs.dtype)
+  print(counts)
+  return vecs / counts.clamp(min=1)[obj_to_img].unsqueeze(1)
+
+
 def boxes_to_layout(vecs, boxes, obj_to_img, H, W=None, pooling='sum', num_imgs=None):
   """sg2im/layout.py:30-63."""
-  if pooling != 'sum':
-    raise NotImplementedError("sg2im_b200: only pooling='sum' (what the model uses)")
   if W is None:
     W = H
   N = _num_imgs(obj_to_img, num_imgs)
+  vecs = _pooling_weights(vecs, obj_to_img, N, pooling)
   out = ops.Layout.apply(vecs, boxes, None, obj_to_img, N, H, W, None, ALIGN_CORNERS)
   return out.permute(0, 3, 1, 2)
 
 
 def masks_to_layout(vecs, boxes, masks, obj_to_img, H, W=None, pooling='sum', num_imgs=None):
   """sg2im/layout.py:66-91."""
-  if pooling != 'sum':
-    raise NotImplementedError("sg2im_b200: only pooling='sum' (what the model uses)")
   O, D = vecs.size()
   M = masks.size(1)
   assert masks.size() == (O, M, M)
   if W is None:
     W = H
   N = _num_imgs(obj_to_img, num_imgs)
+  vecs = _pooling_weights(vecs, obj_to_img, N, pooling)
   out = ops.Layout.apply(vecs, boxes, masks, obj_to_img, N, H, W, None, ALIGN_CORNERS)
   return out.permute(0, 3, 1, 2)

@@ -636,6 +636,36 @@ class ConvKCC(torch.autograd.Function):
     return (dx, dw, db) + (None,) * 12
 
 
+class Pool2d(torch.autograd.Function):
+  """nn.AvgPool2d (mode 0) / nn.MaxPool2d (mode 1) with kernel_size = stride = factor on an
+  NHWC tensor — build_cnn's 'PX' token (sg2im/layers.py:195-201).  Floor mode: trailing rows /
+  columns that do not fill a window are dropped and get zero gradient."""
+
+  @staticmethod
+  def forward(ctx, h, factor, mode):
+    h = _chk(h).contiguous()
+    N, H, W, C = h.shape
+    out = torch.empty(N, H // factor, W // factor, C, dtype=torch.float32, device=h.device)
+    _call_b(4 * (h.numel() + out.numel()),
+            'sg2im_pool2d_fwd', _p(h), N, H, W, C, int(factor), int(mode), _p(out), _stream())
+    _count()
+    ctx.cfg = (N, H, W, C, int(factor), int(mode))
+    ctx.save_for_backward(h if mode == 1 else None)        # max: the arg-max is re-derived from x
+    return out
+
+  @staticmethod
+  def backward(ctx, dy):
+    N, H, W, C, f, mode = ctx.cfg
+    x, = ctx.saved_tensors
+    dy = dy.contiguous()
+    ragged = H % f != 0 or W % f != 0
+    dx = (torch.zeros if ragged else torch.empty)(N, H, W, C, dtype=torch.float32, device=dy.device)
+    _call_b(4 * (dx.numel() * (2 if mode == 1 else 1) + dy.numel()),
+            'sg2im_pool2d_bwd', _p(dy), _p(x), N, H, W, C, f, mode, _p(dx), _stream())
+    _count()
+    return dx, None, None
+
+
 class S2D(torch.autograd.Function):
   """Space-to-depth by 2 with zero padding to even size: (N,H,W,C) ->
   (N,ceil(H/2),ceil(W/2),4C), channel = ((y&1)*2+(x&1))*C + c."""

@@ -134,6 +134,12 @@ def _avgpool2_bwd(dcoarse, dc_coff, C, dfine, df_coff, accumulate):
     dfine[..., df_coff:df_coff + C] = g
 
 
+def _pool2d(h, factor, mode):
+  x = h.permute(0, 3, 1, 2)
+  y = F.avg_pool2d(x, factor, factor) if mode == 0 else F.max_pool2d(x, factor, factor)
+  return y.permute(0, 2, 3, 1)
+
+
 def _round_tf32(src, dst):
   u = src.view(torch.int32)
   finite = (u & 0x7f800000) != 0x7f800000
@@ -168,7 +174,8 @@ def cpu_ops():
               adam_flat=_adam_flat, round_tf32=_round_tf32, avgpool2_fwd=_avgpool2_fwd, avgpool2_bwd=_avgpool2_bwd,
               csr_build=lambda idx, nroles, num_rows: (None, None),
               LayoutStack=_Apply(_layout_stack), Layout=_Apply(_layout), Crop=_Apply(_crop),
-              TripleGather=_Apply(_triple_gather), GraphPool=_Apply(_graph_pool))
+              TripleGather=_Apply(_triple_gather), GraphPool=_Apply(_graph_pool),
+              Pool2d=_Apply(_pool2d))
   for k, v in repl.items():
     saved[k] = getattr(ops, k)
     setattr(ops, k, v)

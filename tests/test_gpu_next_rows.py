@@ -711,3 +711,131 @@ def test_cta_pair_halo_matches_single_cta(N, H, W, Ci, Co):
     assert torch.allclose(s0, s1, rtol=1e-6, atol=1e-4)       # atomics in another order
   finally:
     ops.set_conv_math('fp32')
+
+
+# ---- factory-surface rows a9 / a10: normalization='instance', build_cnn's 'R'
+# and 'PX' tokens.  Instance normalisation and the residual block reuse hardware-validated kernels
+# (per-image BatchNorm statistics / apply, convolutions); csrc/pool.cu is new device code.
+
+@pytest.mark.parametrize('N,H,W,C,f', [(2, 8, 8, 8, 2), (3, 13, 9, 6, 3), (1, 4, 4, 4, 4),
+                                       (2, 7, 10, 5, 2), (2, 6, 6, 12, 1)])
+@pytest.mark.parametrize('mode', [0, 1])
+def test_pool2d_forward_backward_vs_torch(N, H, W, C, f, mode):
+  """sg2im_pool2d_fwd / _bwd vs F.avg_pool2d / F.max_pool2d (kernel = stride = f, floor mode):
+  ragged sizes, channel counts off the float4 path, and — for max — exact ties (first element in
+  row-major window order wins, like ATen)."""
+  import torch.nn.functional as F
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(N * 100 + H * 10 + f + mode)
+  x = torch.randn(N, C, H, W, generator=g)
+  if mode == 1:
+    x = (x * 2).round() / 2                           # plenty of exact ties inside windows
+  xr = x.clone().requires_grad_(True)
+  want = (F.avg_pool2d if mode == 0 else F.max_pool2d)(xr, f, f)
+  wgt = torch.randn(want.shape, generator=g)
+  (want * wgt).sum().backward()
+  h = x.permute(0, 2, 3, 1).contiguous().to(dev()).requires_grad_(True)
+  got = ops.Pool2d.apply(h, f, mode)
+  (got * wgt.permute(0, 2, 3, 1).to(dev())).sum().backward()
+  assert got.shape == (N, H // f, W // f, C)
+  if mode == 1:
+    assert torch.equal(got.detach().cpu().permute(0, 3, 1, 2), want.detach())
+    assert torch.equal(h.grad.cpu().permute(0, 3, 1, 2), xr.grad)
+  else:
+    assert rel_err(got.detach().cpu().permute(0, 3, 1, 2), want.detach()) < 1e-6
+    assert rel_err(h.grad.cpu().permute(0, 3, 1, 2), xr.grad) < 1e-6
+
+
+def test_pool2d_refuses_empty_output():
+  from sg2im_b200 import ops
+  with pytest.raises(RuntimeError):
+    ops.Pool2d.apply(torch.zeros(1, 2, 2, 4, device=dev()), 3, 1)
+
+
+@pytest.mark.parametrize('up,slope,sliced', [(1, 1.0, False), (1, 0.2, False), (2, 0.2, True)])
+def test_instance_norm_vs_oracle(up, slope, sliced):
+  """layers.InstanceNorm2d / layers.norm_act(+ LeakyReLU, + nearest x2 upsample into a channel
+  slice, as the CRN uses it) vs oracle.instancenorm2d; forward and gradient."""
+  import torch.nn.functional as F
+  from oracle import sg2im_oracle as orc
+  from sg2im_b200.layers import InstanceNorm2d, norm_act
+  g = torch.Generator().manual_seed(7)
+  N, H, W, C, coff = 3, 6, 5, 8, 4
+  x = torch.randn(N, C, H, W, generator=g) * 2 + 0.5
+  xr = x.clone().requires_grad_(True)
+  want = F.leaky_relu(orc.instancenorm2d(xr), slope) if slope != 1.0 else orc.instancenorm2d(xr)
+  if up > 1:
+    want = F.interpolate(want, scale_factor=up, mode='nearest')
+  wgt = torch.randn(want.shape, generator=g)
+  (want * wgt).sum().backward()
+  norm = InstanceNorm2d(C)
+  assert len(norm.state_dict()) == 0
+  for training in (True, False):                      # instance statistics in both modes
+    norm.train(training)
+    h = x.permute(0, 2, 3, 1).contiguous().to(dev()).requires_grad_(True)
+    if sliced:
+      buf = torch.full((N, H * up, W * up, coff + C + 4), 3.0, device=dev())
+      out = norm_act(h, norm, slope, up=up, out=buf, out_coff=coff)
+      got = out[..., coff:coff + C]
+      assert bool((out[..., :coff] == 3.0).all()) and bool((out[..., coff + C:] == 3.0).all())
+    else:
+      got = norm_act(h, norm, slope, up=up)
+    (got * wgt.permute(0, 2, 3, 1).to(dev())).sum().backward()
+    assert rel_err(got.detach().cpu().permute(0, 3, 1, 2), want.detach()) < TOL
+    assert rel_err(h.grad.cpu().permute(0, 3, 1, 2), xr.grad) < TOL
+
+
+@pytest.mark.parametrize('arch,norm,pool,size', [('R,C3-8,R,P2,R', 'batch', 'max', 8),
+                                                 ('I4,C3-4,R,P3', 'instance', 'avg', 9)])
+def test_build_cnn_residual_pool_instance_vs_torch(arch, norm, pool, size):
+  """build_cnn with 'R' / 'PX' tokens and instance normalisation against the same network spelled
+  with torch.nn.functional on the CPU (sg2im/layers.py:89-117,129-213), forward, input gradient,
+  running statistics (the residual block evaluates its body twice per forward in train mode)."""
+  import torch.nn.functional as F
+  from oracle import sg2im_oracle as orc
+  from sg2im_b200.layers import build_cnn, ResidualBlock
+  torch.manual_seed(3)
+  with contextlib.redirect_stdout(io.StringIO()):
+    net, _ = build_cnn(arch, normalization=norm, activation='leakyrelu-0.2', padding='same',
+                       pooling=pool)
+  sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+  net = net.to(dev()).train()
+  cin = int(arch[1]) if arch.startswith('I') else 3
+  x = torch.randn(2, cin, size, size)
+
+  def run_ref(mods, sd, prefix, t, twice=False):
+    for i, m in enumerate(mods):
+      key = '%s%d' % (prefix, i)
+      if isinstance(m, ResidualBlock):
+        if any(isinstance(c, torch.nn.BatchNorm2d) for c in m.net):
+          run_ref(list(m.net), sd, key + '.net.', t.detach())          # discarded first evaluation
+        t = t + run_ref(list(m.net), sd, key + '.net.', t)
+      elif isinstance(m, torch.nn.Conv2d):
+        t = F.conv2d(t, sd[key + '.weight'], sd[key + '.bias'], stride=m.stride, padding=m.padding)
+      elif isinstance(m, torch.nn.BatchNorm2d):
+        t = orc.batchnorm2d(sd, key, t, True)
+      elif isinstance(m, torch.nn.InstanceNorm2d):
+        t = orc.instancenorm2d(t)
+      elif isinstance(m, torch.nn.LeakyReLU):
+        t = F.leaky_relu(t, m.negative_slope)
+      elif isinstance(m, torch.nn.MaxPool2d):
+        t = F.max_pool2d(t, m.kernel_size, m.stride)
+      elif isinstance(m, torch.nn.AvgPool2d):
+        t = F.avg_pool2d(t, m.kernel_size, m.stride)
+      else:
+        raise AssertionError(type(m))
+    return t
+
+  xr = x.clone().requires_grad_(True)
+  sd = {k: v.clone() for k, v in sd0.items()}
+  want = run_ref(list(net), sd, '', xr)
+  wgt = torch.randn(want.shape)
+  (want * wgt).sum().backward()
+  xg = x.to(dev()).requires_grad_(True)
+  got = net(xg)
+  (got * wgt.to(dev())).sum().backward()
+  assert rel_err(got.detach().cpu(), want.detach()) < TOL
+  assert rel_err(xg.grad.cpu(), xr.grad) < TOL
+  for k, v in net.state_dict().items():
+    if 'running' in k or 'num_batches' in k:
+      assert rel_err(v.cpu().float(), sd[k].float()) < TOL, k

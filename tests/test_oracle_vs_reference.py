@@ -31,6 +31,9 @@ CONFIGS = [
     dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=0,
          refinement_dims=(8, 8), mask_size=8, layout_noise_dim=4, image_size=(16, 16),
          gconv_pooling='sum', activation='leakyrelu'),
+    dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=1,
+         refinement_dims=(16, 8), mask_size=8, layout_noise_dim=4, image_size=(16, 16),
+         normalization='instance'),
 ]
 
 
@@ -98,6 +101,7 @@ def test_generator_oracle_and_mirror_vs_live_reference(idx):
 
 @pytest.mark.parametrize('arch,norm,pad', [('C4-8-2,C4-16-2,C4-16-2', 'batch', 'valid'),
                                           ('C3-8,C3-8-2', 'none', 'same'),
+                                          ('C4-8-2,C4-16-2', 'instance', 'valid'),
                                           ('C4-8-2', 'batch', 'valid')])
 def test_discriminators_mirror_vs_live_reference(arch, norm, pad):
   import_reference()
@@ -162,7 +166,12 @@ def test_build_mlp_mirror_vs_live_reference(dims, act, bn, final, drop):
     ('I5,C3-8,U2,C3-6', 'batch', 'same', 'avg', 8),
     ('C3-8,P2,C3-8-2,FC-32-10,FC-10-3', 'none', 'same', 'avg', 8),
     ('C4-8-2,C4-8-2', 'batch', 'valid', 'avg', 16),
-    ('C1-4,C3-4', 'none', 'same', 'avg', 6)])
+    ('C1-4,C3-4', 'none', 'same', 'avg', 6),
+    ('C3-8,U2,C3-6,C3-4-2', 'instance', 'same', 'avg', 8),
+    ('C3-8,P2,C3-8,P3', 'batch', 'same', 'max', 13),          # max pooling, ragged 13 -> 6 -> 2
+    ('C3-4,P4,C1-4', 'none', 'same', 'avg', 9),               # average pooling by 4, ragged
+    ('R,C3-8,R,P2,R', 'batch', 'same', 'max', 8),             # residual blocks (first one un-normalised)
+    ('I4,C3-4,R', 'instance', 'same', 'avg', 6)])
 def test_build_cnn_mirror_vs_live_reference(arch, norm, pad, pool, size):
   """sg2im/layers.py:129-213: input-channel spec, upsample, average pooling,
   fully-connected tail, stride / padding variants."""
@@ -179,7 +188,7 @@ def test_build_cnn_mirror_vs_live_reference(arch, norm, pad, pool, size):
   assert c_ref == c_mine
   assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
   mine.load_state_dict(ref.state_dict())
-  cin = 5 if arch.startswith('I5') else 3
+  cin = int(arch[1]) if arch.startswith('I') else 3
   x = torch.randn(2, cin, size, size)
   for training in (True, False):
     ref.train(training); mine.train(training)
@@ -187,6 +196,9 @@ def test_build_cnn_mirror_vs_live_reference(arch, norm, pad, pool, size):
       got = mine(x)
     want = ref(x)
     assert got.shape == want.shape and rel_err(got, want) < TOL
+  # running statistics incl. the residual block's double evaluation (layers.py:115-116)
+  for k, v in ref.state_dict().items():
+    assert rel_err(mine.state_dict()[k].float(), v.float()) < TOL, k
 
 
 def test_generator_with_batchnorm_mlps_vs_live_reference():
@@ -249,3 +261,37 @@ def test_refinement_network_standalone_forward_backward_vs_live_reference():
     if k.endswith('net.0.bias') or k.endswith('net.3.bias'):
       continue                                           # conv bias in front of BatchNorm: rounding noise only
     assert rel_err(p.grad, gr[k].grad) < 1e-3, k
+
+
+@pytest.mark.parametrize('pooling', ['sum', 'avg'])
+def test_layout_functions_mirror_vs_live_reference(pooling):
+  """sg2im/layout.py:30-91,131-162: boxes_to_layout / masks_to_layout as free functions, both
+  pooling modes ('avg' divides by the per-image object count, clamped at 1 — image 1 below has no
+  objects — and prints the counts like the reference), forward and gradient w.r.t. the vectors."""
+  import_reference()
+  from sg2im import layout as ref
+  from sg2im_b200 import layout as mine
+  from cpu_shim import cpu_ops
+  g = torch.Generator().manual_seed(17)
+  O, D, M, H, W = 7, 6, 4, 12, 10
+  vecs = torch.randn(O, D, generator=g)
+  xy = torch.rand(O, 2, generator=g) * 0.5
+  boxes = torch.cat([xy, xy + 0.2 + 0.3 * torch.rand(O, 2, generator=g)], 1)
+  masks = torch.rand(O, M, M, generator=g)
+  o2i = torch.tensor([0, 0, 0, 2, 2, 3, 3])                 # image 1 is empty
+  for fn, extra in (('boxes_to_layout', ()), ('masks_to_layout', (masks,))):
+    vr = vecs.clone().requires_grad_(True)
+    vm = vecs.clone().requires_grad_(True)
+    with _quiet():
+      want = getattr(ref, fn)(vr, boxes, *extra, o2i, H, W, pooling=pooling)
+      with cpu_ops():
+        got = getattr(mine, fn)(vm, boxes, *extra, o2i, H, W, pooling=pooling)
+    assert got.shape == want.shape == (4, D, H, W)
+    assert rel_err(got, want) < TOL
+    wgt = torch.randn(want.shape, generator=g)
+    (want * wgt).sum().backward()
+    with cpu_ops():
+      (got * wgt).sum().backward()
+    assert rel_err(vm.grad, vr.grad) < TOL
+  with pytest.raises(ValueError):
+    mine.boxes_to_layout(vecs, boxes, o2i, H, W, pooling='max')

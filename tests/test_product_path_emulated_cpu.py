@@ -301,3 +301,21 @@ def test_hbm_kernel_profiling_hooks_of_the_benchmark(emul, monkeypatch):
   assert all(r['gbs'] > 0 and r['launches_per_step'] > 0 for r in tab['by_kernel'].values())
   import json
   json.dumps(tab)
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_general_pooling_kernels(emul_next, mode):
+  """csrc/pool.cu (build_cnn 'PX', max and average, any factor) executes on the host."""
+  for case in [(2, 8, 8, 8, 2), (3, 13, 9, 6, 3), (1, 4, 4, 4, 4), (2, 7, 10, 5, 2), (2, 6, 6, 12, 1)]:
+    R.test_pool2d_forward_backward_vs_torch(*case, mode)
+  R.test_pool2d_refuses_empty_output()
+
+
+def test_instance_norm_on_the_batchnorm_kernels(emul_next):
+  for case in [(1, 1.0, False), (1, 0.2, False), (2, 0.2, True)]:
+    R.test_instance_norm_vs_oracle(*case)
+
+
+def test_build_cnn_residual_blocks_pooling_instance_norm(emul_next):
+  R.test_build_cnn_residual_pool_instance_vs_torch('R,C3-8,R,P2,R', 'batch', 'max', 8)
+  R.test_build_cnn_residual_pool_instance_vs_torch('I4,C3-4,R,P3', 'instance', 'avg', 9)
