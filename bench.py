@@ -42,8 +42,10 @@ def parse():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--workload', default='vg128')
   ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: config)')
-  ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'],
-                  help='convolution arithmetic: tcgen05 TF32 (default) or exact-fp32 FFMA')
+  ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32', 'tf32x3'],
+                  help='convolution arithmetic: tcgen05 TF32 (default), exact-fp32 FFMA, or '
+                       "error-compensated TF32 on the tensor core ('tf32x3': fp32-grade results, 3x the "
+                       'tensor-core work; opt-in until validated on hardware)')
   ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
   ap.add_argument('--adam', default='torch', choices=['torch', 'flat'],
                   help="'flat': one sg2im_adam_flat kernel per optimiser (opt-in until validated on hardware)")

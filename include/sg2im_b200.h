@@ -238,6 +238,18 @@ int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int64_t dc_coff
                        float* dfine, int64_t df_cstride, int64_t df_coff, int accumulate,
                        sg2im_stream_t stream);
 
+/* TF32 hi / lo split of fp32 rows for the error-compensated tensor-core mode ('tf32x3'):
+ * hi = round-to-nearest-TF32(x), lo = x - hi.  x: `rows` rows of C floats, row stride x_stride
+ * (a channel-prefix view of a wider NHWC buffer is fine).  hi / lo / hi2 are optional
+ * destinations (NULL = skip) with their own row strides: pass three pointers into one
+ * (rows, 3C) buffer for the concatenated operand [hi | lo | hi], or separate tensors.  With
+ * x3 = [hi_x | lo_x | hi_x] and w3 = [hi_w | hi_w | lo_w] along the input-channel axis, one
+ * sg2im_conv_tc launch evaluates hi*hi + lo*hi + hi*lo with fp32 accumulation — the
+ * reference's fp32 nn.Conv2d / nn.Linear arithmetic to ~2^-21 on the TF32 tensor core. */
+int sg2im_split_tf32(const float* x, int64_t rows, int64_t C, int64_t x_stride,
+                     float* hi, int64_t hi_stride, float* lo, int64_t lo_stride,
+                     float* hi2, int64_t hi2_stride, sg2im_stream_t stream);
+
 /* Non-overlapping pooling, NHWC contiguous: nn.MaxPool2d / nn.AvgPool2d(kernel_size = stride =
  * factor) as built by build_cnn's 'PX' token (sg2im/layers.py:195-201).  mode 0 = average,
  * 1 = max (ties: first element in row-major window order, like ATen).  y is

@@ -56,7 +56,7 @@ class Linear(nn.Linear):
     x2 = x.reshape(-1, x.size(-1))
     nout = self.out_features
     pad = (-nout) % 4
-    if pad and ops.CONV_MATH == 'tf32' and nout >= 32 and self.in_features % 4 == 0:
+    if pad and ops._tc_math() and nout >= 32 and self.in_features % 4 == 0:
       # e.g. the object classifier (1024 -> num_objects = 179): pad the output
       # width to a multiple of 4 with zero rows so the GEMM and its data
       # gradient run on the tensor-core kernel; the extra columns are sliced off

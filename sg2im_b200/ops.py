@@ -153,11 +153,67 @@ def set_conv_math(mode):
   'tf32': stride-1 convolutions and Linears whose shape tiles run on the
   tcgen05 tensor-core kernel (TF32 multiply, fp32 accumulate — the arithmetic
   cuDNN uses for the reference under torch's default allow_tf32); everything
-  else stays on the FFMA kernels."""
+  else stays on the FFMA kernels.
+  'tf32x3': the same tensor-core kernels fed error-compensated operands — every
+  operand split into a TF32 hi part and an fp32 remainder, the three significant
+  products hi*hi + lo*hi + hi*lo laid side by side along the reduction dimension
+  of ONE launch (forward, data gradient) or two (weight gradient) — so results
+  agree with the fp32 reference to ~1e-6 (the 1e-3 parity bar with margin) at
+  three times the tensor-core work of 'tf32'.  Activations stay unrounded fp32."""
   global CONV_MATH
-  if mode not in ('fp32', 'tf32'):
-    raise ValueError("conv math must be 'fp32' or 'tf32'")
+  if mode not in ('fp32', 'tf32', 'tf32x3'):
+    raise ValueError("conv math must be 'fp32', 'tf32' or 'tf32x3'")
   CONV_MATH = mode
+
+
+def _tc_math():
+  return CONV_MATH in ('tf32', 'tf32x3')
+
+
+def _tc_shape_ok(N, H, W, C, KH, KW, P, Cout, out_hw):
+  """conv_tc_ok for a contiguous, 16-byte aligned NHWC tensor that does not exist yet."""
+  return bool(_lib.load().sg2im_conv_tc_supported(N, H, W, C, C, KH, KW, 1, P, out_hw[0],
+                                                  out_hw[1], Cout, Cout, 0))
+
+
+def split_tf32(x, parts, separate=False):
+  """x: (N,H,W,C)-shaped NHWC tensor or channel-prefix view.  hi = RN-TF32(x), lo = x - hi.
+  parts=3 -> (N,H,W,3C) [hi | lo | hi]; parts=2 -> (N,H,W,2C) [hi | lo];
+  separate=True -> (hi, lo) as two contiguous tensors."""
+  _chk(x)
+  N, H, W, C = x.shape
+  cs = _pixel_stride(x)
+  if cs is None:
+    x = x.contiguous()
+    cs = C
+  rows = N * H * W
+  dev = x.device
+  if separate:
+    hi = torch.empty(N, H, W, C, dtype=torch.float32, device=dev)
+    lo = torch.empty(N, H, W, C, dtype=torch.float32, device=dev)
+    _call_b(12 * rows * C, 'sg2im_split_tf32', _p(x), rows, C, cs, _p(hi), C, _p(lo), C, None, 0,
+            _stream())
+    _count()
+    return hi, lo
+  out = torch.empty(N, H, W, parts * C, dtype=torch.float32, device=dev)
+  base = out.data_ptr()
+  _call_b(4 * rows * C * (1 + parts), 'sg2im_split_tf32', _p(x), rows, C, cs, base, parts * C,
+          base + 4 * C, parts * C, (base + 8 * C) if parts == 3 else None, parts * C, _stream())
+  _count()
+  return out
+
+
+def _rn_tf32_host(t):
+  """Round-to-nearest TF32 of a (small: weights) tensor with integer ops, ties away from zero
+  like cvt.rna."""
+  u = t.contiguous().view(torch.int32)
+  finite = (u & 0x7f800000) != 0x7f800000
+  return torch.where(finite, (u + 0x1000) & ~0x1fff, u).view(torch.float32)
+
+
+def _split_weight(w):
+  hi = _rn_tf32_host(w)
+  return hi, w - hi
 
 
 def _pixel_stride(x):
@@ -175,7 +231,7 @@ def _pixel_stride(x):
 
 
 def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
-  if CONV_MATH != 'tf32' or S != 1:
+  if not _tc_math() or S != 1:
     return False
   cs = _pixel_stride(x)
   if cs is None or x.data_ptr() % 16:
@@ -254,10 +310,12 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   return grad
 
 
-def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
+def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None):
   """Returns dw packed (KH*KW*Cin, Cout).  accumulate_into: a contiguous buffer of that size
   the kernels ADD into (they combine partial tiles with atomics anyway) instead of a fresh
-  zeroed one — e.g. the parameter's slice of the flat gradient bucket."""
+  zeroed one — e.g. the parameter's slice of the flat gradient bucket.  tc: use the tensor-core
+  kernel when the shape allows (default: only in 'tf32' mode; the 'tf32x3' route passes its
+  split operands with tc=True)."""
   _chk(x)
   dy = _chk(dy).contiguous()
   N, Hin, Win, Cin = x.shape
@@ -268,7 +326,7 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
     dw = accumulate_into.view(KH * KW * Cin, Cout)
   else:
     dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
-  if CONV_MATH == 'tf32' and S == 1:
+  if (CONV_MATH == 'tf32' if tc is None else tc) and S == 1:
     cs = _pixel_stride(x)
     if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
         N, Hin, Win, Cin, cs, KH, KW, S, P, Hout, Wout, Cout)):
@@ -284,6 +342,29 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
           Hout, Wout, Cout, _p(dw), _stream())
   _count()
   return dw
+
+
+def conv_wgrad_x3(x, dy, KH, KW, P):
+  """Weight gradient of a stride-1 conv in 'tf32x3' mode: dW = sum over pixels of x (x) dy with
+  x = hi_x + lo_x, dy = hi_dy + lo_dy.  The reduction runs over pixels, so the three products
+  cannot share one accumulator along K; instead the input-channel axis carries two of them:
+  wgrad([hi_x | lo_x], hi_dy) -> rows [hi*hi ; lo*hi], plus wgrad(hi_x, lo_dy).  Returns dw
+  packed (KH*KW*Cin, Cout), or None when the channel counts rule the split form out."""
+  N, H, W, Ci = x.shape
+  Co = dy.size(3)
+  if Ci % 4 or Co % 4:
+    return None
+  Ho, Wo = dy.size(1), dy.size(2)
+  sup = _lib.load().sg2im_conv_wgrad_tc_supported
+  if not (sup(N, H, W, 2 * Ci, 2 * Ci, KH, KW, 1, P, Ho, Wo, Co)
+          and sup(N, H, W, Ci, 2 * Ci, KH, KW, 1, P, Ho, Wo, Co)):
+    return None                                  # the exact-fp32 kernel takes the unsplit operands
+  T = KH * KW
+  x2 = split_tf32(x, 2)
+  dy_hi, dy_lo = split_tf32(dy, 2, separate=True)
+  a = conv_wgrad(x2, dy_hi, KH, KW, 1, P, tc=True).view(T, 2 * Ci, Co)
+  b = conv_wgrad(x2[..., :Ci], dy_lo, KH, KW, 1, P, tc=True).view(T, Ci, Co)
+  return (a[:, :Ci] + a[:, Ci:] + b).reshape(T * Ci, Co)
 
 
 def colsum(x2d):
@@ -467,7 +548,15 @@ class Conv(torch.autograd.Function):
       Hout, Wout = out_hw
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
     w_dgrad = None
-    if conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
+    x3 = (CONV_MATH == 'tf32x3' and stride == 1 and Ci % 4 == 0
+          and _tc_shape_ok(x.size(0), x.size(1), x.size(2), 3 * Ci, KH, KW, pad, Co, (Hout, Wout)))
+    if x3:
+      # error-compensated operands, one launch: [hi_x | lo_x | hi_x] * [hi_w | hi_w | lo_w]
+      w_hi, w_lo = _split_weight(w_used)
+      y = conv_tc(split_tf32(x, 3), pack_tc_fwd(torch.cat([w_hi, w_hi, w_lo], 1)), bias, KH, KW,
+                  pad, Co, act, slope, out_hw=(Hout, Wout),
+                  stats=stats_out if fused_stats else None)
+    elif CONV_MATH == 'tf32' and conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
       if (PACK_BOTH and ctx.needs_input_grad[0] and KH == KW and stride == 1
           and KH - 1 - pad >= 0):
         w_fwd, w_dgrad = _pack(weight, Ci, True, True)
@@ -485,6 +574,7 @@ class Conv(torch.autograd.Function):
       _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
+    ctx.x3 = CONV_MATH == 'tf32x3'
     ctx.w_dgrad = w_dgrad                       # packed in the forward pass (PACK_BOTH) or None
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.bias_ref = bias                         # the Parameter itself (its .grad slot), not a saved value
@@ -509,8 +599,14 @@ class Conv(torch.autograd.Function):
     if ctx.needs_input_grad[0]:
       w_used = weight if Ci == Ci_w else weight[:, :Ci]
       pad_t = KH - 1 - pad
-      if (KH == KW and pad_t >= 0 and stride == 1
-          and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
+      if (ctx.x3 and KH == KW and pad_t >= 0 and stride == 1 and Co % 4 == 0
+          and _tc_shape_ok(dy.size(0), dy.size(1), dy.size(2), 3 * Co, KH, KW, pad_t, Ci,
+                           (x.size(1), x.size(2)))):
+        w_hi, w_lo = _split_weight(weight)
+        dx = conv_tc(split_tf32(dy, 3), pack_tc_dgrad(torch.cat([w_hi, w_hi, w_lo], 0), Ci), None,
+                     KH, KW, pad_t, Ci, tag='conv_dgrad_tc', out_hw=(x.size(1), x.size(2)))
+      elif (not ctx.x3 and KH == KW and pad_t >= 0 and stride == 1
+            and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
         w_dgrad = ctx.w_dgrad if ctx.w_dgrad is not None else pack_tc_dgrad(weight, Ci)
         dx = conv_tc(dy, w_dgrad, None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
                      out_hw=(x.size(1), x.size(2)))
@@ -518,7 +614,9 @@ class Conv(torch.autograd.Function):
         dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
                         (x.size(1), x.size(2)), Ci)
     if ctx.needs_input_grad[1]:
-      dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
+      dwp = conv_wgrad_x3(x, dy, KH, KW, pad) if (ctx.x3 and stride == 1) else None
+      if dwp is None:
+        dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
       dw = unpack_wgrad_oihw(dwp, wshape, Ci)
     if ctx.has_bias and ctx.needs_input_grad[2] and not db_done:
       if ctx.zero_bias_grad:
@@ -730,8 +828,13 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
   round_out = bool(round_out) and CONV_MATH == 'tf32'
   Co, C, KH, KW = weight.shape
   kcc = CONV_MATH == 'tf32' and is_kcc(weight)
-  if (CONV_MATH == 'tf32' and stride == 2 and pad == 0 and in_ch is None
-      and KH == 4 and KW == 4 and x.size(1) >= 4 and x.size(2) >= 4 and Co % 32 == 0):
+  s2d = (_tc_math() and stride == 2 and pad == 0 and in_ch is None
+         and KH == 4 and KW == 4 and x.size(1) >= 4 and x.size(2) >= 4 and Co % 32 == 0)
+  if s2d and CONV_MATH == 'tf32x3':
+    # the cropped-output form exists on the tensor-core kernel only: the split operand must tile
+    s2d = _tc_shape_ok(x.size(0), (x.size(1) + 1) // 2, (x.size(2) + 1) // 2, 12 * C, 2, 2, 0, Co,
+                       (conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)))
+  if s2d:
     # 4x4 stride-2 'valid' conv (the discriminators, scripts/train.py:122-130) ==
     # 2x2 stride-1 conv on the space-to-depth input: runs on the tensor-core
     # kernels (forward, dgrad, wgrad) with no strided gathers.

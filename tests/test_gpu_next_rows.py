@@ -839,3 +839,60 @@ def test_build_cnn_residual_pool_instance_vs_torch(arch, norm, pool, size):
   for k, v in net.state_dict().items():
     if 'running' in k or 'num_batches' in k:
       assert rel_err(v.cpu().float(), sd[k].float()) < TOL, k
+
+
+# ---- 'tf32x3': error-compensated operands on the tcgen05 kernels (ops.set_conv_math('tf32x3')).
+# Launches only hardware-validated convolution kernels plus csrc/split.cu (new, trivial).  The bar
+# is the fp32 one: the same tolerances as the exact-fp32 configuration's tests.
+
+def _with_math(mode, fn):
+  from sg2im_b200 import ops
+  ops.set_conv_math(mode)
+  try:
+    return fn()
+  finally:
+    ops.set_conv_math('fp32')
+
+
+def test_split_tf32_kernel():
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(4)
+  x = (torch.randn(3, 5, 7, 12, generator=g) * 10.0 ** torch.randint(-3, 4, (3, 5, 7, 12), generator=g)).to(dev())
+  x[0, 0, 0, 0] = 0.0
+  x3 = ops.split_tf32(x, 3)
+  hi, lo = ops.split_tf32(x, 2, separate=True)
+  assert torch.equal(x3[..., :12], hi) and torch.equal(x3[..., 12:24], lo) and torch.equal(x3[..., 24:], hi)
+  assert torch.equal(hi + lo, x)                                     # the split is exact
+  assert bool(((hi.view(torch.int32) & 0x1fff) == 0).all())           # hi is a TF32 number
+  assert bool((lo.abs() <= x.abs() * 2.0 ** -11 * 1.0001).all())
+  wide = torch.randn(2, 4, 4, 20, generator=g).to(dev())              # channel-prefix view, scalar path
+  v = wide[..., :6]
+  assert torch.equal(ops.split_tf32(v, 2)[..., :6] + ops.split_tf32(v, 2)[..., 6:], v)
+
+
+def test_tf32x3_generator_forward_meets_the_fp32_bar():
+  import test_gpu_model as G
+
+  def run():
+    g = load_golden('generator.pt')
+    imgs, objs, boxes, triples, o2i, _ = [t.to(dev()) for t in g['batch']]
+    kw = g['kwargs']
+    noise = G._noise(g['noise_seed'], imgs.size(0), kw['layout_noise_dim'], kw['image_size']).to(dev())
+    m = G._build_generator(g)
+    m.train()
+    out = m(objs, triples, o2i, boxes_gt=boxes, noise=noise)
+    errs = [rel_err(a, b) for a, b in zip(out, g['out_vg'])]
+    print('tf32x3 end-to-end rel err (img, boxes, masks, rel):', errs)
+    assert max(errs) < TOL                       # 1e-4; the plain TF32 path sits at 2.7e-3
+  _with_math('tf32x3', run)
+
+
+def test_tf32x3_gradients_and_training_iterations_meet_the_fp32_bar(monkeypatch):
+  """Parameter gradients vs the oracle's autograd and the reference's two training iterations
+  (losses 1e-3, parameters after two Adam steps) — the exact-fp32 tests' own assertions, with the
+  convolutions / Linears on the tensor-core kernels."""
+  import test_gpu_model as G
+  monkeypatch.setattr(G, 'dev', dev)
+  _with_math('tf32x3', G.test_generator_gradients_vs_oracle)
+  _with_math('tf32x3', G.test_two_training_iterations_match_reference)
+  _with_math('tf32x3', G.test_discriminators_forward)

@@ -319,3 +319,13 @@ def test_instance_norm_on_the_batchnorm_kernels(emul_next):
 def test_build_cnn_residual_blocks_pooling_instance_norm(emul_next):
   R.test_build_cnn_residual_pool_instance_vs_torch('R,C3-8,R,P2,R', 'batch', 'max', 8)
   R.test_build_cnn_residual_pool_instance_vs_torch('I4,C3-4,R,P3', 'instance', 'avg', 9)
+
+
+@needs_tc
+def test_error_compensated_tensor_core_mode(emul_next, monkeypatch):
+  """ops.set_conv_math('tf32x3') on the functional tensor-core model: split kernel, generator
+  forward at 1e-4 of the fp32 reference (plain TF32: 2.7e-3), gradients and the reference's two
+  training iterations within the exact-fp32 tests' tolerances."""
+  R.test_split_tf32_kernel()
+  R.test_tf32x3_generator_forward_meets_the_fp32_bar()
+  R.test_tf32x3_gradients_and_training_iterations_meet_the_fp32_bar(monkeypatch)

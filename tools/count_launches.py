@@ -54,11 +54,12 @@ def main():
                          ('pack-both', {}, {'PACK_BOTH': True}),
                          ('flat Adam', {'fused_adam': 'flat'}, {}),
                          ('kcc weights, torch Adam', {'weights': 'kcc'}, {}),
-                         ('kcc weights, flat Adam', {'weights': 'kcc', 'fused_adam': 'flat'}, {})):
+                         ('kcc weights, flat Adam', {'weights': 'kcc', 'fused_adam': 'flat'}, {}),
+                         ("error-compensated ('tf32x3')", {}, {'MATH': 'tf32x3'})):
     null = NullLib(real)
     _lib._lib = null
     ops.PACK_BOTH = bool(env.get('PACK_BOTH'))
-    ops.set_conv_math('tf32')
+    ops.set_conv_math(env.get('MATH', 'tf32'))
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
       model = Sg2ImModel(vocab, **bench.model_kwargs(cfg))
@@ -71,9 +72,10 @@ def main():
     c = null.calls
     total = sum(c.values())
     print('%-40s %4d library calls' % (label, total))
-    for k, v in c.most_common(8):
+    for k, v in c.most_common(10):
       print('    %-32s %4d' % (k, v))
   ops.PACK_BOTH = False
+  ops.set_conv_math('fp32')
 
 
 if __name__ == '__main__':

@@ -28,6 +28,7 @@ group halosmall 300 "small_image_halo"
 group halopair 300 "cta_pair_halo"
 group steps 600 "train_step_with"
 group factory 300 "pool2d or instance_norm or build_cnn_residual"
+group x3 600 "split_tf32 or tf32x3"
 grep -E "^exit|passed|failed" $LOG
 echo "== tcgen05 issue-rate probe" >> $LOG
 (timeout 120 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I sg2im_b200/csrc \
@@ -57,6 +58,8 @@ echo "== bench small-image halo kernel (8-row maps)" >> gpurun_out/r02_first.log
 [ "$RC_halosmall" = 0 ] && SG2IM_HALO_SMALL=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halosmall.json 2>> gpurun_out/r02_first.log
 echo "== bench CTA-pair halo kernel (cta_group::2)" >> gpurun_out/r02_first.log
 [ "$RC_halopair" = 0 ] && SG2IM_HALO_PAIR=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_halopair.json 2>> gpurun_out/r02_first.log
+echo "== bench error-compensated tensor-core mode (tf32x3: the 1e-3 parity bar on tcgen05)" >> gpurun_out/r02_first.log
+[ "$RC_x3" = 0 ] && timeout 300 python bench.py --no-cpu-baseline --math tf32x3 > gpurun_out/r02_bench_tf32x3.json 2>> gpurun_out/r02_first.log
 echo "== bench pack-both" >> gpurun_out/r02_first.log
 SG2IM_PACK_BOTH=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r02_bench_packboth.json 2>> gpurun_out/r02_first.log
 echo "== bench weights in the gradient layout (no pack / unpack)" >> gpurun_out/r02_first.log
