@@ -203,17 +203,35 @@ def split_tf32(x, parts, separate=False):
   return out
 
 
-def _rn_tf32_host(t):
-  """Round-to-nearest TF32 of a (small: weights) tensor with integer ops, ties away from zero
-  like cvt.rna."""
-  u = t.contiguous().view(torch.int32)
-  finite = (u & 0x7f800000) != 0x7f800000
-  return torch.where(finite, (u + 0x1000) & ~0x1fff, u).view(torch.float32)
+def _w3_fwd(w):
+  """OIHW weight (or the channel-prefix view weight[:, :Ci] of a contiguous one) ->
+  cat([hi, hi, lo], dim=1), shape (Co, 3*Ci, KH, KW): the forward operand of 'tf32x3'.  One
+  launch of the split kernel: per output channel the Ci*KH*KW floats are one row."""
+  Co, Ci, KH, KW = w.shape
+  T = KH * KW
+  if not (w.stride(3) == 1 and w.stride(2) == KW and w.stride(1) == T and w.stride(0) >= Ci * T):
+    w = w.contiguous()
+  C = Ci * T
+  out = torch.empty(Co, 3 * Ci, KH, KW, dtype=torch.float32, device=w.device)
+  base = out.data_ptr()
+  _call_b(16 * Co * C, 'sg2im_split_tf32', _p(w), Co, C, w.stride(0), base, 3 * C,
+          base + 8 * C, 3 * C, base + 4 * C, 3 * C, _stream())
+  _count()
+  return out
 
 
-def _split_weight(w):
-  hi = _rn_tf32_host(w)
-  return hi, w - hi
+def _w3_dgrad(weight):
+  """OIHW weight -> cat([hi, hi, lo], dim=0), shape (3*Co, Ci, KH, KW): the data-gradient
+  operand of 'tf32x3' (its reduction runs over the output channels)."""
+  weight = weight.contiguous()
+  Co, Ci, KH, KW = weight.shape
+  n = weight.numel()
+  out = torch.empty(3 * Co, Ci, KH, KW, dtype=torch.float32, device=weight.device)
+  base = out.data_ptr()
+  _call_b(16 * n, 'sg2im_split_tf32', _p(weight), 1, n, n, base, n, base + 8 * n, n,
+          base + 4 * n, n, _stream())
+  _count()
+  return out
 
 
 def _pixel_stride(x):
@@ -552,8 +570,7 @@ class Conv(torch.autograd.Function):
           and _tc_shape_ok(x.size(0), x.size(1), x.size(2), 3 * Ci, KH, KW, pad, Co, (Hout, Wout)))
     if x3:
       # error-compensated operands, one launch: [hi_x | lo_x | hi_x] * [hi_w | hi_w | lo_w]
-      w_hi, w_lo = _split_weight(w_used)
-      y = conv_tc(split_tf32(x, 3), pack_tc_fwd(torch.cat([w_hi, w_hi, w_lo], 1)), bias, KH, KW,
+      y = conv_tc(split_tf32(x, 3), pack_tc_fwd(_w3_fwd(w_used)), bias, KH, KW,
                   pad, Co, act, slope, out_hw=(Hout, Wout),
                   stats=stats_out if fused_stats else None)
     elif CONV_MATH == 'tf32' and conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
@@ -602,8 +619,7 @@ class Conv(torch.autograd.Function):
       if (ctx.x3 and KH == KW and pad_t >= 0 and stride == 1 and Co % 4 == 0
           and _tc_shape_ok(dy.size(0), dy.size(1), dy.size(2), 3 * Co, KH, KW, pad_t, Ci,
                            (x.size(1), x.size(2)))):
-        w_hi, w_lo = _split_weight(weight)
-        dx = conv_tc(split_tf32(dy, 3), pack_tc_dgrad(torch.cat([w_hi, w_hi, w_lo], 0), Ci), None,
+        dx = conv_tc(split_tf32(dy, 3), pack_tc_dgrad(_w3_dgrad(weight), Ci), None,
                      KH, KW, pad_t, Ci, tag='conv_dgrad_tc', out_hw=(x.size(1), x.size(2)))
       elif (not ctx.x3 and KH == KW and pad_t >= 0 and stride == 1
             and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
