@@ -34,6 +34,10 @@ CONFIGS = [
     dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=1,
          refinement_dims=(16, 8), mask_size=8, layout_noise_dim=4, image_size=(16, 16),
          normalization='instance'),
+    # SURVEY §8d C4 shape in miniature: a SIX-stage refinement network (VG-256 has one stage more
+    # than the 128x128 default; check_args only needs H // 2^stages >= 1, train.py:153-158)
+    dict(embedding_dim=8, gconv_dim=8, gconv_hidden_dim=16, gconv_num_layers=2,
+         refinement_dims=(16, 16, 8, 8, 8, 4), mask_size=16, layout_noise_dim=4, image_size=(64, 64)),
 ]
 
 
