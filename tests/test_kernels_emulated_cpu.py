@@ -494,3 +494,55 @@ def test_act_backward_with_bias_gradient_source_on_cpu(api, M, C):
   want = torch.where(y > 0, dy, dy * 0.2)
   assert torch.equal(dx, want)
   assert torch.allclose(db - 2.0, want.double().sum(0).float(), rtol=1e-5, atol=1e-4)
+
+
+# ---- csrc/pool.cu, csrc/split.cu: direct C-ABI calls (so tools/emul_sanitize.sh covers them)
+
+@pytest.mark.parametrize('N,H,W,C,f,mode', [(2, 8, 8, 8, 2, 1), (3, 13, 9, 6, 3, 1), (2, 7, 10, 5, 2, 0),
+                                            (1, 4, 4, 4, 4, 0), (1, 9, 9, 12, 3, 1)])
+def test_pool2d_kernels(lib, N, H, W, C, f, mode):
+  lib.sg2im_pool2d_fwd.argtypes = [_ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr]
+  lib.sg2im_pool2d_bwd.argtypes = [_ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr]
+  g = torch.Generator().manual_seed(H * 31 + C)
+  x = (torch.randn(N, C, H, W, generator=g) * 2).round() / 2          # exact ties inside windows
+  xr = x.clone().requires_grad_(True)
+  want = (F.avg_pool2d if mode == 0 else F.max_pool2d)(xr, f, f)
+  dy = torch.randn(want.shape, generator=g)
+  want.backward(dy)
+  h = x.permute(0, 2, 3, 1).contiguous()
+  y = torch.full((N, H // f, W // f, C), float('nan'))
+  _ok(lib, lib.sg2im_pool2d_fwd(_p(h), N, H, W, C, f, mode, _p(y), None))
+  dx = torch.zeros(N, H, W, C)
+  dyh = dy.permute(0, 2, 3, 1).contiguous()            # keep alive across the call
+  _ok(lib, lib.sg2im_pool2d_bwd(_p(dyh), _p(h), N, H, W, C, f, mode, _p(dx), None))
+  if mode == 1:
+    assert torch.equal(y.permute(0, 3, 1, 2), want.detach())
+    assert torch.equal(dx.permute(0, 3, 1, 2), xr.grad)
+  else:
+    assert rel_err(y.permute(0, 3, 1, 2), want.detach()) < 1e-6
+    assert rel_err(dx.permute(0, 3, 1, 2), xr.grad) < 1e-6
+  assert lib.sg2im_pool2d_fwd(_p(h), N, H, W, C, H + 1, mode, _p(y), None) != 0     # empty output refused
+
+
+@pytest.mark.parametrize('rows,C,xs', [(37, 12, 12), (5, 6, 20), (1, 1000, 1000), (64, 4, 8)])
+def test_split_tf32_kernel(lib, rows, C, xs):
+  lib.sg2im_split_tf32.argtypes = [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr]
+  g = torch.Generator().manual_seed(rows + C)
+  buf = torch.randn(rows, xs, generator=g) * 10.0 ** torch.randint(-4, 5, (rows, xs), generator=g)
+  buf[0, 0] = 0.0
+  x = buf[:, :C]
+  out = torch.full((rows, 3 * C), float('nan'))
+  base = out.data_ptr()
+  _ok(lib, lib.sg2im_split_tf32(_p(buf), rows, C, xs, base, 3 * C, base + 4 * C, 3 * C, base + 8 * C,
+                               3 * C, None))
+  hi, lo, hi2 = out[:, :C], out[:, C:2 * C], out[:, 2 * C:]
+  assert torch.equal(hi, hi2) and torch.equal(hi + lo, x)
+  assert bool(((hi.contiguous().view(torch.int32) & 0x1fff) == 0).all())
+  assert bool((lo.abs() <= x.abs() * 2.0 ** -11 * 1.0001).all())
+  # round to NEAREST: |x - hi| never exceeds half a TF32 ulp of x
+  ulp = 2.0 ** (torch.floor(torch.log2(x.abs().clamp(min=1e-30))) - 10)
+  assert bool((lo.abs() <= 0.5 * ulp * 1.0001).all())
+  only_lo = torch.full((rows, C), float('nan'))
+  _ok(lib, lib.sg2im_split_tf32(_p(buf), rows, C, xs, None, 0, _p(only_lo), C, None, 0, None))
+  assert torch.equal(only_lo, lo)
+  assert lib.sg2im_split_tf32(_p(buf), rows, C, xs, None, 0, None, 0, None, 0, None) != 0
