@@ -287,6 +287,16 @@ int sg2im_layout_bwd(const float* dout, int64_t dout_cstride,
                      int64_t H, int64_t W, int align_corners,
                      float* dvecs, float* dmasks, sg2im_stream_t stream);
 
+/* dboxes[o,0:4] = d(loss)/d(x0,y0,x1,y1) of object o through the sampling grid
+ * (sg2im/layout.py:94-128 + F.grid_sample's grid gradient); only reached when the generator
+ * trains on its predicted boxes (sg2im/model.py:151-160, no boxes_gt).  Every entry of dboxes
+ * is written.  masks NULL => the constant 8x8 ones image of boxes_to_layout. */
+int sg2im_layout_bwd_boxes(const float* dout, int64_t dout_cstride,
+                           const float* vecs, const float* boxes, const float* masks, int64_t M,
+                           const int64_t* obj_to_img, int64_t N, int64_t O, int64_t D,
+                           int64_t H, int64_t W, int align_corners, float* dboxes,
+                           sg2im_stream_t stream);
+
 /* ----------------------------------------------------------------- crop --
  * crop_bbox_batch (sg2im/bilinear.py:28-132,249-278): out[b,i,j,c] = bilinear
  * sample (zeros padding) of feats[idx[b]] at X_j = (1-a_j)(2x0-1)+a_j(2x1-1),

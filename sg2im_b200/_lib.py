@@ -52,6 +52,8 @@ SIGNATURES = {
                                 _ptr, _f32, _int, _int, _ptr, _ptr, _ptr, _ptr, _ptr],
   'sg2im_avgpool2_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr],
   'sg2im_avgpool2_bwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _ptr],
+  'sg2im_layout_bwd_boxes': [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
+                             _ptr, _ptr],
   'sg2im_split_tf32': [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr],
   'sg2im_pool2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr],
   'sg2im_pool2d_bwd': [_ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr],

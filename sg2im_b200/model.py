@@ -121,8 +121,8 @@ class Sg2ImModel(nn.Module):
     elif self.layout_noise_dim == 0:
       noise = None
 
-    if boxes_gt is None and torch.is_grad_enabled() and layout_boxes.requires_grad:
-      layout_boxes = layout_boxes.detach()      # box gradients: see ops.Layout.backward
+    # without boxes_gt the image loss reaches box_net through the sampling grid
+    # (model.py:151-160): ops.LayoutStack.backward returns the box gradient
     bufs = ops.LayoutStack.apply(obj_vecs, layout_boxes, layout_masks, obj_to_img, N, H, W,
                                  noise, _layout.ALIGN_CORNERS,
                                  tuple(self.refinement_net.stage_extras()))

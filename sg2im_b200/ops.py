@@ -1018,10 +1018,6 @@ class Layout(torch.autograd.Function):
   def backward(ctx, dout):
     vecs, boxes, masks, obj_to_img = ctx.saved_tensors
     N, H, W, M, align = ctx.cfg
-    if ctx.needs_input_grad[1]:
-      raise NotImplementedError(
-          'sg2im_b200: gradient w.r.t. layout boxes is outside the accelerated training path '
-          '(scripts/train.py always passes boxes_gt, train.py:525-528)')
     dout = dout.contiguous()
     O, D = vecs.shape
     dvecs = torch.zeros_like(vecs)
@@ -1032,7 +1028,21 @@ class Layout(torch.autograd.Function):
             'sg2im_layout_bwd', _p(dout), dout.size(3), _p(vecs), _p(boxes), _p(masks), M,
             _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
     _count()
-    return dvecs, None, dmasks, None, None, None, None, None, None
+    dboxes = _layout_dboxes(ctx, dout, vecs, boxes, masks, M, obj_to_img, N, H, W, align)
+    return dvecs, dboxes, dmasks, None, None, None, None, None, None
+
+
+def _layout_dboxes(ctx, dout, vecs, boxes, masks, M, obj_to_img, N, H, W, align):
+  """Gradient w.r.t. the boxes (training on predicted boxes, model.py:151-160) or None."""
+  if not ctx.needs_input_grad[1]:
+    return None
+  O, D = vecs.shape
+  dboxes = torch.empty(O, 4, dtype=torch.float32, device=vecs.device)
+  _call_b(4 * N * H * W * D + 4 * O * (D + 8), 'sg2im_layout_bwd_boxes', _p(dout), dout.size(3),
+          _p(vecs), _p(boxes), _p(masks), M, _p(obj_to_img), N, O, D, H, W, int(align), _p(dboxes),
+          _stream())
+  _count()
+  return dboxes
 
 
 def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners, out,
@@ -1087,10 +1097,6 @@ class LayoutStack(torch.autograd.Function):
   def backward(ctx, *douts):
     vecs, boxes, masks, obj_to_img = ctx.saved_tensors
     N, H, W, C, align = ctx.cfg
-    if ctx.needs_input_grad[1]:
-      raise NotImplementedError(
-          'sg2im_b200: gradient w.r.t. layout boxes is outside the accelerated training path '
-          '(scripts/train.py always passes boxes_gt, train.py:525-528)')
     L = len(douts)
     g = [d.contiguous() for d in douts]
     # the stage gradients are private temporaries of this backward pass (fresh
@@ -1107,7 +1113,8 @@ class LayoutStack(torch.autograd.Function):
             'sg2im_layout_bwd', _p(g[L - 1]), g[L - 1].size(3), _p(vecs), _p(boxes), _p(masks), M,
             _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
     _count()
-    return dvecs, None, dmasks, None, None, None, None, None, None, None
+    dboxes = _layout_dboxes(ctx, g[L - 1], vecs, boxes, masks, M, obj_to_img, N, H, W, align)
+    return dvecs, dboxes, dmasks, None, None, None, None, None, None, None
 
 
 class Crop(torch.autograd.Function):

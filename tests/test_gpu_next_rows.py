@@ -896,3 +896,74 @@ def test_tf32x3_gradients_and_training_iterations_meet_the_fp32_bar(monkeypatch)
   _with_math('tf32x3', G.test_generator_gradients_vs_oracle)
   _with_math('tf32x3', G.test_two_training_iterations_match_reference)
   _with_math('tf32x3', G.test_discriminators_forward)
+
+
+# ---- gradient w.r.t. the layout boxes (csrc/layout_boxes.cu): the generator trained on its own
+# predicted boxes (Sg2ImModel.forward without boxes_gt, sg2im/model.py:151-160)
+
+@pytest.mark.parametrize('with_masks,align,O,N,D,M,H,W,nc', [
+    (True, False, 9, 3, 16, 8, 24, 20, 0), (False, False, 7, 2, 12, 0, 16, 16, 4),
+    (True, True, 6, 2, 8, 5, 12, 18, 0), (True, False, 5, 2, 132, 16, 32, 32, 0)])
+def test_layout_gradient_wrt_boxes(with_masks, align, O, N, D, M, H, W, nc):
+  from oracle import sg2im_oracle as orc
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(O * 7 + D)
+  vecs = torch.randn(O, D, generator=g)
+  xy = torch.rand(O, 2, generator=g) * 0.5
+  boxes = torch.cat([xy, xy + 0.15 + 0.35 * torch.rand(O, 2, generator=g)], 1)
+  boxes[0] = torch.tensor([-0.1, 0.2, 0.7, 1.3])              # partly outside the image
+  masks = torch.rand(O, M, M, generator=g) if with_masks else None
+  o2i = torch.sort(torch.randint(0, N, (O,), generator=g)).values
+  noise = torch.randn(N, nc, H, W, generator=g) if nc else None
+  br = boxes.clone().requires_grad_(True)
+  vr = vecs.clone().requires_grad_(True)
+  if with_masks:
+    want = orc.masks_to_layout(vr, br, masks, o2i, H, W, N, align_corners=align)
+  else:
+    want = orc.boxes_to_layout(vr, br, o2i, H, W, N, align_corners=align)
+  wgt = torch.randn(want.shape, generator=g)
+  (want * wgt).sum().backward()
+  bm = boxes.clone().to(dev()).requires_grad_(True)
+  vm = vecs.clone().to(dev()).requires_grad_(True)
+  got = ops.Layout.apply(vm, bm, None if masks is None else masks.to(dev()), o2i.to(dev()), N, H, W,
+                         None if noise is None else noise.to(dev()), align)
+  (got[..., :D] * wgt.permute(0, 2, 3, 1).to(dev())).sum().backward()
+  assert rel_err(got[..., :D].detach().cpu().permute(0, 3, 1, 2), want.detach()) < TOL
+  assert rel_err(vm.grad.cpu(), vr.grad) < TOL
+  assert rel_err(bm.grad.cpu(), br.grad) < 5 * TOL, (bm.grad.cpu(), br.grad)
+
+
+def test_generator_trains_on_predicted_boxes():
+  """No boxes_gt: the layout is built from boxes_pred and the image loss reaches box_net and the
+  graph convolution through the sampling grid (model.py:151-160).  Parameter gradients vs the
+  oracle's autograd."""
+  import test_gpu_model as G
+  from oracle import sg2im_oracle as orc
+  g = load_golden('generator.pt')
+  imgs, objs, boxes, triples, o2i, _ = g['batch']
+  kw = g['kwargs']
+  N = imgs.size(0)
+  noise = G._noise(5, N, kw['layout_noise_dim'], kw['image_size'])
+  sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k
+            else v.clone()) for k, v in g['sd'].items()}
+  ref = orc.generator_forward(sd, kw['image_size'], objs, triples, o2i, boxes_gt=None, noise=noise,
+                              training=True, num_imgs=N)
+  wimg = torch.randn(ref[0].shape, generator=torch.Generator().manual_seed(9))
+  (ref[0] * wimg).sum().backward()
+  m = G._build_generator(g)
+  if m.box_net[0].weight.device != dev():
+    m = m.to(dev())
+  m.train()
+  d = dev()
+  out = m(objs.to(d), triples.to(d), o2i.to(d), boxes_gt=None, noise=noise.to(d), num_imgs=N)
+  (out[0] * wimg.to(d)).sum().backward()
+  assert rel_err(out[0].detach().cpu(), ref[0].detach()) < TOL
+  seen_box = False
+  for k, p in m.named_parameters():
+    rg = sd[k].grad
+    if rg is None or '.net.0.bias' in k or '.net.3.bias' in k:
+      continue
+    if k.startswith('box_net'):
+      seen_box = seen_box or float(rg.abs().max()) > 0
+    assert rel_err(p.grad.cpu(), rg) < 10 * TOL, (k, rel_err(p.grad.cpu(), rg))
+  assert seen_box                                  # box_net is reached ONLY through the layout here

@@ -546,3 +546,29 @@ def test_split_tf32_kernel(lib, rows, C, xs):
   _ok(lib, lib.sg2im_split_tf32(_p(buf), rows, C, xs, None, 0, _p(only_lo), C, None, 0, None))
   assert torch.equal(only_lo, lo)
   assert lib.sg2im_split_tf32(_p(buf), rows, C, xs, None, 0, None, 0, None, 0, None) != 0
+
+
+@pytest.mark.parametrize('with_masks,align', [(True, 0), (False, 0), (True, 1)])
+def test_layout_bwd_boxes_kernel(lib, with_masks, align):
+  """csrc/layout_boxes.cu vs torch's grid_sample grid gradient (direct C-ABI call)."""
+  from oracle import sg2im_oracle as orc
+  lib.sg2im_layout_bwd_boxes.argtypes = [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64,
+                                         _i64, _i64, _int, _ptr, _ptr]
+  g = torch.Generator().manual_seed(5 + align)
+  O, N, D, M, H, W, CS = 6, 2, 20, 6, 14, 11, 27
+  vecs = torch.randn(O, D, generator=g)
+  xy = torch.rand(O, 2, generator=g) * 0.5
+  boxes = torch.cat([xy, xy + 0.2 + 0.3 * torch.rand(O, 2, generator=g)], 1)
+  masks = torch.rand(O, M, M, generator=g) if with_masks else None
+  o2i = torch.tensor([0, 0, 0, 1, 1, 1])
+  br = boxes.clone().requires_grad_(True)
+  if with_masks:
+    want = orc.masks_to_layout(vecs, br, masks, o2i, H, W, N, align_corners=bool(align))
+  else:
+    want = orc.boxes_to_layout(vecs, br, o2i, H, W, N, align_corners=bool(align))
+  dout = torch.randn(N, H, W, CS, generator=g)                  # gradient slice of a wider buffer
+  (want * dout[..., :D].permute(0, 3, 1, 2)).sum().backward()
+  db = torch.full((O, 4), float('nan'))
+  _ok(lib, lib.sg2im_layout_bwd_boxes(_p(dout), CS, _p(vecs), _p(boxes), _p(masks), M, _p(o2i), N, O, D,
+                                     H, W, align, _p(db), None))
+  assert rel_err(db, br.grad) < 2e-4, (db, br.grad)

@@ -329,3 +329,15 @@ def test_error_compensated_tensor_core_mode(emul_next, monkeypatch):
   R.test_split_tf32_kernel()
   R.test_tf32x3_generator_forward_meets_the_fp32_bar()
   R.test_tf32x3_gradients_and_training_iterations_meet_the_fp32_bar(monkeypatch)
+
+
+def test_layout_gradient_wrt_boxes_kernel(emul_next, monkeypatch):
+  """csrc/layout_boxes.cu on the host: d(layout)/d(boxes) vs torch's grid_sample grid gradient
+  (masks / constant image, both align_corners conventions, D off the warp width, a box partly
+  outside the image), and the generator trained on its predicted boxes vs the oracle's autograd."""
+  import test_gpu_model as GM
+  monkeypatch.setattr(GM, 'dev', lambda: torch.device('cpu'))
+  for case in [(True, False, 9, 3, 16, 8, 24, 20, 0), (False, False, 7, 2, 12, 0, 16, 16, 4),
+               (True, True, 6, 2, 8, 5, 12, 18, 0), (True, False, 5, 2, 132, 16, 32, 32, 0)]:
+    R.test_layout_gradient_wrt_boxes(*case)
+  R.test_generator_trains_on_predicted_boxes()

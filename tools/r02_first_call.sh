@@ -29,6 +29,7 @@ group halopair 300 "cta_pair_halo"
 group steps 600 "train_step_with"
 group factory 300 "pool2d or instance_norm or build_cnn_residual"
 group x3 600 "split_tf32 or tf32x3"
+group boxes 300 "wrt_boxes or predicted_boxes"
 grep -E "^exit|passed|failed" $LOG
 echo "== tcgen05 issue-rate probe" >> $LOG
 (timeout 120 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I sg2im_b200/csrc \
