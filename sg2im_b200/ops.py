@@ -262,7 +262,7 @@ def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
 
 
 def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
-            tag='conv_fwd_tc', out_hw=None, stats=None, round_out=False):
+            tag='conv_fwd_tc', out_hw=None, stats=None, round_out=False, flops_div=1):
   """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
   w_tc packed [KH*KW][Cout][Cin]; out_hw: explicit output size (reads outside
   the input are zero)."""
@@ -271,7 +271,8 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
   Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
   if out is None:
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
-  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
+  # flops_div: the 'tf32x3' route issues 3x the MMAs for the same ALGORITHMIC work
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW / flops_div, (N, H, W, C, Cout, KH, 1)):
     _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Hout, Wout,
           Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _p(stats),
           int(round_out), _stream())
@@ -328,7 +329,7 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   return grad
 
 
-def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None):
+def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None, flops_div=1):
   """Returns dw packed (KH*KW*Cin, Cout).  accumulate_into: a contiguous buffer of that size
   the kernels ADD into (they combine partial tiles with atomics anyway) instead of a fresh
   zeroed one — e.g. the parameter's slice of the flat gradient bucket.  tc: use the tensor-core
@@ -348,7 +349,7 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None):
     cs = _pixel_stride(x)
     if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
         N, Hin, Win, Cin, cs, KH, KW, S, P, Hout, Wout, Cout)):
-      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
+      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW / flops_div,
                  (N, Hin, Win, Cin, Cout, KH, S)):
         _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Hout, Wout,
               Cout, _p(dw), _stream())
@@ -380,8 +381,8 @@ def conv_wgrad_x3(x, dy, KH, KW, P):
   T = KH * KW
   x2 = split_tf32(x, 2)
   dy_hi, dy_lo = split_tf32(dy, 2, separate=True)
-  a = conv_wgrad(x2, dy_hi, KH, KW, 1, P, tc=True).view(T, 2 * Ci, Co)
-  b = conv_wgrad(x2[..., :Ci], dy_lo, KH, KW, 1, P, tc=True).view(T, Ci, Co)
+  a = conv_wgrad(x2, dy_hi, KH, KW, 1, P, tc=True, flops_div=3).view(T, 2 * Ci, Co)
+  b = conv_wgrad(x2[..., :Ci], dy_lo, KH, KW, 1, P, tc=True, flops_div=3).view(T, Ci, Co)
   return (a[:, :Ci] + a[:, Ci:] + b).reshape(T * Ci, Co)
 
 
@@ -572,7 +573,7 @@ class Conv(torch.autograd.Function):
       # error-compensated operands, one launch: [hi_x | lo_x | hi_x] * [hi_w | hi_w | lo_w]
       y = conv_tc(split_tf32(x, 3), pack_tc_fwd(_w3_fwd(w_used)), bias, KH, KW,
                   pad, Co, act, slope, out_hw=(Hout, Wout),
-                  stats=stats_out if fused_stats else None)
+                  stats=stats_out if fused_stats else None, flops_div=3)
     elif CONV_MATH == 'tf32' and conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
       if (PACK_BOTH and ctx.needs_input_grad[0] and KH == KW and stride == 1
           and KH - 1 - pad >= 0):
@@ -620,7 +621,8 @@ class Conv(torch.autograd.Function):
           and _tc_shape_ok(dy.size(0), dy.size(1), dy.size(2), 3 * Co, KH, KW, pad_t, Ci,
                            (x.size(1), x.size(2)))):
         dx = conv_tc(split_tf32(dy, 3), pack_tc_dgrad(_w3_dgrad(weight), Ci), None,
-                     KH, KW, pad_t, Ci, tag='conv_dgrad_tc', out_hw=(x.size(1), x.size(2)))
+                     KH, KW, pad_t, Ci, tag='conv_dgrad_tc', out_hw=(x.size(1), x.size(2)),
+                     flops_div=3)
       elif (not ctx.x3 and KH == KW and pad_t >= 0 and stride == 1
             and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
         w_dgrad = ctx.w_dgrad if ctx.w_dgrad is not None else pack_tc_dgrad(weight, Ci)
