@@ -78,6 +78,10 @@ ARGS="--adam flat"
 [ "$RC_kcc" = 0 ] && [ "$RC_steps" = 0 ] && ARGS="$ARGS --weights kcc"
 echo "all: $ALL $ARGS" >> gpurun_out/r02_first.log
 env $ALL timeout 300 python bench.py --no-cpu-baseline $ARGS > gpurun_out/r02_bench_all.json 2>> gpurun_out/r02_first.log
+echo "== the other configurations of BASELINE.json (C2 COCO-64, C4 VG-256 six-stage CRN, C5 dense graphs)" >> gpurun_out/r02_first.log
+for wl in coco64 vg256 dense128; do
+  timeout 300 python bench.py --no-cpu-baseline --workload $wl --steps 20 --warmup 5 > gpurun_out/r02_bench_wl_$wl.json 2>> gpurun_out/r02_first.log
+done
 echo "== conv tile sweep" >> gpurun_out/r02_first.log
 timeout 300 python tools/sweep_conv.py --out gpurun_out/r02_sweep_conv.json >> gpurun_out/r02_first.log 2>&1
 echo "== kernel table (BN v2)" >> gpurun_out/r02_first.log
