@@ -38,7 +38,7 @@ class NullLib(object):
 
 
 def main():
-  cfg = dict(CONFIGS['vg128'])
+  cfg = dict(CONFIGS[os.environ.get('WORKLOAD', 'vg128')])
   cfg['N'] = int(os.environ.get('N', 4))                 # launch counts do not depend on the batch size
   real = ctypes.CDLL(build_lib())
   for name, sig in _lib.SIGNATURES.items():
