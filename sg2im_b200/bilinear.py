@@ -23,3 +23,20 @@ def crop_bbox(feats, bbox, HH, WW=None, backend='cudnn'):
   import torch
   idx = torch.arange(feats.size(0), device=feats.device, dtype=torch.int64)
   return crop_bbox_batch(feats, bbox, idx, HH, WW, backend)
+
+
+def crop_bbox_batch_cudnn(feats, bbox, bbox_to_feats, HH, WW=None):
+  """sg2im/bilinear.py:69-100 — the reference groups the boxes by image, crops per image and
+  inverse-permutes; the gather kernel needs none of that, so this is crop_bbox_batch."""
+  return crop_bbox_batch(feats, bbox, bbox_to_feats, HH, WW)
+
+
+def tensor_linspace(start, end, steps=10):
+  """sg2im/bilinear.py:249-278: out[..., i] = w0[i] * start + w1[i] * end with
+  w0 = linspace(1, 0, steps), w1 = linspace(0, 1, steps); result shape start.shape + (steps,).
+  Host helper (tiny tensors); the crop kernel evaluates the same expression per sample."""
+  import torch
+  assert start.size() == end.size()
+  w0 = torch.linspace(1, 0, steps=steps).to(start)
+  w1 = torch.linspace(0, 1, steps=steps).to(start)
+  return w0 * start.unsqueeze(-1) + w1 * end.unsqueeze(-1)

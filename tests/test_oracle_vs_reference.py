@@ -299,3 +299,24 @@ def test_layout_functions_mirror_vs_live_reference(pooling):
     assert rel_err(vm.grad, vr.grad) < TOL
   with pytest.raises(ValueError):
     mine.boxes_to_layout(vecs, boxes, o2i, H, W, pooling='max')
+
+
+def test_bilinear_helpers_mirror_vs_live_reference():
+  """sg2im/bilinear.py: tensor_linspace (bit for bit) and the crop entry points under their three
+  names (crop_bbox_batch, crop_bbox_batch_cudnn, crop_bbox), objects not grouped by image."""
+  import_reference()
+  from sg2im import bilinear as ref
+  from sg2im_b200 import bilinear as mine
+  from cpu_shim import cpu_ops
+  g = torch.Generator().manual_seed(23)
+  a, b = torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g)
+  assert torch.equal(mine.tensor_linspace(a, b, steps=7), ref.tensor_linspace(a, b, steps=7))
+  feats = torch.randn(3, 4, 12, 10, generator=g)
+  xy = torch.rand(6, 2, generator=g) * 0.5
+  boxes = torch.cat([xy, xy + 0.2 + 0.3 * torch.rand(6, 2, generator=g)], 1)
+  idx = torch.tensor([2, 0, 1, 0, 2, 1])
+  want = ref.crop_bbox_batch(feats, boxes, idx, 6, 5)
+  with cpu_ops():
+    assert rel_err(mine.crop_bbox_batch(feats, boxes, idx, 6, 5), want) < TOL
+    assert rel_err(mine.crop_bbox_batch_cudnn(feats, boxes, idx, 6, 5), want) < TOL
+    assert rel_err(mine.crop_bbox(feats, boxes[:3], 6), ref.crop_bbox(feats, boxes[:3], 6)) < TOL
