@@ -15,7 +15,8 @@ pytestmark = pytest.mark.skipif(shutil.which('g++') is None or not HAVE_TC,
 
 
 def test_fuzz_slice():
-  out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_tc_emulated.py'), '14', '7'],
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_tc_emulated.py'),
+                        '14' if os.environ.get('SG2IM_FULL_EMUL') == '1' else '7', '7'],
                        capture_output=True, text=True, timeout=900)
   assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
   assert 'all cases agree' in out.stdout
