@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2 (run under gpurun from the repo root):
-#   gpurun --timeout 2700 -- 'bash tools/r02_first_call.sh'      (about 25-30 GPU-minutes)
+#   gpurun --timeout 3000 -- 'bash tools/r02_first_call.sh'      (about 35-40 GPU-minutes)
 # 1. hardware validation of everything written after round 1's GPU budget ran out
 # 2. A/B of the opt-in kernels on the default bench
 # 3. tile sweep of the conv kernel over the step's shapes
