@@ -103,8 +103,21 @@ int sg2im_conv_igemm(int mode, const float* x, int64_t sxn, int64_t sxh, int64_t
  * round_out: write the outputs rounded to nearest TF32 (for outputs that feed another
  * tensor-core op: the hardware truncates its fp32 operands, which biases products toward
  * zero; RN-rounded operands are consumed exactly).
+ * math: the tensor-core arithmetic (same HBM traffic in all three; activations and weights stay
+ * fp32 in HBM):
+ *   SG2IM_MATH_TF32    kind::tf32 on the fp32 words as they are (2^-11 operand precision);
+ *   SG2IM_MATH_BF16X3  converter warps split every landed shared-memory tile into bf16 hi / mid
+ *                      halves and every fp32 product is issued as hi*hi + mid*hi + hi*mid on
+ *                      kind::f16 MMAs with fp32 accumulation (2^-17 operand precision: the mode
+ *                      that meets the 1e-3 bar against the fp32 reference,
+ *                      scripts/train.py:423), 1.5x the tensor-pipe time of TF32;
+ *   SG2IM_MATH_BF16    the same kernels issuing hi*hi only (plain bf16 operands, BASELINE.json
+ *                      configs[3]); round_out is ignored outside SG2IM_MATH_TF32.
  * sg2im_conv_tc_supported(): S == 1, Cin % 4 == 0, Cout % 4 == 0, 16-byte
  * aligned slices; otherwise sg2im_conv_tc returns -2 (use sg2im_conv_igemm). */
+#define SG2IM_MATH_TF32 0
+#define SG2IM_MATH_BF16X3 1
+#define SG2IM_MATH_BF16 2
 int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
                             int64_t x_cstride, int KH, int KW, int S, int P,
                             int64_t Hout, int64_t Wout, int64_t Cout, int64_t y_cstride,
@@ -112,7 +125,7 @@ int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t Cin,
 int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                   int64_t Cin, const float* w_tc, const float* bias, int KH, int KW, int P,
                   int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope, float* y,
-                  int64_t y_cstride, int64_t y_coff, double* stats, int round_out,
+                  int64_t y_cstride, int64_t y_coff, double* stats, int round_out, int math,
                   sg2im_stream_t stream);
 
 /* The same convolution with the weights taken straight from the WEIGHT-GRADIENT layout
@@ -123,12 +136,13 @@ int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int
  *   dgrad != 0  data gradient of that conv: call with x = dY, Cin = cols, Cout = rows used,
  *               P' = K-1-P; the kernel flips the tap index itself.
  * w_rows_full = row pitch of one tap (>= rows used: the CRN's first stage uses a channel prefix).
- * Opt-in: validated so far only under the functional tensor-core model of the CPU test suite. */
+ * Validated on the B200 (round 2): what TrainStep(weights='kcc') runs. */
 int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                       int64_t Cin, const float* w_kcc, int64_t w_rows_full, int dgrad,
                       const float* bias, int KH, int KW, int P, int64_t Hout, int64_t Wout,
                       int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
-                      int64_t y_coff, double* stats, int round_out, sg2im_stream_t stream);
+                      int64_t y_coff, double* stats, int round_out, int math,
+                      sg2im_stream_t stream);
 
 /* dw[(ky*KW+kx)*Cin + ci][co] += sum_{n,oy,ox} dy[n,oy,ox,co] *
  *      x[n, oy*S-P+ky, ox*S-P+kx, ci]      (dw must be zero-initialised: the
@@ -140,7 +154,8 @@ int sg2im_conv_wgrad(const float* x, int64_t sxn, int64_t sxh, int64_t sxw, int6
                      float* dw, sg2im_stream_t stream);
 
 /* Tensor-core weight gradient of a stride-1 convolution or a Linear
- * (tcgen05.mma kind::tf32, MN-major operands straight from NHWC, one smem halo
+ * (tcgen05.mma kind::tf32 or kind::f16 on in-kernel bf16 pairs — `math` as in sg2im_conv_tc —,
+ * MN-major operands straight from NHWC, one smem halo
  * tile serves all taps): dw[(ky*KW+kx)*Cin + ci][co] += sum_pix
  * x[pix+tap-P, ci] * dy[pix, co] over the Hout x Wout outputs; dw
  * zero-initialised by the caller (partial tiles are combined with vector
@@ -151,7 +166,7 @@ int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t C
                                   int64_t Hout, int64_t Wout, int64_t Cout);
 int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                         int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Hout,
-                        int64_t Wout, int64_t Cout, float* dw, sg2im_stream_t stream);
+                        int64_t Wout, int64_t Cout, float* dw, int math, sg2im_stream_t stream);
 
 /* Space-to-depth by 2 (and its adjoint): out[n, y/2, x/2, ((y&1)*2+(x&1))*C + c]
  * = x[n,y,x,c], zero padded to even H, W.  x addressed with element strides.
@@ -237,18 +252,6 @@ int sg2im_avgpool2_bwd(const float* dcoarse, int64_t dc_cstride, int64_t dc_coff
                        int64_t N, int64_t H, int64_t W, int64_t C,
                        float* dfine, int64_t df_cstride, int64_t df_coff, int accumulate,
                        sg2im_stream_t stream);
-
-/* TF32 hi / lo split of fp32 rows for the error-compensated tensor-core mode ('tf32x3'):
- * hi = round-to-nearest-TF32(x), lo = x - hi.  x: `rows` rows of C floats, row stride x_stride
- * (a channel-prefix view of a wider NHWC buffer is fine).  hi / lo / hi2 are optional
- * destinations (NULL = skip) with their own row strides: pass three pointers into one
- * (rows, 3C) buffer for the concatenated operand [hi | lo | hi], or separate tensors.  With
- * x3 = [hi_x | lo_x | hi_x] and w3 = [hi_w | hi_w | lo_w] along the input-channel axis, one
- * sg2im_conv_tc launch evaluates hi*hi + lo*hi + hi*lo with fp32 accumulation — the
- * reference's fp32 nn.Conv2d / nn.Linear arithmetic to ~2^-21 on the TF32 tensor core. */
-int sg2im_split_tf32(const float* x, int64_t rows, int64_t C, int64_t x_stride,
-                     float* hi, int64_t hi_stride, float* lo, int64_t lo_stride,
-                     float* hi2, int64_t hi2_stride, sg2im_stream_t stream);
 
 /* Non-overlapping pooling, NHWC contiguous: nn.MaxPool2d / nn.AvgPool2d(kernel_size = stride =
  * factor) as built by build_cnn's 'PX' token (sg2im/layers.py:195-201).  mode 0 = average,

@@ -26,13 +26,13 @@ SIGNATURES = {
   'sg2im_conv_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64, _i64,
                               _i64, _i64, _i64],
   'sg2im_conv_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _int, _int, _i64, _i64,
-                    _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
+                    _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
   'sg2im_conv_tc_kcc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr, _int, _int, _int,
-                        _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
+                        _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
   'sg2im_conv_wgrad_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64,
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,
-                          _i64, _ptr, _ptr],
+                          _i64, _ptr, _int, _ptr],
   'sg2im_pack_weights': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr],
   'sg2im_unpack_wgrad': [_ptr, _i64, _i64, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_s2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
@@ -54,7 +54,6 @@ SIGNATURES = {
   'sg2im_avgpool2_bwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _int, _ptr],
   'sg2im_layout_bwd_boxes': [_ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _int,
                              _ptr, _ptr],
-  'sg2im_split_tf32': [_ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr],
   'sg2im_pool2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr],
   'sg2im_pool2d_bwd': [_ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _ptr, _ptr],
   'sg2im_layout_fwd': [_ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int,

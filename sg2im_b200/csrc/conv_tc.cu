@@ -1,5 +1,5 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM convolution, stride 1, NHWC fp32
-// in HBM, TF32 multiply / fp32 accumulate in TMEM.
+// in HBM, fp32 accumulate in TMEM.
 //
 //   D[pixel, co] = sum_{tap, ci} X[pixel + tap - P, ci] * Wt[tap][co][ci]
 //
@@ -7,15 +7,21 @@
 //   128 B) per (tap, 32-channel block), fetched at the tap-shifted coordinate;
 //   the TMA unit zero-fills out-of-bounds pixels, which IS the conv padding, and
 //   lays rows out in the 128B-swizzled K-major form tcgen05 reads directly.
-// * B operand: weights pre-packed [tap][Cout][Cin] (K-major), 3-D TMA box.
-// * tcgen05.mma kind::tf32, M=128 x N=BN x K=8, one elected thread; fp32 data is
-//   consumed as-is (the tensor core ignores the low 13 mantissa bits), so there
-//   is no conversion pass and activations stay fp32 in HBM.
+// * B operand: weights [tap][Cout][Cin] (K-major, packed) or read in place from the
+//   weight-gradient layout [tap][Cin][Cout] (WMODE 1 / 2, below), 3-D TMA box.
+// * Arithmetic (template parameter MATH):
+//     0  kind::tf32, M=128 x N=BN x K=8: fp32 data consumed as-is (the tensor core ignores the
+//        low 13 mantissa bits) — 2^-11 operand precision, the fast labelled mode;
+//     1  kind::f16 on bf16 pairs, M=128 x N=BN x K=16: four converter warps split every landed
+//        tile in place into [bf16 hi | bf16 mid] (tc_common.cuh) and each fp32 product is
+//        issued as hi*hi + mid*hi + hi*mid (p.nprod = 3, 'bf16x3': 2^-17 operand precision —
+//        the mode that meets the 1e-3 parity bar against the fp32 reference) or as hi*hi only
+//        (p.nprod = 1, plain bf16).  HBM / L2 / TMA traffic is identical to mode 0.
 // * Accumulators double-buffered in TMEM (2 x BN columns) so the epilogue of tile
 //   i overlaps the MMAs of tile i+1; persistent CTAs, static tile striding.
 // * Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
 //   epilogue (tcgen05.ld -> bias/LeakyReLU -> 128-bit global stores into the
-//   destination channel slice).
+//   destination channel slice), warps 6-9 operand converters (MATH 1 only).
 // Replaces cuDNN's conv behind nn.Conv2d (sg2im/crn.py:41-45,80-82;
 // model.py:100) for the shapes that dominate the step.
 #include <cstdlib>
@@ -27,6 +33,7 @@ constexpr int TILE_M = 128;
 constexpr int KB_BYTES = 128;                 // 32 fp32 channels per k-block row
 constexpr int A_STAGE_BYTES = TILE_M * KB_BYTES;
 constexpr int NUM_THREADS = 192;
+constexpr int CONV_THREADS = 128;             // converter warps of the bf16 arithmetic
 
 struct TcParams {
   int N, Hout, Wout, Cin, Cout;
@@ -39,13 +46,16 @@ struct TcParams {
   int act; float slope;
   float* y; long long y_cstride, y_coff;
   double* stats;                   // optional [2*Cout] per-channel sum / sum of squares
-  int round_out;                   // write RN-TF32 values (output feeds another tensor-core op)
+  int round_out;                   // write RN-TF32 values (output feeds another tf32 tensor-core op)
+  int nprod;                       // MATH 1: products per fp32 multiply (3 = bf16x3, 1 = bf16)
 };
 
 using namespace tc;
 
 // K-major SWIZZLE_128B descriptors are assembled in the MMA warps as (lo, hi) words:
 // lo = start>>4 | LBO(=1, ignored)<<16, hi = SBO>>4 | version 1<<14 | layout 2<<29.
+// bf16 tiles after the in-place split: a 128-byte row = [hi: 2 K-steps of 32 B | mid: 2 K-steps],
+// so hi sits at +0 / +2 and mid at +4 / +6 (16-byte units) of the same descriptor.
 
 template <int BN>
 struct Cfg {
@@ -54,23 +64,25 @@ struct Cfg {
   static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;                     // 128 / 256 / 512
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 + 8192 /*BN partials*/;
-  // instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
-  // N>>3 at bit 17, M>>4 at bit 24
+  // instruction descriptor: D=F32 (1<<4), A/B format at bits 7 / 10 (TF32 = 2, BF16 = 1), K-major
+  // both, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC =
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  static constexpr uint32_t IDESC16 =
+      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 };
 
 // WMODE selects where the B operand (weights) comes from:
-//   0  packed [tap][Cout][Cin] (K-major; sg2im_pack_weights)                — the validated default
+//   0  packed [tap][Cout][Cin] (K-major; sg2im_pack_weights)
 //   1  FORWARD straight from the weight-gradient layout [tap][Cin][Cout]: B is MN-major
-//      (32-co atoms of 32 ci rows, SWIZZLE_128B_BASE32B like the wgrad kernel's operands)
+//      (tf32: 32-co atoms of 32 ci rows, SWIZZLE_128B_BASE32B like the wgrad kernel's operands;
+//      bf16: the converters fold atom pairs into 64-co hi / mid atoms, plain SWIZZLE_128B)
 //   2  DATA GRADIENT straight from the same layout [tap][Cin_w][Cout_w]: conv-Cin = Cout_w is
 //      contiguous => K-major as in mode 0, only the tap index is flipped
 // Modes 1/2 remove every pack / unpack pass when the master weights live in that layout
-// (DESIGN.md §7b); they are opt-in (sg2im_conv_tc_kcc) and so far only run under the functional
-// tensor-core model of tests/emul/tc_emul.h.
-template <int BN, int WMODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// (sg2im_conv_tc_kcc; validated on the B200 in round 2).
+template <int BN, int WMODE, int MATH>
+__global__ void __launch_bounds__(NUM_THREADS + (MATH ? CONV_THREADS : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using C = Cfg<BN>;
@@ -85,6 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * C::STAGES;                      // [2]
   uint64_t* tempty = bars + 2 * C::STAGES + 2;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* ready = bars + 2 * C::STAGES + 5;                  // [STAGES] operands split (MATH 1)
   float* s_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][1024]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +108,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1);
+      if (MATH) mbar_init(&ready[i], CONV_THREADS / 32);
+    }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
     mbar_fence_init();
@@ -158,11 +174,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[s], ph);
+          mbar_wait(MATH ? &ready[s] : &full[s], ph);
           tc_fence_after();
           const uint32_t at = sA16 + (uint32_t)s * (A_STAGE_BYTES >> 4);
           const uint32_t bt = sB16 + (uint32_t)s * (C::B_STAGE_BYTES >> 4);
-          if constexpr (WMODE == 1) {
+          if constexpr (MATH == 1) {
+            // products hi*hi, mid*hi, hi*mid; two K = 16 steps (32 B) per 32-channel block
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+              if (pr >= p.nprod) break;
+              const uint32_t ao = pr == 1 ? 4u : 0u;
+              if constexpr (WMODE == 1) {
+                // B MN-major bf16: 64-co atoms (hi = even 4 KB atom of a pair, mid = odd), pairs
+                // 8 KB apart (LBO), 8 ci rows = 1 KB per group (SBO), 16 ci rows per K step
+                constexpr uint32_t IDESC_MN = C::IDESC16 | (1u << 16);
+                const uint32_t bm_hi = 64u | (1u << 14) | (2u << 29);
+                const uint32_t btm = ((bt + (pr == 2 ? 256u : 0u)) & 0xffffu) | ((8192u >> 4) << 16);
+                tc_mma_f16_lh(d_tmem, at + ao, d_hi, btm, bm_hi, IDESC_MN, (kb | pr) ? 1u : 0u, leader);
+                tc_mma_f16_lh(d_tmem, at + ao + 2, d_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
+              } else {
+                const uint32_t bo = pr == 2 ? 4u : 0u;
+                tc_mma_f16_lh(d_tmem, at + ao, d_hi, bt + bo, d_hi, C::IDESC16, (kb | pr) ? 1u : 0u, leader);
+                tc_mma_f16_lh(d_tmem, at + ao + 2, d_hi, bt + bo + 2, d_hi, C::IDESC16, 1u, leader);
+              }
+            }
+          } else if constexpr (WMODE == 1) {
             // B MN-major: atoms of 32 co (LBO = 4 KB apart), 8 ci rows = 1 KB per K step
             constexpr uint32_t IDESC_MN = C::IDESC | (1u << 16);
             const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);         // SBO 512 B, SWIZZLE_128B_BASE32B
@@ -172,10 +208,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_mma_tf32_lh(d_tmem, at + 4, d_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
             tc_mma_tf32_lh(d_tmem, at + 6, d_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
           } else {
-          tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
+            tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
           }
           tc_commit(&empty[s], leader);                    // frees the smem stage when the MMAs retire
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
@@ -184,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                // TMEM lane quadrant this warp may read
     const int r = q * 32 + lane;                           // tile row = TMEM lane
@@ -214,6 +250,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+  } else if constexpr (MATH == 1) {
+    // ===================== operand converters (warps 6..9) =====================
+    // every landed stage: the 128 A rows and the B rows (WMODE 1: the row pairs of adjacent
+    // 32-co atoms) are split in place, then each warp signals `ready`
+    const int ct = (int)threadIdx.x - 6 * 32;
+    int s = 0; uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        uint8_t* a = sA + s * A_STAGE_BYTES;
+        uint8_t* b = sB + s * C::B_STAGE_BYTES;
+        split_row_inplace(a + ct * 128);
+        if constexpr (WMODE == 1) {
+          for (int i = ct; i < BN / 2; i += CONV_THREADS) {
+            uint8_t* r0 = b + (i >> 5) * 8192 + (i & 31) * 128;
+            split_rowpair_inplace(r0, r0 + 4096);
+          }
+        } else {
+          for (int i = ct; i < BN; i += CONV_THREADS) split_row_inplace(b + i * 128);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
   }
 
   tc_fence_before();
@@ -229,204 +291,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
   }
 }
-
-// Cluster / TMA-multicast variant of conv_tc_kernel (opt-in: SG2IM_CONV_MC=1; DERIVED TEXTUALLY from the
-// kernel above, which stays byte-identical): the CS CTAs of a thread-block cluster take the CS
-// consecutive Cout tiles of one pixel tile in lockstep; rank 0 fetches every activation (A) tile
-// once and TMA-multicasts it into all of them, each CTA fetches only its own weight tile.  Same
-// protocol as conv_wgrad_tc_mc.cu: full[s] counts A (multicast) + own B bytes; `empty` is the
-// local release, empty_a[s] (count CS, rank 0's copy) collects every CTA's release of the A half
-// through a multicast tcgen05.commit; cluster barriers after init and before exit.  Meant for the
-// small-spatial / wide-channel stages where the per-tap kernel re-fetches A once per Cout tile.
-template <int BN, int WMODE, int CS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
-  using C = Cfg<BN>;
-  SG_DYN_SMEM(uint8_t, smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                          // STAGES x 16 KB
-  uint8_t* sB = smem + C::STAGES * A_STAGE_BYTES;              // STAGES x BN*128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;                                       // [STAGES]
-  uint64_t* empty = bars + C::STAGES;                          // [STAGES]
-  uint64_t* tfull = bars + 2 * C::STAGES;                      // [2]
-  uint64_t* tempty = bars + 2 * C::STAGES + 2;                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  uint64_t* empty_a = bars + 2 * C::STAGES + 5;                // [STAGES]: A-half releases, used on rank 0
-  float* s_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);   // [2][1024]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
-  // work unit = the CS tiles of a cluster: same pixels, CS consecutive Cout tiles (n_tiles % CS == 0)
-  const uint32_t rank = cluster_rank();
-  const int unit0 = (int)blockIdx.x / CS, unit_step = (int)gridDim.x / CS, units = total_tiles / CS;
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&empty_a[i], CS);
-    }
-    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tc_alloc(tmem_slot, (uint32_t)C::TMEM_COLS);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                              // every CTA's barriers exist before any remote signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // tile -> (n-tile over Cout fastest, so CTAs running together share A in L2)
-  auto decode = [&](int tile, int& nt, int& n0, int& y0, int& x0) {
-    nt = tile % p.n_tiles;
-    int m = tile / p.n_tiles;
-    int tw = m % p.tiles_w; m /= p.tiles_w;
-    int th = m % p.tiles_h; m /= p.tiles_h;
-    n0 = m * p.BI; y0 = th * p.BH; x0 = tw * p.BW;
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int unit = unit0; unit < units; unit += unit_step) {
-        int nt, n0, y0, x0;
-        decode(unit * CS + (int)rank, nt, n0, y0, x0);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          int ky = tap / p.KW, kx = tap - ky * p.KW;
-          mbar_wait(&empty[s], ph ^ 1);                      // own MMAs released the stage
-          if (rank == 0) mbar_wait(&empty_a[s], ph ^ 1);     // ... and every peer's released the A half
-          mbar_expect_tx(&full[s], C::STAGE_BYTES);
-          if (rank == 0)
-            tma_load_4d_mc(sA + s * A_STAGE_BYTES, &tmA, &full[s], (uint16_t)((1u << CS) - 1u), cb * 32,
-                           x0 + kx - p.P, y0 + ky - p.P, n0);
-          if constexpr (WMODE == 1) {
-#pragma unroll
-            for (int a = 0; a < BN / 32; ++a)
-              tma_load_3d(sB + s * C::B_STAGE_BYTES + a * 4096, &tmB, &full[s], nt * BN + a * 32,
-                          cb * 32, tap);
-          } else {
-            tma_load_3d(sB + s * C::B_STAGE_BYTES, &tmB, &full[s], cb * 32, nt * BN,
-                        WMODE == 2 ? p.KH * p.KW - 1 - tap : tap);
-          }
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
-    {
-      const uint32_t leader = lane == 0 ? 1u : 0u;
-      const uint32_t d_hi = 64u | (1u << 14) | (2u << 29);          // SBO 1024 B, v1, SWIZZLE_128B
-      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
-      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
-      int s = 0; uint32_t ph = 0;
-      int acc = 0; uint32_t acc_ph = 0;
-      for (int unit = unit0; unit < units; unit += unit_step) {
-        mbar_wait(&tempty[acc], acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t at = sA16 + (uint32_t)s * (A_STAGE_BYTES >> 4);
-          const uint32_t bt = sB16 + (uint32_t)s * (C::B_STAGE_BYTES >> 4);
-          if constexpr (WMODE == 1) {
-            // B MN-major: atoms of 32 co (LBO = 4 KB apart), 8 ci rows = 1 KB per K step
-            constexpr uint32_t IDESC_MN = C::IDESC | (1u << 16);
-            const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);         // SBO 512 B, SWIZZLE_128B_BASE32B
-            const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
-            tc_mma_tf32_lh(d_tmem, at, d_hi, btm, bm_hi, IDESC_MN, kb ? 1u : 0u, leader);
-            tc_mma_tf32_lh(d_tmem, at + 2, d_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
-            tc_mma_tf32_lh(d_tmem, at + 4, d_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
-            tc_mma_tf32_lh(d_tmem, at + 6, d_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
-          } else {
-          tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, kb ? 1u : 0u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 2, d_hi, bt + 2, d_hi, C::IDESC, 1u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 4, d_hi, bt + 4, d_hi, C::IDESC, 1u, leader);
-          tc_mma_tf32_lh(d_tmem, at + 6, d_hi, bt + 6, d_hi, C::IDESC, 1u, leader);
-          }
-          tc_commit(&empty[s], leader);                    // frees the smem stage when the MMAs retire
-          tc_commit_mc(&empty_a[s], (uint16_t)1);          // A half: tell rank 0
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
-        }
-        tc_commit(&tfull[acc], leader);                    // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
-    const int r = q * 32 + lane;                           // tile row = TMEM lane
-    const int img = r / (p.BH * p.BW);
-    const int hh = (r / p.BW) % p.BH, ww = r % p.BW;
-    int acc = 0; uint32_t acc_ph = 0;
-    for (int unit = unit0; unit < units; unit += unit_step) {
-      int nt, n0, y0, x0;
-      decode(unit * CS + (int)rank, nt, n0, y0, x0);
-      mbar_wait(&tfull[acc], acc_ph);
-      tc_fence_after();
-      const int n = n0 + img;
-      const bool valid = n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
-      float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
-                    p.y_coff + (long long)nt * BN;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        if (nt * BN + ch * 32 >= p.Cout) break;              // partial last N tile (warp-uniform)
-        float v[32];
-        tc_ld32(taddr + ch * 32, v);
-        epilogue_chunk(v, valid, nt * BN + ch * 32, p.Cout, p.bias, p.act, p.slope, yrow + ch * 32,
-                       p.stats ? s_part : nullptr, lane, p.round_out);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (p.stats) {
-    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
-      float a = s_part[c], b = s_part[1024 + c];
-      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
-    }
-  }
-  cluster_sync_all();                              // peers may still signal this CTA's barriers until here
-  if (warp == 1) {
-    tc_fence_after();
-    tc_dealloc(tmem_base, (uint32_t)C::TMEM_COLS);
-  }
-}
-
 
 // =============================================================================
-// Halo variant for KxK (K <= 3) stride-1 convs with narrow outputs (N tile 64):
-// the per-tap kernel above re-fetches every activation tile once per tap and
-// every weight tile once per pixel tile, which saturates the L2->SM fabric
-// (~10 TB/s, profiles/r01_prof_conv_tc_fwd.txt) long before the tensor pipe.
-// Here, per 32-channel block,
-//   * ONE TMA box brings the (16+KH-1) x (8+KW-1) pixel halo of an 8x16 tile;
-//     each tap's A operand is that tile at a row-shifted start address with an
-//     8-row-group stride of (8+KW-1) rows (tcgen05 swizzles on absolute smem
-//     address bits; shifted starts and SBO = 1280 B verified by
-//     tools/umma_probe.cu);
+// Halo / weight-stationary variant for narrow outputs (Cout tile of 64) on real
+// images (KH*KW > 1, H >= 16, W >= 8).  N = 64 MMAs are bound by the shared-memory
+// operand feed (48.1 cycles per 128x64 MMA measured, tools/umma_rate_probe.cu),
+// so the kernel minimises everything else: per 128x64 tile and tap the generic kernel
+// refills 16 KB (A) + 8 KB (B) of shared memory from L2, which caps it well below that.
+// Here
+//   * ONE TMA halo box per (pixel tile, 32-channel block) serves all KH*KW taps:
+//     the A tile of tap (ky,kx) is the same shared memory read with the matrix
+//     descriptor's start address shifted by (ky*pitch + kx) rows and a stride of
+//     `pitch` rows between 8-row groups (tile = 8 columns x 16 rows, so each
+//     8-row core group is one image row of 8 pixels; tcgen05 applies the 128B
+//     swizzle to the final address, so the shift is free — validated on the B200);
 //   * the KH*KW weight tiles are loaded once and reused by T = 4 pixel tiles
 //     whose accumulators sit side by side in TMEM (2 sets x 4 x 64 columns,
 //     so the epilogue of one group overlaps the MMAs of the next).
 // L2->SM bytes per MMA drop ~5x.  Warp roles: 0 = halo (A) producer, 1 = MMA
-// issuer + TMEM owner, 2 = weight (B) producer, 4-7 = epilogue.
+// issuer + TMEM owner, 2 = weight (B) producer, 4-7 = epilogue, 8-11 = operand
+// converters (bf16 arithmetic only: every halo box and weight tile is split once
+// and then read by all the taps / pixel tiles it serves).
 // =============================================================================
 constexpr int H_BN = 64, H_T = 4, H_BW = 8, H_BH = 16;
 constexpr int H_A_SLOT = 23 * 1024;           // 180 rows x 128 B = 23040, padded to 1 KB
@@ -434,7 +319,7 @@ constexpr int H_A_SLOTS = 3;
 constexpr int H_B_TILE = H_BN * KB_BYTES;     // 8 KB
 constexpr int H_MAX_TAPS = 9;
 constexpr int H_THREADS = 256;
-constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512 + 8192;
+constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 1024 + 8192;
 
 struct HaloParams {
   int N, Hout, Wout, Cin, Cout;
@@ -447,11 +332,11 @@ struct HaloParams {
   float* y; long long y_cstride, y_coff;
   double* stats;
   int round_out;
-  int ti;                          // images per pixel tile (small-image variant only)
+  int nprod;                       // MATH 1: 3 = bf16x3, 1 = bf16
 };
 
-template <int WMODE>                              // weight source, see conv_tc_kernel
-__global__ void __launch_bounds__(H_THREADS, 1)
+template <int WMODE, int MATH>                    // weight source / arithmetic, see conv_tc_kernel
+__global__ void __launch_bounds__(H_THREADS + (MATH ? CONV_THREADS : 0), 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p) {
   SG_DYN_SMEM(uint8_t, smem_raw);
@@ -467,7 +352,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = bars + 6 + 36;            // [2]
   uint64_t* tempty = bars + 6 + 38;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 40);
-  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][1024]
+  uint64_t* a_ready = bars + 48;              // [3]     operands split (MATH 1)
+  uint64_t* b_ready = bars + 51;              // [2][9]
+  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [2][1024]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.groups * p.n_tiles;
   if (p.stats)
@@ -476,8 +363,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+      if (MATH) mbar_init(&a_ready[i], CONV_THREADS / 32);
+    }
+    for (int i = 0; i < 18; ++i) {
+      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+      if (MATH) mbar_init(&b_ready[i], CONV_THREADS / 32);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_fence_init();
   }
@@ -550,6 +443,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t leader = lane == 0 ? 1u : 0u;
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
                                  ((uint32_t)(TILE_M >> 4) << 24);
+      constexpr uint32_t IDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
+                                   ((uint32_t)(TILE_M >> 4) << 24);
       // descriptor words: lo = start>>4 | LBO(=1)<<16, hi = SBO>>4 | version 1<<14 | SWIZZLE_128B<<29
       // A: 8-row groups `pitch` rows apart (halo rows); B: dense (1024 B)
       const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
@@ -566,10 +461,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
           const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
-          uint64_t* bf = &b_full[set * H_MAX_TAPS];
+          uint64_t* bf = MATH ? &b_ready[set * H_MAX_TAPS] : &b_full[set * H_MAX_TAPS];
           uint64_t* be = &b_empty[set * H_MAX_TAPS];
           for (int t = 0; t < H_T; ++t) {
-            mbar_wait(&a_full[s], ph);
+            mbar_wait(MATH ? &a_ready[s] : &a_full[s], ph);
             tc_fence_after();
             uint32_t at = sA16 + (uint32_t)s * (H_A_SLOT >> 4);
             uint32_t bt = b_set;
@@ -577,7 +472,26 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int kx = 0;
             for (int tap = 0; tap < p.taps; ++tap) {
               if (t == 0) { mbar_wait(&bf[tap], bph); tc_fence_after(); }
-              if constexpr (WMODE == 1) {
+              if constexpr (MATH == 1) {
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr) {
+                  if (pr >= p.nprod) break;
+                  const uint32_t ao = pr == 1 ? 4u : 0u;
+                  const uint32_t accf = (cb | tap | pr) ? 1u : 0u;
+                  if constexpr (WMODE == 1) {
+                    // B MN-major bf16: one 64-co atom (hi = first 4 KB, mid = second), 8 ci rows per
+                    // 1 KB group, 16 ci rows per K step
+                    constexpr uint32_t IDESC_MN = IDESC16 | (1u << 16);
+                    const uint32_t btm = ((bt + (pr == 2 ? 256u : 0u)) & 0xffffu) | ((8192u >> 4) << 16);
+                    tc_mma_f16_lh(d_tmem, at + ao, a_hi, btm, b_hi, IDESC_MN, accf, leader);
+                    tc_mma_f16_lh(d_tmem, at + ao + 2, a_hi, btm + 128, b_hi, IDESC_MN, 1u, leader);
+                  } else {
+                    const uint32_t bo = pr == 2 ? 4u : 0u;
+                    tc_mma_f16_lh(d_tmem, at + ao, a_hi, bt + bo, b_hi, IDESC16, accf, leader);
+                    tc_mma_f16_lh(d_tmem, at + ao + 2, a_hi, bt + bo + 2, b_hi, IDESC16, 1u, leader);
+                  }
+                }
+              } else if constexpr (WMODE == 1) {
                 constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
                 const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
                 const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
@@ -586,10 +500,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_mma_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
                 tc_mma_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
               } else {
-              tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
+                tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
               }
               if (t == H_T - 1) tc_commit(&be[tap], leader);
               at += 8u; bt += (H_B_TILE >> 4);
@@ -603,7 +517,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++aset == 2) { aset = 0; acc_ph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===================== epilogue (warps 4..7) =====================
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -635,473 +549,42 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty[aset]);
       if (++aset == 2) { aset = 0; acc_ph ^= 1; }
     }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (p.stats) {
-    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
-      float a = s_part[c], b = s_part[1024 + c];
-      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
-    }
-  }
-  if (warp == 1) {
-    tc_fence_after();
-    tc_dealloc(tmem_base, 512u);
-  }
-}
-
-// =============================================================================
-// Small-image halo variant (opt-in: SG2IM_HALO_SMALL=1; DERIVED TEXTUALLY from conv_tc_halo_kernel,
-// which stays byte-identical).  The halo kernel needs 16 output rows per tile, so 8x8 (and smaller)
-// feature maps — the first CRN stage with 1024 channels, the 8x8 mask-head layer — fall back to the
-// per-tap kernel, which re-fetches every activation tile once per tap and per Cout tile.  Here a
-// tile is TI images x (16 / TI) rows x 8 columns: the TMA box is taken from a tensor map whose
-// dimensions are ordered (C, W, N, H), so the halo rows of the TI images land INTERLEAVED in shared
-// memory (row = (y * TI + image) * pitch + x) and the 8-row groups of the A operand keep one
-// uniform stride (pitch rows) exactly as before; a filter row further down is TI halo rows away.
-// Two A slots of 26 KB instead of three of 23 KB keep the kernel inside the shared-memory budget.
-// =============================================================================
-constexpr int HS_A_SLOT = 26 * 1024;          // (16/TI + 2) x TI x 10 rows x 128 B <= 25.6 KB for TI = 2
-constexpr int HS_A_SLOTS = 2;
-constexpr int HS_SMEM = HS_A_SLOTS * HS_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 512 + 8192;
-
-template <int WMODE>
-__global__ void __launch_bounds__(H_THREADS, 1)
-conv_tc_halo_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const HaloParams p) {
-  SG_DYN_SMEM(uint8_t, smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + HS_A_SLOTS * HS_A_SLOT;                    // [2][taps][8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H_B_TILE);
-  uint64_t* a_full = bars;                    // [3]
-  uint64_t* a_empty = bars + 3;               // [3]
-  uint64_t* b_full = bars + 6;                // [2][9]
-  uint64_t* b_empty = bars + 6 + 18;          // [2][9]
-  uint64_t* tfull = bars + 6 + 36;            // [2]
-  uint64_t* tempty = bars + 6 + 38;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 40);
-  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][1024]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = p.groups * p.n_tiles;
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < HS_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tc_alloc(tmem_slot, 512u);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // work item -> (Cout tile, first pixel tile of the group)
-  auto decode = [&](int item, int& nt, int& pt0) {
-    nt = item % p.n_tiles;
-    pt0 = (item / p.n_tiles) * H_T;
-  };
-  // a pixel tile = TI images x TH rows x 8 columns (TI * TH == 16); n = first image of the group
-  const int TI = p.ti, TH = H_BH / p.ti;
-  auto tile_xy = [&](int pt, int& n, int& y0, int& x0) {
-    int tw = pt % p.tiles_w; int r = pt / p.tiles_w;
-    int th = r % p.tiles_h; n = (r / p.tiles_h) * TI;     // n >= N for padding tiles: TMA zero-fills
-    y0 = th * TH; x0 = tw * H_BW;
-  };
-
-  if (warp == 0) {
-    // ===================== halo (A) producer =====================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        int nt, pt0;
-        decode(item, nt, pt0);
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          for (int t = 0; t < H_T; ++t) {
-            int n, y0, x0;
-            tile_xy(pt0 + t, n, y0, x0);
-            mbar_wait(&a_empty[s], ph ^ 1);
-            mbar_expect_tx(&a_full[s], p.a_bytes);
-            tma_load_4d(sA + s * HS_A_SLOT, &tmA, &a_full[s], cb * 32, x0 - p.P, n, y0 - p.P);
-            if (++s == HS_A_SLOTS) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== weight (B) producer =====================
-    if (lane == 0) {
-      uint32_t bcnt = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        int nt, pt0;
-        decode(item, nt, pt0);
-        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
-            mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
-            mbar_expect_tx(fb, H_B_TILE);
-            if constexpr (WMODE == 1) {
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, nt * H_BN, cb * 32, tap);
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE + 4096, &tmB, fb, nt * H_BN + 32,
-                          cb * 32, tap);
-            } else {
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN,
-                          WMODE == 2 ? p.taps - 1 - tap : tap);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, lane 0 issues) =====================
-    {
-      const uint32_t leader = lane == 0 ? 1u : 0u;
-      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
-                                 ((uint32_t)(TILE_M >> 4) << 24);
-      // descriptor words: lo = start>>4 | LBO(=1)<<16, hi = SBO>>4 | version 1<<14 | SWIZZLE_128B<<29
-      // A: 8-row groups `pitch` rows apart (halo rows); B: dense (1024 B)
-      const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t b_hi = 64u | (1u << 14) | (2u << 29);
-      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
-      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
-      const uint32_t row_wrap = (uint32_t)(p.ti * p.pitch - p.KW) * 8u;   // next ky: TI interleaved halo rows down
+  } else if (warp >= 8) {
+    if constexpr (MATH == 1) {
+      // ===================== operand converters (warps 8..11) =====================
+      // same order as the MMA issuer consumes: A(cb, 0), B(cb, taps...), A(cb, 1..3)
+      const int ct = (int)threadIdx.x - 8 * 32;
+      const int a_rows = (int)(p.a_bytes >> 7);
       int s = 0; uint32_t ph = 0;
       uint32_t bcnt = 0;
-      int aset = 0; uint32_t acc_ph = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        mbar_wait(&tempty[aset], acc_ph ^ 1);
-        tc_fence_after();
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
-          const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
-          uint64_t* bf = &b_full[set * H_MAX_TAPS];
-          uint64_t* be = &b_empty[set * H_MAX_TAPS];
           for (int t = 0; t < H_T; ++t) {
             mbar_wait(&a_full[s], ph);
-            tc_fence_after();
-            uint32_t at = sA16 + (uint32_t)s * (HS_A_SLOT >> 4);
-            uint32_t bt = b_set;
-            const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
-            int kx = 0;
-            for (int tap = 0; tap < p.taps; ++tap) {
-              if (t == 0) { mbar_wait(&bf[tap], bph); tc_fence_after(); }
-              if constexpr (WMODE == 1) {
-                constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
-                const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
-                const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
-                tc_mma_tf32_lh(d_tmem, at, a_hi, btm, bm_hi, IDESC_MN, (cb | tap) ? 1u : 0u, leader);
-                tc_mma_tf32_lh(d_tmem, at + 2, a_hi, btm + 64, bm_hi, IDESC_MN, 1u, leader);
-                tc_mma_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u, leader);
-                tc_mma_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u, leader);
-              } else {
-              tc_mma_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u, leader);
-              tc_mma_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u, leader);
-              }
-              if (t == H_T - 1) tc_commit(&be[tap], leader);
-              at += 8u; bt += (H_B_TILE >> 4);
-              if (++kx == p.KW) { kx = 0; at += row_wrap; }
-            }
-            tc_commit(&a_empty[s], leader);
-            if (++s == HS_A_SLOTS) { s = 0; ph ^= 1; }
-          }
-        }
-        tc_commit(&tfull[aset], leader);
-        if (++aset == 2) { aset = 0; acc_ph ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7) =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int hh = (r >> 3) / TI, img = (r >> 3) % TI, ww = r & 7;   // row group g = y * TI + image
-    int aset = 0; uint32_t acc_ph = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      int nt, pt0;
-      decode(item, nt, pt0);
-      mbar_wait(&tfull[aset], acc_ph);
-      tc_fence_after();
-      for (int t = 0; t < H_T; ++t) {
-        int n, y0, x0;
-        tile_xy(pt0 + t, n, y0, x0);
-        const bool valid = (pt0 + t) < p.ptiles && (n + img) < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
-        float* yrow = p.y + (((long long)(n + img) * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
-                      p.y_coff + (long long)nt * H_BN;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((aset * H_T + t) * H_BN);
-#pragma unroll 1
-        for (int ch = 0; ch < H_BN / 32; ++ch) {
-          if (nt * H_BN + ch * 32 >= p.Cout) break;
-          float v[32];
-          tc_ld32(taddr + ch * 32, v);
-          epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
-                         yrow + ch * 32, p.stats ? s_part : nullptr, lane, p.round_out);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[aset]);
-      if (++aset == 2) { aset = 0; acc_ph ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (p.stats) {
-    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
-      float a = s_part[c], b = s_part[1024 + c];
-      if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
-    }
-  }
-  if (warp == 1) {
-    tc_fence_after();
-    tc_dealloc(tmem_base, 512u);
-  }
-}
-
-// =============================================================================
-// CTA-pair halo variant (opt-in: SG2IM_HALO_PAIR=1; DERIVED TEXTUALLY from conv_tc_halo_kernel, which
-// stays byte-identical; NOT yet run on hardware — built on the cta_group::2 semantics that
-// tools/umma_2cta_probe.cu is there to pin).  Motivation: the N = 64 kernels run at ~63 cycles per
-// 128 x 64 x 8 MMA against 32 cycles of math, i.e. bound by the shared-memory operand feed (4 KB of
-// A + 2 KB of B per MMA, profiles/r01_prof_conv_tc_halo.txt).  Two CTAs of a cluster work as one
-// M = 256 tile: each keeps its own group of H_T pixel tiles (own halo tiles, own accumulators, own
-// epilogue — all as in the single-CTA kernel) but loads only HALF of every weight tile; rank 0
-// issues tcgen05.mma.cta_group::2, which reads A from both CTAs and the two B halves.
-// Per SM: 5 KB instead of 6 KB of operands per MMA, half the weight traffic from L2.
-// Protocol on top of the single-CTA one:
-//   * rank 1's warp 1 (idle otherwise) relays "my A tile / B half has landed" to rank 0's
-//     a_peer / b_peer barriers (remote mbarrier arrive);
-//   * slot releases and accumulator-ready signals are multicast commits to both CTAs;
-//   * rank 1's epilogue warps release the accumulators on rank 0's tempty (count 8);
-//   * cluster barriers after init and before TMEM is freed.
-// =============================================================================
-constexpr int H2_B_TILE = (H_BN / 2) * KB_BYTES;     // this CTA's 32 of the 64 weight columns: 4 KB
-constexpr int H2_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H2_B_TILE + 1024 + 1024 + 8192;
-
-template <int WMODE>
-__global__ void __launch_bounds__(H_THREADS, 1)
-conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const HaloParams p) {
-  SG_DYN_SMEM(uint8_t, smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + H_A_SLOTS * H_A_SLOT;                    // [2][taps][4 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H2_B_TILE);
-  uint64_t* a_full = bars;                    // [3]
-  uint64_t* a_empty = bars + 3;               // [3]
-  uint64_t* b_full = bars + 6;                // [2][9]
-  uint64_t* b_empty = bars + 6 + 18;          // [2][9]
-  uint64_t* tfull = bars + 6 + 36;            // [2]
-  uint64_t* tempty = bars + 6 + 38;           // [2]   used on rank 0: 4 local + 4 remote epilogue warps
-  uint64_t* a_peer = bars + 6 + 40;           // [3]   used on rank 0: rank 1's A tile has landed
-  uint64_t* b_peer = bars + 6 + 43;           // [2][9] used on rank 0: rank 1's B half has landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 61);
-  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // [2][1024]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_rank();
-  // work unit = (Cout tile, PAIR of pixel-tile groups); rank r owns group 2 * gp + r (a group past
-  // the end is all padding: TMA zero-fills, the epilogue masks)
-  const int gpairs = (p.groups + 1) / 2;
-  const int total = gpairs * p.n_tiles;
-  const int unit0 = (int)blockIdx.x / 2, unit_step = (int)gridDim.x / 2;
-  if (p.stats)
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_part[i] = 0.f;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_peer[i], 1); }
-    for (int i = 0; i < 18; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&b_peer[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tc_alloc2(tmem_slot, 512u);                     // warp 1 of BOTH CTAs
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                               // both CTAs' barriers exist before any remote signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  auto decode = [&](int item, int& nt, int& pt0) {
-    nt = item % p.n_tiles;
-    pt0 = ((item / p.n_tiles) * 2 + (int)rank) * H_T;
-  };
-  auto tile_xy = [&](int pt, int& n, int& y0, int& x0) {
-    int tw = pt % p.tiles_w; int r = pt / p.tiles_w;
-    int th = r % p.tiles_h; n = r / p.tiles_h;            // n >= N for padding tiles: TMA zero-fills
-    y0 = th * H_BH; x0 = tw * H_BW;
-  };
-
-  if (warp == 0) {
-    // ===================== halo (A) producer: this CTA's own pixel tiles =====================
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int item = unit0; item < total; item += unit_step) {
-        int nt, pt0;
-        decode(item, nt, pt0);
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          for (int t = 0; t < H_T; ++t) {
-            int n, y0, x0;
-            tile_xy(pt0 + t, n, y0, x0);
-            mbar_wait(&a_empty[s], ph ^ 1);
-            mbar_expect_tx(&a_full[s], p.a_bytes);
-            tma_load_4d(sA + s * H_A_SLOT, &tmA, &a_full[s], cb * 32, x0 - p.P, y0 - p.P, n);
+            uint8_t* a = sA + s * H_A_SLOT;
+            for (int i = ct; i < a_rows; i += CONV_THREADS) split_row_inplace(a + i * 128);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[s]);
             if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== weight (B) producer: columns 32 * rank .. + 32 of the tile =====================
-    if (lane == 0) {
-      uint32_t bcnt = 0;
-      for (int item = unit0; item < total; item += unit_step) {
-        int nt, pt0;
-        decode(item, nt, pt0);
-        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
-            mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
-            mbar_expect_tx(fb, H2_B_TILE);
-            if constexpr (WMODE == 1) {
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H2_B_TILE, &tmB, fb, nt * H_BN + (int)rank * 32,
-                          cb * 32, tap);
-            } else {
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H2_B_TILE, &tmB, fb, cb * 32,
-                          nt * H_BN + (int)rank * 32, WMODE == 2 ? p.taps - 1 - tap : tap);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1 && rank != 0) {
-    // ===================== rank 1: relay "landed" to rank 0 (whole warp walks the loops, lane 0 signals) ==
-    {
-      int s = 0; uint32_t ph = 0;
-      uint32_t bcnt = 0;
-      for (int item = unit0; item < total; item += unit_step) {
-        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
-          for (int t = 0; t < H_T; ++t) {
-            mbar_wait(&a_full[s], ph);
-            if (lane == 0) mbar_arrive_cluster(&a_peer[s], 0u);
             if (t == 0) {
               for (int tap = 0; tap < p.taps; ++tap) {
                 mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
-                if (lane == 0) mbar_arrive_cluster(&b_peer[set * H_MAX_TAPS + tap], 0u);
+                uint8_t* b = sB + (set * H_MAX_TAPS + tap) * H_B_TILE;
+                if constexpr (WMODE == 1) {
+                  if (ct < 32) split_rowpair_inplace(b + ct * 128, b + 4096 + ct * 128);
+                } else {
+                  if (ct < H_BN) split_row_inplace(b + ct * 128);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_ready[set * H_MAX_TAPS + tap]);
               }
             }
-            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== rank 0: pair-MMA issuer (converged warp, lane 0 issues) =====================
-    {
-      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H_BN >> 3) << 17) |
-                                 ((uint32_t)(256 >> 4) << 24);
-      const uint32_t a_hi = (uint32_t)((p.pitch * 128) >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t b_hi = 64u | (1u << 14) | (2u << 29);
-      const uint32_t sA16 = (smem_u32(sA) >> 4) | (1u << 16);
-      const uint32_t sB16 = (smem_u32(sB) >> 4) | (1u << 16);
-      const uint32_t row_wrap = (uint32_t)(p.pitch - p.KW) * 8u;     // 16-byte units, row = 128 B
-      int s = 0; uint32_t ph = 0;
-      uint32_t bcnt = 0;
-      int aset = 0; uint32_t acc_ph = 0;
-      for (int item = unit0; item < total; item += unit_step) {
-        mbar_wait(&tempty[aset], acc_ph ^ 1);
-        tc_fence_after();
-        for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
-          const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H2_B_TILE >> 4);
-          uint64_t* bf = &b_full[set * H_MAX_TAPS];
-          uint64_t* bp = &b_peer[set * H_MAX_TAPS];
-          uint64_t* be = &b_empty[set * H_MAX_TAPS];
-          for (int t = 0; t < H_T; ++t) {
-            mbar_wait(&a_full[s], ph);
-            mbar_wait(&a_peer[s], ph);
-            tc_fence_after();
-            uint32_t at = sA16 + (uint32_t)s * (H_A_SLOT >> 4);
-            uint32_t bt = b_set;
-            const uint32_t d_tmem = tmem_base + (uint32_t)((aset * H_T + t) * H_BN);
-            int kx = 0;
-            for (int tap = 0; tap < p.taps; ++tap) {
-              if (t == 0) { mbar_wait(&bf[tap], bph); mbar_wait(&bp[tap], bph); tc_fence_after(); }
-              if constexpr (WMODE == 1) {
-                constexpr uint32_t IDESC_MN = IDESC | (1u << 16);
-                const uint32_t bm_hi = 32u | (1u << 14) | (1u << 29);     // SBO 512 B, SWIZZLE_128B_BASE32B
-                const uint32_t btm = (bt & 0xffffu) | ((4096u >> 4) << 16);
-                tc_mma2_tf32_lh(d_tmem, at, a_hi, btm, bm_hi, IDESC_MN, (cb | tap) ? 1u : 0u);
-                tc_mma2_tf32_lh(d_tmem, at + 2, a_hi, btm + 64, bm_hi, IDESC_MN, 1u);
-                tc_mma2_tf32_lh(d_tmem, at + 4, a_hi, btm + 128, bm_hi, IDESC_MN, 1u);
-                tc_mma2_tf32_lh(d_tmem, at + 6, a_hi, btm + 192, bm_hi, IDESC_MN, 1u);
-              } else {
-                tc_mma2_tf32_lh(d_tmem, at, a_hi, bt, b_hi, IDESC, (cb | tap) ? 1u : 0u);
-                tc_mma2_tf32_lh(d_tmem, at + 2, a_hi, bt + 2, b_hi, IDESC, 1u);
-                tc_mma2_tf32_lh(d_tmem, at + 4, a_hi, bt + 4, b_hi, IDESC, 1u);
-                tc_mma2_tf32_lh(d_tmem, at + 6, a_hi, bt + 6, b_hi, IDESC, 1u);
-              }
-              if (t == H_T - 1) tc_commit2_mc(&be[tap], (uint16_t)3);
-              at += 8u; bt += (H2_B_TILE >> 4);
-              if (++kx == p.KW) { kx = 0; at += row_wrap; }
-            }
-            tc_commit2_mc(&a_empty[s], (uint16_t)3);
-            if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
-          }
-        }
-        tc_commit2_mc(&tfull[aset], (uint16_t)3);
-        if (++aset == 2) { aset = 0; acc_ph ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7): this CTA's own accumulators =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int hh = r >> 3, ww = r & 7;                      // 8-wide x 16-high tile
-    int aset = 0; uint32_t acc_ph = 0;
-    for (int item = unit0; item < total; item += unit_step) {
-      int nt, pt0;
-      decode(item, nt, pt0);
-      mbar_wait(&tfull[aset], acc_ph);
-      tc_fence_after();
-      for (int t = 0; t < H_T; ++t) {
-        int n, y0, x0;
-        tile_xy(pt0 + t, n, y0, x0);
-        const bool valid = (pt0 + t) < p.ptiles && n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
-        float* yrow = p.y + (((long long)n * p.Hout + (y0 + hh)) * p.Wout + (x0 + ww)) * p.y_cstride +
-                      p.y_coff + (long long)nt * H_BN;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((aset * H_T + t) * H_BN);
-#pragma unroll 1
-        for (int ch = 0; ch < H_BN / 32; ++ch) {
-          if (nt * H_BN + ch * 32 >= p.Cout) break;
-          float v[32];
-          tc_ld32(taddr + ch * 32, v);
-          epilogue_chunk(v, valid, nt * H_BN + ch * 32, p.Cout, p.bias, p.act, p.slope,
-                         yrow + ch * 32, p.stats ? s_part : nullptr, lane, p.round_out);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (rank == 0) mbar_arrive(&tempty[aset]); else mbar_arrive_cluster(&tempty[aset], 0u);
-      }
-      if (++aset == 2) { aset = 0; acc_ph ^= 1; }
     }
   }
 
@@ -1113,119 +596,20 @@ conv_tc_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (a != 0.f || b != 0.f) { atomicAdd(p.stats + c, (double)a); atomicAdd(p.stats + p.Cout + c, (double)b); }
     }
   }
-  cluster_sync_all();                               // the peer may still signal / be read until here
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc2(tmem_base, 512u);
+    tc_dealloc(tmem_base, 512u);
   }
 }
-
 
 // ------------------------------------------------------------- host side ---
-template <int WMODE>
-int launch_halo_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& h, cudaStream_t st) {
-  const int units = ((h.groups + 1) / 2) * h.n_tiles;
-#ifdef SG2IM_EMUL
-  int nclusters = units < num_sms() / 2 ? units : num_sms() / 2;
-  if (nclusters < 1) nclusters = 1;
-  emul_launch_cluster(2, dim3((unsigned)(nclusters * 2)), dim3(H_THREADS), (size_t)H2_SMEM,
-                      [=]() { conv_tc_halo_pair_kernel<WMODE>(tmA, tmB, h); });
-  (void)st;
-  return 0;
-#else
-  auto kern = conv_tc_halo_pair_kernel<WMODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H2_SMEM);
-    if (e != cudaSuccess) {
-      sg2im_set_error("conv_tc_halo_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(H_THREADS);
-  cfg.dynamicSmemBytes = H2_SMEM;
-  cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cfg.gridDim = dim3((unsigned)(num_sms() / 2 * 2));
-  int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
-    (void)cudaGetLastError();
-    max_clusters = num_sms() / 4 > 0 ? num_sms() / 4 : 1;
-  }
-  int nclusters = units < max_clusters ? units : max_clusters;
-  cfg.gridDim = dim3((unsigned)(nclusters * 2));
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, h);
-  if (e != cudaSuccess) {
-    sg2im_set_error("conv_tc_halo_pair: launch failed: %s", cudaGetErrorString(e));
-    return (int)e;
-  }
-  return 0;
-#endif
-}
-
-template <int BN, int WMODE, int CS>
-int launch_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
-  const int units = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles / CS;
-#ifdef SG2IM_EMUL
-  int nclusters = units < num_sms() / CS ? units : num_sms() / CS;
-  if (nclusters < 1) nclusters = 1;
-  emul_launch_cluster(CS, dim3((unsigned)(nclusters * CS)), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES,
-                      [=]() { conv_tc_mc_kernel<BN, WMODE, CS>(tmA, tmB, p); });
-  (void)st;
-  return 0;
-#else
-  auto kern = conv_tc_mc_kernel<BN, WMODE, CS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      sg2im_set_error("conv_tc (cluster): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cfg.gridDim = dim3((unsigned)(num_sms() / CS * CS));
-  int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
-    (void)cudaGetLastError();
-    max_clusters = num_sms() / CS / 2 > 0 ? num_sms() / CS / 2 : 1;
-  }
-  int nclusters = units < max_clusters ? units : max_clusters;
-  cfg.gridDim = dim3((unsigned)(nclusters * CS));
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
-  if (e != cudaSuccess) {
-    sg2im_set_error("conv_tc (cluster): launch failed: %s", cudaGetErrorString(e));
-    return (int)e;
-  }
-  return 0;
-#endif
-}
-
-template <int BN, int WMODE>
+template <int BN, int WMODE, int MATH>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  if (const char* mc = getenv("SG2IM_CONV_MC")) {          // read per call: tests toggle it in-process
-    if (mc[0] == '1' && p.n_tiles % 4 == 0) return launch_mc<BN, WMODE, 4>(tmA, tmB, p, st);
-    if (mc[0] == '1' && p.n_tiles % 2 == 0) return launch_mc<BN, WMODE, 2>(tmA, tmB, p, st);
-  }
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WMODE>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WMODE, MATH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1236,15 +620,44 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
 #endif
   int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  SG_LAUNCH((conv_tc_kernel<BN, WMODE>), grid, NUM_THREADS, C::SMEM_BYTES, st, tmA, tmB, p);
+  SG_LAUNCH((conv_tc_kernel<BN, WMODE, MATH>), grid, NUM_THREADS + (MATH ? CONV_THREADS : 0),
+            C::SMEM_BYTES, st, tmA, tmB, p);
+  return 0;
+}
+
+template <int BN, int MATH>
+int launch_w(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int wmode, cudaStream_t st) {
+  return wmode == 1 ? launch<BN, 1, MATH>(tmA, tmB, p, st)
+       : wmode == 2 ? launch<BN, 2, MATH>(tmA, tmB, p, st) : launch<BN, 0, MATH>(tmA, tmB, p, st);
+}
+
+template <int WMODE, int MATH>
+int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& h, cudaStream_t st) {
+#ifndef SG2IM_EMUL
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<WMODE, MATH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
+    if (e != cudaSuccess) {
+      sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+#endif
+  int items = h.groups * h.n_tiles;
+  int grid = items < num_sms() ? items : num_sms();
+  SG_LAUNCH((conv_tc_halo_kernel<WMODE, MATH>), grid, H_THREADS + (MATH ? CONV_THREADS : 0), H_SMEM,
+            st, hA, hB, h);
   return 0;
 }
 
 }  // namespace
 
-// Tensor map of the B operand for the three weight sources (see conv_tc_kernel).
+// Tensor map of the B operand for the three weight sources (see conv_tc_kernel).  bf16 arithmetic:
+// every tile is rewritten by the converter warps, which assume the plain SWIZZLE_128B pattern.
 static int encode_weights(tc::EncodeTiledFn enc, CUtensorMap* map, const float* w, int64_t Cin,
-                          int64_t Cout, int taps, int BN, int wmode, int64_t w_rows_full) {
+                          int64_t Cout, int taps, int BN, int wmode, int64_t w_rows_full, int math) {
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -1256,7 +669,7 @@ static int encode_weights(tc::EncodeTiledFn enc, CUtensorMap* map, const float* 
     gdim[0] = (cuuint64_t)Cout; gdim[1] = (cuuint64_t)Cin;
     gstr[0] = (cuuint64_t)Cout * 4; gstr[1] = (cuuint64_t)w_rows_full * Cout * 4;
     box[1] = 32;
-    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!math) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   } else {                                // [taps][rows = conv Cout][cols = conv Cin], K-major
     gdim[0] = (cuuint64_t)Cin; gdim[1] = (cuuint64_t)Cout;
     gstr[0] = (cuuint64_t)Cin * 4; gstr[1] = (cuuint64_t)w_rows_full * Cin * 4;
@@ -1297,13 +710,15 @@ extern "C" int sg2im_conv_tc_supported(int64_t N, int64_t Hin, int64_t Win, int6
 // [taps][w_rows][w_cols] of the conv's weight (rows = its input channels, cols = its output
 // channels; w_rows_full >= rows actually used = row pitch of a tap): 1 = forward (Cin rows used,
 // Cout == w_cols), 2 = data gradient (conv-Cin == w_cols, conv-Cout rows used).
+// math: SG2IM_MATH_TF32 / SG2IM_MATH_BF16X3 / SG2IM_MATH_BF16 (include/sg2im_b200.h).
 static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
                         int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
                         int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
                         int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
                         double* stats, int round_out, sg2im_stream_t stream, int wmode,
-                        int64_t w_rows_full) {
+                        int64_t w_rows_full, int math) {
   SG_ARG(x && w_tc && y);
+  SG_ARG(math == SG2IM_MATH_TF32 || math == SG2IM_MATH_BF16X3 || math == SG2IM_MATH_BF16);
   if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
                                y_cstride, y_coff)) {
     sg2im_set_error("sg2im_conv_tc: unsupported shape (use sg2im_conv_igemm)");
@@ -1313,9 +728,12 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
   SG_ARG(stats == nullptr || (Cout <= 1024 && act == 0));
   EncodeTiledFn enc = get_encode();
   if (!enc) { sg2im_set_error("sg2im_conv_tc: cuTensorMapEncodeTiled unavailable"); return -3; }
+  const int bf = math != SG2IM_MATH_TF32;
+  const int nprod = math == SG2IM_MATH_BF16X3 ? 3 : 1;
+  if (bf) round_out = 0;                  // RN-TF32 hand-over is a tf32-mode contract
 
   TcParams p;
-  p.stats = stats; p.round_out = round_out;
+  p.stats = stats; p.round_out = round_out; p.nprod = nprod;
   p.N = (int)N; p.Hout = (int)Hout; p.Wout = (int)Wout;
   p.Cin = (int)Cin; p.Cout = (int)Cout; p.KH = KH; p.KW = KW; p.P = P;
   tc_geometry(p.Hout, p.Wout, p.BW, p.BH, p.BI);
@@ -1341,68 +759,12 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
   p.num_kb = KH * KW * p.cblocks;
   p.bias = bias; p.act = act; p.slope = slope;
   p.y = y; p.y_cstride = y_cstride; p.y_coff = y_coff;
+  cudaStream_t st = as_stream(stream);
 
   // narrow outputs on real images: halo + weight-stationary kernel
-  // 8-row feature maps (CRN stage 0, 8x8 mask-head layer): two images per tile, opt-in
-  if (const char* hs = getenv("SG2IM_HALO_SMALL")) {
-    if (hs[0] == '1' && KH * KW > 1 && KH <= 3 && KW <= 3 && Hout > 4 && Hout <= 8 && N >= 2) {
-      HaloParams h;
-      const int TI = 2, TH = H_BH / TI;
-      h.ti = TI;
-      h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
-      h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
-      h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, TH);
-      h.ptiles = (int)(ceil_div64(N, TI) * h.tiles_h * h.tiles_w);
-      h.groups = (int)ceil_div64(h.ptiles, H_T);
-      h.n_tiles = (int)ceil_div64(Cout, H_BN);
-      h.cblocks = (int)ceil_div64(Cin, 32);
-      h.a_bytes = (uint32_t)((TH + KH - 1) * TI * h.pitch * 128);
-      h.bias = bias; h.act = act; h.slope = slope;
-      h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
-      h.stats = stats; h.round_out = round_out;
-      CUtensorMap hA, hB;
-      {
-        // dimensions ordered (C, W, N, H): the TI images' halo rows interleave in shared memory
-        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)N, (cuuint64_t)Hin};
-        cuuint64_t gstr[3] = {(cuuint64_t)x_cstride * 4, (cuuint64_t)Hin * Win * x_cstride * 4,
-                              (cuuint64_t)Win * x_cstride * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)h.pitch, (cuuint32_t)TI, (cuuint32_t)(TH + KH - 1)};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&hA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
-                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode small-halo A failed (%d)", (int)r); return -4; }
-      }
-      if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full)) return rc;
-#ifndef SG2IM_EMUL
-      static bool small_attr = false;
-      if (!small_attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<0>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
-        if (e == cudaSuccess)
-          e = cudaFuncSetAttribute(conv_tc_halo_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HS_SMEM);
-        if (e != cudaSuccess) {
-          sg2im_set_error("conv_tc_halo_small: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-          return (int)e;
-        }
-        small_attr = true;
-      }
-#endif
-      int items = h.groups * h.n_tiles;
-      int grid = items < num_sms() ? items : num_sms();
-      if (wmode == 1) SG_LAUNCH(conv_tc_halo_small_kernel<1>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
-      else if (wmode == 2) SG_LAUNCH(conv_tc_halo_small_kernel<2>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
-      else SG_LAUNCH(conv_tc_halo_small_kernel<0>, grid, H_THREADS, HS_SMEM, as_stream(stream), hA, hB, h);
-      SG_LAUNCH_OK();
-      return 0;
-    }
-  }
   if (KH * KW > 1 && KH <= 3 && KW <= 3 && Hout >= H_BH && Wout >= H_BW && BN <= 128 &&
       getenv("SG2IM_NO_HALO") == nullptr) {
     HaloParams h;
-    h.ti = 1;
     h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
     h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
     h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, H_BH);
@@ -1413,7 +775,7 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
     h.a_bytes = (uint32_t)((H_BH + KH - 1) * h.pitch * 128);
     h.bias = bias; h.act = act; h.slope = slope;
     h.y = y; h.y_cstride = y_cstride; h.y_coff = y_coff;
-    h.stats = stats; h.round_out = round_out;
+    h.stats = stats; h.round_out = round_out; h.nprod = nprod;
     CUtensorMap hA, hB;
     {
       cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
@@ -1426,37 +788,13 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
     }
-    if (const char* hp = getenv("SG2IM_HALO_PAIR")) {
-      if (hp[0] == '1') {
-        // CTA pairs (cta_group::2): every CTA loads 32 of the 64 columns of each weight tile
-        if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN / 2, wmode, w_rows_full)) return rc;
-        return wmode == 1 ? launch_halo_pair<1>(hA, hB, h, as_stream(stream))
-             : wmode == 2 ? launch_halo_pair<2>(hA, hB, h, as_stream(stream))
-                          : launch_halo_pair<0>(hA, hB, h, as_stream(stream));
-      }
-    }
-    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full)) return rc;
-#ifndef SG2IM_EMUL
-    static bool halo_attr = false;
-    if (!halo_attr) {
-      cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<0>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
-      if (e != cudaSuccess) {
-        sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return (int)e;
-      }
-      halo_attr = true;
-    }
-#endif
-    int items = h.groups * h.n_tiles;
-    int grid = items < num_sms() ? items : num_sms();
-    if (wmode == 1) SG_LAUNCH(conv_tc_halo_kernel<1>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
-    else if (wmode == 2) SG_LAUNCH(conv_tc_halo_kernel<2>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
-    else SG_LAUNCH(conv_tc_halo_kernel<0>, grid, H_THREADS, H_SMEM, as_stream(stream), hA, hB, h);
+    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full, bf)) return rc;
+    int rc;
+    if (bf) rc = wmode == 1 ? launch_halo<1, 1>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 1>(hA, hB, h, st)
+                                                                           : launch_halo<0, 1>(hA, hB, h, st);
+    else rc = wmode == 1 ? launch_halo<1, 0>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 0>(hA, hB, h, st)
+                                                                         : launch_halo<0, 0>(hA, hB, h, st);
+    if (rc) return rc;
     SG_LAUNCH_OK();
     return 0;
   }
@@ -1473,18 +811,15 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode A failed (%d)", (int)r); return -4; }
   }
-  if (int rc = encode_weights(enc, &tmB, w_tc, Cin, Cout, KH * KW, BN, wmode, w_rows_full)) return rc;
-  cudaStream_t st = as_stream(stream);
+  if (int rc = encode_weights(enc, &tmB, w_tc, Cin, Cout, KH * KW, BN, wmode, w_rows_full, bf)) return rc;
   int rc = 0;
-  if (wmode == 1) {
-    rc = BN == 256 ? launch<256, 1>(tmA, tmB, p, st) : BN == 128 ? launch<128, 1>(tmA, tmB, p, st)
-                                                                   : launch<64, 1>(tmA, tmB, p, st);
-  } else if (wmode == 2) {
-    rc = BN == 256 ? launch<256, 2>(tmA, tmB, p, st) : BN == 128 ? launch<128, 2>(tmA, tmB, p, st)
-                                                                   : launch<64, 2>(tmA, tmB, p, st);
-  } else if (BN == 256) rc = launch<256, 0>(tmA, tmB, p, st);
-  else if (BN == 128) rc = launch<128, 0>(tmA, tmB, p, st);
-  else rc = launch<64, 0>(tmA, tmB, p, st);
+  if (bf) {
+    rc = BN == 256 ? launch_w<256, 1>(tmA, tmB, p, wmode, st)
+       : BN == 128 ? launch_w<128, 1>(tmA, tmB, p, wmode, st) : launch_w<64, 1>(tmA, tmB, p, wmode, st);
+  } else {
+    rc = BN == 256 ? launch_w<256, 0>(tmA, tmB, p, wmode, st)
+       : BN == 128 ? launch_w<128, 0>(tmA, tmB, p, wmode, st) : launch_w<64, 0>(tmA, tmB, p, wmode, st);
+  }
   if (rc) return rc;
   SG_LAUNCH_OK();
   return 0;
@@ -1494,9 +829,9 @@ extern "C" int sg2im_conv_tc(const float* x, int64_t x_cstride, int64_t N, int64
                              int64_t Win, int64_t Cin, const float* w_tc, const float* bias,
                              int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
                              int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
-                             double* stats, int round_out, sg2im_stream_t stream) {
+                             double* stats, int round_out, int math, sg2im_stream_t stream) {
   return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_tc, bias, KH, KW, P, Hout, Wout, Cout, act,
-                      slope, y, y_cstride, y_coff, stats, round_out, stream, 0, 0);
+                      slope, y, y_cstride, y_coff, stats, round_out, stream, 0, 0, math);
 }
 
 extern "C" int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
@@ -1504,9 +839,9 @@ extern "C" int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, i
                                  int dgrad, const float* bias, int KH, int KW, int P, int64_t Hout,
                                  int64_t Wout, int64_t Cout, int act, float slope, float* y,
                                  int64_t y_cstride, int64_t y_coff, double* stats, int round_out,
-                                 sg2im_stream_t stream) {
+                                 int math, sg2im_stream_t stream) {
   SG_ARG(w_rows_full >= (dgrad ? Cout : Cin));
   return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_kcc, bias, KH, KW, P, Hout, Wout, Cout, act,
                       slope, y, y_cstride, y_coff, stats, round_out, stream, dgrad ? 2 : 1,
-                      w_rows_full);
+                      w_rows_full, math);
 }

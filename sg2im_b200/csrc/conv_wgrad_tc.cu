@@ -19,20 +19,22 @@
 // * Work item = (ci tile, co tile, tap pass, pixel split); persistent CTAs; the
 //   epilogue adds the partial tile into dW with vector atomics (dW zeroed by
 //   the caller).
+// * Arithmetic (template parameter MATH, as in conv_tc.cu): 0 = kind::tf32 on the fp32 words as
+//   they are; 1 = kind::f16 on bf16 pairs — the TMA boxes land as plain SWIZZLE_128B rows, four
+//   converter warps fold every pair of adjacent 32-channel atoms in place into one 64-channel
+//   bf16 hi atom and one mid atom (tc_common.cuh: split_rowpair_inplace), and each fp32 product
+//   is issued as hi*hi + mid*hi + hi*mid (K = 16 pixels per MMA; nprod = 1: hi*hi only).
 // Replaces cuDNN's backward-filter behind nn.Conv2d / nn.Linear
 // (sg2im/crn.py:41-45,80-82; model.py:100; layers.py:221).
 #include <cstdlib>
 #include "tc_common.cuh"
-
-// cluster / TMA-multicast variant (conv_wgrad_tc_mc.cu), opt-in with SG2IM_WGRAD_MC=1
-int sg2im_wgrad_mc_launch(const CUtensorMap* tmX, const CUtensorMap* tmDY, const int* f, float* dw,
-                          int BN, cudaStream_t st);
 
 using namespace tc;
 
 namespace {
 
 constexpr int WG_THREADS = 192;
+constexpr int WG_CONV_THREADS = 128;        // converter warps of the bf16 arithmetic
 constexpr int A_ATOM_BYTES = 8192;          // halo tile of one 32-channel atom, padded to 1 KB
 constexpr int B_ATOM_BYTES = 4096;          // 32 pixel rows x 128 B
 constexpr int A_STAGE = 4 * A_ATOM_BYTES;   // M = 128 channels = 4 atoms
@@ -43,6 +45,7 @@ struct WgParams {
   int tiles_w, tiles_h, total_ptiles;
   int ci_tiles, co_tiles, passes, T, splits, per_split;
   int a_bytes, b_atom_rows;      // bytes of one A atom box, pixel rows of a B atom (=8*RH)
+  int nprod;                     // MATH 1: products per fp32 multiply (3 = bf16x3, 1 = bf16)
   float* dw;
 };
 
@@ -58,10 +61,12 @@ struct WCfg {
   // D=F32, A=B=TF32, both MN-major (bits 15,16), N>>3, M>>4
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                     ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t IDESC16 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
-template <int BN>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+template <int BN, int MATH>
+__global__ void __launch_bounds__(WG_THREADS + (MATH ? WG_CONV_THREADS : 0), 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const WgParams p) {
   using C = WCfg<BN>;
@@ -74,13 +79,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  uint64_t* ready = tempty + 2;                                  // [STAGES] operands split (MATH 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmDY);
-    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1);
+      if (MATH) mbar_init(&ready[i], WG_CONV_THREADS / 32);
+    }
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
     mbar_fence_init();
@@ -112,6 +121,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         decode(item, ci0, co0, pass, t0, t1);
         int na = (p.Cin - ci0 + 31) / 32; if (na > 4) na = 4;
         int nb = (p.Cout - co0 + 31) / 32; if (nb > BN / 32) nb = BN / 32;
+        if (MATH) { na = 4; nb = BN / 32; }     // atoms are folded in pairs: fetch all (past the edge: zeros)
         const uint32_t bytes = (uint32_t)(na * p.a_bytes + nb * B_ATOM_BYTES);
         for (int pt = t0; pt < t1; ++pt) {
           int tw = pt % p.tiles_w;
@@ -153,7 +163,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait(tempty, acc_ph ^ 1);
         tc_fence_after();
         for (int pt = t0; pt < t1; ++pt) {
-          mbar_wait(&full[s], ph);
+          mbar_wait(MATH ? &ready[s] : &full[s], ph);
           tc_fence_after();
           const uint32_t first = (pt > t0) ? 1u : 0u;
           uint32_t at = a_lo0 + (uint32_t)s * (C::STAGE >> 4) + tap_off0;
@@ -161,11 +171,31 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           uint32_t d_tmem = tmem_base;
           int kx = kx0;
           for (int tl = 0; tl < ntap; ++tl) {
+            if constexpr (MATH == 1) {
+              // 4 output rows of 8 pixels: K = 16 pixels (two rows) per MMA.  hi atoms are the even
+              // 32-channel atoms of each folded pair, mid atoms the odd ones; 64-channel atoms are
+              // one pair (LBO) apart; the second 8-pixel group is the next halo row (A) / 1 KB (B)
+              const uint32_t a16 = (at & 0xffffu) | ((uint32_t)(2 * A_ATOM_BYTES >> 4) << 16);
+              const uint32_t b16 = (bt & 0xffffu) | ((uint32_t)(2 * B_ATOM_BYTES >> 4) << 16);
+              const uint32_t a_hi16 = pitch16 | (1u << 14) | (2u << 29);
+              const uint32_t b_hi16 = 64u | (1u << 14) | (2u << 29);
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr) {
+                if (pr >= p.nprod) break;
+                const uint32_t ao = pr == 1 ? (uint32_t)(A_ATOM_BYTES >> 4) : 0u;
+                const uint32_t bo = pr == 2 ? (uint32_t)(B_ATOM_BYTES >> 4) : 0u;
+                tc_mma_f16_lh(d_tmem, a16 + ao, a_hi16, b16 + bo, b_hi16, C::IDESC16,
+                              pr ? 1u : first, leader);
+                tc_mma_f16_lh(d_tmem, a16 + ao + 2 * pitch16, a_hi16, b16 + bo + 128, b_hi16, C::IDESC16,
+                              1u, leader);
+              }
+            } else {
             // 4 output rows of 8 pixels (RH == 4): K = 8 pixels per MMA
             tc_mma_tf32_lh(d_tmem, at, d_hi, bt, d_hi, C::IDESC, first, leader);
             tc_mma_tf32_lh(d_tmem, at + pitch16, d_hi, bt + 64, d_hi, C::IDESC, 1u, leader);
             tc_mma_tf32_lh(d_tmem, at + 2 * pitch16, d_hi, bt + 128, d_hi, C::IDESC, 1u, leader);
             tc_mma_tf32_lh(d_tmem, at + 3 * pitch16, d_hi, bt + 192, d_hi, C::IDESC, 1u, leader);
+            }
             d_tmem += BN;
             at += 8u;
             if (++kx == p.KW) { kx = 0; at += row_wrap; }
@@ -177,7 +207,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         acc_ph ^= 1;
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue: TMEM -> vector atomics into dW =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;                           // ci row within the tile
@@ -212,6 +242,38 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       if (lane == 0) mbar_arrive(tempty);
       acc_ph ^= 1;
     }
+  } else if constexpr (MATH == 1) {
+    // ===================== operand converters (warps 6..9) =====================
+    // per landed stage: the two atom pairs of the X halo tile and the BN/64 atom pairs of the dY
+    // tile are folded in place into 64-channel bf16 hi / mid atoms
+    const int ct = (int)threadIdx.x - 6 * 32;
+    const int a_rows = p.a_bytes >> 7;
+    const int n_items = 2 * a_rows + (BN / 64) * 32;
+    int s = 0; uint32_t ph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int ci0, co0, pass, t0, t1;
+      decode(item, ci0, co0, pass, t0, t1);
+      for (int pt = t0; pt < t1; ++pt) {
+        mbar_wait(&full[s], ph);
+        uint8_t* sa = smem + s * C::STAGE;
+        uint8_t* sb = sa + A_STAGE;
+        for (int i = ct; i < n_items; i += WG_CONV_THREADS) {
+          if (i < 2 * a_rows) {
+            const int pair = i >= a_rows ? 1 : 0, r = i - pair * a_rows;
+            uint8_t* r0 = sa + pair * 2 * A_ATOM_BYTES + r * 128;
+            split_rowpair_inplace(r0, r0 + A_ATOM_BYTES);
+          } else {
+            const int j = i - 2 * a_rows;
+            uint8_t* r0 = sb + (j >> 5) * 2 * B_ATOM_BYTES + (j & 31) * 128;
+            split_rowpair_inplace(r0, r0 + B_ATOM_BYTES);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
   }
 
   tc_fence_before();
@@ -222,13 +284,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
-template <int BN>
+template <int BN, int MATH>
 int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p, cudaStream_t st) {
   using C = WCfg<BN>;
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, MATH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -239,7 +301,8 @@ int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p
 #endif
   int items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
   int grid = items < num_sms() ? items : num_sms();
-  SG_LAUNCH(conv_wgrad_tc_kernel<BN>, grid, WG_THREADS, C::SMEM_BYTES, st, tmX, tmDY, p);
+  SG_LAUNCH((conv_wgrad_tc_kernel<BN, MATH>), grid, WG_THREADS + (MATH ? WG_CONV_THREADS : 0),
+            C::SMEM_BYTES, st, tmX, tmDY, p);
   return 0;
 }
 
@@ -276,8 +339,10 @@ extern "C" int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win
 extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
                                    int64_t Win, int64_t Cin, const float* dy, int KH, int KW,
                                    int P, int64_t Hout, int64_t Wout, int64_t Cout, float* dw,
-                                   sg2im_stream_t stream) {
+                                   int math, sg2im_stream_t stream) {
   SG_ARG(x && dy && dw);
+  SG_ARG(math == SG2IM_MATH_TF32 || math == SG2IM_MATH_BF16X3 || math == SG2IM_MATH_BF16);
+  const int bf = math != SG2IM_MATH_TF32;
   if (!sg2im_conv_wgrad_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout)) {
     sg2im_set_error("sg2im_conv_wgrad_tc: unsupported shape (use sg2im_conv_wgrad)");
     return -2;
@@ -295,12 +360,6 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   p.tiles_w = (int)ceil_div64(g.yW, 8); p.tiles_h = (int)ceil_div64(g.yH, RH);
   p.total_ptiles = (int)(g.yN * p.tiles_h * p.tiles_w);
   int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-  // read per call: tests toggle it in-process.  The cluster variant always uses N = 64 tiles:
-  // 2 tap passes x ceil(Cout/64) co tiles share one X stream (cluster of 2 or 4), the fewest
-  // L2->SM bytes per accumulator column
-  const char* mc_env = getenv("SG2IM_WGRAD_MC");
-  const bool mc = mc_env && mc_env[0] == '1';
-  if (mc) BN = 64;
   p.ci_tiles = (int)ceil_div64(Cin, 128);
   p.co_tiles = (int)ceil_div64(Cout, BN);
   p.passes = (int)ceil_div64((int64_t)p.taps * BN, 512);
@@ -315,8 +374,11 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   p.splits = (int)ceil_div64(p.total_ptiles, p.per_split);
   p.a_bytes = (RH + KH - 1) * p.pitch * 128;
   p.b_atom_rows = 8 * RH;
+  p.nprod = math == SG2IM_MATH_BF16X3 ? 3 : 1;
   p.dw = dw;
 
+  // bf16 arithmetic: the converter warps rewrite every tile and assume plain SWIZZLE_128B rows
+  const CUtensorMapSwizzle sw = bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap tmX, tmDY;
   {
     // x viewed as (C, gW, gH, gN) pixels-of-8 rows; for K>1 this is the real NHWC tensor
@@ -326,7 +388,7 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
     cuuint32_t box[4] = {32, (cuuint32_t)p.pitch, (cuuint32_t)(RH + KH - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_wgrad_tc: encode X failed (%d)", (int)r); return -4; }
   }
@@ -337,24 +399,19 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
     cuuint32_t box[4] = {32, 8, (cuuint32_t)RH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmDY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), gdim, gstr,
-                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_wgrad_tc: encode dY failed (%d)", (int)r); return -4; }
   }
   cudaStream_t st = as_stream(stream);
   int rc;
-  {
-    if (mc) {
-      const int f[16] = {p.Cin, p.Cout, p.KH, p.KW, p.P, p.taps, p.RH, p.pitch, p.tiles_w, p.tiles_h,
-                         p.total_ptiles, p.ci_tiles, p.co_tiles, p.passes, p.T, p.a_bytes};
-      rc = sg2im_wgrad_mc_launch(&tmX, &tmDY, f, dw, BN, st);
-      if (rc == 0) { SG_LAUNCH_OK(); return 0; }
-      if (rc > 0) return rc;                               // -1: shape forms no cluster -> plain kernel
-    }
+  if (bf) {
+    rc = BN == 256 ? launch_wg<256, 1>(tmX, tmDY, p, st)
+       : BN == 128 ? launch_wg<128, 1>(tmX, tmDY, p, st) : launch_wg<64, 1>(tmX, tmDY, p, st);
+  } else {
+    rc = BN == 256 ? launch_wg<256, 0>(tmX, tmDY, p, st)
+       : BN == 128 ? launch_wg<128, 0>(tmX, tmDY, p, st) : launch_wg<64, 0>(tmX, tmDY, p, st);
   }
-  if (BN == 256) rc = launch_wg<256>(tmX, tmDY, p, st);
-  else if (BN == 128) rc = launch_wg<128>(tmX, tmDY, p, st);
-  else rc = launch_wg<64>(tmX, tmDY, p, st);
   if (rc) return rc;
   SG_LAUNCH_OK();
   return 0;

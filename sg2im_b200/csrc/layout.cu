@@ -317,7 +317,7 @@ extern "C" int sg2im_layout_fwd(const float* vecs, const float* boxes, const flo
              (D / 4) * LF_PIX <= LF_MAXACC * LF_THREADS;
   cudaStream_t st = as_stream(stream);
   const char* v2 = getenv("SG2IM_LAYOUT_V2");            // read per call: tests toggle it in-process
-  if (vec && v2 && v2[0] == '1' && D <= 1024 && N * ceil_div64(H, 4) < (1ll << 31)) {
+  if (vec && !(v2 && v2[0] == '0') && D <= 1024 && N * ceil_div64(H, 4) < (1ll << 31)) {
     sg2im_layout_fwd_v2(vecs, boxes, masks, M, img_row_ptr, img_entries, N, D, H, W, align_corners,
                         noise, noise_c, nsn, nsc, nsh, nsw, out, out_cstride, round_tf32, st);
     SG_LAUNCH_OK();
@@ -360,7 +360,7 @@ extern "C" int sg2im_layout_bwd(const float* dout, int64_t dout_cstride, const f
   SG_ARG(dout_cstride % 4 == 0 && dout_cstride >= D && aligned16(dout) && aligned16(vecs) &&
          aligned16(boxes));
   const char* v2 = getenv("SG2IM_LAYOUT_V2");           // read per call: tests toggle it in-process
-  if (v2 && v2[0] == '1' && ceil_div64(H, 8) <= 65535 && ceil_div64(W, 32) <= 65535 &&
+  if (!(v2 && v2[0] == '0') && ceil_div64(H, 8) <= 65535 && ceil_div64(W, 32) <= 65535 &&
       H * W < (1ll << 31)) {
     sg2im_layout_bwd_v2(dout, dout_cstride, vecs, boxes, masks, M, obj_to_img, N, O, D, H, W,
                         align_corners, dvecs, dmasks, as_stream(stream));

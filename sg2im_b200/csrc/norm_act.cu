@@ -25,13 +25,13 @@ int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int6
 int sg2im_colsum_small(const float* x, int64_t M, int64_t C, float* out, cudaStream_t st);
 
 static bool bn_fwd_v2_enabled() {
-  const char* e = getenv("SG2IM_BNFWD_V2");
-  return e && e[0] == '1';
+  const char* e = getenv("SG2IM_BNFWD_V2");          // default since round 2 (validated on the B200); "0" = first generation
+  return !(e && e[0] == '0');
 }
 
 static bool bn_bwd_v2_enabled() {
-  const char* e = getenv("SG2IM_BNBWD_V2");          // read per call: tests toggle it in-process
-  return e && e[0] == '1';
+  const char* e = getenv("SG2IM_BNBWD_V2");          // read per call: tests toggle it in-process ("0" = first generation)
+  return !(e && e[0] == '0');
 }
 
 namespace {
@@ -469,7 +469,7 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
   cudaStream_t st = as_stream(stream);
   {
     const char* e = getenv("SG2IM_COLSUM_V2");            // read per call: tests toggle it in-process
-    if (e && e[0] == '1' && M <= 8192 && M * C < (1ll << 31)) {
+    if (!(e && e[0] == '0') && M <= 8192 && M * C < (1ll << 31)) {
       sg2im_colsum_small(x, M, C, out, st);
       SG_LAUNCH_OK();
       return 0;

@@ -119,6 +119,34 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
 }
 
 
+// tcgen05.mma kind::f16 (bf16 operands, fp32 accumulate): K = 16 elements (32 bytes) per instruction
+__device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                              uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+  (void)leader;
+}
+// generic-proxy writes to shared memory (the in-kernel operand split) -> visible to the async
+// proxy (tcgen05.mma operand reads); executed by every writing thread before it signals
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// (x0, x1) -> packed bf16x2 of the round-to-nearest-even bf16 values (x0 in the low half) and of
+// the bf16-rounded remainders: x = hi + mid up to 2^-17 |x| (the subtraction is exact)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+}
+
 // --- setup / teardown pieces the kernels share
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -218,6 +246,59 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 #endif  // !SG2IM_EMUL
 
 namespace tc {
+
+// ---- in-kernel operand split of the 'bf16x3' arithmetic -------------------------------------
+// The convolution kernels keep fp32 NHWC tensors in HBM and TMA them into shared memory as
+// SWIZZLE_128B rows of 32 floats.  Before the tensor core reads a tile, converter warps rewrite
+// every row IN PLACE as [32 x bf16 hi | 32 x bf16 mid] (hi = RN_bf16(x), mid = RN_bf16(x - hi)),
+// so one fp32 product becomes hi*hi + mid*hi + hi*mid on kind::f16 MMAs with fp32 accumulation:
+// 2^-17 relative operand error instead of TF32's 2^-11, at 1.5x the tensor-pipe time of TF32.
+// SWIZZLE_128B: the 16-byte chunk c of a 128-byte row lives at chunk c ^ ((address >> 7) & 7).
+
+// one row (K-major operands: a pixel's / an output channel's 32 reduction-axis channels)
+__device__ __forceinline__ void split_row_inplace(uint8_t* row) {
+  const uint32_t x = (smem_u32(row) >> 7) & 7u;
+  uint32_t hi[16], mid[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ x) << 4));
+    split_bf16x2(v.x, v.y, hi[2 * c], mid[2 * c]);
+    split_bf16x2(v.z, v.w, hi[2 * c + 1], mid[2 * c + 1]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) =
+        make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    *reinterpret_cast<uint4*>(row + (((4 + j) ^ x) << 4)) =
+        make_uint4(mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
+  }
+}
+// a row pair (MN-major operands: the same pixel / reduction row in two adjacent 32-channel
+// atoms): row0 becomes the 64 bf16 hi values of the 64 channels, row1 their 64 mid values, i.e.
+// atom 2q turns into the hi half and atom 2q+1 into the mid half of one 64-wide bf16 atom
+__device__ __forceinline__ void split_rowpair_inplace(uint8_t* row0, uint8_t* row1) {
+  const uint32_t x0 = (smem_u32(row0) >> 7) & 7u, x1 = (smem_u32(row1) >> 7) & 7u;
+  uint32_t hi[32], mid[32];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row0 + ((c ^ x0) << 4));
+    split_bf16x2(v.x, v.y, hi[2 * c], mid[2 * c]);
+    split_bf16x2(v.z, v.w, hi[2 * c + 1], mid[2 * c + 1]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row1 + ((c ^ x1) << 4));
+    split_bf16x2(v.x, v.y, hi[16 + 2 * c], mid[16 + 2 * c]);
+    split_bf16x2(v.z, v.w, hi[16 + 2 * c + 1], mid[16 + 2 * c + 1]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint4*>(row0 + ((j ^ x0) << 4)) =
+        make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    *reinterpret_cast<uint4*>(row1 + ((j ^ x1) << 4)) =
+        make_uint4(mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
+  }
+}
 
 // Column sums across the 32 lanes of a warp for 32 per-lane values: lane j
 // returns sum over lanes of v[j] (31 shuffles via recursive halving instead of

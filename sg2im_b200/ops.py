@@ -148,90 +148,41 @@ def conv_igemm(mode, x, w_packed, bias, KH, KW, S, P, out_hw, Cout, act=0, slope
   return out
 
 
+TC_MODES = ('tf32', 'bf16x3', 'bf16')
+_MATH_ID = {'tf32': 0, 'bf16x3': 1, 'bf16': 2}     # SG2IM_MATH_* of include/sg2im_b200.h
+
+
 def set_conv_math(mode):
   """'fp32': every convolution / Linear on the exact-fp32 FFMA kernels.
-  'tf32': stride-1 convolutions and Linears whose shape tiles run on the
-  tcgen05 tensor-core kernel (TF32 multiply, fp32 accumulate — the arithmetic
-  cuDNN uses for the reference under torch's default allow_tf32); everything
-  else stays on the FFMA kernels.
-  'tf32x3': the same tensor-core kernels fed error-compensated operands — every
-  operand split into a TF32 hi part and an fp32 remainder, the three significant
-  products hi*hi + lo*hi + hi*lo laid side by side along the reduction dimension
-  of ONE launch (forward, data gradient) or two (weight gradient) — so results
-  agree with the fp32 reference to ~1e-6 (the 1e-3 parity bar with margin) at
-  three times the tensor-core work of 'tf32'.  Activations stay unrounded fp32."""
+  The other modes run stride-1 convolutions and Linears whose shape tiles on the
+  tcgen05 tensor-core kernels (fp32 accumulate in TMEM; activations and weights stay
+  fp32 in HBM in all of them, only what the tensor core multiplies differs):
+  'bf16x3': converter warps split every shared-memory operand tile into bf16 hi / mid
+  halves and each fp32 product is issued as hi*hi + mid*hi + hi*mid (kind::f16) — 2^-17
+  operand precision, the mode that meets the 1e-3 parity bar against the fp32 reference
+  (scripts/train.py:423) on the tensor core, and what bench.py measures by default.
+  'tf32': kind::tf32 on the fp32 words (2^-11 operand precision; producers hand over
+  round-to-nearest TF32 values) — 2/3 of the tensor-pipe time of 'bf16x3', ~1e-2 off the
+  reference end to end at benchmark size (tools/tf32_attribution.py): the labelled fast line.
+  'bf16': the bf16x3 kernels issuing hi*hi only (plain bf16 operands, BASELINE.json configs[3])."""
   global CONV_MATH
-  if mode not in ('fp32', 'tf32', 'tf32x3'):
-    raise ValueError("conv math must be 'fp32', 'tf32' or 'tf32x3'")
+  if mode not in ('fp32',) + TC_MODES:
+    raise ValueError("conv math must be one of 'fp32', 'tf32', 'bf16x3', 'bf16'")
   CONV_MATH = mode
 
 
 def _tc_math():
-  return CONV_MATH in ('tf32', 'tf32x3')
+  return CONV_MATH in TC_MODES
+
+
+def _math_id():
+  return _MATH_ID[CONV_MATH]
 
 
 def _tc_shape_ok(N, H, W, C, KH, KW, P, Cout, out_hw):
   """conv_tc_ok for a contiguous, 16-byte aligned NHWC tensor that does not exist yet."""
   return bool(_lib.load().sg2im_conv_tc_supported(N, H, W, C, C, KH, KW, 1, P, out_hw[0],
                                                   out_hw[1], Cout, Cout, 0))
-
-
-def split_tf32(x, parts, separate=False):
-  """x: (N,H,W,C)-shaped NHWC tensor or channel-prefix view.  hi = RN-TF32(x), lo = x - hi.
-  parts=3 -> (N,H,W,3C) [hi | lo | hi]; parts=2 -> (N,H,W,2C) [hi | lo];
-  separate=True -> (hi, lo) as two contiguous tensors."""
-  _chk(x)
-  N, H, W, C = x.shape
-  cs = _pixel_stride(x)
-  if cs is None:
-    x = x.contiguous()
-    cs = C
-  rows = N * H * W
-  dev = x.device
-  if separate:
-    hi = torch.empty(N, H, W, C, dtype=torch.float32, device=dev)
-    lo = torch.empty(N, H, W, C, dtype=torch.float32, device=dev)
-    _call_b(12 * rows * C, 'sg2im_split_tf32', _p(x), rows, C, cs, _p(hi), C, _p(lo), C, None, 0,
-            _stream())
-    _count()
-    return hi, lo
-  out = torch.empty(N, H, W, parts * C, dtype=torch.float32, device=dev)
-  base = out.data_ptr()
-  _call_b(4 * rows * C * (1 + parts), 'sg2im_split_tf32', _p(x), rows, C, cs, base, parts * C,
-          base + 4 * C, parts * C, (base + 8 * C) if parts == 3 else None, parts * C, _stream())
-  _count()
-  return out
-
-
-def _w3_fwd(w):
-  """OIHW weight (or the channel-prefix view weight[:, :Ci] of a contiguous one) ->
-  cat([hi, hi, lo], dim=1), shape (Co, 3*Ci, KH, KW): the forward operand of 'tf32x3'.  One
-  launch of the split kernel: per output channel the Ci*KH*KW floats are one row."""
-  Co, Ci, KH, KW = w.shape
-  T = KH * KW
-  if not (w.stride(3) == 1 and w.stride(2) == KW and w.stride(1) == T and w.stride(0) >= Ci * T):
-    w = w.contiguous()
-  C = Ci * T
-  out = torch.empty(Co, 3 * Ci, KH, KW, dtype=torch.float32, device=w.device)
-  base = out.data_ptr()
-  _call_b(16 * Co * C, 'sg2im_split_tf32', _p(w), Co, C, w.stride(0), base, 3 * C,
-          base + 8 * C, 3 * C, base + 4 * C, 3 * C, _stream())
-  _count()
-  return out
-
-
-def _w3_dgrad(weight):
-  """OIHW weight -> cat([hi, hi, lo], dim=0), shape (3*Co, Ci, KH, KW): the data-gradient
-  operand of 'tf32x3' (its reduction runs over the output channels)."""
-  weight = weight.contiguous()
-  Co, Ci, KH, KW = weight.shape
-  n = weight.numel()
-  out = torch.empty(3 * Co, Ci, KH, KW, dtype=torch.float32, device=weight.device)
-  base = out.data_ptr()
-  _call_b(16 * n, 'sg2im_split_tf32', _p(weight), 1, n, n, base, n, base + 8 * n, n,
-          base + 4 * n, n, _stream())
-  _count()
-  return out
 
 
 def _pixel_stride(x):
@@ -262,7 +213,7 @@ def conv_tc_ok(x, KH, KW, S, P, Cout, out_hw=None, y_cstride=None, y_coff=0):
 
 
 def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff=0,
-            tag='conv_fwd_tc', out_hw=None, stats=None, round_out=False, flops_div=1):
+            tag='conv_fwd_tc', out_hw=None, stats=None, round_out=False):
   """Tensor-core stride-1 convolution; x NHWC (channel-prefix view allowed),
   w_tc packed [KH*KW][Cout][Cin]; out_hw: explicit output size (reads outside
   the input are zero)."""
@@ -271,11 +222,10 @@ def conv_tc(x, w_tc, bias, KH, KW, P, Cout, act=0, slope=0.0, out=None, out_coff
   Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
   if out is None:
     out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
-  # flops_div: the 'tf32x3' route issues 3x the MMAs for the same ALGORITHMIC work
-  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW / flops_div, (N, H, W, C, Cout, KH, 1)):
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
     _call('sg2im_conv_tc', _p(x), cs, N, H, W, C, _p(w_tc), _p(bias), KH, KW, P, Hout, Wout,
           Cout, int(act), float(slope), _p(out), out.size(3), out_coff, _p(stats),
-          int(round_out), _stream())
+          int(round_out), _math_id(), _stream())
   _count()
   return out
 
@@ -293,18 +243,12 @@ def _pack(weight, cin_use, want_fwd, want_dgrad=None):
   f = torch.empty((T, Co, cu), dtype=torch.float32, device=dev) if want_fwd else None
   d = torch.empty((T, cu, Co), dtype=torch.float32, device=dev) if want_dgrad else None
   _call_b(4 * T * Co * cu * (1 + int(want_fwd) + int(want_dgrad)),
-          'sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(f), _p(d), 1,
-          _stream())                                        # RN-TF32: the tensor core would truncate
+          'sg2im_pack_weights', _p(weight), Co, Ci, cu, T, _p(f), _p(d), int(CONV_MATH == 'tf32'),
+          _stream())                                        # tf32: RN-TF32 (the tensor core would truncate)
   _count()
   if want_fwd and want_dgrad:
     return f, d
   return f if want_fwd else d
-
-
-# Training: pack the forward AND the data-gradient operand layouts in the forward
-# pass with one launch (the weights are read once; the dgrad copy is kept for the
-# backward pass) instead of one launch per pass.  Off until timed on hardware.
-PACK_BOTH = os.environ.get('SG2IM_PACK_BOTH') == '1'
 
 
 def pack_tc_fwd(weight, cin_use=None):
@@ -329,12 +273,10 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   return grad
 
 
-def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None, flops_div=1):
+def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
   """Returns dw packed (KH*KW*Cin, Cout).  accumulate_into: a contiguous buffer of that size
   the kernels ADD into (they combine partial tiles with atomics anyway) instead of a fresh
-  zeroed one — e.g. the parameter's slice of the flat gradient bucket.  tc: use the tensor-core
-  kernel when the shape allows (default: only in 'tf32' mode; the 'tf32x3' route passes its
-  split operands with tc=True)."""
+  zeroed one — e.g. the parameter's slice of the flat gradient bucket."""
   _chk(x)
   dy = _chk(dy).contiguous()
   N, Hin, Win, Cin = x.shape
@@ -345,14 +287,14 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None, flops_div=1):
     dw = accumulate_into.view(KH * KW * Cin, Cout)
   else:
     dw = torch.zeros(KH * KW * Cin, Cout, dtype=torch.float32, device=x.device)
-  if (CONV_MATH == 'tf32' if tc is None else tc) and S == 1:
+  if _tc_math() and S == 1:
     cs = _pixel_stride(x)
     if (cs is not None and x.data_ptr() % 16 == 0 and _lib.load().sg2im_conv_wgrad_tc_supported(
         N, Hin, Win, Cin, cs, KH, KW, S, P, Hout, Wout, Cout)):
-      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW / flops_div,
+      with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
                  (N, Hin, Win, Cin, Cout, KH, S)):
         _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Hout, Wout,
-              Cout, _p(dw), _stream())
+              Cout, _p(dw), _math_id(), _stream())
       _count()
       return dw
   with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
@@ -361,29 +303,6 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, tc=None, flops_div=1):
           Hout, Wout, Cout, _p(dw), _stream())
   _count()
   return dw
-
-
-def conv_wgrad_x3(x, dy, KH, KW, P):
-  """Weight gradient of a stride-1 conv in 'tf32x3' mode: dW = sum over pixels of x (x) dy with
-  x = hi_x + lo_x, dy = hi_dy + lo_dy.  The reduction runs over pixels, so the three products
-  cannot share one accumulator along K; instead the input-channel axis carries two of them:
-  wgrad([hi_x | lo_x], hi_dy) -> rows [hi*hi ; lo*hi], plus wgrad(hi_x, lo_dy).  Returns dw
-  packed (KH*KW*Cin, Cout), or None when the channel counts rule the split form out."""
-  N, H, W, Ci = x.shape
-  Co = dy.size(3)
-  if Ci % 4 or Co % 4:
-    return None
-  Ho, Wo = dy.size(1), dy.size(2)
-  sup = _lib.load().sg2im_conv_wgrad_tc_supported
-  if not (sup(N, H, W, 2 * Ci, 2 * Ci, KH, KW, 1, P, Ho, Wo, Co)
-          and sup(N, H, W, Ci, 2 * Ci, KH, KW, 1, P, Ho, Wo, Co)):
-    return None                                  # the exact-fp32 kernel takes the unsplit operands
-  T = KH * KW
-  x2 = split_tf32(x, 2)
-  dy_hi, dy_lo = split_tf32(dy, 2, separate=True)
-  a = conv_wgrad(x2, dy_hi, KH, KW, 1, P, tc=True, flops_div=3).view(T, 2 * Ci, Co)
-  b = conv_wgrad(x2[..., :Ci], dy_lo, KH, KW, 1, P, tc=True, flops_div=3).view(T, Ci, Co)
-  return (a[:, :Ci] + a[:, Ci:] + b).reshape(T * Ci, Co)
 
 
 def colsum(x2d):
@@ -407,8 +326,9 @@ def act_bwd(dy, y, slope):
 
 # One pass for the activation backward and the bias gradient of a conv+bias+LeakyReLU epilogue
 # (instead of act_bwd + the three-launch colsum), accumulating straight into the bias' slot of the
-# flat gradient bucket inside TrainStep (DIRECT_WGRAD).  Off until timed on hardware.
-FUSE_ACT_BWD = os.environ.get('SG2IM_ACTBWD_FUSED') == '1'
+# flat gradient bucket inside TrainStep (DIRECT_WGRAD).  Default since round 2 (validated and timed
+# on the B200); SG2IM_ACTBWD_FUSED=0 restores the separate passes.
+FUSE_ACT_BWD = os.environ.get('SG2IM_ACTBWD_FUSED') != '0'
 
 
 def act_bwd_bias(dy, y, slope, bias):
@@ -424,8 +344,9 @@ def act_bwd_bias(dy, y, slope, bias):
   direct = (DIRECT_WGRAD and g is not None and g.is_contiguous() and g.numel() == C
             and g.data_ptr() % 4 == 0)
   db = g if direct else torch.zeros(C, dtype=torch.float32, device=dy.device)
-  _call('sg2im_act_bwd_colsum', _p(dy), _p(y), float(slope), dy.numel() // C, C, _p(dx), _p(db),
-        _stream())
+  _call_b(12 * dy.numel() + 4 * C,
+          'sg2im_act_bwd_colsum', _p(dy), _p(y), float(slope), dy.numel() // C, C, _p(dx), _p(db),
+          _stream())
   _count()
   return dx, (None if direct else db)
 
@@ -566,21 +487,8 @@ class Conv(torch.autograd.Function):
       assert out_hw[0] <= Hout and out_hw[1] <= Wout and conv_tc_ok(x, KH, KW, stride, pad, Co, out_hw)
       Hout, Wout = out_hw
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
-    w_dgrad = None
-    x3 = (CONV_MATH == 'tf32x3' and stride == 1 and Ci % 4 == 0
-          and _tc_shape_ok(x.size(0), x.size(1), x.size(2), 3 * Ci, KH, KW, pad, Co, (Hout, Wout)))
-    if x3:
-      # error-compensated operands, one launch: [hi_x | lo_x | hi_x] * [hi_w | hi_w | lo_w]
-      y = conv_tc(split_tf32(x, 3), pack_tc_fwd(_w3_fwd(w_used)), bias, KH, KW,
-                  pad, Co, act, slope, out_hw=(Hout, Wout),
-                  stats=stats_out if fused_stats else None, flops_div=3)
-    elif CONV_MATH == 'tf32' and conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
-      if (PACK_BOTH and ctx.needs_input_grad[0] and KH == KW and stride == 1
-          and KH - 1 - pad >= 0):
-        w_fwd, w_dgrad = _pack(weight, Ci, True, True)
-      else:
-        w_fwd = pack_tc_fwd(weight, Ci)
-      y = conv_tc(x, w_fwd, bias, KH, KW, pad, Co, act, slope,
+    if _tc_math() and conv_tc_ok(x, KH, KW, stride, pad, Co, (Hout, Wout)):
+      y = conv_tc(x, pack_tc_fwd(weight, Ci), bias, KH, KW, pad, Co, act, slope,
                   out_hw=(Hout, Wout), stats=stats_out if fused_stats else None,
                   round_out=round_out)
     else:
@@ -592,8 +500,6 @@ class Conv(torch.autograd.Function):
       _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (stride, pad, act, slope, Ci, tuple(weight.shape))
-    ctx.x3 = CONV_MATH == 'tf32x3'
-    ctx.w_dgrad = w_dgrad                       # packed in the forward pass (PACK_BOTH) or None
     ctx.save_for_backward(x, weight, y if act else None)
     ctx.bias_ref = bias                         # the Parameter itself (its .grad slot), not a saved value
     ctx.has_bias = bias is not None
@@ -617,24 +523,15 @@ class Conv(torch.autograd.Function):
     if ctx.needs_input_grad[0]:
       w_used = weight if Ci == Ci_w else weight[:, :Ci]
       pad_t = KH - 1 - pad
-      if (ctx.x3 and KH == KW and pad_t >= 0 and stride == 1 and Co % 4 == 0
-          and _tc_shape_ok(dy.size(0), dy.size(1), dy.size(2), 3 * Co, KH, KW, pad_t, Ci,
-                           (x.size(1), x.size(2)))):
-        dx = conv_tc(split_tf32(dy, 3), pack_tc_dgrad(_w3_dgrad(weight), Ci), None,
-                     KH, KW, pad_t, Ci, tag='conv_dgrad_tc', out_hw=(x.size(1), x.size(2)),
-                     flops_div=3)
-      elif (not ctx.x3 and KH == KW and pad_t >= 0 and stride == 1
-            and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
-        w_dgrad = ctx.w_dgrad if ctx.w_dgrad is not None else pack_tc_dgrad(weight, Ci)
-        dx = conv_tc(dy, w_dgrad, None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
+      if (KH == KW and pad_t >= 0 and stride == 1
+          and conv_tc_ok(dy, KH, KW, stride, pad_t, Ci, (x.size(1), x.size(2)))):
+        dx = conv_tc(dy, pack_tc_dgrad(weight, Ci), None, KH, KW, pad_t, Ci, tag='conv_dgrad_tc',
                      out_hw=(x.size(1), x.size(2)))
       else:
         dx = conv_igemm(1, dy, pack_conv_dgrad(w_used), None, KH, KW, stride, pad,
                         (x.size(1), x.size(2)), Ci)
     if ctx.needs_input_grad[1]:
-      dwp = conv_wgrad_x3(x, dy, KH, KW, pad) if (ctx.x3 and stride == 1) else None
-      if dwp is None:
-        dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
+      dwp = conv_wgrad(x, dy, KH, KW, stride, pad)
       dw = unpack_wgrad_oihw(dwp, wshape, Ci)
     if ctx.has_bias and ctx.needs_input_grad[2] and not db_done:
       if ctx.zero_bias_grad:
@@ -668,7 +565,7 @@ def conv_tc_kcc(x, w_kcc, rows_full, dgrad, bias, KH, KW, P, Cout, act=0, slope=
   with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
     _call('sg2im_conv_tc_kcc', _p(x), cs, N, H, W, C, _p(w_kcc), rows_full, int(dgrad), _p(bias), KH,
           KW, P, Hout, Wout, Cout, int(act), float(slope), _p(out), Cout, 0, _p(stats),
-          int(round_out), _stream())
+          int(round_out), _math_id(), _stream())
   _count()
   return out
 
@@ -824,7 +721,9 @@ def _grad_slot(weight):
 
 
 def _shadow(weight):
-  sh = getattr(weight, '_tc_shadow', None)
+  """RN-TF32 shadow of a parameter (FlatAdam keeps it current): what the 'tf32' kernels read —
+  the hardware would truncate the fp32 master.  The bf16 modes split the master itself."""
+  sh = getattr(weight, '_tc_shadow', None) if CONV_MATH == 'tf32' else None
   return None if sh is None else _kcc_view(sh)
 
 
@@ -845,13 +744,9 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
   normalise/activate pass in between that would round it): write RN-TF32 values."""
   round_out = bool(round_out) and CONV_MATH == 'tf32'
   Co, C, KH, KW = weight.shape
-  kcc = CONV_MATH == 'tf32' and is_kcc(weight)
+  kcc = _tc_math() and is_kcc(weight)
   s2d = (_tc_math() and stride == 2 and pad == 0 and in_ch is None
          and KH == 4 and KW == 4 and x.size(1) >= 4 and x.size(2) >= 4 and Co % 32 == 0)
-  if s2d and CONV_MATH == 'tf32x3':
-    # the cropped-output form exists on the tensor-core kernel only: the split operand must tile
-    s2d = _tc_shape_ok(x.size(0), (x.size(1) + 1) // 2, (x.size(2) + 1) // 2, 12 * C, 2, 2, 0, Co,
-                       (conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)))
   if s2d:
     # 4x4 stride-2 'valid' conv (the discriminators, scripts/train.py:122-130) ==
     # 2x2 stride-1 conv on the space-to-depth input: runs on the tensor-core
@@ -863,7 +758,7 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
       w2 = weight.permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
       w2 = w2.reshape(4, 4 * C, Co)
       if conv_tc_ok(xs, 2, 2, 1, 0, Co, (Ho, Wo)):
-        sh = getattr(weight, '_tc_shadow', None)
+        sh = getattr(weight, '_tc_shadow', None) if CONV_MATH == 'tf32' else None
         w2r = None
         if sh is not None:
           w2r = sh.detach().permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
@@ -890,7 +785,7 @@ def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
   M, K = x2d.shape
   rnd = bool(round_out) and CONV_MATH == 'tf32'
   x4 = x2d.reshape(M, 1, 1, K)
-  if CONV_MATH == 'tf32' and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
+  if _tc_math() and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
     y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd,
                       _grad_slot(weight), _shadow(weight))
   else:

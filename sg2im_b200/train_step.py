@@ -180,8 +180,10 @@ class TrainStep(object):
       if fused_adam == 'flat':
         # one streaming kernel per optimiser over flat parameter / moment buckets
         self.buckets[name] = FlatGrads(net.parameters(), align=4)
+        # 'tf32' reads an RN-TF32 shadow of the weights; the bf16 modes split the masters in-kernel
+        from . import ops as _ops
         self.opts[name] = FlatAdam(self.buckets[name], lr=a['learning_rate'],
-                                   shadow=weights == 'kcc')
+                                   shadow=weights == 'kcc' and _ops.CONV_MATH == 'tf32')
       else:
         # kcc: the weight-gradient kernels write float4 atomics straight into the slots
         self.buckets[name] = FlatGrads(net.parameters(), align=4 if weights == 'kcc' else 1)

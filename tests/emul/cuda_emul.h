@@ -35,6 +35,8 @@ typedef int cudaError_t;
 
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
   unsigned x, y, z;

@@ -19,6 +19,11 @@
 //   * MN-major SWIZZLE_128B_BASE32B operand, tf32: element (mn, k) at
 //     start + (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + 4*(mn%32);
 //   * tcgen05.mma kind::tf32 ignores the 13 low mantissa bits of its operands, accumulates fp32;
+//   * kind::f16 with bf16 operands (K = 16): K-major SWIZZLE_128B element (row r, k) at
+//     start + (r/8)*SBO + (r%8)*128 + 2k; MN-major SWIZZLE_128B element (mn, k) at
+//     start + (mn/64)*LBO + (k/8)*SBO + (k%8)*128 + 2*(mn%64) (CUTLASS's canonical layouts,
+//     cute/atom/mma_traits_sm100.hpp; the 16-bit MN-major form is pinned on hardware by
+//     tools/umma_probe_bf16.cu), both through the 16-byte-chunk XOR of SWIZZLE_128B;
 //   * accumulator D[row][col] lives at TMEM lane `row`, column `d_tmem.col + col`.
 // Only the exact XOR pattern of SWIZZLE_128B_ATOM_32B is an assumption; it cancels out because
 // producer (TMA) and consumer (MMA) use the same function.
@@ -303,6 +308,66 @@ static inline float emul_desc_elem(Block* blk, uint32_t lo, uint32_t hi, bool mn
   if (a < emul::SMEM_VA || a - emul::SMEM_VA + 4 > blk->smem_bytes) { std::fprintf(stderr, "emul: MMA operand read outside shared memory\n"); std::abort(); }
   float v; std::memcpy(&v, emul::host_of(blk, a), 4);
   return emul::tf32_trunc(v);
+}
+
+// one bf16 operand element (kind::f16) through a shared-memory matrix descriptor
+static inline float emul_desc_elem16(Block* blk, uint32_t lo, uint32_t hi, bool mn_major, int idx, int k) {
+  const uint32_t start = (lo & 0x3fffu) << 4, lbo = ((lo >> 16) & 0x3fffu) << 4, sbo = (hi & 0x3fffu) << 4;
+  const uint32_t layout = (hi >> 29) & 7u;
+  if (layout != 2u) { std::fprintf(stderr, "emul: bf16 operand must be SWIZZLE_128B\n"); std::abort(); }
+  uint32_t a;
+  if (!mn_major)
+    a = emul::swz128(start + (uint32_t)(idx >> 3) * sbo + (uint32_t)(idx & 7) * 128u + (uint32_t)k * 2u);
+  else
+    a = emul::swz128(start + (uint32_t)(idx >> 6) * lbo + (uint32_t)(k >> 3) * sbo +
+                     (uint32_t)(k & 7) * 128u + (uint32_t)(idx & 63) * 2u);
+  if (a < emul::SMEM_VA || a - emul::SMEM_VA + 2 > blk->smem_bytes) { std::fprintf(stderr, "emul: MMA operand read outside shared memory\n"); std::abort(); }
+  uint16_t h; std::memcpy(&h, emul::host_of(blk, a), 2);
+  uint32_t u = (uint32_t)h << 16;
+  float v; std::memcpy(&v, &u, 4);
+  return v;
+}
+static inline void emul_mma1_f16(Block* blk, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  if (M != 128 || N < 16 || N > 256 || (N & 15) || ((idesc >> 7) & 7u) != 1u || ((idesc >> 10) & 7u) != 1u ||
+      ((idesc >> 4) & 3u) != 1u) {
+    std::fprintf(stderr, "emul: unsupported kind::f16 instruction descriptor %x\n", idesc); std::abort();
+  }
+  const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xffffu;
+  if (lane0 != 0 || col0 + (uint32_t)N > 512u) { std::fprintf(stderr, "emul: accumulator outside TMEM\n"); std::abort(); }
+  static float A[128][16], B[256][16];
+  for (int m = 0; m < M; ++m) for (int k = 0; k < 16; ++k) A[m][k] = emul_desc_elem16(blk, a_lo, a_hi, a_mn, m, k);
+  for (int n = 0; n < N; ++n) for (int k = 0; k < 16; ++k) B[n][k] = emul_desc_elem16(blk, b_lo, b_hi, b_mn, n, k);
+  for (int m = 0; m < M; ++m) {
+    float* drow = &blk->tmem[(size_t)m * 512 + col0];
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? drow[n] : 0.f;
+      for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      drow[n] = acc;
+    }
+  }
+}
+static inline void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t) {
+  if (emul_lane() != 0) return;                           // elect.sync: one lane issues
+  Block* blk = emul::current();
+  emul::pipe_push(blk->rank, [=]() { emul_mma1_f16(blk, d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); });
+}
+static inline void fence_proxy_async() {}
+// round-to-nearest-even bf16 (what cvt.rn.bf16x2.f32 does), packed pair, x0 in the low half
+static inline uint32_t emul_bf16_rn(float f) {
+  uint32_t u; std::memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;  // inf / nan: truncate
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+static inline void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+  const uint32_t h0 = emul_bf16_rn(x0), h1 = emul_bf16_rn(x1);
+  hi = h0 | (h1 << 16);
+  uint32_t u0 = h0 << 16, u1 = h1 << 16;
+  float f0, f1; std::memcpy(&f0, &u0, 4); std::memcpy(&f1, &u1, 4);
+  mid = emul_bf16_rn(x0 - f0) | (emul_bf16_rn(x1 - f1) << 16);
 }
 
 // tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words: what the tensor pipe does

@@ -1,0 +1,308 @@
+"""GPU parity tests of the 'bf16x3' tensor-core arithmetic — the mode bench.py measures.
+
+The tcgen05 kernels keep fp32 tensors in HBM; converter warps split every shared-memory operand
+tile into bf16 hi / mid halves and each fp32 product is issued as hi*hi + mid*hi + hi*mid
+(kind::f16, fp32 accumulate).  Operand precision 2^-17, so — unlike 'tf32' (2^-11) — the north
+star's 1e-3 bound against the fp32 reference (scripts/train.py:423: fp32 everywhere) holds with
+two orders of magnitude to spare, on ARBITRARY fp32 operands:
+
+  * per convolution / Linear (forward, data gradient, weight gradient; packed OIHW masters and
+    weights read in place from the weight-gradient layout): 5e-5 against an fp64 convolution;
+  * generator / discriminator forward vs the reference-generated goldens and the losses of the
+    reference's two training iterations: the SAME 1e-3 assertions the exact-fp32 FFMA path is held
+    to (tests/test_gpu_model.py), i.e. tensor-core path == parity path;
+  * parameter gradients through the whole network vs the oracle's autograd: to the limit the
+    LeakyReLU / ReLU kinks allow any non-bit-identical implementation (explained at the test).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 5e-5
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+@pytest.fixture(autouse=True)
+def _math():
+  from sg2im_b200 import ops
+  ops.set_conv_math('bf16x3')
+  yield
+  ops.set_conv_math('fp32')
+
+
+def _kcc(w):
+  """OIHW-shaped tensor stored tap-major / input channel / output channel fastest
+  (layers.to_kcc_): ops.conv2d then reads it in place (no pack pass)."""
+  return w.permute(2, 3, 1, 0).contiguous().permute(3, 2, 0, 1)
+
+
+TC_CASES = [
+    # N, H, W, Cin, Cout, K, P
+    (2, 8, 8, 32, 64, 3, 1),           # per-tap kernel
+    (1, 64, 64, 64, 64, 3, 1),         # halo kernel
+    (5, 4, 4, 128, 128, 3, 1),         # mask head sizes
+    (7, 2, 2, 128, 128, 3, 1),
+    (2, 16, 16, 288, 512, 3, 1),       # two N tiles
+    (448, 1, 1, 384, 512, 1, 0),       # Linear as a 1x1 convolution over rows
+    (70, 1, 1, 512, 1152, 1, 0),
+    (2, 16, 16, 64, 64, 1, 0),
+    (2, 32, 16, 36, 64, 3, 1),         # Cin not a multiple of 32 (TMA zero fill), H != W
+    (2, 16, 16, 288, 64, 3, 1),        # dgrad output width 288 = 256 + 32: partial last N tile
+    (1, 32, 32, 160, 96, 3, 1),        # Cout 96: partial N tile / an unpaired 32-co atom
+    (4, 64, 64, 64, 64, 3, 1),         # wgrad: several pixel splits
+    (1, 128, 128, 288, 64, 3, 1),      # CRN stage-4 conv1 shape (one image)
+    (2, 16, 16, 512, 256, 3, 1),       # wgrad: 4 ci tiles, 2 taps per pass
+    (2, 8, 8, 1184, 1024, 3, 1),       # CRN stage-0 conv1 (8x8, widest reduction)
+]
+
+
+@pytest.mark.parametrize('kcc', [False, True], ids=['oihw', 'kcc'])
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P', TC_CASES)
+def test_conv_forward_dgrad_wgrad_arbitrary_fp32_operands(N, H, W, Ci, Co, K, P, kcc):
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(Ci + 7 * Co + H)
+  x = torch.randn(N, Ci, H, W, generator=g)
+  w = torch.randn(Co, Ci, K, K, generator=g) * 0.1
+  b = torch.randn(Co, generator=g)
+  gy = torch.randn(N, Co, H + 2 * P - K + 1, W + 2 * P - K + 1, generator=g)
+  xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+  yr = F.conv2d(xr, wr, br, padding=P)
+  yr.backward(gy.double())
+  xd = x.to(dev()).permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+  wd = (_kcc(w.to(dev())) if kcc else w.to(dev())).requires_grad_(True)
+  bd = b.to(dev()).requires_grad_(True)
+  assert ops.conv_tc_ok(xd, K, K, 1, P, Co), 'shape should take the tensor-core path'
+  assert ops.is_kcc(wd) == kcc
+  y_act = ops.conv2d(xd, wd, bd, 1, P, 1, 0.2)               # fused bias + LeakyReLU epilogue
+  assert rel_err(y_act.permute(0, 3, 1, 2), F.leaky_relu(yr, 0.2)) < TOL
+  y = ops.conv2d(xd, wd, bd, 1, P)
+  assert rel_err(y.permute(0, 3, 1, 2), yr) < TOL
+  y.backward(gy.to(dev()).permute(0, 2, 3, 1))
+  assert rel_err(xd.grad.permute(0, 3, 1, 2), xr.grad) < TOL
+  assert rel_err(wd.grad, wr.grad) < TOL
+  assert rel_err(bd.grad, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize('kcc', [False, True], ids=['oihw', 'kcc'])
+@pytest.mark.parametrize('N,H,W,Ci,Co', [(2, 32, 32, 3, 64), (2, 15, 15, 64, 128), (2, 63, 63, 64, 128),
+                                         (5, 16, 20, 8, 32)])
+def test_stride2_space_to_depth_route(N, H, W, Ci, Co, kcc):
+  """The discriminators' 4x4 stride-2 'valid' convolutions (2x2 stride-1 on the space-to-depth
+  input), incl. the 12-channel image layer whose single 32-channel block is mostly TMA zero fill."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(H * 7 + Ci)
+  x = torch.randn(N, Ci, H, W, generator=g)
+  w = torch.randn(Co, Ci, 4, 4, generator=g) * 0.1
+  b = torch.randn(Co, generator=g)
+  xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+  yr = F.conv2d(xr, wr, br, stride=2)
+  gy = torch.randn(yr.shape, generator=g)
+  yr.backward(gy.double())
+  xd = x.to(dev()).requires_grad_(True)
+  wd = (_kcc(w.to(dev())) if kcc else w.to(dev())).requires_grad_(True)
+  bd = b.to(dev()).requires_grad_(True)
+  y = ops.conv2d(xd.permute(0, 2, 3, 1), wd, bd, 2, 0)
+  assert rel_err(y.permute(0, 3, 1, 2), yr) < TOL
+  y.backward(gy.to(dev()).permute(0, 2, 3, 1))
+  assert rel_err(xd.grad, xr.grad) < TOL
+  assert rel_err(wd.grad, wr.grad) < TOL
+  assert rel_err(bd.grad, br.grad) < 1e-4
+
+
+def test_three_arithmetics_on_the_same_arbitrary_operands():
+  """tf32 / bf16 / bf16x3 on identical fp32 operands against an fp64 convolution: the compensated
+  form is >= 30x closer than TF32 and >= 100x closer than plain bf16."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(11)
+  N, H, W, Ci, Co = 2, 32, 32, 256, 128
+  x = torch.randn(N, H, W, Ci, generator=g)
+  w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.05
+  ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=1).permute(0, 2, 3, 1)
+  err = {}
+  for mode in ('tf32', 'bf16', 'bf16x3'):
+    ops.set_conv_math(mode)
+    y = ops.conv_tc(x.to(dev()), ops.pack_tc_fwd(w.to(dev())), None, 3, 3, 1, Co)
+    err[mode] = rel_err(y, ref)
+  print('rel err vs fp64:', err)
+  assert err['bf16x3'] < 2e-5
+  assert err['tf32'] > 30 * err['bf16x3'] and err['bf16'] > 100 * err['bf16x3']
+
+
+def test_full_size_stage4_conv_vs_exact_fp32_kernels():
+  """CRN stage-4 conv1 at the benchmark size (32 x 128 x 128, 288 -> 64), arbitrary fp32
+  operands: forward, data gradient and weight gradient of the tensor-core path against the
+  exact-fp32 FFMA kernels (which the small-size tests pin to the CPU oracle)."""
+  from sg2im_b200 import ops
+  torch.manual_seed(0)
+  N, H, W, Ci, Co = 32, 128, 128, 288, 64
+  d = dev()
+  x = torch.randn(N, H, W, Ci, device=d)
+  w = torch.randn(Co, Ci, 3, 3, device=d) * 0.05
+  gy = torch.randn(N, H, W, Co, device=d)
+  res = {}
+  for mode in ('fp32', 'bf16x3'):
+    ops.set_conv_math(mode)
+    xx = x.clone().requires_grad_(True)
+    ww = w.clone().requires_grad_(True)
+    y = ops.conv2d(xx, ww, None, 1, 1)
+    y.backward(gy)
+    res[mode] = (y.detach(), xx.grad, ww.grad)
+  for a, b, name in zip(res['bf16x3'], res['fp32'], ('fwd', 'dgrad', 'wgrad')):
+    assert rel_err(a, b) < 1e-4, name
+
+
+# ---------------------------------------------------------------------------
+# whole networks: the exact-fp32 path's own assertions, on the tensor core
+# ---------------------------------------------------------------------------
+
+def test_generator_and_discriminators_meet_the_fp32_bar():
+  import test_gpu_model as G
+  G.test_generator_forward_vg_coco_eval()
+  G.test_config1_sheep_forward_json()
+  G.test_discriminators_forward()
+
+
+def _pair(t):
+  hi = t.bfloat16().float()
+  return hi, (t - hi).bfloat16().float()
+
+
+class _PairRoundedFunctional(object):
+  """torch.nn.functional with conv2d / linear evaluated as this mode evaluates them — operands
+  split into bf16 hi + mid, products hi*hi + mid*hi + hi*mid, fp32 accumulation — i.e. the
+  REFERENCE restated in the mode's arithmetic.  Forward values only: the backward stays the
+  exact fp32 one (value = exact + (restated - exact).detach())."""
+
+  def __getattr__(self, k):
+    return getattr(F, k)
+
+  @staticmethod
+  def _three(op, x, w, b):
+    y = op(x, w, b)
+    with torch.no_grad():
+      (xh, xm), (wh, wm) = _pair(x), _pair(w)
+      y3 = op(xh, wh, b) + op(xm, wh, None) + op(xh, wm, None)
+    return y + (y3 - y).detach()
+
+  def conv2d(self, x, w, b=None, **kw):
+    return self._three(lambda a, c, d: F.conv2d(a, c, d, **kw), x, w, b)
+
+  def linear(self, x, w, b=None):
+    return self._three(F.linear, x, w, b)
+
+
+def test_parameter_gradients_vs_oracle_to_the_activation_kink_limit():
+  """Full backward (CRN, layout, mask head, graph convolution) vs the oracle's autograd.  The
+  convolution gradients themselves agree with fp64 to 5e-5 (tests above: no activation in between).
+  Through the network the bound is NOT the operand precision: an output y_i within the forward
+  error d of a LeakyReLU / ReLU kink takes the other branch, which changes that element's gradient
+  by (1 - slope) * dy_i; a parameter gradient summing n such elements moves by
+  ~sqrt(n * p(0) * 2d) * |dy| against sqrt(n) * |dy|, i.e. by ~sqrt(d / sigma_y) RELATIVE whatever
+  n is — ~5e-3 per layer at this mode's forward error d = 2e-5 (the exact-fp32 kernels, d ~ 1e-6,
+  sit at ~1e-3 for the same reason, as would cuDNN vs MKL), compounding towards the embeddings
+  which sit behind every kink.  So the check is made against the REFERENCE RESTATED with the same
+  arithmetic (the oracle with conv2d / linear evaluated as three bf16-pair products): the product
+  must reproduce ITS gradients to 5e-3 — same branches taken but for accumulation-order-level
+  differences, measured 2.5e-3 — while both sit the
+  same distance from the exact-fp32 gradients (printed; up to ~1e-1 on the embeddings, of which
+  one flipped element of 65536 in the last LeakyReLU already explains 3.8e-3 on that layer)."""
+  import test_gpu_model as G
+  from oracle import sg2im_oracle as orc
+  g = load_golden('generator.pt')
+  imgs, objs, boxes, triples, o2i, _ = g['batch']
+  kw = g['kwargs']
+  N = imgs.size(0)
+  noise = G._noise(5, N, kw['layout_noise_dim'], kw['image_size'])
+  wimg = torch.randn(N, 3, *kw['image_size'], generator=torch.Generator().manual_seed(9))
+  refs = {}
+  for name, fn in (('exact', None), ('pairs', _PairRoundedFunctional())):
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k
+              else v.clone()) for k, v in g['sd'].items()}
+    saved = orc.F
+    if fn is not None:
+      orc.F = fn
+    try:
+      ref = orc.generator_forward(sd, kw['image_size'], objs, triples, o2i, boxes_gt=boxes,
+                                  noise=noise, training=True, num_imgs=N)
+    finally:
+      orc.F = saved
+    (ref[0] * wimg).sum().add(ref[1].pow(2).sum()).backward()
+    refs[name] = sd
+  m = G._build_generator(g)
+  m.train()
+  d = dev()
+  out = m(objs.to(d), triples.to(d), o2i.to(d), boxes_gt=boxes.to(d), noise=noise.to(d), num_imgs=N)
+  ((out[0] * wimg.to(d)).sum() + out[1].pow(2).sum()).backward()
+  worst, worst_exact, inherent = 0.0, 0.0, 0.0
+  for k, p in m.named_parameters():
+    rg = refs['pairs'][k].grad
+    if rg is None or '.net.0.bias' in k or '.net.3.bias' in k:     # conv bias feeding a train-mode BN: true gradient 0
+      continue
+    e = rel_err(p.grad, rg)
+    worst = max(worst, e)
+    worst_exact = max(worst_exact, rel_err(p.grad, refs['exact'][k].grad))
+    inherent = max(inherent, rel_err(rg, refs['exact'][k].grad))
+    assert e < 5e-3, (k, e)
+  print('param-grad rel err: vs the reference in this arithmetic %.2e; vs exact fp32 %.2e '
+        '(the restated reference itself: %.2e)' % (worst, worst_exact, inherent))
+  assert worst_exact < 3 * inherent + 1e-3
+
+
+@pytest.mark.parametrize('weights,adam', [('oihw', None), ('kcc', 'flat')])
+def test_two_reference_training_iterations(weights, adam):
+  """The reference's two training iterations (golden losses from the unmodified scripts/train.py
+  step) with every convolution / Linear on the tensor core: losses within 1e-3 relative."""
+  import test_gpu_model as G
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  m, d_obj, d_img = G._build_all(g)
+  step = TrainStep(m, d_obj, d_img, weights=weights, fused_adam=adam)
+  batch = [t.to(dev()) for t in g['batch']]
+  kw = g['kwargs']
+  worst = 0.0
+  for it, seed in enumerate(g['noise_seeds']):
+    noise = G._noise(seed, batch[0].size(0), kw['layout_noise_dim'], kw['image_size']).to(dev())
+    losses, _ = step.step(batch, noise=noise)
+    for k, v in g['losses'][it].items():
+      e = abs(losses[k] - v) / max(1.0, abs(v))
+      worst = max(worst, e)
+      assert e <= 1e-3, (it, k, losses[k], v)
+  print('worst loss deviation under bf16x3 (%s)' % weights, worst)
+
+
+def test_benchmark_size_generator_forward_vs_exact_fp32_path():
+  """VG-128 generator (default architecture, 4 images) forward: tensor-core 'bf16x3' against the
+  exact-fp32 FFMA path of this library on the same weights / inputs / noise — the 1e-3 bar at
+  the benchmark architecture, where plain TF32 is ~1e-2 off (tools/tf32_attribution.py)."""
+  import contextlib
+  import io
+  from sg2im_b200 import ops
+  from sg2im_b200.model import Sg2ImModel
+  from sg2im_b200.synth import make_vocab, synth_batch
+  torch.manual_seed(0)
+  vocab = make_vocab(179, 46)
+  with contextlib.redirect_stdout(io.StringIO()):
+    m = Sg2ImModel(vocab, image_size=(128, 128), embedding_dim=128, gconv_dim=128, gconv_hidden_dim=512,
+                   gconv_num_layers=5, mask_size=16, layout_noise_dim=32,
+                   refinement_dims=(1024, 512, 256, 128, 64)).to(dev())
+  m.train()
+  batch = [t.to(dev()) for t in synth_batch(N=4, objs_per_img=9, rels_per_img=5, image_size=(128, 128),
+                                            num_objs=179, num_preds=46, seed=1)]
+  imgs, objs, boxes, triples, o2i, _ = batch
+  noise = torch.randn(4, 32, 128, 128, device=dev())
+  outs = {}
+  for mode in ('fp32', 'bf16x3', 'tf32'):
+    ops.set_conv_math(mode)
+    with torch.no_grad():
+      outs[mode] = [t.clone() for t in m(objs, triples, o2i, boxes_gt=boxes, noise=noise, num_imgs=4)]
+  e3 = [rel_err(a, b) for a, b in zip(outs['bf16x3'], outs['fp32'])]
+  e1 = [rel_err(a, b) for a, b in zip(outs['tf32'], outs['fp32'])]
+  print('bf16x3 vs fp32 (img, boxes, masks, rel):', e3, ' tf32 vs fp32:', e1)
+  assert max(e3) < 1e-3

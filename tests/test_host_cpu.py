@@ -199,7 +199,7 @@ def test_unsupported_tensor_core_call_is_refused_without_a_device():
   ptr = ctypes.addressof(buf)
   with pytest.raises(RuntimeError) as e:
     _lib.call('sg2im_conv_tc', ptr, 161, 1, 4, 4, 161, ptr, None, 3, 3, 1, 4, 4, 64, 0, 0.0, ptr, 64, 0,
-              None, 0, None)
+              None, 0, 1, None)
   assert 'unsupported shape' in str(e.value)
 
 

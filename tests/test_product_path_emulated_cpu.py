@@ -160,10 +160,8 @@ def test_flat_adam_training_iterations_fp32(emul_next):
 
 @needs_tc
 def test_staged_tensor_core_switches_through_the_op_layer(emul_next):
-  R.test_pack_both_layouts_in_one_launch()
-  R.test_wgrad_cluster_multicast_matches_single_cta(4, 16, 16, 64, 64, 3)
-  R.test_wgrad_cluster_multicast_matches_single_cta(2, 16, 24, 64, 192, 3)
   R.test_eval_bn_folding_sheep('tf32')
+  R.test_eval_bn_folding_sheep('bf16x3')
 
 
 @needs_tc
@@ -290,7 +288,7 @@ def test_hbm_kernel_profiling_hooks_of_the_benchmark(emul, monkeypatch):
   seen = {e[0] for e in entries}
   want = {'sg2im_triple_gather', 'sg2im_segment_sum', 'sg2im_layout_fwd', 'sg2im_layout_bwd',
           'sg2im_crop_fwd', 'sg2im_crop_bwd', 'sg2im_scale_act_fwd', 'sg2im_scale_act_bwd_reduce',
-          'sg2im_scale_act_bwd_apply', 'sg2im_bn_stats', 'sg2im_act_bwd', 'sg2im_avgpool2_fwd',
+          'sg2im_scale_act_bwd_apply', 'sg2im_bn_stats', 'sg2im_act_bwd_colsum', 'sg2im_avgpool2_fwd',
           'sg2im_avgpool2_bwd'}
   if HAVE_TC:
     want |= {'sg2im_s2d_fwd', 'sg2im_s2d_bwd', 'sg2im_pack_weights', 'sg2im_unpack_wgrad'}
@@ -322,17 +320,19 @@ def test_build_cnn_residual_blocks_pooling_instance_norm(emul_next):
 
 
 @needs_tc
-def test_error_compensated_tensor_core_mode(emul_next, monkeypatch):
-  """ops.set_conv_math('tf32x3') on the functional tensor-core model: split kernel, generator
-  forward at 1e-4 of the fp32 reference (plain TF32: 2.7e-3), gradients and the reference's two
-  training iterations within the exact-fp32 tests' tolerances."""
-  R.test_split_tf32_kernel()
-  R.test_tf32x3_generator_forward_meets_the_fp32_bar()
+def test_bf16x3_tensor_core_mode_meets_the_fp32_bar(emul_next, monkeypatch):
+  """ops.set_conv_math('bf16x3') end to end on the functional tensor-core model — the product's op
+  layer, the in-kernel operand split and the three-product MMA issue of every convolution /
+  Linear: generator forward vs the reference-generated golden and parameter gradients vs the
+  oracle's autograd to the activation-kink limit (see tests/test_gpu_bf16x3.py)."""
+  import test_gpu_bf16x3 as B
+  monkeypatch.setattr(G, 'dev', lambda: torch.device('cpu'))
+  R._with_math('bf16x3', G.test_generator_forward_vg_coco_eval)
+  monkeypatch.setattr(B, 'dev', lambda: torch.device('cpu'))
+  R._with_math('bf16x3', B.test_parameter_gradients_vs_oracle_to_the_activation_kink_limit)
   if os.environ.get('SG2IM_FULL_EMUL') == '1':
-    R.test_tf32x3_gradients_and_training_iterations_meet_the_fp32_bar(monkeypatch)
-  else:                                              # default suite: the gradient check only
-    monkeypatch.setattr(G, 'dev', lambda: torch.device('cpu'))
-    R._with_math('tf32x3', G.test_generator_gradients_vs_oracle)
+    for args in (('oihw', None), ('kcc', 'flat')):
+      R._with_math('bf16x3', lambda: B.test_two_reference_training_iterations(*args))
 
 
 def test_layout_gradient_wrt_boxes_kernel(emul_next, monkeypatch):
