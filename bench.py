@@ -69,6 +69,7 @@ def model_kwargs(cfg):
 
 
 D_ARCH = 'C4-64-2,C4-128-2,C4-256-2'
+MMA_WORK = {'bf16x3': 3.0, 'tf32': 2.0, 'bf16': 1.0}
 
 
 def hbm_table(entries, steps, peak_gbs, step_ms):
@@ -204,14 +205,24 @@ def cpu_reference_arm(cfg, steps, warmup, sample_imgs, budget_s=25.0):
               ms_per_step=mean * 1e3)
 
 
+def cpu_sample_images(cfg):
+  """Images per CPU step: the full per-GPU shard (the same batch as one GPU
+  processes, so BatchNorm statistics and the per-step work match the GPU arm's), unless the
+  reference's (O, D, H, W) layout temporary (sg2im/layout.py:86-90) would exceed ~6 GB of host
+  memory (the dense-graph stress config): then 8 images."""
+  H, W = cfg['image_size']
+  objs = cfg['N'] * (cfg['objs_per_img'] + 1)
+  return cfg['N'] if objs * 128 * H * W * 4 <= 6e9 else min(cfg['N'], 8)
+
+
 def run_reference(args, cfg):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   steps = max(1, min(args.steps, 3))
   warm = 1 if args.warmup > 0 else 0
-  sample = min(cfg['N'], 8)
-  r = cpu_reference_arm(cfg, steps, warm, sample, budget_s=120.0)
+  sample = cpu_sample_images(cfg)
+  r = cpu_reference_arm(cfg, steps, warm, sample, budget_s=150.0)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
       'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': r['ms_per_step'],
@@ -329,6 +340,12 @@ def run_b200(args, cfg):
     f = fam.setdefault(name, [0.0, 0.0, 0])
     f[0] += flops; f[1] += t; f[2] += 1
   roof = None
+  traffic = {}
+  try:
+    tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    traffic = tj.get(args.math, {}) if args.workload == 'vg128' else {}
+  except Exception:
+    traffic = {}
   if fam:
     conv_ms = sum(v[1] for v in fam.values())
     conv_fl = sum(v[0] for v in fam.values())
@@ -336,10 +353,12 @@ def run_b200(args, cfg):
     ach = conv_fl / (conv_ms * 1e-3) / 1e12
     roof = {'bound': 'tensor', 'kernel': 'conv implicit GEMM (fwd+dgrad+wgrad)',
             'achieved': ach, 'peak': pk['tf'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf'],
-            # dram__bytes_read.sum + dram__bytes_write.sum of the top kernel (conv_tc_halo_kernel,
-            # stage-4 conv1 shape, one launch) from the committed ncu --set full capture
-            # profiles/r01_prof_conv_tc_halo.txt: 630.0 + 109.9 MB = the algorithmic 604 + 134 MB
-            'traffic': 739.9e6, 'traffic_unit': 'bytes/launch (top kernel, ncu)',
+            # dram__bytes_read.sum + dram__bytes_write.sum of the top kernel from the committed
+            # `ncu --set full` capture of THIS build and arithmetic (profiles/traffic.json, written by
+            # tools/ncu_traffic.py from the .ncu-rep); null when no capture of the current build exists
+            'traffic': traffic.get('bytes_per_launch'), 'traffic_unit': 'bytes/launch (top kernel, ncu)',
+            'traffic_kernel': traffic.get('kernel'), 'traffic_algorithmic_bytes': traffic.get('algorithmic_bytes'),
+            'traffic_source': traffic.get('source'),
             'peak_source': pk['src'],
             'share_of_step': (conv_ms / prof_steps) / (ms / args.steps),
             'launches_per_step': sum(v[2] for v in fam.values()) / prof_steps,
@@ -351,9 +370,11 @@ def run_b200(args, cfg):
                           'tflops': round(v[0] / (v[1] * 1e-3) / 1e12, 1) if v[1] > 0 else 0.0,
                           'launches_per_step': v[2] / prof_steps}
                          for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])[:12]],
-            # the path multiplies in TF32, whose tensor-pipe rate is half the bf16 rate the
-            # measured peak was taken at: fraction against that halved figure as well
-            'peak_tf32_est': pk['tf'] / 2.0, 'frac_of_tf32_est': ach / (pk['tf'] / 2.0),
+            # tensor-pipe work per algorithmic FLOP in this arithmetic, in units of a dense bf16 FLOP
+            # (the measured peak's): bf16x3 issues 3 bf16 products, tf32 runs at half the bf16 rate
+            'mma_work_per_flop': MMA_WORK.get(ops.CONV_MATH),
+            'frac_of_arithmetic_ceiling': (ach * MMA_WORK[ops.CONV_MATH] / pk['tf']
+                                           if ops.CONV_MATH in MMA_WORK else None),
             'note': 'achieved = algorithmic conv FLOPs / summed CUDA-event kernel time of the same '
                     'step launched eagerly right after the timed (graph-replayed) region; traffic: '
                     'see profiles/ (ncu --set full per kernel)'}
@@ -381,7 +402,7 @@ def run_b200(args, cfg):
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    r = cpu_reference_arm(cfg, steps=2, warmup=1, sample_imgs=min(cfg['N'], 8))
+    r = cpu_reference_arm(cfg, steps=2, warmup=1, sample_imgs=cpu_sample_images(cfg), budget_s=40.0)
     cpu = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
 
   if rank == 0:

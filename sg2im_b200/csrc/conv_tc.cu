@@ -21,7 +21,8 @@
 //   i overlaps the MMAs of tile i+1; persistent CTAs, static tile striding.
 // * Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
 //   epilogue (tcgen05.ld -> bias/LeakyReLU -> 128-bit global stores into the
-//   destination channel slice), warps 6-9 operand converters (MATH 1 only).
+//   destination channel slice), warps 6-13 operand converters (MATH 1 only; two groups of four
+//   warps that take alternate pipeline stages).
 // Replaces cuDNN's conv behind nn.Conv2d (sg2im/crn.py:41-45,80-82;
 // model.py:100) for the shapes that dominate the step.
 #include <cstdlib>
@@ -33,7 +34,8 @@ constexpr int TILE_M = 128;
 constexpr int KB_BYTES = 128;                 // 32 fp32 channels per k-block row
 constexpr int A_STAGE_BYTES = TILE_M * KB_BYTES;
 constexpr int NUM_THREADS = 192;
-constexpr int CONV_THREADS = 128;             // converter warps of the bf16 arithmetic
+constexpr int CONV_THREADS = 128;             // one converter group (4 warps) of the bf16 arithmetic
+constexpr int CONV_GROUPS = 2;                // per-tap kernel: groups take alternate pipeline stages
 
 struct TcParams {
   int N, Hout, Wout, Cin, Cout;
@@ -82,7 +84,7 @@ struct Cfg {
 // Modes 1/2 remove every pack / unpack pass when the master weights live in that layout
 // (sg2im_conv_tc_kcc; validated on the B200 in round 2).
 template <int BN, int WMODE, int MATH>
-__global__ void __launch_bounds__(NUM_THREADS + (MATH ? CONV_THREADS : 0), 1)
+__global__ void __launch_bounds__(NUM_THREADS + (MATH ? CONV_GROUPS * CONV_THREADS : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   using C = Cfg<BN>;
@@ -251,28 +253,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   } else if constexpr (MATH == 1) {
-    // ===================== operand converters (warps 6..9) =====================
+    // ===================== operand converters (warps 6..13, two groups) =====================
     // every landed stage: the 128 A rows and the B rows (WMODE 1: the row pairs of adjacent
-    // 32-co atoms) are split in place, then each warp signals `ready`
-    const int ct = (int)threadIdx.x - 6 * 32;
+    // 32-co atoms) are split in place, then each warp of the group signals `ready`.  Group g owns
+    // the pipeline slots of parity g (STAGES is even: consecutive stages alternate), so the fixed
+    // latency of one wait -> load -> split -> store -> fence -> arrive round trip overlaps with the
+    // other group's.  A slot must always be served by the SAME group: a group that skipped one use
+    // of a slot would find the full barrier's parity wait satisfied one lap early
+    const int ct = ((int)threadIdx.x - 6 * 32) & (CONV_THREADS - 1);
+    const int grp = ((int)threadIdx.x - 6 * 32) / CONV_THREADS;
     int s = 0; uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full[s], ph);
-        uint8_t* a = sA + s * A_STAGE_BYTES;
-        uint8_t* b = sB + s * C::B_STAGE_BYTES;
-        split_row_inplace(a + ct * 128);
-        if constexpr (WMODE == 1) {
-          for (int i = ct; i < BN / 2; i += CONV_THREADS) {
-            uint8_t* r0 = b + (i >> 5) * 8192 + (i & 31) * 128;
-            split_rowpair_inplace(r0, r0 + 4096);
+        if ((s & 1) == grp) {
+          mbar_wait(&full[s], ph);
+          uint8_t* a = sA + s * A_STAGE_BYTES;
+          uint8_t* b = sB + s * C::B_STAGE_BYTES;
+          split_row_inplace(a + ct * 128);
+          if constexpr (WMODE == 1) {
+            for (int i = ct; i < BN / 2; i += CONV_THREADS) {
+              uint8_t* r0 = b + (i >> 5) * 8192 + (i & 31) * 128;
+              split_rowpair_inplace(r0, r0 + 4096);
+            }
+          } else {
+            for (int i = ct; i < BN; i += CONV_THREADS) split_row_inplace(b + i * 128);
           }
-        } else {
-          for (int i = ct; i < BN; i += CONV_THREADS) split_row_inplace(b + i * 128);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[s]);
         if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -309,9 +318,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //     whose accumulators sit side by side in TMEM (2 sets x 4 x 64 columns,
 //     so the epilogue of one group overlaps the MMAs of the next).
 // L2->SM bytes per MMA drop ~5x.  Warp roles: 0 = halo (A) producer, 1 = MMA
-// issuer + TMEM owner, 2 = weight (B) producer, 4-7 = epilogue, 8-11 = operand
-// converters (bf16 arithmetic only: every halo box and weight tile is split once
-// and then read by all the taps / pixel tiles it serves).
+// issuer + TMEM owner, 2 = weight (B) producer, 4-7 = epilogue; bf16 arithmetic only:
+// 3 = weight-tile converter, 8-11 = halo-box converters (every halo box and weight
+// tile is split once and then read by all the taps / pixel tiles it serves).
 // =============================================================================
 constexpr int H_BN = 64, H_T = 4, H_BW = 8, H_BH = 16;
 constexpr int H_A_SLOT = 23 * 1024;           // 180 rows x 128 B = 23040, padded to 1 KB
@@ -369,7 +378,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 18; ++i) {
       mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
-      if (MATH) mbar_init(&b_ready[i], CONV_THREADS / 32);
+      if (MATH) mbar_init(&b_ready[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_fence_init();
@@ -549,17 +558,39 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty[aset]);
       if (++aset == 2) { aset = 0; acc_ph ^= 1; }
     }
-  } else if (warp >= 8) {
+  } else if (warp == 3) {
     if constexpr (MATH == 1) {
-      // ===================== operand converters (warps 8..11) =====================
-      // same order as the MMA issuer consumes: A(cb, 0), B(cb, taps...), A(cb, 1..3)
-      const int ct = (int)threadIdx.x - 8 * 32;
-      const int a_rows = (int)(p.a_bytes >> 7);
-      int s = 0; uint32_t ph = 0;
+      // ===================== weight-tile converter (warp 3) =====================
+      // each tap's 64 weight rows (WMODE 1: its 32 row pairs) as soon as the tile lands, in the
+      // order the MMA issuer first touches them; independent of the halo converters below
       uint32_t bcnt = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
+            uint8_t* b = sB + (set * H_MAX_TAPS + tap) * H_B_TILE;
+            if constexpr (WMODE == 1) {
+              split_rowpair_inplace(b + lane * 128, b + 4096 + lane * 128);
+            } else {
+              split_row_inplace(b + lane * 128);
+              split_row_inplace(b + (32 + lane) * 128);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_ready[set * H_MAX_TAPS + tap]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    if constexpr (MATH == 1) {
+      // ===================== halo-box converters (warps 8..11) =====================
+      const int ct = (int)threadIdx.x - 8 * 32;
+      const int a_rows = (int)(p.a_bytes >> 7);
+      int s = 0; uint32_t ph = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        for (int cb = 0; cb < p.cblocks; ++cb) {
           for (int t = 0; t < H_T; ++t) {
             mbar_wait(&a_full[s], ph);
             uint8_t* a = sA + s * H_A_SLOT;
@@ -568,20 +599,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[s]);
             if (++s == H_A_SLOTS) { s = 0; ph ^= 1; }
-            if (t == 0) {
-              for (int tap = 0; tap < p.taps; ++tap) {
-                mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
-                uint8_t* b = sB + (set * H_MAX_TAPS + tap) * H_B_TILE;
-                if constexpr (WMODE == 1) {
-                  if (ct < 32) split_rowpair_inplace(b + ct * 128, b + 4096 + ct * 128);
-                } else {
-                  if (ct < H_BN) split_row_inplace(b + ct * 128);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&b_ready[set * H_MAX_TAPS + tap]);
-              }
-            }
           }
         }
       }
@@ -620,7 +637,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
 #endif
   int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  SG_LAUNCH((conv_tc_kernel<BN, WMODE, MATH>), grid, NUM_THREADS + (MATH ? CONV_THREADS : 0),
+  SG_LAUNCH((conv_tc_kernel<BN, WMODE, MATH>), grid, NUM_THREADS + (MATH ? CONV_GROUPS * CONV_THREADS : 0),
             C::SMEM_BYTES, st, tmA, tmB, p);
   return 0;
 }

@@ -34,7 +34,8 @@ using namespace tc;
 namespace {
 
 constexpr int WG_THREADS = 192;
-constexpr int WG_CONV_THREADS = 128;        // converter warps of the bf16 arithmetic
+constexpr int WG_CONV_THREADS = 128;        // one converter group (4 warps) of the bf16 arithmetic
+constexpr int WG_CONV_GROUPS = 2;           // the groups take alternate pipeline stages
 constexpr int A_ATOM_BYTES = 8192;          // halo tile of one 32-channel atom, padded to 1 KB
 constexpr int B_ATOM_BYTES = 4096;          // 32 pixel rows x 128 B
 constexpr int A_STAGE = 4 * A_ATOM_BYTES;   // M = 128 channels = 4 atoms
@@ -66,7 +67,7 @@ struct WCfg {
 };
 
 template <int BN, int MATH>
-__global__ void __launch_bounds__(WG_THREADS + (MATH ? WG_CONV_THREADS : 0), 1)
+__global__ void __launch_bounds__(WG_THREADS + (MATH ? WG_CONV_GROUPS * WG_CONV_THREADS : 0), 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                      const WgParams p) {
   using C = WCfg<BN>;
@@ -243,10 +244,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       acc_ph ^= 1;
     }
   } else if constexpr (MATH == 1) {
-    // ===================== operand converters (warps 6..9) =====================
+    // ===================== operand converters (warps 6..13, two groups) =====================
     // per landed stage: the two atom pairs of the X halo tile and the BN/64 atom pairs of the dY
-    // tile are folded in place into 64-channel bf16 hi / mid atoms
-    const int ct = (int)threadIdx.x - 6 * 32;
+    // tile are folded in place into 64-channel bf16 hi / mid atoms.  Group g owns the pipeline slots
+    // of parity g, so one group's wait -> split -> fence -> arrive latency overlaps the other's (a
+    // slot is always served by the same group: skipping a use would alias the barrier's parity)
+    const int ct = ((int)threadIdx.x - 6 * 32) & (WG_CONV_THREADS - 1);
+    const int grp = ((int)threadIdx.x - 6 * 32) / WG_CONV_THREADS;
     const int a_rows = p.a_bytes >> 7;
     const int n_items = 2 * a_rows + (BN / 64) * 32;
     int s = 0; uint32_t ph = 0;
@@ -254,23 +258,25 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int ci0, co0, pass, t0, t1;
       decode(item, ci0, co0, pass, t0, t1);
       for (int pt = t0; pt < t1; ++pt) {
-        mbar_wait(&full[s], ph);
-        uint8_t* sa = smem + s * C::STAGE;
-        uint8_t* sb = sa + A_STAGE;
-        for (int i = ct; i < n_items; i += WG_CONV_THREADS) {
-          if (i < 2 * a_rows) {
-            const int pair = i >= a_rows ? 1 : 0, r = i - pair * a_rows;
-            uint8_t* r0 = sa + pair * 2 * A_ATOM_BYTES + r * 128;
-            split_rowpair_inplace(r0, r0 + A_ATOM_BYTES);
-          } else {
-            const int j = i - 2 * a_rows;
-            uint8_t* r0 = sb + (j >> 5) * 2 * B_ATOM_BYTES + (j & 31) * 128;
-            split_rowpair_inplace(r0, r0 + B_ATOM_BYTES);
+        if ((s & 1) == grp) {
+          mbar_wait(&full[s], ph);
+          uint8_t* sa = smem + s * C::STAGE;
+          uint8_t* sb = sa + A_STAGE;
+          for (int i = ct; i < n_items; i += WG_CONV_THREADS) {
+            if (i < 2 * a_rows) {
+              const int pair = i >= a_rows ? 1 : 0, r = i - pair * a_rows;
+              uint8_t* r0 = sa + pair * 2 * A_ATOM_BYTES + r * 128;
+              split_rowpair_inplace(r0, r0 + A_ATOM_BYTES);
+            } else {
+              const int j = i - 2 * a_rows;
+              uint8_t* r0 = sb + (j >> 5) * 2 * B_ATOM_BYTES + (j & 31) * 128;
+              split_rowpair_inplace(r0, r0 + B_ATOM_BYTES);
+            }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[s]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[s]);
         if (++s == C::STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -301,7 +307,7 @@ int launch_wg(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgParams& p
 #endif
   int items = p.ci_tiles * p.co_tiles * p.passes * p.splits;
   int grid = items < num_sms() ? items : num_sms();
-  SG_LAUNCH((conv_wgrad_tc_kernel<BN, MATH>), grid, WG_THREADS + (MATH ? WG_CONV_THREADS : 0),
+  SG_LAUNCH((conv_wgrad_tc_kernel<BN, MATH>), grid, WG_THREADS + (MATH ? WG_CONV_GROUPS * WG_CONV_THREADS : 0),
             C::SMEM_BYTES, st, tmX, tmDY, p);
   return 0;
 }

@@ -949,7 +949,9 @@ def _layout_launch(vecs, boxes, masks, obj_to_img, N, H, W, noise, align_corners
   img_ptr, img_ent = csr_build(obj_to_img, 1, N)
   nc = 0 if noise is None else noise.size(1)
   ns = (0, 0, 0, 0) if noise is None else noise.stride()      # (n, c, h, w)
-  _call_b(4 * N * H * W * (out.size(3) + nc) + 4 * O * D,
+  # algorithmic bytes: the D + nc channels WRITTEN per pixel (out may be a wider stage buffer whose
+  # other channels another kernel fills), the nc noise channels read, vectors / boxes / masks read
+  _call_b(4 * N * H * W * (D + 2 * nc) + 4 * O * (D + 4 + M * M),
           'sg2im_layout_fwd', _p(vecs), _p(boxes), _p(masks), M, _p(img_ptr), _p(img_ent), N, O,
           D, H, W, int(align_corners), _p(noise), nc, ns[0], ns[1], ns[2], ns[3], _p(out),
           out.size(3), int(round_tf32), _stream())

@@ -2,7 +2,7 @@
 (profiles/).  Not part of the library.
 
   ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 2 \
-      -o gpurun_out/prof_conv_tc python tools/prof_conv.py fwd
+      -o gpurun_out/prof_conv_tc python tools/prof_conv.py fwd [big|mid|small|n64] [bf16x3|tf32|bf16]
 """
 import os
 import sys
@@ -15,15 +15,18 @@ SHAPES = {
     # name: (N, H, W, Cin, Cout, K, P)   CRN stage-4 conv1 at VG-128, batch 32
     'big': (32, 128, 128, 288, 64, 3, 1),
     'mid': (32, 32, 32, 672, 256, 3, 1),
+    'small': (32, 8, 8, 1024, 1024, 3, 1),      # CRN stage-0 conv2: 8x8 maps, widest channels
+    'n64': (32, 128, 128, 64, 64, 3, 1),        # the two other 128x128 convolutions
 }
 
 
 def main():
   what = sys.argv[1] if len(sys.argv) > 1 else 'fwd'
   shape = SHAPES[sys.argv[2] if len(sys.argv) > 2 else 'big']
+  math = sys.argv[3] if len(sys.argv) > 3 else 'bf16x3'
   N, H, W, Ci, Co, K, P = shape
   dev = torch.device('cuda:0')
-  ops.set_conv_math('tf32')
+  ops.set_conv_math(math)
   torch.manual_seed(0)
   x = torch.randn(N, H, W, Ci, device=dev)
   w = torch.randn(Co, Ci, K, K, device=dev) * 0.05
@@ -52,7 +55,7 @@ def main():
   e1.record()
   torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / 10
-  print('%s %s: %.1f us, %.1f TFLOP/s' % (what, shape, ms * 1e3, flops / ms / 1e9))
+  print('%s %s %s: %.1f us, %.1f TFLOP/s (algorithmic)' % (what, math, shape, ms * 1e3, flops / ms / 1e9))
 
 
 if __name__ == '__main__':

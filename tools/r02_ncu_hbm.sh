@@ -11,9 +11,9 @@ OUT=gpurun_out/r02_hbm_kernels.txt
 : > $OUT
 echo "== CUDA-event timing, no profiler (tools/prof_hbm.py all)" >> $OUT
 timeout 300 python tools/prof_hbm.py all >> $OUT 2>&1
-# with the opt-in second-generation kernels where they exist
-echo "== same, SG2IM_LAYOUT_V2=1 SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1" >> $OUT
-SG2IM_LAYOUT_V2=1 SG2IM_BNBWD_V2=1 SG2IM_BNFWD_V2=1 timeout 300 python tools/prof_hbm.py all >> $OUT 2>&1
+# the first-generation kernels for comparison (the v2 kernels are the defaults now)
+echo "== same, first-generation kernels (SG2IM_LAYOUT_V2=0 SG2IM_BNBWD_V2=0 SG2IM_BNFWD_V2=0)" >> $OUT
+SG2IM_LAYOUT_V2=0 SG2IM_BNBWD_V2=0 SG2IM_BNFWD_V2=0 timeout 300 python tools/prof_hbm.py all >> $OUT 2>&1
 cap() {   # name, workload, kernel regex, launches to skip (warm-up + earlier repetitions)
   timeout 300 ncu --set full --clock-control none --import-source on -k "regex:$3" -s "$4" -c 1 \
     -f -o "gpurun_out/r02_prof_$1" python tools/prof_hbm.py "$2" > "gpurun_out/r02_prof_$1.log" 2>&1
@@ -29,6 +29,6 @@ cap segment_sum graph segment_sum 6
 cap crop_fwd crop crop_fwd 3
 cap crop_bwd crop crop_bwd 3
 cap scale_act_fwd bn scale_act_fwd 3
-cap scale_act_bwd_apply bn scale_act_bwd_apply 3
-cap bn_bwd_reduce bn "colreduce|bwd_reduce" 3
+cap scale_act_bwd_apply bn "bwd_apply" 3
+cap bn_bwd_reduce bn "bwd_reduce" 3
 tail -40 $OUT
