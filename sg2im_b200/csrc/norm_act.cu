@@ -469,7 +469,10 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
   cudaStream_t st = as_stream(stream);
   {
     const char* e = getenv("SG2IM_COLSUM_V2");            // read per call: tests toggle it in-process
-    if (!(e && e[0] == '0') && M <= 8192 && M * C < (1ll << 31)) {
+    // one CTA per 32 columns walks all M rows: right for the small GEMMs (a few hundred rows);
+    // taller inputs (6272 x 256 of the image discriminator: 61 us on 8 CTAs, measured) go to the
+    // split reduction below
+    if (!(e && e[0] == '0') && M <= 1024 && M * C < (1ll << 31)) {
       sg2im_colsum_small(x, M, C, out, st);
       SG_LAUNCH_OK();
       return 0;

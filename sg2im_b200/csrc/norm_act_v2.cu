@@ -361,9 +361,9 @@ int sg2im_scale_act_fwd_v2(const float* x, int64_t N, int64_t H, int64_t W, int6
 // ----------------------------------------------------------- small colsum ---
 // Bias gradients of the small GEMMs (scene-graph MLPs: 320/448 rows; discriminator
 // heads): out[c] = sum_m x[m, c].  The generic path is three launches (zero fp64
-// scratch, reduce with atomics, convert); for M <= 8192 one CTA per 32 columns
-// finishes the job in a single launch with no atomics and no scratch.
-// Opt-in with SG2IM_COLSUM_V2=1 until validated on hardware.
+// scratch, reduce with atomics, convert); for M <= 1024 one CTA per 32 columns
+// finishes the job in a single launch with no atomics and no scratch
+// (SG2IM_COLSUM_V2=0 disables it).
 namespace {
 
 __global__ void __launch_bounds__(256)
