@@ -168,6 +168,25 @@ int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                         int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Hout,
                         int64_t Wout, int64_t Cout, float* dw, int math, sg2im_stream_t stream);
 
+/* Pre-split weight operands of the bf16 arithmetic (SG2IM_MATH_BF16X3 / SG2IM_MATH_BF16): all
+ * convolution / Linear weights of a network in ONE launch.  `table`: n_entries x 8 int64 in device
+ * memory — {src, fwd, dgrad, taps, Cin, Cout, first_tile, 0} per weight — with src the fp32 master
+ * stored [taps][Cin][Cout] (the weight-gradient layout), fwd / dgrad (either may be 0) the operand
+ * copies [taps][Cout][cin_pad] and [taps, flipped][Cin][cout_pad] (pads = channels rounded up to 32)
+ * whose rows are 32-channel blocks of [32 x bf16 hi | 32 x bf16 mid], and first_tile the running sum
+ * of taps * ceil(Cin/32) * ceil(Cout/32) over the preceding entries (total_tiles = the full sum).
+ * sg2im_conv_tc_presplit consumes them: the kernels then split only the activation tiles. */
+int sg2im_split_weights(const int64_t* table, int64_t n_entries, int64_t total_tiles,
+                        sg2im_stream_t stream);
+/* sg2im_conv_tc with a pre-split B operand: w_split = rows of w_pitch floats (w_pitch % 32 == 0,
+ * >= Cin rounded up to 32), w_rows_per_tap rows per tap (>= Cout: the data gradient of a channel
+ * prefix uses the first Cout rows).  math: SG2IM_MATH_BF16X3 or SG2IM_MATH_BF16. */
+int sg2im_conv_tc_presplit(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
+                           int64_t Cin, const float* w_split, int64_t w_pitch, int64_t w_rows_per_tap,
+                           const float* bias, int KH, int KW, int P, int64_t Hout, int64_t Wout,
+                           int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
+                           int64_t y_coff, double* stats, int math, sg2im_stream_t stream);
+
 /* Space-to-depth by 2 (and its adjoint): out[n, y/2, x/2, ((y&1)*2+(x&1))*C + c]
  * = x[n,y,x,c], zero padded to even H, W.  x addressed with element strides.
  * Turns the discriminators' 4x4 stride-2 'valid' convolutions
@@ -362,7 +381,7 @@ int sg2im_coco_relations(const float* boxes, const int64_t* masks, int64_t MH, i
 int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                     float* step, const float* found_inf, float* rounded_out,
-                    sg2im_stream_t stream);
+                    float grad_scale, sg2im_stream_t stream);
 /* dx = dy * leaky'(y) and db[c] += sum_m dx[m,c] in one pass (the activation backward of a
  * conv+bias+LeakyReLU epilogue and its bias gradient, layers.py:39 / crn.py:43-47; autograd
  * derives both in the reference).  db is accumulated into: zeroed buffer or gradient slot.

@@ -29,6 +29,9 @@ SIGNATURES = {
                     _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
   'sg2im_conv_tc_kcc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr, _int, _int, _int,
                         _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
+  'sg2im_split_weights': [_ptr, _i64, _i64, _ptr],
+  'sg2im_conv_tc_presplit': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr, _int, _int, _int,
+                             _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_conv_wgrad_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64,
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,
@@ -67,7 +70,7 @@ SIGNATURES = {
   'sg2im_deprocess': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int,
                       _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr],
   'sg2im_adam_flat': [_ptr, _ptr, _ptr, _ptr, _i64, _f32, _f32, _f32, _f32, _f32, _ptr, _ptr,
-                      _ptr, _ptr],
+                      _ptr, _f32, _ptr],
   'sg2im_round_tf32': [_ptr, _i64, _ptr, _ptr],
   'sg2im_act_bwd_colsum': [_ptr, _ptr, _f32, _i64, _i64, _ptr, _ptr, _ptr],
   'sg2im_coco_relations': [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr,

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256)
 adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                  float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                  float wd, const float* __restrict__ step, const float* __restrict__ found_inf,
-                 float* __restrict__ rounded) {
+                 float* __restrict__ rounded, float gscale) {
   if (found_inf && *found_inf != 0.f) return;
   const float t = *step;
   // bias corrections in double like the host-side reference implementation
@@ -45,7 +45,8 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float gj = wd != 0.f ? fmaf(wd, pa[j], ga[j]) : ga[j];
+      float gj = ga[j] * gscale;                          // 1 / world of a SUM all-reduce (1 = exact no-op)
+      gj = wd != 0.f ? fmaf(wd, pa[j], gj) : gj;
       ma[j] = ma[j] + (gj - ma[j]) * (1.f - b1);
       va[j] = b2 * va[j] + (1.f - b2) * gj * gj;
       float denom = sqrtf(va[j]) / bc2_sqrt + eps;
@@ -61,7 +62,8 @@ adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   // tail (n % 4 elements), one thread
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int64_t i = n4 << 2; i < n; ++i) {
-      float gj = wd != 0.f ? fmaf(wd, p[i], g[i]) : g[i];
+      float gj = g[i] * gscale;
+      gj = wd != 0.f ? fmaf(wd, p[i], gj) : gj;
       float mj = m[i] + (gj - m[i]) * (1.f - b1);
       float vj = b2 * v[i] + (1.f - b2) * gj * gj;
       m[i] = mj; v[i] = vj;
@@ -92,7 +94,7 @@ extern "C" int sg2im_round_tf32(const float* x, int64_t n, float* y, sg2im_strea
 extern "C" int sg2im_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                int64_t n, float lr, float beta1, float beta2, float eps,
                                float weight_decay, float* step, const float* found_inf,
-                               float* rounded_out, sg2im_stream_t stream) {
+                               float* rounded_out, float grad_scale, sg2im_stream_t stream) {
   SG_ARG(params && grads && exp_avg && exp_avg_sq && step && n >= 0);
   SG_ARG(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq));
   SG_ARG(rounded_out == nullptr || aligned16(rounded_out));
@@ -106,7 +108,7 @@ extern "C" int sg2im_adam_flat(float* params, const float* grads, float* exp_avg
     if (blocks < 1) blocks = 1;
     SG_LAUNCH(adam_flat_kernel, (unsigned)blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, lr,
                                                        beta1, beta2, eps, weight_decay, step,
-                                                       found_inf, rounded_out);
+                                                       found_inf, rounded_out, grad_scale);
   }
   SG_LAUNCH_OK();
   return 0;

@@ -68,6 +68,26 @@ __device__ __forceinline__ float tf32_rn(float v) {
   return __uint_as_float(u);
 }
 
+// (x0, x1) -> packed bf16x2 of the round-to-nearest-even bf16 values (x0 in the low half) and of
+// the bf16-rounded remainders: x = hi + mid up to 2^-17 |x| (the subtraction is exact).  The
+// operand split of the 'bf16x3' tensor-core arithmetic (tc_common.cuh, pack.cu).
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+#ifdef SG2IM_EMUL
+  auto rn = [](float f) -> uint32_t {                    // what cvt.rn.bf16x2.f32 does per element
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;
+    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+  };
+  const uint32_t h0 = rn(x0), h1 = rn(x1);
+  hi = h0 | (h1 << 16);
+  mid = rn(x0 - __uint_as_float(h0 << 16)) | (rn(x1 - __uint_as_float(h1 << 16)) << 16);
+#else
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
+#endif
+}
+
 // Bilinear sampling footprint of one normalised coordinate g in [-1,1] on an
 // axis of `size` texels (torch grid_sample, zeros padding): lower texel index
 // and the weight of the upper texel.

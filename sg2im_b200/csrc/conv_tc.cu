@@ -83,7 +83,9 @@ struct Cfg {
 //      contiguous => K-major as in mode 0, only the tap index is flipped
 // Modes 1/2 remove every pack / unpack pass when the master weights live in that layout
 // (sg2im_conv_tc_kcc; validated on the B200 in round 2).
-template <int BN, int WMODE, int MATH>
+// PS (MATH 1, WMODE 0 only): the B operand arrives PRE-SPLIT from HBM (sg2im_split_weights wrote
+// its rows as [hi | mid] blocks once per training step), so the converters touch only A.
+template <int BN, int WMODE, int MATH, int PS = 0>
 __global__ void __launch_bounds__(NUM_THREADS + (MATH ? CONV_GROUPS * CONV_THREADS : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
@@ -270,7 +272,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* a = sA + s * A_STAGE_BYTES;
           uint8_t* b = sB + s * C::B_STAGE_BYTES;
           split_row_inplace(a + ct * 128);
-          if constexpr (WMODE == 1) {
+          if constexpr (PS) {
+            (void)b;
+          } else if constexpr (WMODE == 1) {
             for (int i = ct; i < BN / 2; i += CONV_THREADS) {
               uint8_t* r0 = b + (i >> 5) * 8192 + (i & 31) * 128;
               split_rowpair_inplace(r0, r0 + 4096);
@@ -344,7 +348,7 @@ struct HaloParams {
   int nprod;                       // MATH 1: 3 = bf16x3, 1 = bf16
 };
 
-template <int WMODE, int MATH>                    // weight source / arithmetic, see conv_tc_kernel
+template <int WMODE, int MATH, int PS = 0>        // weight source / arithmetic / pre-split B, see conv_tc_kernel
 __global__ void __launch_bounds__(H_THREADS + (MATH ? CONV_THREADS : 0), 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p) {
@@ -470,7 +474,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
           const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
-          uint64_t* bf = MATH ? &b_ready[set * H_MAX_TAPS] : &b_full[set * H_MAX_TAPS];
+          uint64_t* bf = (MATH && !PS) ? &b_ready[set * H_MAX_TAPS] : &b_full[set * H_MAX_TAPS];
           uint64_t* be = &b_empty[set * H_MAX_TAPS];
           for (int t = 0; t < H_T; ++t) {
             mbar_wait(MATH ? &a_ready[s] : &a_full[s], ph);
@@ -559,7 +563,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++aset == 2) { aset = 0; acc_ph ^= 1; }
     }
   } else if (warp == 3) {
-    if constexpr (MATH == 1) {
+    if constexpr (MATH == 1 && !PS) {
       // ===================== weight-tile converter (warp 3) =====================
       // each tap's 64 weight rows (WMODE 1: its 32 row pairs) as soon as the tile lands, in the
       // order the MMA issuer first touches them; independent of the halo converters below
@@ -620,13 +624,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------- host side ---
-template <int BN, int WMODE, int MATH>
+template <int BN, int WMODE, int MATH, int PS = 0>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WMODE, MATH>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, WMODE, MATH, PS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -637,7 +641,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cu
 #endif
   int total = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  SG_LAUNCH((conv_tc_kernel<BN, WMODE, MATH>), grid, NUM_THREADS + (MATH ? CONV_GROUPS * CONV_THREADS : 0),
+  SG_LAUNCH((conv_tc_kernel<BN, WMODE, MATH, PS>), grid, NUM_THREADS + (MATH ? CONV_GROUPS * CONV_THREADS : 0),
             C::SMEM_BYTES, st, tmA, tmB, p);
   return 0;
 }
@@ -648,12 +652,12 @@ int launch_w(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, 
        : wmode == 2 ? launch<BN, 2, MATH>(tmA, tmB, p, st) : launch<BN, 0, MATH>(tmA, tmB, p, st);
 }
 
-template <int WMODE, int MATH>
+template <int WMODE, int MATH, int PS = 0>
 int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& h, cudaStream_t st) {
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<WMODE, MATH>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<WMODE, MATH, PS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -664,7 +668,7 @@ int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& 
 #endif
   int items = h.groups * h.n_tiles;
   int grid = items < num_sms() ? items : num_sms();
-  SG_LAUNCH((conv_tc_halo_kernel<WMODE, MATH>), grid, H_THREADS + (MATH ? CONV_THREADS : 0), H_SMEM,
+  SG_LAUNCH((conv_tc_halo_kernel<WMODE, MATH, PS>), grid, H_THREADS + (MATH ? CONV_THREADS : 0), H_SMEM,
             st, hA, hB, h);
   return 0;
 }
@@ -674,12 +678,16 @@ int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& 
 // Tensor map of the B operand for the three weight sources (see conv_tc_kernel).  bf16 arithmetic:
 // every tile is rewritten by the converter warps, which assume the plain SWIZZLE_128B pattern.
 static int encode_weights(tc::EncodeTiledFn enc, CUtensorMap* map, const float* w, int64_t Cin,
-                          int64_t Cout, int taps, int BN, int wmode, int64_t w_rows_full, int math) {
+                          int64_t Cout, int taps, int BN, int wmode, int64_t w_rows_full, int math,
+                          int64_t ps_pitch = 0) {
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  if (wmode == 0) {                       // [taps][Cout][Cin]
+  if (wmode == 0 && ps_pitch) {           // pre-split [taps][w_rows_full][ps_pitch], Cout rows used
+    gdim[0] = (cuuint64_t)ps_pitch; gdim[1] = (cuuint64_t)Cout;
+    gstr[0] = (cuuint64_t)ps_pitch * 4; gstr[1] = (cuuint64_t)w_rows_full * ps_pitch * 4;
+  } else if (wmode == 0) {                // [taps][Cout][Cin]
     gdim[0] = (cuuint64_t)Cin; gdim[1] = (cuuint64_t)Cout;
     gstr[0] = (cuuint64_t)Cin * 4; gstr[1] = (cuuint64_t)Cout * Cin * 4;
   } else if (wmode == 1) {                // [taps][rows = Cin][cols = Cout], cols contiguous, MN-major atoms
@@ -733,8 +741,10 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                         int KH, int KW, int P, int64_t Hout, int64_t Wout, int64_t Cout,
                         int act, float slope, float* y, int64_t y_cstride, int64_t y_coff,
                         double* stats, int round_out, sg2im_stream_t stream, int wmode,
-                        int64_t w_rows_full, int math) {
+                        int64_t w_rows_full, int math, int64_t ps_pitch = 0) {
   SG_ARG(x && w_tc && y);
+  SG_ARG(ps_pitch == 0 || (wmode == 0 && math != SG2IM_MATH_TF32 && ps_pitch % 32 == 0 &&
+                           ps_pitch >= Cin && w_rows_full >= Cout));
   SG_ARG(math == SG2IM_MATH_TF32 || math == SG2IM_MATH_BF16X3 || math == SG2IM_MATH_BF16);
   if (!sg2im_conv_tc_supported(N, Hin, Win, Cin, x_cstride, KH, KW, 1, P, Hout, Wout, Cout,
                                y_cstride, y_coff)) {
@@ -805,9 +815,10 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
     }
-    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full, bf)) return rc;
+    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full, bf, ps_pitch)) return rc;
     int rc;
-    if (bf) rc = wmode == 1 ? launch_halo<1, 1>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 1>(hA, hB, h, st)
+    if (ps_pitch) rc = launch_halo<0, 1, 1>(hA, hB, h, st);
+    else if (bf) rc = wmode == 1 ? launch_halo<1, 1>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 1>(hA, hB, h, st)
                                                                            : launch_halo<0, 1>(hA, hB, h, st);
     else rc = wmode == 1 ? launch_halo<1, 0>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 0>(hA, hB, h, st)
                                                                          : launch_halo<0, 0>(hA, hB, h, st);
@@ -828,9 +839,12 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode A failed (%d)", (int)r); return -4; }
   }
-  if (int rc = encode_weights(enc, &tmB, w_tc, Cin, Cout, KH * KW, BN, wmode, w_rows_full, bf)) return rc;
+  if (int rc = encode_weights(enc, &tmB, w_tc, Cin, Cout, KH * KW, BN, wmode, w_rows_full, bf, ps_pitch)) return rc;
   int rc = 0;
-  if (bf) {
+  if (ps_pitch) {
+    rc = BN == 256 ? launch<256, 0, 1, 1>(tmA, tmB, p, st)
+       : BN == 128 ? launch<128, 0, 1, 1>(tmA, tmB, p, st) : launch<64, 0, 1, 1>(tmA, tmB, p, st);
+  } else if (bf) {
     rc = BN == 256 ? launch_w<256, 1>(tmA, tmB, p, wmode, st)
        : BN == 128 ? launch_w<128, 1>(tmA, tmB, p, wmode, st) : launch_w<64, 1>(tmA, tmB, p, wmode, st);
   } else {
@@ -861,4 +875,16 @@ extern "C" int sg2im_conv_tc_kcc(const float* x, int64_t x_cstride, int64_t N, i
   return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_kcc, bias, KH, KW, P, Hout, Wout, Cout, act,
                       slope, y, y_cstride, y_coff, stats, round_out, stream, dgrad ? 2 : 1,
                       w_rows_full, math);
+}
+
+extern "C" int sg2im_conv_tc_presplit(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
+                                      int64_t Win, int64_t Cin, const float* w_split, int64_t w_pitch,
+                                      int64_t w_rows_per_tap, const float* bias, int KH, int KW, int P,
+                                      int64_t Hout, int64_t Wout, int64_t Cout, int act, float slope,
+                                      float* y, int64_t y_cstride, int64_t y_coff, double* stats,
+                                      int math, sg2im_stream_t stream) {
+  SG_ARG(math == SG2IM_MATH_BF16X3 || math == SG2IM_MATH_BF16);
+  SG_ARG(w_pitch > 0);
+  return conv_tc_impl(x, x_cstride, N, Hin, Win, Cin, w_split, bias, KH, KW, P, Hout, Wout, Cout, act,
+                      slope, y, y_cstride, y_coff, stats, 0, stream, 0, w_rows_per_tap, math, w_pitch);
 }

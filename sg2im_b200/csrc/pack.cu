@@ -6,6 +6,8 @@
 //                             dgr[T-1-t][ci][co]        (data-gradient B operand:
 //                                                        flipped taps, channels swapped)
 //   unpack: dw[t][ci][co] ->  grad[co][ci][t]  (+= optional)   (wgrad output -> OIHW)
+//   split:  kcc[t][ci][co] -> bf16 hi / mid operand copies of ALL convolution weights of a
+//           network in one launch (the 'bf16x3' arithmetic's pre-split B operands, below)
 #include "common.cuh"
 
 namespace {
@@ -135,6 +137,81 @@ extern "C" int sg2im_unpack_wgrad(const float* dw, int64_t Cout, int64_t Cin, in
     case 16: launch_unpack<16>(grid, smem, st, dw, Co, Ci, cu, T, grad_oihw, accumulate); break;
     default: launch_unpack<0>(grid, smem, st, dw, Co, Ci, cu, T, grad_oihw, accumulate); break;
   }
+  SG_LAUNCH_OK();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Pre-split weight operands of the bf16 arithmetic.  The tensor-core kernels can split fp32
+// operand tiles themselves (converter warps, tc_common.cuh), but weights are constant within a
+// training step and every CTA re-reads them: splitting them once per step removes that work —
+// and its shared-memory traffic, which is what bounds those kernels — from every tile of every
+// launch.  One launch per network: entry e describes a weight stored tap-major / input channel /
+// output channel fastest ("kcc", what the weight-gradient kernel writes and Adam updates) and the
+// two operand copies, each a K-major matrix whose rows hold 32-channel blocks
+// [32 x bf16 hi | 32 x bf16 mid] (the layout the converter warps produce in shared memory):
+//   fwd[t][co][ci blocks]          B operand of the forward convolution
+//   dgr[T-1-t][ci][co blocks]      B operand of the data gradient (flipped taps)
+// Pad channels inside the last block are written as zeros.
+namespace {
+struct SplitEntry {           // 8 x int64, built by the host (ops.SplitShadows)
+  long long src, fwd, dgr, taps, Cin, Cout, first_tile, pad_;
+};
+
+__global__ void __launch_bounds__(256)
+split_weights_kernel(const SplitEntry* __restrict__ tab, int n_entries) {
+  __shared__ float tile[32][33];
+  const int bid = (int)blockIdx.x;
+  int e = 0;
+  while (e + 1 < n_entries && (long long)bid >= tab[e + 1].first_tile) ++e;   // n_entries is small
+  const SplitEntry E = tab[e];
+  const int Cin = (int)E.Cin, Cout = (int)E.Cout, T = (int)E.taps;
+  const int tci = (Cin + 31) >> 5, tco = (Cout + 31) >> 5;
+  int r = bid - (int)E.first_tile;
+  const int bco = r % tco; r /= tco;
+  const int bci = r % tci; const int tap = r / tci;
+  const int ci0 = bci * 32, co0 = bco * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* src = reinterpret_cast<const float*>(E.src) + ((size_t)tap * Cin + ci0) * Cout + co0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ci = warp + 8 * k;
+    tile[ci][lane] = (ci0 + ci < Cin && co0 + lane < Cout) ? src[(size_t)ci * Cout + lane] : 0.f;
+  }
+  __syncthreads();
+  const int cin_pad = tci * 32, cout_pad = tco * 32;
+  uint32_t* fwd = reinterpret_cast<uint32_t*>(E.fwd);
+  uint32_t* dgr = reinterpret_cast<uint32_t*>(E.dgr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int row = warp + 8 * k;
+    if (dgr && ci0 + row < Cin) {                       // row = input channel, lanes = output channels
+      const float v = tile[row][lane], nb = __shfl_xor_sync(0xffffffffu, v, 1);
+      uint32_t hi, mid;
+      split_bf16x2(v, nb, hi, mid);
+      if (!(lane & 1)) {
+        uint32_t* d = dgr + ((size_t)(T - 1 - tap) * Cin + ci0 + row) * cout_pad + co0 + (lane >> 1);
+        d[0] = hi; d[16] = mid;
+      }
+    }
+    if (fwd && co0 + row < Cout) {                      // row = output channel, lanes = input channels
+      const float v = tile[lane][row], nb = __shfl_xor_sync(0xffffffffu, v, 1);
+      uint32_t hi, mid;
+      split_bf16x2(v, nb, hi, mid);
+      if (!(lane & 1)) {
+        uint32_t* d = fwd + ((size_t)tap * Cout + co0 + row) * cin_pad + ci0 + (lane >> 1);
+        d[0] = hi; d[16] = mid;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int sg2im_split_weights(const int64_t* table, int64_t n_entries, int64_t total_tiles,
+                                   sg2im_stream_t stream) {
+  SG_ARG(table && n_entries >= 1 && total_tiles >= 1 && total_tiles < (1ll << 31));
+  SG_LAUNCH(split_weights_kernel, (unsigned)total_tiles, 256, 0, as_stream(stream),
+            reinterpret_cast<const SplitEntry*>(table), (int)n_entries);
   SG_LAUNCH_OK();
   return 0;
 }

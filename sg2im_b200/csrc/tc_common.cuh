@@ -139,14 +139,6 @@ __device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, ui
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// (x0, x1) -> packed bf16x2 of the round-to-nearest-even bf16 values (x0 in the low half) and of
-// the bf16-rounded remainders: x = hi + mid up to 2^-17 |x| (the subtraction is exact)
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(r1), "f"(r0));
-}
-
 // --- setup / teardown pieces the kernels share
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

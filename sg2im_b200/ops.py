@@ -432,18 +432,19 @@ def round_tf32(src, dst):
 
 
 def adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
-              found_inf=None, shadow=None):
+              found_inf=None, shadow=None, grad_scale=1.0):
   """One Adam update of a flat fp32 bucket in place (torch.optim.Adam arithmetic);
   `step` is a 0-dim device float incremented by the call, `found_inf` (0-dim
   device float or None) nonzero skips update and increment; `shadow` (or None)
-  receives the updated parameters rounded to nearest TF32."""
+  receives the updated parameters rounded to nearest TF32; `grad_scale` multiplies every gradient
+  first (1 / world after a SUM all-reduce: the mean without a separate pass over the bucket)."""
   for t in (params, grads, exp_avg, exp_avg_sq):
     _chk(t)
     if not t.is_contiguous() or t.numel() != params.numel():
       raise RuntimeError('sg2im_b200: adam_flat needs four contiguous buffers of equal length')
   _call('sg2im_adam_flat', _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(),
         float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), _p(step),
-        _p(found_inf), _p(shadow), _stream())
+        _p(found_inf), _p(shadow), float(grad_scale), _stream())
   _count(2)
 
 
@@ -570,6 +571,75 @@ def conv_tc_kcc(x, w_kcc, rows_full, dgrad, bias, KH, KW, P, Cout, act=0, slope=
   return out
 
 
+def conv_tc_presplit(x, w_split, rows_per_tap, bias, KH, KW, P, Cout, act=0, slope=0.0, out_hw=None,
+                     stats=None, tag='conv_fwd_tc'):
+  """Tensor-core stride-1 convolution (bf16 arithmetic) with a PRE-SPLIT B operand: w_split
+  (taps, rows_per_tap, pitch) fp32-typed storage whose rows are 32-channel blocks of
+  [32 x bf16 hi | 32 x bf16 mid] (SplitShadows); the kernels then split only the activation tiles."""
+  N, H, W, C = x.shape
+  cs = _pixel_stride(x)
+  Hout, Wout = out_hw if out_hw is not None else (H + 2 * P - KH + 1, W + 2 * P - KW + 1)
+  out = torch.empty(N, Hout, Wout, Cout, dtype=torch.float32, device=x.device)
+  with _prof(tag, 2.0 * N * Hout * Wout * C * Cout * KH * KW, (N, H, W, C, Cout, KH, 1)):
+    _call('sg2im_conv_tc_presplit', _p(x), cs, N, H, W, C, _p(w_split), w_split.size(2), rows_per_tap,
+          _p(bias), KH, KW, P, Hout, Wout, Cout, int(act), float(slope), _p(out), Cout, 0, _p(stats),
+          _math_id(), _stream())
+  _count()
+  return out
+
+
+# Inside TrainStep.step (bf16 arithmetic, weights='kcc'): read the weights' pre-split operand copies
+# (SplitShadows, refreshed at the start of every step) instead of splitting weight tiles in-kernel.
+USE_SPLIT_SHADOWS = False
+
+
+class SplitShadows(object):
+  """bf16 hi / mid operand copies of the convolution / Linear weights of one network, for the
+  'bf16x3' / 'bf16' arithmetic: weights are constant within a training step and re-read by every
+  CTA of every launch, so they are split ONCE per step (one launch for the whole network,
+  sg2im_split_weights) instead of by the converter warps of every tile.  Each weight stored in the
+  weight-gradient layout gets `_split_fwd` (T, Co, cin_pad) and `_split_dgrad` (T, Ci, cout_pad)
+  attributes; ops.conv2d / ops.linear pick them up while USE_SPLIT_SHADOWS is set."""
+
+  def __init__(self, params):
+    self.weights, rows, tiles = [], [], 0
+    for w in params:
+      if not (w.dim() in (2, 4) and is_kcc(w) and w.size(0) % 4 == 0):
+        continue
+      if w.dim() == 4 and w.size(2) == 4:          # 4x4 stride-2 route re-tiles its weights per call
+        continue
+      v = _kcc_view(w.detach())
+      T, Ci, Co = v.shape
+      cip, cop = (Ci + 31) // 32 * 32, (Co + 31) // 32 * 32
+      w._split_fwd = torch.zeros(T, Co, cip, dtype=torch.float32, device=w.device)
+      w._split_dgrad = torch.zeros(T, Ci, cop, dtype=torch.float32, device=w.device)
+      rows.append([v.data_ptr(), w._split_fwd.data_ptr(), w._split_dgrad.data_ptr(), T, Ci, Co, tiles, 0])
+      tiles += T * (cip // 32) * (cop // 32)
+      self.weights.append(w)
+    self.tiles = tiles
+    self.table = (torch.tensor(rows, dtype=torch.int64).to(self.weights[0].device)
+                  if rows else None)
+    self._rows = rows
+
+  def refresh(self):
+    if self.table is None:
+      return
+    for w, r in zip(self.weights, self._rows):       # the masters must not have been re-allocated
+      if w.data_ptr() != r[0]:
+        raise RuntimeError('sg2im_b200: a parameter moved after SplitShadows was built')
+    _call_b(12 * sum(w.numel() for w in self.weights),
+            'sg2im_split_weights', _p(self.table), len(self._rows), self.tiles, _stream())
+    _count()
+
+
+def _split_of(weight):
+  if USE_SPLIT_SHADOWS and CONV_MATH in ('bf16x3', 'bf16'):
+    f = getattr(weight, '_split_fwd', None)
+    if f is not None:
+      return f, weight._split_dgrad
+  return None
+
+
 class ConvKCC(torch.autograd.Function):
   """y = act(conv(x, W) + b) on the tensor-core kernels with W given as w_kcc
   (T, Ci_w, Co) — the weight-gradient layout — so that neither the forward, nor the
@@ -580,7 +650,7 @@ class ConvKCC(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w_kcc, bias, KH, KW, pad, act, slope, in_ch, out_hw, zero_bias_grad,
-              stats_out, round_out, grad_into=None, w_read=None):
+              stats_out, round_out, grad_into=None, w_read=None, split=None):
     T, Ci_w, Co = w_kcc.shape
     if w_read is not None:
       # RN-TF32 shadow of the same weights (FlatAdam keeps it current): what the kernels read
@@ -592,12 +662,18 @@ class ConvKCC(torch.autograd.Function):
     Hout = x.size(1) + 2 * pad - KH + 1 if out_hw is None else out_hw[0]
     Wout = x.size(2) + 2 * pad - KW + 1 if out_hw is None else out_hw[1]
     fused_stats = stats_out is not None and act == 0 and Co <= 1024
-    y = conv_tc_kcc(x, w_read, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
-                    stats_out if fused_stats else None, round_out)
+    if split is not None:
+      # pre-split operand copies of the same weights (SplitShadows): (T, Co, cin_pad) forward
+      y = conv_tc_presplit(x, split[0], Co, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
+                           stats_out if fused_stats else None)
+    else:
+      y = conv_tc_kcc(x, w_read, Ci_w, 0, bias, KH, KW, pad, Co, act, slope, (Hout, Wout),
+                      stats_out if fused_stats else None, round_out)
     if stats_out is not None and not fused_stats:
       _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
     ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
+    ctx.split_dgrad = None if split is None else split[1]
     ctx.save_for_backward(x, w_read, y if act else None)
     ctx.bias_ref = bias
     ctx.has_bias = bias is not None
@@ -623,8 +699,12 @@ class ConvKCC(torch.autograd.Function):
       pad_t = KH - 1 - pad
       if (KH == KW and pad_t >= 0
           and conv_tc_ok(dy, KH, KW, 1, pad_t, Ci, (x.size(1), x.size(2)))):
-        dx = conv_tc_kcc(dy, w_kcc, Ci_w, 1, None, KH, KW, pad_t, Ci, out_hw=(x.size(1), x.size(2)),
-                         tag='conv_dgrad_tc')
+        if ctx.split_dgrad is not None:                      # (T flipped, Ci_w, cout_pad)
+          dx = conv_tc_presplit(dy, ctx.split_dgrad, Ci_w, None, KH, KW, pad_t, Ci,
+                                out_hw=(x.size(1), x.size(2)), tag='conv_dgrad_tc')
+        else:
+          dx = conv_tc_kcc(dy, w_kcc, Ci_w, 1, None, KH, KW, pad_t, Ci, out_hw=(x.size(1), x.size(2)),
+                           tag='conv_dgrad_tc')
       else:
         wd = w_kcc[:, :Ci].permute(0, 2, 1).reshape(KH * KW * Co, Ci).contiguous()   # exact-fp32 kernel
         dx = conv_igemm(1, dy, wd, None, KH, KW, 1, pad, (x.size(1), x.size(2)), Ci)
@@ -646,7 +726,7 @@ class ConvKCC(torch.autograd.Function):
         db = None if DIRECT_WGRAD else torch.zeros(Co, dtype=torch.float32, device=dy.device)
       else:
         db = colsum(dy.view(-1, Co))
-    return (dx, dw, db) + (None,) * 12
+    return (dx, dw, db) + (None,) * 13
 
 
 class Pool2d(torch.autograd.Function):
@@ -774,7 +854,7 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Hout, Wout = conv_out_size(x.size(1), KH, 1, pad), conv_out_size(x.size(2), KW, 1, pad)
     if conv_tc_ok(x, KH, KW, 1, pad, Co, (Hout, Wout)) and x.size(3) == Ci:
       return ConvKCC.apply(x, _kcc_view(weight), bias, KH, KW, pad, act, slope, in_ch, None, feeds_bn,
-                           stats_out, round_out, _grad_slot(weight), _shadow(weight))
+                           stats_out, round_out, _grad_slot(weight), _shadow(weight), _split_of(weight))
   return Conv.apply(x, weight, bias, stride, pad, act, slope, in_ch, None, feeds_bn, stats_out,
                     round_out)
 
@@ -787,7 +867,7 @@ def linear(x2d, weight, bias, act=0, slope=0.0, round_out=False):
   x4 = x2d.reshape(M, 1, 1, K)
   if _tc_math() and is_kcc(weight) and conv_tc_ok(x4, 1, 1, 1, 0, weight.size(0), (1, 1)):
     y = ConvKCC.apply(x4, _kcc_view(weight), bias, 1, 1, 0, act, slope, None, None, False, None, rnd,
-                      _grad_slot(weight), _shadow(weight))
+                      _grad_slot(weight), _shadow(weight), _split_of(weight))
   else:
     w4 = weight.reshape(weight.size(0), K, 1, 1) if not weight.is_contiguous() else \
         weight.view(weight.size(0), K, 1, 1)

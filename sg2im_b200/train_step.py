@@ -54,13 +54,19 @@ class FlatGrads(object):
       if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
         p.grad = self._slot(p, o)
 
-  def all_reduce_mean(self, group=None):
+  def all_reduce_mean(self, group=None, opt=None):
+    """Gradient mean over the ranks: one SUM all-reduce of the flat bucket.  The division by the
+    world size is folded into the optimiser's gradient scale when it has one (FlatAdam: no extra
+    pass over the bucket), else done in place."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
       world = dist.get_world_size(group)
       if world > 1:
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.div_(world)
+        if isinstance(opt, FlatAdam):
+          opt.grad_scale = 1.0 / world
+        else:
+          self.flat.div_(world)
 
 
 class FlatAdam(object):
@@ -94,7 +100,7 @@ class FlatAdam(object):
     self.exp_avg_sq = torch.zeros_like(flat)
     self.step_count = torch.zeros((), dtype=torch.float32, device=flat.device)
     self.found_inf = None            # set by the graph path, like torch's capturable Adam
-    self.grad_scale = None
+    self.grad_scale = 1.0            # multiplies the gradients (FlatGrads.all_reduce_mean: 1 / world)
     self.shadow = None
     if shadow:
       self.shadow = torch.zeros_like(flat)
@@ -111,7 +117,7 @@ class FlatAdam(object):
     from . import ops
     ops.adam_flat(self.flat_params, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
                   self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                  self.weight_decay, self.found_inf, self.shadow)
+                  self.weight_decay, self.found_inf, self.shadow, self.grad_scale)
 
 
 def _all_finite(value, group=None):
@@ -188,6 +194,16 @@ class TrainStep(object):
         # kcc: the weight-gradient kernels write float4 atomics straight into the slots
         self.buckets[name] = FlatGrads(net.parameters(), align=4 if weights == 'kcc' else 1)
         self.opts[name] = torch.optim.Adam(self.buckets[name].params, **kw)
+    # bf16 arithmetic with in-place weights: one launch per network and step splits every weight
+    # into the bf16 hi / mid operand copies the tensor-core kernels read (ops.SplitShadows)
+    from . import ops as _ops
+    self.split_shadows = []
+    if weights == 'kcc' and _ops.CONV_MATH in ('bf16x3', 'bf16'):
+      for net in self.nets.values():
+        if net is not None:
+          sh = _ops.SplitShadows(list(net.parameters()))
+          if sh.table is not None:
+            self.split_shadows.append(sh)
     self.skipped = 0
 
   # -- loss assembly, scripts/train.py:387-412 + :539-550
@@ -227,15 +243,16 @@ class TrainStep(object):
     into the static input buffers).  Returns (losses dict of python floats,
     imgs_pred detached)."""
     from . import ops
-    prev = ops.DIRECT_WGRAD
+    prev = ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS
     # kcc: the weight-gradient kernels accumulate in place in the flat gradient buckets
     ops.DIRECT_WGRAD = self.weights == 'kcc'
+    ops.USE_SPLIT_SHADOWS = bool(self.split_shadows)
     try:
       if self.cuda_graph:
         return self._step_graphed(batch, noise)
       return self._step_eager(batch, noise)
     finally:
-      ops.DIRECT_WGRAD = prev
+      ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS = prev
 
   # ------------------------------------------------------------------ graph mode
   def _step_graphed(self, batch, noise):
@@ -267,7 +284,6 @@ class TrainStep(object):
     static_noise = None if noise is None else noise.to(dev).clone()
     found_inf = torch.zeros((), dtype=torch.float32, device=dev)
     for opt in self.opts.values():
-      opt.grad_scale = None
       opt.found_inf = found_inf
     from . import _lib
     torch.cuda.synchronize()
@@ -291,6 +307,8 @@ class TrainStep(object):
     else:
       imgs, objs, boxes, masks, triples, obj_to_img, _ = batch
     N = imgs.size(0)
+    for sh in self.split_shadows:          # this step's weights -> bf16 hi / mid operand copies
+      sh.refresh()
     imgs_pred, boxes_pred, masks_pred, predicate_scores = self.model(
         objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, num_imgs=N, noise=noise)
     total, losses = self.generator_losses(imgs, imgs_pred, boxes, boxes_pred, masks,
@@ -320,7 +338,7 @@ class TrainStep(object):
 
     self.buckets['g'].zero()
     total.backward()
-    self.buckets['g'].all_reduce_mean(self.group)
+    self.buckets['g'].all_reduce_mean(self.group, self.opts['g'])
     self.opts['g'].step()
 
     if self.d_obj is not None:
@@ -331,7 +349,7 @@ class TrainStep(object):
       losses.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
       self.buckets['d_obj'].zero()
       (d_obj_gan + ac_real + ac_fake).backward()
-      self.buckets['d_obj'].all_reduce_mean(self.group)
+      self.buckets['d_obj'].all_reduce_mean(self.group, self.opts['d_obj'])
       self.opts['d_obj'].step()
     if self.d_img is not None:
       self._freeze(self.d_img, False)
@@ -341,7 +359,7 @@ class TrainStep(object):
       losses['d_img_gan_loss'] = d_img_gan
       self.buckets['d_img'].zero()
       d_img_gan.backward()
-      self.buckets['d_img'].all_reduce_mean(self.group)
+      self.buckets['d_img'].all_reduce_mean(self.group, self.opts['d_img'])
       self.opts['d_img'].step()
     return losses, imgs_fake
 
@@ -357,6 +375,8 @@ class TrainStep(object):
       raise ValueError('batch must have 6 or 7 entries')
     N = imgs.size(0)
     predicates = triples[:, 1]
+    for sh in self.split_shadows:          # this step's weights -> bf16 hi / mid operand copies
+      sh.refresh()
 
     # ---------------- generator: train.py:524-560
     imgs_pred, boxes_pred, masks_pred, predicate_scores = self.model(
@@ -393,7 +413,7 @@ class TrainStep(object):
 
     self.buckets['g'].zero()
     total.backward()
-    self.buckets['g'].all_reduce_mean(self.group)
+    self.buckets['g'].all_reduce_mean(self.group, self.opts['g'])
     self.opts['g'].step()
 
     # ---------------- object discriminator: train.py:566-579
@@ -407,7 +427,7 @@ class TrainStep(object):
       d_vals.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
       self.buckets['d_obj'].zero()
       d_total.backward()
-      self.buckets['d_obj'].all_reduce_mean(self.group)
+      self.buckets['d_obj'].all_reduce_mean(self.group, self.opts['d_obj'])
       self.opts['d_obj'].step()
 
     # ---------------- image discriminator: train.py:581-592
@@ -419,7 +439,7 @@ class TrainStep(object):
       d_vals['d_img_gan_loss'] = d_img_gan
       self.buckets['d_img'].zero()
       d_img_gan.backward()
-      self.buckets['d_img'].all_reduce_mean(self.group)
+      self.buckets['d_img'].all_reduce_mean(self.group, self.opts['d_img'])
       self.opts['d_img'].step()
 
     if d_vals:

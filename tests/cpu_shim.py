@@ -147,7 +147,7 @@ def _round_tf32(src, dst):
 
 
 def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, weight_decay=0.0,
-               found_inf=None, shadow=None):
+               found_inf=None, shadow=None, grad_scale=1.0):
   """Mathematical definition of sg2im_adam_flat (csrc/adam.cu), torch/optim/adam.py
   single-tensor arithmetic, in place."""
   if found_inf is not None and float(found_inf) != 0.0:
@@ -155,7 +155,8 @@ def _adam_flat(params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, 
   with torch.no_grad():
     step += 1
     t = float(step)
-    g = grads if weight_decay == 0 else grads + weight_decay * params
+    g = grads * grad_scale
+    g = g if weight_decay == 0 else g + weight_decay * params
     exp_avg.add_((g - exp_avg) * (1 - beta1))
     exp_avg_sq.mul_(beta2).add_((1 - beta2) * g * g)
     bc1 = 1 - beta1 ** t

@@ -356,20 +356,6 @@ static inline void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, 
   emul::pipe_push(blk->rank, [=]() { emul_mma1_f16(blk, d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); });
 }
 static inline void fence_proxy_async() {}
-// round-to-nearest-even bf16 (what cvt.rn.bf16x2.f32 does), packed pair, x0 in the low half
-static inline uint32_t emul_bf16_rn(float f) {
-  uint32_t u; std::memcpy(&u, &f, 4);
-  if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;  // inf / nan: truncate
-  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
-}
-static inline void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
-  const uint32_t h0 = emul_bf16_rn(x0), h1 = emul_bf16_rn(x1);
-  hi = h0 | (h1 << 16);
-  uint32_t u0 = h0 << 16, u1 = h1 << 16;
-  float f0, f1; std::memcpy(&f0, &u0, 4); std::memcpy(&f1, &u1, 4);
-  mid = emul_bf16_rn(x0 - f0) | (emul_bf16_rn(x1 - f1) << 16);
-}
-
 // tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words: what the tensor pipe does
 // when the instruction EXECUTES (operands are read from shared memory then, not at issue)
 static inline void emul_mma1(Block* blk, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,

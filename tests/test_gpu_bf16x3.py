@@ -263,18 +263,31 @@ def test_two_reference_training_iterations(weights, adam):
   from sg2im_b200.train_step import TrainStep
   g = load_golden('train_step.pt')
   m, d_obj, d_img = G._build_all(g)
+  from sg2im_b200 import _lib, ops
   step = TrainStep(m, d_obj, d_img, weights=weights, fused_adam=adam)
   batch = [t.to(dev()) for t in g['batch']]
   kw = g['kwargs']
   worst = 0.0
-  for it, seed in enumerate(g['noise_seeds']):
-    noise = G._noise(seed, batch[0].size(0), kw['layout_noise_dim'], kw['image_size']).to(dev())
-    losses, _ = step.step(batch, noise=noise)
-    for k, v in g['losses'][it].items():
-      e = abs(losses[k] - v) / max(1.0, abs(v))
-      worst = max(worst, e)
-      assert e <= 1e-3, (it, k, losses[k], v)
+  calls = []
+  real_call = _lib.call
+  _lib.call = ops._call = lambda name, *a: (calls.append(name), real_call(name, *a))[1]
+  try:
+    for it, seed in enumerate(g['noise_seeds']):
+      noise = G._noise(seed, batch[0].size(0), kw['layout_noise_dim'], kw['image_size']).to(dev())
+      losses, _ = step.step(batch, noise=noise)
+      for k, v in g['losses'][it].items():
+        e = abs(losses[k] - v) / max(1.0, abs(v))
+        worst = max(worst, e)
+        assert e <= 1e-3, (it, k, losses[k], v)
+  finally:
+    _lib.call = ops._call = real_call
   print('worst loss deviation under bf16x3 (%s)' % weights, worst)
+  if weights == 'kcc':
+    # in-place weights: no pack pass; forward / data gradient read the per-step pre-split operand
+    # copies (one sg2im_split_weights launch per network and iteration), the rest splits in-kernel
+    assert 'sg2im_pack_weights' not in calls
+    assert calls.count('sg2im_split_weights') == 2 * len(step.split_shadows) > 0
+    assert calls.count('sg2im_conv_tc_presplit') > 50
 
 
 def test_benchmark_size_generator_forward_vs_exact_fp32_path():

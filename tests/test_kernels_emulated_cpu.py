@@ -50,7 +50,7 @@ def lib(tmp_path_factory):
                                       _i64, _int]
   L.emul_colsum_small.argtypes = [_ptr, _i64, _i64, _ptr]
   L.sg2im_adam_flat.argtypes = [_ptr, _ptr, _ptr, _ptr, _i64, _f32, _f32, _f32, _f32, _f32, _ptr, _ptr,
-                                _ptr, _ptr]
+                                _ptr, _f32, _ptr]
   L.sg2im_deprocess.argtypes = [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _int,
                                 _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr]
   L.emul_last_error.restype = ctypes.c_char_p
@@ -242,7 +242,7 @@ def test_adam_flat_source_on_cpu(lib):
       opt.step()
       shadow = torch.full((n,), float('nan'))
       _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
-                                   _p(step), None, _p(shadow), None))
+                                   _p(step), None, _p(shadow), 1.0, None))
       assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7), (n, it)
       # the RN-TF32 shadow: low 13 mantissa bits clear, within half a TF32 ulp of the master
       assert int((shadow.view(torch.int32) & 0x1fff).abs().max()) == 0
@@ -251,8 +251,16 @@ def test_adam_flat_source_on_cpu(lib):
     before = p.clone()
     inf = torch.ones(())
     _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
-                                 _p(step), _p(inf), None, None))
+                                 _p(step), _p(inf), None, 1.0, None))
     assert torch.equal(p, before) and float(step) == 5
+    # gradient scale (1 / world of a SUM all-reduce): same update as Adam on the scaled gradient
+    p2, m2, v2, s2 = p.clone(), m.clone(), v.clone(), step.clone()
+    _ok(lib, lib.sg2im_adam_flat(_p(p), _p(grad), _p(m), _p(v), n, 1e-2, 0.9, 0.999, 1e-8, wd,
+                                 _p(step), None, None, 0.25, None))
+    g4 = (grad * 0.25).contiguous()
+    _ok(lib, lib.sg2im_adam_flat(_p(p2), _p(g4), _p(m2), _p(v2), n, 1e-2, 0.9, 0.999, 1e-8, wd,
+                                 _p(s2), None, None, 1.0, None))
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
 
 
 def test_deprocess_source_on_cpu_bit_exact(lib):

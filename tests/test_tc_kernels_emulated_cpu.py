@@ -271,3 +271,56 @@ def test_operand_split_is_exact_to_bf16_pairs(lib):
   assert lib.sg2im_conv_tc(_p(x), C, 128, 1, 1, C, _p(wt), None, 1, 1, 0, 1, 1, C, 0, 0.0, _p(y1), C, 0,
                            None, 0, BF16, None) == 0
   assert torch.equal(y1, x.bfloat16().float())             # plain bf16: round-to-nearest-even hi only
+
+
+@pytest.mark.parametrize('N,H,W,Ci,Co,K,P,Cf,e', KCC_CASES)
+def test_presplit_weight_operands(lib, env, N, H, W, Ci, Co, K, P, Cf, e):
+  """sg2im_split_weights (all weights of a network in one launch -> bf16 hi / mid operand copies)
+  + sg2im_conv_tc_presplit (the converters then split only the activation tiles): forward and data
+  gradient, bit-identical to the in-kernel split of the same weights (same values, same products,
+  same accumulation order)."""
+  env(**e)
+  g = torch.Generator().manual_seed(Ci * 3 + Co)
+  T = K * K
+  x = torch.randn(N, H, W, Ci, generator=g)
+  w_full = torch.randn(Co, Cf, K, K, generator=g) * 0.1
+  b = torch.randn(Co, generator=g)
+  kcc = w_full.permute(2, 3, 1, 0).reshape(T, Cf, Co).contiguous()
+  other = torch.randn(3, 40, 36, generator=g)                  # a second entry of the table
+  cip, cop = (Cf + 31) // 32 * 32, (Co + 31) // 32 * 32
+  fwd, dgr = torch.full((T, Co, cip), 7.0), torch.full((T, Cf, cop), 7.0)
+  f2, d2 = torch.zeros(3, 36, 64), torch.zeros(3, 40, 64)
+  t0 = 3 * 2 * 2
+  table = torch.tensor([[other.data_ptr(), f2.data_ptr(), d2.data_ptr(), 3, 40, 36, 0, 0],
+                        [kcc.data_ptr(), fwd.data_ptr(), dgr.data_ptr(), T, Cf, Co, t0, 0]], dtype=torch.int64)
+  total = t0 + T * (cip // 32) * (cop // 32)
+  assert lib.sg2im_split_weights(_p(table), 2, total, None) == 0, lib.emul_last_error()
+  # hi + mid reproduces the weights to 2^-17; pad channels are zero
+  def join(t):                                               # (.., blocks*32 floats) -> hi + mid per channel
+    u = t.contiguous().view(torch.int32).reshape(*t.shape[:-1], t.shape[-1] // 32, 2, 16)
+    lo16 = (u << 16).view(torch.float32)
+    hi16 = (u & ~0xffff).view(torch.float32)
+    vals = torch.stack([lo16, hi16], -1).reshape(*t.shape[:-1], t.shape[-1] // 32, 2, 32)
+    return (vals[..., 0, :] + vals[..., 1, :]).reshape(*t.shape[:-1], -1)
+  wf = join(fwd)                                             # (T, Co, cip)
+  ref_f = kcc.permute(0, 2, 1)                               # (T, Co, Cf)
+  assert float((wf[..., :Cf] - ref_f).abs().max()) <= 2.0 ** -16 * float(ref_f.abs().max())
+  assert float(wf[..., Cf:].abs().max()) == 0 if cip > Cf else True
+  wd = join(dgr)                                             # (T flipped, Cf, cop)
+  assert float((wd[..., :Co] - kcc.flip(0)).abs().max()) <= 2.0 ** -16 * float(kcc.abs().max())
+  # forward / data gradient through the pre-split operands == the in-kernel split, bit for bit
+  Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
+  for math in (BF16X3, BF16):
+    y0, y1 = torch.empty(N, Ho, Wo, Co), torch.empty(N, Ho, Wo, Co)
+    assert lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kcc), Cf, 0, _p(b), K, K, P, Ho, Wo, Co, 1, 0.2,
+                                 _p(y0), Co, 0, None, 0, math, None) == 0, lib.emul_last_error()
+    assert lib.sg2im_conv_tc_presplit(_p(x), Ci, N, H, W, Ci, _p(fwd), cip, Co, _p(b), K, K, P, Ho, Wo, Co, 1,
+                                      0.2, _p(y1), Co, 0, None, math, None) == 0, lib.emul_last_error()
+    assert torch.equal(y0, y1)
+    gy = torch.randn(N, Ho, Wo, Co, generator=g)
+    d0, d1 = torch.empty(N, H, W, Ci), torch.empty(N, H, W, Ci)
+    assert lib.sg2im_conv_tc_kcc(_p(gy), Co, N, Ho, Wo, Co, _p(kcc), Cf, 1, None, K, K, K - 1 - P, H, W, Ci, 0,
+                                 0.0, _p(d0), Ci, 0, None, 0, math, None) == 0, lib.emul_last_error()
+    assert lib.sg2im_conv_tc_presplit(_p(gy), Co, N, Ho, Wo, Co, _p(dgr), cop, Cf, None, K, K, K - 1 - P, H, W,
+                                      Ci, 0, 0.0, _p(d1), Ci, 0, None, math, None) == 0, lib.emul_last_error()
+    assert torch.equal(d0, d1)
