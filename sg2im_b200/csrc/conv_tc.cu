@@ -326,19 +326,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 3 = weight-tile converter, 8-11 = halo-box converters (every halo box and weight
 // tile is split once and then read by all the taps / pixel tiles it serves).
 // =============================================================================
-constexpr int H_BN = 64, H_T = 4, H_BW = 8, H_BH = 16;
+constexpr int H_BW = 8, H_BH = 16;
+// Cout tile HB = 64: T = 4 pixel tiles per weight set, two weight sets (double buffered per channel
+// block).  HB = 128 (outputs >= 128 channels wide): T = 2, ONE weight set whose tap tiles are
+// refilled for the next channel block as soon as the last pixel tile has used them (eight taps of
+// MMA time ahead of their next use) — N = 128 MMAs run at the math rate (64.1 cycles measured)
+// instead of the shared-memory-bound 48.1 per N = 64 half, and every activation tile is read,
+// converted and fed once per 128 instead of once per 64 output channels.
+template <int HB> struct HCfg {
+  static constexpr int T = HB == 64 ? 4 : 2;
+  static constexpr int SETS = HB == 64 ? 2 : 1;
+  static constexpr int B_TILE = HB * KB_BYTES;          // 8 / 16 KB
+};
 constexpr int H_A_SLOT = 23 * 1024;           // 180 rows x 128 B = 23040, padded to 1 KB
 constexpr int H_A_SLOTS = 3;
-constexpr int H_B_TILE = H_BN * KB_BYTES;     // 8 KB
 constexpr int H_MAX_TAPS = 9;
 constexpr int H_THREADS = 256;
-constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * H_B_TILE + 1024 + 1024 + 8192;
+constexpr int H_SMEM = H_A_SLOTS * H_A_SLOT + 2 * H_MAX_TAPS * 64 * KB_BYTES + 1024 + 1024 + 8192;
 
 struct HaloParams {
   int N, Hout, Wout, Cin, Cout;
   int KH, KW, P, taps, pitch;      // pitch = 8 + KW - 1 halo pixels per tile row
   int tiles_w, tiles_h, ptiles;    // pixel tiles of 8 x 16
-  int groups, n_tiles, cblocks;    // groups of H_T pixel tiles; Cout tiles of 64
+  int groups, n_tiles, cblocks;    // groups of T pixel tiles; Cout tiles of HB
   uint32_t a_bytes;                // bytes of one halo box
   const float* bias;
   int act; float slope;
@@ -348,16 +358,17 @@ struct HaloParams {
   int nprod;                       // MATH 1: 3 = bf16x3, 1 = bf16
 };
 
-template <int WMODE, int MATH, int PS = 0>        // weight source / arithmetic / pre-split B, see conv_tc_kernel
+template <int WMODE, int MATH, int PS = 0, int HB = 64>   // weight source / arithmetic / pre-split B / Cout tile
 __global__ void __launch_bounds__(H_THREADS + (MATH ? CONV_THREADS : 0), 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const HaloParams p) {
+  constexpr int H_BN = HB, H_T = HCfg<HB>::T, H_B_TILE = HCfg<HB>::B_TILE, SETS = HCfg<HB>::SETS;
   SG_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + H_A_SLOTS * H_A_SLOT;                    // [2][taps][8 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * H_MAX_TAPS * H_B_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SETS * H_MAX_TAPS * H_B_TILE);
   uint64_t* a_full = bars;                    // [3]
   uint64_t* a_empty = bars + 3;               // [3]
   uint64_t* b_full = bars + 6;                // [2][9]
@@ -433,15 +444,16 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int nt, pt0;
         decode(item, nt, pt0);
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const int set = (int)(bcnt % SETS); const uint32_t bph = (bcnt / SETS) & 1;
           for (int tap = 0; tap < p.taps; ++tap) {
             uint64_t* fb = &b_full[set * H_MAX_TAPS + tap];
             mbar_wait(&b_empty[set * H_MAX_TAPS + tap], bph ^ 1);
             mbar_expect_tx(fb, H_B_TILE);
             if constexpr (WMODE == 1) {
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, nt * H_BN, cb * 32, tap);
-              tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE + 4096, &tmB, fb, nt * H_BN + 32,
-                          cb * 32, tap);
+#pragma unroll
+              for (int a = 0; a < H_BN / 32; ++a)
+                tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE + a * 4096, &tmB, fb,
+                            nt * H_BN + a * 32, cb * 32, tap);
             } else {
               tma_load_3d(sB + (set * H_MAX_TAPS + tap) * H_B_TILE, &tmB, fb, cb * 32, nt * H_BN,
                           WMODE == 2 ? p.taps - 1 - tap : tap);
@@ -472,7 +484,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty[aset], acc_ph ^ 1);
         tc_fence_after();
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const int set = (int)(bcnt % SETS); const uint32_t bph = (bcnt / SETS) & 1;
           const uint32_t b_set = sB16 + (uint32_t)(set * H_MAX_TAPS) * (H_B_TILE >> 4);
           uint64_t* bf = (MATH && !PS) ? &b_ready[set * H_MAX_TAPS] : &b_full[set * H_MAX_TAPS];
           uint64_t* be = &b_empty[set * H_MAX_TAPS];
@@ -570,15 +582,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t bcnt = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
-          const int set = bcnt & 1; const uint32_t bph = (bcnt >> 1) & 1;
+          const int set = (int)(bcnt % SETS); const uint32_t bph = (bcnt / SETS) & 1;
           for (int tap = 0; tap < p.taps; ++tap) {
             mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
             uint8_t* b = sB + (set * H_MAX_TAPS + tap) * H_B_TILE;
             if constexpr (WMODE == 1) {
-              split_rowpair_inplace(b + lane * 128, b + 4096 + lane * 128);
+#pragma unroll
+              for (int q = 0; q < H_BN / 64; ++q)
+                split_rowpair_inplace(b + q * 8192 + lane * 128, b + q * 8192 + 4096 + lane * 128);
             } else {
-              split_row_inplace(b + lane * 128);
-              split_row_inplace(b + (32 + lane) * 128);
+#pragma unroll
+              for (int q = 0; q < H_BN / 32; ++q) split_row_inplace(b + (q * 32 + lane) * 128);
             }
             fence_proxy_async();
             __syncwarp();
@@ -652,12 +666,12 @@ int launch_w(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, 
        : wmode == 2 ? launch<BN, 2, MATH>(tmA, tmB, p, st) : launch<BN, 0, MATH>(tmA, tmB, p, st);
 }
 
-template <int WMODE, int MATH, int PS = 0>
+template <int WMODE, int MATH, int PS = 0, int HB = 64>
 int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& h, cudaStream_t st) {
 #ifndef SG2IM_EMUL
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<WMODE, MATH, PS>,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<WMODE, MATH, PS, HB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM);
     if (e != cudaSuccess) {
       sg2im_set_error("conv_tc_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -668,7 +682,7 @@ int launch_halo(const CUtensorMap& hA, const CUtensorMap& hB, const HaloParams& 
 #endif
   int items = h.groups * h.n_tiles;
   int grid = items < num_sms() ? items : num_sms();
-  SG_LAUNCH((conv_tc_halo_kernel<WMODE, MATH, PS>), grid, H_THREADS + (MATH ? CONV_THREADS : 0), H_SMEM,
+  SG_LAUNCH((conv_tc_halo_kernel<WMODE, MATH, PS, HB>), grid, H_THREADS + (MATH ? CONV_THREADS : 0), H_SMEM,
             st, hA, hB, h);
   return 0;
 }
@@ -789,15 +803,22 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
   cudaStream_t st = as_stream(stream);
 
   // narrow outputs on real images: halo + weight-stationary kernel
-  if (KH * KW > 1 && KH <= 3 && KW <= 3 && Hout >= H_BH && Wout >= H_BW && BN <= 128 &&
+  // (tf32: only where the per-tap kernel would use N <= 128 tiles; bf16 arithmetic: every such shape —
+  // the per-tap kernel moves 2.3x the L2 -> SM bytes per FLOP even with N = 256 tiles and sits on the
+  // ~6.6 TB/s the L2 fabric delivers, profiles/r02_call3_conv_kernels_bf16x3_ncu.txt)
+  if (KH * KW > 1 && KH <= 3 && KW <= 3 && Hout >= H_BH && Wout >= H_BW && (BN <= 128 || bf) &&
       getenv("SG2IM_NO_HALO") == nullptr) {
     HaloParams h;
     h.N = (int)N; h.Hout = (int)Hout; h.Wout = (int)Wout; h.Cin = (int)Cin; h.Cout = (int)Cout;
     h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
     h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, H_BH);
     h.ptiles = (int)(N * h.tiles_h * h.tiles_w);
-    h.groups = (int)ceil_div64(h.ptiles, H_T);
-    h.n_tiles = (int)ceil_div64(Cout, H_BN);
+    // Cout tile: 128 for outputs at least 128 channels wide (bf16 arithmetic; SG2IM_HALO_BN=64|128 pins it)
+    int HB = (bf && Cout >= 128) ? 128 : 64;
+    if (const char* e = getenv("SG2IM_HALO_BN")) { int f = atoi(e); if (f == 64 || (f == 128 && bf)) HB = f; }
+    const int HT = HB == 64 ? 4 : 2;
+    h.groups = (int)ceil_div64(h.ptiles, HT);
+    h.n_tiles = (int)ceil_div64(Cout, HB);
     h.cblocks = (int)ceil_div64(Cin, 32);
     h.a_bytes = (uint32_t)((H_BH + KH - 1) * h.pitch * 128);
     h.bias = bias; h.act = act; h.slope = slope;
@@ -815,9 +836,13 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { sg2im_set_error("sg2im_conv_tc: encode halo A failed (%d)", (int)r); return -4; }
     }
-    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, H_BN, wmode, w_rows_full, bf, ps_pitch)) return rc;
+    if (int rc = encode_weights(enc, &hB, w_tc, Cin, Cout, KH * KW, HB, wmode, w_rows_full, bf, ps_pitch)) return rc;
     int rc;
-    if (ps_pitch) rc = launch_halo<0, 1, 1>(hA, hB, h, st);
+    if (HB == 128) {
+      if (ps_pitch) rc = launch_halo<0, 1, 1, 128>(hA, hB, h, st);
+      else rc = wmode == 1 ? launch_halo<1, 1, 0, 128>(hA, hB, h, st)
+              : wmode == 2 ? launch_halo<2, 1, 0, 128>(hA, hB, h, st) : launch_halo<0, 1, 0, 128>(hA, hB, h, st);
+    } else if (ps_pitch) rc = launch_halo<0, 1, 1>(hA, hB, h, st);
     else if (bf) rc = wmode == 1 ? launch_halo<1, 1>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 1>(hA, hB, h, st)
                                                                            : launch_halo<0, 1>(hA, hB, h, st);
     else rc = wmode == 1 ? launch_halo<1, 0>(hA, hB, h, st) : wmode == 2 ? launch_halo<2, 0>(hA, hB, h, st)

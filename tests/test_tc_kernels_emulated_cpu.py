@@ -92,7 +92,10 @@ FWD_CASES = [  # N, H, W, Ci, Co, K, P, env
     (4, 1, 1, 64, 128, 1, 0, {}),                              # Linear
     (1, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 256}),            # N tile 256
     (1, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 128}),
-    (2, 15, 15, 48, 32, 2, 0, {})]                             # 2x2 taps of the space-to-depth route
+    (2, 15, 15, 48, 32, 2, 0, {}),                             # 2x2 taps of the space-to-depth route
+    (3, 16, 16, 96, 128, 3, 1, {}),                            # halo kernel, Cout tile 128 (bf16 arithmetic)
+    (2, 32, 8, 40, 160, 3, 1, {}),                             # ... ragged second Cout tile, ragged channels
+    (5, 17, 9, 32, 256, 2, 0, {'SG2IM_EMUL_SMS': 2})]          # ... many groups per CTA: weight tiles refilled in flight
 
 
 @pytest.mark.parametrize('math', MATHS, ids=MATH_IDS)
@@ -183,7 +186,9 @@ KCC_CASES = [  # N, H, W, Ci, Co, K, P, Ci_full, env
     (4, 1, 1, 64, 128, 1, 0, 64, {}),                          # Linear
     (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 256}),
     (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 128}),
-    (2, 15, 15, 48, 32, 2, 0, 48, {})]
+    (2, 15, 15, 48, 32, 2, 0, 48, {}),
+    (3, 16, 24, 64, 128, 3, 1, 64, {}),                        # halo kernel, Cout tile 128
+    (2, 16, 16, 96, 192, 3, 1, 104, {'SG2IM_EMUL_SMS': 2})]    # ... two Cout tiles (one half empty), channel prefix
 
 
 @pytest.mark.parametrize('math', MATHS, ids=MATH_IDS)
@@ -247,6 +252,17 @@ def test_converter_protocol_under_adversarial_schedules(lib, env, sched):
   y = torch.empty(N, H, W, Co)
   assert lib.sg2im_conv_tc_kcc(_p(x), Ci, N, H, W, Ci, _p(kw), Ci, 0, None, 3, 3, 1, H, W, Co, 0, 0.0,
                                _p(y), Co, 0, None, 0, BF16X3, None) == 0, lib.emul_last_error()
+  ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, padding=1).permute(0, 2, 3, 1)
+  assert rel_err(y, ref) < 3e-5
+  # halo kernel with the 128-wide Cout tile and ONE weight set refilled tap by tap: 2 CTAs, 8 items
+  env(SG2IM_EMUL_SMS=2, **sched)
+  N, H, W, Ci, Co = 4, 32, 16, 96, 256
+  x = torch.randn(N, H, W, Ci, generator=g)
+  w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.1
+  wt = w.permute(2, 3, 0, 1).reshape(9, Co, Ci).contiguous()
+  y = torch.empty(N, H, W, Co)
+  assert lib.sg2im_conv_tc(_p(x), Ci, N, H, W, Ci, _p(wt), None, 3, 3, 1, H, W, Co, 0, 0.0, _p(y), Co, 0,
+                           None, 0, BF16X3, None) == 0, lib.emul_last_error()
   ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, padding=1).permute(0, 2, 3, 1)
   assert rel_err(y, ref) < 3e-5
   # weight gradient
