@@ -53,6 +53,10 @@ def parse():
   ap.add_argument('--weights', default='kcc', choices=['oihw', 'kcc'],
                   help="'kcc': conv / linear weights stored in the weight-gradient layout, no pack / unpack "
                        "passes; 'oihw': the reference's layout, packed per use")
+  ap.add_argument('--shape-jitter', type=int, default=0,
+                  help='K > 0: the timed batches cycle through K different (objects, triples) signatures, '
+                       'like a real VG / COCO loader; K <= 4 recurring signatures are captured and replayed, '
+                       'a large K (every batch different) exercises the eager fallback of the bounded graph cache')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--shapes-out', default=None, help='write per-shape conv timings (JSON)')
@@ -271,8 +275,15 @@ def run_b200(args, cfg):
                    fused_adam='flat' if args.adam == 'flat' else None, weights=args.weights)
   torch.manual_seed(1234 + rank)                         # noise stream differs per rank
 
-  n_pool = 4
-  host = [[t.pin_memory() for t in synth_batch(seed=1000 * rank + i, **cfg)]
+  n_pool = max(4, args.shape_jitter)
+  def pool_cfg(i):
+    c = dict(cfg)
+    if args.shape_jitter:                                # fewer objects / relations per image, same images
+      k = i % args.shape_jitter
+      c['objs_per_img'] = max(2, cfg['objs_per_img'] - (k % 7))
+      c['rels_per_img'] = max(1, cfg['rels_per_img'] - (k // 7) % 4)
+    return c
+  host = [[t.pin_memory() for t in synth_batch(seed=1000 * rank + i, **pool_cfg(i))]
           for i in range(n_pool)]
   resident = [[t.to(dev) for t in b] for b in host]
   h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -292,8 +303,12 @@ def run_b200(args, cfg):
     e0.record()
     last = None
     for i in range(n_steps):
-      if profile is not None or profile_hbm is not None:  # per-kernel events need eager launches
-        last, _ = step._step_eager(resident[i % n_pool])
+      if profile is not None or profile_hbm is not None:  # per-kernel events need eager launches:
+        graphed, step.cuda_graph = step.cuda_graph, False  # the SAME configuration (pre-split weights,
+        try:                                               # direct gradient accumulation), not replayed
+          last, _ = step.step(resident[i % n_pool])
+        finally:
+          step.cuda_graph = graphed
       elif from_host and step.cuda_graph:
         last, _ = step.step(host[i % n_pool])            # H2D into the graph's static inputs
       elif from_host:
@@ -313,7 +328,9 @@ def run_b200(args, cfg):
     return ms, n_launch, last
 
   if step.cuda_graph:
-    timed(4, False)                                      # setup: 3 eager iterations + graph capture
+    # setup: 3 eager iterations + graph capture (with --shape-jitter: two passes over the pool so that
+    # every recurring signature has been seen twice and is captured, if the cache holds it)
+    timed(4 if not args.shape_jitter else 3 + 2 * n_pool, False)
   timed(args.warmup, False)                              # the W untimed warm-up steps
   sampler = ClockSampler(local)
   sampler.start()
@@ -400,6 +417,36 @@ def run_b200(args, cfg):
     rows.sort(key=lambda r: -r['ms_per_step'])
     json.dump(rows, open(args.shapes_out, 'w'), indent=1)
 
+  # ---- measured parity of THIS arithmetic at the benchmark architecture: generator forward (train-mode
+  # BatchNorm, same weights / batch / noise) against the exact-fp32 FFMA kernels of this library,
+  # which the GPU tests pin to the CPU oracle / the reference's goldens at ~1e-6
+  parity = None
+  if rank == 0 and ops.CONV_MATH != 'fp32':
+    try:
+      b0 = resident[0]
+      masks0 = b0[3] if len(b0) == 7 else None
+      objs0, boxes0, triples0, o2i0 = b0[1], b0[2], b0[-3], b0[-2]
+      H_, W_ = cfg['image_size']
+      gen = torch.Generator(device=dev).manual_seed(7)
+      noise0 = torch.randn(cfg['N'], 32, H_, W_, device=dev, generator=gen)
+      outs = {}
+      mode0 = ops.CONV_MATH
+      for mode in (mode0, 'fp32'):
+        ops.set_conv_math(mode)
+        with torch.no_grad():
+          outs[mode] = [t.float().clone() for t in model(objs0, triples0, o2i0, boxes_gt=boxes0,
+                                                         masks_gt=masks0, num_imgs=cfg['N'], noise=noise0)]
+      ops.set_conv_math(mode0)
+      errs = [float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+              for a, b in zip(outs[mode0], outs['fp32'])]
+      parity = {'rel_err': dict(zip(('image', 'boxes', 'masks', 'rel_scores'), errs)), 'bar': 1e-3,
+                'meets_bar': max(errs) < 1e-3, 'metric': 'max|a-b| / max|b|',
+                'against': 'generator forward on the exact-fp32 FFMA kernels of this library (pinned to the '
+                           'CPU oracle and the reference-generated goldens by tests/test_gpu_model.py)'}
+    except Exception as e:                               # instrumentation only
+      ops.set_conv_math(args.math)
+      parity = {'error': repr(e)[:200]}
+
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     r = cpu_reference_arm(cfg, steps=2, warmup=1, sample_imgs=cpu_sample_images(cfg), budget_s=40.0)
@@ -416,13 +463,15 @@ def run_b200(args, cfg):
                    'triples_per_gpu': int(resident[0][-3].size(0)),
                    'image_size': list(cfg['image_size']), 'global_batch': cfg['N'] * world,
                    'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph), 'adam': args.adam, 'weights': args.weights,
+                   'shape_jitter': args.shape_jitter, 'graphs_cached': len(step._graphs),
+                   'graph_evictions': step.graph_evictions, 'graph_replays': step.replays,
                    'switches': sorted(k for k in os.environ if k.startswith('SG2IM_') and os.environ[k] == '1'),
                    'setup': '4 untimed iterations before the warm-up (3 eager + CUDA-graph capture)'
                             if step.cuda_graph else 'none',
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
                          'no explicit flush'},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roof,
-        'hbm_kernels': hbm,
+        'hbm_kernels': hbm, 'parity': parity,
         'cpu_baseline': cpu, 'last_losses': last,
     }
     print(json.dumps(line), flush=True)

@@ -813,8 +813,10 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
     h.KH = KH; h.KW = KW; h.P = P; h.taps = KH * KW; h.pitch = H_BW + KW - 1;
     h.tiles_w = (int)ceil_div64(Wout, H_BW); h.tiles_h = (int)ceil_div64(Hout, H_BH);
     h.ptiles = (int)(N * h.tiles_h * h.tiles_w);
-    // Cout tile: 128 for outputs at least 128 channels wide (bf16 arithmetic; SG2IM_HALO_BN=64|128 pins it)
-    int HB = (bf && Cout >= 128) ? 128 : 64;
+    // Cout tile: 128 for outputs at least 128 channels wide when the weights arrive pre-split (its single
+    // weight set leaves no slack for an in-kernel split of 9 x 128 weight rows per channel block:
+    // measured slower than the 64-wide tile then); SG2IM_HALO_BN=64|128 pins it
+    int HB = (ps_pitch && Cout >= 128) ? 128 : 64;
     if (const char* e = getenv("SG2IM_HALO_BN")) { int f = atoi(e); if (f == 64 || (f == 128 && bf)) HB = f; }
     const int HT = HB == 64 ? 4 : 2;
     h.groups = (int)ceil_div64(h.ptiles, HT);

@@ -42,7 +42,11 @@ def _count(n=1):
 # bench.py sets PROFILE to a list to time the conv kernels with CUDA events on
 # the launching stream: entries (kernel family, algorithmic flops, start, end)
 PROFILE = None
-CONV_MATH = 'fp32'          # arithmetic of the convolution path ('fp32' FFMA | 'tf32' tcgen05)
+# arithmetic of the convolution / Linear path (set_conv_math): 'bf16x3' (default) = tcgen05 tensor cores
+# on in-kernel bf16 hi / mid operand pairs, three products per fp32 multiply — fp32-grade results
+# (1e-3 parity bar met with ~2 orders of magnitude to spare); 'tf32' / 'bf16' = faster, less exact
+# tensor-core modes; 'fp32' = the exact FFMA kernels
+CONV_MATH = 'bf16x3'
 
 
 class _prof(object):

@@ -9,6 +9,7 @@ iteration: an NCCL all-reduce (sum, then / world) of that network's flat fp32
 gradient bucket.  The non-finite-loss skip of train.py:552-555 is made
 collective (all-reduce MIN of the finite flag) so ranks cannot diverge.
 """
+import collections
 import math
 
 import torch
@@ -113,8 +114,43 @@ class FlatAdam(object):
       from . import ops
       ops.round_tf32(self.flat_params, self.shadow)
 
+  def _check_attached(self):
+    for p, o in zip(self.bucket.params, self.bucket.offsets):
+      if p.data_ptr() != self.flat_params.data_ptr() + 4 * o:
+        raise RuntimeError('sg2im_b200: a parameter was re-allocated (model.to() / .float() / '
+                           'assignment to .data) after FlatAdam took it over')
+
+  def state_dict(self):
+    """torch.optim.Adam's format (per-parameter `step`, `exp_avg`, `exp_avg_sq`; one param group),
+    so checkpoints written by scripts/train.py:633-641 style code resume with either optimiser."""
+    state = {}
+    for i, (p, o) in enumerate(zip(self.bucket.params, self.bucket.offsets)):
+      sl = slice(o, o + p.numel())
+      state[i] = {'step': self.step_count.detach().clone(),
+                  'exp_avg': self.exp_avg[sl].as_strided(p.shape, p.stride()).clone(),
+                  'exp_avg_sq': self.exp_avg_sq[sl].as_strided(p.shape, p.stride()).clone()}
+    group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay,
+                 amsgrad=False, params=list(range(len(self.bucket.params))))
+    return {'state': state, 'param_groups': [group]}
+
+  def load_state_dict(self, sd):
+    g = sd['param_groups'][0]
+    self.lr, self.betas, self.eps = g['lr'], tuple(g['betas']), g['eps']
+    self.weight_decay = g.get('weight_decay', 0.0)
+    with torch.no_grad():
+      for i, (p, o) in enumerate(zip(self.bucket.params, self.bucket.offsets)):
+        st = sd['state'].get(i, sd['state'].get(str(i)))
+        if st is None:
+          continue
+        sl = slice(o, o + p.numel())
+        self.exp_avg[sl].as_strided(p.shape, p.stride()).copy_(st['exp_avg'])
+        self.exp_avg_sq[sl].as_strided(p.shape, p.stride()).copy_(st['exp_avg_sq'])
+        self.step_count.fill_(float(st['step']))
+    self.refresh_shadow()
+
   def step(self):
     from . import ops
+    self._check_attached()
     ops.adam_flat(self.flat_params, self.bucket.flat, self.exp_avg, self.exp_avg_sq,
                   self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
                   self.weight_decay, self.found_inf, self.shadow, self.grad_scale)
@@ -144,7 +180,8 @@ class TrainStep(object):
   which leaves parameters, moments and step counts untouched."""
 
   def __init__(self, model, obj_discriminator, img_discriminator, args=None,
-               fused_adam=None, group=None, cuda_graph=False, graph_warmup=3, weights='oihw'):
+               fused_adam=None, group=None, cuda_graph=False, graph_warmup=3, weights='oihw',
+               max_graphs=4, graph_min_seen=2):
     a = dict(DEFAULT_ARGS)
     if args is not None:
       a.update(args if isinstance(args, dict) else
@@ -164,7 +201,18 @@ class TrainStep(object):
       kw['fused'] = True
       kw['capturable'] = True
     self.graph_warmup = graph_warmup
-    self._graphs = {}                     # shape signature -> captured state
+    # Captured graphs are keyed by the exact batch-shape signature.  Real VG / COCO batches change
+    # their object / triple counts almost every iteration, so the cache is BOUNDED (least recently
+    # used graph — and its private memory pool and static input copies — dropped beyond
+    # `max_graphs`) and a signature is captured only once it has been seen `graph_min_seen` times;
+    # everything else runs eagerly.  Fixed-shape loaders (the benchmark's synthetic batches, a
+    # bucketing collate) get the replay path, variable-shape loaders degrade to the eager path
+    # instead of recapturing ~1500 launches per step and growing memory without bound.
+    self.max_graphs = max(1, int(max_graphs))
+    self.graph_min_seen = max(1, int(graph_min_seen))
+    self._graphs = collections.OrderedDict()   # shape signature -> captured state (LRU order)
+    self._seen = collections.Counter()
+    self.graph_evictions = 0
     self._eager_calls = 0
     self.launches_per_replay = 0
     self.replays = 0
@@ -205,6 +253,32 @@ class TrainStep(object):
           if sh.table is not None:
             self.split_shadows.append(sh)
     self.skipped = 0
+    self.sync_replicas()
+
+  def sync_replicas(self):
+    """Data parallel: make every rank start from rank 0's parameters AND buffers (what
+    torch DDP does at construction and, for buffers, every forward with broadcast_buffers=True).
+    Gradients are averaged each step, so identical replicas stay identical; BatchNorm running
+    statistics are rank-LOCAL during training like the reference run at the per-GPU batch (no
+    SyncBN) — call this again before saving a checkpoint or evaluating to publish rank 0's.
+    No-op without an initialised process group or with one rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) < 2:
+      return
+    src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+    with torch.no_grad():
+      for name, net in self.nets.items():
+        if net is None:
+          continue
+        opt = self.opts.get(name)
+        if isinstance(opt, FlatAdam):
+          dist.broadcast(opt.flat_params, src, group=self.group)     # every parameter lives in it
+          opt.refresh_shadow()
+        else:
+          for p in net.parameters():
+            dist.broadcast(p.data, src, group=self.group)
+        for b in net.buffers():
+          dist.broadcast(b, src, group=self.group)
 
   # -- loss assembly, scripts/train.py:387-412 + :539-550
   def generator_losses(self, imgs, imgs_pred, boxes, boxes_pred, masks, masks_pred,
@@ -260,11 +334,21 @@ class TrainStep(object):
     st = self._graphs.get(sig)
     dev = next(self.model.parameters()).device
     if st is None:
-      if self._eager_calls < self.graph_warmup:
+      self._seen[sig] += 1
+      if self._eager_calls < self.graph_warmup or self._seen[sig] < self.graph_min_seen:
         self._eager_calls += 1
-        return self._step_eager([t.to(dev, non_blocking=True) for t in batch], noise)
+        return self._step_eager([t.to(dev, non_blocking=True) for t in batch],
+                                None if noise is None else noise.to(dev, non_blocking=True))
+      while len(self._graphs) >= self.max_graphs:      # drop the least recently used graph first
+        _, old = self._graphs.popitem(last=False)
+        old.clear()
+        self.graph_evictions += 1
       st = self._capture([t.to(dev) for t in batch], noise)
       self._graphs[sig] = st
+      if len(self._seen) > 4096:
+        self._seen.clear()
+    else:
+      self._graphs.move_to_end(sig)
     for dst, src in zip(st['batch'], batch):
       dst.copy_(src, non_blocking=True)
     if noise is not None:
@@ -276,6 +360,9 @@ class TrainStep(object):
     if not math.isfinite(out['total_loss']):
       print('WARNING: Got loss = NaN, not backpropping')
       self.skipped += 1
+    # NOTE: the returned images are the graph's static output buffer — valid until the next step()
+    # with the same batch signature overwrites it (clone it to keep it; the training loop of
+    # scripts/train.py only logs / detaches it within the iteration)
     return out, st['imgs_fake']
 
   def _capture(self, batch, noise):

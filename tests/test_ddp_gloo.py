@@ -88,13 +88,25 @@ def _train_worker(rank, world, port, q):
       d_obj = AcCropDiscriminator(vocab=g['vocab'], arch=g['arch'], normalization='batch',
                                   activation='leakyrelu-0.2', padding='valid', object_size=g['crop'])
     m.load_state_dict(g['sd_g']); d_img.load_state_dict(g['sd_img']); d_obj.load_state_dict(g['sd_obj'])
+    if rank == 1:
+      # a replica that starts from DIFFERENT weights and running statistics (a resumed / differently
+      # seeded rank): TrainStep must bring it to rank 0's state before the first step
+      with torch.no_grad():
+        for net in (m, d_img, d_obj):
+          for p in net.parameters():
+            p.add_(0.25)
+          for b in net.buffers():
+            if b.dtype.is_floating_point:
+              b.add_(1.0)
     H, W = kw['image_size']
     N = g['batch'][0].size(0)
     # every rank its own shard (same shapes, different content), as bench.py does under torchrun
     shard = synth_batch(N=N, objs_per_img=3, rels_per_img=2, image_size=(H, W), num_objs=9,
                         num_preds=5, seed=1000 * rank)
     with cpu_ops():
-      step = TrainStep(m, d_obj, d_img)
+      step = TrainStep(m, d_obj, d_img, fused_adam='flat' if os.environ.get('SG2IM_TEST_FLAT') else None)
+      synced = all(torch.equal(v, g['sd_g'][k]) for k, v in m.state_dict().items())
+      assert synced, 'rank %d did not start from rank 0 weights / buffers' % rank
       out = []
       for it in range(2):
         torch.manual_seed(50 + 10 * it + rank)

@@ -752,3 +752,36 @@ def test_generator_trains_on_predicted_boxes():
       seen_box = seen_box or float(rg.abs().max()) > 0
     assert rel_err(p.grad.cpu(), rg) < 10 * TOL, (k, rel_err(p.grad.cpu(), rg))
   assert seen_box                                  # box_net is reached ONLY through the layout here
+
+
+def test_cuda_graph_cache_is_bounded_for_variable_batch_shapes():
+  """Real VG / COCO loaders change the object / triple counts almost every iteration.  The graph
+  cache of TrainStep is LRU-bounded and a signature is captured only after it was seen twice:
+  one-off shapes run eagerly, recurring ones replay, and evicted graphs release their memory."""
+  import test_gpu_model as G
+  from sg2im_b200.synth import synth_batch
+  from sg2im_b200.train_step import TrainStep
+  g = load_golden('train_step.pt')
+  m, d_obj, d_img = G._build_all(g)
+  kw = g['kwargs']
+  H, W = kw['image_size']
+  N = g['batch'][0].size(0)
+  step = TrainStep(m, d_obj, d_img, cuda_graph=True, graph_warmup=1, max_graphs=2, graph_min_seen=2)
+  def batch(objs, rels, seed):
+    return [t.to(dev()) for t in synth_batch(N=N, objs_per_img=objs, rels_per_img=rels, image_size=(H, W),
+                                             num_objs=9, num_preds=5, seed=seed)]
+  shapes = [(3, 2), (2, 1), (4, 3), (3, 1)]
+  torch.cuda.synchronize()
+  hist = []
+  for it in range(24):
+    o, r = shapes[it % 3] if it < 18 else shapes[3]            # three recurring signatures, then a fourth
+    noise = G._noise(100 + it, N, kw['layout_noise_dim'], (H, W)).to(dev())
+    losses, imgs = step.step(batch(o, r, it), noise=noise)
+    assert all(v == v for v in losses.values())
+    hist.append((len(step._graphs), step.replays))
+  assert max(h[0] for h in hist) <= 2                          # never more than max_graphs captured graphs
+  assert step.graph_evictions >= 1 and step.replays >= 4       # recurring shapes replay; LRU evicts
+  # a shape seen once runs eagerly and is not captured
+  before = len(step._graphs), step.replays
+  step.step(batch(1, 1, 999), noise=G._noise(5, N, kw['layout_noise_dim'], (H, W)).to(dev()))
+  assert (len(step._graphs), step.replays) == before

@@ -246,6 +246,53 @@ def test_flat_adam_matches_torch_adam():
     assert bucket.params[0].data_ptr() == opt.flat_params.data_ptr()
 
 
+def test_flat_adam_checkpoint_in_torch_adam_format():
+  """FlatAdam.state_dict() is torch.optim.Adam's (per-parameter step / exp_avg / exp_avg_sq, one
+  param group): a run checkpointed with either optimiser resumes with the other, like the
+  reference's `optimizer.state_dict()` round trip (scripts/train.py:633-641, :454-463); and a
+  parameter re-allocated behind the optimiser's back is detected instead of silently detached."""
+  import pytest
+  from sg2im_b200.train_step import FlatGrads, FlatAdam
+  def net():
+    torch.manual_seed(5)
+    return torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3))
+  def batches(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(11, 7, generator=g) for _ in range(n)]
+  with cpu_ops():
+    # 3 steps with torch Adam -> checkpoint -> 3 more with FlatAdam  ==  6 steps of torch Adam
+    ref = net(); opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    for x in batches(6, 1):
+      opt_ref.zero_grad(); ref(x).pow(2).mean().backward(); opt_ref.step()
+    a = net(); opt_a = torch.optim.Adam(a.parameters(), lr=1e-2)
+    xs = batches(6, 1)
+    for x in xs[:3]:
+      opt_a.zero_grad(); a(x).pow(2).mean().backward(); opt_a.step()
+    b = net(); b.load_state_dict(a.state_dict())
+    bucket = FlatGrads(b.parameters(), align=4)
+    opt_b = FlatAdam(bucket, lr=1e-2)
+    opt_b.load_state_dict(opt_a.state_dict())
+    for x in xs[3:]:
+      bucket.zero(); b(x).pow(2).mean().backward(); opt_b.step()
+    for pr, pb in zip(ref.parameters(), b.parameters()):
+      assert torch.allclose(pr, pb, rtol=1e-5, atol=1e-7)
+    # ... and back: FlatAdam's checkpoint loads into torch.optim.Adam
+    sd = opt_b.state_dict()
+    assert set(sd) == {'state', 'param_groups'} and len(sd['state']) == 4
+    c = net(); c.load_state_dict(b.state_dict())
+    opt_c = torch.optim.Adam(c.parameters(), lr=1e-2)
+    opt_c.load_state_dict(sd)
+    x = batches(1, 9)[0]
+    opt_c.zero_grad(); c(x).pow(2).mean().backward(); opt_c.step()
+    bucket.zero(); b(x).pow(2).mean().backward(); opt_b.step()
+    for pc, pb in zip(c.parameters(), b.parameters()):
+      assert torch.allclose(pc, pb, rtol=1e-5, atol=1e-7)
+    # a parameter moved out of the flat bucket: loud failure
+    next(b.parameters()).data = next(b.parameters()).data.clone()
+    with pytest.raises(RuntimeError, match='re-allocated'):
+      opt_b.step()
+
+
 def test_training_iteration_with_flat_adam():
   """TrainStep(fused_adam='flat') reproduces the reference's two iterations like
   the torch.optim.Adam configuration does."""

@@ -71,7 +71,7 @@ def _tol(math):
 
 @pytest.fixture
 def env():
-  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_EMUL_ASYNC_SLOW3D', 'SG2IM_EMUL_SLOW_EPILOGUE',
+  keys = ('SG2IM_NO_HALO', 'SG2IM_TC_BN', 'SG2IM_HALO_BN', 'SG2IM_EMUL_ASYNC_SLOW3D', 'SG2IM_EMUL_SLOW_EPILOGUE',
           'SG2IM_EMUL_SMS', 'SG2IM_EMUL_SLOW_PIPE')
   def set_(**kw):
     for k in keys:
@@ -93,9 +93,9 @@ FWD_CASES = [  # N, H, W, Ci, Co, K, P, env
     (1, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 256}),            # N tile 256
     (1, 8, 8, 64, 256, 3, 1, {'SG2IM_TC_BN': 128}),
     (2, 15, 15, 48, 32, 2, 0, {}),                             # 2x2 taps of the space-to-depth route
-    (3, 16, 16, 96, 128, 3, 1, {}),                            # halo kernel, Cout tile 128 (bf16 arithmetic)
-    (2, 32, 8, 40, 160, 3, 1, {}),                             # ... ragged second Cout tile, ragged channels
-    (5, 17, 9, 32, 256, 2, 0, {'SG2IM_EMUL_SMS': 2})]          # ... many groups per CTA: weight tiles refilled in flight
+    (3, 16, 16, 96, 128, 3, 1, {'SG2IM_HALO_BN': 128}),        # halo kernel, Cout tile 128 (bf16 arithmetic)
+    (2, 32, 8, 40, 160, 3, 1, {'SG2IM_HALO_BN': 128}),         # ... ragged second Cout tile, ragged channels
+    (5, 17, 9, 32, 256, 2, 0, {'SG2IM_EMUL_SMS': 2, 'SG2IM_HALO_BN': 128})]   # ... weight tiles refilled in flight
 
 
 @pytest.mark.parametrize('math', MATHS, ids=MATH_IDS)
@@ -187,8 +187,8 @@ KCC_CASES = [  # N, H, W, Ci, Co, K, P, Ci_full, env
     (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 256}),
     (1, 8, 8, 64, 256, 3, 1, 64, {'SG2IM_TC_BN': 128}),
     (2, 15, 15, 48, 32, 2, 0, 48, {}),
-    (3, 16, 24, 64, 128, 3, 1, 64, {}),                        # halo kernel, Cout tile 128
-    (2, 16, 16, 96, 192, 3, 1, 104, {'SG2IM_EMUL_SMS': 2})]    # ... two Cout tiles (one half empty), channel prefix
+    (3, 16, 24, 64, 128, 3, 1, 64, {'SG2IM_HALO_BN': 128}),    # halo kernel, Cout tile 128
+    (2, 16, 16, 96, 192, 3, 1, 104, {'SG2IM_EMUL_SMS': 2, 'SG2IM_HALO_BN': 128})]   # ... two Cout tiles, channel prefix
 
 
 @pytest.mark.parametrize('math', MATHS, ids=MATH_IDS)
@@ -255,7 +255,7 @@ def test_converter_protocol_under_adversarial_schedules(lib, env, sched):
   ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, padding=1).permute(0, 2, 3, 1)
   assert rel_err(y, ref) < 3e-5
   # halo kernel with the 128-wide Cout tile and ONE weight set refilled tap by tap: 2 CTAs, 8 items
-  env(SG2IM_EMUL_SMS=2, **sched)
+  env(SG2IM_EMUL_SMS=2, SG2IM_HALO_BN=128, **sched)
   N, H, W, Ci, Co = 4, 32, 16, 96, 256
   x = torch.randn(N, H, W, Ci, generator=g)
   w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.1

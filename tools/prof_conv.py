@@ -44,9 +44,26 @@ def main():
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   wf, wd = ops.pack_tc_fwd(w), ops.pack_tc_dgrad(w)
+  presplit = math in ('bf16x3', 'bf16') and os.environ.get('SG2IM_PROF_PRESPLIT', '1') != '0'
+  if presplit:
+    # the training step's configuration: weights in the weight-gradient layout, split once per step
+    wk = w.permute(2, 3, 1, 0).contiguous().permute(3, 2, 0, 1)
+    sh = ops.SplitShadows([wk])
+    sh.refresh()
+    sf, sd = wk._split_fwd, wk._split_dgrad
+    for _ in range(3):
+      if what == 'fwd':
+        ops.conv_tc_presplit(x, sf, Co, b, K, K, P, Co)
+      elif what == 'dgrad':
+        ops.conv_tc_presplit(dy, sd, Ci, None, K, K, K - 1 - P, Ci)
+    torch.cuda.synchronize()
   e0.record()
   for _ in range(10):
-    if what == 'fwd':
+    if what == 'fwd' and presplit:
+      ops.conv_tc_presplit(x, sf, Co, b, K, K, P, Co)
+    elif what == 'dgrad' and presplit:
+      ops.conv_tc_presplit(dy, sd, Ci, None, K, K, K - 1 - P, Ci)
+    elif what == 'fwd':
       ops.conv_tc(x, wf, b, K, K, P, Co)
     elif what == 'dgrad':
       ops.conv_tc(dy, wd, None, K, K, K - 1 - P, Ci)
