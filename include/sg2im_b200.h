@@ -254,6 +254,9 @@ int sg2im_scale_act_bwd_reduce(const float* dy, int64_t dy_cstride, int64_t dy_c
                                const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
                                const float* scale, const float* shift, const float* save,
                                float slope, int up, double* sums, sg2im_stream_t stream);
+/* (sg2im_scale_act_bwd_apply: `training` bit 0 = batch statistics were used; bit 1 = ADD the
+ * parameter gradients into dgamma / dbeta — the parameters' slots of a zeroed gradient bucket —
+ * instead of overwriting them.) */
 int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, int64_t dy_coff,
                               const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
                               const float* scale, const float* shift, const float* save,

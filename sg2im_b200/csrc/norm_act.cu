@@ -381,11 +381,13 @@ __global__ void scale_act_bwd_apply_kernel(ActGrad ag, const float* __restrict__
 }
 
 __global__ void bn_param_grads(const double* __restrict__ sums, int64_t C, float* dgamma,
-                               float* dbeta) {
+                               float* dbeta, int accumulate) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dbeta) dbeta[c] = (float)sums[c];
-  if (dgamma) dgamma[c] = (float)sums[C + c];
+  // accumulate: dgamma / dbeta are the parameters' slots of a gradient bucket (zeroed at the start
+  // of the step; a layer that runs twice per backward, like the discriminators', adds twice)
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sums[c];
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sums[C + c];
 }
 
 template <int VEC>
@@ -553,6 +555,8 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
                                          const double* sums, float* dx, float* dgamma,
                                          float* dbeta, sg2im_stream_t stream) {
   SG_ARG(dy && x && dx && N >= 1 && H >= 1 && W >= 1 && C >= 1 && up >= 1);
+  const int accumulate = (training >> 1) & 1;       // bit 1: ADD the parameter gradients into dgamma / dbeta
+  training &= 1;
   SG_ARG(!training || !save || sums);
   cudaStream_t st = as_stream(stream);
   ActGrad ag{dy, dy_cstride, dy_coff, x, H, W, C, scale, shift, slope, up};
@@ -571,7 +575,7 @@ extern "C" int sg2im_scale_act_bwd_apply(const float* dy, int64_t dy_cstride, in
     SG_LAUNCH(scale_act_bwd_apply_kernel, (unsigned)ceil_div64(M * C, 256), 256, 0, st, 
         ag, save, M, C, training, sums, dx);
   if ((dgamma || dbeta) && sums)
-    SG_LAUNCH(bn_param_grads, (unsigned)ceil_div64(C, 128), 128, 0, st, sums, C, dgamma, dbeta);
+    SG_LAUNCH(bn_param_grads, (unsigned)ceil_div64(C, 128), 128, 0, st, sums, C, dgamma, dbeta, accumulate);
   SG_LAUNCH_OK();
   return 0;
 }

@@ -90,6 +90,54 @@ def _call_b(nbytes, name, *args):
 # raw kernel wrappers (no autograd)
 # --------------------------------------------------------------------------
 
+class ZeroArena(object):
+  """Small zero-initialised scratch buffers (BatchNorm statistics, per-channel sums, tiny gradient
+  accumulators) carved out of ONE persistent buffer that is cleared by ONE memset at the start of a
+  training step, instead of one torch.zeros fill kernel per buffer (~85 launches per step).  Only
+  active inside TrainStep.step (ops.ZERO_ARENA): buffers are valid until the next step begins, and
+  nothing handed out is kept across steps (parameter gradients live in the flat buckets)."""
+
+  def __init__(self, nbytes, device):
+    self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    self.off = 0
+    self.high = 0
+
+  def reset(self):
+    self.high = max(self.off, self.high)            # monotone: a captured memset covers every later step
+    if self.high:
+      self.buf[:self.high].zero_()
+    self.off = 0
+
+  def take(self, shape, dtype):
+    n = 1
+    for d in shape:
+      n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    start = (self.off + 15) // 16 * 16
+    if start + nbytes > self.buf.numel():
+      return None
+    self.off = start + nbytes
+    self.high = max(self.high, self.off)
+    return self.buf[start:start + nbytes].view(dtype).view(shape)
+
+
+ZERO_ARENA = None           # set by TrainStep.step
+
+
+def _zeros(shape, dtype, device):
+  """torch.zeros, from the step's zero arena when one is active and the buffer is small."""
+  shape = tuple(int(d) for d in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+  if ZERO_ARENA is not None:
+    n = 1
+    for d in shape:
+      n *= d
+    if n <= (1 << 18):
+      t = ZERO_ARENA.take(shape, dtype)
+      if t is not None:
+        return t
+  return torch.zeros(shape, dtype=dtype, device=device)
+
+
 def csr_build(idx, nroles, num_rows):
   """idx: int64 (T,) for nroles=1 or (T,2) for nroles=2.  Returns
   (row_ptr int32[R+1], entries int32[nroles*T])."""
@@ -347,7 +395,7 @@ def act_bwd_bias(dy, y, slope, bias):
   g = bias.grad if bias is not None else None
   direct = (DIRECT_WGRAD and g is not None and g.is_contiguous() and g.numel() == C
             and g.data_ptr() % 4 == 0)
-  db = g if direct else torch.zeros(C, dtype=torch.float32, device=dy.device)
+  db = g if direct else _zeros(C, torch.float32, dy.device)
   _call_b(12 * dy.numel() + 4 * C,
           'sg2im_act_bwd_colsum', _p(dy), _p(y), float(slope), dy.numel() // C, C, _p(dx), _p(db),
           _stream())
@@ -365,7 +413,7 @@ def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum
   shift = torch.empty(C, dtype=torch.float32, device=dev)
   save = torch.empty(2 * C, dtype=torch.float32, device=dev)
   if training and sums is None:
-    sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    sums = _zeros(2 * C, torch.float64, dev)
     _call_b(4 * M * C, 'sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
     _count()
   _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, _p(gamma), _p(beta), float(eps),
@@ -386,29 +434,37 @@ def scale_act_fwd(x, scale, shift, slope, up, out=None, out_coff=0):
   return out
 
 
-def scale_act_bwd(dy, dy_coff, x, scale, shift, save, slope, up, training, want_param_grads):
+def scale_act_bwd(dy, dy_coff, x, scale, shift, save, slope, up, training, want_param_grads,
+                  grad_into=None):
   """dy: (N,H*up,W*up,Ctot) contiguous, slice [dy_coff, dy_coff+C).  Returns
-  (dx, dgamma, dbeta)."""
+  (dx, dgamma, dbeta).  grad_into = (gamma.grad, beta.grad): ADD the parameter gradients straight
+  into those slots of the flat gradient bucket (returns None for them)."""
   N, H, W, C = x.shape
   dev = x.device
   sums = None
   need_sums = (training and save is not None) or want_param_grads
   if need_sums:
-    sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+    sums = _zeros(2 * C, torch.float64, dev)
     _call_b(4 * x.numel() * (1 + up * up),
             'sg2im_scale_act_bwd_reduce', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C,
             _p(scale), _p(shift), _p(save), float(slope), up, _p(sums), _stream())
     _count()
   dx = torch.empty_like(x)
   dgamma = dbeta = None
-  if want_param_grads:
+  flag = int(training)
+  if want_param_grads and grad_into is not None:
+    dgamma, dbeta = grad_into
+    flag |= 2                                       # accumulate into the bucket slots
+  elif want_param_grads:
     dgamma = torch.empty(C, dtype=torch.float32, device=dev)
     dbeta = torch.empty(C, dtype=torch.float32, device=dev)
   _call_b(4 * x.numel() * (2 + up * up),
           'sg2im_scale_act_bwd_apply', _p(dy), dy.size(3), dy_coff, _p(x), N, H, W, C, _p(scale),
-          _p(shift), _p(save), float(slope), up, int(training), _p(sums), _p(dx), _p(dgamma),
+          _p(shift), _p(save), float(slope), up, flag, _p(sums), _p(dx), _p(dgamma),
           _p(dbeta), _stream())
   _count(2 if want_param_grads else 1)
+  if grad_into is not None and want_param_grads:
+    return dx, None, None
   return dx, dgamma, dbeta
 
 
@@ -897,6 +953,7 @@ class BNAct(torch.autograd.Function):
     if out is not None:
       ctx.mark_dirty(out)
     ctx.cfg = (use_bn, training, slope, up, out_coff, out is not None)
+    ctx.params = (gamma, beta)                    # the Parameters themselves (their .grad slots)
     ctx.save_for_backward(x, scale, shift, save)
     return y
 
@@ -906,8 +963,15 @@ class BNAct(torch.autograd.Function):
     x, scale, shift, save = ctx.saved_tensors
     dy = dy.contiguous()
     want_pg = use_bn and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+    into = None
+    if want_pg and DIRECT_WGRAD and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+      gg, gb = (getattr(p, 'grad', None) for p in ctx.params)
+      C = x.size(3)
+      if (gg is not None and gb is not None and gg.is_contiguous() and gb.is_contiguous()
+          and gg.numel() == C and gb.numel() == C and gg.dtype == torch.float32):
+        into = (gg, gb)                           # slots of the flat gradient bucket: add in place
     dx, dgamma, dbeta = scale_act_bwd(dy, coff, x, scale, shift, save, slope, up,
-                                      training and use_bn, want_pg)
+                                      training and use_bn, want_pg, into)
     dout = dy if sliced else None
     return (dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, dout, None,
             None)
@@ -928,7 +992,7 @@ def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0, sum
 
 
 def new_stats(channels, device):
-  return torch.zeros(2 * channels, dtype=torch.float64, device=device)
+  return _zeros(2 * channels, torch.float64, device)
 
 
 class TripleGather(torch.autograd.Function):
@@ -970,7 +1034,7 @@ class GraphPool(torch.autograd.Function):
     H, Dout, avg = ctx.cfg
     row_ptr, _ = ctx.csr
     if dpooled is None:
-      dpooled = torch.zeros(row_ptr.numel() - 1, H, dtype=torch.float32, device=row_ptr.device)
+      dpooled = _zeros((row_ptr.numel() - 1, H), torch.float32, row_ptr.device)
     dnew_t = triple_gather(dpooled, dnew_p, ctx.edges, Dout, row_ptr if avg else None)
     return dnew_t, None, None, None, None, None, None
 
@@ -1001,10 +1065,10 @@ class Layout(torch.autograd.Function):
     N, H, W, M, align = ctx.cfg
     dout = dout.contiguous()
     O, D = vecs.shape
-    dvecs = torch.zeros_like(vecs)
+    dvecs = _zeros(vecs.shape, torch.float32, vecs.device)
     dmasks = None
     if masks is not None and ctx.needs_input_grad[2]:
-      dmasks = torch.zeros_like(masks)
+      dmasks = _zeros(masks.shape, torch.float32, masks.device)
     _call_b(4 * N * H * W * D + 8 * O * D,
             'sg2im_layout_bwd', _p(dout), dout.size(3), _p(vecs), _p(boxes), _p(masks), M,
             _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())
@@ -1088,10 +1152,10 @@ class LayoutStack(torch.autograd.Function):
       avgpool2_bwd(g[k - 1], 0, C, g[k], 0, True)
     O, D = vecs.shape
     M = 0 if masks is None else masks.size(1)
-    dvecs = torch.zeros_like(vecs)
+    dvecs = _zeros(vecs.shape, torch.float32, vecs.device)
     dmasks = None
     if masks is not None and ctx.needs_input_grad[2]:
-      dmasks = torch.zeros_like(masks)
+      dmasks = _zeros(masks.shape, torch.float32, masks.device)
     _call_b(4 * N * H * W * D + 8 * O * D,
             'sg2im_layout_bwd', _p(g[L - 1]), g[L - 1].size(3), _p(vecs), _p(boxes), _p(masks), M,
             _p(obj_to_img), N, O, D, H, W, int(align), _p(dvecs), _p(dmasks), _stream())

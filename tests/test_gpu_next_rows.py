@@ -766,7 +766,8 @@ def test_cuda_graph_cache_is_bounded_for_variable_batch_shapes():
   kw = g['kwargs']
   H, W = kw['image_size']
   N = g['batch'][0].size(0)
-  step = TrainStep(m, d_obj, d_img, cuda_graph=True, graph_warmup=1, max_graphs=2, graph_min_seen=2)
+  step = TrainStep(m, d_obj, d_img, cuda_graph=True, graph_warmup=1, max_graphs=2, graph_min_seen=2,
+                   capture_cooldown=4)
   def batch(objs, rels, seed):
     return [t.to(dev()) for t in synth_batch(N=N, objs_per_img=objs, rels_per_img=rels, image_size=(H, W),
                                              num_objs=9, num_preds=5, seed=seed)]
@@ -785,3 +786,10 @@ def test_cuda_graph_cache_is_bounded_for_variable_batch_shapes():
   before = len(step._graphs), step.replays
   step.step(batch(1, 1, 999), noise=G._noise(5, N, kw['layout_noise_dim'], (H, W)).to(dev()))
   assert (len(step._graphs), step.replays) == before
+  # a loader cycling through more signatures than the cache holds: evicting captures are rate-limited
+  # (capture_cooldown), the rest of the steps run eagerly instead of re-capturing every time
+  ev0 = step.graph_evictions
+  for it in range(12):
+    o, r = shapes[it % 4]
+    step.step(batch(o, r, 500 + it), noise=G._noise(7, N, kw['layout_noise_dim'], (H, W)).to(dev()))
+  assert step.graph_evictions - ev0 <= 12 // 4 + 1
