@@ -122,6 +122,11 @@ class ZeroArena(object):
 
 
 ZERO_ARENA = None           # set by TrainStep.step
+# Data parallel: called (no arguments) when the backward pass of the cascaded-refinement network has
+# finished, i.e. when the layout's backward starts — 95 % of the generator's gradient bytes are then
+# final, and TrainStep starts their all-reduce while the layout / mask-head / graph-convolution
+# backward still runs.
+GRAD_READY_HOOK = None
 
 
 def _zeros(shape, dtype, device):
@@ -1142,6 +1147,8 @@ class LayoutStack(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, *douts):
+    if GRAD_READY_HOOK is not None:
+      GRAD_READY_HOOK()
     vecs, boxes, masks, obj_to_img = ctx.saved_tensors
     N, H, W, C, align = ctx.cfg
     L = len(douts)

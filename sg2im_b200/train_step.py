@@ -261,8 +261,57 @@ class TrainStep(object):
     # small zero-initialised scratch (BatchNorm statistics, column sums, tiny gradient accumulators):
     # one arena cleared by one memset per step instead of ~85 fill kernels
     self.zero_arena = _ops.ZeroArena(8 << 20, dev) if weights == 'kcc' else None
+    # offset of the cascaded-refinement network's parameters in the generator's flat bucket (they
+    # are its tail: `refinement_net` is Sg2ImModel's last child) for the overlapped all-reduce
+    self._crn_offset = None
+    crn = getattr(model, 'refinement_net', None)
+    if crn is not None:
+      ids = {id(p) for p in crn.parameters()}
+      b = self.buckets['g']
+      inside = [id(p) in ids for p in b.params]
+      if any(inside):
+        first = inside.index(True)
+        if all(inside[first:]) and b.offsets[first] % 4 == 0:
+          self._crn_offset = b.offsets[first]
     self.skipped = 0
     self.sync_replicas()
+
+  def _g_backward_and_reduce(self, total):
+    """Generator backward + gradient mean.  With more than one rank the all-reduce of the cascaded-
+    refinement network's slice of the flat bucket (the last ~95 % of it: `refinement_net` is the
+    generator's last child) is issued asynchronously as soon as its backward has finished
+    (ops.GRAD_READY_HOOK, fired by the layout's backward) and overlaps the layout / mask-head /
+    graph-convolution backward; the remaining head of the bucket is reduced afterwards."""
+    import torch.distributed as dist
+    from . import ops
+    bucket, opt = self.buckets['g'], self.opts['g']
+    multi = (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1)
+    split = self._crn_offset if multi else None
+    if not split:
+      total.backward()
+      bucket.all_reduce_mean(self.group, opt)
+      return
+    work = []
+
+    def crn_done():
+      if not work:
+        work.append(dist.all_reduce(bucket.flat[split:], op=dist.ReduceOp.SUM, group=self.group,
+                                    async_op=True))
+    prev, ops.GRAD_READY_HOOK = ops.GRAD_READY_HOOK, crn_done
+    try:
+      total.backward()
+    finally:
+      ops.GRAD_READY_HOOK = prev
+    if work:
+      dist.all_reduce(bucket.flat[:split], op=dist.ReduceOp.SUM, group=self.group)
+      work[0].wait()
+    else:                                            # no layout in the graph (never for Sg2ImModel)
+      dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+    world = dist.get_world_size(self.group)
+    if isinstance(opt, FlatAdam):
+      opt.grad_scale = 1.0 / world
+    else:
+      bucket.flat.div_(world)
 
   def sync_replicas(self):
     """Data parallel: make every rank start from rank 0's parameters AND buffers (what
@@ -440,8 +489,7 @@ class TrainStep(object):
     imgs_fake = imgs_pred.detach()
 
     self.buckets['g'].zero()
-    total.backward()
-    self.buckets['g'].all_reduce_mean(self.group, self.opts['g'])
+    self._g_backward_and_reduce(total)
     self.opts['g'].step()
 
     if self.d_obj is not None:
@@ -517,8 +565,7 @@ class TrainStep(object):
       return out, imgs_fake
 
     self.buckets['g'].zero()
-    total.backward()
-    self.buckets['g'].all_reduce_mean(self.group, self.opts['g'])
+    self._g_backward_and_reduce(total)
     self.opts['g'].step()
 
     # ---------------- object discriminator: train.py:566-579
