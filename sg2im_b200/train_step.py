@@ -10,6 +10,7 @@ gradient bucket.  The non-finite-loss skip of train.py:552-555 is made
 collective (all-reduce MIN of the finite flag) so ranks cannot diverge.
 """
 import collections
+import os
 import math
 
 import torch
@@ -286,7 +287,8 @@ class TrainStep(object):
     from . import ops
     bucket, opt = self.buckets['g'], self.opts['g']
     multi = (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1)
-    split = self._crn_offset if multi else None
+    # SG2IM_OVERLAP_ALLREDUCE=0: one all-reduce of the whole bucket after the backward
+    split = self._crn_offset if (multi and os.environ.get('SG2IM_OVERLAP_ALLREDUCE', '1') != '0') else None
     if not split:
       total.backward()
       bucket.all_reduce_mean(self.group, opt)

@@ -1,4 +1,7 @@
 #!/bin/bash
+# HISTORIC: this is the script that ran as round 2's first GPU call (profiles/r02_call1_*), against
+# the tree of commit 95c8e88.  The variants it A/B-tested that lost or failed (cluster multicast, CTA
+# pair, two-image halo, pack-both, tf32x3) have since been deleted, so it no longer runs as is.
 # First GPU call of round 2 (run under gpurun from the repo root):
 #   gpurun --timeout 3000 -- 'bash tools/r02_first_call.sh'      (about 35-40 GPU-minutes)
 # 1. hardware validation of everything written after round 1's GPU budget ran out
