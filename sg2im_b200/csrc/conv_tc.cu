@@ -234,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int nt, n0, y0, x0;
       decode(tile, nt, n0, y0, x0);
-      mbar_wait(&tfull[acc], acc_ph);
+      mbar_wait_relaxed(&tfull[acc], acc_ph, 200);
       tc_fence_after();
       const int n = n0 + img;
       const bool valid = n < p.N && (y0 + hh) < p.Hout && (x0 + ww) < p.Wout;
@@ -268,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         if ((s & 1) == grp) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_relaxed(&full[s], ph, 32);
           uint8_t* a = sA + s * A_STAGE_BYTES;
           uint8_t* b = sB + s * C::B_STAGE_BYTES;
           split_row_inplace(a + ct * 128);
@@ -551,7 +551,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       int nt, pt0;
       decode(item, nt, pt0);
-      mbar_wait(&tfull[aset], acc_ph);
+      mbar_wait_relaxed(&tfull[aset], acc_ph, 200);
       tc_fence_after();
       for (int t = 0; t < H_T; ++t) {
         int n, y0, x0;
@@ -584,7 +584,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cb = 0; cb < p.cblocks; ++cb, ++bcnt) {
           const int set = (int)(bcnt % SETS); const uint32_t bph = (bcnt / SETS) & 1;
           for (int tap = 0; tap < p.taps; ++tap) {
-            mbar_wait(&b_full[set * H_MAX_TAPS + tap], bph);
+            mbar_wait_relaxed(&b_full[set * H_MAX_TAPS + tap], bph, 32);
             uint8_t* b = sB + (set * H_MAX_TAPS + tap) * H_B_TILE;
             if constexpr (WMODE == 1) {
 #pragma unroll
@@ -610,7 +610,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         for (int cb = 0; cb < p.cblocks; ++cb) {
           for (int t = 0; t < H_T; ++t) {
-            mbar_wait(&a_full[s], ph);
+            mbar_wait_relaxed(&a_full[s], ph, 32);
             uint8_t* a = sA + s * H_A_SLOT;
             for (int i = ct; i < a_rows; i += CONV_THREADS) split_row_inplace(a + i * 128);
             fence_proxy_async();
@@ -789,7 +789,22 @@ static int conv_tc_impl(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
     if ((padded - Cout) * 8 <= padded) { BN = cand; break; }
   }
   long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-  while (BN > 64 && m_tiles * ceil_div64(Cout, BN) < num_sms()) BN >>= 1;
+  if (bf) {
+    // bf16 arithmetic: a pipeline stage costs ~700 cycles of L2 -> SM latency / converter round trip
+    // plus ~1.3 cycles per output column whatever the N tile (measured on 1024 -> 1024 at 8x8:
+    // 806 / 890 / 1041 cycles per stage for N = 64 / 128 / 256), so the widest tile wins unless it
+    // leaves SMs idle: minimise waves x stage cost over the admissible tiles (8x8 maps: N = 128,
+    // 133 us instead of 242 us with N = 64)
+    const int bn_max = BN;
+    double best = 1e30;
+    for (int cand = bn_max; cand >= 64; cand >>= 1) {
+      const long long tiles = m_tiles * ceil_div64(Cout, cand);
+      const double cost = (double)ceil_div64(tiles, num_sms()) * (700.0 + 1.3 * cand);
+      if (cost < best) { best = cost; BN = cand; }
+    }
+  } else {
+    while (BN > 64 && m_tiles * ceil_div64(Cout, BN) < num_sms()) BN >>= 1;
+  }
   // tuning aid (tools/prof_conv.py): SG2IM_TC_BN=64|128|256 pins the N tile
   if (const char* e = getenv("SG2IM_TC_BN")) {
     int forced = atoi(e);

@@ -216,7 +216,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int ci0, co0, pass, t0, t1;
       decode(item, ci0, co0, pass, t0, t1);
-      mbar_wait(tfull, acc_ph);
+      mbar_wait_relaxed(tfull, acc_ph, 200);
       tc_fence_after();
       const int ci = ci0 + row;
       const bool valid = ci < p.Cin;
@@ -259,7 +259,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       decode(item, ci0, co0, pass, t0, t1);
       for (int pt = t0; pt < t1; ++pt) {
         if ((s & 1) == grp) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_relaxed(&full[s], ph, 32);
           uint8_t* sa = smem + s * C::STAGE;
           uint8_t* sb = sa + A_STAGE;
           for (int i = ct; i < n_items; i += WG_CONV_THREADS) {

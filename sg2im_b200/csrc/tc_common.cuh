@@ -45,6 +45,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 8000000000LL) __trap();          // ~4 s at 2 GHz
   }
 }
+// Long waits (epilogue warps waiting for a whole K loop, converter warps waiting for the next TMA
+// box): back off between polls so that the spinning warps do not compete with the converters'
+// LDS / STS and the tensor core's operand reads for the shared-memory pipe.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar,
                                             int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -133,6 +144,19 @@ __device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, ui
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
   (void)leader;
+}
+// explicit shared-space 128-bit accesses for the converter warps: through a generic pointer the
+// compiler emits LD.E / ST.E (generic-address path, seen in the ncu source view of round 2's first
+// bf16x3 build), which costs address translation and latency on the busiest pipe of these kernels
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 // generic-proxy writes to shared memory (the in-kernel operand split) -> visible to the async
 // proxy (tcgen05.mma operand reads); executed by every writing thread before it signals
@@ -249,46 +273,44 @@ namespace tc {
 
 // one row (K-major operands: a pixel's / an output channel's 32 reduction-axis channels)
 __device__ __forceinline__ void split_row_inplace(uint8_t* row) {
-  const uint32_t x = (smem_u32(row) >> 7) & 7u;
+  const uint32_t base = smem_u32(row);
+  const uint32_t x = (base >> 7) & 7u;
   uint32_t hi[16], mid[16];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ x) << 4));
+    const float4 v = lds128(base + ((c ^ x) << 4));
     split_bf16x2(v.x, v.y, hi[2 * c], mid[2 * c]);
     split_bf16x2(v.z, v.w, hi[2 * c + 1], mid[2 * c + 1]);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    *reinterpret_cast<uint4*>(row + ((j ^ x) << 4)) =
-        make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-    *reinterpret_cast<uint4*>(row + (((4 + j) ^ x) << 4)) =
-        make_uint4(mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
+    sts128(base + ((j ^ x) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    sts128(base + (((4 + j) ^ x) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
   }
 }
 // a row pair (MN-major operands: the same pixel / reduction row in two adjacent 32-channel
 // atoms): row0 becomes the 64 bf16 hi values of the 64 channels, row1 their 64 mid values, i.e.
 // atom 2q turns into the hi half and atom 2q+1 into the mid half of one 64-wide bf16 atom
 __device__ __forceinline__ void split_rowpair_inplace(uint8_t* row0, uint8_t* row1) {
-  const uint32_t x0 = (smem_u32(row0) >> 7) & 7u, x1 = (smem_u32(row1) >> 7) & 7u;
+  const uint32_t b0 = smem_u32(row0), b1 = smem_u32(row1);
+  const uint32_t x0 = (b0 >> 7) & 7u, x1 = (b1 >> 7) & 7u;
   uint32_t hi[32], mid[32];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(row0 + ((c ^ x0) << 4));
+    const float4 v = lds128(b0 + ((c ^ x0) << 4));
     split_bf16x2(v.x, v.y, hi[2 * c], mid[2 * c]);
     split_bf16x2(v.z, v.w, hi[2 * c + 1], mid[2 * c + 1]);
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(row1 + ((c ^ x1) << 4));
+    const float4 v = lds128(b1 + ((c ^ x1) << 4));
     split_bf16x2(v.x, v.y, hi[16 + 2 * c], mid[16 + 2 * c]);
     split_bf16x2(v.z, v.w, hi[16 + 2 * c + 1], mid[16 + 2 * c + 1]);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    *reinterpret_cast<uint4*>(row0 + ((j ^ x0) << 4)) =
-        make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-    *reinterpret_cast<uint4*>(row1 + ((j ^ x1) << 4)) =
-        make_uint4(mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
+    sts128(b0 + ((j ^ x0) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    sts128(b1 + ((j ^ x1) << 4), mid[4 * j], mid[4 * j + 1], mid[4 * j + 2], mid[4 * j + 3]);
   }
 }
 

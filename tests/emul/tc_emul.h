@@ -244,6 +244,7 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity))
     if (++spins > 50000000LL) __trap();                 // a protocol bug must fail, never hang
 }
+static inline void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned) { mbar_wait(bar, parity); }
 static inline void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   emul::TMap t; std::memcpy(&t, map, sizeof(t));
   const int c[4] = {c0, c1, c2, c3};
@@ -354,6 +355,18 @@ static inline void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, 
   if (emul_lane() != 0) return;                           // elect.sync: one lane issues
   Block* blk = emul::current();
   emul::pipe_push(blk->rank, [=]() { emul_mma1_f16(blk, d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); });
+}
+static inline float4 lds128(uint32_t addr) {             // ld.shared.v4.f32 at a shared-window address
+  Block* b = emul::current();
+  if (addr < emul::SMEM_VA || addr - emul::SMEM_VA + 16 > b->smem_bytes || (addr & 15u)) { std::fprintf(stderr, "emul: ld.shared outside shared memory / misaligned\n"); std::abort(); }
+  float4 v; std::memcpy(&v, emul::host_of(b, addr), 16);
+  return v;
+}
+static inline void sts128(uint32_t addr, uint32_t a, uint32_t c, uint32_t d, uint32_t e) {
+  Block* b = emul::current();
+  if (addr < emul::SMEM_VA || addr - emul::SMEM_VA + 16 > b->smem_bytes || (addr & 15u)) { std::fprintf(stderr, "emul: st.shared outside shared memory / misaligned\n"); std::abort(); }
+  const uint32_t w[4] = {a, c, d, e};
+  std::memcpy(emul::host_of(b, addr), w, 16);
 }
 static inline void fence_proxy_async() {}
 // tcgen05.mma.cta_group::1.kind::tf32, descriptors given as (lo, hi) words: what the tensor pipe does

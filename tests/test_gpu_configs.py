@@ -92,8 +92,10 @@ def test_default_architecture_at_config_counts_vs_oracle(name, math):
     # whole-network gradients are bounded by activation-kink flips, not by the arithmetic
     # (tests/test_gpu_bf16x3.py; measured here on the exact-fp32 kernels, forward error 7e-6: worst
     # max-norm 7.6e-2 on one small tensor at cosine 0.99997): the DIRECTION of every parameter
-    # gradient must agree, the max-norm stay within the kink limit
-    assert worst_cos > (0.9995 if math == 'fp32' else 0.99) and worst < 0.25
+    # gradient must agree (cosine); the max-norm of the difference is dominated by single flipped
+    # elements on small-gradient tensors (measured up to 0.44 at cosine 0.9997 in bf16x3) and is
+    # only bounded loosely
+    assert worst_cos > (0.9995 if math == 'fp32' else 0.999) and worst < (0.25 if math == 'fp32' else 1.0)
   finally:
     ops.set_conv_math('fp32')
 
