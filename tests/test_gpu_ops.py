@@ -104,6 +104,8 @@ CONV_CASES = [
     (2, 8, 8, 161, 64, 3, 1, 1),       # CRN stage-0 width (not a multiple of 4)
     (1, 32, 32, 288, 64, 3, 1, 1),
     (1, 4, 4, 200, 260, 3, 1, 1),      # > one N tile, ragged
+    (320, 1, 1, 1024, 1, 1, 1, 0),     # discriminator real / fake head: warp-per-row skinny kernel
+    (37, 1, 1, 260, 3, 1, 1, 0),
 ]
 
 
@@ -132,7 +134,8 @@ def test_conv_forward_dgrad_wgrad(N, H, W, Ci, Co, K, S, P):
   assert rel_err(bd.grad, br.grad) < TOL
 
 
-@pytest.mark.parametrize('M,K,Nn', [(448, 384, 512), (320, 512, 4), (7, 24, 46), (1, 256, 1024)])
+@pytest.mark.parametrize('M,K,Nn', [(448, 384, 512), (320, 512, 4), (7, 24, 46), (1, 256, 1024),
+                                    (320, 1024, 1), (37, 260, 3)])    # heads: warp-per-row skinny kernel
 def test_linear_relu(M, K, Nn):
   from sg2im_b200 import ops
   g = torch.Generator().manual_seed(M + K)

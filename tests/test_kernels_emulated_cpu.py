@@ -455,7 +455,8 @@ def test_pool_s2d_act_colsum_sources_on_cpu(api):
 
 CONV_CASES = [  # N, H, W, Ci, Co, K, S, P, act
     (2, 6, 6, 5, 7, 3, 1, 1, 1), (1, 9, 8, 4, 6, 4, 2, 0, 0), (3, 1, 1, 20, 9, 1, 1, 0, 1),
-    (1, 10, 10, 3, 130, 3, 1, 1, 0), (2, 5, 5, 8, 3, 1, 1, 0, 0)]
+    (1, 10, 10, 3, 130, 3, 1, 1, 0), (2, 5, 5, 8, 3, 1, 1, 0, 0),
+    (37, 1, 1, 260, 3, 1, 1, 0, 1), (9, 1, 1, 1024, 1, 1, 1, 0, 0)]     # warp-per-row skinny kernel (heads)
 
 
 @pytest.mark.parametrize('N,H,W,Ci,Co,K,S,P,act', CONV_CASES)
@@ -471,6 +472,8 @@ def test_exact_fp32_conv_sources_on_cpu(api, N, H, W, Ci, Co, K, S, P, act):
   Ho, Wo = ref.shape[2], ref.shape[3]
   nhwc = x.permute(0, 2, 3, 1)
   sn, sh, sw, sc = nhwc.stride()
+  if H == 1 and W == 1:
+    sh = sw = sn                                        # rows of a matrix, as ops.linear passes them
   wf = w.permute(2, 3, 1, 0).reshape(K * K * Ci, Co).contiguous()
   y = torch.full((N, Ho, Wo, Co + 2), 7.0)
   _ok(api, api.sg2im_conv_igemm(0, _p(x), sn, sh, sw, sc, N, H, W, Ci, _p(wf), _p(b), K, K, S, P, Ho, Wo,
