@@ -366,6 +366,10 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   p.tiles_w = (int)ceil_div64(g.yW, 8); p.tiles_h = (int)ceil_div64(g.yH, RH);
   p.total_ptiles = (int)(g.yN * p.tiles_h * p.tiles_w);
   int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  if (const char* e = getenv("SG2IM_WG_BN")) {           // tuning aid: pins the Cout tile
+    int f = atoi(e);
+    if (f == 64 || f == 128 || f == 256) BN = f;
+  }
   p.ci_tiles = (int)ceil_div64(Cin, 128);
   p.co_tiles = (int)ceil_div64(Cout, BN);
   p.passes = (int)ceil_div64((int64_t)p.taps * BN, 512);
