@@ -238,7 +238,8 @@ int sg2im_bn_stats(const float* x, int64_t M, int64_t C, double* sums,
 int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbias_mult, int64_t C,
                       const float* gamma, const float* beta, float eps, float momentum,
                       int training, float* running_mean, float* running_var,
-                      float* scale, float* shift, float* save, sg2im_stream_t stream);
+                      float* scale, float* shift, float* save, int64_t* num_batches_tracked,
+                      sg2im_stream_t stream);   /* num_batches_tracked (may be NULL): +1 in training mode */
 int sg2im_scale_act_fwd(const float* x, int64_t N, int64_t H, int64_t W, int64_t C,
                         const float* scale, const float* shift, float slope, int up,
                         float* y, int64_t y_cstride, int64_t y_coff, int round_tf32,

@@ -46,7 +46,7 @@ SIGNATURES = {
   'sg2im_act_bwd': [_ptr, _ptr, _f32, _i64, _ptr, _ptr],
   'sg2im_bn_stats': [_ptr, _i64, _i64, _ptr, _ptr],
   'sg2im_bn_finalize': [_ptr, _i64, _i64, _i64, _ptr, _ptr, _f32, _f32, _int, _ptr, _ptr,
-                        _ptr, _ptr, _ptr, _ptr],
+                        _ptr, _ptr, _ptr, _ptr, _ptr],
   'sg2im_scale_act_fwd': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _f32, _int, _ptr, _i64,
                           _i64, _int, _ptr],
   'sg2im_scale_act_bwd_reduce': [_ptr, _i64, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr,

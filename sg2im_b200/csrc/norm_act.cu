@@ -184,8 +184,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t coun
                                    int64_t unbias_mult, int64_t C, const float* gamma,
                                    const float* beta, float eps, float momentum, int training,
                                    float* running_mean, float* running_var, float* scale,
-                                   float* shift, float* save) {
+                                   float* shift, float* save, long long* num_batches_tracked) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;   // nn.BatchNorm's counter
   if (c >= C) return;
   float mean, invstd;
   if (training) {
@@ -492,12 +493,12 @@ extern "C" int sg2im_colsum(const float* x, int64_t M, int64_t C, float* out, do
 extern "C" int sg2im_bn_finalize(const double* sums, int64_t count, int64_t unbias_mult, int64_t C,
                                  const float* gamma, const float* beta, float eps, float momentum,
                                  int training, float* running_mean, float* running_var,
-                                 float* scale, float* shift, float* save, sg2im_stream_t stream) {
+                                 float* scale, float* shift, float* save, int64_t* num_batches_tracked, sg2im_stream_t stream) {
   SG_ARG(scale && shift && save && C >= 1 && count >= 1 && unbias_mult >= 1);
   SG_ARG(training ? sums != nullptr : (running_mean && running_var));
   SG_LAUNCH(bn_finalize_kernel, (unsigned)ceil_div64(C, 128), 128, 0, as_stream(stream), 
       sums, count, unbias_mult, C, gamma, beta, eps, momentum, training, running_mean,
-      running_var, scale, shift, save);
+      running_var, scale, shift, save, reinterpret_cast<long long*>(num_batches_tracked));
   SG_LAUNCH_OK();
   return 0;
 }

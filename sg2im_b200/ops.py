@@ -409,7 +409,7 @@ def act_bwd_bias(dy, y, slope, bias):
 
 
 def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum, eps,
-                   unbias_mult=1, sums=None):
+                   unbias_mult=1, sums=None, num_batches_tracked=None):
   """Batch statistics of x (rows = all dims but the last) -> (scale, shift, save)."""
   C = x.size(-1)
   M = x.numel() // C
@@ -423,7 +423,7 @@ def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum
     _count()
   _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, _p(gamma), _p(beta), float(eps),
         float(momentum), int(training), _p(running_mean), _p(running_var), _p(scale), _p(shift),
-        _p(save), _stream())
+        _p(save), _p(num_batches_tracked), _stream())
   _count()
   return scale, shift, save
 
@@ -948,12 +948,13 @@ class BNAct(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, gamma, beta, running_mean, running_var, use_bn, training, momentum, eps,
-              slope, up, unbias_mult, out, out_coff, sums=None):
+              slope, up, unbias_mult, out, out_coff, sums=None, nbt=None):
     x = _chk(x).contiguous()
     scale = shift = save = None
     if use_bn:
       scale, shift, save = bn_scale_shift(x, gamma, beta, running_mean, running_var, training,
-                                          momentum, eps, unbias_mult, sums if training else None)
+                                          momentum, eps, unbias_mult, sums if training else None,
+                                          nbt if training else None)
     y = scale_act_fwd(x, scale, shift, slope, up, out, out_coff)
     if out is not None:
       ctx.mark_dirty(out)
@@ -979,7 +980,7 @@ class BNAct(torch.autograd.Function):
                                       training and use_bn, want_pg, into)
     dout = dy if sliced else None
     return (dx, dgamma, dbeta, None, None, None, None, None, None, None, None, None, dout, None,
-            None)
+            None, None)
 
 
 def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0, sums=None):
@@ -989,11 +990,14 @@ def bn_act(x, bn=None, slope=1.0, up=1, unbias_mult=1, out=None, out_coff=0, sum
     return BNAct.apply(x, None, None, None, None, False, False, 0.0, 0.0, slope, up, 1, out,
                        out_coff)
   training = bn.training or bn.running_mean is None
-  if training and bn.num_batches_tracked is not None:
-    bn.num_batches_tracked.add_(1)
   momentum = 0.1 if bn.momentum is None else bn.momentum
+  # nn.BatchNorm's num_batches_tracked += 1 happens inside the finalize kernel (one launch less per layer)
+  nbt = bn.num_batches_tracked if (training and bn.num_batches_tracked is not None) else None
+  if nbt is not None and nbt.dtype != torch.int64:
+    nbt.add_(1)
+    nbt = None
   return BNAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, True, training,
-                     momentum, bn.eps, slope, up, unbias_mult, out, out_coff, sums)
+                     momentum, bn.eps, slope, up, unbias_mult, out, out_coff, sums, nbt)
 
 
 def new_stats(channels, device):

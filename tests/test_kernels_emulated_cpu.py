@@ -392,8 +392,10 @@ def test_norm_act_kernels_source_on_cpu(api, N, H, W, C, up, extra):
   assert torch.allclose(sums[:C], x.double().reshape(M, C).sum(0), rtol=1e-6, atol=1e-6)
   rm, rv = torch.zeros(C), torch.ones(C)
   scale, shift, save = torch.empty(C), torch.empty(C), torch.empty(2 * C)
+  nbt = torch.tensor(4, dtype=torch.int64)
   _ok(api, api.sg2im_bn_finalize(_p(sums), M, 1, C, _p(gamma), _p(beta), 1e-5, 0.1, 1, _p(rm), _p(rv),
-                                 _p(scale), _p(shift), _p(save), None))
+                                 _p(scale), _p(shift), _p(save), _p(nbt), None))
+  assert int(nbt) == 5                                    # nn.BatchNorm's counter advances in-kernel
   bn = torch.nn.BatchNorm2d(C)
   with torch.no_grad():
     bn.weight.copy_(gamma); bn.bias.copy_(beta)
