@@ -166,7 +166,12 @@ int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win, int64_t C
                                   int64_t Hout, int64_t Wout, int64_t Cout);
 int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin, int64_t Win,
                         int64_t Cin, const float* dy, int KH, int KW, int P, int64_t Hout,
-                        int64_t Wout, int64_t Cout, float* dw, int math, sg2im_stream_t stream);
+                        int64_t Wout, int64_t Cout, float* dw, int math, int64_t s2d_channels,
+                        sg2im_stream_t stream);
+/* s2d_channels = C > 0 (2x2 taps, Cin = 4C, x = the space-to-depth form of the input of a 4x4 stride-2
+ * convolution): dw is THAT filter's gradient [16][C][Cout] — the kernel maps tap (ty, tx), channel
+ * (py, px, c) to filter tap (2 ty + py, 2 tx + px), channel c — so that the discriminators' weight
+ * gradients land directly in the parameter's slot of the gradient bucket.  0 = plain. */
 
 /* Pre-split weight operands of the bf16 arithmetic (SG2IM_MATH_BF16X3 / SG2IM_MATH_BF16): all
  * convolution / Linear weights of a network in ONE launch.  `table`: n_entries x 8 int64 in device
@@ -175,6 +180,8 @@ int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hi
  * copies [taps][Cout][cin_pad] and [taps, flipped][Cin][cout_pad] (pads = channels rounded up to 32)
  * whose rows are 32-channel blocks of [32 x bf16 hi | 32 x bf16 mid], and first_tile the running sum
  * of taps * ceil(Cin/32) * ceil(Cout/32) over the preceding entries (total_tiles = the full sum).
+ * The 8th field (0 above) = C > 0 marks a 4x4 stride-2 filter stored [16][C][Cout]: its copies are
+ * those of the equivalent 2x2 stride-1 filter on the space-to-depth input (taps = 4, Cin = 4C).
  * sg2im_conv_tc_presplit consumes them: the kernels then split only the activation tiles. */
 int sg2im_split_weights(const int64_t* table, int64_t n_entries, int64_t total_tiles,
                         sg2im_stream_t stream);
@@ -186,6 +193,15 @@ int sg2im_conv_tc_presplit(const float* x, int64_t x_cstride, int64_t N, int64_t
                            const float* bias, int KH, int KW, int P, int64_t Hout, int64_t Wout,
                            int64_t Cout, int act, float slope, float* y, int64_t y_cstride,
                            int64_t y_coff, double* stats, int math, sg2im_stream_t stream);
+
+/* Mean BCE-with-logits against a constant target t (0 or 1): the GAN losses bce_loss(scores, ones /
+ * zeros) of sg2im/losses.py:39-57,60-103 in one pass forward (scratch: one caller-zeroed double) and
+ * one backward (gout: the upstream scalar gradient on the device), instead of ~20 elementwise ATen
+ * kernels per evaluation. */
+int sg2im_bce_logits_mean_fwd(const float* x, int64_t n, float target, double* scratch, float* out,
+                              sg2im_stream_t stream);
+int sg2im_bce_logits_mean_bwd(const float* x, int64_t n, float target, const float* gout, float* dx,
+                              sg2im_stream_t stream);
 
 /* Space-to-depth by 2 (and its adjoint): out[n, y/2, x/2, ((y&1)*2+(x&1))*C + c]
  * = x[n,y,x,c], zero padded to even H, W.  x addressed with element strides.

@@ -29,13 +29,15 @@ SIGNATURES = {
                     _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
   'sg2im_conv_tc_kcc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _int, _ptr, _int, _int, _int,
                         _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _int, _ptr],
+  'sg2im_bce_logits_mean_fwd': [_ptr, _i64, _f32, _ptr, _ptr, _ptr],
+  'sg2im_bce_logits_mean_bwd': [_ptr, _i64, _f32, _ptr, _ptr, _ptr],
   'sg2im_split_weights': [_ptr, _i64, _i64, _ptr],
   'sg2im_conv_tc_presplit': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr, _int, _int, _int,
                              _i64, _i64, _i64, _int, _f32, _ptr, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_conv_wgrad_tc_supported': [_i64, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _i64,
                                     _i64, _i64],
   'sg2im_conv_wgrad_tc': [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _int, _int, _int, _i64, _i64,
-                          _i64, _ptr, _int, _ptr],
+                          _i64, _ptr, _int, _i64, _ptr],
   'sg2im_pack_weights': [_ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _int, _ptr],
   'sg2im_unpack_wgrad': [_ptr, _i64, _i64, _i64, _i64, _ptr, _int, _ptr],
   'sg2im_s2d_fwd': [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],

@@ -47,6 +47,8 @@ struct WgParams {
   int ci_tiles, co_tiles, passes, T, splits, per_split;
   int a_bytes, b_atom_rows;      // bytes of one A atom box, pixel rows of a B atom (=8*RH)
   int nprod;                     // MATH 1: products per fp32 multiply (3 = bf16x3, 1 = bf16)
+  int s2d_c;                     // > 0: x is the space-to-depth form (4 * s2d_c channels, 2x2 taps) of a
+                                 // 4x4 stride-2 convolution; dw is that filter's [16][s2d_c][Cout] gradient
   float* dw;
 };
 
@@ -223,7 +225,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int tl = 0; tl < p.T; ++tl) {
         int tap = pass * p.T + tl;
         if (tap >= p.taps) break;
-        float* drow = p.dw + ((long long)tap * p.Cin + ci) * p.Cout + co0;
+        long long wrow = (long long)tap * p.Cin + ci;
+        if (p.s2d_c > 0) {                                   // (ty, tx), (py, px, c) -> (2 ty + py, 2 tx + px, c)
+          const int blk = ci / p.s2d_c, c = ci - blk * p.s2d_c;
+          wrow = (long long)((2 * (tap >> 1) + (blk >> 1)) * 4 + 2 * (tap & 1) + (blk & 1)) * p.s2d_c + c;
+        }
+        float* drow = p.dw + wrow * p.Cout + co0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * BN);
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
@@ -345,7 +352,8 @@ extern "C" int sg2im_conv_wgrad_tc_supported(int64_t N, int64_t Hin, int64_t Win
 extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N, int64_t Hin,
                                    int64_t Win, int64_t Cin, const float* dy, int KH, int KW,
                                    int P, int64_t Hout, int64_t Wout, int64_t Cout, float* dw,
-                                   int math, sg2im_stream_t stream) {
+                                   int math, int64_t s2d_channels, sg2im_stream_t stream) {
+  SG_ARG(s2d_channels == 0 || (KH == 2 && KW == 2 && P == 0 && Cin == 4 * s2d_channels));
   SG_ARG(x && dy && dw);
   SG_ARG(math == SG2IM_MATH_TF32 || math == SG2IM_MATH_BF16X3 || math == SG2IM_MATH_BF16);
   const int bf = math != SG2IM_MATH_TF32;
@@ -385,6 +393,7 @@ extern "C" int sg2im_conv_wgrad_tc(const float* x, int64_t x_cstride, int64_t N,
   p.a_bytes = (RH + KH - 1) * p.pitch * 128;
   p.b_atom_rows = 8 * RH;
   p.nprod = math == SG2IM_MATH_BF16X3 ? 3 : 1;
+  p.s2d_c = (int)s2d_channels;
   p.dw = dw;
 
   // bf16 arithmetic: the converter warps rewrite every tile and assume plain SWIZZLE_128B rows

@@ -155,7 +155,10 @@ extern "C" int sg2im_unpack_wgrad(const float* dw, int64_t Cout, int64_t Cin, in
 // Pad channels inside the last block are written as zeros.
 namespace {
 struct SplitEntry {           // 8 x int64, built by the host (ops.SplitShadows)
-  long long src, fwd, dgr, taps, Cin, Cout, first_tile, pad_;
+  long long src, fwd, dgr, taps, Cin, Cout, first_tile, s2d_c;
+  // s2d_c > 0: src is a 4x4 stride-2 filter [16][s2d_c][Cout]; the copies are those of the
+  // equivalent 2x2 stride-1 filter on the space-to-depth input: taps = 4 (ty, tx),
+  // Cin = 4 * s2d_c with channel (py * 2 + px) * s2d_c + c  <->  filter tap (2 ty + py, 2 tx + px)
 };
 
 __global__ void __launch_bounds__(256)
@@ -172,11 +175,17 @@ split_weights_kernel(const SplitEntry* __restrict__ tab, int n_entries) {
   const int bci = r % tci; const int tap = r / tci;
   const int ci0 = bci * 32, co0 = bco * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* src = reinterpret_cast<const float*>(E.src) + ((size_t)tap * Cin + ci0) * Cout + co0;
+  const float* src0 = reinterpret_cast<const float*>(E.src);
+  const int sc = (int)E.s2d_c;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int ci = warp + 8 * k;
-    tile[ci][lane] = (ci0 + ci < Cin && co0 + lane < Cout) ? src[(size_t)ci * Cout + lane] : 0.f;
+    const int ci = ci0 + warp + 8 * k;
+    size_t row = (size_t)tap * Cin + ci;                 // row of the [taps][Cin][Cout] master
+    if (sc > 0) {
+      const int q = ci / sc, c = ci - q * sc;            // (py, px) block of the space-to-depth channels
+      row = (size_t)((2 * (tap >> 1) + (q >> 1)) * 4 + 2 * (tap & 1) + (q & 1)) * sc + c;
+    }
+    tile[warp + 8 * k][lane] = (ci < Cin && co0 + lane < Cout) ? src0[row * Cout + co0 + lane] : 0.f;
   }
   __syncthreads();
   const int cin_pad = tci * 32, cout_pad = tco * 32;

@@ -235,8 +235,8 @@ def to_kcc_(module):
   kernel writes and `sg2im_conv_tc_kcc` reads in place, so a training step needs no weight
   pack / unpack pass (ops.ConvKCC).  The parameters keep their OIHW / (out, in) SHAPE as
   permuted views: `state_dict` keys, shapes and values are unchanged, `load_state_dict`
-  copies into the new storage.  Opt-in (TrainStep(weights='kcc')); validated so far under
-  the functional tensor-core model of the CPU suite only.  Returns `module`."""
+  copies into the new storage.  TrainStep(weights='kcc') — what bench.py measures; parity on
+  hardware in tests/test_gpu_bf16x3.py and tests/test_gpu_next_rows.py.  Returns `module`."""
   with torch.no_grad():
     for m in module.modules():
       if isinstance(m, nn.Conv2d):

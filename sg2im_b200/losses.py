@@ -1,5 +1,8 @@
-"""GAN losses with the reference's surface (sg2im/losses.py).  Scalar
-reductions over discriminator scores: these stay PyTorch."""
+"""GAN losses with the reference's surface (sg2im/losses.py).  Scalar reductions over discriminator
+scores.  The 'gan' losses — bce_loss against all-ones / all-zeros — run as ONE fused kernel forward
+and one backward on CUDA tensors (ops.BCELogitsMean: the reference's ~20 elementwise ATen ops per
+evaluation, six evaluations per step, were the largest group of tiny launches left); everything else,
+and CPU tensors, use the reference's torch composition."""
 import torch
 
 
@@ -26,15 +29,22 @@ def _flat(x):
   return x.reshape(-1) if x.dim() > 1 else x
 
 
+def _bce_const(s, target):
+  """bce_loss(s, full_like(s, target)), target 0 or 1."""
+  if s.is_cuda and s.dtype == torch.float32:
+    from . import ops
+    return ops.BCELogitsMean.apply(s, float(target))
+  return bce_loss(s, torch.full_like(s, float(target)))
+
+
 def gan_g_loss(scores_fake):
-  s = _flat(scores_fake)
-  return bce_loss(s, torch.ones_like(s))
+  return _bce_const(_flat(scores_fake), 1.0)
 
 
 def gan_d_loss(scores_real, scores_fake):
   assert scores_real.size() == scores_fake.size()
   r, f = _flat(scores_real), _flat(scores_fake)
-  return bce_loss(r, torch.ones_like(r)) + bce_loss(f, torch.zeros_like(f))
+  return _bce_const(r, 1.0) + _bce_const(f, 0.0)
 
 
 def wgan_g_loss(scores_fake):

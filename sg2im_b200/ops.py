@@ -330,10 +330,13 @@ def unpack_wgrad_oihw(dw, wshape, cin_use):
   return grad
 
 
-def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
+def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None, s2d_c=0):
   """Returns dw packed (KH*KW*Cin, Cout).  accumulate_into: a contiguous buffer of that size
   the kernels ADD into (they combine partial tiles with atomics anyway) instead of a fresh
-  zeroed one — e.g. the parameter's slice of the flat gradient bucket."""
+  zeroed one — e.g. the parameter's slice of the flat gradient bucket.
+  s2d_c = C > 0: x is the space-to-depth form of a 4x4 stride-2 convolution's input (2x2 taps,
+  4C channels) and the rows are written in THAT filter's (16, C, Cout) order (tensor-core
+  kernel only)."""
   _chk(x)
   dy = _chk(dy).contiguous()
   N, Hin, Win, Cin = x.shape
@@ -351,9 +354,11 @@ def conv_wgrad(x, dy, KH, KW, S, P, accumulate_into=None):
       with _prof('conv_wgrad_tc', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
                  (N, Hin, Win, Cin, Cout, KH, S)):
         _call('sg2im_conv_wgrad_tc', _p(x), cs, N, Hin, Win, Cin, _p(dy), KH, KW, P, Hout, Wout,
-              Cout, _p(dw), _math_id(), _stream())
+              Cout, _p(dw), _math_id(), int(s2d_c), _stream())
       _count()
       return dw
+  if s2d_c:
+    raise RuntimeError('sg2im_b200: the re-tiled 4x4 stride-2 weight gradient needs the tensor-core kernel')
   with _prof('conv_wgrad', 2.0 * N * Hout * Wout * Cin * Cout * KH * KW,
              (N, Hin, Win, Cin, Cout, KH, S)):
     _call('sg2im_conv_wgrad', _p(x), sn, sh, sw, sc, N, Hin, Win, Cin, _p(dy), KH, KW, S, P,
@@ -671,14 +676,20 @@ class SplitShadows(object):
     for w in params:
       if not (w.dim() in (2, 4) and is_kcc(w) and w.size(0) % 4 == 0):
         continue
-      if w.dim() == 4 and w.size(2) == 4:          # 4x4 stride-2 route re-tiles its weights per call
-        continue
       v = _kcc_view(w.detach())
       T, Ci, Co = v.shape
+      s2d_c = 0
+      if w.dim() == 4 and w.size(2) == 4 and w.size(3) == 4:
+        # the discriminators' 4x4 stride-2 filters run as 2x2 stride-1 on the space-to-depth
+        # input: the kernel writes the copies in that re-tiled order straight from the master
+        if Co % 32:
+          continue
+        s2d_c, T, Ci = Ci, 4, 4 * Ci
       cip, cop = (Ci + 31) // 32 * 32, (Co + 31) // 32 * 32
       w._split_fwd = torch.zeros(T, Co, cip, dtype=torch.float32, device=w.device)
       w._split_dgrad = torch.zeros(T, Ci, cop, dtype=torch.float32, device=w.device)
-      rows.append([v.data_ptr(), w._split_fwd.data_ptr(), w._split_dgrad.data_ptr(), T, Ci, Co, tiles, 0])
+      rows.append([v.data_ptr(), w._split_fwd.data_ptr(), w._split_dgrad.data_ptr(), T, Ci, Co, tiles,
+                   s2d_c])
       tiles += T * (cip // 32) * (cop // 32)
       self.weights.append(w)
     self.tiles = tiles
@@ -715,8 +726,15 @@ class ConvKCC(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, x, w_kcc, bias, KH, KW, pad, act, slope, in_ch, out_hw, zero_bias_grad,
-              stats_out, round_out, grad_into=None, w_read=None, split=None):
+              stats_out, round_out, grad_into=None, w_read=None, split=None, s2d_c=0):
     T, Ci_w, Co = w_kcc.shape
+    if s2d_c:
+      # w_kcc is a 4x4 stride-2 filter (16, C, Co) and x the space-to-depth form of its input:
+      # the pre-split copies are already re-tiled (SplitShadows), the weight gradient is written
+      # in the filter's own order into its bucket slot — w_kcc itself is never read
+      assert (T, Ci_w) == (16, s2d_c) and split is not None and grad_into is not None \
+          and w_read is None and in_ch is None
+      T, Ci_w = 4, 4 * s2d_c
     if w_read is not None:
       # RN-TF32 shadow of the same weights (FlatAdam keeps it current): what the kernels read
       assert w_read.shape == w_kcc.shape and w_read.is_contiguous()
@@ -737,7 +755,7 @@ class ConvKCC(torch.autograd.Function):
     if stats_out is not None and not fused_stats:
       _call_b(4 * y.numel(), 'sg2im_bn_stats', _p(y), y.numel() // Co, Co, _p(stats_out), _stream())
       _count()
-    ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co)
+    ctx.cfg = (KH, KW, pad, act, slope, Ci, Ci_w, Co, int(s2d_c))
     ctx.split_dgrad = None if split is None else split[1]
     ctx.save_for_backward(x, w_read, y if act else None)
     ctx.bias_ref = bias
@@ -749,7 +767,7 @@ class ConvKCC(torch.autograd.Function):
 
   @staticmethod
   def backward(ctx, dy):
-    KH, KW, pad, act, slope, Ci, Ci_w, Co = ctx.cfg
+    KH, KW, pad, act, slope, Ci, Ci_w, Co, s2d_c = ctx.cfg
     x, w_kcc, y = ctx.saved_tensors
     dy = dy.contiguous()
     dx = dw = db = None
@@ -771,12 +789,13 @@ class ConvKCC(torch.autograd.Function):
           dx = conv_tc_kcc(dy, w_kcc, Ci_w, 1, None, KH, KW, pad_t, Ci, out_hw=(x.size(1), x.size(2)),
                            tag='conv_dgrad_tc')
       else:
+        assert not s2d_c
         wd = w_kcc[:, :Ci].permute(0, 2, 1).reshape(KH * KW * Co, Ci).contiguous()   # exact-fp32 kernel
         dx = conv_igemm(1, dy, wd, None, KH, KW, 1, pad, (x.size(1), x.size(2)), Ci)
     if ctx.needs_input_grad[1] and ctx.grad_into is not None:
       # the weight-gradient kernel adds straight into the gradient bucket: no temporary, no zero
       # fill, no autograd accumulation kernel (the returned gradient is None)
-      conv_wgrad(x, dy, KH, KW, 1, pad, accumulate_into=ctx.grad_into)
+      conv_wgrad(x, dy, KH, KW, 1, pad, accumulate_into=ctx.grad_into, s2d_c=s2d_c)
     elif ctx.needs_input_grad[1]:
       dwp = conv_wgrad(x, dy, KH, KW, 1, pad)                # (T*Ci, Co): already the w_kcc layout
       if Ci == Ci_w:
@@ -791,7 +810,7 @@ class ConvKCC(torch.autograd.Function):
         db = None if DIRECT_WGRAD else torch.zeros(Co, dtype=torch.float32, device=dy.device)
       else:
         db = colsum(dy.view(-1, Co))
-    return (dx, dw, db) + (None,) * 13
+    return (dx, dw, db) + (None,) * 14
 
 
 class Pool2d(torch.autograd.Function):
@@ -898,6 +917,15 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     # kernels (forward, dgrad, wgrad) with no strided gathers.
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
+    split, slot = _split_of(weight), _grad_slot(weight)
+    if (kcc and split is not None and slot is not None and split[0].size(0) == 4
+        and conv_tc_ok(xs, 2, 2, 1, 0, Co, (Ho, Wo)) and xs.data_ptr() % 16 == 0
+        and _lib.load().sg2im_conv_wgrad_tc_supported(xs.size(0), xs.size(1), xs.size(2), 4 * C, 4 * C,
+                                                      2, 2, 1, 0, Ho, Wo, Co)):
+      # training step: re-tiled pre-split copies (no per-call copy of the filter) and the weight
+      # gradient accumulated in the filter's own order into its slot of the gradient bucket
+      return ConvKCC.apply(xs, _kcc_view(weight), bias, 2, 2, 0, act, slope, None, (Ho, Wo), feeds_bn,
+                           stats_out, round_out, slot, None, split, C)
     if kcc:
       # [ky][kx][c][co] -> [(ty,tx)][(py,px,c)][co]: one small copy, no pack pass
       w2 = weight.permute(2, 3, 1, 0).reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5)
@@ -1173,6 +1201,32 @@ class LayoutStack(torch.autograd.Function):
     _count()
     dboxes = _layout_dboxes(ctx, g[L - 1], vecs, boxes, masks, M, obj_to_img, N, H, W, align)
     return dvecs, dboxes, dmasks, None, None, None, None, None, None, None
+
+
+class BCELogitsMean(torch.autograd.Function):
+  """mean(max(x, 0) - x * t + log(1 + exp(-|x|))) for a constant target t — bce_loss(scores,
+  ones / zeros) of sg2im/losses.py:39-57 — as one forward and one backward pass."""
+
+  @staticmethod
+  def forward(ctx, x, target):
+    x = _chk(x).contiguous()
+    n = x.numel()
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    scratch = _zeros(1, torch.float64, x.device)
+    _call('sg2im_bce_logits_mean_fwd', _p(x), n, float(target), _p(scratch), _p(out), _stream())
+    _count(2)
+    ctx.save_for_backward(x)
+    ctx.target = float(target)
+    return out
+
+  @staticmethod
+  def backward(ctx, gout):
+    x, = ctx.saved_tensors
+    gout = gout.contiguous().to(torch.float32)
+    dx = torch.empty_like(x)
+    _call('sg2im_bce_logits_mean_bwd', _p(x), x.numel(), ctx.target, _p(gout), _p(dx), _stream())
+    _count()
+    return dx, None
 
 
 class Crop(torch.autograd.Function):

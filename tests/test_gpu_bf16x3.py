@@ -116,6 +116,51 @@ def test_stride2_space_to_depth_route(N, H, W, Ci, Co, kcc):
   assert rel_err(bd.grad, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize('N,H,W,Ci,Co', [(2, 32, 32, 3, 64), (2, 15, 15, 64, 128), (4, 63, 63, 64, 128),
+                                         (5, 16, 20, 8, 32)])
+def test_stride2_filter_in_place_in_the_training_step(N, H, W, Ci, Co):
+  """What the training step does with the discriminators' 4x4 stride-2 filters: pre-split operand
+  copies re-tiled straight from the kcc master (SplitShadows) for forward / data gradient, and the
+  weight gradient ADDED in the filter's own order into its slot of the gradient bucket — the
+  parameter itself is never copied.  Same numbers as an fp64 convolution, gradient slot included."""
+  from sg2im_b200 import ops
+  g = torch.Generator().manual_seed(H * 7 + Ci)
+  x = torch.randn(N, Ci, H, W, generator=g)
+  w = torch.randn(Co, Ci, 4, 4, generator=g) * 0.1
+  b = torch.randn(Co, generator=g)
+  xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+  yr = F.leaky_relu(F.conv2d(xr, wr, br, stride=2), 0.2)
+  gy = torch.randn(yr.shape, generator=g)
+  yr.backward(gy.double())
+  xd = x.to(dev()).requires_grad_(True)
+  wd = _kcc(w.to(dev())).requires_grad_(True)
+  bd = b.to(dev()).requires_grad_(True)
+  prior = torch.randn(w.shape, generator=g).to(dev())
+  wd.grad = _kcc(prior.clone())                              # the bucket slot, already holding something
+  slot_ptr = wd.grad.data_ptr()
+  shadows = ops.SplitShadows([wd])
+  assert shadows.weights and wd._split_fwd.shape[0] == 4
+  from sg2im_b200 import _lib
+  calls = []
+  real_call = _lib.call
+  old = (ops.USE_SPLIT_SHADOWS, ops.DIRECT_WGRAD)
+  ops.USE_SPLIT_SHADOWS, ops.DIRECT_WGRAD = True, True
+  _lib.call = ops._call = lambda name, *a: (calls.append(name), real_call(name, *a))[1]
+  try:
+    shadows.refresh()
+    y = ops.conv2d(xd.permute(0, 2, 3, 1), wd, bd, 2, 0, act=1, slope=0.2)
+    y.backward(gy.to(dev()).permute(0, 2, 3, 1))
+  finally:
+    ops.USE_SPLIT_SHADOWS, ops.DIRECT_WGRAD = old
+    _lib.call = ops._call = real_call
+  assert calls.count('sg2im_conv_tc_presplit') == 2 and 'sg2im_conv_tc_kcc' not in calls
+  assert rel_err(y.permute(0, 3, 1, 2), yr) < TOL
+  assert rel_err(xd.grad, xr.grad) < TOL
+  assert wd.grad.data_ptr() == slot_ptr
+  assert rel_err(wd.grad - prior, wr.grad) < TOL
+  assert rel_err(bd.grad, br.grad) < 1e-4
+
+
 def test_three_arithmetics_on_the_same_arbitrary_operands():
   """tf32 / bf16 / bf16x3 on identical fp32 operands against an fp64 convolution: the compensated
   form is >= 30x closer than TF32 and >= 100x closer than plain bf16."""

@@ -793,3 +793,28 @@ def test_cuda_graph_cache_is_bounded_for_variable_batch_shapes():
     o, r = shapes[it % 4]
     step.step(batch(o, r, 500 + it), noise=G._noise(7, N, kw['layout_noise_dim'], (H, W)).to(dev()))
   assert step.graph_evictions - ev0 <= 12 // 4 + 1
+
+
+@pytest.mark.parametrize('shape,target', [((320, 1), 1.0), ((32, 256, 14, 14), 0.0), ((5,), 1.0)])
+def test_fused_gan_bce_loss_matches_the_reference_composition(shape, target):
+  """ops.BCELogitsMean (csrc/loss.cu) — what gan_g_loss / gan_d_loss launch on CUDA tensors — vs
+  bce_loss(scores, ones / zeros) composed from torch ops as in sg2im/losses.py:39-57, value and
+  gradient (through a non-trivial upstream factor)."""
+  from sg2im_b200 import ops
+  from sg2im_b200.losses import bce_loss, gan_d_loss
+  g = torch.Generator().manual_seed(len(shape))
+  x = (torch.randn(*shape, generator=g) * 3).to(dev())
+  xr = x.clone().requires_grad_(True)
+  ref = bce_loss(xr.reshape(-1), torch.full((x.numel(),), target, device=dev()))
+  (ref * 0.3).backward()
+  xd = x.clone().requires_grad_(True)
+  out = ops.BCELogitsMean.apply(xd.reshape(-1), target)
+  (out * 0.3).backward()
+  assert abs(float(out) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+  assert rel_err(xd.grad, xr.grad) < 1e-5
+  # the public loss functions route to it
+  a, b = x.clone().requires_grad_(True), (x * 0.5).clone().requires_grad_(True)
+  d = gan_d_loss(a, b)
+  want = bce_loss(a.detach().reshape(-1), torch.ones(x.numel(), device=dev())) + \
+      bce_loss(b.detach().reshape(-1), torch.zeros(x.numel(), device=dev()))
+  assert abs(float(d) - float(want)) <= 4e-6 * max(1.0, abs(float(want)))

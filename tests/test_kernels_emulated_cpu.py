@@ -561,3 +561,19 @@ def test_layout_bwd_boxes_kernel(lib, with_masks, align):
   _ok(lib, lib.sg2im_layout_bwd_boxes(_p(dout), CS, _p(vecs), _p(boxes), _p(masks), M, _p(o2i), N, O, D,
                                      H, W, align, _p(db), None))
   assert rel_err(db, br.grad) < 2e-4, (db, br.grad)
+
+
+@pytest.mark.parametrize('n,target', [(320, 1.0), (7, 0.0), (5000, 1.0), (1, 0.0)])
+def test_fused_bce_with_logits_mean_source_on_cpu(api, n, target):
+  """csrc/loss.cu vs the reference's composition (sg2im/losses.py:39-57) and its autograd."""
+  from sg2im_b200.losses import bce_loss
+  g = torch.Generator().manual_seed(n)
+  x = (torch.randn(n, generator=g) * 4).requires_grad_(True)
+  ref = bce_loss(x, torch.full_like(x, target))
+  ref.backward(torch.tensor(0.37))
+  out, scratch = torch.empty(()), torch.zeros(1, dtype=torch.float64)
+  _ok(api, api.sg2im_bce_logits_mean_fwd(_p(x), n, target, _p(scratch), _p(out), None))
+  assert abs(float(out) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+  gout, dx = torch.tensor(0.37), torch.empty(n)
+  _ok(api, api.sg2im_bce_logits_mean_bwd(_p(x), n, target, _p(gout), _p(dx), None))
+  assert rel_err(dx, x.grad) < 1e-5

@@ -163,7 +163,7 @@ def _wgrad(lib, N, H, W, Ci, Co, K, math):
   Ho, Wo = H + 2 * P - K + 1, W + 2 * P - K + 1
   dy = _exact(torch.randn(N, Ho, Wo, Co, generator=g), math)
   dw = torch.zeros(K * K * Ci, Co)
-  assert lib.sg2im_conv_wgrad_tc(_p(x), Ci, N, H, W, Ci, _p(dy), K, K, P, Ho, Wo, Co, _p(dw), math, None) == 0, \
+  assert lib.sg2im_conv_wgrad_tc(_p(x), Ci, N, H, W, Ci, _p(dy), K, K, P, Ho, Wo, Co, _p(dw), math, 0, None) == 0, \
       lib.emul_last_error()
   ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Co, Ci, K, K),
                                     dy.permute(0, 3, 1, 2).double(), padding=P)
@@ -287,6 +287,49 @@ def test_operand_split_is_exact_to_bf16_pairs(lib):
   assert lib.sg2im_conv_tc(_p(x), C, 128, 1, 1, C, _p(wt), None, 1, 1, 0, 1, 1, C, 0, 0.0, _p(y1), C, 0,
                            None, 0, BF16, None) == 0
   assert torch.equal(y1, x.bfloat16().float())             # plain bf16: round-to-nearest-even hi only
+
+
+def _retile_4x4(kcc16, C, Co):
+  """[ky*4+kx][c][co] of a 4x4 stride-2 filter -> [(ty,tx)][(py,px,c)][co] of the equivalent 2x2
+  stride-1 filter on the space-to-depth input (ky = 2 ty + py, kx = 2 tx + px)."""
+  return (kcc16.reshape(2, 2, 2, 2, C, Co).permute(0, 2, 1, 3, 4, 5).reshape(4, 4 * C, Co).contiguous())
+
+
+@pytest.mark.parametrize('C,Co', [(3, 64), (64, 128), (40, 32)])
+def test_stride2_filter_in_place(lib, env, C, Co):
+  """The discriminators' 4x4 stride-2 filters stay in their own [16][C][Cout] order: the split
+  kernel writes the re-tiled 2x2 copies straight from it (table field 8 = C) and the weight
+  gradient kernel maps its rows back (s2d_channels = C) — both equal the plain kernels applied to
+  an explicitly re-tiled filter, bit for bit / up to the order of the atomics."""
+  env()
+  g = torch.Generator().manual_seed(C + Co)
+  w16 = torch.randn(16, C, Co, generator=g) * 0.1
+  w2 = _retile_4x4(w16, C, Co)
+  Ci = 4 * C
+  cip, cop = (Ci + 31) // 32 * 32, (Co + 31) // 32 * 32
+  tiles = 4 * (cip // 32) * (cop // 32)
+  out = []
+  for src, flag in ((w16, C), (w2, 0)):
+    fwd, dgr = torch.full((4, Co, cip), 7.0), torch.full((4, Ci, cop), 7.0)
+    table = torch.tensor([[src.data_ptr(), fwd.data_ptr(), dgr.data_ptr(), 4, Ci, Co, 0, flag]],
+                         dtype=torch.int64)
+    assert lib.sg2im_split_weights(_p(table), 1, tiles, None) == 0, lib.emul_last_error()
+    out.append((fwd, dgr))
+  assert torch.equal(out[0][0].view(torch.int32), out[1][0].view(torch.int32))
+  assert torch.equal(out[0][1].view(torch.int32), out[1][1].view(torch.int32))
+  # weight gradient: rows land in the 4x4 filter's order
+  N, H, W = 2, 9, 7                                          # space-to-depth extent; 2x2 'valid' conv
+  x = torch.randn(N, H, W, Ci, generator=g)
+  dy = torch.randn(N, H - 1, W - 1, Co, generator=g)
+  for math in (BF16X3, TF32):
+    d16, d2 = torch.full((16, C, Co), 0.5), torch.full((4, Ci, Co), 0.5)     # ADDS into the slot
+    assert lib.sg2im_conv_wgrad_tc(_p(x), Ci, N, H, W, Ci, _p(dy), 2, 2, 0, H - 1, W - 1, Co, _p(d16), math, C,
+                                   None) == 0, lib.emul_last_error()
+    assert lib.sg2im_conv_wgrad_tc(_p(x), Ci, N, H, W, Ci, _p(dy), 2, 2, 0, H - 1, W - 1, Co, _p(d2), math, 0,
+                                   None) == 0, lib.emul_last_error()
+    assert rel_err(_retile_4x4(d16, C, Co), d2) < 1e-6
+  assert lib.sg2im_conv_wgrad_tc(_p(x), Ci, N, H, W, Ci, _p(dy), 2, 2, 0, H - 1, W - 1, Co, _p(d16), TF32, C + 1,
+                                 None) != 0                   # Cin != 4 * s2d_channels
 
 
 @pytest.mark.parametrize('N,H,W,Ci,Co,K,P,Cf,e', KCC_CASES)

@@ -107,7 +107,7 @@ def main():
     # weight gradient
     if L.sg2im_conv_wgrad_tc_supported(N, H, W, Ci, Ci, K, K, 1, P, Ho, Wo, Co):
       dw = torch.zeros(T * Ci, Co)
-      assert L.sg2im_conv_wgrad_tc(p(x), Ci, N, H, W, Ci, p(gy), K, K, P, Ho, Wo, Co, p(dw), MATH, None) == 0, \
+      assert L.sg2im_conv_wgrad_tc(p(x), Ci, N, H, W, Ci, p(gy), K, K, P, Ho, Wo, Co, p(dw), MATH, 0, None) == 0, \
           L.emul_last_error()
       errs['wgrad'] = rel(dw, wr.grad.permute(2, 3, 1, 0).reshape(T * Ci, Co))
     bad = {k: v for k, v in errs.items() if v > (3e-5 if MATH == 1 else 5e-6)}
