@@ -24,6 +24,10 @@
 //   converter warps fold every pair of adjacent 32-channel atoms in place into one 64-channel
 //   bf16 hi atom and one mid atom (tc_common.cuh: split_rowpair_inplace), and each fp32 product
 //   is issued as hi*hi + mid*hi + hi*mid (K = 16 pixels per MMA; nprod = 1: hi*hi only).
+//   A ci tile with at most 64 channels (the 64 -> 64 layers, the tail of 288 = 128 + 128 + 32)
+//   is "stacked": its one folded pair IS an M = 128 operand [hi rows ; mid rows], so two MMAs
+//   ([hi;mid] x dY_hi, [hi;mid] x dY_mid) give all four partial products — 2/3 of the tensor time,
+//   half of the loads and splits — and the epilogue adds rows r and r + 64 into the same dW row.
 // Replaces cuDNN's backward-filter behind nn.Conv2d / nn.Linear
 // (sg2im/crn.py:41-45,80-82; model.py:100; layers.py:221).
 #include <cstdlib>
@@ -115,6 +119,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     t1 = t0 + p.per_split < p.total_ptiles ? t0 + p.per_split : p.total_ptiles;
   };
 
+  // bf16x3 on a ci tile of <= 64 channels: stacked [hi ; mid] A operand (see the header)
+  auto stacked = [&](int ci0) { return MATH == 1 && p.nprod == 3 && p.Cin - ci0 <= 64; };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -124,7 +131,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         decode(item, ci0, co0, pass, t0, t1);
         int na = (p.Cin - ci0 + 31) / 32; if (na > 4) na = 4;
         int nb = (p.Cout - co0 + 31) / 32; if (nb > BN / 32) nb = BN / 32;
-        if (MATH) { na = 4; nb = BN / 32; }     // atoms are folded in pairs: fetch all (past the edge: zeros)
+        if (MATH) { na = stacked(ci0) ? 2 : 4; nb = BN / 32; }   // folded in pairs: fetch whole pairs (past the edge: zeros)
         const uint32_t bytes = (uint32_t)(na * p.a_bytes + nb * B_ATOM_BYTES);
         for (int pt = t0; pt < t1; ++pt) {
           int tw = pt % p.tiles_w;
@@ -163,6 +170,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int ntap = (p.taps - tap0) < p.T ? (p.taps - tap0) : p.T;
         const int ky0 = tap0 / p.KW, kx0 = tap0 - ky0 * p.KW;
         const uint32_t tap_off0 = (uint32_t)(ky0 * p.pitch + kx0) * 8u;
+        const bool stk = stacked(ci0);
         mbar_wait(tempty, acc_ph ^ 1);
         tc_fence_after();
         for (int pt = t0; pt < t1; ++pt) {
@@ -178,15 +186,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               // 4 output rows of 8 pixels: K = 16 pixels (two rows) per MMA.  hi atoms are the even
               // 32-channel atoms of each folded pair, mid atoms the odd ones; 64-channel atoms are
               // one pair (LBO) apart; the second 8-pixel group is the next halo row (A) / 1 KB (B)
-              const uint32_t a16 = (at & 0xffffu) | ((uint32_t)(2 * A_ATOM_BYTES >> 4) << 16);
+              // (stacked: rows 64..127 of A are the mid atom, one atom after the hi atom)
+              const uint32_t a16 = (at & 0xffffu) | ((uint32_t)((stk ? 1 : 2) * A_ATOM_BYTES >> 4) << 16);
               const uint32_t b16 = (bt & 0xffffu) | ((uint32_t)(2 * B_ATOM_BYTES >> 4) << 16);
               const uint32_t a_hi16 = pitch16 | (1u << 14) | (2u << 29);
               const uint32_t b_hi16 = 64u | (1u << 14) | (2u << 29);
+              const int nprod = stk ? 2 : p.nprod;
 #pragma unroll
               for (int pr = 0; pr < 3; ++pr) {
-                if (pr >= p.nprod) break;
-                const uint32_t ao = pr == 1 ? (uint32_t)(A_ATOM_BYTES >> 4) : 0u;
-                const uint32_t bo = pr == 2 ? (uint32_t)(B_ATOM_BYTES >> 4) : 0u;
+                if (pr >= nprod) break;
+                const uint32_t ao = (pr == 1 && !stk) ? (uint32_t)(A_ATOM_BYTES >> 4) : 0u;
+                const uint32_t bo = (pr == 2 || (pr == 1 && stk)) ? (uint32_t)(B_ATOM_BYTES >> 4) : 0u;
                 tc_mma_f16_lh(d_tmem, a16 + ao, a_hi16, b16 + bo, b_hi16, C::IDESC16,
                               pr ? 1u : first, leader);
                 tc_mma_f16_lh(d_tmem, a16 + ao + 2 * pitch16, a_hi16, b16 + bo + 128, b_hi16, C::IDESC16,
@@ -220,7 +230,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       decode(item, ci0, co0, pass, t0, t1);
       mbar_wait_relaxed(tfull, acc_ph, 200);
       tc_fence_after();
-      const int ci = ci0 + row;
+      const int ci = ci0 + (stacked(ci0) ? (row & 63) : row);   // stacked: rows r, r + 64 -> the same dW row
       const bool valid = ci < p.Cin;
       for (int tl = 0; tl < p.T; ++tl) {
         int tap = pass * p.T + tl;
@@ -259,23 +269,24 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int ct = ((int)threadIdx.x - 6 * 32) & (WG_CONV_THREADS - 1);
     const int grp = ((int)threadIdx.x - 6 * 32) / WG_CONV_THREADS;
     const int a_rows = p.a_bytes >> 7;
-    const int n_items = 2 * a_rows + (BN / 64) * 32;
     int s = 0; uint32_t ph = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int ci0, co0, pass, t0, t1;
       decode(item, ci0, co0, pass, t0, t1);
+      const int n_a = (stacked(ci0) ? 1 : 2) * a_rows;       // stacked: only the first pair was fetched
+      const int n_items = n_a + (BN / 64) * 32;
       for (int pt = t0; pt < t1; ++pt) {
         if ((s & 1) == grp) {
           mbar_wait_relaxed(&full[s], ph, 32);
           uint8_t* sa = smem + s * C::STAGE;
           uint8_t* sb = sa + A_STAGE;
           for (int i = ct; i < n_items; i += WG_CONV_THREADS) {
-            if (i < 2 * a_rows) {
+            if (i < n_a) {
               const int pair = i >= a_rows ? 1 : 0, r = i - pair * a_rows;
               uint8_t* r0 = sa + pair * 2 * A_ATOM_BYTES + r * 128;
               split_rowpair_inplace(r0, r0 + A_ATOM_BYTES);
             } else {
-              const int j = i - 2 * a_rows;
+              const int j = i - n_a;
               uint8_t* r0 = sb + (j >> 5) * 2 * B_ATOM_BYTES + (j & 31) * 128;
               split_rowpair_inplace(r0, r0 + B_ATOM_BYTES);
             }

@@ -732,8 +732,8 @@ class ConvKCC(torch.autograd.Function):
       # w_kcc is a 4x4 stride-2 filter (16, C, Co) and x the space-to-depth form of its input:
       # the pre-split copies are already re-tiled (SplitShadows), the weight gradient is written
       # in the filter's own order into its bucket slot — w_kcc itself is never read
-      assert (T, Ci_w) == (16, s2d_c) and split is not None and grad_into is not None \
-          and w_read is None and in_ch is None
+      assert (T, Ci_w) == (16, s2d_c) and split is not None and w_read is None and in_ch is None \
+          and (grad_into is not None or not ctx.needs_input_grad[1])
       T, Ci_w = 4, 4 * s2d_c
     if w_read is not None:
       # RN-TF32 shadow of the same weights (FlatAdam keeps it current): what the kernels read
@@ -918,7 +918,8 @@ def conv2d(x, weight, bias, stride=1, pad=0, act=0, slope=0.0, in_ch=None, feeds
     Ho, Wo = conv_out_size(x.size(1), 4, 2, 0), conv_out_size(x.size(2), 4, 2, 0)
     xs = S2D.apply(x)
     split, slot = _split_of(weight), _grad_slot(weight)
-    if (kcc and split is not None and slot is not None and split[0].size(0) == 4
+    if (kcc and split is not None and (slot is not None or not weight.requires_grad)
+        and split[0].size(0) == 4
         and conv_tc_ok(xs, 2, 2, 1, 0, Co, (Ho, Wo)) and xs.data_ptr() % 16 == 0
         and _lib.load().sg2im_conv_wgrad_tc_supported(xs.size(0), xs.size(1), xs.size(2), 4 * C, 4 * C,
                                                       2, 2, 1, 0, Ho, Wo, Co)):
