@@ -165,8 +165,11 @@ __global__ void __launch_bounds__(256)
 split_weights_kernel(const SplitEntry* __restrict__ tab, int n_entries) {
   __shared__ float tile[32][33];
   const int bid = (int)blockIdx.x;
-  int e = 0;
-  while (e + 1 < n_entries && (long long)bid >= tab[e + 1].first_tile) ++e;   // n_entries is small
+  int e = 0, hi = n_entries - 1;                       // last entry whose first_tile <= bid
+  while (e < hi) {
+    const int mid = (e + hi + 1) >> 1;
+    if ((long long)bid >= tab[mid].first_tile) e = mid; else hi = mid - 1;
+  }
   const SplitEntry E = tab[e];
   const int Cin = (int)E.Cin, Cout = (int)E.Cout, T = (int)E.taps;
   const int tci = (Cin + 31) >> 5, tco = (Cout + 31) >> 5;
