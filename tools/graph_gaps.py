@@ -89,6 +89,16 @@ def main():
       after[n] += d
       after_n[n] += 1
       hist[min(int(d), 10)] += 1
+  last = max(groups, key=len)
+  tot = collections.Counter()
+  cnt = collections.Counter()
+  for e in last:
+    tot[short(e['name'])] += e['dur']
+    cnt[short(e['name'])] += 1
+  print('kernel time inside the longest replayed step (CUPTI durations, %d activities, %.1f us busy):' % (
+      len(last), sum(tot.values())))
+  for n, d in tot.most_common(40):
+    print('  %8.1f us  %4d x  %7.2f us each  %s' % (d, cnt[n], d / cnt[n], n))
   print('idle-interval histogram (us, floor; 10 = 10 or more), all steps:', dict(sorted(hist.items())))
   print('idle time by preceding kernel (all steps):')
   for n, d in after.most_common(25):
