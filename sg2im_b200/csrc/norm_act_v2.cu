@@ -92,7 +92,7 @@ template <int UP> struct RowsPerIter { static constexpr int value = UP == 1 ? 4 
 // sums[c] += sum_m g, sums[C+c] += sum_m g * xhat.  Block = TX channel groups x
 // TY = 256/TX row lanes; grid (cblocks, rblocks).
 template <int UP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, UP == 1 ? 4 : 3)
 bn_bwd_reduce_v2_kernel(const float* __restrict__ dy, uint32_t dcs, uint32_t dco,
                         const float* __restrict__ x, uint32_t H, uint32_t W, uint32_t C,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -235,10 +235,10 @@ int sg2im_bn_bwd_reduce_v2(const float* dy, int64_t dcs, int64_t dco, const floa
   tile_channels(C, TX, cblocks);
   const int TY = 256 / TX;
   const int R = up == 1 ? 4 : 2;
-  // 3 CTAs per SM (register budget of __launch_bounds__(256, 3)): ptxas keeps ~5 16-byte loads
+  // 3-4 CTAs per SM (register budget of the __launch_bounds__): ptxas keeps ~5 16-byte loads
   // in flight per thread, so 768 threads/SM cover the HBM latency-bandwidth product; more CTAs
   // would only lengthen the tail of same-address fp64 atomics (2*4*TX per CTA and channel group)
-  int64_t want = ceil_div64(148 * 3, cblocks);
+  int64_t want = ceil_div64(148 * (up == 1 ? 4 : 3), cblocks);   // up = 1 fits 64 registers: 4 CTAs per SM
   int64_t rpb = ceil_div64(M, want);
   if (rpb < (int64_t)R * TY) rpb = (int64_t)R * TY;
   int64_t rblocks = ceil_div64(M, rpb);
