@@ -18,21 +18,8 @@
   emul_launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
 #define SG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul_dynamic_smem())
 #else
-// SG2IM_CARVEOUT=1 (experiment): every kernel asks for the maximum shared-memory carve-out, so an SM
-// never re-partitions L1 / shared memory between the big-smem convolution kernels and the small
-// streaming kernels around them.
-#include <cstdlib>
-inline bool sg_prefer_smem(const void* fn) {
-  static const bool on = [] { const char* e = getenv("SG2IM_CARVEOUT"); return e && e[0] == '1'; }();
-  if (on) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return on;
-}
-#define SG_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
-  do {                                                                            \
-    static const bool sg_once_ = sg_prefer_smem((const void*)(kernel));           \
-    (void)sg_once_;                                                               \
-    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                           \
-  } while (0)
+#define SG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define SG_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
