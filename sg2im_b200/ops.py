@@ -1237,6 +1237,10 @@ class Crop(torch.autograd.Function):
   @staticmethod
   def forward(ctx, feats, boxes, idx, HH, WW, align_corners):
     _chk(feats)
+    if ctx.needs_input_grad[1]:
+      # the reference crops with the batch's ground-truth boxes (scripts/train.py:539,569-570); a
+      # gradient w.r.t. the crop boxes is not implemented and must not be dropped silently
+      raise RuntimeError('sg2im_b200: crop boxes that require grad are not supported')
     boxes = _chk(boxes).contiguous()
     idx = _chk(idx, torch.int64, 'bbox_to_feats').contiguous()
     N, H, W, C = feats.shape
