@@ -275,6 +275,7 @@ class TrainStep(object):
         if all(inside[first:]) and b.offsets[first] % 4 == 0:
           self._crn_offset = b.offsets[first]
     self.skipped = 0
+    self._side_stream = None
     self.sync_replicas()
 
   def _g_backward_and_reduce(self, total):
@@ -490,31 +491,59 @@ class TrainStep(object):
     found_inf.copy_(bad)
     imgs_fake = imgs_pred.detach()
 
+    # The discriminator iteration (train.py:566-592) needs only the detached images and the
+    # discriminators' pre-update weights, the generator backward only reads those weights: the two
+    # run on two streams (one fork / join inside the captured graph) so that the discriminators'
+    # medium-sized launches fill the SMs the generator backward leaves idle (tails of the persistent
+    # convolution kernels, the 32-CTA launches of the graph-convolution backward).  The
+    # discriminators' all-reduce and Adam steps come after the join: their weights must not move
+    # under the generator backward, and one communicator's collectives stay on one stream.
+    overlap = (imgs_fake.is_cuda and (self.d_obj is not None or self.d_img is not None)
+               and os.environ.get('SG2IM_OVERLAP_DSTEP', '1') != '0')
+    if overlap:
+      main = torch.cuda.current_stream()
+      if self._side_stream is None:
+        self._side_stream = torch.cuda.Stream()
+      self._side_stream.wait_stream(main)
+      with torch.cuda.stream(self._side_stream):
+        d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
+
     self.buckets['g'].zero()
     self._g_backward_and_reduce(total)
     self.opts['g'].step()
 
+    if overlap:
+      main.wait_stream(self._side_stream)
+    else:
+      d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
+    losses.update(d_losses)
+    for name, net in (('d_obj', self.d_obj), ('d_img', self.d_img)):
+      if net is not None:
+        self.buckets[name].all_reduce_mean(self.group, self.opts[name])
+        self.opts[name].step()
+    return losses, imgs_fake
+
+  def _d_forward_backward(self, imgs, imgs_fake, objs, boxes, obj_to_img):
+    """Forward + backward of both discriminators on real and generated images (train.py:566-575,
+    581-588); gradients land in their buckets, nothing is reduced or stepped here."""
+    out = {}
     if self.d_obj is not None:
       self._freeze(self.d_obj, False)
       s_fake, ac_fake = self.d_obj(imgs_fake, objs, boxes, obj_to_img)
       s_real, ac_real = self.d_obj(imgs, objs, boxes, obj_to_img)
       d_obj_gan = self.gan_d_loss(s_real, s_fake)
-      losses.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
+      out.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
       self.buckets['d_obj'].zero()
       (d_obj_gan + ac_real + ac_fake).backward()
-      self.buckets['d_obj'].all_reduce_mean(self.group, self.opts['d_obj'])
-      self.opts['d_obj'].step()
     if self.d_img is not None:
       self._freeze(self.d_img, False)
       s_fake = self.d_img(imgs_fake)
       s_real = self.d_img(imgs)
       d_img_gan = self.gan_d_loss(s_real, s_fake)
-      losses['d_img_gan_loss'] = d_img_gan
+      out['d_img_gan_loss'] = d_img_gan
       self.buckets['d_img'].zero()
       d_img_gan.backward()
-      self.buckets['d_img'].all_reduce_mean(self.group, self.opts['d_img'])
-      self.opts['d_img'].step()
-    return losses, imgs_fake
+    return out
 
   # ------------------------------------------------------------------ eager mode
   def _step_eager(self, batch, noise=None):
