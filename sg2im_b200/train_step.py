@@ -276,6 +276,7 @@ class TrainStep(object):
           self._crn_offset = b.offsets[first]
     self.skipped = 0
     self._side_stream = None
+    self._side_stream2 = None
     self.sync_replicas()
 
   def _g_backward_and_reduce(self, total):
@@ -468,6 +469,21 @@ class TrainStep(object):
         objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, num_imgs=N, noise=noise)
     total, losses = self.generator_losses(imgs, imgs_pred, boxes, boxes_pred, masks,
                                           masks_pred, triples[:, 1], predicate_scores)
+    # the two discriminators' scores of the generated images (train.py:539-548): the image
+    # discriminator runs on a second stream beside the object discriminator, forward and — autograd
+    # replays a node on its forward stream — backward (2499 vs 2472 img/s, profiles/r02_call22*;
+    # SG2IM_GLOSS_STREAMS=1 serialises them)
+    fork = (imgs_pred.is_cuda and self.d_img is not None and self.d_obj is not None
+            and os.environ.get('SG2IM_GLOSS_STREAMS', '2') != '1')
+    g_img = None
+    if fork:
+      main = torch.cuda.current_stream()
+      if self._side_stream2 is None:
+        self._side_stream2 = torch.cuda.Stream()     # not the discriminator iteration's stream: this
+      self._side_stream2.wait_stream(main)           # branch's backward is on the generator's chain
+      self._freeze(self.d_img, True)
+      with torch.cuda.stream(self._side_stream2):
+        g_img = self.gan_g_loss(self.d_img(imgs_pred)) * (a['discriminator_loss_weight'] * a['d_img_weight'])
     if self.d_obj is not None:
       self._freeze(self.d_obj, True)
       scores_fake, ac_loss = self.d_obj(imgs_pred, objs, boxes, obj_to_img)
@@ -477,10 +493,12 @@ class TrainStep(object):
           a['discriminator_loss_weight'] * a['d_obj_weight'])
       total = total + losses['g_gan_obj_loss']
     if self.d_img is not None:
-      self._freeze(self.d_img, True)
-      scores_fake = self.d_img(imgs_pred)
-      losses['g_gan_img_loss'] = self.gan_g_loss(scores_fake) * (
-          a['discriminator_loss_weight'] * a['d_img_weight'])
+      if fork:
+        main.wait_stream(self._side_stream2)
+      else:
+        self._freeze(self.d_img, True)
+        g_img = self.gan_g_loss(self.d_img(imgs_pred)) * (a['discriminator_loss_weight'] * a['d_img_weight'])
+      losses['g_gan_img_loss'] = g_img
       total = total + losses['g_gan_img_loss']
     losses['total_loss'] = total
     # on-device, collective finite flag -> fused Adam's found_inf
@@ -498,6 +516,8 @@ class TrainStep(object):
     # convolution kernels, the 32-CTA launches of the graph-convolution backward).  The
     # discriminators' all-reduce and Adam steps come after the join: their weights must not move
     # under the generator backward, and one communicator's collectives stay on one stream.
+    # Measured (profiles/r02_call20*, r02_call21*): 2487 vs 2247 img/s; one stream per discriminator
+    # is slower (2418: more contention on the generator's chain), stream priorities change nothing.
     overlap = (imgs_fake.is_cuda and (self.d_obj is not None or self.d_img is not None)
                and os.environ.get('SG2IM_OVERLAP_DSTEP', '1') != '0')
     if overlap:
