@@ -127,23 +127,6 @@ ZERO_ARENA = None           # set by TrainStep.step
 # final, and TrainStep starts their all-reduce while the layout / mask-head / graph-convolution
 # backward still runs.
 GRAD_READY_HOOK = None
-# Weight gradients are leaves of the backward graph: nothing downstream waits for them until the
-# all-reduce / Adam step.  While TrainStep runs a backward it sets WGRAD_STREAM; the tensor-core
-# weight-gradient launches that accumulate straight into a gradient bucket then go to that stream
-# (forked after the activation backward produced dy, joined once by TrainStep before the bucket is
-# consumed) and overlap the data-gradient chain.  The operand tensors are kept alive in
-# _WGRAD_KEEP until the join, so the caching allocator cannot hand their memory to the main stream
-# while the side stream still reads it.
-WGRAD_STREAM = None
-_WGRAD_KEEP = []
-
-
-def join_wgrad_stream():
-  """Make the current stream wait for every weight-gradient launch issued so far; release the
-  operands kept alive for them."""
-  if WGRAD_STREAM is not None:
-    torch.cuda.current_stream().wait_stream(WGRAD_STREAM)
-  del _WGRAD_KEEP[:]
 
 
 def _zeros(shape, dtype, device):
@@ -795,15 +778,6 @@ class ConvKCC(torch.autograd.Function):
         db_done = True
       else:
         dy = act_bwd(dy, y, slope)
-    wgrad_done = False
-    if (ctx.needs_input_grad[1] and ctx.grad_into is not None and WGRAD_STREAM is not None
-        and dy.is_cuda):
-      # issued BEFORE the data gradient: the side stream waits only for what produced dy
-      WGRAD_STREAM.wait_stream(torch.cuda.current_stream())
-      with torch.cuda.stream(WGRAD_STREAM):
-        conv_wgrad(x, dy, KH, KW, 1, pad, accumulate_into=ctx.grad_into, s2d_c=s2d_c)
-      _WGRAD_KEEP.append((x, dy))
-      wgrad_done = True
     if ctx.needs_input_grad[0]:
       pad_t = KH - 1 - pad
       if (KH == KW and pad_t >= 0
@@ -818,9 +792,7 @@ class ConvKCC(torch.autograd.Function):
         assert not s2d_c
         wd = w_kcc[:, :Ci].permute(0, 2, 1).reshape(KH * KW * Co, Ci).contiguous()   # exact-fp32 kernel
         dx = conv_igemm(1, dy, wd, None, KH, KW, 1, pad, (x.size(1), x.size(2)), Ci)
-    if wgrad_done:
-      pass
-    elif ctx.needs_input_grad[1] and ctx.grad_into is not None:
+    if ctx.needs_input_grad[1] and ctx.grad_into is not None:
       # the weight-gradient kernel adds straight into the gradient bucket: no temporary, no zero
       # fill, no autograd accumulation kernel (the returned gradient is None)
       conv_wgrad(x, dy, KH, KW, 1, pad, accumulate_into=ctx.grad_into, s2d_c=s2d_c)

@@ -10,7 +10,6 @@ gradient bucket.  The non-finite-loss skip of train.py:552-555 is made
 collective (all-reduce MIN of the finite flag) so ranks cannot diverge.
 """
 import collections
-import contextlib
 import os
 import math
 
@@ -278,7 +277,6 @@ class TrainStep(object):
     self.skipped = 0
     self._side_stream = None
     self._side_stream2 = None
-    self._wgrad_stream = None
     self.sync_replicas()
 
   def _g_backward_and_reduce(self, total):
@@ -295,27 +293,19 @@ class TrainStep(object):
     split = self._crn_offset if (multi and os.environ.get('SG2IM_OVERLAP_ALLREDUCE', '1') != '0') else None
     if not split:
       total.backward()
-      ops.join_wgrad_stream()
       bucket.all_reduce_mean(self.group, opt)
       return
     work = []
 
     def crn_done():
       if not work:
-        # the refinement network's weight gradients may still be running on the weight-gradient
-        # stream: the collective is ordered after THAT stream (which is not blocked by it)
-        ws = ops.WGRAD_STREAM
-        if ws is not None:
-          ws.wait_stream(torch.cuda.current_stream())     # bias / BatchNorm gradients come from here
-        with torch.cuda.stream(ws) if ws is not None else contextlib.nullcontext():
-          work.append(dist.all_reduce(bucket.flat[split:], op=dist.ReduceOp.SUM, group=self.group,
-                                      async_op=True))
+        work.append(dist.all_reduce(bucket.flat[split:], op=dist.ReduceOp.SUM, group=self.group,
+                                    async_op=True))
     prev, ops.GRAD_READY_HOOK = ops.GRAD_READY_HOOK, crn_done
     try:
       total.backward()
     finally:
       ops.GRAD_READY_HOOK = prev
-    ops.join_wgrad_stream()
     if work:
       dist.all_reduce(bucket.flat[:split], op=dist.ReduceOp.SUM, group=self.group)
       work[0].wait()
@@ -389,25 +379,17 @@ class TrainStep(object):
     into the static input buffers).  Returns (losses dict of python floats,
     imgs_pred detached)."""
     from . import ops
-    prev = ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA, ops.WGRAD_STREAM
+    prev = ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA
     # kcc: the weight-gradient kernels accumulate in place in the flat gradient buckets
     ops.DIRECT_WGRAD = self.weights == 'kcc'
     ops.USE_SPLIT_SHADOWS = bool(self.split_shadows)
     ops.ZERO_ARENA = self.zero_arena
-    # ... and run on their own stream beside the data-gradient chain (ops.WGRAD_STREAM; joined
-    # before every all-reduce / Adam step).  SG2IM_WGRAD_STREAM=0: same stream as everything else
-    if (ops.DIRECT_WGRAD and next(self.model.parameters()).is_cuda
-        and os.environ.get('SG2IM_WGRAD_STREAM', '1') != '0'):
-      if self._wgrad_stream is None:
-        self._wgrad_stream = torch.cuda.Stream()
-      ops.WGRAD_STREAM = self._wgrad_stream
     try:
       if self.cuda_graph:
         return self._step_graphed(batch, noise)
       return self._step_eager(batch, noise)
     finally:
-      ops.join_wgrad_stream()
-      ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA, ops.WGRAD_STREAM = prev
+      ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA = prev
 
   # ------------------------------------------------------------------ graph mode
   def _step_graphed(self, batch, noise):
@@ -472,7 +454,6 @@ class TrainStep(object):
 
   def _body(self, batch, noise, found_inf):
     """The whole iteration with no host synchronisation (graph-capturable)."""
-    from . import ops
     a = self.args
     masks = None
     if len(batch) == 6:
@@ -556,7 +537,6 @@ class TrainStep(object):
     else:
       d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
     losses.update(d_losses)
-    ops.join_wgrad_stream()
     for name, net in (('d_obj', self.d_obj), ('d_img', self.d_img)):
       if net is not None:
         self.buckets[name].all_reduce_mean(self.group, self.opts[name])
@@ -587,7 +567,6 @@ class TrainStep(object):
 
   # ------------------------------------------------------------------ eager mode
   def _step_eager(self, batch, noise=None):
-    from . import ops
     a = self.args
     masks = None
     if len(batch) == 6:
@@ -651,7 +630,6 @@ class TrainStep(object):
       d_vals.update(d_obj_gan_loss=d_obj_gan, d_ac_loss_real=ac_real, d_ac_loss_fake=ac_fake)
       self.buckets['d_obj'].zero()
       d_total.backward()
-      ops.join_wgrad_stream()
       self.buckets['d_obj'].all_reduce_mean(self.group, self.opts['d_obj'])
       self.opts['d_obj'].step()
 
@@ -664,7 +642,6 @@ class TrainStep(object):
       d_vals['d_img_gan_loss'] = d_img_gan
       self.buckets['d_img'].zero()
       d_img_gan.backward()
-      ops.join_wgrad_stream()
       self.buckets['d_img'].all_reduce_mean(self.group, self.opts['d_img'])
       self.opts['d_img'].step()
 
