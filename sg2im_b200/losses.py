@@ -18,22 +18,6 @@ def get_gan_losses(gan_type):
     raise ValueError('Unrecognized GAN type "%s"' % gan_type)
 
 
-def get_gan_d_parts(gan_type):
-  """The discriminator loss of `get_gan_losses` as (real_part, fake_part) with
-  d_loss(scores_real, scores_fake) == real_part(scores_real) + fake_part(scores_fake) bit for bit
-  (every one of the reference's discriminator losses is such a sum) — TrainStep evaluates and
-  back-propagates the two halves at different times."""
-  if gan_type == 'gan':
-    return (lambda r: _bce_const(_flat(r), 1.0)), (lambda f: _bce_const(_flat(f), 0.0))
-  elif gan_type == 'wgan':
-    return (lambda r: -r.mean()), (lambda f: f.mean())
-  elif gan_type == 'lsgan':
-    mse = torch.nn.functional.mse_loss
-    return ((lambda r: mse(_flat(r).sigmoid(), torch.ones_like(_flat(r)))),
-            (lambda f: mse(_flat(f).sigmoid(), torch.zeros_like(_flat(f)))))
-  raise ValueError('Unrecognized GAN type "%s"' % gan_type)
-
-
 def bce_loss(input, target):
   """Numerically stable BCE-with-logits, mean reduced (sg2im/losses.py:39-57)."""
   neg_abs = -input.abs()

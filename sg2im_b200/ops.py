@@ -413,24 +413,6 @@ def act_bwd_bias(dy, y, slope, bias):
   return dx, (None if direct else db)
 
 
-# While a list: train-mode BatchNorm forwards normalise with their batch statistics as usual but do
-# NOT touch running_mean / running_var / num_batches_tracked; they append what the update needs.
-# TrainStep runs the discriminators on the REAL images early (beside the generator forward) and
-# replays those updates with apply_deferred_bn once the forwards the reference runs before them
-# have made theirs — the buffers go through exactly the reference's sequence of values.
-DEFER_BN_RUNNING = None
-
-
-def apply_deferred_bn(entries):
-  for (sums, M, unbias_mult, C, eps, momentum, running_mean, running_var, nbt) in entries:
-    scratch = torch.empty(4 * C, dtype=torch.float32, device=running_mean.device)
-    _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, None, None, float(eps), float(momentum), 1,
-          _p(running_mean), _p(running_var), _p(scratch), _p(scratch[C:]), _p(scratch[2 * C:]), _p(nbt),
-          _stream())
-    _count()
-  del entries[:]
-
-
 def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum, eps,
                    unbias_mult=1, sums=None, num_batches_tracked=None):
   """Batch statistics of x (rows = all dims but the last) -> (scale, shift, save)."""
@@ -444,10 +426,6 @@ def bn_scale_shift(x, gamma, beta, running_mean, running_var, training, momentum
     sums = _zeros(2 * C, torch.float64, dev)
     _call_b(4 * M * C, 'sg2im_bn_stats', _p(x), M, C, _p(sums), _stream())
     _count()
-  if training and DEFER_BN_RUNNING is not None and running_mean is not None:
-    DEFER_BN_RUNNING.append((sums, M, unbias_mult, C, eps, momentum, running_mean, running_var,
-                             num_batches_tracked))
-    running_mean = running_var = num_batches_tracked = None
   _call('sg2im_bn_finalize', _p(sums), M, unbias_mult, C, _p(gamma), _p(beta), float(eps),
         float(momentum), int(training), _p(running_mean), _p(running_var), _p(scale), _p(shift),
         _p(save), _p(num_batches_tracked), _stream())

@@ -10,14 +10,13 @@ gradient bucket.  The non-finite-loss skip of train.py:552-555 is made
 collective (all-reduce MIN of the finite flag) so ranks cannot diverge.
 """
 import collections
-import contextlib
 import os
 import math
 
 import torch
 import torch.nn.functional as F
 
-from .losses import get_gan_losses, get_gan_d_parts
+from .losses import get_gan_losses
 
 DEFAULT_ARGS = dict(                      # scripts/train.py:94-131
     l1_pixel_loss_weight=1.0, bbox_pred_loss_weight=10.0,
@@ -192,7 +191,6 @@ class TrainStep(object):
     self.model, self.d_obj, self.d_img = model, obj_discriminator, img_discriminator
     self.group = group
     self.gan_g_loss, self.gan_d_loss = get_gan_losses(a['gan_loss_type'])
-    self.gan_d_real, self.gan_d_fake = get_gan_d_parts(a['gan_loss_type'])
     dev = next(model.parameters()).device
     if fused_adam is None:
       fused_adam = dev.type == 'cuda'
@@ -456,7 +454,6 @@ class TrainStep(object):
 
   def _body(self, batch, noise, found_inf):
     """The whole iteration with no host synchronisation (graph-capturable)."""
-    from . import ops
     a = self.args
     masks = None
     if len(batch) == 6:
@@ -468,28 +465,6 @@ class TrainStep(object):
       sh.refresh()
     if self.zero_arena is not None:
       self.zero_arena.reset()
-    # Streams inside the step (all forks joined before the discriminators' all-reduce / Adam steps):
-    #  * the discriminators' REAL-image half (forward + backward of their loss terms on the real
-    #    images, train.py:570-575, 583-588) depends on nothing the generator computes: it starts
-    #    here on the side stream, beside the generator forward whose graph-convolution / mask-head
-    #    launches leave most SMs idle.  Its BatchNorm running-statistics updates are deferred
-    #    (ops.DEFER_BN_RUNNING) and replayed after the generated-image forwards the reference runs
-    #    first, so the buffers go through the reference's sequence of values;
-    #  * the generated-image half runs on the same stream beside the generator backward (below).
-    have_d = self.d_obj is not None or self.d_img is not None
-    overlap = imgs.is_cuda and have_d and os.environ.get('SG2IM_OVERLAP_DSTEP', '1') != '0'
-    # (without CUDA — the emulated device of the CPU suite — the same order runs on one stream)
-    early = have_d and (overlap or not imgs.is_cuda) and os.environ.get('SG2IM_EARLY_DREAL', '1') != '0'
-    d_real, deferred = {}, []
-    if overlap:
-      main = torch.cuda.current_stream()
-      if self._side_stream is None:
-        self._side_stream = torch.cuda.Stream()
-    if early:
-      if overlap:
-        self._side_stream.wait_stream(main)
-      with torch.cuda.stream(self._side_stream) if overlap else contextlib.nullcontext():
-        d_real = self._d_half(True, imgs, objs, boxes, obj_to_img, deferred)
     imgs_pred, boxes_pred, masks_pred, predicate_scores = self.model(
         objs, triples, obj_to_img, boxes_gt=boxes, masks_gt=masks, num_imgs=N, noise=noise)
     total, losses = self.generator_losses(imgs, imgs_pred, boxes, boxes_pred, masks,
@@ -543,16 +518,15 @@ class TrainStep(object):
     # under the generator backward, and one communicator's collectives stay on one stream.
     # Measured (profiles/r02_call20*, r02_call21*): 2487 vs 2247 img/s; one stream per discriminator
     # is slower (2418: more contention on the generator's chain), stream priorities change nothing.
+    overlap = (imgs_fake.is_cuda and (self.d_obj is not None or self.d_img is not None)
+               and os.environ.get('SG2IM_OVERLAP_DSTEP', '1') != '0')
     if overlap:
+      main = torch.cuda.current_stream()
+      if self._side_stream is None:
+        self._side_stream = torch.cuda.Stream()
       self._side_stream.wait_stream(main)
-    if overlap or early:
-      with torch.cuda.stream(self._side_stream) if overlap else contextlib.nullcontext():
-        if early:
-          d_fake = self._d_half(False, imgs_fake, objs, boxes, obj_to_img, None)
-          ops.apply_deferred_bn(deferred)          # the real-image forwards' running statistics, in order
-          d_losses = self._d_join_losses(d_real, d_fake)
-        else:
-          d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
+      with torch.cuda.stream(self._side_stream):
+        d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
 
     self.buckets['g'].zero()
     self._g_backward_and_reduce(total)
@@ -560,7 +534,7 @@ class TrainStep(object):
 
     if overlap:
       main.wait_stream(self._side_stream)
-    elif not early:
+    else:
       d_losses = self._d_forward_backward(imgs, imgs_fake, objs, boxes, obj_to_img)
     losses.update(d_losses)
     for name, net in (('d_obj', self.d_obj), ('d_img', self.d_img)):
@@ -568,42 +542,6 @@ class TrainStep(object):
         self.buckets[name].all_reduce_mean(self.group, self.opts[name])
         self.opts[name].step()
     return losses, imgs_fake
-
-  def _d_half(self, real, images, objs, boxes, obj_to_img, deferred):
-    """One half of the discriminator iteration: the loss terms of both discriminators on the real
-    (real=True) or on the generated images, forward + backward into their gradient buckets (the
-    real half, which comes first, also clears them).  `deferred`: list receiving the BatchNorm
-    running-statistics updates instead of applying them (ops.DEFER_BN_RUNNING)."""
-    from . import ops
-    part = self.gan_d_real if real else self.gan_d_fake
-    out = {}
-    prev, ops.DEFER_BN_RUNNING = ops.DEFER_BN_RUNNING, deferred
-    try:
-      if self.d_obj is not None:
-        self._freeze(self.d_obj, False)
-        scores, ac = self.d_obj(images, objs, boxes, obj_to_img)
-        out['obj_gan'], out['obj_ac'] = part(scores), ac
-        if real:
-          self.buckets['d_obj'].zero()
-        (out['obj_gan'] + ac).backward()
-      if self.d_img is not None:
-        self._freeze(self.d_img, False)
-        out['img_gan'] = part(self.d_img(images))
-        if real:
-          self.buckets['d_img'].zero()
-        out['img_gan'].backward()
-    finally:
-      ops.DEFER_BN_RUNNING = prev
-    return out
-
-  def _d_join_losses(self, r, f):
-    out = {}
-    if self.d_obj is not None:
-      out.update(d_obj_gan_loss=r['obj_gan'].detach() + f['obj_gan'].detach(),
-                 d_ac_loss_real=r['obj_ac'].detach(), d_ac_loss_fake=f['obj_ac'].detach())
-    if self.d_img is not None:
-      out['d_img_gan_loss'] = r['img_gan'].detach() + f['img_gan'].detach()
-    return out
 
   def _d_forward_backward(self, imgs, imgs_fake, objs, boxes, obj_to_img):
     """Forward + backward of both discriminators on real and generated images (train.py:566-575,

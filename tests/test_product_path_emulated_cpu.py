@@ -164,43 +164,6 @@ def test_staged_tensor_core_switches_through_the_op_layer(emul_next):
   R.test_eval_bn_folding_sheep('bf16x3')
 
 
-def test_capturable_step_order_reproduces_the_reference_iterations(emul):
-  """TrainStep._body — the graph-capturable form of the iteration — runs the discriminators'
-  real-image half FIRST (on the GPU: on a second stream beside the generator forward) with its
-  BatchNorm running-statistics updates deferred, and the generated-image half beside the generator
-  backward.  Same losses as the reference's two iterations, and the same parameters AND buffers
-  afterwards (running_mean / running_var / num_batches_tracked of both discriminators go through
-  the reference's update order: generated (G step), generated, real)."""
-  from sg2im_b200 import ops
-  from sg2im_b200.train_step import TrainStep
-  g = G.load_golden('train_step.pt')
-  m, d_obj, d_img = G._build_all(g)
-  step = TrainStep(m, d_obj, d_img, fused_adam='flat')      # (torch's CPU Adam has no found_inf input)
-  kw = g['kwargs']
-  prev = ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA
-  ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA = step.weights == 'kcc', False, step.zero_arena
-  try:
-    for it, seed in enumerate(g['noise_seeds']):
-      noise = G._noise(seed, g['batch'][0].size(0), kw['layout_noise_dim'], kw['image_size'])
-      found_inf = torch.zeros(())
-      for opt in step.opts.values():
-        opt.found_inf = found_inf
-      losses, _ = step._body(list(g['batch']), noise, found_inf)
-      assert ops.DEFER_BN_RUNNING is None
-      for k, v in g['losses'][it].items():
-        assert abs(float(losses[k].detach()) - v) <= 1e-4 * max(1.0, abs(v)), (it, k, float(losses[k].detach()), v)
-  finally:
-    ops.DIRECT_WGRAD, ops.USE_SPLIT_SHADOWS, ops.ZERO_ARENA = prev
-  for net, after in ((m, g['sd_g_after']), (d_obj, g['sd_obj_after']), (d_img, g['sd_img_after'])):
-    sd = net.state_dict()
-    for k, v in after.items():
-      if v.dtype.is_floating_point:
-        assert (sd[k] - v).abs().max() < 2.5e-4, k
-      else:
-        assert torch.equal(sd[k], v), k
-  assert any('running_var' in k for k in g['sd_obj_after']) and any('running_var' in k for k in g['sd_img_after'])
-
-
 @needs_tc
 @pytest.mark.parametrize('adam', [pytest.param(None, marks=full), 'flat'])
 def test_training_iterations_with_weights_in_the_gradient_layout(emul, adam):
