@@ -220,15 +220,23 @@ def test_cuda_graph_step_matches_eager_step():
       noise = _noise(900 + it, N, kw['layout_noise_dim'], kw['image_size']).to(dev())
       losses, imgs = step.step(batch, noise=noise)
       hist.append(losses)
-    runs[mode] = (hist, {k: v.detach().clone() for k, v in m.state_dict().items()})
+    state = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    # the discriminators too (parameters and BatchNorm buffers): the graph-mode step runs their
+    # iteration on a second stream beside the generator backward
+    state.update({'d_obj.' + k: v.detach().clone() for k, v in d_obj.state_dict().items()})
+    state.update({'d_img.' + k: v.detach().clone() for k, v in d_img.state_dict().items()})
+    runs[mode] = (hist, state)
     if mode:
       assert step.replays == 4 and step.launches_per_replay > 100     # calls 2..5 replay
   for it in range(6):
     for k, v in runs[False][0][it].items():
       assert abs(runs[True][0][it][k] - v) <= 2e-4 * max(1.0, abs(v)), (it, k)
+  assert any('running_mean' in k and k.startswith('d_') for k in runs[False][1])
   for k, v in runs[False][1].items():
     if v.dtype.is_floating_point:
       assert (runs[True][1][k] - v).abs().max() < 1e-3, k
+    else:
+      assert torch.equal(runs[True][1][k], v), k                       # num_batches_tracked
 
 
 def test_generator_forward_tf32_error_vs_fp32_reference():
