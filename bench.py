@@ -393,8 +393,11 @@ def run_b200(args, cfg):
             'frac_of_arithmetic_ceiling': (ach * MMA_WORK[ops.CONV_MATH] / pk['tf']
                                            if ops.CONV_MATH in MMA_WORK else None),
             'note': 'achieved = algorithmic conv FLOPs / summed CUDA-event kernel time of the same '
-                    'step launched eagerly right after the timed (graph-replayed) region; traffic: '
-                    'see profiles/ (ncu --set full per kernel)'}
+                    'step launched eagerly, ONE stream, right after the timed (graph-replayed) region; '
+                    'share_of_step divides that serial kernel time by the timed step, in which the '
+                    'discriminator iteration runs on a second stream beside the generator backward, '
+                    'so the shares of the kernel families can add up to more than 1; traffic: see '
+                    'profiles/ (ncu --set full per kernel)'}
 
   # ---- the HBM-bound kernels (graph gather / pooling, layout warp, crops, normalise / activate
   # passes, layout conversions): the same eager step once more with THOSE launches bracketed by
