@@ -377,8 +377,8 @@ extern "C" int sg2im_layout_bwd(const float* dout, int64_t dout_cstride, const f
 }
 
 // =============================================================================
-// Second-generation layout backward (opt-in: SG2IM_LAYOUT_V2=1 until validated on
-// hardware).  Same mathematics as layout_bwd_kernel; restructured because the
+// Second-generation layout backward (default since round 2, 447 -> 280 us on the B200;
+// SG2IM_LAYOUT_V2=0 selects the first generation).  Same mathematics as layout_bwd_kernel; restructured because the
 // first generation is latency-bound and unbalanced (0.44 ms for ~0.45 GB of
 // reads, profiles/r01_kernel_table_tf32.txt): there, one CTA owns an object x
 // 8-row band however wide the object is (the `__image__` object of every image
@@ -511,7 +511,7 @@ layout_bwd_v2_kernel(const float* __restrict__ dout, int64_t dcs, const float* _
 }  // namespace
 
 // =============================================================================
-// Second-generation layout forward (opt-in: SG2IM_LAYOUT_V2=1).  The first
+// Second-generation layout forward (default since round 2, 269 -> 195 us; SG2IM_LAYOUT_V2=0: first generation).  The first
 // generation launches one CTA per (image, row, 32-pixel segment) = 16 384 CTAs
 // at VG-128, and each of them walks the same dependent chain of global loads
 // (image -> object list -> boxes / mask texels / vectors) before it can write

@@ -8,8 +8,7 @@
 #include <cstdlib>
 #include "common.cuh"
 
-// second-generation BatchNorm-backward kernels (norm_act_v2.cu), opt-in until
-// they have been validated and timed on hardware
+// second-generation BatchNorm kernels (norm_act_v2.cu): the defaults since round 2
 int sg2im_bn_bwd_reduce_v2(const float* dy, int64_t dcs, int64_t dco, const float* x, int64_t N,
                            int64_t H, int64_t W, int64_t C, const float* scale, const float* shift,
                            const float* save, float slope, int up, double* sums, cudaStream_t st);

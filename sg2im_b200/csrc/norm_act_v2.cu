@@ -19,7 +19,8 @@
 //     loads; R = 2 for up = 2: 10) with no control flow between them; ptxas
 //     schedules ~5 of them back to back (cuobjdump -sass), and 3-4 resident CTAs
 //     per SM supply the rest of the latency-bandwidth product.
-// Selected by SG2IM_BNBWD_V2=1 (see norm_act.cu) until validated on hardware.
+// Default since round 2 (validated and timed on the B200: apply 6.0 TB/s, reduce 3.0-3.7 TB/s,
+// profiles/r02_hbm_kernels_ncu.txt); SG2IM_BNBWD_V2=0 selects the first-generation kernels (norm_act.cu).
 #include "common.cuh"
 
 namespace {
@@ -289,7 +290,7 @@ int sg2im_bn_bwd_apply_v2(const float* dy, int64_t dcs, int64_t dco, const float
 // fetched UP*UP times and each output pays eight 32-bit divisions.  Here a thread
 // owns an INPUT float4 (x is contiguous: element i of the float4 stream), computes
 // it once and writes the UP*UP replicas; four elements per thread are in flight.
-// Opt-in with SG2IM_BNFWD_V2=1 (norm_act.cu) until validated on hardware.
+// Default since round 2 (5.8-6.9 TB/s on the B200); SG2IM_BNFWD_V2=0 selects the generic kernel (norm_act.cu).
 namespace {
 
 template <int UP>
