@@ -376,6 +376,9 @@ def run_b200(args, cfg):
             'traffic': traffic.get('bytes_per_launch'), 'traffic_unit': 'bytes/launch (top kernel, ncu)',
             'traffic_kernel': traffic.get('kernel'), 'traffic_algorithmic_bytes': traffic.get('algorithmic_bytes'),
             'traffic_source': traffic.get('source'),
+            # sm__pipe_tensor_cycles_active of the step's largest convolution kernels, from the same
+            # committed captures (with bf16x3 the pipe issues 3 MMAs per algorithmic product)
+            'tensor_pipe_active_pct_ncu': traffic.get('tensor_pipe_active_pct_ncu'),
             'peak_source': pk['src'],
             'share_of_step': (conv_ms / prof_steps) / (ms / args.steps),
             'launches_per_step': sum(v[2] for v in fam.values()) / prof_steps,
