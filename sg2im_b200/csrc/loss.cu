@@ -3,7 +3,7 @@
 // The reference composes it from ~10 elementwise ATen ops forward and as many backward; the step
 // evaluates it six times, which made it the largest group of tiny launches left in the iteration.
 //   loss = mean_i( max(x_i, 0) - x_i * t + log(1 + exp(-|x_i|)) )        (the reference's formula)
-//   dx_i = (sigmoid(x_i) - t) * g / n
+//   dx_i = (sigmoid(x_i) - t) * g / n        (x_i == 0: (1 - t) * g / n, the reference's subgradient)
 #include "common.cuh"
 
 namespace {
@@ -36,7 +36,9 @@ bce_bwd_kernel(const float* __restrict__ x, int64_t n, float t, const float* __r
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const float e = expf(-fabsf(v));
-    const float sig = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    // x == 0 exactly: the reference's composition differentiates clamp(x, min=0) as 1 and |x| as 0
+    // there, i.e. d = 1 - t (not the analytic 0.5 - t); kept so that autograd results are identical
+    const float sig = v > 0.f ? 1.f / (1.f + e) : (v < 0.f ? e / (1.f + e) : 1.f);
     dx[i] = (sig - t) * g;
   }
 }

@@ -818,3 +818,21 @@ def test_fused_gan_bce_loss_matches_the_reference_composition(shape, target):
   want = bce_loss(a.detach().reshape(-1), torch.ones(x.numel(), device=dev())) + \
       bce_loss(b.detach().reshape(-1), torch.zeros(x.numel(), device=dev()))
   assert abs(float(d) - float(want)) <= 4e-6 * max(1.0, abs(float(want)))
+
+
+@pytest.mark.parametrize('target', [0.0, 1.0])
+def test_fused_gan_bce_loss_on_saturated_and_zero_scores(target):
+  """Saturated logits stay finite, and a score of exactly 0 gets the reference composition's
+  subgradient (clamp(x, min=0) differentiates as 1, |x| as 0 there: 1 - t, not 0.5 - t)."""
+  from sg2im_b200 import ops
+  from sg2im_b200.losses import bce_loss
+  x = torch.tensor([-1e4, -88.0, -30.0, -1e-8, 0.0, 1e-8, 30.0, 88.0, 1e4, 3.0e38, -3.0e38], device=dev())
+  xr = x.clone().requires_grad_(True)
+  ref = bce_loss(xr, torch.full_like(xr, target))
+  ref.backward()
+  xd = x.clone().requires_grad_(True)
+  out = ops.BCELogitsMean.apply(xd, target)
+  out.backward()
+  assert bool(torch.isfinite(out)) and abs(float(out) - float(ref)) <= 1e-6 * abs(float(ref))
+  assert bool(torch.isfinite(xd.grad).all())
+  assert float((xd.grad - xr.grad).abs().max()) <= 1e-7

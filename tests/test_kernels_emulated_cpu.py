@@ -577,3 +577,22 @@ def test_fused_bce_with_logits_mean_source_on_cpu(api, n, target):
   gout, dx = torch.tensor(0.37), torch.empty(n)
   _ok(api, api.sg2im_bce_logits_mean_bwd(_p(x), n, target, _p(gout), _p(dx), None))
   assert rel_err(dx, x.grad) < 1e-5
+
+
+@pytest.mark.parametrize('target', [0.0, 1.0])
+def test_fused_bce_extreme_logits(api, target):
+  """Saturated scores (a discriminator that has won): the reference's formula is stable there
+  (max(x,0) - x t + log1p(exp(-|x|))), so is the kernel; gradients are exactly sigmoid(x) - t."""
+  from sg2im_b200.losses import bce_loss
+  x = torch.tensor([-1e4, -88.0, -30.0, -1e-8, 0.0, 1e-8, 30.0, 88.0, 1e4, 3.0e38, -3.0e38]).requires_grad_(True)
+  n = x.numel()
+  ref = bce_loss(x, torch.full_like(x, target))
+  ref.backward()
+  out, scratch = torch.empty(()), torch.zeros(1, dtype=torch.float64)
+  _ok(api, api.sg2im_bce_logits_mean_fwd(_p(x), n, target, _p(scratch), _p(out), None))
+  assert torch.isfinite(out) and abs(float(out) - float(ref)) <= 1e-6 * abs(float(ref))
+  gout, dx = torch.tensor(1.0), torch.empty(n)
+  _ok(api, api.sg2im_bce_logits_mean_bwd(_p(x), n, target, _p(gout), _p(dx), None))
+  assert bool(torch.isfinite(dx).all())
+  assert float((dx - x.grad).abs().max()) <= 1e-7
+
