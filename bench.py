@@ -471,7 +471,10 @@ def run_b200(args, cfg):
                    'parallelism': 'dp%d' % world, 'cuda_graph': bool(step.cuda_graph), 'adam': args.adam, 'weights': args.weights,
                    'shape_jitter': args.shape_jitter, 'graphs_cached': len(step._graphs),
                    'graph_evictions': step.graph_evictions, 'graph_replays': step.replays,
-                   'switches': sorted(k for k in os.environ if k.startswith('SG2IM_') and os.environ[k] == '1'),
+                   'switches': sorted('%s=%s' % (k, os.environ[k]) for k in os.environ if k.startswith('SG2IM_')),
+                   'streams': ('graph replay forks twice: the discriminator iteration beside the generator '
+                               'backward, the generator step\'s two discriminators beside each other'
+                               if step.cuda_graph else 'one'),
                    'setup': '4 untimed iterations before the warm-up (3 eager + CUDA-graph capture)'
                             if step.cuda_graph else 'none',
                    'l2': 'per-step working set (GBs of activations) far exceeds the 126 MB L2; '
