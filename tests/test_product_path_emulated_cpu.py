@@ -222,6 +222,7 @@ def test_fused_activation_backward_and_direct_bias_gradients(emul):
   from sg2im_b200.train_step import TrainStep
   g = G.load_golden('train_step.pt')
   results = []
+  default_fused = ops.FUSE_ACT_BWD
   for fused in (False, True):
     m, d_obj, d_img = G._build_all(g)
     ops.set_conv_math('tf32')
@@ -240,7 +241,7 @@ def test_fused_activation_backward_and_direct_bias_gradients(emul):
     finally:
       _lib.call = real_call
       ops._call = real_call
-      ops.FUSE_ACT_BWD = False
+      ops.FUSE_ACT_BWD = default_fused
       ops.set_conv_math('fp32')
     results.append((losses, {k: v.clone() for k, v in m.state_dict().items()}, calls))
   (l0, sd0, c0), (l1, sd1, c1) = results
